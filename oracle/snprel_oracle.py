@@ -1,0 +1,428 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY -- never imported by the product path.
+
+A plain numpy (float64 / int64) restatement of the reference's N x N
+relatedness-matrix path.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` leg of ``bench.py`` may import this module; the product
+(``snprelate_b200``) must never route through it.
+
+Parity status: PINNED.  ``tests/test_oracle_golden.py`` checks every function
+below against the reference's own golden vectors
+(``inst/unitTests/valid/Validate.{IBS,PCA,KING,Beta,EIGMIX}.RData`` decoded
+into ``tests/golden/``) on the bundled HapMap fixture.  GCTA-with-missing has no
+golden in the reference; it follows
+``src/genPCA.cpp:1148-1237`` literally and is additionally checked against the
+compiled reference sources in ``oracle/_ref`` when those are built.
+
+Genotype convention everywhere: ``geno`` is uint8 ``[nsnp, nsamp]`` (SNP-major,
+sample fastest -- the layout ``CdBaseWorkSpace::snpRead(..., RDim_Sample_X_SNP)``
+produces, ``src/dGenGWAS.cpp:677-733``); values 0/1/2 = number of A alleles,
+anything > 2 = missing (``src/dGenGWAS.cpp:33-39``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# ---------------------------------------------------------------------------
+# SNP selection  (CdBaseWorkSpace::Select_SNP_Base, src/dGenGWAS.cpp:361-397;
+# Get_AF_MR_perSNP :472-552; thresholds as mapped by R/Internal.R:438-439)
+# ---------------------------------------------------------------------------
+
+
+def snp_stats(geno: np.ndarray):
+    """Per-SNP (sum, num): vec_u8_geno_count, src/dVect.cpp:30-117."""
+    valid = geno <= 2
+    num = valid.sum(axis=1).astype(np.int64)
+    s = np.where(valid, geno, 0).sum(axis=1).astype(np.int64)
+    return s, num
+
+
+def select_snp_base(geno: np.ndarray, remove_monosnp=True, maf=np.nan,
+                    missing_rate=np.nan) -> np.ndarray:
+    """Boolean mask of kept SNPs (src/dGenGWAS.cpp:361-397)."""
+    maf_t = -1.0 if not np.isfinite(maf) else float(maf)        # R/Internal.R:438
+    mr_t = 2.0 if not np.isfinite(missing_rate) else float(missing_rate)  # :439
+    s, num = snp_stats(geno)
+    nsamp = geno.shape[1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        af = np.where(num > 0, s / (2.0 * num), np.nan)
+    mafv = np.minimum(af, 1 - af)
+    mr = 1.0 - num / float(nsamp)
+    keep = np.isfinite(mafv)
+    if remove_monosnp:
+        keep &= ~(mafv <= 0)
+    keep &= ~(mafv < maf_t)
+    keep &= ~(mr > mr_t)
+    return keep
+
+
+# ---------------------------------------------------------------------------
+# GRM / PCA / EIGMIX numerators
+# ---------------------------------------------------------------------------
+
+
+def _avg_geno(geno):
+    """DivideGeno: avg = sum/num, 0 if num == 0 (src/genPCA.cpp:98-142)."""
+    s, num = snp_stats(geno)
+    avg = np.where(num > 0, s / np.maximum(num, 1), 0.0)
+    return s, num, avg
+
+
+def _rsqrt_prod(avg):
+    """scale = 1/sqrt(p(1-p)), p = avg/2, 0 unless 0<p<1 (src/genPCA.cpp:145-181)."""
+    p = avg * 0.5
+    ok = (0 < p) & (p < 1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sc = np.where(ok, 1.0 / np.sqrt(p * (1 - p)), 0.0)
+    return sc
+
+
+def _centred(geno, avg, scale=None):
+    """TransposeGenotype + GenoSub (+ GenoMul): Z[i,l] = (g - avg_l) * scale_l,
+    missing -> exactly 0 (src/genPCA.h:93-108, src/genPCA.cpp:315-368).
+    Returns Z as [nsamp, nsnp] float64."""
+    valid = geno <= 2
+    z = np.where(valid, geno.astype(np.float64) - avg[:, None], 0.0)
+    if scale is not None:
+        z = z * scale[:, None]
+    return np.ascontiguousarray(z.T)
+
+
+def _zzt(z, block=4096):
+    n = z.shape[0]
+    c = np.zeros((n, n))
+    for s in range(0, z.shape[1], block):
+        zb = z[:, s:s + block]
+        c += zb @ zb.T
+    return c
+
+
+def cov_eigenstrat(geno, bayesian=False):
+    """CExactPCA::Run (src/genPCA.cpp:395-464): un-normalised Z Z^T."""
+    s, num, avg = _avg_geno(geno)
+    if bayesian:
+        p = (s + 1.0) / (2 * num + 2)                # :445-452
+        scale = 1.0 / np.sqrt(p * (1 - p))
+    else:
+        scale = _rsqrt_prod(avg)
+    return _zzt(_centred(geno, avg, scale))
+
+
+def pca_genmat(geno, bayesian=False):
+    """gnrPCA normalisation (src/genPCA.cpp:1381-1390).
+    Returns (genmat, TraceXTX, TraceVal)."""
+    c = cov_eigenstrat(geno, bayesian)
+    n = c.shape[0]
+    tr = np.trace(c)
+    c = c * ((n - 1) / tr)
+    return c, tr, np.trace(c)
+
+
+def pca_eigen(genmat, eigen_cnt):
+    """CalcEigen on -C (src/genPCA.cpp:1262-1346): top-k eigenpairs, descending.
+    The reference's own tests pin eigenvectors only through rounded loadings,
+    so this is pinned against LAPACK (numpy eigh) on the oracle matrix."""
+    w, v = np.linalg.eigh(-genmat)
+    k = min(eigen_cnt, genmat.shape[0])
+    return -w[:k], v[:, :k]
+
+
+def _missing_pair_denom(geno, d):
+    """Denom[i,j] = sum_l d_l [i missing or j missing]
+    (src/genPCA.cpp:1201-1224, src/genEIGMIX.cpp:113-138)."""
+    m = (geno > 2).astype(np.float64).T          # [nsamp, nsnp]
+    dm = m * d[None, :]
+    r = dm.sum(axis=1)
+    return r[:, None] + r[None, :] - dm @ m.T
+
+
+def grm_gcta(geno):
+    """CGCTA_AlgArith::Run (src/genPCA.cpp:1148-1237)."""
+    s, num, avg = _avg_geno(geno)
+    scale = _rsqrt_prod(avg)
+    c = _zzt(_centred(geno, avg, scale))
+    poly = ((0 < s) & (s < 2 * num)).astype(np.float64)      # :1206
+    nlocus = int(poly.sum())
+    denom = np.rint(_missing_pair_denom(geno, poly))
+    return c / (2.0 * (nlocus - denom))
+
+
+def grm_eigenstrat(geno):
+    """gnrGRM method "Eigenstrat" (src/genPCA.cpp:1636-1647)."""
+    return pca_genmat(geno)[0]
+
+
+def grm_corr(geno):
+    """gnrGRM method "Corr" (src/genPCA.cpp:1658-1685)."""
+    g = grm_gcta(geno)
+    d = np.sqrt(np.diag(g))
+    out = g / (d[:, None] * d[None, :])
+    np.fill_diagonal(out, 1.0)
+    return out
+
+
+def eigmix_ibd(geno, diagadj=True):
+    """CEigMix_AlgArith::Run (src/genEIGMIX.cpp:60-156).
+    Returns (ibd, afreq)."""
+    s, num, avg = _avg_geno(geno)
+    c = _zzt(_centred(geno, avg, None))
+    af = 0.5 * avg
+    d = 4 * af * (1 - af)
+    sum_den = d.sum()
+    denom = _missing_pair_denom(geno, d)
+    if diagadj:
+        het = (geno == 1).sum(axis=0).astype(np.float64)
+        c[np.diag_indices_from(c)] -= het
+    return c / (sum_den - denom), af
+
+
+def grm_eigmix(geno):
+    """CalcEigMixGRM (src/genEIGMIX.cpp:645-652)."""
+    return 2.0 * eigmix_ibd(geno, diagadj=False)[0]
+
+
+# ---------------------------------------------------------------------------
+# Bit-plane packers and packed-bit pair kernels
+# ---------------------------------------------------------------------------
+
+_B1 = np.array([0, 1, 1, 0], dtype=np.uint8)   # src/dGenGWAS.cpp:1429-1475
+_B2 = np.array([0, 0, 1, 1], dtype=np.uint8)
+
+
+def pack_geno1b(geno, n_total=None):
+    """PackSNPGeno1b for every sample: returns (plane1, plane2) uint8
+    [nsamp, n_total/8]; SNP l sits at bit (l % 8) of byte l // 8; padding SNPs
+    encode as missing (plane1=0, plane2=1) (src/dGenGWAS.cpp:1467-1472)."""
+    nsnp, nsamp = geno.shape
+    if n_total is None:
+        n_total = (nsnp + 7) // 8 * 8
+    g = np.minimum(geno, 3).T                      # [nsamp, nsnp]
+    b1 = np.zeros((nsamp, n_total), dtype=np.uint8)
+    b2 = np.ones((nsamp, n_total), dtype=np.uint8)
+    b1[:, :nsnp] = _B1[g]
+    b2[:, :nsnp] = _B2[g]
+    p1 = np.packbits(b1, axis=1, bitorder="little")
+    p2 = np.packbits(b2, axis=1, bitorder="little")
+    return p1, p2
+
+
+def _popcount_rows(x):
+    return np.unpackbits(x, axis=-1).sum(axis=-1, dtype=np.int64)
+
+
+def ibs_counts_packed(geno):
+    """CIBSCount::thread_ibs_num (src/genIBS.cpp:154-273), literally on the
+    bit planes.  O(N^2 M/8) numpy work -- small inputs only."""
+    p1, p2 = pack_geno1b(geno)
+    n = p1.shape[0]
+    out = np.zeros((3, n, n), dtype=np.int64)
+    for i in range(n):
+        a1, a2 = p1[i][None, :], p2[i][None, :]
+        mask = (a1 | ~a2) & (p1 | ~p2)
+        ibs0 = ~((a1 ^ ~p1) | (a2 ^ ~p2)) & mask
+        ibs2 = ~((a1 ^ p1) | (a2 ^ p2)) & mask
+        n0 = _popcount_rows(ibs0)
+        n2 = _popcount_rows(ibs2)
+        out[0, i] = n0
+        out[2, i] = n2
+        out[1, i] = _popcount_rows(mask) - n0 - n2
+    return out
+
+
+def _channels(geno):
+    valid = (geno <= 2)
+    x = np.where(valid, geno, 0).astype(np.float64).T     # [nsamp, nsnp]
+    a = valid.astype(np.float64).T
+    return x, a
+
+
+def ibs_counts(geno):
+    """Same integers as ibs_counts_packed via indicator Grams (exact in f64
+    while counts < 2^53).  Returns int64 [3, n, n] = IBS0, IBS1, IBS2."""
+    valid = geno <= 2
+    e = [((geno == k) & valid).astype(np.float64).T for k in range(3)]
+    a = valid.astype(np.float64).T
+    nv = a @ a.T
+    ibs2 = sum(ek @ ek.T for ek in e)
+    ibs0 = e[0] @ e[2].T + e[2] @ e[0].T
+    out = np.stack([ibs0, nv - ibs0 - ibs2, ibs2])
+    return np.rint(out).astype(np.int64)
+
+
+def ibs_ave(counts):
+    """gnrIBSAve (src/genIBS.cpp:463-490)."""
+    c = counts.astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return (0.5 * c[1] + c[2]) / (c[0] + c[1] + c[2])
+
+
+def king_robust_counts(geno):
+    """CKINGRobust::thread_ibs_num (src/genKING.cpp:292-426): int64 [5, n, n]
+    = IBS0, nLoci, SumSq, N1_Aa, N2_Aa where N1_Aa[i,j] counts het loci of the
+    ROW sample i restricted to loci where j is valid (:328,377)."""
+    valid = geno <= 2
+    x, a = _channels(geno)
+    e0 = ((geno == 0) & valid).astype(np.float64).T
+    e1 = ((geno == 1) & valid).astype(np.float64).T
+    e2 = ((geno == 2) & valid).astype(np.float64).T
+    nloci = a @ a.T
+    ibs0 = e0 @ e2.T + e2 @ e0.T
+    x2 = x * x
+    sumsq = x2 @ a.T + a @ x2.T - 2 * (x @ x.T)
+    n1 = e1 @ a.T
+    n2 = a @ e1.T
+    return np.rint(np.stack([ibs0, nloci, sumsq, n1, n2])).astype(np.int64)
+
+
+def king_robust(counts, family_id=None):
+    """gnrIBD_KING_Robust epilogue (src/genKING.cpp:626-641).
+    family_id: int array with negative / None entries meaning NA."""
+    ibs0, nloci, sumsq, n1, n2 = [c.astype(np.float64) for c in counts]
+    n = ibs0.shape[0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r_ibs0 = np.where(nloci > 0, ibs0 / nloci, np.nan)
+        between = 0.5 - sumsq / (4.0 * np.minimum(n1, n2))
+        within = 0.5 - sumsq / (2.0 * (n1 + n2))
+    if family_id is None:
+        kin = between
+    else:
+        f = np.asarray(family_id)
+        same = (f[:, None] == f[None, :]) & (f[:, None] >= 0)
+        kin = np.where(same, within, between)
+    kin = np.where(np.isfinite(kin), kin, np.nan)
+    r_ibs0[np.diag_indices(n)] = 0.0
+    kin[np.diag_indices(n)] = 0.5
+    return r_ibs0, kin
+
+
+def king_homo(geno):
+    """CKINGHomo + gnrIBD_KING_Homo (src/genKING.cpp:69-266,493-570).
+    Returns (k0, k1)."""
+    s, num = snp_stats(geno)
+    p = np.where(num > 0, 0.5 * s / np.maximum(num, 1), 0.0)
+    af = p * (1 - p)
+    x, a = _channels(geno)
+    valid = geno <= 2
+    e0 = ((geno == 0) & valid).astype(np.float64).T
+    e2 = ((geno == 2) & valid).astype(np.float64).T
+    ibs0 = e0 @ e2.T + e2 @ e0.T
+    x2 = x * x
+    sumsq = x2 @ a.T + a @ x2.T - 2 * (x @ x.T)
+    s1 = (a * af[None, :]) @ a.T
+    s2 = (a * (af * af)[None, :]) @ a.T
+    with np.errstate(divide="ignore", invalid="ignore"):
+        theta = 0.5 - sumsq / (8 * s1)
+        k0 = ibs0 / (2 * s2)
+        k1 = 2 - 2 * k0 - 4 * theta
+    k0 = np.where(np.isfinite(k0), k0, np.nan)
+    k1 = np.where(np.isfinite(k1), k1, np.nan)
+    n = k0.shape[0]
+    k0[np.diag_indices(n)] = 0.0
+    k1[np.diag_indices(n)] = 0.0
+    return k0, k1
+
+
+def beta_counts(geno):
+    """CIndivBeta::thread_ibs_num (src/genBeta.cpp:65-178): int64 [2, n, n]
+    = ibscnt, num.  ibscnt = #(either het, both valid) + 2 #(same homozygote)."""
+    valid = geno <= 2
+    a = valid.astype(np.float64).T
+    e0 = ((geno == 0) & valid).astype(np.float64).T
+    e1 = ((geno == 1) & valid).astype(np.float64).T
+    e2 = ((geno == 2) & valid).astype(np.float64).T
+    num = a @ a.T
+    anyhet = e1 @ a.T + a @ e1.T - e1 @ e1.T
+    samehom = e0 @ e0.T + e2 @ e2.T
+    return np.rint(np.stack([anyhet + 2 * samehom, num])).astype(np.int64)
+
+
+def _offdiag_upper_sum_rowmajor(m):
+    """avg += s in the reference's row-major upper-triangle order."""
+    n = m.shape[0]
+    iu = np.triu_indices(n, 1)
+    return m[iu].sum()
+
+
+def indiv_beta(counts, inbreeding=True):
+    """gnrIBD_Beta (src/genBeta.cpp:361-460). Returns (beta, avg)."""
+    ibscnt, num = [c.astype(np.float64) for c in counts]
+    n = num.shape[0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        b = 0.5 * ibscnt / num
+        d = np.diag(ibscnt) / np.diag(num) - 1 if inbreeding else np.diag(b).copy()
+    avg = _offdiag_upper_sum_rowmajor(b) / (n * (n - 1) // 2)
+    b[np.diag_indices(n)] = d
+    return (b - avg) * (1.0 / (1 - avg)), avg
+
+
+def grm_indivbeta(counts):
+    """CalcIndivBetaGRM (src/genBeta.cpp:308-357). Returns (grm, avg)."""
+    ibscnt, num = [c.astype(np.float64) for c in counts]
+    n = num.shape[0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        b = 0.5 * ibscnt / num
+        b[np.diag_indices(n)] = np.diag(ibscnt) / np.diag(num) - 1
+    avg = _offdiag_upper_sum_rowmajor(b) / (n * (n - 1) // 2)
+    mn = b.min()
+    scale = 2.0 / (1 - mn)
+    out = (b - mn) * scale
+    out[np.diag_indices(n)] = (np.diag(b) - mn) * scale * 0.5 + 1
+    return out, avg
+
+
+# ---------------------------------------------------------------------------
+# Packed triangle helpers  (CdMatTri, src/dGenGWAS.h:511-583)
+# ---------------------------------------------------------------------------
+
+
+def to_packed_upper(m):
+    """Row-packed upper triangle: idx(r,c) = c + r(2N-r-1)/2, r <= c."""
+    n = m.shape[0]
+    return m[np.triu_indices(n)]
+
+
+def merge_grm(grms, weights):
+    """snpgdsMergeGRM weighted merge (src/genPCA.cpp:1834-1855)."""
+    w = np.asarray(weights, dtype=np.float64)
+    w = w / w.sum()
+    return sum(wi * g for wi, g in zip(w, grms))
+
+
+# ---------------------------------------------------------------------------
+# Synthetic genotypes: counter-based, any shard is
+# reproducible without communication.  The CUDA generator uses the same mixer.
+# ---------------------------------------------------------------------------
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+    z = x
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+    return z ^ (z >> np.uint64(31))
+
+
+def synth_geno(nsamp, nsnp, seed=20261017, maf_lo=0.05, maf_hi=0.5,
+               miss_rate=0.005, snp_start=0):
+    """uint8 [nsnp, nsamp] with p_l ~ U(maf_lo, maf_hi), g ~ Binomial(2, p_l),
+    missing (code 3) with probability miss_rate.  Bit-identical to the device
+    generator in snprelate_b200/csrc (same 64-bit mixer, same thresholds)."""
+    with np.errstate(over="ignore"):
+        l = (np.arange(nsnp, dtype=np.uint64) + np.uint64(snp_start))
+        seed = np.uint64(seed)
+        hp = _splitmix64(seed ^ (l * np.uint64(0xD1342543DE82EF95)))
+        u = (hp >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+        p = maf_lo + (maf_hi - maf_lo) * u
+        t0 = (1 - p) ** 2
+        t1 = t0 + 2 * p * (1 - p)
+        th0 = np.minimum(np.floor(t0 * 4294967296.0), 4294967295.0).astype(np.uint64)
+        th1 = np.minimum(np.floor(t1 * 4294967296.0), 4294967295.0).astype(np.uint64)
+        thm = np.uint64(min(int(miss_rate * 4294967296.0), 4294967295))
+        i = np.arange(nsamp, dtype=np.uint64)
+        key = _splitmix64((hp[:, None] + i[None, :] * np.uint64(0x9E3779B97F4A7C15)) & _M64)
+        r = key >> np.uint64(32)
+        rm = key & np.uint64(0xFFFFFFFF)
+        g = (r >= th0[:, None]).astype(np.uint8) + (r >= th1[:, None]).astype(np.uint8)
+        g = np.where(rm < thm, np.uint8(3), g).astype(np.uint8)
+    return g
