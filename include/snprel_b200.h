@@ -1,0 +1,196 @@
+/*
+ * snprel_b200.h -- C ABI of libsnprel_b200.so
+ *
+ * B200-native (sm_100a) replacement for ONE path of zhengxwen/SNPRelate: the
+ * pairwise N x N relatedness-matrix accumulation over 2-bit SNP genotype blocks
+ * behind snpgdsGRM / snpgdsPCA / snpgdsEIGMIX / snpgdsIBS / snpgdsIBSNum /
+ * snpgdsIBDKING / snpgdsIndivBeta.  Every entry point below names the reference
+ * interface (file:line under the reference's source tree) it stands in for; the
+ * R-side binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 on success and a
+ *     non-zero code on failure, never throws; snprel_last_error() returns the
+ *     message (the reference stores it via GDS_SetError and exposes it through
+ *     gnrErrMsg, src/SNPRelate.cpp:1099-1104).
+ *   - a context owns one CUDA device; it is the analogue of the reference's
+ *     process-global GWAS::MCWorkingGeno (src/dGenGWAS.cpp:2000): first the
+ *     genotype workspace is set, then estimators run on it with no genotype
+ *     argument.  One context per host thread; not re-entrant (like the
+ *     reference, src/dGenGWAS.cpp:2198-2200).
+ *   - host genotype blocks are SNP-major, sample-fastest uint8 [cnt][n_samp]
+ *     with 0/1/2 = #A alleles and anything > 2 = missing: exactly what
+ *     CdBaseWorkSpace::snpRead(start, cnt, buf, RDim_Sample_X_SNP) produces
+ *     (src/dGenGWAS.h:94, src/dGenGWAS.cpp:677-733).
+ *   - n x n outputs are full symmetric column-major doubles (Rf_allocMatrix
+ *     layout, src/genPCA.cpp:1593-1594) or, with packed != 0, the row-packed
+ *     upper triangle of n(n+1)/2 doubles (CdMatTri order, src/dGenGWAS.h:556-561;
+ *     what useMatrix=TRUE returns, src/genPCA.cpp:1596-1598).
+ *   - there is no CPU fallback: every call fails loudly without a device.
+ */
+#ifndef SNPREL_B200_H
+#define SNPREL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct snprel_ctx snprel_ctx;
+
+/* ---- context ---------------------------------------------------------- */
+
+/* Create a context on CUDA device `device`. */
+int snprel_create(snprel_ctx **out, int device);
+void snprel_destroy(snprel_ctx *ctx);
+/* Last error message of this context (or of the failed create when ctx==NULL).
+ * Replaces gnrErrMsg (src/SNPRelate.cpp:1099-1104). */
+const char *snprel_last_error(snprel_ctx *ctx);
+/* Library version string. */
+const char *snprel_version(void);
+
+/* ---- genotype workspace  (gnrSetGenoSpace, src/SNPRelate.cpp:76-114;
+ *      CGenoReadBySNP block iterator, src/dGenGWAS.cpp:1218-1397) ---------- */
+
+/* Start a workspace of n_samp samples and room for up to snp_capacity SNPs.
+ * Device layout: 2-bit genotypes, SNP-major rows padded to 256 samples. */
+int snprel_geno_begin(snprel_ctx *ctx, int64_t n_samp, int64_t snp_capacity);
+/* Append `cnt` SNPs from a HOST uint8 block [cnt][n_samp] (what one
+ * CGenoReadBySNP::Read() yields).  Packed to 2 bits on the device. */
+int snprel_geno_push_u8(snprel_ctx *ctx, const uint8_t *geno, int64_t cnt);
+/* Append `cnt` SNPs from HOST 2-bit rows (4 genotypes per byte, LSB first,
+ * code 3 = missing; GDS dBit2 encoding) with `row_bytes` bytes per SNP row. */
+int snprel_geno_push_2b(snprel_ctx *ctx, const uint8_t *packed, int64_t cnt,
+                        int64_t row_bytes);
+/* Fill the workspace with `n_snp` synthetic SNPs on the device (counter-based
+ * generator; SNP l uses global index snp_start+l so SNP shards of one data
+ * set can be generated independently).  Benchmark / test input only. */
+int snprel_geno_synth(snprel_ctx *ctx, int64_t n_snp, uint64_t seed,
+                      double maf_lo, double maf_hi, double miss_rate,
+                      int64_t snp_start);
+/* gnrGetGenoDim (src/SNPRelate.cpp): current selected dimensions. */
+int snprel_geno_dim(snprel_ctx *ctx, int64_t *n_samp, int64_t *n_snp);
+/* Copy the workspace back as HOST uint8 [n_snp][n_samp] (gnrCopyGenoMem,
+ * src/SNPRelate.cpp:322). */
+int snprel_geno_copy_u8(snprel_ctx *ctx, uint8_t *out);
+
+/* gnrSNPRateFreq (src/SNPRelate.cpp:243) / Get_AF_MR_perSNP
+ * (src/dGenGWAS.cpp:472-552): per-SNP allele frequency, minor allele frequency
+ * and missing rate (any pointer may be NULL). NaN where all samples missing. */
+int snprel_snp_ratefreq(snprel_ctx *ctx, double *af, double *maf, double *mr);
+/* gnrSelSNP_Base (src/SNPRelate.cpp:184, src/dGenGWAS.cpp:361-397): drop SNPs
+ * failing the filters and compact the workspace.  maf < 0 / missrate > 1
+ * disable that filter (R passes -1 / 2 for NaN, R/Internal.R:438-439).
+ * out_sel (nullable) receives the 0/1 keep flag per SNP BEFORE compaction;
+ * n_removed (nullable) the number of SNPs dropped. */
+int snprel_select_snp_base(snprel_ctx *ctx, int remove_mono, double maf,
+                           double missrate, uint8_t *out_sel,
+                           int64_t *n_removed);
+
+/* ---- packed-bit estimators (integer, bit exact) ----------------------- */
+
+/* gnrIBSNum (src/genIBS.cpp:500-550): three n x n int32 matrices. */
+int snprel_ibs_num(snprel_ctx *ctx, int32_t *ibs0, int32_t *ibs1, int32_t *ibs2);
+/* gnrIBSAve (src/genIBS.cpp:441-497). */
+int snprel_ibs_ave(snprel_ctx *ctx, double *out, int packed);
+/* gnrIBD_KING_Robust (src/genKING.cpp:576-679).  family_id: int[n_samp], same
+ * id (and not SNPREL_NA_INT) = within-family estimator; NULL = all unrelated. */
+int snprel_king_robust(snprel_ctx *ctx, const int32_t *family_id, double *ibs0,
+                       double *kinship, int packed);
+/* Raw KING-robust counters (TS_KINGRobust, src/genKING.cpp:274-281) as five
+ * n x n int32 matrices: IBS0, nLoci, SumSq, N1_Aa, N2_Aa (row = sample 1). */
+int snprel_king_robust_counts(snprel_ctx *ctx, int32_t *out5);
+/* gnrIBD_KING_Homo (src/genKING.cpp:493-570): k0, k1. */
+int snprel_king_homo(snprel_ctx *ctx, double *k0, double *k1, int packed);
+/* gnrIBD_Beta (src/genBeta.cpp:361-460).  avg_out (nullable) receives the
+ * value the reference publishes through gnrGRM_avg_val (src/genPCA.cpp:1608). */
+int snprel_indiv_beta(snprel_ctx *ctx, int inbreeding, double *out, int packed,
+                      double *avg_out);
+/* Raw IndivBeta counters (TS_Beta, src/genBeta.cpp:50-54): ibscnt, num. */
+int snprel_indiv_beta_counts(snprel_ctx *ctx, int32_t *out2);
+
+/* ---- covariance-type estimators (tcgen05 table-Gram) ------------------ */
+
+#define SNPREL_GRM_EIGENSTRAT 0
+#define SNPREL_GRM_GCTA       1
+#define SNPREL_GRM_CORR       2
+#define SNPREL_GRM_EIGMIX     3
+#define SNPREL_GRM_INDIVBETA  4
+
+#define SNPREL_NA_INT INT32_MIN
+
+/* gnrGRM (src/genPCA.cpp:1614-1717): method is one of SNPREL_GRM_*.
+ * "Corr" ignores `packed` like the reference (src/genPCA.cpp:1658-1685).
+ * avg_out (nullable): gnrGRM_avg_val for IndivBeta. */
+int snprel_grm(snprel_ctx *ctx, int method, double *out, int packed,
+               double *avg_out);
+/* gnrPCA, algorithm "exact" (src/genPCA.cpp:1355-1452): covariance
+ * (genmat, nullable), TraceXTX, TraceVal, and the top eigen_cnt eigenpairs of
+ * the normalised matrix (eigval[n_samp] with NaN beyond eigen_cnt, eigvec
+ * n_samp x eigen_cnt column-major; both nullable => genmat.only). */
+int snprel_pca(snprel_ctx *ctx, int eigen_cnt, int bayesian, double *genmat,
+               double *trace_xtx, double *trace_val, double *eigval,
+               double *eigvec);
+/* gnrEigMix (src/genEIGMIX.cpp:656-735): ibd (nullable), afreq[n_snp]
+ * (nullable), eigenpairs as in snprel_pca (eigen_cnt == 0 => none). */
+int snprel_eigmix(snprel_ctx *ctx, int eigen_cnt, int diagadj, double *ibd,
+                  double *afreq, double *eigval, double *eigvec);
+
+/* ---- split accumulate / reduce / finish (multi-GPU SNP sharding) ------- */
+
+#define SNPREL_EST_IBS          10
+#define SNPREL_EST_KING_ROBUST  11
+#define SNPREL_EST_BETA         12
+#define SNPREL_EST_KING_HOMO    13
+/* estimator ids 0..3 are the SNPREL_GRM_* covariance methods */
+
+/* Per-rank plan statistics of the covariance estimators; all ranks must agree
+ * on the fixed-point format, so the host max/sum-reduces these before
+ * snprel_accumulate (see snprelate_b200/dist.py). */
+typedef struct snprel_plan {
+    double max_abs;       /* max |table value| over local SNPs            */
+    double sum_bound;     /* sum over local SNPs of the per-SNP magnitude */
+    int64_t max_missing;  /* max over samples of local missing count      */
+    int64_t n_snp;        /* local SNP count                              */
+    int32_t frac_bits;    /* in: <0 = auto; out: chosen                    */
+    int32_t bayesian;     /* Eigenstrat only                              */
+} snprel_plan;
+
+int snprel_plan_local(snprel_ctx *ctx, int estimator, snprel_plan *plan);
+/* Accumulate this rank's SNPs into the device accumulators. */
+int snprel_accumulate(snprel_ctx *ctx, int estimator, const snprel_plan *plan);
+/* Enumerate the device buffers that must be sum-reduced across ranks.
+ * kind: 0 = int64, 1 = uint32, 2 = float64.  Returns the number of buffers;
+ * call with idx in [0, count). */
+int snprel_reduce_buffer_count(snprel_ctx *ctx);
+int snprel_reduce_buffer(snprel_ctx *ctx, int idx, void **dev_ptr,
+                         int64_t *count, int *kind);
+/* After the reduction: the snprel_grm / snprel_pca / snprel_eigmix /
+ * snprel_ibs_* / snprel_king_* / snprel_indiv_beta calls above finish from the
+ * reduced accumulators instead of accumulating again. */
+int snprel_mark_reduced(snprel_ctx *ctx);
+
+/* ---- introspection for benchmarks / tests ------------------------------ */
+
+/* Number of kernels this library launched on the context so far. */
+int64_t snprel_kernel_launches(snprel_ctx *ctx);
+/* Device-side duration (ms, CUDA events on the library's stream) and launch
+ * count of the dominant kernel of the last accumulate call. */
+int snprel_last_hot_kernel(snprel_ctx *ctx, double *ms, int64_t *launches,
+                           double *algorithmic_units);
+/* Run the estimator's accumulation `reps` times on the resident workspace and
+ * return the average device time per repetition in ms (bench.py `value`). */
+int snprel_time_accumulate(snprel_ctx *ctx, int estimator, int reps, double *ms);
+/* Exact integer table-Gram of the tcgen05 kernel for tests:
+ * out[i][j] = sum_l tabA[l][g_il] * tabB[g_jl], int8 tables, int64 out
+ * (n_samp x n_samp row-major, all entries). */
+int snprel_table_gram(snprel_ctx *ctx, const int8_t *tabA /*[n_snp][4]*/,
+                      const int8_t *tabB /*[4]*/, int64_t *out);
+/* Same product on the CUDA-core fp64 reference kernel (device cross-check). */
+int snprel_debug_flags(snprel_ctx *ctx, uint32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNPREL_B200_H */

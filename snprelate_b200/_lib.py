@@ -1,0 +1,315 @@
+"""ctypes binding of libsnprel_b200.so (the C ABI declared in include/snprel_b200.h).
+
+This is the same binding an R ``.Call`` shim would use (INTEGRATION.md shows it);
+Python is only the test / benchmark host here because the image has no R.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+GRM_METHODS = {"Eigenstrat": 0, "GCTA": 1, "Corr": 2, "EIGMIX": 3, "IndivBeta": 4}
+EST_IBS, EST_KING_ROBUST, EST_BETA, EST_KING_HOMO = 10, 11, 12, 13
+NA_INT = -2147483648
+
+
+class SNPRelError(RuntimeError):
+    """Raised for every failure reported by the CUDA library (the analogue of the
+    R error raised through COREARRAY_CATCH / gnrErrMsg)."""
+
+
+class Plan(C.Structure):
+    _fields_ = [("max_abs", C.c_double), ("sum_bound", C.c_double),
+                ("max_missing", C.c_int64), ("n_snp", C.c_int64),
+                ("frac_bits", C.c_int32), ("bayesian", C.c_int32)]
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libsnprel_b200.so")
+
+
+def load_library():
+    """Load the CUDA library; fails loudly when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise SNPRelError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    p, i32, i64, u64, dbl, u32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_uint32
+    sig = {
+        "snprel_create": [C.POINTER(p), i32],
+        "snprel_geno_begin": [p, i64, i64],
+        "snprel_geno_push_u8": [p, p, i64],
+        "snprel_geno_push_2b": [p, p, i64, i64],
+        "snprel_geno_synth": [p, i64, u64, dbl, dbl, dbl, i64],
+        "snprel_geno_dim": [p, C.POINTER(i64), C.POINTER(i64)],
+        "snprel_geno_copy_u8": [p, p],
+        "snprel_snp_ratefreq": [p, p, p, p],
+        "snprel_select_snp_base": [p, i32, dbl, dbl, p, C.POINTER(i64)],
+        "snprel_ibs_num": [p, p, p, p],
+        "snprel_ibs_ave": [p, p, i32],
+        "snprel_king_robust": [p, p, p, p, i32],
+        "snprel_king_robust_counts": [p, p],
+        "snprel_king_homo": [p, p, p, i32],
+        "snprel_indiv_beta": [p, i32, p, i32, C.POINTER(dbl)],
+        "snprel_indiv_beta_counts": [p, p],
+        "snprel_grm": [p, i32, p, i32, C.POINTER(dbl)],
+        "snprel_pca": [p, i32, i32, p, C.POINTER(dbl), C.POINTER(dbl), p, p],
+        "snprel_eigmix": [p, i32, i32, p, p, p, p],
+        "snprel_plan_local": [p, i32, C.POINTER(Plan)],
+        "snprel_accumulate": [p, i32, C.POINTER(Plan)],
+        "snprel_reduce_buffer_count": [p],
+        "snprel_reduce_buffer": [p, i32, C.POINTER(p), C.POINTER(i64), C.POINTER(i32)],
+        "snprel_mark_reduced": [p],
+        "snprel_last_hot_kernel": [p, C.POINTER(dbl), C.POINTER(i64), C.POINTER(dbl)],
+        "snprel_time_accumulate": [p, i32, i32, C.POINTER(dbl)],
+        "snprel_table_gram": [p, p, p, p],
+        "snprel_debug_flags": [p, u32],
+    }
+    for name, args in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = i32
+    lib.snprel_destroy.argtypes = [p]
+    lib.snprel_destroy.restype = None
+    lib.snprel_last_error.argtypes = [p]
+    lib.snprel_last_error.restype = C.c_char_p
+    lib.snprel_version.argtypes = []
+    lib.snprel_version.restype = C.c_char_p
+    lib.snprel_kernel_launches.argtypes = [p]
+    lib.snprel_kernel_launches.restype = i64
+    _LIB = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "snprel_create", "snprel_destroy", "snprel_last_error", "snprel_version",
+    "snprel_geno_begin", "snprel_geno_push_u8", "snprel_geno_push_2b", "snprel_geno_synth",
+    "snprel_geno_dim", "snprel_geno_copy_u8", "snprel_snp_ratefreq", "snprel_select_snp_base",
+    "snprel_ibs_num", "snprel_ibs_ave", "snprel_king_robust", "snprel_king_robust_counts",
+    "snprel_king_homo", "snprel_indiv_beta", "snprel_indiv_beta_counts", "snprel_grm",
+    "snprel_pca", "snprel_eigmix", "snprel_plan_local", "snprel_accumulate",
+    "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced",
+    "snprel_kernel_launches", "snprel_last_hot_kernel", "snprel_time_accumulate",
+    "snprel_table_gram", "snprel_debug_flags",
+]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One CUDA device + one genotype workspace (the reference's process-global
+    MCWorkingGeno, src/dGenGWAS.cpp:2000)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.snprel_create(C.byref(h), int(device))
+        if rc != 0:
+            raise SNPRelError(self.lib.snprel_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.snprel_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SNPRelError(self.lib.snprel_last_error(self.h).decode())
+
+    # ---- workspace ----
+    def geno_begin(self, n_samp, snp_capacity):
+        self._ck(self.lib.snprel_geno_begin(self.h, int(n_samp), int(snp_capacity)))
+
+    def geno_push_u8(self, block):
+        block = np.ascontiguousarray(block, dtype=np.uint8)
+        if block.ndim != 2:
+            raise SNPRelError("geno_push_u8: block must be [cnt, n_samp]")
+        self._ck(self.lib.snprel_geno_push_u8(self.h, _ptr(block), block.shape[0]))
+
+    def geno_push_2b(self, packed):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        self._ck(self.lib.snprel_geno_push_2b(self.h, _ptr(packed), packed.shape[0], packed.shape[1]))
+
+    def geno_synth(self, n_snp, seed=20261017, maf_lo=0.05, maf_hi=0.5, miss_rate=0.005, snp_start=0):
+        self._ck(self.lib.snprel_geno_synth(self.h, int(n_snp), int(seed), float(maf_lo), float(maf_hi),
+                                            float(miss_rate), int(snp_start)))
+
+    def geno_dim(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self.lib.snprel_geno_dim(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def geno_copy_u8(self):
+        n, m = self.geno_dim()
+        out = np.empty((m, n), dtype=np.uint8)
+        self._ck(self.lib.snprel_geno_copy_u8(self.h, _ptr(out)))
+        return out
+
+    def snp_ratefreq(self):
+        _, m = self.geno_dim()
+        af, maf, mr = (np.empty(m) for _ in range(3))
+        self._ck(self.lib.snprel_snp_ratefreq(self.h, _ptr(af), _ptr(maf), _ptr(mr)))
+        return af, maf, mr
+
+    def select_snp_base(self, remove_mono=True, maf=-1.0, missrate=2.0):
+        _, m = self.geno_dim()
+        sel = np.empty(m, dtype=np.uint8)
+        nrm = C.c_int64()
+        self._ck(self.lib.snprel_select_snp_base(self.h, int(bool(remove_mono)), float(maf), float(missrate),
+                                                 _ptr(sel), C.byref(nrm)))
+        return sel.astype(bool), nrm.value
+
+    # ---- estimators ----
+    def _out(self, packed):
+        n, _ = self.geno_dim()
+        return np.empty(n * (n + 1) // 2) if packed else np.empty((n, n))
+
+    def ibs_num(self):
+        n, _ = self.geno_dim()
+        o = [np.empty((n, n), dtype=np.int32) for _ in range(3)]
+        self._ck(self.lib.snprel_ibs_num(self.h, _ptr(o[0]), _ptr(o[1]), _ptr(o[2])))
+        return o
+
+    def ibs_ave(self, packed=False):
+        o = self._out(packed)
+        self._ck(self.lib.snprel_ibs_ave(self.h, _ptr(o), int(packed)))
+        return o
+
+    def king_robust(self, family_id=None, packed=False):
+        a, b = self._out(packed), self._out(packed)
+        fam = None if family_id is None else np.ascontiguousarray(family_id, dtype=np.int32)
+        self._ck(self.lib.snprel_king_robust(self.h, _ptr(fam), _ptr(a), _ptr(b), int(packed)))
+        return a, b
+
+    def king_robust_counts(self):
+        n, _ = self.geno_dim()
+        o = np.empty((5, n, n), dtype=np.int32)
+        self._ck(self.lib.snprel_king_robust_counts(self.h, _ptr(o)))
+        return o
+
+    def king_homo(self, packed=False):
+        a, b = self._out(packed), self._out(packed)
+        self._ck(self.lib.snprel_king_homo(self.h, _ptr(a), _ptr(b), int(packed)))
+        return a, b
+
+    def indiv_beta(self, inbreeding=True, packed=False):
+        o = self._out(packed)
+        avg = C.c_double()
+        self._ck(self.lib.snprel_indiv_beta(self.h, int(inbreeding), _ptr(o), int(packed), C.byref(avg)))
+        return o, avg.value
+
+    def indiv_beta_counts(self):
+        n, _ = self.geno_dim()
+        o = np.empty((2, n, n), dtype=np.int32)
+        self._ck(self.lib.snprel_indiv_beta_counts(self.h, _ptr(o)))
+        return o
+
+    def grm(self, method="GCTA", packed=False):
+        if method not in GRM_METHODS:
+            raise SNPRelError("Invalid 'method'!")
+        if method == "Corr":
+            packed = False
+        o = self._out(packed)
+        avg = C.c_double()
+        self._ck(self.lib.snprel_grm(self.h, GRM_METHODS[method], _ptr(o), int(packed), C.byref(avg)))
+        return o, avg.value
+
+    def pca(self, eigen_cnt=32, bayesian=False, need_genmat=False, genmat_only=False):
+        n, _ = self.geno_dim()
+        k = min(int(eigen_cnt), n)
+        genmat = np.empty((n, n)) if (need_genmat or genmat_only) else None
+        tx, tv = C.c_double(), C.c_double()
+        eigval = eigvec = None
+        if not genmat_only:
+            eigval = np.empty(n)
+            eigvec = np.empty((k, n))      # column-major n x k == C-order k x n
+        self._ck(self.lib.snprel_pca(self.h, k, int(bool(bayesian)), _ptr(genmat), C.byref(tx), C.byref(tv),
+                                     _ptr(eigval), _ptr(eigvec)))
+        return dict(TraceXTX=tx.value, TraceVal=tv.value, genmat=genmat, eigenval=eigval,
+                    eigenvect=None if eigvec is None else eigvec.T)
+
+    def eigmix(self, eigen_cnt=32, diagadj=True, ibdmat=False):
+        n, m = self.geno_dim()
+        k = n if (eigen_cnt < 0 or eigen_cnt > n) else int(eigen_cnt)
+        ibd = np.empty((n, n)) if ibdmat else None
+        af = np.empty(m)
+        eigval = np.empty(n) if k > 0 else None
+        eigvec = np.empty((k, n)) if k > 0 else None
+        self._ck(self.lib.snprel_eigmix(self.h, k, int(bool(diagadj)), _ptr(ibd), _ptr(af), _ptr(eigval),
+                                        _ptr(eigvec)))
+        return dict(eigenval=eigval, eigenvect=None if eigvec is None else eigvec.T, afreq=af, ibd=ibd)
+
+    # ---- split accumulate / reduce / finish ----
+    def plan_local(self, est, bayesian=False):
+        pl = Plan()
+        pl.frac_bits = -1
+        pl.bayesian = int(bool(bayesian))
+        self._ck(self.lib.snprel_plan_local(self.h, int(est), C.byref(pl)))
+        return pl
+
+    def accumulate(self, est, plan=None):
+        self._ck(self.lib.snprel_accumulate(self.h, int(est), None if plan is None else C.byref(plan)))
+
+    def reduce_buffers(self):
+        out = []
+        for i in range(self.lib.snprel_reduce_buffer_count(self.h)):
+            ptr, cnt, kind = C.c_void_p(), C.c_int64(), C.c_int()
+            self._ck(self.lib.snprel_reduce_buffer(self.h, i, C.byref(ptr), C.byref(cnt), C.byref(kind)))
+            out.append((ptr.value, cnt.value, kind.value))
+        return out
+
+    def mark_reduced(self):
+        self._ck(self.lib.snprel_mark_reduced(self.h))
+
+    # ---- introspection ----
+    def kernel_launches(self):
+        return int(self.lib.snprel_kernel_launches(self.h))
+
+    def last_hot_kernel(self):
+        ms, n, u = C.c_double(), C.c_int64(), C.c_double()
+        self._ck(self.lib.snprel_last_hot_kernel(self.h, C.byref(ms), C.byref(n), C.byref(u)))
+        return ms.value, n.value, u.value
+
+    def time_accumulate(self, est, reps=1):
+        ms = C.c_double()
+        self._ck(self.lib.snprel_time_accumulate(self.h, int(est), int(reps), C.byref(ms)))
+        return ms.value
+
+    def table_gram(self, tabA, tabB):
+        n, m = self.geno_dim()
+        tabA = np.ascontiguousarray(tabA, dtype=np.int8)
+        tabB = np.ascontiguousarray(tabB, dtype=np.int8)
+        if tabA.shape != (m, 4) or tabB.shape != (4,):
+            raise SNPRelError("table_gram: tabA must be [n_snp, 4] and tabB [4] int8")
+        out = np.empty((n, n), dtype=np.int64)
+        self._ck(self.lib.snprel_table_gram(self.h, _ptr(tabA), _ptr(tabB), _ptr(out)))
+        return out
+
+    def debug_flags(self, flags):
+        self._ck(self.lib.snprel_debug_flags(self.h, int(flags)))

@@ -1,0 +1,281 @@
+"""Host-side mirror of the reference's R interface for the relatedness path.
+
+Function names, argument names (``.`` -> ``_``), defaults, selection semantics and
+error messages follow ``R/IBD.R``, ``R/PCA.R``, ``R/IBS.R`` and ``.InitFile2``
+(``R/Internal.R:166-484``); results come back as dicts with the reference's list
+element names (``sample.id``, ``snp.id``, ``grm``, ``eigenval`` ...).  All compute
+runs in libsnprel_b200.so; this module only selects samples / SNPs, streams
+genotype blocks to the device the way ``CGenoReadBySNP`` would
+(``src/dGenGWAS.cpp:1218-1397``) and shapes the outputs.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from ._lib import Context, SNPRelError, EST_IBS, EST_KING_ROBUST, EST_BETA, NA_INT
+
+_BLOCK_BYTES = 64 << 20   # host block size for push_u8 (the reference reads cache-sized blocks)
+
+
+class GenotypeData:
+    """Stand-in for an open SNP GDS file object (``snpgdsOpen``).
+
+    ``genotype`` is uint8 ``[n_snp, n_samp]`` (SNP-major, sample fastest, the
+    ``snp.order``-free layout ``snpRead`` produces; 0/1/2, >2 missing) or, with
+    ``packed_2bit=True``, GDS dBit2 rows ``[n_snp, ceil(n_samp/4)]``.
+    """
+
+    def __init__(self, genotype, sample_id=None, snp_id=None, chromosome=None,
+                 packed_2bit=False, n_samp=None):
+        g = np.asarray(genotype)
+        if g.dtype != np.uint8 or g.ndim != 2:
+            raise SNPRelError("genotype must be a 2-D uint8 array [n_snp, n_samp]")
+        self.packed = bool(packed_2bit)
+        self.genotype = g
+        self.n_snp = g.shape[0]
+        if self.packed:
+            if n_samp is None:
+                raise SNPRelError("n_samp is required for 2-bit packed genotypes")
+            self.n_samp = int(n_samp)
+        else:
+            self.n_samp = g.shape[1]
+        self.sample_id = np.arange(1, self.n_samp + 1) if sample_id is None else np.asarray(sample_id)
+        self.snp_id = np.arange(1, self.n_snp + 1) if snp_id is None else np.asarray(snp_id)
+        self.chromosome = None if chromosome is None else np.asarray(chromosome)
+        if len(self.sample_id) != self.n_samp or len(self.snp_id) != self.n_snp:
+            raise SNPRelError("sample_id / snp_id length does not match the genotype matrix")
+
+    def block_u8(self, snp_idx, samp_mask):
+        """uint8 block [len(snp_idx), n_selected_samples]."""
+        if self.packed:
+            rows = self.genotype[snp_idx]
+            g = np.stack([(rows >> (2 * k)) & 3 for k in range(4)], axis=-1)
+            g = g.reshape(rows.shape[0], -1)[:, :self.n_samp]
+        else:
+            g = self.genotype[snp_idx]
+        if samp_mask is not None:
+            g = g[:, samp_mask]
+        return np.ascontiguousarray(g, dtype=np.uint8)
+
+
+def _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, missing_rate,
+                num_thread, verbose, device=0, ctx=None):
+    """.InitFile2 (R/Internal.R:166-484): select, load the workspace, QC-filter."""
+    if not isinstance(gdsobj, GenotypeData):
+        raise SNPRelError("'gdsobj' should be a GenotypeData object")
+    if not (isinstance(num_thread, (int, np.integer)) and num_thread >= 1):
+        raise SNPRelError("`num.thread' should be a positive value or NA.")
+    # samples: membership, file order kept (R/Internal.R:292-303)
+    samp_mask = None
+    sample_ids = gdsobj.sample_id
+    if sample_id is not None:
+        sample_id = np.asarray(sample_id)
+        samp_mask = np.isin(gdsobj.sample_id, sample_id)
+        if samp_mask.sum() != len(sample_id):
+            raise SNPRelError("Some of sample.id do not exist!")
+        if samp_mask.sum() <= 0:
+            raise SNPRelError("No sample in the working dataset.")
+        sample_ids = gdsobj.sample_id[samp_mask]
+    # SNPs (R/Internal.R:316-422)
+    snp_mask = np.ones(gdsobj.n_snp, dtype=bool)
+    if snp_id is not None:
+        snp_id = np.asarray(snp_id)
+        snp_mask = np.isin(gdsobj.snp_id, snp_id)
+        if snp_mask.sum() != len(snp_id):
+            raise SNPRelError("Some of snp.id do not exist!")
+        if snp_mask.sum() <= 0:
+            raise SNPRelError("No SNP in the working dataset.")
+    if autosome_only is not False and gdsobj.chromosome is not None:
+        if autosome_only is True:
+            snp_mask &= (gdsobj.chromosome >= 1) & (gdsobj.chromosome <= 22)   # snpgdsOption defaults
+        else:
+            snp_mask &= (gdsobj.chromosome == autosome_only)
+    snp_idx = np.nonzero(snp_mask)[0]
+    snp_ids = gdsobj.snp_id[snp_idx]
+
+    # gnrSetGenoSpace: stream blocks to the device
+    ctx = ctx or Context(device)
+    n_samp = int(samp_mask.sum()) if samp_mask is not None else gdsobj.n_samp
+    ctx.geno_begin(n_samp, len(snp_idx))
+    rows_per_block = max(1, _BLOCK_BYTES // max(n_samp, 1))
+    for s in range(0, len(snp_idx), rows_per_block):
+        ctx.geno_push_u8(gdsobj.block_u8(snp_idx[s:s + rows_per_block], samp_mask))
+
+    # gnrSelSNP_Base (R/Internal.R:434-462)
+    if remove_monosnp or math.isfinite(maf) or math.isfinite(missing_rate):
+        t_maf = maf if math.isfinite(maf) else -1.0
+        t_mr = missing_rate if math.isfinite(missing_rate) else 2.0
+        sel, nrm = ctx.select_snp_base(remove_monosnp, t_maf, t_mr)
+        snp_ids = snp_ids[sel]
+        if verbose:
+            print(f"Excluding {nrm} SNP{'s' if nrm != 1 else ''} (monomorphic: {remove_monosnp}, "
+                  f"MAF: {maf}, missing rate: {missing_rate})")
+    n, m = ctx.geno_dim()
+    if verbose:
+        print(f"    # of samples: {n}\n    # of SNPs: {m}")
+    return dict(ctx=ctx, sample_id=sample_ids, snp_id=snp_ids, n_snp=m, n_samp=n)
+
+
+def _newmat(n, packed_values):
+    """R/Internal.R:46-51 wraps the packed vector into Matrix::dspMatrix(uplo='L');
+    here the packed row-upper vector is returned as-is with its dimension."""
+    return dict(n=n, x=packed_values, uplo="L")
+
+
+def snpgdsGRM(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_monosnp=True,
+              maf=float("nan"), missing_rate=0.01,
+              method="GCTA", num_thread=1, useMatrix=False, with_id=True, verbose=False, device=0):
+    """R/IBD.R:543-615 -> gnrGRM (src/genPCA.cpp:1614-1717)."""
+    methods = ("GCTA", "Eigenstrat", "EIGMIX", "Weighted", "Corr", "IndivBeta")
+    if method not in methods:
+        raise SNPRelError("'arg' should be one of " + ", ".join(f'"{m}"' for m in methods))
+    mtxt = method
+    if method == "Weighted":          # R/IBD.R:552-555
+        method = "EIGMIX"
+    ws = _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, missing_rate,
+                     num_thread, verbose, device)
+    with ws["ctx"] as ctx:
+        grm, avg = ctx.grm(method, packed=bool(useMatrix))
+    if useMatrix and method != "Corr":
+        grm = _newmat(ws["n_samp"], grm)
+    if not with_id:
+        return grm
+    rv = {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "method": mtxt, "grm": grm}
+    if method == "IndivBeta":
+        rv["avg_val"] = avg           # R/IBD.R:605-606
+    return rv
+
+
+def snpgdsPCA(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_monosnp=True,
+              maf=float("nan"), missing_rate=0.01, algorithm="exact", eigen_cnt=32, num_thread=1,
+              bayesian=False, need_genmat=False, genmat_only=False, eigen_method="DSPEVX",
+              verbose=False, device=0):
+    """R/PCA.R:22-91 -> gnrPCA "exact" (src/genPCA.cpp:1355-1452)."""
+    if algorithm != "exact":
+        raise SNPRelError("only algorithm='exact' is on the accelerated path "
+                          "(randomized PCA is out of scope, SURVEY.md section 2)")
+    if eigen_method not in ("DSPEVX", "DSPEV"):
+        raise SNPRelError("Unknown 'eigen.method'.")
+    ws = _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, missing_rate,
+                     num_thread, verbose, device)
+    if genmat_only:
+        need_genmat = True
+    if eigen_cnt <= 0:
+        eigen_cnt = ws["n_samp"]
+    with ws["ctx"] as ctx:
+        r = ctx.pca(eigen_cnt, bayesian, need_genmat, genmat_only)
+    eigenval = r["eigenval"]
+    return {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "eigenval": eigenval,
+            "eigenvect": r["eigenvect"],
+            "varprop": None if eigenval is None else eigenval / r["TraceVal"],
+            "TraceXTX": r["TraceXTX"], "Bayesian": bayesian, "genmat": r["genmat"]}
+
+
+def snpgdsEIGMIX(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_monosnp=True,
+                 maf=float("nan"), missing_rate=0.01, num_thread=1, eigen_cnt=32, diagadj=True,
+                 ibdmat=False, verbose=False, device=0):
+    """R/PCA.R:311-338 -> gnrEigMix (src/genEIGMIX.cpp:656-735)."""
+    ws = _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, missing_rate,
+                     num_thread, verbose, device)
+    if eigen_cnt < 0:
+        eigen_cnt = ws["n_samp"]
+    with ws["ctx"] as ctx:
+        r = ctx.eigmix(eigen_cnt, diagadj, ibdmat)
+    return {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "eigenval": r["eigenval"],
+            "eigenvect": r["eigenvect"], "afreq": r["afreq"], "ibd": r["ibd"], "diagadj": diagadj}
+
+
+def snpgdsIBS(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_monosnp=True,
+              maf=float("nan"), missing_rate=0.01, num_thread=1, useMatrix=False, verbose=False,
+              device=0):
+    """R/IBS.R:22-46 -> gnrIBSAve (src/genIBS.cpp:441-497)."""
+    ws = _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, missing_rate,
+                     num_thread, verbose, device)
+    with ws["ctx"] as ctx:
+        ibs = ctx.ibs_ave(packed=bool(useMatrix))
+    if useMatrix:
+        ibs = _newmat(ws["n_samp"], ibs)
+    return {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "ibs": ibs}
+
+
+def snpgdsIBSNum(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_monosnp=True,
+                 maf=float("nan"), missing_rate=0.01, num_thread=1, verbose=False, device=0):
+    """R/IBS.R:55-73 -> gnrIBSNum (src/genIBS.cpp:500-550)."""
+    ws = _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, missing_rate,
+                     num_thread, verbose, device)
+    with ws["ctx"] as ctx:
+        i0, i1, i2 = ctx.ibs_num()
+    return {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "ibs0": i0, "ibs1": i1, "ibs2": i2}
+
+
+def _family_codes(family_id, gdsobj, sample_id, ws):
+    """R/IBD.R:348-372: family.id -> integer factor codes, "" / None -> NA."""
+    if family_id is None:
+        return None
+    family_id = list(family_id)
+    if len(family_id) != ws["n_samp"]:
+        raise SNPRelError("'length(family.id)' should be the number of samples.")
+    if sample_id is not None:          # re-index to file order (R/IBD.R:356-357)
+        order = {s: k for k, s in enumerate(np.asarray(sample_id).tolist())}
+        family_id = [family_id[order[s]] for s in ws["sample_id"].tolist()]
+    levels = sorted({f for f in family_id if f is not None and f != "" and f == f})
+    code = {f: k + 1 for k, f in enumerate(levels)}
+    return np.array([code.get(f, NA_INT) if (f is not None and f != "" and f == f) else NA_INT
+                     for f in family_id], dtype=np.int32)
+
+
+def snpgdsIBDKING(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_monosnp=True,
+                  maf=float("nan"), missing_rate=0.01, type="KING-robust", family_id=None,
+                  num_thread=1, useMatrix=False, verbose=False, device=0):
+    """R/IBD.R:333-419 -> gnrIBD_KING_Robust / gnrIBD_KING_Homo."""
+    if type not in ("KING-robust", "KING-homo"):
+        raise SNPRelError("Invalid 'type'.")
+    ws = _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, missing_rate,
+                     num_thread, verbose, device)
+    fam = _family_codes(family_id, gdsobj, sample_id, ws)
+    rv = {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "afreq": None}
+    with ws["ctx"] as ctx:
+        if type == "KING-homo":
+            a, b = ctx.king_homo(packed=bool(useMatrix))
+            names = ("k0", "k1")
+        else:
+            a, b = ctx.king_robust(fam, packed=bool(useMatrix))
+            names = ("IBS0", "kinship")
+    if useMatrix:
+        a, b = _newmat(ws["n_samp"], a), _newmat(ws["n_samp"], b)
+    rv[names[0]], rv[names[1]] = a, b
+    return rv
+
+
+def snpgdsIndivBeta(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_monosnp=True,
+                    maf=float("nan"), missing_rate=0.01, method="weighted", inbreeding=True,
+                    num_thread=1, with_id=True, useMatrix=False, verbose=False, device=0):
+    """R/IBD.R:838-866 -> gnrIBD_Beta (src/genBeta.cpp:361-460)."""
+    if method != "weighted":
+        raise SNPRelError("'arg' should be \"weighted\"")
+    if not isinstance(inbreeding, (bool, np.bool_)):
+        raise SNPRelError("'inbreeding' must be TRUE or FALSE.")
+    ws = _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, missing_rate,
+                     num_thread, verbose, device)
+    with ws["ctx"] as ctx:
+        beta, avg = ctx.indiv_beta(inbreeding, packed=bool(useMatrix))
+    if useMatrix:
+        beta = _newmat(ws["n_samp"], beta)
+    if not with_id:
+        return beta
+    return {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "inbreeding": inbreeding,
+            "beta": beta, "avg_val": avg}
+
+
+def snpgdsSNPRateFreq(gdsobj, sample_id=None, snp_id=None, with_id=False, device=0):
+    """R/AllUtilities.R snpgdsSNPRateFreq -> gnrSNPRateFreq (src/SNPRelate.cpp:243)."""
+    ws = _init_file2(gdsobj, sample_id, snp_id, False, False, float("nan"), float("nan"), 1, False,
+                     device)
+    with ws["ctx"] as ctx:
+        af, maf, mr = ctx.snp_ratefreq()
+    rv = {"AlleleFreq": af, "MinorFreq": maf, "MissingRate": mr}
+    if with_id:
+        rv["sample.id"], rv["snp.id"] = ws["sample_id"], ws["snp_id"]
+    return rv

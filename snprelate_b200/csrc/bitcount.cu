@@ -1,0 +1,451 @@
+// Packed-bit pair kernels: IBS (CIBSCount::thread_ibs_num, src/genIBS.cpp:154-273),
+// KING-robust (CKINGRobust::thread_ibs_num, src/genKING.cpp:292-426) and IndivBeta
+// (CIndivBeta::thread_ibs_num, src/genBeta.cpp:65-178) counters, plus their
+// epilogues (gnrIBSAve/gnrIBSNum src/genIBS.cpp:441-550, gnrIBD_KING_Robust
+// src/genKING.cpp:576-679, gnrIBD_Beta / CalcIndivBetaGRM src/genBeta.cpp:263-460).
+//
+// Input: bit planes [word64][sample] of uint4 {p1.lo,p1.hi,p2.lo,p2.hi}
+// (geno.cu:planes_kernel).  One CTA owns a 64 x 64 tile of sample pairs, streams
+// the two 64-sample panels through shared memory with cp.async (16-byte chunks,
+// double buffered) and keeps a 4 x 4 block of pairs per thread in registers.
+// All arithmetic is integer (XOR/AND + __popc); counters are exact uint32 like
+// the reference's (TIBS / TS_KINGRobust / TS_Beta).
+#include "common.cuh"
+
+namespace snprel {
+
+constexpr int BT = 64;        // pairs tile edge
+constexpr int BKW = 8;        // 64-SNP words per pipeline stage
+constexpr int BTHREADS = 256;
+
+template <int EST> struct EstTraits;
+template <> struct EstTraits<SNPREL_EST_IBS> { static constexpr int NC = 3; };          // ibs0, ibs2, mask
+template <> struct EstTraits<SNPREL_EST_KING_ROBUST> { static constexpr int NC = 5; };  // ibs0, mask, het, Aa1, Aa2
+template <> struct EstTraits<SNPREL_EST_BETA> { static constexpr int NC = 3; };         // het, ibs2, mask
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+template <int EST>
+__device__ __forceinline__ void pair_update(uint32_t (&acc)[EstTraits<EST>::NC], uint32_t a1,
+                                            uint32_t a2, uint32_t b1, uint32_t b2) {
+    // validity: a genotype is missing iff (plane1, plane2) == (0, 1)
+    uint32_t mask = (a1 | ~a2) & (b1 | ~b2);
+    uint32_t x1 = a1 ^ b1, x2 = a2 ^ b2;
+    if (EST == SNPREL_EST_IBS) {
+        acc[0] += __popc(x1 & x2 & mask);      // ibs0: (0,0) vs (1,1)
+        acc[1] += __popc(~(x1 | x2) & mask);   // ibs2: identical
+        acc[2] += __popc(mask);
+    } else if (EST == SNPREL_EST_KING_ROBUST) {
+        acc[0] += __popc(x1 & x2 & mask);                 // ibs0
+        acc[1] += __popc(mask);                           // nLoci
+        acc[2] += __popc((x1 ^ x2) & mask);               // het: exactly one of the two is Aa
+        acc[3] += __popc(a1 & ~a2 & mask);                // N1_Aa (row sample)
+        acc[4] += __popc(b1 & ~b2 & mask);                // N2_Aa (column sample)
+    } else {
+        uint32_t het = (a1 ^ a2) | (b1 ^ b2);
+        acc[0] += __popc(het & mask);                     // either heterozygous
+        acc[1] += __popc(~(het | x1) & mask);             // same homozygote
+        acc[2] += __popc(mask);
+    }
+}
+
+template <int EST>
+__global__ void __launch_bounds__(BTHREADS)
+pair_count_kernel(const uint4 *__restrict__ planes, uint32_t *__restrict__ cnt, int64_t n_pad,
+                  int64_t n_words, int words_per_split) {
+    constexpr int NC = EstTraits<EST>::NC;
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    if (ti > tj) return;   // upper block triangle only
+    __shared__ uint4 sA[2][BKW][BT];
+    __shared__ uint4 sB[2][BKW][BT];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int64_t w_begin = (int64_t)blockIdx.z * words_per_split;
+    const int64_t w_end = min(n_words, w_begin + (int64_t)words_per_split);
+    const int64_t i0 = (int64_t)ti * BT, j0 = (int64_t)tj * BT;
+
+    uint32_t acc[4][4][NC];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int k = 0; k < NC; k++) acc[r][q][k] = 0;
+
+    auto load_stage = [&](int buf, int64_t w0) {
+        // BKW*BT = 512 uint4 per panel; 256 threads -> 2 per panel
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            int e = tid + h * BTHREADS;
+            int w = e >> 6, s = e & 63;
+            int64_t gw = w0 + w;
+            if (gw < w_end) {
+                cp_async16(&sA[buf][w][s], planes + gw * n_pad + i0 + s);
+                cp_async16(&sB[buf][w][s], planes + gw * n_pad + j0 + s);
+            }
+        }
+    };
+
+    int buf = 0;
+    if (w_begin < w_end) load_stage(0, w_begin);
+    cp_async_commit();
+    for (int64_t w0 = w_begin; w0 < w_end; w0 += BKW) {
+        if (w0 + BKW < w_end) load_stage(buf ^ 1, w0 + BKW);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const int nw = (int)min((int64_t)BKW, w_end - w0);
+        for (int w = 0; w < nw; w++) {
+            uint4 a[4], b[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) a[r] = sA[buf][w][ty + 16 * r];
+#pragma unroll
+            for (int q = 0; q < 4; q++) b[q] = sB[buf][w][tx + 16 * q];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    pair_update<EST>(acc[r][q], a[r].x, a[r].z, b[q].x, b[q].z);
+                    pair_update<EST>(acc[r][q], a[r].y, a[r].w, b[q].y, b[q].w);
+                }
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+    cp_async_wait<0>();
+
+    const int64_t plane = n_pad * n_pad;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            int64_t i = i0 + ty + 16 * r, j = j0 + tx + 16 * q;
+            if (j < i) continue;   // only the upper triangle is kept (CdMatTri)
+#pragma unroll
+            for (int k = 0; k < NC; k++)
+                if (acc[r][q][k]) atomicAdd(cnt + k * plane + i * n_pad + j, acc[r][q][k]);
+        }
+}
+
+template <int EST>
+static void launch_pair_count(snprel_ctx *c) {
+    const int64_t npad = c->n_samp_pad;
+    const int64_t tiles = (c->n_samp + BT - 1) / BT;
+    const int64_t n_words = c->plane_words;
+    // split the SNP words when the tile grid alone cannot fill the chip
+    int64_t ntile = tiles * (tiles + 1) / 2;
+    int64_t want = (int64_t)c->num_sms * 4;
+    int64_t splits = std::max<int64_t>(1, std::min<int64_t>((want + ntile - 1) / ntile,
+                                                           (n_words + BKW - 1) / BKW));
+    splits = std::min<int64_t>(splits, 65535);
+    int64_t wps = round_up((n_words + splits - 1) / splits, BKW);
+    splits = (n_words + wps - 1) / wps;
+    dim3 grid((unsigned)tiles, (unsigned)tiles, (unsigned)splits);
+    pair_count_kernel<EST><<<grid, BTHREADS, 0, c->stream>>>(c->planes.p, c->cnt.p, npad, n_words,
+                                                            (int)wps);
+    KERNEL_CHECK(c);
+}
+
+void bitcount_accumulate(snprel_ctx *c, int est) {
+    ensure_planes(c);
+    int nc = est == SNPREL_EST_KING_ROBUST ? 5 : 3;
+    if (est == SNPREL_EST_KING_ROBUST && c->n_snp >= 1073741824ll)
+        fail("The number of SNPs should be less than 1,073,741,824.");   // src/genKING.cpp:598
+    c->cnt.alloc((size_t)nc * c->n_samp_pad * c->n_samp_pad);
+    c->cnt_planes = nc;
+    c->cnt.zero(c->stream);
+    CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+    switch (est) {
+        case SNPREL_EST_IBS: launch_pair_count<SNPREL_EST_IBS>(c); break;
+        case SNPREL_EST_KING_ROBUST: launch_pair_count<SNPREL_EST_KING_ROBUST>(c); break;
+        case SNPREL_EST_BETA: launch_pair_count<SNPREL_EST_BETA>(c); break;
+        default: fail("internal: bad packed-bit estimator %d", est);
+    }
+    CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->hot_ms = ms;
+    c->hot_launches = 1;
+    c->hot_units = 0.5 * (double)c->n_samp * (double)c->n_samp * (double)c->n_snp;
+    c->accum_est = est;
+    c->accum_reduced = false;
+    c->reduce_list.clear();
+    c->reduce_list.push_back({c->cnt.p, (int64_t)c->cnt.n, 1});
+}
+
+// ---------------------------------------------------------------------------
+// epilogues
+// ---------------------------------------------------------------------------
+
+// out index helpers: full symmetric n x n (column-major == row-major) or the
+// row-packed upper triangle idx(r,c) = c + r(2n-r-1)/2 (src/dGenGWAS.h:556-561)
+__device__ __forceinline__ void store_sym(double *out, int packed, int64_t n, int64_t i,
+                                          int64_t j, double v) {
+    if (packed) {
+        out[j + i * (2 * n - i - 1) / 2] = v;
+    } else {
+        out[i * n + j] = v;
+        out[j * n + i] = v;
+    }
+}
+
+__global__ void ibs_num_kernel(const uint32_t *__restrict__ cnt, int32_t *__restrict__ o0,
+                               int32_t *__restrict__ o1, int32_t *__restrict__ o2, int64_t n,
+                               int64_t npad) {
+    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= n || j < i) return;
+    int64_t plane = npad * npad, k = i * npad + j;
+    uint32_t n0 = cnt[k], n2 = cnt[plane + k], nm = cnt[2 * plane + k];
+    uint32_t n1 = nm - n0 - n2;
+    o0[i * n + j] = o0[j * n + i] = (int32_t)n0;
+    o1[i * n + j] = o1[j * n + i] = (int32_t)n1;
+    o2[i * n + j] = o2[j * n + i] = (int32_t)n2;
+}
+
+__global__ void ibs_ave_kernel(const uint32_t *__restrict__ cnt, double *__restrict__ out,
+                               int packed, int64_t n, int64_t npad) {
+    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= n || j < i) return;
+    int64_t plane = npad * npad, k = i * npad + j;
+    uint32_t n0 = cnt[k], n2 = cnt[plane + k], nm = cnt[2 * plane + k];
+    uint32_t n1 = nm - n0 - n2;
+    // (0.5*IBS1 + IBS2) / (IBS0 + IBS1 + IBS2), src/genIBS.cpp:472-473
+    double v = (0.5 * (double)n1 + (double)n2) / (double)(n0 + n1 + n2);
+    store_sym(out, packed, n, i, j, v);
+}
+
+__global__ void king_robust_kernel(const uint32_t *__restrict__ cnt,
+                                   const int32_t *__restrict__ fam, double *__restrict__ oibs0,
+                                   double *__restrict__ okin, int packed, int64_t n, int64_t npad) {
+    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= n || j < i) return;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    if (i == j) {   // src/genKING.cpp:628
+        store_sym(oibs0, packed, n, i, j, 0.0);
+        store_sym(okin, packed, n, i, j, 0.5);
+        return;
+    }
+    int64_t plane = npad * npad, k = i * npad + j;
+    uint32_t ibs0 = cnt[k], nloci = cnt[plane + k], het = cnt[2 * plane + k];
+    uint32_t n1 = cnt[3 * plane + k], n2 = cnt[4 * plane + k];
+    uint32_t sumsq = het + 4u * ibs0;   // sum (g_i - g_j)^2, src/genKING.cpp:421
+    double r0 = nloci > 0 ? (double)ibs0 / (double)nloci : nan;
+    int f1 = fam ? fam[i] : SNPREL_NA_INT, f2 = fam ? fam[j] : SNPREL_NA_INT;
+    double v;
+    if (f1 == f2 && f1 != SNPREL_NA_INT)
+        v = 0.5 - (double)sumsq / (2.0 * (double)(n1 + n2));
+    else
+        v = 0.5 - (double)sumsq / (4.0 * (double)min(n1, n2));
+    if (!isfinite(v)) v = nan;
+    store_sym(oibs0, packed, n, i, j, r0);
+    store_sym(okin, packed, n, i, j, v);
+}
+
+// copy counter planes to full symmetric int32 matrices (row = first sample)
+__global__ void counts_sym_kernel(const uint32_t *__restrict__ cnt, int32_t *__restrict__ out,
+                                  int est, int nplanes_out, int64_t n, int64_t npad) {
+    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= n || j < i) return;
+    int64_t plane = npad * npad, k = i * npad + j, nn = n * n;
+    if (est == SNPREL_EST_KING_ROBUST) {
+        uint32_t ibs0 = cnt[k], nloci = cnt[plane + k], het = cnt[2 * plane + k];
+        uint32_t n1 = cnt[3 * plane + k], n2 = cnt[4 * plane + k];
+        uint32_t v[5] = {ibs0, nloci, het + 4u * ibs0, n1, n2};
+        uint32_t vt[5] = {ibs0, nloci, het + 4u * ibs0, n2, n1};   // roles swap below the diagonal
+        for (int p = 0; p < 5; p++) {
+            out[p * nn + i * n + j] = (int32_t)v[p];
+            out[p * nn + j * n + i] = (int32_t)vt[p];
+        }
+    } else {   // beta: ibscnt = het + 2*ibs2, num
+        uint32_t ibscnt = cnt[k] + 2u * cnt[plane + k], num = cnt[2 * plane + k];
+        out[i * n + j] = out[j * n + i] = (int32_t)ibscnt;
+        out[nn + i * n + j] = out[nn + j * n + i] = (int32_t)num;
+    }
+}
+
+// IndivBeta pass 1: raw beta into the upper triangle of a full n x n buffer and the
+// per-row sums / minima of the off-diagonal (diag handled separately)
+__global__ void beta_raw_kernel(const uint32_t *__restrict__ cnt, double *__restrict__ raw,
+                                double *__restrict__ rowsum, double *__restrict__ rowmin,
+                                int diag_inbreeding, int64_t n, int64_t npad) {
+    int64_t i = blockIdx.x;
+    int64_t plane = npad * npad;
+    double s = 0, mn = __longlong_as_double(0x7ff0000000000000ll);
+    for (int64_t j = i + threadIdx.x; j < n; j += blockDim.x) {
+        int64_t k = i * npad + j;
+        double ibscnt = (double)(cnt[k] + 2u * cnt[plane + k]), num = (double)cnt[2 * plane + k];
+        double v;
+        if (j == i) {
+            v = diag_inbreeding ? ibscnt / num - 1 : (0.5 * ibscnt) / num;
+        } else {
+            v = (0.5 * ibscnt) / num;
+            s += v;
+        }
+        mn = fmin(mn, v);   // the GRM flavour takes the minimum over diag + off-diag
+        raw[i * n + j] = v;
+    }
+    __shared__ double ss[256], sm[256];
+    ss[threadIdx.x] = s;
+    sm[threadIdx.x] = mn;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o; o >>= 1) {
+        if (threadIdx.x < o) {
+            ss[threadIdx.x] += ss[threadIdx.x + o];
+            sm[threadIdx.x] = fmin(sm[threadIdx.x], sm[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        rowsum[i] = ss[0];
+        rowmin[i] = sm[0];
+    }
+}
+
+// IndivBeta pass 2: (beta - shift) * scale, GRM flavour diag * 0.5 + 1
+__global__ void beta_final_kernel(const double *__restrict__ raw, double *__restrict__ out,
+                                  int packed, double shift, double scale, int grm_flavour,
+                                  int64_t n) {
+    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= n || j < i) return;
+    double v = (raw[i * n + j] - shift) * scale;
+    if (grm_flavour && i == j) v = v * 0.5 + 1;
+    store_sym(out, packed, n, i, j, v);
+}
+
+static void need_accum(snprel_ctx *c, int est) {
+    if (c->accum_est == est && c->accum_reduced) return;   // reduced across ranks already
+    bitcount_accumulate(c, est);
+}
+
+static dim3 tri_grid(int64_t n) { return dim3((unsigned)n, (unsigned)((n + 127) / 128)); }
+
+static void check_grid_rows(int64_t n) {
+    if (n > 2147483647ll) fail("too many samples for the epilogue grid");
+}
+
+template <class T>
+static void d2h(snprel_ctx *c, T *host, const T *dev, size_t count) {
+    CUDA_CHECK(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+static size_t out_count(int64_t n, int packed) {
+    return packed ? (size_t)n * (n + 1) / 2 : (size_t)n * n;
+}
+
+void ibs_num_finish(snprel_ctx *c, int32_t *i0, int32_t *i1, int32_t *i2) {
+    if (!i0 || !i1 || !i2) fail("snprel_ibs_num: NULL output");
+    need_accum(c, SNPREL_EST_IBS);
+    int64_t n = c->n_samp;
+    check_grid_rows(n);
+    DevBuf<int32_t> o;
+    o.alloc((size_t)3 * n * n);
+    ibs_num_kernel<<<tri_grid(n), 128, 0, c->stream>>>(c->cnt.p, o.p, o.p + n * n, o.p + 2 * n * n,
+                                                       n, c->n_samp_pad);
+    KERNEL_CHECK(c);
+    d2h(c, i0, o.p, (size_t)n * n);
+    d2h(c, i1, o.p + n * n, (size_t)n * n);
+    d2h(c, i2, o.p + 2 * n * n, (size_t)n * n);
+}
+
+void ibs_ave_finish(snprel_ctx *c, double *out, int packed) {
+    if (!out) fail("snprel_ibs_ave: NULL output");
+    need_accum(c, SNPREL_EST_IBS);
+    int64_t n = c->n_samp;
+    check_grid_rows(n);
+    DevBuf<double> o;
+    o.alloc(out_count(n, packed));
+    ibs_ave_kernel<<<tri_grid(n), 128, 0, c->stream>>>(c->cnt.p, o.p, packed, n, c->n_samp_pad);
+    KERNEL_CHECK(c);
+    d2h(c, out, o.p, out_count(n, packed));
+}
+
+void king_robust_finish(snprel_ctx *c, const int32_t *fam, double *ibs0, double *kin, int packed) {
+    if (!ibs0 || !kin) fail("snprel_king_robust: NULL output");
+    need_accum(c, SNPREL_EST_KING_ROBUST);
+    int64_t n = c->n_samp;
+    check_grid_rows(n);
+    DevBuf<int32_t> dfam;
+    if (fam) {
+        dfam.alloc((size_t)n);
+        CUDA_CHECK(cudaMemcpyAsync(dfam.p, fam, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                   c->stream));
+    }
+    DevBuf<double> o;
+    size_t oc = out_count(n, packed);
+    o.alloc(2 * oc);
+    king_robust_kernel<<<tri_grid(n), 128, 0, c->stream>>>(c->cnt.p, fam ? dfam.p : nullptr, o.p,
+                                                           o.p + oc, packed, n, c->n_samp_pad);
+    KERNEL_CHECK(c);
+    d2h(c, ibs0, o.p, oc);
+    d2h(c, kin, o.p + oc, oc);
+}
+
+static void counts_finish(snprel_ctx *c, int est, int np, int32_t *out) {
+    if (!out) fail("NULL output");
+    need_accum(c, est);
+    int64_t n = c->n_samp;
+    check_grid_rows(n);
+    DevBuf<int32_t> o;
+    o.alloc((size_t)np * n * n);
+    counts_sym_kernel<<<tri_grid(n), 128, 0, c->stream>>>(c->cnt.p, o.p, est, np, n, c->n_samp_pad);
+    KERNEL_CHECK(c);
+    d2h(c, out, o.p, (size_t)np * n * n);
+}
+
+void king_robust_counts_finish(snprel_ctx *c, int32_t *out5) {
+    counts_finish(c, SNPREL_EST_KING_ROBUST, 5, out5);
+}
+void beta_counts_finish(snprel_ctx *c, int32_t *out2) { counts_finish(c, SNPREL_EST_BETA, 2, out2); }
+
+// gnrIBD_Beta (src/genBeta.cpp:361-460) when grm_flavour == 0,
+// CalcIndivBetaGRM (src/genBeta.cpp:308-357) when grm_flavour != 0
+void indiv_beta_finish(snprel_ctx *c, int inbreeding, int grm_flavour, double *out, int packed,
+                       double *avg_out) {
+    if (!out) fail("snprel_indiv_beta: NULL output");
+    need_accum(c, SNPREL_EST_BETA);
+    int64_t n = c->n_samp;
+    check_grid_rows(n);
+    DevBuf<double> raw, rs, rm, o;
+    raw.alloc((size_t)n * n);
+    rs.alloc((size_t)n);
+    rm.alloc((size_t)n);
+    beta_raw_kernel<<<(unsigned)n, 256, 0, c->stream>>>(c->cnt.p, raw.p, rs.p, rm.p,
+                                                        grm_flavour ? 1 : inbreeding, n,
+                                                        c->n_samp_pad);
+    KERNEL_CHECK(c);
+    std::vector<double> hs((size_t)n), hm((size_t)n);
+    d2h(c, hs.data(), rs.p, (size_t)n);
+    d2h(c, hm.data(), rm.p, (size_t)n);
+    double avg = 0, mn = hm[0];
+    for (int64_t i = 0; i < n; i++) {
+        avg += hs[i];
+        if (hm[i] < mn) mn = hm[i];
+    }
+    avg /= (double)((long long)n * (n - 1) / 2);
+    if (avg_out) *avg_out = avg;
+    double shift, scale;
+    if (grm_flavour) {
+        shift = mn;
+        scale = 2.0 / (1 - mn);
+    } else {
+        shift = avg;
+        scale = 1.0 / (1 - avg);
+    }
+    o.alloc(out_count(n, packed));
+    beta_final_kernel<<<tri_grid(n), 128, 0, c->stream>>>(raw.p, o.p, packed, shift, scale,
+                                                          grm_flavour, n);
+    KERNEL_CHECK(c);
+    d2h(c, out, o.p, out_count(n, packed));
+}
+
+}  // namespace snprel

@@ -1,0 +1,264 @@
+// extern "C" surface of libsnprel_b200.so (see include/snprel_b200.h).
+// Every entry point catches snprel::Error and returns a code; messages are kept
+// per context (and in a process-wide slot for failures before a context exists).
+#include "common.cuh"
+
+using namespace snprel;
+
+static std::string g_create_error;
+
+#define API_BEGIN(ctx)                                       \
+    if (!(ctx)) {                                            \
+        g_create_error = "NULL snprel_ctx";                  \
+        return 1;                                            \
+    }                                                        \
+    try {                                                    \
+        cudaError_t _se = cudaSetDevice((ctx)->device);      \
+        if (_se != cudaSuccess) fail("cudaSetDevice(%d): %s", (ctx)->device, cudaGetErrorString(_se));
+
+#define API_END(ctx)                                         \
+    return 0;                                                \
+    }                                                        \
+    catch (const Error &e) {                                 \
+        (ctx)->err = e.msg;                                  \
+        return 1;                                            \
+    }                                                        \
+    catch (const std::exception &e) {                        \
+        (ctx)->err = e.what();                               \
+        return 2;                                            \
+    }
+
+extern "C" {
+
+const char *snprel_version(void) { return "snprel_b200 0.1 (sm_100a)"; }
+
+int snprel_create(snprel_ctx **out, int device) {
+    if (!out) {
+        g_create_error = "snprel_create: NULL output pointer";
+        return 1;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        // no CPU fallback: the product path needs a CUDA device
+        g_create_error = std::string("snprel_create: no CUDA device available (") +
+                         (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + ")";
+        return 3;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "snprel_create: device index out of range";
+        return 1;
+    }
+    snprel_ctx *c = new snprel_ctx();
+    c->device = device;
+    try {
+        CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            fail("snprel_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                 prop.major, prop.minor);
+        c->num_sms = prop.multiProcessorCount;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreate(&c->ev0));
+        CUDA_CHECK(cudaEventCreate(&c->ev1));
+    } catch (const Error &err) {
+        g_create_error = err.msg;
+        delete c;
+        return 1;
+    }
+    *out = c;
+    return 0;
+}
+
+void snprel_destroy(snprel_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    cudaStream_t s = c->stream;
+    delete c;   // frees device buffers
+    if (s) cudaStreamDestroy(s);
+}
+
+const char *snprel_last_error(snprel_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int snprel_geno_begin(snprel_ctx *c, int64_t n_samp, int64_t cap) {
+    API_BEGIN(c) geno_begin(c, n_samp, cap);
+    API_END(c)
+}
+int snprel_geno_push_u8(snprel_ctx *c, const uint8_t *geno, int64_t cnt) {
+    API_BEGIN(c) geno_push_u8(c, geno, cnt);
+    API_END(c)
+}
+int snprel_geno_push_2b(snprel_ctx *c, const uint8_t *packed, int64_t cnt, int64_t row_bytes) {
+    API_BEGIN(c) geno_push_2b(c, packed, cnt, row_bytes);
+    API_END(c)
+}
+int snprel_geno_synth(snprel_ctx *c, int64_t n_snp, uint64_t seed, double maf_lo, double maf_hi,
+                      double miss_rate, int64_t snp_start) {
+    API_BEGIN(c) geno_synth(c, n_snp, seed, maf_lo, maf_hi, miss_rate, snp_start);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    API_END(c)
+}
+int snprel_geno_dim(snprel_ctx *c, int64_t *n_samp, int64_t *n_snp) {
+    API_BEGIN(c)
+    if (n_samp) *n_samp = c->n_samp;
+    if (n_snp) *n_snp = c->n_snp;
+    API_END(c)
+}
+int snprel_geno_copy_u8(snprel_ctx *c, uint8_t *out) {
+    API_BEGIN(c) geno_copy_u8(c, out);
+    API_END(c)
+}
+int snprel_snp_ratefreq(snprel_ctx *c, double *af, double *maf, double *mr) {
+    API_BEGIN(c) snp_ratefreq(c, af, maf, mr);
+    API_END(c)
+}
+int snprel_select_snp_base(snprel_ctx *c, int remove_mono, double maf, double missrate,
+                           uint8_t *out_sel, int64_t *n_removed) {
+    API_BEGIN(c) select_snp_base(c, remove_mono, maf, missrate, out_sel, n_removed);
+    API_END(c)
+}
+
+// ---- packed-bit estimators -------------------------------------------------
+int snprel_ibs_num(snprel_ctx *c, int32_t *i0, int32_t *i1, int32_t *i2) {
+    API_BEGIN(c) ibs_num_finish(c, i0, i1, i2);
+    API_END(c)
+}
+int snprel_ibs_ave(snprel_ctx *c, double *out, int packed) {
+    API_BEGIN(c) ibs_ave_finish(c, out, packed);
+    API_END(c)
+}
+int snprel_king_robust(snprel_ctx *c, const int32_t *fam, double *ibs0, double *kin, int packed) {
+    API_BEGIN(c) king_robust_finish(c, fam, ibs0, kin, packed);
+    API_END(c)
+}
+int snprel_king_robust_counts(snprel_ctx *c, int32_t *out5) {
+    API_BEGIN(c) king_robust_counts_finish(c, out5);
+    API_END(c)
+}
+int snprel_king_homo(snprel_ctx *c, double *k0, double *k1, int packed) {
+    API_BEGIN(c) king_homo_finish(c, k0, k1, packed);
+    API_END(c)
+}
+int snprel_indiv_beta(snprel_ctx *c, int inbreeding, double *out, int packed, double *avg_out) {
+    API_BEGIN(c)
+    if (inbreeding != 0 && inbreeding != 1) fail("'inbreeding' must be TRUE or FALSE.");   // src/genBeta.cpp:365-366
+    indiv_beta_finish(c, inbreeding, 0, out, packed, avg_out);
+    API_END(c)
+}
+int snprel_indiv_beta_counts(snprel_ctx *c, int32_t *out2) {
+    API_BEGIN(c) beta_counts_finish(c, out2);
+    API_END(c)
+}
+
+// ---- covariance-type estimators --------------------------------------------
+int snprel_grm(snprel_ctx *c, int method, double *out, int packed, double *avg_out) {
+    API_BEGIN(c)
+    switch (method) {
+        case SNPREL_GRM_EIGENSTRAT:
+        case SNPREL_GRM_GCTA:
+        case SNPREL_GRM_CORR:
+        case SNPREL_GRM_EIGMIX: grm_finish(c, method, out, packed); break;
+        case SNPREL_GRM_INDIVBETA: indiv_beta_finish(c, 1, 1, out, packed, avg_out); break;
+        default: fail("Invalid 'method'!");   // src/genPCA.cpp:1709
+    }
+    API_END(c)
+}
+int snprel_pca(snprel_ctx *c, int eigen_cnt, int bayesian, double *genmat, double *trace_xtx,
+               double *trace_val, double *eigval, double *eigvec) {
+    API_BEGIN(c) pca_finish(c, eigen_cnt, bayesian, genmat, trace_xtx, trace_val, eigval, eigvec);
+    API_END(c)
+}
+int snprel_eigmix(snprel_ctx *c, int eigen_cnt, int diagadj, double *ibd, double *afreq, double *eigval,
+                  double *eigvec) {
+    API_BEGIN(c)
+    if (diagadj != 0 && diagadj != 1) fail("'diagadj' must be TRUE or FALSE.");   // src/genEIGMIX.cpp:661-662
+    eigmix_finish(c, eigen_cnt, diagadj, ibd, afreq, eigval, eigvec);
+    API_END(c)
+}
+
+// ---- split accumulate / reduce / finish -------------------------------------
+static bool is_cov(int est) { return est >= SNPREL_GRM_EIGENSTRAT && est <= SNPREL_GRM_EIGMIX; }
+
+int snprel_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
+    API_BEGIN(c)
+    if (!plan) fail("snprel_plan_local: NULL plan");
+    if (is_cov(est)) {
+        grm_plan_local(c, est == SNPREL_GRM_CORR ? SNPREL_GRM_GCTA : est, plan);
+    } else {
+        plan->max_abs = 0;
+        plan->sum_bound = 0;
+        plan->max_missing = 0;
+        plan->n_snp = c->n_snp;
+    }
+    API_END(c)
+}
+int snprel_accumulate(snprel_ctx *c, int est, const snprel_plan *plan) {
+    API_BEGIN(c)
+    if (is_cov(est)) {
+        if (!plan) fail("snprel_accumulate: covariance estimators need a plan");
+        grm_accumulate(c, est, plan);
+    } else if (est == SNPREL_EST_IBS || est == SNPREL_EST_KING_ROBUST || est == SNPREL_EST_BETA) {
+        bitcount_accumulate(c, est);
+    } else {
+        fail("snprel_accumulate: unsupported estimator %d", est);
+    }
+    API_END(c)
+}
+int snprel_reduce_buffer_count(snprel_ctx *c) { return c ? (int)c->reduce_list.size() : 0; }
+int snprel_reduce_buffer(snprel_ctx *c, int idx, void **dev_ptr, int64_t *count, int *kind) {
+    API_BEGIN(c)
+    if (idx < 0 || idx >= (int)c->reduce_list.size()) fail("snprel_reduce_buffer: index out of range");
+    if (dev_ptr) *dev_ptr = c->reduce_list[idx].ptr;
+    if (count) *count = c->reduce_list[idx].count;
+    if (kind) *kind = c->reduce_list[idx].kind;
+    API_END(c)
+}
+int snprel_mark_reduced(snprel_ctx *c) {
+    API_BEGIN(c)
+    if (c->accum_est < 0) fail("snprel_mark_reduced: nothing accumulated");
+    c->accum_reduced = true;
+    API_END(c)
+}
+
+// ---- introspection -----------------------------------------------------------
+int64_t snprel_kernel_launches(snprel_ctx *c) { return c ? c->launches : 0; }
+int snprel_last_hot_kernel(snprel_ctx *c, double *ms, int64_t *launches, double *units) {
+    API_BEGIN(c)
+    if (ms) *ms = c->hot_ms;
+    if (launches) *launches = c->hot_launches;
+    if (units) *units = c->hot_units;
+    API_END(c)
+}
+int snprel_time_accumulate(snprel_ctx *c, int est, int reps, double *ms) {
+    API_BEGIN(c)
+    if (reps <= 0) fail("snprel_time_accumulate: reps must be positive");
+    double total = 0;
+    for (int r = 0; r < reps; r++) {
+        if (is_cov(est)) {
+            snprel_plan plan{};
+            plan.frac_bits = -1;
+            grm_plan_local(c, est == SNPREL_GRM_CORR ? SNPREL_GRM_GCTA : est, &plan);
+            grm_accumulate(c, est, &plan);
+        } else {
+            bitcount_accumulate(c, est);
+        }
+        total += c->hot_ms;
+    }
+    if (ms) *ms = total / reps;
+    API_END(c)
+}
+int snprel_table_gram(snprel_ctx *c, const int8_t *tabA, const int8_t *tabB, int64_t *out) {
+    API_BEGIN(c) table_gram_debug(c, tabA, tabB, out);
+    API_END(c)
+}
+int snprel_debug_flags(snprel_ctx *c, uint32_t flags) {
+    API_BEGIN(c) c->debug_flags = flags;
+    API_END(c)
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+// Internal definitions shared by the translation units of libsnprel_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/snprel_b200.h"
+
+namespace snprel {
+
+// ---------------------------------------------------------------------------
+// errors: never throw across the C ABI
+// ---------------------------------------------------------------------------
+struct Error {
+    std::string msg;
+};
+
+[[noreturn]] inline void fail(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    throw Error{buf};
+}
+
+#define CUDA_CHECK(expr)                                                        \
+    do {                                                                        \
+        cudaError_t _e = (expr);                                                \
+        if (_e != cudaSuccess)                                                  \
+            ::snprel::fail("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e),  \
+                           __FILE__, __LINE__, cudaGetErrorString(_e));         \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// device buffer (RAII over cudaMalloc) -- the allocator of this library
+// ---------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count) {
+        if (count <= n && p) return;
+        release();
+        if (count == 0) return;
+        CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+        n = count;
+    }
+    void zero(cudaStream_t s) {
+        if (p) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// ---------------------------------------------------------------------------
+// geometry of the 2-bit workspace
+// ---------------------------------------------------------------------------
+constexpr int SAMP_PAD = 256;   // samples per row are padded to a multiple of this
+constexpr int SNP_PAD = 128;    // SNP rows are padded (all-missing) to a multiple of this
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// per-SNP statistics produced by the stats kernel
+struct SnpStat {
+    int32_t sum;   // sum of genotypes over non-missing samples
+    int32_t num;   // number of non-missing samples
+    int32_t n1;    // heterozygotes
+    int32_t pad;
+};
+
+struct ReduceBuf {
+    void *ptr;
+    int64_t count;
+    int kind;   // 0 int64, 1 uint32, 2 float64
+};
+
+}  // namespace snprel
+
+// ---------------------------------------------------------------------------
+// the context
+// ---------------------------------------------------------------------------
+struct snprel_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    uint32_t debug_flags = 0;
+    int num_sms = 148;
+
+    // workspace
+    int64_t n_samp = 0;        // N
+    int64_t n_samp_pad = 0;    // N rounded up to SAMP_PAD
+    int64_t row_bytes = 0;     // n_samp_pad / 4
+    int64_t snp_cap = 0;       // allocated SNP rows (multiple of SNP_PAD)
+    int64_t n_snp = 0;         // valid SNP rows
+    snprel::DevBuf<uint8_t> geno2b;       // [snp_cap][row_bytes]
+    snprel::DevBuf<snprel::SnpStat> stat; // [snp_cap]
+    bool stat_valid = false;
+    snprel::DevBuf<uint8_t> stage_u8;     // host->device staging for push_u8
+
+    // bit planes for the packed-bit estimators: [n_word64][n_samp_pad] uint4
+    snprel::DevBuf<uint4> planes;
+    int64_t plane_words = 0;
+    bool planes_valid = false;
+
+    // accumulators
+    int accum_est = -1;          // estimator the accumulators belong to
+    bool accum_reduced = false;  // true after snprel_mark_reduced
+    snprel::DevBuf<uint32_t> cnt;         // packed-bit counters [ncnt][npad][npad]
+    int cnt_planes = 0;
+    snprel::DevBuf<double> cnt_f64;       // KING-homo f64 pair sums [2][npad][npad]
+    snprel::DevBuf<long long> acc;        // fixed-point Gram planes [nplane][npad][npad]
+    int acc_planes = 0;
+    snprel::DevBuf<long long> samp_sum;   // per-sample fixed-point sums [nvec][npad]
+    int samp_vecs = 0;
+    snprel::DevBuf<double> scalars;       // global f64 scalars (SumDenominator, ...)
+    snprel::DevBuf<long long> iscalars;   // global int64 scalars (nLocus, ...)
+    snprel_plan plan{};
+    std::vector<snprel::ReduceBuf> reduce_list;
+
+    // hot-kernel bookkeeping for bench.py
+    double hot_ms = 0;
+    int64_t hot_launches = 0;
+    double hot_units = 0;
+};
+
+namespace snprel {
+
+inline void count_launch(snprel_ctx *c, int64_t n = 1) { c->launches += n; }
+
+#define KERNEL_CHECK(ctx)                                   \
+    do {                                                    \
+        CUDA_CHECK(cudaGetLastError());                     \
+        ::snprel::count_launch(ctx);                        \
+    } while (0)
+
+// geno.cu
+void geno_begin(snprel_ctx *c, int64_t n_samp, int64_t cap);
+void geno_push_u8(snprel_ctx *c, const uint8_t *host, int64_t cnt);
+void geno_push_2b(snprel_ctx *c, const uint8_t *host, int64_t cnt, int64_t row_bytes);
+void geno_synth(snprel_ctx *c, int64_t n_snp, uint64_t seed, double maf_lo, double maf_hi,
+                double miss_rate, int64_t snp_start);
+void geno_copy_u8(snprel_ctx *c, uint8_t *out);
+void geno_pad_tail(snprel_ctx *c);
+void ensure_stats(snprel_ctx *c);
+void snp_ratefreq(snprel_ctx *c, double *af, double *maf, double *mr);
+void select_snp_base(snprel_ctx *c, int remove_mono, double maf, double missrate,
+                     uint8_t *out_sel, int64_t *n_removed);
+void ensure_planes(snprel_ctx *c);
+
+// bitcount.cu
+void bitcount_accumulate(snprel_ctx *c, int estimator);
+void ibs_num_finish(snprel_ctx *c, int32_t *i0, int32_t *i1, int32_t *i2);
+void ibs_ave_finish(snprel_ctx *c, double *out, int packed);
+void king_robust_finish(snprel_ctx *c, const int32_t *fam, double *ibs0, double *kin, int packed);
+void king_robust_counts_finish(snprel_ctx *c, int32_t *out5);
+void beta_counts_finish(snprel_ctx *c, int32_t *out2);
+void indiv_beta_finish(snprel_ctx *c, int inbreeding, int grm_flavour, double *out, int packed,
+                       double *avg_out);
+
+// gram_tc.cu
+struct GramPass {
+    const uint32_t *tabA;   // device [snp_cap] : 4 int8 digits per SNP (byte g = genotype code g)
+    uint32_t tabB;          // 4 int8 values (byte g = genotype code g)
+    int plane;              // output plane
+    int shift;              // contribution = acc << shift
+};
+void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *out_planes,
+                 bool upper_only);
+
+// grm.cu
+void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan);
+void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan);
+void grm_finish(snprel_ctx *c, int method, double *out, int packed);
+void pca_finish(snprel_ctx *c, int eigen_cnt, int bayesian, double *genmat, double *trace_xtx,
+                double *trace_val, double *eigval, double *eigvec);
+void eigmix_finish(snprel_ctx *c, int eigen_cnt, int diagadj, double *ibd, double *afreq,
+                   double *eigval, double *eigvec);
+void king_homo_finish(snprel_ctx *c, double *k0, double *k1, int packed);
+void table_gram_debug(snprel_ctx *c, const int8_t *tabA, const int8_t *tabB, int64_t *out);
+
+}  // namespace snprel

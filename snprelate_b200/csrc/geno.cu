@@ -1,0 +1,434 @@
+// Genotype workspace on the device: the B200 counterpart of the reference's
+// CdBaseWorkSpace / CGenoReadBySNP / PackSNPGeno1b layer
+// (src/dGenGWAS.h:80-150,295-355; src/dGenGWAS.cpp:361-397,472-552,1218-1475).
+//
+// HBM layout: 2-bit genotypes (GDS dBit2 code: 0/1/2 = #A alleles, 3 = missing),
+// SNP-major, sample fastest, 4 genotypes per byte LSB first, every SNP row padded
+// with missing codes to a multiple of 256 samples; SNP rows padded with
+// all-missing rows to a multiple of 128.  N*M/4 bytes -- a 10k x 1M data set is
+// 2.5 GB, 500k x 800k is 100 GB (fits one 180 GB B200).
+#include "common.cuh"
+
+namespace snprel {
+
+// ---------------------------------------------------------------------------
+// pack: uint8 [cnt][n_samp] -> 2-bit rows
+// ---------------------------------------------------------------------------
+__global__ void pack_u8_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                               int64_t cnt, int64_t n_samp, int64_t row_bytes) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = cnt * row_bytes;
+    if (idx >= total) return;
+    int64_t r = idx / row_bytes, b = idx - r * row_bytes;
+    const uint8_t *s = src + r * n_samp + b * 4;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int64_t i = b * 4 + k;
+        uint32_t g = 3;
+        if (i < n_samp) {
+            g = s[k];
+            if (g > 2) g = 3;   // vec_u8_geno_valid: anything > 2 is missing (src/dVect.cpp:121-144)
+        }
+        out |= g << (2 * k);
+    }
+    dst[idx] = (uint8_t)out;
+}
+
+// repack host 2-bit rows (row_bytes_in per SNP) into padded device rows
+__global__ void repack_2b_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                 int64_t cnt, int64_t n_samp, int64_t row_bytes_in,
+                                 int64_t row_bytes) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = cnt * row_bytes;
+    if (idx >= total) return;
+    int64_t r = idx / row_bytes, b = idx - r * row_bytes;
+    uint32_t v = 0xFF;
+    if (b * 4 < n_samp) {
+        v = src[r * row_bytes_in + b];
+        int64_t rem = n_samp - b * 4;   // valid genotypes in this byte
+        if (rem < 4) v |= (0xFFu << (2 * rem)) & 0xFF;
+    }
+    dst[idx] = (uint8_t)v;
+}
+
+__global__ void unpack_u8_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                 int64_t cnt, int64_t n_samp, int64_t row_bytes) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cnt * n_samp) return;
+    int64_t r = idx / n_samp, i = idx - r * n_samp;
+    dst[idx] = (src[r * row_bytes + (i >> 2)] >> (2 * (i & 3))) & 3;
+}
+
+// ---------------------------------------------------------------------------
+// synthetic generator (bit-identical to oracle/snprel_oracle.py:synth_geno)
+// ---------------------------------------------------------------------------
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void synth_kernel(uint8_t *__restrict__ dst, int64_t n_snp, int64_t n_samp,
+                             int64_t row_bytes, uint64_t seed, double maf_lo, double maf_hi,
+                             uint32_t thm, int64_t snp_start) {
+    // one thread per output byte (4 samples); grid.y = SNP row
+    int64_t r = blockIdx.y;
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_snp || b >= row_bytes) return;
+    uint64_t l = (uint64_t)(r + snp_start);
+    uint64_t hp = splitmix64(seed ^ (l * 0xD1342543DE82EF95ull));
+    double u = __dmul_rn((double)(hp >> 11), 1.0 / 9007199254740992.0);
+    double p = __dadd_rn(maf_lo, __dmul_rn(__dsub_rn(maf_hi, maf_lo), u));
+    double q = __dsub_rn(1.0, p);
+    double t0 = __dmul_rn(q, q);
+    double t1 = __dadd_rn(t0, __dmul_rn(__dmul_rn(2.0, p), q));
+    double f0 = fmin(floor(__dmul_rn(t0, 4294967296.0)), 4294967295.0);
+    double f1 = fmin(floor(__dmul_rn(t1, 4294967296.0)), 4294967295.0);
+    uint32_t th0 = (uint32_t)f0, th1 = (uint32_t)f1;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int64_t i = b * 4 + k;
+        uint32_t g = 3;
+        if (i < n_samp) {
+            uint64_t key = splitmix64(hp + (uint64_t)i * 0x9E3779B97F4A7C15ull);
+            uint32_t rr = (uint32_t)(key >> 32), rm = (uint32_t)key;
+            g = (rr >= th0) + (rr >= th1);
+            if (rm < thm) g = 3;
+        }
+        out |= g << (2 * k);
+    }
+    dst[r * row_bytes + b] = (uint8_t)out;
+}
+
+// ---------------------------------------------------------------------------
+// per-SNP statistics: vec_u8_geno_count (src/dVect.cpp:30-117) on packed rows.
+// One warp per SNP row, uint4 loads (64 samples per lane per step).
+// ---------------------------------------------------------------------------
+__global__ void snp_stat_kernel(const uint8_t *__restrict__ g, SnpStat *__restrict__ st,
+                                int64_t n_rows, int64_t row_bytes, int n_samp_pad) {
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    int lane = threadIdx.x & 31;
+    const uint4 *p = reinterpret_cast<const uint4 *>(g + row * row_bytes);
+    int nq = (int)(row_bytes >> 4);
+    int nmiss = 0, n1 = 0, n2 = 0;
+    for (int q = lane; q < nq; q += 32) {
+        uint4 v = __ldg(p + q);
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t lo = w[k] & 0x55555555u, hi = (w[k] >> 1) & 0x55555555u;
+            nmiss += __popc(lo & hi);
+            n1 += __popc(lo & ~hi);
+            n2 += __popc(hi & ~lo);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        nmiss += __shfl_xor_sync(0xffffffffu, nmiss, o);
+        n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    }
+    if (lane == 0) {
+        SnpStat s;
+        s.sum = n1 + 2 * n2;
+        s.num = n_samp_pad - nmiss;
+        s.n1 = n1;
+        s.pad = 0;
+        st[row] = s;
+    }
+}
+
+// gather SNP rows (compaction after gnrSelSNP_Base)
+__global__ void gather_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                   const int64_t *__restrict__ idx, int64_t n_out,
+                                   int64_t row_bytes) {
+    int64_t r = blockIdx.y;
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_out || q >= (row_bytes >> 4)) return;
+    const uint4 *s = reinterpret_cast<const uint4 *>(src + idx[r] * row_bytes);
+    uint4 *d = reinterpret_cast<uint4 *>(dst + r * row_bytes);
+    d[q] = s[q];
+}
+
+// ---------------------------------------------------------------------------
+// 2-bit -> bit planes: the device PackSNPGeno1b (src/dGenGWAS.cpp:1429-1475).
+// Encoding 0->(0,0) 1->(1,0) 2->(1,1) NA->(0,1) as (plane1, plane2); padding SNPs
+// are all-missing rows, i.e. (0,1) as the reference requires (:1467-1472).
+// Output [word64][sample] of uint4 {p1.lo, p1.hi, p2.lo, p2.hi}: the pair kernel
+// reads one coalesced uint4 per (sample, 64-SNP word).
+// ---------------------------------------------------------------------------
+__global__ void planes_kernel(const uint8_t *__restrict__ g, uint4 *__restrict__ planes,
+                              int64_t n_words, int64_t row_bytes, int64_t n_samp_pad) {
+    int64_t w = blockIdx.y;
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // byte column = 4 samples
+    if (w >= n_words || b >= row_bytes) return;
+    unsigned long long p1[4] = {0, 0, 0, 0}, p2[4] = {0, 0, 0, 0};
+    const uint8_t *src = g + (w * 64) * row_bytes + b;
+#pragma unroll 8
+    for (int s = 0; s < 64; s++) {
+        uint32_t v = src[(int64_t)s * row_bytes];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t code = (v >> (2 * k)) & 3;
+            unsigned long long lo = code & 1, hi = code >> 1;
+            p1[k] |= (lo ^ hi) << s;
+            p2[k] |= hi << s;
+        }
+    }
+    uint4 *dst = planes + w * n_samp_pad + b * 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        dst[k] = make_uint4((uint32_t)p1[k], (uint32_t)(p1[k] >> 32), (uint32_t)p2[k],
+                            (uint32_t)(p2[k] >> 32));
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+void geno_begin(snprel_ctx *c, int64_t n_samp, int64_t cap) {
+    if (n_samp <= 0) fail("snprel_geno_begin: n_samp must be positive");
+    if (cap < 0) fail("snprel_geno_begin: negative SNP capacity");
+    if (n_samp >= (1ll << 30)) fail("snprel_geno_begin: too many samples");
+    c->n_samp = n_samp;
+    c->n_samp_pad = round_up(n_samp, SAMP_PAD);
+    c->row_bytes = c->n_samp_pad / 4;
+    c->snp_cap = round_up(cap > 0 ? cap : 1, SNP_PAD);
+    c->n_snp = 0;
+    c->geno2b.release();
+    c->geno2b.alloc((size_t)c->snp_cap * c->row_bytes);
+    c->stat.alloc(c->snp_cap);
+    c->stat_valid = false;
+    c->planes_valid = false;
+    c->accum_est = -1;
+    c->accum_reduced = false;
+}
+
+static void need_room(snprel_ctx *c, int64_t cnt, const char *who) {
+    if (c->n_samp <= 0) fail("%s: no genotype workspace (call snprel_geno_begin first)", who);
+    if (cnt < 0) fail("%s: negative SNP count", who);
+    if (c->n_snp + cnt > c->snp_cap)
+        fail("%s: SNP capacity exceeded (%lld + %lld > %lld)", who, (long long)c->n_snp,
+             (long long)cnt, (long long)c->snp_cap);
+}
+
+static void invalidate(snprel_ctx *c) {
+    c->stat_valid = false;
+    c->planes_valid = false;
+    c->accum_est = -1;
+    c->accum_reduced = false;
+}
+
+void geno_push_u8(snprel_ctx *c, const uint8_t *host, int64_t cnt) {
+    need_room(c, cnt, "snprel_geno_push_u8");
+    if (cnt == 0) return;
+    if (!host) fail("snprel_geno_push_u8: NULL block");
+    // stream the block through a bounded staging buffer so host pages are touched once
+    const int64_t max_rows = std::max<int64_t>(1, (int64_t)(256ll << 20) / c->n_samp);
+    c->stage_u8.alloc((size_t)std::min(cnt, max_rows) * c->n_samp);
+    for (int64_t done = 0; done < cnt; done += max_rows) {
+        int64_t rows = std::min(max_rows, cnt - done);
+        CUDA_CHECK(cudaMemcpyAsync(c->stage_u8.p, host + done * c->n_samp, (size_t)rows * c->n_samp,
+                                   cudaMemcpyHostToDevice, c->stream));
+        int64_t total = rows * c->row_bytes;
+        pack_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(
+            c->stage_u8.p, c->geno2b.p + (c->n_snp + done) * c->row_bytes, rows, c->n_samp,
+            c->row_bytes);
+        KERNEL_CHECK(c);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));   // staging buffer is reused
+    }
+    c->n_snp += cnt;
+    invalidate(c);
+}
+
+void geno_push_2b(snprel_ctx *c, const uint8_t *host, int64_t cnt, int64_t row_bytes_in) {
+    need_room(c, cnt, "snprel_geno_push_2b");
+    if (cnt == 0) return;
+    if (!host) fail("snprel_geno_push_2b: NULL block");
+    if (row_bytes_in < (c->n_samp + 3) / 4)
+        fail("snprel_geno_push_2b: row_bytes %lld too small for %lld samples",
+             (long long)row_bytes_in, (long long)c->n_samp);
+    uint8_t *dst = c->geno2b.p + c->n_snp * c->row_bytes;
+    if (row_bytes_in == c->row_bytes && (c->n_samp % 4) == 0 && c->n_samp == c->n_samp_pad) {
+        CUDA_CHECK(cudaMemcpyAsync(dst, host, (size_t)cnt * row_bytes_in, cudaMemcpyHostToDevice,
+                                   c->stream));
+    } else {
+        const int64_t max_rows = std::max<int64_t>(1, (int64_t)(256ll << 20) / row_bytes_in);
+        c->stage_u8.alloc((size_t)std::min(cnt, max_rows) * row_bytes_in);
+        for (int64_t done = 0; done < cnt; done += max_rows) {
+            int64_t rows = std::min(max_rows, cnt - done);
+            CUDA_CHECK(cudaMemcpyAsync(c->stage_u8.p, host + done * row_bytes_in,
+                                       (size_t)rows * row_bytes_in, cudaMemcpyHostToDevice,
+                                       c->stream));
+            int64_t total = rows * c->row_bytes;
+            repack_2b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(
+                c->stage_u8.p, dst + done * c->row_bytes, rows, c->n_samp, row_bytes_in,
+                c->row_bytes);
+            KERNEL_CHECK(c);
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        }
+    }
+    c->n_snp += cnt;
+    invalidate(c);
+}
+
+void geno_synth(snprel_ctx *c, int64_t n_snp, uint64_t seed, double maf_lo, double maf_hi,
+                double miss_rate, int64_t snp_start) {
+    need_room(c, n_snp, "snprel_geno_synth");
+    if (n_snp == 0) return;
+    if (!(maf_lo > 0 && maf_hi <= 1.0 && maf_lo <= maf_hi)) fail("snprel_geno_synth: bad MAF range");
+    if (!(miss_rate >= 0 && miss_rate < 1)) fail("snprel_geno_synth: bad missing rate");
+    double t = miss_rate * 4294967296.0;
+    uint32_t thm = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    dim3 grid((unsigned)((c->row_bytes + 255) / 256), 1);
+    // grid.y is limited to 65535: loop in slabs
+    for (int64_t r0 = 0; r0 < n_snp; r0 += 65535) {
+        int64_t rows = std::min<int64_t>(65535, n_snp - r0);
+        grid.y = (unsigned)rows;
+        synth_kernel<<<grid, 256, 0, c->stream>>>(c->geno2b.p + (c->n_snp + r0) * c->row_bytes,
+                                                  rows, c->n_samp, c->row_bytes, seed, maf_lo,
+                                                  maf_hi, thm, snp_start + r0);
+        KERNEL_CHECK(c);
+    }
+    c->n_snp += n_snp;
+    invalidate(c);
+}
+
+// rows [n_snp, round_up(n_snp, SNP_PAD)) must read as all-missing
+void geno_pad_tail(snprel_ctx *c) {
+    int64_t end = round_up(std::max<int64_t>(c->n_snp, 1), SNP_PAD);
+    if (end > c->snp_cap) fail("internal: SNP padding exceeds capacity");
+    if (end > c->n_snp)
+        CUDA_CHECK(cudaMemsetAsync(c->geno2b.p + c->n_snp * c->row_bytes, 0xFF,
+                                   (size_t)(end - c->n_snp) * c->row_bytes, c->stream));
+}
+
+void geno_copy_u8(snprel_ctx *c, uint8_t *out) {
+    if (c->n_samp <= 0) fail("snprel_geno_copy_u8: no genotype workspace");
+    if (!out) fail("snprel_geno_copy_u8: NULL output");
+    const int64_t max_rows = std::max<int64_t>(1, (int64_t)(256ll << 20) / c->n_samp);
+    c->stage_u8.alloc((size_t)std::min(std::max<int64_t>(c->n_snp, 1), max_rows) * c->n_samp);
+    for (int64_t done = 0; done < c->n_snp; done += max_rows) {
+        int64_t rows = std::min(max_rows, c->n_snp - done);
+        int64_t total = rows * c->n_samp;
+        unpack_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(
+            c->geno2b.p + done * c->row_bytes, c->stage_u8.p, rows, c->n_samp, c->row_bytes);
+        KERNEL_CHECK(c);
+        CUDA_CHECK(cudaMemcpyAsync(out + done * c->n_samp, c->stage_u8.p, (size_t)total,
+                                   cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+}
+
+void ensure_stats(snprel_ctx *c) {
+    if (c->n_samp <= 0) fail("no genotype workspace (call snprel_geno_begin first)");
+    if (c->stat_valid) return;
+    geno_pad_tail(c);
+    int64_t rows = round_up(std::max<int64_t>(c->n_snp, 1), SNP_PAD);
+    const int warps = 8;
+    snp_stat_kernel<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, c->stream>>>(
+        c->geno2b.p, c->stat.p, rows, c->row_bytes, (int)c->n_samp_pad);
+    KERNEL_CHECK(c);
+    c->stat_valid = true;
+}
+
+static std::vector<SnpStat> stats_to_host(snprel_ctx *c) {
+    ensure_stats(c);
+    std::vector<SnpStat> h((size_t)c->n_snp);
+    if (c->n_snp > 0)
+        CUDA_CHECK(cudaMemcpyAsync(h.data(), c->stat.p, h.size() * sizeof(SnpStat),
+                                   cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    // padding samples were counted as missing against n_samp_pad; num is exact already
+    return h;
+}
+
+// Get_AF_MR_perSNP, SNP-major branch (src/dGenGWAS.cpp:535-551)
+void snp_ratefreq(snprel_ctx *c, double *af, double *maf, double *mr) {
+    std::vector<SnpStat> h = stats_to_host(c);
+    const double nan = __builtin_nan("");
+    for (int64_t l = 0; l < c->n_snp; l++) {
+        int num = h[l].num, sum = h[l].sum;
+        double f = num > 0 ? (double)sum / (2 * num) : nan;
+        if (af) af[l] = f;
+        if (maf) maf[l] = f < 1 - f ? f : (1 - f == 1 - f ? 1 - f : nan);
+        if (mr) mr[l] = 1 - ((double)num) / (double)c->n_samp;
+    }
+}
+
+// Select_SNP_Base (src/dGenGWAS.cpp:361-397)
+void select_snp_base(snprel_ctx *c, int remove_mono, double maf, double missrate,
+                     uint8_t *out_sel, int64_t *n_removed) {
+    std::vector<SnpStat> h = stats_to_host(c);
+    std::vector<int64_t> keep;
+    keep.reserve((size_t)c->n_snp);
+    for (int64_t l = 0; l < c->n_snp; l++) {
+        int num = h[l].num, sum = h[l].sum;
+        bool flag = false;
+        if (num > 0) {
+            double f = (double)sum / (2 * num);
+            double m = f < 1 - f ? f : 1 - f;
+            double r = 1 - ((double)num) / (double)c->n_samp;
+            flag = true;
+            if (remove_mono && m <= 0) flag = false;
+            if (flag && m < maf) flag = false;
+            if (flag && r > missrate) flag = false;
+        }
+        if (out_sel) out_sel[l] = flag ? 1 : 0;
+        if (flag) keep.push_back(l);
+    }
+    int64_t removed = c->n_snp - (int64_t)keep.size();
+    if (n_removed) *n_removed = removed;
+    if (removed == 0) return;
+    // compact rows into a fresh buffer
+    int64_t n_out = (int64_t)keep.size();
+    int64_t cap = round_up(std::max<int64_t>(n_out, 1), SNP_PAD);
+    DevBuf<uint8_t> fresh;
+    fresh.alloc((size_t)cap * c->row_bytes);
+    if (n_out > 0) {
+        DevBuf<int64_t> idx;
+        idx.alloc(keep.size());
+        CUDA_CHECK(cudaMemcpyAsync(idx.p, keep.data(), keep.size() * sizeof(int64_t),
+                                   cudaMemcpyHostToDevice, c->stream));
+        dim3 grid((unsigned)(((c->row_bytes >> 4) + 127) / 128), 1);
+        for (int64_t r0 = 0; r0 < n_out; r0 += 65535) {
+            int64_t rows = std::min<int64_t>(65535, n_out - r0);
+            grid.y = (unsigned)rows;
+            gather_rows_kernel<<<grid, 128, 0, c->stream>>>(
+                c->geno2b.p, fresh.p + r0 * c->row_bytes, idx.p + r0, rows, c->row_bytes);
+            KERNEL_CHECK(c);
+        }
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    std::swap(c->geno2b.p, fresh.p);
+    std::swap(c->geno2b.n, fresh.n);
+    c->snp_cap = cap;
+    c->n_snp = n_out;
+    c->stat.alloc(cap);
+    invalidate(c);
+}
+
+void ensure_planes(snprel_ctx *c) {
+    if (c->n_samp <= 0) fail("no genotype workspace (call snprel_geno_begin first)");
+    if (c->planes_valid) return;
+    geno_pad_tail(c);
+    int64_t words = round_up(std::max<int64_t>(c->n_snp, 1), SNP_PAD) / 64;
+    c->planes.alloc((size_t)words * c->n_samp_pad);
+    c->plane_words = words;
+    dim3 grid((unsigned)((c->row_bytes + 127) / 128), 1);
+    for (int64_t w0 = 0; w0 < words; w0 += 65535) {
+        int64_t nw = std::min<int64_t>(65535, words - w0);
+        grid.y = (unsigned)nw;
+        planes_kernel<<<grid, 128, 0, c->stream>>>(c->geno2b.p + w0 * 64 * c->row_bytes,
+                                                   c->planes.p + w0 * c->n_samp_pad, nw,
+                                                   c->row_bytes, c->n_samp_pad);
+        KERNEL_CHECK(c);
+    }
+    c->planes_valid = true;
+}
+
+}  // namespace snprel

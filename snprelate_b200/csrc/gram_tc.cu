@@ -1,0 +1,463 @@
+// K1: the tcgen05 "table Gram" -- the tensor-core hot loop that replaces
+// CProdMat_AlgArith::MulAdd (src/genPCA.cpp:229-312) together with its block
+// preparation (TransposeGenotype / GenoSub / GenoMul, src/genPCA.h:93-108,
+// src/genPCA.cpp:315-368) and the missing-pair denominator loops
+// (src/genPCA.cpp:1201-1224, src/genEIGMIX.cpp:113-138).
+//
+// It computes, for up to two "passes" p that share one B table,
+//
+//     Acc_p[i][j] = sum over SNPs l of  tabA_p[l][g_il] * tabB[g_jl]      (exact, int32)
+//
+// where g is the 2-bit genotype code, tabA_p[l] is a per-SNP table of four int8
+// digits and tabB a table of four small int8 values, and adds Acc_p << shift_p into
+// an int64 fixed-point output plane with 64-bit atomics.  The per-SNP real weights
+// (1/(p(1-p)), 2p, 4p(1-p) ...) live in the digits of tabA: grm.cu slices each
+// table value into balanced base-256 digits, one pass per digit, so the sum over
+// passes reproduces the float64 result to a proven bound while every tensor-core
+// product and every accumulation is exact integer arithmetic (order independent,
+// hence bit-identical for any tiling, split or GPU count).
+//
+// Mapping onto sm_100a:
+//   * one CTA per (128 x 256 sample tile, SNP split); 9 warps.
+//   * warps 1..8 are producers: each thread reads 64 packed genotypes of one SNP
+//     with one 16-byte load, turns every 32-bit word (16 samples) into byte-permute
+//     selectors (3 logic ops + 2 shifts) and emits int8 operand rows with PRMT
+//     against the 4-entry tables -- the "unpack, centre and scale on the fly" step.
+//     Operands are written MN-major (16 consecutive samples = one 16-byte core row),
+//     the layout in which a packed genotype word expands without any transpose.
+//   * warp 0 issues tcgen05.mma.kind::i8 (M=128, N=256, K=32) from shared-memory
+//     descriptors into two 128x256 int32 accumulators that fill the 512 TMEM columns;
+//     tcgen05.commit releases pipeline stages back to the producers through mbarriers.
+//   * after the last SNP stage the producer warps become the epilogue: tcgen05.ld the
+//     accumulators and issue the 64-bit atomics.
+#include "common.cuh"
+
+namespace snprel {
+namespace tc {
+
+constexpr int TM = 128;            // A rows (samples) per tile
+constexpr int TN = 256;            // B rows (samples) per tile
+constexpr int SK = 128;            // SNPs per pipeline stage
+constexpr int MMA_K = 32;          // SNPs per tcgen05.mma (int8)
+constexpr int NSTAGE = 3;
+constexpr int MAXP = 2;            // passes per launch = TMEM accumulators
+constexpr int PROD_WARPS = 8;
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int THREADS = 32 + PROD_THREADS;
+constexpr int A_BYTES = TM * SK;   // one pass, one stage (16 KB)
+constexpr int B_BYTES = TN * SK;   // one stage (32 KB)
+constexpr int STAGE_BYTES = MAXP * A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024;
+constexpr int A_LBO = (TM / 16) * 128;   // byte stride between 8-SNP groups (K direction)
+constexpr int B_LBO = (TN / 16) * 128;
+constexpr int CORE_SBO = 128;            // byte stride between 16-sample cores (MN direction)
+constexpr uint32_t TMEM_COLS = 512;
+
+struct Params {
+    const uint8_t *geno;
+    long long row_bytes;
+    const uint32_t *tabA[MAXP];
+    uint32_t tabB;
+    int npass;
+    int plane[MAXP];
+    int shift[MAXP];
+    long long *out;
+    long long ld;            // leading dimension of an output plane (n_samp_pad)
+    long long plane_stride;  // elements per plane
+    long long n_samp;
+    const int2 *tiles;       // (tile_m, tile_n) work list
+    int stages_total;
+    int stages_per_split;
+    int upper_only;
+    uint32_t flags;          // bit0: swap LBO/SBO in the descriptors (bring-up probe)
+    int *error_flag;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must surface as an error, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *error_flag, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {   // ~2 s at 2 GHz
+            if (error_flag) atomicExch(error_flag, code);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                        uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+          "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+          "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c),
+                 "r"(d)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ld_nc_v4(const uint8_t *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// shared-memory matrix descriptor, MN-major, no swizzle (SWIZZLE_NONE / "interleave"):
+// core matrix = 8 K-rows x 16 bytes (16 consecutive samples), 128 contiguous bytes.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);   // bits 46-47: version 1 (sm_100)
+}
+
+// instruction descriptor for kind::i8: D=s32, A=s8, B=s8, both MN-major, M=128, N=256
+__device__ __forceinline__ uint32_t make_idesc() {
+    return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TN >> 3) << 17) |
+           ((uint32_t)(TM >> 4) << 24);
+}
+
+// position inside a 16-sample core row -> sample offset (the producer emits even
+// samples first: bytes [0,2,4,6 | 1,3,5,7 | 8,10,12,14 | 9,11,13,15])
+__device__ __forceinline__ int core_pos_to_sample(int pos) {
+    int grp = pos >> 2;
+    return ((grp >> 1) << 3) + (grp & 1) + ((pos & 3) << 1);
+}
+
+// expand one packed word (16 genotypes) against `np` tables and store the rows
+template <int NP>
+__device__ __forceinline__ void expand_word(uint32_t x, const uint32_t (&tab)[NP],
+                                            const uint32_t (&dst)[NP]) {
+    uint32_t e = x & 0x33333333u;           // even samples: selector nibbles 00gg
+    uint32_t o = (x >> 2) & 0x33333333u;    // odd samples
+    uint32_t eh = e >> 16, oh = o >> 16;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        uint32_t t = tab[p];
+        st_shared_v4(dst[p], __byte_perm(t, 0, e), __byte_perm(t, 0, o), __byte_perm(t, 0, eh),
+                     __byte_perm(t, 0, oh));
+    }
+}
+
+template <int NP>
+__global__ void __launch_bounds__(THREADS, 1) table_gram_kernel(const __grid_constant__ Params P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + NSTAGE * STAGE_BYTES;
+    // barriers: full[NSTAGE], empty[NSTAGE], accum; then the TMEM address slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
+    const uint32_t accum_bar = bar_base + 8u * (2 * NSTAGE);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE + 1);
+    volatile uint32_t *tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t *>(smem + NSTAGE * STAGE_BYTES + 8 * (2 * NSTAGE + 1));
+
+    const int2 tile = P.tiles[blockIdx.x];
+    const int st_begin = blockIdx.y * P.stages_per_split;
+    const int st_end = min(P.stages_total, st_begin + P.stages_per_split);
+    const int nst = st_end - st_begin;
+    if (nst <= 0) return;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int s = 0; s < NSTAGE; s++) {
+                mbar_init(full_bar(s), PROD_THREADS);
+                mbar_init(empty_bar(s), 1);
+            }
+            mbar_init(accum_bar, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc();
+        const bool swap = (P.flags & 1u) != 0;
+        const uint32_t a_lbo = swap ? CORE_SBO : A_LBO, a_sbo = swap ? A_LBO : CORE_SBO;
+        const uint32_t b_lbo = swap ? CORE_SBO : B_LBO, b_sbo = swap ? B_LBO : CORE_SBO;
+        for (int it = 0; it < nst; it++) {
+            const int s = it % NSTAGE;
+            const uint32_t phase = (uint32_t)(it / NSTAGE) & 1u;
+            mbar_wait(full_bar(s), phase, P.error_flag, 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t stage_addr = smem_base + s * STAGE_BYTES;
+#pragma unroll
+                for (int j = 0; j < SK / MMA_K; j++) {
+                    // K step j covers 4 groups of 8 SNPs
+                    uint64_t bdesc = make_desc(stage_addr + MAXP * A_BYTES + j * 4 * B_LBO, b_lbo, b_sbo);
+#pragma unroll
+                    for (int p = 0; p < NP; p++) {
+                        uint64_t adesc =
+                            make_desc(stage_addr + p * A_BYTES + j * 4 * A_LBO, a_lbo, a_sbo);
+                        umma_i8(tmem_base + (uint32_t)(p * TN), adesc, bdesc, idesc,
+                                (it > 0 || j > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(empty_bar(s));   // frees the stage once these MMAs have read it
+            }
+            __syncwarp();
+        }
+        if (lane == 0) umma_commit(accum_bar);
+        __syncwarp();
+    } else {
+        // ===================== producers =====================
+        const int p = threadIdx.x - 32;
+        const int sl = p & (SK - 1);   // SNP within the stage
+        const int half = p >> 7;       // which 64-sample quad of A / which 128-sample half of B
+        const int kg = sl >> 3, r = sl & 7;
+        const uint8_t *rowp = P.geno + ((long long)st_begin * SK + sl) * P.row_bytes;
+        const uint8_t *ap = rowp + (long long)tile.x * (TM / 4) + half * 16;
+        const uint8_t *bp = rowp + (long long)tile.y * (TN / 4) + half * 32;
+        const long long stage_stride = (long long)SK * P.row_bytes;
+        const uint32_t *ta[NP];
+#pragma unroll
+        for (int q = 0; q < NP; q++) ta[q] = P.tabA[q] + (long long)st_begin * SK + sl;
+        uint32_t tb[1] = {P.tabB};
+
+        uint4 na = ld_nc_v4(ap), nb0 = ld_nc_v4(bp), nb1 = ld_nc_v4(bp + 16);
+        uint32_t nt[NP];
+#pragma unroll
+        for (int q = 0; q < NP; q++) nt[q] = __ldg(ta[q]);
+
+        const uint32_t a_off = kg * A_LBO + (half * 4) * CORE_SBO + r * 16;
+        const uint32_t b_off = MAXP * A_BYTES + kg * B_LBO + (half * 8) * CORE_SBO + r * 16;
+
+        for (int it = 0; it < nst; it++) {
+            const int s = it % NSTAGE;
+            const uint32_t phase = (uint32_t)(it / NSTAGE) & 1u;
+            uint4 ca = na, cb0 = nb0, cb1 = nb1;
+            uint32_t ct[NP];
+#pragma unroll
+            for (int q = 0; q < NP; q++) ct[q] = nt[q];
+            if (it + 1 < nst) {   // prefetch the next stage's packed genotypes and tables
+                ap += stage_stride;
+                bp += stage_stride;
+                na = ld_nc_v4(ap);
+                nb0 = ld_nc_v4(bp);
+                nb1 = ld_nc_v4(bp + 16);
+#pragma unroll
+                for (int q = 0; q < NP; q++) {
+                    ta[q] += SK;
+                    nt[q] = __ldg(ta[q]);
+                }
+            }
+            mbar_wait(empty_bar(s), phase ^ 1u, P.error_flag, 2);
+            const uint32_t stage_addr = smem_base + s * STAGE_BYTES;
+            const uint32_t aw[4] = {ca.x, ca.y, ca.z, ca.w};
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                uint32_t dst[NP];
+#pragma unroll
+                for (int q = 0; q < NP; q++) dst[q] = stage_addr + q * A_BYTES + a_off + w * CORE_SBO;
+                expand_word<NP>(aw[w], ct, dst);
+            }
+            const uint32_t bw[8] = {cb0.x, cb0.y, cb0.z, cb0.w, cb1.x, cb1.y, cb1.z, cb1.w};
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                uint32_t dst[1] = {stage_addr + b_off + w * CORE_SBO};
+                expand_word<1>(bw[w], tb, dst);
+            }
+            fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core
+            mbar_arrive(full_bar(s));
+        }
+
+        // ===================== epilogue =====================
+        mbar_wait(accum_bar, 0, P.error_flag, 3);
+        tc_fence_after();
+        const int quarter = warp & 3;            // TMEM lanes this warp may touch
+        const int colhalf = (warp - 1) >> 2;     // two warps share a lane quarter
+        const int row = quarter * 32 + lane;
+        const long long gi = (long long)tile.x * TM + (row & ~15) + core_pos_to_sample(row & 15);
+#pragma unroll 1
+        for (int q = 0; q < NP; q++) {
+            long long *outp = P.out + (long long)P.plane[q] * P.plane_stride + gi * P.ld;
+            const long long mul = 1ll << P.shift[q];
+#pragma unroll 1
+            for (int cc = 0; cc < 4; cc++) {
+                const int col0 = colhalf * 128 + cc * 32;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(q * TN + col0), v);
+                if (gi < P.n_samp) {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) {
+                        int col = col0 + k;
+                        long long gj = (long long)tile.y * TN + (col & ~15) + core_pos_to_sample(col & 15);
+                        int val = (int)v[k];
+                        if (val != 0 && gj < P.n_samp && (!P.upper_only || gj >= gi))
+                            atomicAdd(reinterpret_cast<unsigned long long *>(outp + gj),
+                                      (unsigned long long)((long long)val * mul));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------
+// host driver: group passes that share a B table into launches of <= 2
+// ---------------------------------------------------------------------------
+void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *out_planes,
+                 bool upper_only) {
+    using namespace tc;
+    if (npass <= 0) return;
+    geno_pad_tail(c);
+    const int64_t n = c->n_samp, npad = c->n_samp_pad;
+    const int tiles_m = (int)((n + TM - 1) / TM), tiles_n = (int)((n + TN - 1) / TN);
+    std::vector<int2> tiles;
+    for (int tm = 0; tm < tiles_m; tm++)
+        for (int tn = 0; tn < tiles_n; tn++)
+            if (!upper_only || (int64_t)tn * TN + TN - 1 >= (int64_t)tm * TM) tiles.push_back(make_int2(tm, tn));
+    DevBuf<int2> dtiles;
+    dtiles.alloc(tiles.size());
+    CUDA_CHECK(cudaMemcpyAsync(dtiles.p, tiles.data(), tiles.size() * sizeof(int2),
+                               cudaMemcpyHostToDevice, c->stream));
+    DevBuf<int> derr;
+    derr.alloc(1);
+    derr.zero(c->stream);
+
+    const int stages_total = (int)(round_up(std::max<int64_t>(c->n_snp, 1), SK) / SK);
+    // split the SNP range when the tile list alone cannot fill the SMs
+    int64_t want = (int64_t)c->num_sms * 2;
+    int64_t splits = std::max<int64_t>(1, std::min<int64_t>((want + (int64_t)tiles.size() - 1) /
+                                                               (int64_t)tiles.size(),
+                                                           stages_total));
+    splits = std::min<int64_t>(splits, 65535);
+    int sps = (int)((stages_total + splits - 1) / splits);
+    splits = (stages_total + sps - 1) / sps;
+    // int32 accumulator headroom: |digit| <= 128, |tabB| <= 2  ->  256 per SNP
+    const int max_stages_i32 = (int)((2147483647ll / 256) / SK);
+    if (sps > max_stages_i32) {
+        sps = max_stages_i32;
+        splits = (stages_total + sps - 1) / sps;
+    }
+
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        SMEM_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        SMEM_BYTES));
+        attr_done = true;
+    }
+
+    std::vector<char> used((size_t)npass, 0);
+    for (int i = 0; i < npass; i++) {
+        if (used[i]) continue;
+        Params P{};
+        P.geno = c->geno2b.p;
+        P.row_bytes = c->row_bytes;
+        P.tabB = passes[i].tabB;
+        P.out = out_planes;
+        P.ld = npad;
+        P.plane_stride = npad * npad;
+        P.n_samp = n;
+        P.tiles = dtiles.p;
+        P.stages_total = stages_total;
+        P.stages_per_split = sps;
+        P.upper_only = upper_only ? 1 : 0;
+        P.flags = c->debug_flags;
+        P.error_flag = derr.p;
+        int np = 0;
+        for (int j = i; j < npass && np < MAXP; j++) {
+            if (used[j] || passes[j].tabB != passes[i].tabB) continue;
+            P.tabA[np] = passes[j].tabA;
+            P.plane[np] = passes[j].plane;
+            P.shift[np] = passes[j].shift;
+            used[j] = 1;
+            np++;
+        }
+        P.npass = np;
+        dim3 grid((unsigned)tiles.size(), (unsigned)splits);
+        if (np == 2)
+            table_gram_kernel<2><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P);
+        else
+            table_gram_kernel<1><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P);
+        KERNEL_CHECK(c);
+        c->hot_launches++;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    int herr = 0;
+    CUDA_CHECK(cudaMemcpy(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (herr) fail("table_gram_kernel: pipeline barrier %d timed out", herr);
+}
+
+}  // namespace snprel

@@ -1,0 +1,704 @@
+// Covariance-type estimators on top of the tcgen05 table Gram (gram_tc.cu):
+//   Eigenstrat / PCA   CExactPCA::Run + gnrPCA       src/genPCA.cpp:395-464,1355-1452
+//   GCTA, Corr         CGCTA_AlgArith::Run + gnrGRM  src/genPCA.cpp:1148-1237,1614-1717
+//   EIGMIX             CEigMix_AlgArith::Run         src/genEIGMIX.cpp:60-156,645-735
+//   KING-homo sums     CKINGHomo                     src/genKING.cpp:69-266,493-570
+//
+// Algebra.  With x = genotype (0 when missing), m = missing indicator, mu_l the mean
+// genotype of SNP l over non-missing samples and w_l the per-SNP weight
+// (1/(p(1-p)) for Eigenstrat/GCTA, 1 for EIGMIX), the reference accumulates
+//     C_ij = sum_l w_l (x_il - mu_l (1-m_il)) (x_jl - mu_l (1-m_jl)).
+// Define the per-SNP 4-entry tables over the genotype code g (0,1,2,3=missing)
+//     U_l[g] = w_l (g - mu_l)  (U_l[3] = 0),      W_l[g] = mu_l U_l[g].
+// Then  C_ij = sum_l U_l[g_il] x_jl  -  sum_l W_l[g_il]  +  sum_l W_l[g_il] m_jl.
+// The first and third sums are table Grams against the small-integer channels x and
+// m; the middle one is a per-sample vector.  Tables are quantised to fixed point
+// (2^-frac_bits) and split into balanced base-256 digits, one int8 tensor-core pass
+// per digit; the quantisation error of an entry is bounded by
+// 2^-(frac_bits+1) * (2 #SNP + #missing) and everything after quantisation is exact
+// integer arithmetic.  Denominators (GCTA: #polymorphic SNPs with i or j missing;
+// EIGMIX: sum 4p(1-p) over SNPs with i or j missing) use
+//     D_ij = r_i + r_j - sum_l d_l m_il m_jl,   r_i = sum_l d_l m_il,
+// i.e. one more table Gram (channel m on both sides) and a per-sample vector.
+#include <cusolverDn.h>
+
+#include <cmath>
+
+#include "common.cuh"
+
+namespace snprel {
+
+constexpr uint32_t TABB_X = 0x00020100u;   // x channel: code -> {0,1,2,0}
+constexpr uint32_t TABB_M = 0x01000000u;   // m channel: code -> {0,0,0,1}
+constexpr int MAX_DIGITS = 8;
+
+enum { VEC_W = 0, VEC_D = 1, VEC_HET = 2, VEC_D2 = 3, NVEC = 4 };
+// scalars[]: 0 = sum of d_l (EIGMIX SumDenominator / KING-homo sum p(1-p)), 1 = sum d2_l
+// iscalars[]: 0 = nLocus (GCTA), 1 = total missing genotypes (valid samples only)
+
+struct SnpTables {
+    long long qU[4];   // fixed-point U
+    long long qW[4];   // fixed-point W
+    long long qD;      // fixed-point d (GCTA: 0/1 unscaled; EIGMIX / KING-homo: 2^frac_bits scaled)
+    long long qD2;     // KING-homo: (p(1-p))^2
+    double d, d2;      // float64 d, d2 (for the global scalars)
+    double maxU, maxW;
+};
+
+// est: SNPREL_GRM_EIGENSTRAT / GCTA / CORR / EIGMIX, or SNPREL_EST_KING_HOMO
+__device__ __forceinline__ void snp_tables(const SnpStat st, int est, int bayesian, int frac_bits,
+                                           SnpTables &t) {
+    const double sc = exp2((double)frac_bits);
+    double mu = st.num > 0 ? (double)st.sum / (double)st.num : 0.0;   // DivideGeno, src/genPCA.cpp:98-142
+    double w = 0, d = 0, d2 = 0;
+    long long qD = 0, qD2 = 0;
+    if (est == SNPREL_GRM_EIGMIX) {
+        w = 1.0;
+        double af = 0.5 * mu;
+        d = 4 * af * (1 - af);                    // src/genEIGMIX.cpp:116-119
+        qD = llrint(d * sc);
+    } else if (est == SNPREL_EST_KING_HOMO) {
+        double p = st.num > 0 ? 0.5 * (double)st.sum / (double)st.num : 0.0;   // src/genKING.cpp:239-241
+        d = p * (1 - p);
+        d2 = d * d;
+        qD = llrint(d * sc);
+        qD2 = llrint(d2 * sc);
+    } else {
+        if (bayesian) {                           // src/genPCA.cpp:445-452
+            double s = ((double)st.sum + 1.0) / (double)(2 * st.num + 2);
+            double r = 1.0 / sqrt(s * (1 - s));
+            w = r * r;
+        } else {                                  // rsqrt_prod, src/genPCA.cpp:145-181
+            double s = mu * 0.5;
+            if (0 < s && s < 1) {
+                double r = 1.0 / sqrt(s * (1 - s));
+                w = r * r;
+            }
+        }
+        bool poly = (0 < st.sum) && (st.sum < 2 * st.num);   // src/genPCA.cpp:1206
+        d = poly ? 1.0 : 0.0;
+        qD = poly ? 1 : 0;
+    }
+    t.maxU = 0;
+    t.maxW = 0;
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+        double u = (est == SNPREL_EST_KING_HOMO) ? 0.0 : w * ((double)g - mu);
+        double ww = mu * u;
+        t.qU[g] = llrint(u * sc);
+        t.qW[g] = llrint(ww * sc);
+        t.maxU = fmax(t.maxU, fabs(u));
+        t.maxW = fmax(t.maxW, fabs(ww));
+    }
+    t.qU[3] = 0;
+    t.qW[3] = 0;
+    t.qD = qD;
+    t.qD2 = qD2;
+    t.d = d;
+    t.d2 = d2;
+}
+
+__device__ __forceinline__ uint32_t digit_of(long long &q) {
+    long long dgt = ((q + 128) & 255) - 128;   // balanced digit in [-128, 127]
+    q = (q - dgt) >> 8;
+    return (uint32_t)(dgt & 255);
+}
+
+// ---- plan statistics ---------------------------------------------------------
+__global__ void plan_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int64_t n_samp, int est,
+                            int bayesian, double *__restrict__ out /*[3]: max_abs, sum_bound, total_missing*/) {
+    double mx = 0, sb = 0, tm = 0;
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n_snp;
+         l += (int64_t)gridDim.x * blockDim.x) {
+        SnpTables t;
+        snp_tables(st[l], est, bayesian, 0, t);
+        double dmax = (est == SNPREL_GRM_EIGMIX || est == SNPREL_EST_KING_HOMO) ? fmax(t.d, t.d2) : 0.0;
+        mx = fmax(mx, fmax(fmax(t.maxU, t.maxW), dmax));
+        sb += 2 * t.maxU + 2 * t.maxW + 2 * dmax;
+        tm += (double)(n_samp - st[l].num);
+    }
+    __shared__ double s0[256], s1[256], s2[256];
+    s0[threadIdx.x] = mx;
+    s1[threadIdx.x] = sb;
+    s2[threadIdx.x] = tm;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o; o >>= 1) {
+        if (threadIdx.x < o) {
+            s0[threadIdx.x] = fmax(s0[threadIdx.x], s0[threadIdx.x + o]);
+            s1[threadIdx.x] += s1[threadIdx.x + o];
+            s2[threadIdx.x] += s2[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        atomicMax(reinterpret_cast<unsigned long long *>(out), (unsigned long long)__double_as_longlong(s0[0]));
+        atomicAdd(out + 1, s1[0]);
+        atomicAdd(out + 2, s2[0]);
+    }
+}
+
+// ---- digit tables: tab[pass][snp] ------------------------------------------
+// pass order: U digits (nU), W digits (nW), D digits (nD), D2 digits (nD2)
+__global__ void tables_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int64_t cap, int est,
+                              int bayesian, int frac_bits, int nU, int nW, int nD, int nD2,
+                              uint32_t *__restrict__ tab, double *__restrict__ scalars,
+                              long long *__restrict__ iscalars, int *__restrict__ overflow) {
+    int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double d = 0, d2 = 0;
+    long long poly = 0;
+    if (l < n_snp) {
+        SnpTables t;
+        snp_tables(st[l], est, bayesian, frac_bits, t);
+        d = t.d;
+        d2 = t.d2;
+        poly = (est == SNPREL_GRM_GCTA || est == SNPREL_GRM_CORR) ? t.qD : 0;
+        int pass = 0;
+        long long q[4];
+        for (int g = 0; g < 4; g++) q[g] = t.qU[g];
+        for (int k = 0; k < nU; k++, pass++) {
+            uint32_t word = 0;
+            for (int g = 0; g < 4; g++) word |= digit_of(q[g]) << (8 * g);
+            tab[(int64_t)pass * cap + l] = word;
+        }
+        for (int g = 0; g < 4; g++)
+            if (nU > 0 && q[g] != 0) atomicExch(overflow, 1);
+        for (int g = 0; g < 4; g++) q[g] = t.qW[g];
+        for (int k = 0; k < nW; k++, pass++) {
+            uint32_t word = 0;
+            for (int g = 0; g < 4; g++) word |= digit_of(q[g]) << (8 * g);
+            tab[(int64_t)pass * cap + l] = word;
+        }
+        for (int g = 0; g < 4; g++)
+            if (nW > 0 && q[g] != 0) atomicExch(overflow, 2);
+        long long qd = t.qD;
+        for (int k = 0; k < nD; k++, pass++) tab[(int64_t)pass * cap + l] = digit_of(qd) << 24;
+        if (nD > 0 && qd != 0) atomicExch(overflow, 3);
+        long long qd2 = t.qD2;
+        for (int k = 0; k < nD2; k++, pass++) tab[(int64_t)pass * cap + l] = digit_of(qd2) << 24;
+        if (nD2 > 0 && qd2 != 0) atomicExch(overflow, 4);
+    }
+    // global scalars: deterministic per-block tree, then one atomic per block
+    __shared__ double s0[256], s1[256];
+    __shared__ long long s2[256];
+    s0[threadIdx.x] = d;
+    s1[threadIdx.x] = d2;
+    s2[threadIdx.x] = poly;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o; o >>= 1) {
+        if (threadIdx.x < o) {
+            s0[threadIdx.x] += s0[threadIdx.x + o];
+            s1[threadIdx.x] += s1[threadIdx.x + o];
+            s2[threadIdx.x] += s2[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(scalars + 0, s0[0]);
+        atomicAdd(scalars + 1, s1[0]);
+        atomicAdd(reinterpret_cast<unsigned long long *>(iscalars), (unsigned long long)s2[0]);
+    }
+}
+
+// ---- per-sample sums: vec[v][i] = sum_l T_v,l[g_il]  (exact int64) ---------
+constexpr int SS_SNPS = 512;   // SNPs per block
+__global__ void __launch_bounds__(128)
+sample_sum_kernel(const uint8_t *__restrict__ geno, const SnpStat *__restrict__ st, int64_t n_snp,
+                  int64_t row_bytes, int64_t npad, int est, int bayesian, int frac_bits,
+                  long long *__restrict__ vec) {
+    __shared__ long long tW[SS_SNPS][4];
+    __shared__ long long tD[SS_SNPS], tD2[SS_SNPS];
+    const int64_t l0 = (int64_t)blockIdx.y * SS_SNPS;
+    const int nl = (int)min((int64_t)SS_SNPS, n_snp - l0);
+    for (int s = threadIdx.x; s < nl; s += blockDim.x) {
+        SnpTables t;
+        snp_tables(st[l0 + s], est, bayesian, frac_bits, t);
+        for (int g = 0; g < 4; g++) tW[s][g] = t.qW[g];
+        tD[s] = t.qD;
+        tD2[s] = t.qD2;
+    }
+    __syncthreads();
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // byte column (4 samples)
+    if (b >= row_bytes) return;
+    long long aw[4] = {0, 0, 0, 0}, ad[4] = {0, 0, 0, 0}, ad2[4] = {0, 0, 0, 0};
+    int ah[4] = {0, 0, 0, 0};
+    const uint8_t *p = geno + l0 * row_bytes + b;
+    for (int s = 0; s < nl; s++) {
+        uint32_t v = p[(int64_t)s * row_bytes];
+        long long dd = tD[s], dd2 = tD2[s];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t code = (v >> (2 * k)) & 3;
+            aw[k] += tW[s][code];
+            if (code == 3) {
+                ad[k] += dd;
+                ad2[k] += dd2;
+            }
+            ah[k] += (code == 1);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int64_t i = b * 4 + k;
+        unsigned long long *o = reinterpret_cast<unsigned long long *>(vec);
+        if (aw[k]) atomicAdd(o + VEC_W * npad + i, (unsigned long long)aw[k]);
+        if (ad[k]) atomicAdd(o + VEC_D * npad + i, (unsigned long long)ad[k]);
+        if (ah[k]) atomicAdd(o + VEC_HET * npad + i, (unsigned long long)(long long)ah[k]);
+        if (ad2[k]) atomicAdd(o + VEC_D2 * npad + i, (unsigned long long)ad2[k]);
+    }
+}
+
+// ---- helpers ---------------------------------------------------------------
+static int digits_needed(double max_abs, int frac_bits) {
+    if (!(max_abs > 0)) return 1;
+    // |q| <= max_abs * 2^f + 0.5 must be representable with balanced digits:
+    // K digits cover |q| <= (2^(8K) - 1) / 2 - 128 ...  use a safe margin of one bit
+    double bits = std::log2(max_abs) + frac_bits + 2.0;
+    int k = (int)std::ceil(bits / 8.0);
+    return std::max(1, std::min(k, MAX_DIGITS));
+}
+
+void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
+    if (!plan) fail("snprel_plan_local: NULL plan");
+    ensure_stats(c);
+    DevBuf<double> out;
+    out.alloc(3);
+    out.zero(c->stream);
+    if (c->n_snp > 0) {
+        int blocks = (int)std::min<int64_t>((c->n_snp + 255) / 256, 1024);
+        plan_kernel<<<blocks, 256, 0, c->stream>>>(c->stat.p, c->n_snp, c->n_samp, est,
+                                                   plan->bayesian, out.p);
+        KERNEL_CHECK(c);
+    }
+    double h[3];
+    CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    plan->max_abs = h[0];
+    plan->sum_bound = h[1];
+    plan->max_missing = (int64_t)h[2];
+    plan->n_snp = c->n_snp;
+}
+
+// choose frac_bits from the (global) plan statistics
+static int choose_frac_bits(const snprel_plan *plan) {
+    if (plan->frac_bits >= 0) return plan->frac_bits;
+    const int target = 40;
+    int head = 61 - (int)std::ceil(std::log2(std::max(plan->sum_bound, 1.0)));
+    int f = std::min(target, head);
+    if (f < 20) fail("fixed-point accumulator cannot hold this data set (sum bound %.3g)", plan->sum_bound);
+    return f;
+}
+
+void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
+    if (est == SNPREL_GRM_CORR) est = SNPREL_GRM_GCTA;
+    ensure_stats(c);
+    snprel_plan plan = *plan_in;
+    const int f = choose_frac_bits(&plan);
+    plan.frac_bits = f;
+    const bool any_missing = plan.max_missing > 0;
+    const bool homo = est == SNPREL_EST_KING_HOMO;
+    int nU = homo ? 0 : digits_needed(plan.max_abs, f);
+    int nW = (!homo && any_missing) ? nU : 0;
+    int nD = 0, nD2 = 0;
+    if (any_missing) {
+        if (est == SNPREL_GRM_GCTA) nD = 1;
+        if (est == SNPREL_GRM_EIGMIX) nD = digits_needed(1.0, f);
+        if (homo) nD = nD2 = digits_needed(0.25, f);
+    }
+    const int npass = nU + nW + nD + nD2;
+    const int64_t cap = c->snp_cap, npad = c->n_samp_pad;
+
+    DevBuf<uint32_t> tab;
+    tab.alloc((size_t)std::max(npass, 1) * cap);
+    tab.zero(c->stream);
+    c->scalars.alloc(4);
+    c->scalars.zero(c->stream);
+    c->iscalars.alloc(4);
+    c->iscalars.zero(c->stream);
+    DevBuf<int> ovf;
+    ovf.alloc(1);
+    ovf.zero(c->stream);
+    if (c->n_snp > 0) {
+        tables_kernel<<<(unsigned)((c->n_snp + 255) / 256), 256, 0, c->stream>>>(
+            c->stat.p, c->n_snp, cap, est, plan.bayesian, f, nU, nW, nD, nD2, tab.p, c->scalars.p,
+            c->iscalars.p, ovf.p);
+        KERNEL_CHECK(c);
+    }
+    int hovf = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&hovf, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (hovf) fail("internal: fixed-point digit overflow (table %d, frac_bits %d)", hovf, f);
+
+    // per-sample vectors
+    c->samp_sum.alloc((size_t)NVEC * npad);
+    c->samp_sum.zero(c->stream);
+    c->samp_vecs = NVEC;
+    if (c->n_snp > 0) {
+        dim3 grid((unsigned)((c->row_bytes + 127) / 128), (unsigned)((c->n_snp + SS_SNPS - 1) / SS_SNPS));
+        sample_sum_kernel<<<grid, 128, 0, c->stream>>>(c->geno2b.p, c->stat.p, c->n_snp, c->row_bytes,
+                                                       npad, est, plan.bayesian, f, c->samp_sum.p);
+        KERNEL_CHECK(c);
+    }
+
+    // Gram planes: 0 = numerator, 1 = missing-pair denominator (or KING-homo d), 2 = KING-homo d2
+    const int nplanes = homo ? 2 : ((nD > 0) ? 2 : 1);
+    c->acc.alloc((size_t)nplanes * npad * npad);
+    c->acc.zero(c->stream);
+    c->acc_planes = nplanes;
+
+    std::vector<GramPass> passes;
+    int pass = 0;
+    for (int k = 0; k < nU; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, TABB_X, 0, 8 * k});
+    for (int k = 0; k < nW; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, TABB_M, 0, 8 * k});
+    for (int k = 0; k < nD; k++, pass++)
+        passes.push_back({tab.p + (int64_t)pass * cap, TABB_M, homo ? 0 : 1, 8 * k});
+    for (int k = 0; k < nD2; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, TABB_M, 1, 8 * k});
+
+    c->hot_launches = 0;
+    CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+    gram_tc_run(c, passes.data(), (int)passes.size(), c->acc.p, true);
+    CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->hot_ms = ms;
+    c->hot_units = 0.5 * (double)c->n_samp * (double)c->n_samp * (double)c->n_snp;
+
+    c->plan = plan;
+    c->accum_est = est;
+    c->accum_reduced = false;
+    c->reduce_list.clear();
+    c->reduce_list.push_back({c->acc.p, (int64_t)c->acc.n, 0});
+    c->reduce_list.push_back({c->samp_sum.p, (int64_t)c->samp_sum.n, 0});
+    c->reduce_list.push_back({c->scalars.p, (int64_t)c->scalars.n, 2});
+    c->reduce_list.push_back({c->iscalars.p, (int64_t)c->iscalars.n, 0});
+}
+
+// ---------------------------------------------------------------------------
+// epilogues
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void store_sym2(double *out, int packed, int64_t n, int64_t i, int64_t j,
+                                           double v) {
+    if (packed) {
+        out[j + i * (2 * n - i - 1) / 2] = v;
+    } else {
+        out[i * n + j] = v;
+        out[j * n + i] = v;
+    }
+}
+
+// numerator C_ij = (acc0[i][j] - vecW[i]) * 2^-f, into a full n x n matrix (upper triangle)
+__global__ void numerator_kernel(const long long *__restrict__ acc, const long long *__restrict__ vec,
+                                 double *__restrict__ out, double inv_scale, int64_t n, int64_t npad) {
+    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= n || j < i) return;
+    long long q = acc[i * npad + j] - vec[VEC_W * npad + i];
+    out[i * n + j] = (double)q * inv_scale;
+}
+
+// mode 0: Eigenstrat (scale = (n-1)/trace); 1: GCTA; 3: EIGMIX (mul = 1 ibd / 2 GRM)
+__global__ void grm_final_kernel(const double *__restrict__ num, const long long *__restrict__ acc,
+                                 const long long *__restrict__ vec, double *__restrict__ out, int packed,
+                                 int mode, double scale, double sum_den, long long nlocus,
+                                 double inv_fix, int has_den, int diagadj, double mul, int64_t n,
+                                 int64_t npad) {
+    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= n || j < i) return;
+    double c = num[i * n + j];
+    double v;
+    if (mode == 0) {
+        v = c * scale;
+    } else {
+        long long dq = 0;
+        if (has_den)
+            dq = vec[VEC_D * npad + i] + vec[VEC_D * npad + j] - acc[npad * npad + i * npad + j];
+        if (mode == 1) {
+            v = c / (double)(2 * (nlocus - dq));      // src/genPCA.cpp:1233-1236
+        } else {
+            if (diagadj && i == j) c -= (double)vec[VEC_HET * npad + i];   // src/genEIGMIX.cpp:147-151
+            v = c / (sum_den - (double)dq * inv_fix) * mul;                // :153-155, :645-652
+        }
+    }
+    store_sym2(out, packed, n, i, j, v);
+}
+
+__global__ void diag_kernel(const double *__restrict__ m, double *__restrict__ d, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = m[i * n + i];
+}
+
+// gnrGRM "Corr": p_ij / sqrt(p_ii p_jj), diagonal forced to 1 (src/genPCA.cpp:1670-1685)
+__global__ void corr_kernel(double *__restrict__ g, const double *__restrict__ diag, int64_t n) {
+    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= n || j < i) return;
+    double v = (i == j) ? 1.0 : g[i * n + j] / (sqrt(diag[i]) * sqrt(diag[j]));
+    g[i * n + j] = v;
+    g[j * n + i] = v;
+}
+
+__global__ void symmetrize_neg_kernel(const double *__restrict__ src, double *__restrict__ dst,
+                                      double sign, int64_t n) {
+    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= n || j < i) return;
+    double v = sign * src[i * n + j];
+    dst[i * n + j] = v;
+    dst[j * n + i] = v;
+}
+
+static dim3 tri_grid(int64_t n) { return dim3((unsigned)n, (unsigned)((n + 127) / 128)); }
+
+static size_t out_count(int64_t n, int packed) {
+    return packed ? (size_t)n * (n + 1) / 2 : (size_t)n * n;
+}
+
+template <class T>
+static void d2h(snprel_ctx *c, T *host, const T *dev, size_t count) {
+    CUDA_CHECK(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+static void need_grm_accum(snprel_ctx *c, int est, int bayesian) {
+    if (est == SNPREL_GRM_CORR) est = SNPREL_GRM_GCTA;
+    if (c->accum_est == est && c->accum_reduced) return;
+    snprel_plan plan{};
+    plan.frac_bits = -1;
+    plan.bayesian = bayesian;
+    grm_plan_local(c, est, &plan);
+    grm_accumulate(c, est, &plan);
+}
+
+struct Globals {
+    double sum_den, sum_den2;
+    long long nlocus;
+};
+static Globals read_globals(snprel_ctx *c) {
+    double hs[4];
+    long long hi[4];
+    d2h(c, hs, c->scalars.p, 4);
+    d2h(c, hi, c->iscalars.p, 4);
+    return Globals{hs[0], hs[1], hi[0]};
+}
+
+// numerator into dev buffer `num` (n x n, upper triangle valid)
+static void build_numerator(snprel_ctx *c, DevBuf<double> &num) {
+    int64_t n = c->n_samp;
+    num.alloc((size_t)n * n);
+    numerator_kernel<<<tri_grid(n), 128, 0, c->stream>>>(c->acc.p, c->samp_sum.p, num.p,
+                                                         std::ldexp(1.0, -c->plan.frac_bits), n,
+                                                         c->n_samp_pad);
+    KERNEL_CHECK(c);
+}
+
+static double trace_of(snprel_ctx *c, const double *m, int64_t n) {
+    DevBuf<double> d;
+    d.alloc((size_t)n);
+    diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(m, d.p, n);
+    KERNEL_CHECK(c);
+    std::vector<double> h((size_t)n);
+    d2h(c, h.data(), d.p, (size_t)n);
+    double t = 0;
+    for (int64_t i = 0; i < n; i++) t += h[i];   // CdMatTri::Trace order
+    return t;
+}
+
+// device-side result of the covariance family: full symmetric/packed matrix in `o`
+static void grm_device(snprel_ctx *c, int method, int packed, int diagadj, double mul, DevBuf<double> &o,
+                       double *trace_xtx) {
+    int64_t n = c->n_samp, npad = c->n_samp_pad;
+    DevBuf<double> num;
+    build_numerator(c, num);
+    Globals g = read_globals(c);
+    const int has_den = c->acc_planes > 1;
+    o.alloc(out_count(n, packed));
+    if (method == SNPREL_GRM_EIGENSTRAT) {
+        double tr = trace_of(c, num.p, n);
+        if (trace_xtx) *trace_xtx = tr;
+        grm_final_kernel<<<tri_grid(n), 128, 0, c->stream>>>(num.p, c->acc.p, c->samp_sum.p, o.p, packed,
+                                                             0, (double)(n - 1) / tr, 0, 0, 0, 0, 0, 1, n,
+                                                             npad);
+    } else if (method == SNPREL_GRM_GCTA || method == SNPREL_GRM_CORR) {
+        grm_final_kernel<<<tri_grid(n), 128, 0, c->stream>>>(num.p, c->acc.p, c->samp_sum.p, o.p, packed,
+                                                             1, 0, 0, g.nlocus, 1.0, has_den, 0, 1, n,
+                                                             npad);
+    } else {
+        grm_final_kernel<<<tri_grid(n), 128, 0, c->stream>>>(
+            num.p, c->acc.p, c->samp_sum.p, o.p, packed, 3, 0, g.sum_den, 0,
+            std::ldexp(1.0, -c->plan.frac_bits), has_den, diagadj, mul, n, npad);
+    }
+    KERNEL_CHECK(c);
+}
+
+void grm_finish(snprel_ctx *c, int method, double *out, int packed) {
+    if (!out) fail("snprel_grm: NULL output");
+    int64_t n = c->n_samp;
+    need_grm_accum(c, method, 0);
+    DevBuf<double> o;
+    if (method == SNPREL_GRM_CORR) {
+        grm_device(c, SNPREL_GRM_GCTA, 0, 0, 1, o, nullptr);
+        DevBuf<double> d;
+        d.alloc((size_t)n);
+        diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(o.p, d.p, n);
+        KERNEL_CHECK(c);
+        corr_kernel<<<tri_grid(n), 128, 0, c->stream>>>(o.p, d.p, n);
+        KERNEL_CHECK(c);
+        d2h(c, out, o.p, (size_t)n * n);
+        return;
+    }
+    grm_device(c, method, packed, 0, method == SNPREL_GRM_EIGMIX ? 2.0 : 1.0, o, nullptr);
+    d2h(c, out, o.p, out_count(n, packed));
+}
+
+// top-k eigenpairs of the symmetric matrix `m` (upper triangle valid), descending:
+// the reference runs LAPACK dspevx on -C and negates back (src/genPCA.cpp:1262-1346);
+// here cuSOLVER syevdx on -C (a library call is fine for the O(N^3) eigen step).
+static void eigen_topk(snprel_ctx *c, const double *m_upper, int64_t n, int k, double *eigval,
+                       double *eigvec) {
+    if (k <= 0) return;
+    if (k > n) k = (int)n;
+    DevBuf<double> a, w;
+    a.alloc((size_t)n * n);
+    w.alloc((size_t)n);
+    symmetrize_neg_kernel<<<tri_grid(n), 128, 0, c->stream>>>(m_upper, a.p, -1.0, n);
+    KERNEL_CHECK(c);
+    cusolverDnHandle_t h;
+    if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) fail("cusolverDnCreate failed");
+    cusolverDnSetStream(h, c->stream);
+    int lwork = 0, found = 0;
+    DevBuf<int> info;
+    info.alloc(1);
+    cusolverStatus_t st = cusolverDnDsyevdx_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I,
+                                                      CUBLAS_FILL_MODE_LOWER, (int)n, a.p, (int)n, 0, 0, 1,
+                                                      k, &found, w.p, &lwork);
+    if (st != CUSOLVER_STATUS_SUCCESS) {
+        cusolverDnDestroy(h);
+        fail("cusolverDnDsyevdx_bufferSize failed (%d)", (int)st);
+    }
+    DevBuf<double> work;
+    work.alloc((size_t)lwork);
+    st = cusolverDnDsyevdx(h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_LOWER, (int)n,
+                           a.p, (int)n, 0, 0, 1, k, &found, w.p, work.p, lwork, info.p);
+    int hinfo = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    cusolverDnDestroy(h);
+    if (st != CUSOLVER_STATUS_SUCCESS || hinfo != 0)
+        fail("eigen-decomposition error (%d), infinite or missing values in the genetic covariance matrix!",
+             hinfo);   // wording follows src/genPCA.cpp:1330-1334
+    std::vector<double> hw((size_t)n);
+    d2h(c, hw.data(), w.p, (size_t)n);
+    const double nan = __builtin_nan("");
+    if (eigval) {
+        for (int i = 0; i < k; i++) eigval[i] = -hw[i];
+        for (int64_t i = k; i < n; i++) eigval[i] = nan;   // src/genPCA.cpp:1339-1341
+    }
+    if (eigvec) d2h(c, eigvec, a.p, (size_t)n * k);
+}
+
+void pca_finish(snprel_ctx *c, int eigen_cnt, int bayesian, double *genmat, double *trace_xtx,
+                double *trace_val, double *eigval, double *eigvec) {
+    if (eigen_cnt < 0) fail("Invalid 'eigen.cnt'.");   // src/genPCA.cpp:1423-1424
+    int64_t n = c->n_samp;
+    need_grm_accum(c, SNPREL_GRM_EIGENSTRAT, bayesian);
+    DevBuf<double> o;
+    double tx = 0;
+    grm_device(c, SNPREL_GRM_EIGENSTRAT, 0, 0, 1, o, &tx);
+    if (trace_xtx) *trace_xtx = tx;
+    if (trace_val) *trace_val = trace_of(c, o.p, n);
+    if (genmat) d2h(c, genmat, o.p, (size_t)n * n);
+    if (eigval || eigvec) eigen_topk(c, o.p, n, eigen_cnt, eigval, eigvec);
+}
+
+void eigmix_finish(snprel_ctx *c, int eigen_cnt, int diagadj, double *ibd, double *afreq, double *eigval,
+                   double *eigvec) {
+    int64_t n = c->n_samp;
+    need_grm_accum(c, SNPREL_GRM_EIGMIX, 0);
+    if (eigen_cnt < 0 || eigen_cnt > n) eigen_cnt = (int)n;   // src/genEIGMIX.cpp:675-676
+    DevBuf<double> o;
+    grm_device(c, SNPREL_GRM_EIGMIX, 0, diagadj, 1.0, o, nullptr);
+    if (ibd) d2h(c, ibd, o.p, (size_t)n * n);
+    if (afreq) {   // af = 0.5 * avg_geno (src/genEIGMIX.cpp:116-118)
+        std::vector<SnpStat> h((size_t)c->n_snp);
+        d2h(c, h.data(), c->stat.p, (size_t)c->n_snp);
+        for (int64_t l = 0; l < c->n_snp; l++)
+            afreq[l] = 0.5 * (h[l].num > 0 ? (double)h[l].sum / (double)h[l].num : 0.0);
+    }
+    if ((eigval || eigvec) && eigen_cnt > 0) eigen_topk(c, o.p, n, eigen_cnt, eigval, eigvec);
+}
+
+// ---- KING-homo: IBS0/SumSq from the packed-bit kernel, the two float sums from
+// the table Gram (jointly-valid sums = total - r_i - r_j + both-missing Gram) ----
+__global__ void king_homo_kernel(const uint32_t *__restrict__ cnt, const long long *__restrict__ acc,
+                                 const long long *__restrict__ vec, double *__restrict__ k0o,
+                                 double *__restrict__ k1o, int packed, double s1, double s2,
+                                 double inv_fix, int has_den, int64_t n, int64_t npad) {
+    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= n || j < i) return;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    if (i == j) {   // src/genKING.cpp:524
+        store_sym2(k0o, packed, n, i, j, 0.0);
+        store_sym2(k1o, packed, n, i, j, 0.0);
+        return;
+    }
+    int64_t plane = npad * npad, k = i * npad + j;
+    double ibs0 = (double)cnt[k], sumsq = (double)(cnt[2 * plane + k] + 4u * cnt[k]);
+    double a1 = s1, a2 = s2;
+    if (has_den) {
+        long long q1 = vec[VEC_D * npad + i] + vec[VEC_D * npad + j] - acc[k];
+        long long q2 = vec[VEC_D2 * npad + i] + vec[VEC_D2 * npad + j] - acc[plane + k];
+        a1 -= (double)q1 * inv_fix;
+        a2 -= (double)q2 * inv_fix;
+    }
+    double theta = 0.5 - sumsq / (8 * a1);          // src/genKING.cpp:527-529
+    double k0 = ibs0 / (2 * a2);
+    double k1 = 2 - 2 * k0 - 4 * theta;
+    store_sym2(k0o, packed, n, i, j, isfinite(k0) ? k0 : nan);
+    store_sym2(k1o, packed, n, i, j, isfinite(k1) ? k1 : nan);
+}
+
+void king_homo_finish(snprel_ctx *c, double *k0, double *k1, int packed) {
+    if (!k0 || !k1) fail("snprel_king_homo: NULL output");
+    int64_t n = c->n_samp;
+    // float sums first (they own acc/samp_sum), then the integer counters (they own cnt)
+    snprel_plan plan{};
+    plan.frac_bits = -1;
+    grm_plan_local(c, SNPREL_EST_KING_HOMO, &plan);
+    grm_accumulate(c, SNPREL_EST_KING_HOMO, &plan);
+    Globals g = read_globals(c);
+    const int has_den = plan.max_missing > 0;
+    const int fb = c->plan.frac_bits;
+    bitcount_accumulate(c, SNPREL_EST_KING_ROBUST);
+    DevBuf<double> o;
+    size_t oc = out_count(n, packed);
+    o.alloc(2 * oc);
+    king_homo_kernel<<<tri_grid(n), 128, 0, c->stream>>>(c->cnt.p, c->acc.p, c->samp_sum.p, o.p, o.p + oc,
+                                                         packed, g.sum_den, g.sum_den2,
+                                                         std::ldexp(1.0, -fb), has_den, n, c->n_samp_pad);
+    KERNEL_CHECK(c);
+    d2h(c, k0, o.p, oc);
+    d2h(c, k1, o.p + oc, oc);
+    c->accum_est = -1;
+}
+
+// ---- test hook: exact table Gram with caller tables -------------------------
+void table_gram_debug(snprel_ctx *c, const int8_t *tabA, const int8_t *tabB, int64_t *out) {
+    if (!tabA || !tabB || !out) fail("snprel_table_gram: NULL argument");
+    if (c->n_samp <= 0) fail("snprel_table_gram: no genotype workspace");
+    const int64_t cap = c->snp_cap, npad = c->n_samp_pad, n = c->n_samp;
+    DevBuf<uint32_t> tab;
+    tab.alloc((size_t)cap);
+    tab.zero(c->stream);
+    if (c->n_snp > 0)
+        CUDA_CHECK(cudaMemcpyAsync(tab.p, tabA, (size_t)c->n_snp * 4, cudaMemcpyHostToDevice, c->stream));
+    uint32_t tb;
+    memcpy(&tb, tabB, 4);
+    DevBuf<long long> acc;
+    acc.alloc((size_t)npad * npad);
+    acc.zero(c->stream);
+    GramPass p{tab.p, tb, 0, 0};
+    c->hot_launches = 0;
+    gram_tc_run(c, &p, 1, acc.p, false);
+    CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)n * 8, acc.p, (size_t)npad * 8, (size_t)n * 8, (size_t)n,
+                                 cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+}  // namespace snprel
