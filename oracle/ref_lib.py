@@ -1,0 +1,110 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY.
+
+ctypes driver for oracle/_ref/libsnprelate_ref.so: the reference's OWN hot-path
+sources (src/genPCA.cpp, genEIGMIX.cpp, genIBS.cpp, genKING.cpp, genBeta.cpp,
+dGenGWAS.cpp, dVect.cpp, ThreadPool.cpp) compiled unmodified by oracle/Makefile
+against the shim in oracle/ref_shim.  Used to validate the numpy restatement and
+as the CPU baseline (`cpu_baseline.kind = "reference"`)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libsnprelate_ref.so")
+_LIB = None
+
+
+def available() -> bool:
+    return os.path.exists(_PATH)
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(_PATH)
+        _LIB.ref_error.restype = C.c_char_p
+    return _LIB
+
+
+def _ck(rc):
+    if rc != 0:
+        raise RuntimeError(_lib().ref_error().decode())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class RefWorkspace:
+    """Drives the reference like R does: set the genotype space, optionally
+    gnrSelSNP_Base, then the gnr* estimators."""
+
+    def __init__(self, geno: np.ndarray):
+        g = np.ascontiguousarray(geno, dtype=np.uint8)
+        self.nsnp, self.nsamp = g.shape
+        _ck(_lib().ref_set_geno(_p(g), C.c_int(g.shape[0]), C.c_int(g.shape[1])))
+
+    def select_snp_base(self, remove_mono=True, maf=-1.0, missrate=2.0):
+        flags = np.zeros(self.nsnp, dtype=np.uint8)
+        n = C.c_int()
+        _ck(_lib().ref_select_snp_base(int(remove_mono), C.c_double(maf), C.c_double(missrate), _p(flags), C.byref(n)))
+        return flags.astype(bool), n.value
+
+    def dims(self):
+        a, b = C.c_int(), C.c_int()
+        _ck(_lib().ref_dims(C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def grm(self, method="GCTA", nthread=1):
+        n = self.dims()[1]
+        out = np.empty((n, n))
+        _ck(_lib().ref_grm(method.encode(), int(nthread), _p(out)))
+        return out
+
+    def pca(self, nthread=1, bayesian=False, eigen_cnt=0):
+        n = self.dims()[1]
+        genmat = np.empty((n, n))
+        tr = C.c_double()
+        ev = np.empty(n) if eigen_cnt > 0 else None
+        evec = np.empty((eigen_cnt, n)) if eigen_cnt > 0 else None
+        _ck(_lib().ref_pca(int(nthread), int(bayesian), int(eigen_cnt), _p(genmat), C.byref(tr), _p(ev), _p(evec)))
+        return dict(genmat=genmat, TraceXTX=tr.value, eigenval=ev, eigenvect=None if evec is None else evec.T)
+
+    def eigmix(self, nthread=1, diagadj=True):
+        nsnp, n = self.dims()
+        ibd, af = np.empty((n, n)), np.empty(nsnp)
+        _ck(_lib().ref_eigmix(int(nthread), int(diagadj), _p(ibd), _p(af)))
+        return ibd, af
+
+    def ibs_num(self, nthread=1):
+        n = self.dims()[1]
+        o = [np.empty((n, n), dtype=np.int32) for _ in range(3)]
+        _ck(_lib().ref_ibs_num(int(nthread), _p(o[0]), _p(o[1]), _p(o[2])))
+        return o
+
+    def ibs_ave(self, nthread=1):
+        n = self.dims()[1]
+        o = np.empty((n, n))
+        _ck(_lib().ref_ibs_ave(int(nthread), _p(o)))
+        return o
+
+    def king_robust(self, nthread=1, family=None):
+        n = self.dims()[1]
+        a, b = np.empty((n, n)), np.empty((n, n))
+        fam = None if family is None else np.ascontiguousarray(family, dtype=np.int32)
+        _ck(_lib().ref_king_robust(int(nthread), _p(fam), _p(a), _p(b)))
+        return a, b
+
+    def king_homo(self, nthread=1):
+        n = self.dims()[1]
+        a, b = np.empty((n, n)), np.empty((n, n))
+        _ck(_lib().ref_king_homo(int(nthread), _p(a), _p(b)))
+        return a, b
+
+    def indiv_beta(self, nthread=1, inbreeding=True):
+        n = self.dims()[1]
+        o = np.empty((n, n))
+        _ck(_lib().ref_indiv_beta(int(nthread), int(inbreeding), _p(o)))
+        return o

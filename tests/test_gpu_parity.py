@@ -1,0 +1,253 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the
+reference's golden vectors.  Mirrors inst/unitTests/test_rel.R and test_GRM.R.
+
+Tolerances: integer counters bit-exact; GRM-type entries
+|diff| <= 1e-10 * max(|ref|, 1); eigenvectors 1e-6 up to sign."""
+import numpy as np
+import pytest
+
+import snprelate_b200 as S
+from oracle import snprel_oracle as O
+from snprel_testutil import hapmap_subset
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+def relerr(got, ref):
+    return float(np.nanmax(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)))
+
+
+def load(ctx, g):
+    ctx.geno_begin(g.shape[1], g.shape[0])
+    ctx.geno_push_u8(g)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = S.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def gds(hapmap):
+    return S.GenotypeData(hapmap["geno2b"], sample_id=hapmap["sample_id"], snp_id=hapmap["snp_id"],
+                          chromosome=hapmap["chromosome"], packed_2bit=True, n_samp=hapmap["nsamp"])
+
+
+# ---------------------------------------------------------------- goldens (test_rel.R)
+
+def test_ibs_golden(gds, hapmap, goldens):          # test_rel.R:103-129
+    samp = hapmap["sample_id"][:90]
+    r = S.snpgdsIBS(gds, sample_id=samp, missing_rate=float("nan"))
+    assert np.array_equal(r["snp.id"], goldens["ibs_snp_id"])
+    assert np.max(np.abs(r["ibs"] - goldens["ibs"])) == 0.0
+    rp = S.snpgdsIBS(gds, sample_id=samp, missing_rate=float("nan"), useMatrix=True)
+    assert np.array_equal(rp["ibs"]["x"], O.to_packed_upper(r["ibs"]))
+
+
+def test_pca_golden(gds, hapmap, goldens):          # test_rel.R:133-195
+    samp = hapmap["sample_id"][:90]
+    r = S.snpgdsPCA(gds, sample_id=samp, missing_rate=float("nan"), need_genmat=True, eigen_cnt=8)
+    assert relerr(r["genmat"], goldens["pca_genmat"]) < TOL
+    val, vec = O.pca_eigen(goldens["pca_genmat"], 8)
+    assert np.max(np.abs(r["eigenval"][:8] - val)) < 1e-8
+    assert np.all(np.isnan(r["eigenval"][8:]))
+    for k in range(4):          # well separated leading PCs, up to sign
+        d = min(np.max(np.abs(r["eigenvect"][:, k] - vec[:, k])), np.max(np.abs(r["eigenvect"][:, k] + vec[:, k])))
+        assert d < 1e-6
+    assert abs(r["varprop"][0] - r["eigenval"][0] / np.trace(r["genmat"])) < 1e-12
+
+
+def test_king_golden(gds, hapmap, goldens):         # test_rel.R:237-283
+    samp = hapmap["sample_id"][:60]
+    r = S.snpgdsIBDKING(gds, sample_id=samp, missing_rate=float("nan"), type="KING-robust")
+    assert np.array_equal(r["snp.id"], goldens["king_snp_id"])
+    assert np.max(np.abs(r["IBS0"] - goldens["king_robust_ibs0"])) == 0.0
+    assert np.max(np.abs(r["kinship"] - goldens["king_robust_kinship"])) == 0.0
+    h = S.snpgdsIBDKING(gds, sample_id=samp, missing_rate=float("nan"), type="KING-homo")
+    assert relerr(h["k0"], goldens["king_homo_k0"]) < TOL
+    assert relerr(h["k1"], goldens["king_homo_k1"]) < TOL
+
+
+def test_indiv_beta_golden(gds, hapmap, goldens):   # test_rel.R:287-313
+    samp = hapmap["sample_id"][:90]
+    r = S.snpgdsIndivBeta(gds, sample_id=samp, missing_rate=float("nan"))
+    assert relerr(r["beta"], goldens["beta"]) < TOL
+
+
+def test_eigmix_golden(gds, hapmap, goldens):       # test_rel.R:317-339
+    samp = hapmap["sample_id"][:90]
+    r = S.snpgdsEIGMIX(gds, sample_id=samp, missing_rate=float("nan"), ibdmat=True)
+    assert relerr(r["ibd"], goldens["eigmix_ibd"]) < TOL
+
+
+def test_hapmap_config1_all_methods(gds, hapmap):
+    """BASELINE config 1: 279 samples, default filters -> 279 x 8039."""
+    g, _ = hapmap_subset(hapmap, 279, missing_rate=0.01)
+    for method, ref in (("GCTA", O.grm_gcta(g)), ("Eigenstrat", O.grm_eigenstrat(g)),
+                        ("EIGMIX", O.grm_eigmix(g)), ("Corr", O.grm_corr(g)),
+                        ("IndivBeta", O.grm_indivbeta(O.beta_counts(g))[0])):
+        r = S.snpgdsGRM(gds, method=method)
+        assert r["grm"].shape == (279, 279) and len(r["snp.id"]) == 8039
+        assert relerr(r["grm"], ref) < TOL, method
+    w = S.snpgdsGRM(gds, method="Weighted")
+    assert w["method"] == "Weighted"
+    assert relerr(w["grm"], O.grm_eigmix(g)) < TOL
+
+
+def test_grm_merge_identity(gds, hapmap):           # test_GRM.R:15-49
+    g, idx = hapmap_subset(hapmap, 279, missing_rate=0.0)
+    ids = hapmap["snp_id"][idx]
+    parts = [ids[0::3], ids[1::3], ids[2::3]]
+    grms = [S.snpgdsGRM(gds, snp_id=p, missing_rate=0.0, method="GCTA")["grm"] for p in parts]
+    merged = O.merge_grm(grms, [len(p) for p in parts])
+    full = S.snpgdsGRM(gds, snp_id=ids, missing_rate=0.0, method="GCTA")["grm"]
+    assert relerr(merged, full) < TOL
+
+
+# ---------------------------------------------------------------- synthetic vs oracle
+
+@pytest.mark.parametrize("n,m,miss", [(4, 1, 0.0), (17, 33, 0.1), (130, 129, 0.0), (257, 1000, 0.02),
+                                      (513, 777, 0.3), (1000, 4099, 0.005)])
+def test_counts_bit_exact(ctx, n, m, miss):
+    g = O.synth_geno(n, m, seed=n * 7 + m, miss_rate=miss)
+    load(ctx, g)
+    assert np.array_equal(np.stack(ctx.ibs_num()), O.ibs_counts(g))
+    assert np.array_equal(ctx.king_robust_counts(), O.king_robust_counts(g))
+    assert np.array_equal(ctx.indiv_beta_counts(), O.beta_counts(g))
+
+
+@pytest.mark.parametrize("n,m,miss", [(5, 3, 0.0), (130, 129, 0.0), (300, 2000, 0.02), (513, 777, 0.3),
+                                      (1000, 4099, 0.005)])
+def test_grm_family_vs_oracle(ctx, n, m, miss):
+    g = O.synth_geno(n, m, seed=n + m, miss_rate=miss, maf_lo=0.01)
+    load(ctx, g)
+    assert relerr(ctx.grm("GCTA")[0], O.grm_gcta(g)) < TOL
+    assert relerr(ctx.grm("Eigenstrat")[0], O.grm_eigenstrat(g)) < TOL
+    assert relerr(ctx.grm("EIGMIX")[0], O.grm_eigmix(g)) < TOL
+    assert relerr(ctx.grm("Corr")[0], O.grm_corr(g)) < TOL
+    ibd = ctx.eigmix(eigen_cnt=0, diagadj=True, ibdmat=True)
+    ref_ibd, ref_af = O.eigmix_ibd(g, diagadj=True)
+    assert relerr(ibd["ibd"], ref_ibd) < TOL
+    assert np.max(np.abs(ibd["afreq"] - ref_af)) < 1e-15
+    r = ctx.pca(eigen_cnt=2, bayesian=True, need_genmat=True)
+    assert relerr(r["genmat"], O.pca_genmat(g, bayesian=True)[0]) < TOL
+    full, _ = ctx.grm("GCTA")
+    packed, _ = ctx.grm("GCTA", packed=True)
+    assert np.array_equal(packed, O.to_packed_upper(full))
+
+
+def test_estimator_epilogues_vs_oracle(ctx):
+    g = O.synth_geno(200, 1500, seed=9, miss_rate=0.05)
+    load(ctx, g)
+    fam = np.array([(i // 3) if i % 5 else S._lib.NA_INT for i in range(200)], dtype=np.int32)
+    ibs0, kin = ctx.king_robust(fam)
+    r0, rk = O.king_robust(O.king_robust_counts(g), np.where(fam == S._lib.NA_INT, -1, fam))
+    assert np.array_equal(ibs0, r0) and np.allclose(kin, rk, rtol=0, atol=0, equal_nan=True)
+    assert np.array_equal(ctx.ibs_ave(), O.ibs_ave(O.ibs_counts(g)))
+    for inb in (True, False):
+        beta, avg = ctx.indiv_beta(inb)
+        rb, ravg = O.indiv_beta(O.beta_counts(g), inb)
+        assert relerr(beta, rb) < TOL and abs(avg - ravg) < 1e-13
+    k0, k1 = ctx.king_homo()
+    rk0, rk1 = O.king_homo(g)
+    assert relerr(k0, rk0) < TOL and relerr(k1, rk1) < TOL
+    grm, avg = ctx.grm("IndivBeta")
+    rg, ravg = O.grm_indivbeta(O.beta_counts(g))
+    assert relerr(grm, rg) < TOL and abs(avg - ravg) < 1e-13
+
+
+def test_table_gram_exact(ctx):
+    """The tcgen05 kernel alone: exact int64 Gram with random int8 tables."""
+    rng = np.random.default_rng(3)
+    n, m = 700, 3001
+    g = O.synth_geno(n, m, seed=21, miss_rate=0.05)
+    load(ctx, g)
+    tA = rng.integers(-128, 128, size=(m, 4)).astype(np.int8)
+    for tB in (np.array([0, 1, 2, 0], np.int8), np.array([0, 0, 0, 1], np.int8), np.array([-3, 7, 2, -1], np.int8)):
+        gi = g.astype(np.int64)
+        a = np.take_along_axis(tA.astype(np.int64), gi, axis=1)
+        ref = a.T @ tB.astype(np.int64)[gi]
+        assert np.array_equal(ctx.table_gram(tA, tB), ref)
+
+
+def test_degenerate_inputs(ctx):
+    g = O.synth_geno(64, 300, seed=4, miss_rate=0.0)
+    g[:, 5] = 3            # a sample with every genotype missing
+    g[7, :] = 0            # monomorphic SNP
+    g[8, :] = 3            # all-missing SNP
+    g[9, :] = 2
+    load(ctx, g)
+    assert np.array_equal(np.stack(ctx.ibs_num()), O.ibs_counts(g))
+    ibs = ctx.ibs_ave()
+    assert np.isnan(ibs[5, 5]) and np.isnan(ibs[5, 0])          # 0/0, src/genIBS.cpp:472-473
+    assert relerr(ctx.grm("GCTA")[0], O.grm_gcta(g)) < TOL
+    assert relerr(ctx.grm("EIGMIX")[0], O.grm_eigmix(g)) < TOL
+    ibs0, kin = ctx.king_robust()
+    r0, rk = O.king_robust(O.king_robust_counts(g))
+    assert np.array_equal(np.isnan(ibs0), np.isnan(r0)) and np.array_equal(np.isnan(kin), np.isnan(rk))
+
+
+def test_selection_and_ratefreq(ctx, hapmap):
+    g = hapmap["geno"][:, :90]
+    load(ctx, g)
+    af, maf, mr = ctx.snp_ratefreq()
+    s, num = O.snp_stats(g)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        raf = np.where(num > 0, s / (2.0 * num), np.nan)
+    assert np.allclose(af, raf, rtol=0, atol=0, equal_nan=True)
+    assert np.allclose(maf, np.minimum(raf, 1 - raf), rtol=0, atol=0, equal_nan=True)
+    assert np.array_equal(mr, 1 - num / 90.0)
+    sel, nrm = ctx.select_snp_base(True, 0.05, 0.02)
+    ref = O.select_snp_base(g, True, 0.05, 0.02)
+    assert np.array_equal(sel, ref) and nrm == int((~ref).sum())
+    assert np.array_equal(ctx.geno_copy_u8(), g[ref])
+
+
+def test_error_paths(ctx):
+    with pytest.raises(S.SNPRelError, match="Invalid 'method'"):
+        ctx.grm("nope")
+    c2 = S.Context(0)
+    with pytest.raises(S.SNPRelError, match="no genotype workspace"):
+        c2.ibs_ave()
+    c2.geno_begin(8, 4)
+    with pytest.raises(S.SNPRelError, match="capacity"):
+        c2.geno_push_u8(np.zeros((200, 8), np.uint8))
+    c2.close()
+
+
+# ---------------------------------------------------------------- size-independent properties at scale
+
+def test_large_properties(ctx):
+    """N=4096, M=65536: estimator cross-consistency that
+    needs no CPU reference, plus a spot check of entries against the oracle."""
+    n, m = 4096, 65536
+    ctx.geno_begin(n, m)
+    ctx.geno_synth(m, seed=77, miss_rate=0.005)
+    i0, i1, i2 = [x.astype(np.int64) for x in ctx.ibs_num()]
+    kc = ctx.king_robust_counts().astype(np.int64)
+    bc = ctx.indiv_beta_counts().astype(np.int64)
+    nl = i0 + i1 + i2
+    assert np.array_equal(nl, kc[1]) and np.array_equal(nl, bc[1])      # three kernels agree on #jointly valid
+    assert np.array_equal(i0, kc[0])
+    assert np.array_equal(kc[2], i1 + 4 * i0)                           # sum (gi-gj)^2 = #|d|=1 + 4 #|d|=2
+    assert np.array_equal(kc[3], kc[4].T)                               # N1_Aa(i,j) == N2_Aa(j,i)
+    assert np.array_equal(np.diag(i2), np.diag(nl))                     # a sample is IBS2 with itself
+    sub = O.synth_geno(24, m, seed=77, miss_rate=0.005)      # samples 0..23 of the same data set
+    grm, _ = ctx.grm("GCTA")
+    assert np.array_equal(grm, grm.T)
+    # oracle on the 24-sample corner; the all-sample SNP statistics come from the device
+    af, _, mr = ctx.snp_ratefreq()
+    mu = 2 * af
+    w = np.where((af > 0) & (af < 1), 1.0 / (af * (1 - af)), 0.0)
+    z = np.where(sub <= 2, (sub - mu[:, None]) * np.sqrt(w)[:, None], 0.0)
+    poly = (af > 0) & (af < 1)
+    miss = (sub > 2).astype(np.float64) * poly[:, None]
+    mm = (sub > 2).astype(np.float64)
+    den = miss.sum(0)[:, None] + miss.sum(0)[None, :] - miss.T @ mm
+    ref = (z.T @ z) / (2.0 * (poly.sum() - den))
+    assert relerr(grm[:24, :24], ref) < TOL
+    assert np.array_equal(np.stack([i0, i1, i2])[:, :24, :24], O.ibs_counts(sub))

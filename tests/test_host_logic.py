@@ -1,0 +1,55 @@
+"""Host-side mirror of .InitFile2 / family.id handling (R/Internal.R:166-484,
+R/IBD.R:348-372): argument checking and selection logic that runs before any
+device call."""
+import numpy as np
+import pytest
+
+import snprelate_b200 as S
+from snprelate_b200 import api
+
+
+def _gds(nsnp=12, nsamp=6):
+    g = (np.arange(nsnp * nsamp).reshape(nsnp, nsamp) % 3).astype(np.uint8)
+    return S.GenotypeData(g, sample_id=[f"s{i}" for i in range(nsamp)],
+                          snp_id=np.arange(1, nsnp + 1), chromosome=np.r_[np.ones(nsnp - 2), 23, 23])
+
+
+def test_unknown_sample_id_message():
+    with pytest.raises(S.SNPRelError, match="Some of sample.id do not exist!"):
+        S.snpgdsIBS(_gds(), sample_id=["s0", "nope"])
+
+
+def test_unknown_snp_id_message():
+    with pytest.raises(S.SNPRelError, match="Some of snp.id do not exist!"):
+        S.snpgdsGRM(_gds(), snp_id=[1, 99])
+
+
+def test_bad_method_and_type():
+    with pytest.raises(S.SNPRelError):
+        S.snpgdsGRM(_gds(), method="nope")
+    with pytest.raises(S.SNPRelError, match="Invalid 'type'"):
+        S.snpgdsIBDKING(_gds(), type="KING-x")
+    with pytest.raises(S.SNPRelError, match="num.thread"):
+        S.snpgdsIBS(_gds(), num_thread=0)
+
+
+def test_packed_block_decoding():
+    rng = np.random.default_rng(0)
+    g = rng.integers(0, 4, size=(9, 11)).astype(np.uint8)
+    nb = (11 + 3) // 4
+    pad = np.full((9, nb * 4), 3, dtype=np.uint8)
+    pad[:, :11] = g
+    p = pad.reshape(9, nb, 4)
+    packed = (p[:, :, 0] | (p[:, :, 1] << 2) | (p[:, :, 2] << 4) | (p[:, :, 3] << 6)).astype(np.uint8)
+    gd = S.GenotypeData(packed, packed_2bit=True, n_samp=11)
+    mask = np.array([True, False] * 5 + [True])
+    assert np.array_equal(gd.block_u8(np.array([0, 3, 8]), mask), g[[0, 3, 8]][:, mask])
+
+
+def test_family_codes():
+    ws = dict(n_samp=5, sample_id=np.array(["a", "b", "c", "d", "e"]))
+    fam = api._family_codes(["F2", "", "F1", None, "F2"], None, None, ws)
+    assert fam[0] == fam[4] and fam[0] != fam[2]
+    assert fam[1] == api.NA_INT and fam[3] == api.NA_INT
+    with pytest.raises(S.SNPRelError, match="length"):
+        api._family_codes(["x"], None, None, ws)

@@ -1,0 +1,66 @@
+"""The numpy oracle against the reference's OWN sources (oracle/_ref, built by
+oracle/Makefile from /root/reference/src unmodified).  This pins what the
+reference's golden vectors leave open: GCTA / EIGMIX / Corr with missing data,
+KING with family ids, 1 vs several threads (test_rel.R:114-117).  Skipped when
+oracle/_ref has not been built."""
+import numpy as np
+import pytest
+
+from oracle import ref_lib as R
+from oracle import snprel_oracle as O
+from snprel_testutil import hapmap_subset
+
+pytestmark = pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+
+
+@pytest.fixture(scope="module")
+def data():
+    return O.synth_geno(257, 1531, seed=12, miss_rate=0.04, maf_lo=0.005)
+
+
+def test_grm_methods(data):
+    w = R.RefWorkspace(data)
+    for method, ref in (("GCTA", O.grm_gcta(data)), ("Eigenstrat", O.grm_eigenstrat(data)),
+                        ("EIGMIX", O.grm_eigmix(data)), ("Corr", O.grm_corr(data)),
+                        ("IndivBeta", O.grm_indivbeta(O.beta_counts(data))[0])):
+        one = w.grm(method, 1)
+        assert np.max(np.abs(one - ref)) < 1e-12, method
+        assert np.max(np.abs(w.grm(method, 4) - one)) < 1e-12      # thread-count independence
+
+
+def test_integer_estimators(data):
+    w = R.RefWorkspace(data)
+    assert all(np.array_equal(a, b) for a, b in zip(w.ibs_num(3), O.ibs_counts(data)))
+    fam = np.array([(i // 4) if i % 7 else -2147483648 for i in range(data.shape[1])], dtype=np.int32)
+    a, b = w.king_robust(2, fam)
+    ra, rb = O.king_robust(O.king_robust_counts(data), np.where(fam < 0, -1, fam))
+    assert np.array_equal(a, ra) and np.allclose(b, rb, rtol=0, atol=0, equal_nan=True)
+    k0, k1 = w.king_homo(2)
+    r0, r1 = O.king_homo(data)
+    assert np.nanmax(np.abs(k0 - r0)) < 1e-12 and np.nanmax(np.abs(k1 - r1)) < 1e-12
+    for inb in (True, False):
+        assert np.max(np.abs(w.indiv_beta(2, inb) - O.indiv_beta(O.beta_counts(data), inb)[0])) < 1e-12
+
+
+def test_pca_eigmix_and_selection(data):
+    w = R.RefWorkspace(data)
+    r = w.pca(2, False, 6)
+    ref, tr, _ = O.pca_genmat(data)
+    assert np.max(np.abs(r["genmat"] - ref)) < 1e-12 and abs(r["TraceXTX"] - tr) < 1e-8 * tr
+    ev, evec = O.pca_eigen(ref, 6)
+    assert np.max(np.abs(r["eigenval"][:6] - ev)) < 1e-9
+    assert np.max(np.abs(w.pca(2, True, 0)["genmat"] - O.pca_genmat(data, bayesian=True)[0])) < 1e-12
+    ibd, af = w.eigmix(2, True)
+    ri, raf = O.eigmix_ibd(data, True)
+    assert np.max(np.abs(ibd - ri)) < 1e-12 and np.max(np.abs(af - raf)) == 0
+    sel, nrm = w.select_snp_base(True, 0.03, 0.05)
+    assert np.array_equal(sel, O.select_snp_base(data, True, 0.03, 0.05)) and nrm == int((~sel).sum())
+
+
+def test_reference_reproduces_its_own_goldens(hapmap, goldens):
+    g, _ = hapmap_subset(hapmap, 90)
+    w = R.RefWorkspace(g)
+    assert np.max(np.abs(w.ibs_ave(2) - goldens["ibs"])) == 0
+    assert np.max(np.abs(w.pca(2)["genmat"] - goldens["pca_genmat"])) < 1e-12
+    assert np.max(np.abs(w.eigmix(2, True)[0] - goldens["eigmix_ibd"])) < 1e-12
+    assert np.max(np.abs(w.indiv_beta(2, True) - goldens["beta"])) < 1e-12

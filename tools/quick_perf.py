@@ -1,0 +1,21 @@
+"""Quick device-time check of the accumulate phase at a given size (not the bench)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import snprelate_b200 as S
+from snprelate_b200._lib import EST_IBS, EST_KING_ROBUST, EST_BETA
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+m = int(sys.argv[2]) if len(sys.argv) > 2 else 1000000
+ests = sys.argv[3].split(",") if len(sys.argv) > 3 else ["pca", "gcta"]
+miss = float(sys.argv[4]) if len(sys.argv) > 4 else 0.005
+ctx = S.Context(0)
+ctx.geno_begin(n, m)
+t0 = time.time(); ctx.geno_synth(m, miss_rate=miss); print(f"synth {time.time()-t0:.2f}s", flush=True)
+ids = {"pca": 0, "gcta": 1, "eigmix": 3, "ibs": EST_IBS, "king": EST_KING_ROBUST, "beta": EST_BETA}
+for e in ests:
+    t0 = time.time()
+    ms = ctx.time_accumulate(ids[e], 1)
+    wall = time.time() - t0
+    hot, nl, units = ctx.last_hot_kernel()
+    print(f"{e}: N={n} M={m} miss={miss} hot {hot:.1f} ms in {nl} launches, wall {wall*1e3:.1f} ms, "
+          f"{units/hot*1e3:.3e} pair-SNPs/s (hot)", flush=True)
