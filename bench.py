@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: GRM pair-SNPs/sec (N^2*M/2).
+
+Workload at --gpus 1 = BASELINE config[1]: snpgdsPCA covariance on synthetic
+10 000 samples x 1 000 000 SNPs (2-bit packed, 0.5 % missing), one B200, tcgen05
+table-Gram.  A "step" is one full pass of the hot path over that matrix: per-SNP
+statistics, digit tables, per-sample vectors and every tensor-core pass, starting
+from the 2-bit genotypes resident in HBM.  With --gpus N each rank owns a shard of
+the same number of SNPs (weak scaling: N x 1M SNPs in total), accumulates its
+partial N x N planes and one NCCL all-reduce sums them inside the timed step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref: the
+reference's sources compiled unmodified) on a bounded sample of the same workload
+with all host threads.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GRM pair-SNPs/sec (N^2*M/2)"
+UNIT = "pair-SNPs/s"
+N_SAMP = 10000
+N_SNP = 1000000
+MISS = 0.005
+SEED = 20261017
+# bounded CPU sample of the same workload (same generator, same MAF / missing rate)
+CPU_N, CPU_M = 2048, 16384
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if r[3 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(threads, n=CPU_N, m=CPU_M, reps=1):
+    """pair-SNPs/s of the reference's own CPU path (oracle/_ref) for snpgdsPCA's
+    covariance (gnrPCA genmat.only) on an n x m sample of the workload."""
+    from oracle import ref_lib as R
+    from oracle import snprel_oracle as O
+    g = O.synth_geno(n, m, seed=SEED, miss_rate=MISS)
+    w = R.RefWorkspace(g)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        w.pca(threads, False, 0)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return 0.5 * n * n * m / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_lib as R
+    threads = os.cpu_count() or 1
+    kind = "reference" if R.available() else "unavailable"
+    if kind == "unavailable":
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsnprelate_ref.so not built"}))
+        return
+    for _ in range(args.warmup):
+        cpu_reference_rate(threads, 1024, 4096)
+    times = []
+    for _ in range(args.steps):
+        rate, dt = cpu_reference_rate(threads)
+        times.append(dt)
+    dt = sum(times) / len(times)
+    value = 0.5 * CPU_N * CPU_N * CPU_M / dt
+    sample = (f"reference src/genPCA.cpp CExactPCA (gnrPCA genmat.only) compiled -O3 -march=x86-64-v3, "
+              f"{threads} threads, {CPU_N} samples x {CPU_M} SNPs of the same synthetic generator")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(gpus):
+    return {"workload": f"snpgdsPCA covariance (Eigenstrat), synthetic {N_SAMP} samples x {N_SNP} SNPs per GPU, "
+                        f"2-bit packed, missing rate {MISS}, MAF U(0.05,0.5)",
+            "n_samp": N_SAMP, "n_snp_per_gpu": N_SNP, "n_snp_total": N_SNP * gpus, "miss_rate": MISS,
+            "sharding": "SNP blocks per rank, one all-reduce of the int64 partial planes" if gpus > 1 else "single GPU",
+            "l2": "inputs (2.56 GB of 2-bit genotypes per GPU) are larger than the 126 MB L2"}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import snprelate_b200 as S
+    from snprelate_b200 import dist as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    est = 0   # SNPREL_GRM_EIGENSTRAT: snpgdsPCA's covariance
+    ctx = S.Context(local)
+    ctx.geno_begin(N_SAMP, N_SNP)
+    ctx.geno_synth(N_SNP, seed=SEED, miss_rate=MISS, snp_start=rank * N_SNP)
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def step():
+        """one pass of the hot path; returns device ms (library events + collective events)"""
+        if world == 1:
+            return ctx.time_accumulate(est, 1)
+        ctx.invalidate()
+        plan = ctx.plan_local(est)
+        plan = D.reduce_plan(plan, device=dev)
+        ctx.accumulate(est, plan)
+        ms = ctx.last_step_ms()
+        ev0.record()
+        D.allreduce_buffers(ctx.reduce_buffers(), device=dev)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms += ev0.elapsed_time(ev1)
+        return ms
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ctx.kernel_launches()
+    barrier()
+    if sampler:
+        sampler.start()
+    t_wall0 = time.perf_counter()
+    dev_ms, hot_ms, hot_launch = 0.0, 0.0, 0
+    for _ in range(args.steps):
+        dev_ms += step()
+        h, nl, _ = ctx.last_hot_kernel()
+        hot_ms += h
+        hot_launch += nl
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    launches = ctx.kernel_launches() - launches0
+
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(t[0]), float(t[1])
+    ms_per_step = dev_ms / args.steps
+    pair_snps_per_step = 0.5 * N_SAMP * N_SAMP * (N_SNP * world)
+    value = pair_snps_per_step / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the C ABI with HOST buffers (rank-local shard) ----
+    rb = (N_SAMP + 3) // 4
+    host_geno = torch.empty((N_SNP, rb), dtype=torch.uint8, pin_memory=True)
+    ctx.geno_copy_2b(host_geno.numpy())
+    host_out = torch.empty((N_SAMP, N_SAMP), dtype=torch.float64, pin_memory=True)
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_step():
+        ctx.geno_begin(N_SAMP, N_SNP)
+        ctx.geno_push_2b(host_geno.numpy())
+        if world > 1:
+            D.accumulate_sharded(ctx, est, device=dev)
+        ctx.pca(genmat_only=True, genmat_out=host_out.numpy())
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    e2e_s = float(t[0])
+    e2e_value = pair_snps_per_step / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            tdist.destroy_process_group()
+        return
+
+    # ---- top-32 eigenvectors of the covariance (config 2; cuSOLVER, outside the metric) ----
+    eig_ms = None
+    if world == 1 and not args.no_eigen:
+        t0 = time.perf_counter()
+        ctx.pca(eigen_cnt=32)
+        eig_ms = (time.perf_counter() - t0) * 1e3 - ms_per_step
+
+    pk, pk_kind = peaks()
+    hot_per_step_ms = hot_ms / args.steps
+    alg_flops = float(N_SAMP) * N_SAMP * N_SNP           # 2 flop per pair-SNP, symmetric half
+    achieved = alg_flops / (hot_per_step_ms * 1e-3) / 1e12
+    peak = pk.get("bf16_tflops_sustained", 1400.0)
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None,
+                "kernel": "snprel::tc::table_gram_kernel (tcgen05.mma kind::i8)",
+                "launches_per_step": hot_launch // args.steps, "kernel_ms_per_step": hot_per_step_ms,
+                "share_of_step": hot_per_step_ms / ms_per_step,
+                "peak_source": f"bf16_tflops_sustained of {pk_kind} MEASURED_PEAKS.json (kernel timed inside a long step); "
+                               "algorithmic flops = N^2*M; the kernel executes one int8 MMA pass per base-256 digit "
+                               "of the fixed-point weights, see DESIGN.md"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import ref_lib as R
+        if R.available():
+            threads = os.cpu_count() or 1
+            rate, dt = cpu_reference_rate(threads, reps=2)
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "reference",
+                   "sample": f"reference CExactPCA (oracle/_ref) on {CPU_N} samples x {CPU_M} SNPs of the same "
+                             f"generator, {dt:.2f} s"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int8 x int8 -> int32 tensor passes, int64 fixed point (f64-equivalent to 1e-10)",
+        "data": "synthetic", "config": workload_config(world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_geno.numel()) * world,
+                "d2h_bytes_per_step": int(host_out.numel()) * 8,
+                "call": "snprel_geno_begin + snprel_geno_push_2b (pinned host 2-bit rows) + snprel_pca (genmat to host)",
+                "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
+        "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": sampler.summary() if sampler else None,
+        "eigen_top32_ms": eig_ms,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        tdist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-eigen", action="store_true", help="skip the top-32 eigen step")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

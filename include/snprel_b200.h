@@ -74,6 +74,9 @@ int snprel_geno_dim(snprel_ctx *ctx, int64_t *n_samp, int64_t *n_snp);
 /* Copy the workspace back as HOST uint8 [n_snp][n_samp] (gnrCopyGenoMem,
  * src/SNPRelate.cpp:322). */
 int snprel_geno_copy_u8(snprel_ctx *ctx, uint8_t *out);
+/* Copy the workspace back as HOST 2-bit rows (the encoding snprel_geno_push_2b
+ * takes), `row_bytes` >= ceil(n_samp/4) bytes per SNP row. */
+int snprel_geno_copy_2b(snprel_ctx *ctx, uint8_t *out, int64_t row_bytes);
 
 /* gnrSNPRateFreq (src/SNPRelate.cpp:243) / Get_AF_MR_perSNP
  * (src/dGenGWAS.cpp:472-552): per-SNP allele frequency, minor allele frequency
@@ -179,9 +182,16 @@ int64_t snprel_kernel_launches(snprel_ctx *ctx);
  * count of the dominant kernel of the last accumulate call. */
 int snprel_last_hot_kernel(snprel_ctx *ctx, double *ms, int64_t *launches,
                            double *algorithmic_units);
-/* Run the estimator's accumulation `reps` times on the resident workspace and
- * return the average device time per repetition in ms (bench.py `value`). */
+/* Run the estimator's whole accumulation (per-SNP statistics, tables / bit-plane
+ * transpose, pair kernels) `reps` times on the resident 2-bit workspace and return
+ * the average device time per repetition in ms, measured with CUDA events on the
+ * library's stream (bench.py `value`). */
 int snprel_time_accumulate(snprel_ctx *ctx, int estimator, int reps, double *ms);
+/* Device time (ms, CUDA events) of the last snprel_plan_local + snprel_accumulate pair. */
+int snprel_last_step_ms(snprel_ctx *ctx, double *ms);
+/* Drop everything derived from the resident 2-bit matrix (per-SNP statistics, bit
+ * planes, accumulators) so that the next call recomputes it. */
+int snprel_invalidate(snprel_ctx *ctx);
 /* Exact integer table-Gram of the tcgen05 kernel for tests:
  * out[i][j] = sum_l tabA[l][g_il] * tabB[g_jl], int8 tables, int64 out
  * (n_samp x n_samp row-major, all entries). */

@@ -53,6 +53,7 @@ def load_library():
         "snprel_geno_synth": [p, i64, u64, dbl, dbl, dbl, i64],
         "snprel_geno_dim": [p, C.POINTER(i64), C.POINTER(i64)],
         "snprel_geno_copy_u8": [p, p],
+        "snprel_geno_copy_2b": [p, p, i64],
         "snprel_snp_ratefreq": [p, p, p, p],
         "snprel_select_snp_base": [p, i32, dbl, dbl, p, C.POINTER(i64)],
         "snprel_ibs_num": [p, p, p, p],
@@ -72,6 +73,8 @@ def load_library():
         "snprel_mark_reduced": [p],
         "snprel_last_hot_kernel": [p, C.POINTER(dbl), C.POINTER(i64), C.POINTER(dbl)],
         "snprel_time_accumulate": [p, i32, i32, C.POINTER(dbl)],
+        "snprel_last_step_ms": [p, C.POINTER(dbl)],
+        "snprel_invalidate": [p],
         "snprel_table_gram": [p, p, p, p],
         "snprel_debug_flags": [p, u32],
     }
@@ -94,12 +97,12 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "snprel_create", "snprel_destroy", "snprel_last_error", "snprel_version",
     "snprel_geno_begin", "snprel_geno_push_u8", "snprel_geno_push_2b", "snprel_geno_synth",
-    "snprel_geno_dim", "snprel_geno_copy_u8", "snprel_snp_ratefreq", "snprel_select_snp_base",
+    "snprel_geno_dim", "snprel_geno_copy_u8", "snprel_geno_copy_2b", "snprel_snp_ratefreq", "snprel_select_snp_base",
     "snprel_ibs_num", "snprel_ibs_ave", "snprel_king_robust", "snprel_king_robust_counts",
     "snprel_king_homo", "snprel_indiv_beta", "snprel_indiv_beta_counts", "snprel_grm",
     "snprel_pca", "snprel_eigmix", "snprel_plan_local", "snprel_accumulate",
     "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced",
-    "snprel_kernel_launches", "snprel_last_hot_kernel", "snprel_time_accumulate",
+    "snprel_kernel_launches", "snprel_last_hot_kernel", "snprel_time_accumulate", "snprel_last_step_ms", "snprel_invalidate",
     "snprel_table_gram", "snprel_debug_flags",
 ]
 
@@ -171,6 +174,14 @@ class Context:
         self._ck(self.lib.snprel_geno_copy_u8(self.h, _ptr(out)))
         return out
 
+    def geno_copy_2b(self, out=None):
+        n, m = self.geno_dim()
+        rb = (n + 3) // 4
+        if out is None:
+            out = np.empty((m, rb), dtype=np.uint8)
+        self._ck(self.lib.snprel_geno_copy_2b(self.h, _ptr(out), out.shape[1]))
+        return out
+
     def snp_ratefreq(self):
         _, m = self.geno_dim()
         af, maf, mr = (np.empty(m) for _ in range(3))
@@ -240,10 +251,12 @@ class Context:
         self._ck(self.lib.snprel_grm(self.h, GRM_METHODS[method], _ptr(o), int(packed), C.byref(avg)))
         return o, avg.value
 
-    def pca(self, eigen_cnt=32, bayesian=False, need_genmat=False, genmat_only=False):
+    def pca(self, eigen_cnt=32, bayesian=False, need_genmat=False, genmat_only=False, genmat_out=None):
         n, _ = self.geno_dim()
         k = min(int(eigen_cnt), n)
-        genmat = np.empty((n, n)) if (need_genmat or genmat_only) else None
+        genmat = genmat_out
+        if genmat is None and (need_genmat or genmat_only):
+            genmat = np.empty((n, n))
         tx, tv = C.c_double(), C.c_double()
         eigval = eigvec = None
         if not genmat_only:
@@ -300,6 +313,14 @@ class Context:
         ms = C.c_double()
         self._ck(self.lib.snprel_time_accumulate(self.h, int(est), int(reps), C.byref(ms)))
         return ms.value
+
+    def last_step_ms(self):
+        ms = C.c_double()
+        self._ck(self.lib.snprel_last_step_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def invalidate(self):
+        self._ck(self.lib.snprel_invalidate(self.h))
 
     def table_gram(self, tabA, tabB):
         n, m = self.geno_dim()

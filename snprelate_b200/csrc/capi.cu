@@ -63,6 +63,8 @@ int snprel_create(snprel_ctx **out, int device) {
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreate(&c->ev0));
         CUDA_CHECK(cudaEventCreate(&c->ev1));
+        CUDA_CHECK(cudaEventCreate(&c->evs0));
+        CUDA_CHECK(cudaEventCreate(&c->evs1));
     } catch (const Error &err) {
         g_create_error = err.msg;
         delete c;
@@ -78,6 +80,8 @@ void snprel_destroy(snprel_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->evs0) cudaEventDestroy(c->evs0);
+    if (c->evs1) cudaEventDestroy(c->evs1);
     cudaStream_t s = c->stream;
     delete c;   // frees device buffers
     if (s) cudaStreamDestroy(s);
@@ -111,6 +115,10 @@ int snprel_geno_dim(snprel_ctx *c, int64_t *n_samp, int64_t *n_snp) {
 }
 int snprel_geno_copy_u8(snprel_ctx *c, uint8_t *out) {
     API_BEGIN(c) geno_copy_u8(c, out);
+    API_END(c)
+}
+int snprel_geno_copy_2b(snprel_ctx *c, uint8_t *out, int64_t row_bytes) {
+    API_BEGIN(c) geno_copy_2b(c, out, row_bytes);
     API_END(c)
 }
 int snprel_snp_ratefreq(snprel_ctx *c, double *af, double *maf, double *mr) {
@@ -184,9 +192,8 @@ int snprel_eigmix(snprel_ctx *c, int eigen_cnt, int diagadj, double *ibd, double
 // ---- split accumulate / reduce / finish -------------------------------------
 static bool is_cov(int est) { return est >= SNPREL_GRM_EIGENSTRAT && est <= SNPREL_GRM_EIGMIX; }
 
-int snprel_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
-    API_BEGIN(c)
-    if (!plan) fail("snprel_plan_local: NULL plan");
+static void timed_plan(snprel_ctx *c, int est, snprel_plan *plan) {
+    CUDA_CHECK(cudaEventRecord(c->evs0, c->stream));
     if (is_cov(est)) {
         grm_plan_local(c, est == SNPREL_GRM_CORR ? SNPREL_GRM_GCTA : est, plan);
     } else {
@@ -195,10 +202,14 @@ int snprel_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
         plan->max_missing = 0;
         plan->n_snp = c->n_snp;
     }
-    API_END(c)
+    CUDA_CHECK(cudaEventRecord(c->evs1, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, c->evs0, c->evs1));
+    c->plan_ms = ms;
 }
-int snprel_accumulate(snprel_ctx *c, int est, const snprel_plan *plan) {
-    API_BEGIN(c)
+static void timed_accumulate(snprel_ctx *c, int est, const snprel_plan *plan) {
+    CUDA_CHECK(cudaEventRecord(c->evs0, c->stream));
     if (is_cov(est)) {
         if (!plan) fail("snprel_accumulate: covariance estimators need a plan");
         grm_accumulate(c, est, plan);
@@ -207,6 +218,35 @@ int snprel_accumulate(snprel_ctx *c, int est, const snprel_plan *plan) {
     } else {
         fail("snprel_accumulate: unsupported estimator %d", est);
     }
+    CUDA_CHECK(cudaEventRecord(c->evs1, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, c->evs0, c->evs1));
+    c->step_ms = c->plan_ms + ms;
+    c->plan_ms = 0;
+}
+
+int snprel_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
+    API_BEGIN(c)
+    if (!plan) fail("snprel_plan_local: NULL plan");
+    timed_plan(c, est, plan);
+    API_END(c)
+}
+int snprel_accumulate(snprel_ctx *c, int est, const snprel_plan *plan) {
+    API_BEGIN(c) timed_accumulate(c, est, plan);
+    API_END(c)
+}
+int snprel_last_step_ms(snprel_ctx *c, double *ms) {
+    API_BEGIN(c)
+    if (ms) *ms = c->step_ms;
+    API_END(c)
+}
+int snprel_invalidate(snprel_ctx *c) {
+    API_BEGIN(c)
+    c->stat_valid = false;
+    c->planes_valid = false;
+    c->accum_est = -1;
+    c->accum_reduced = false;
     API_END(c)
 }
 int snprel_reduce_buffer_count(snprel_ctx *c) { return c ? (int)c->reduce_list.size() : 0; }
@@ -239,15 +279,14 @@ int snprel_time_accumulate(snprel_ctx *c, int est, int reps, double *ms) {
     if (reps <= 0) fail("snprel_time_accumulate: reps must be positive");
     double total = 0;
     for (int r = 0; r < reps; r++) {
-        if (is_cov(est)) {
-            snprel_plan plan{};
-            plan.frac_bits = -1;
-            grm_plan_local(c, est == SNPREL_GRM_CORR ? SNPREL_GRM_GCTA : est, &plan);
-            grm_accumulate(c, est, &plan);
-        } else {
-            bitcount_accumulate(c, est);
-        }
-        total += c->hot_ms;
+        // everything derived from the resident 2-bit matrix is recomputed inside the timed region
+        c->stat_valid = false;
+        c->planes_valid = false;
+        snprel_plan plan{};
+        plan.frac_bits = -1;
+        timed_plan(c, est, &plan);
+        timed_accumulate(c, est, &plan);
+        total += c->step_ms;
     }
     if (ms) *ms = total / reps;
     API_END(c)

@@ -97,7 +97,7 @@ struct ReduceBuf {
 struct snprel_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs0 = nullptr, evs1 = nullptr;
     std::string err;
     int64_t launches = 0;
     uint32_t debug_flags = 0;
@@ -138,6 +138,8 @@ struct snprel_ctx {
     double hot_ms = 0;
     int64_t hot_launches = 0;
     double hot_units = 0;
+    double step_ms = 0;          // whole plan + accumulate (CUDA events)
+    double plan_ms = 0;
 };
 
 namespace snprel {
@@ -157,6 +159,7 @@ void geno_push_2b(snprel_ctx *c, const uint8_t *host, int64_t cnt, int64_t row_b
 void geno_synth(snprel_ctx *c, int64_t n_snp, uint64_t seed, double maf_lo, double maf_hi,
                 double miss_rate, int64_t snp_start);
 void geno_copy_u8(snprel_ctx *c, uint8_t *out);
+void geno_copy_2b(snprel_ctx *c, uint8_t *out, int64_t row_bytes);
 void geno_pad_tail(snprel_ctx *c);
 void ensure_stats(snprel_ctx *c);
 void snp_ratefreq(snprel_ctx *c, double *af, double *maf, double *mr);

@@ -324,6 +324,18 @@ void geno_copy_u8(snprel_ctx *c, uint8_t *out) {
     }
 }
 
+void geno_copy_2b(snprel_ctx *c, uint8_t *out, int64_t row_bytes_out) {
+    if (c->n_samp <= 0) fail("snprel_geno_copy_2b: no genotype workspace");
+    if (!out) fail("snprel_geno_copy_2b: NULL output");
+    int64_t need = (c->n_samp + 3) / 4;
+    if (row_bytes_out < need) fail("snprel_geno_copy_2b: row_bytes too small");
+    if (c->n_snp == 0) return;
+    int64_t w = std::min(row_bytes_out, c->row_bytes);
+    CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)row_bytes_out, c->geno2b.p, (size_t)c->row_bytes, (size_t)w,
+                                 (size_t)c->n_snp, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
 void ensure_stats(snprel_ctx *c) {
     if (c->n_samp <= 0) fail("no genotype workspace (call snprel_geno_begin first)");
     if (c->stat_valid) return;
@@ -355,7 +367,7 @@ void snp_ratefreq(snprel_ctx *c, double *af, double *maf, double *mr) {
         int num = h[l].num, sum = h[l].sum;
         double f = num > 0 ? (double)sum / (2 * num) : nan;
         if (af) af[l] = f;
-        if (maf) maf[l] = f < 1 - f ? f : (1 - f == 1 - f ? 1 - f : nan);
+        if (maf) maf[l] = num > 0 ? (f < 1 - f ? f : 1 - f) : nan;
         if (mr) mr[l] = 1 - ((double)num) / (double)c->n_samp;
     }
 }

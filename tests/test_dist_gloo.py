@@ -1,0 +1,71 @@
+"""Host-side logic of the multi-GPU path on CPU: SNP shard ranges and the
+plan / buffer reductions, exercised with world_size 2 over gloo."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from snprelate_b200 import dist as D
+from snprelate_b200._lib import Plan
+
+
+def test_shard_ranges_tile_exactly():
+    for n_snp in (0, 1, 127, 128, 129, 1000, 65536, 1000003):
+        for world in (1, 2, 3, 8):
+            ranges = [D.shard_range(n_snp, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n_snp
+            for (a0, a1), (b0, b1) in zip(ranges, ranges[1:]):
+                assert a1 == b0 and a0 <= a1
+            for lo, hi in ranges[:-1]:
+                assert hi % D.SNP_ALIGN == 0 or hi == n_snp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    plan = Plan()
+    plan.max_abs = 10.0 + rank
+    plan.sum_bound = 100.0 * (rank + 1)
+    plan.max_missing = 5 + rank
+    plan.n_snp = 1000 * (rank + 1)
+    plan = D.reduce_plan(plan, device=None)
+    # three buffers of the three kinds the library exposes, as raw host pointers
+    a = np.arange(6, dtype=np.int64) * (rank + 1) - 3
+    b = (np.arange(4, dtype=np.uint32) + 4294967290 + rank).astype(np.uint32)   # wraps mod 2^32
+    c = np.array([0.5, 1.25]) * (rank + 1)
+    bufs = [(a.ctypes.data, a.size, 0), (b.ctypes.data, b.size, 1), (c.ctypes.data, c.size, 2)]
+    D.allreduce_buffers(bufs, device=None)
+    q.put((rank, plan.max_abs, plan.sum_bound, plan.max_missing, plan.n_snp, a.tolist(), b.tolist(), c.tolist()))
+    dist.destroy_process_group()
+
+
+def test_plan_and_buffer_reduction_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    exp_a = ((np.arange(6) * 1 - 3) + (np.arange(6) * 2 - 3)).tolist()
+    exp_b = ((np.arange(4, dtype=np.uint64) + 4294967290) + (np.arange(4, dtype=np.uint64) + 4294967291)) % (1 << 32)
+    for rank, mx, sb, mm, ns, a, b, c in res:
+        assert mx == 11.0 and sb == 300.0 and mm == 11 and ns == 3000
+        assert a == exp_a
+        assert b == exp_b.astype(np.uint32).tolist()
+        assert c == [1.5, 3.75]
