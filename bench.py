@@ -20,7 +20,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -47,43 +46,46 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock / throttle reasons DURING the timed region, read through NVML (the
+    same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints,
+    without spawning a process that contends for the driver lock)."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.sm, self.reasons, self.power = [], set(), []
+        self.max_sm = None
         self.stop_flag = False
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[0].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            return
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 7:
-                continue
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except ValueError:
-                continue
-            for k, nme in enumerate(names):
-                if r[3 + k].lower().startswith("active"):
-                    reasons.add(nme)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(sm),
+                "power_w_max": max(self.power) if self.power else None}
 
 
 def cpu_reference_rate(threads, n=CPU_N, m=CPU_M, reps=1):
@@ -252,6 +254,10 @@ def run_ours(args):
         ctx.pca(eigen_cnt=32)
         eig_ms = (time.perf_counter() - t0) * 1e3 - ms_per_step
 
+    pl = ctx.last_plan()
+    passes = {"digits_per_table": int(pl.digits), "frac_bits": int(pl.frac_bits),
+              "tables": 2 if pl.total_missing > 0 else 1,
+              "tensor_passes_per_step": int(pl.digits) * (2 if pl.total_missing > 0 else 1)}
     pk, pk_kind = peaks()
     hot_per_step_ms = hot_ms / args.steps
     alg_flops = float(N_SAMP) * N_SAMP * N_SNP           # 2 flop per pair-SNP, symmetric half
@@ -260,7 +266,7 @@ def run_ours(args):
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": None,
                 "kernel": "snprel::tc::table_gram_kernel (tcgen05.mma kind::i8)",
-                "launches_per_step": hot_launch // args.steps, "kernel_ms_per_step": hot_per_step_ms,
+                "launches_per_step": hot_launch // args.steps, "fixed_point": passes, "kernel_ms_per_step": hot_per_step_ms,
                 "share_of_step": hot_per_step_ms / ms_per_step,
                 "peak_source": f"bf16_tflops_sustained of {pk_kind} MEASURED_PEAKS.json (kernel timed inside a long step); "
                                "algorithmic flops = N^2*M; the kernel executes one int8 MMA pass per base-256 digit "

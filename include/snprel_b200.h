@@ -148,16 +148,29 @@ int snprel_eigmix(snprel_ctx *ctx, int eigen_cnt, int diagadj, double *ibd,
 #define SNPREL_EST_KING_HOMO    13
 /* estimator ids 0..3 are the SNPREL_GRM_* covariance methods */
 
-/* Per-rank plan statistics of the covariance estimators; all ranks must agree
- * on the fixed-point format, so the host max/sum-reduces these before
- * snprel_accumulate (see snprelate_b200/dist.py). */
+/* Per-rank plan statistics of the covariance estimators.  All ranks must agree on
+ * the fixed-point format, so the host max-reduces max_abs and sum-reduces the other
+ * statistics before snprel_accumulate (see snprelate_b200/dist.py).
+ *
+ * Format choice (grm.cu): every table value v is stored as round(v * 2^frac_bits) and
+ * split into `digits` balanced base-256 digits (one int8 tensor pass each).  The
+ * quantisation error of an output entry is at most 2^-(frac_bits+1) * err_weight, so
+ * the library picks the fewest digits for which that bound is <= tol * scale, where
+ * scale is (a lower bound of) the estimator's normaliser (trace/(n-1), 2 nLocus,
+ * sum 4p(1-p)).  tol defaults to 1e-10. */
 typedef struct snprel_plan {
-    double max_abs;       /* max |table value| over local SNPs            */
-    double sum_bound;     /* sum over local SNPs of the per-SNP magnitude */
-    int64_t max_missing;  /* max over samples of local missing count      */
-    int64_t n_snp;        /* local SNP count                              */
-    int32_t frac_bits;    /* in: <0 = auto; out: chosen                    */
-    int32_t bayesian;     /* Eigenstrat only                              */
+    double max_abs;        /* max |table value| over local SNPs                        */
+    double sum_bound;      /* sum over local SNPs of the per-SNP magnitude (int64 range) */
+    double err_weight;     /* max over samples of (sum of genotypes + #missing)        */
+    double scale;          /* local share of the normaliser of the final matrix        */
+    double tol;            /* in: relative tolerance target (<= 0: 1e-10)              */
+    int64_t total_missing; /* missing genotypes among the selected samples             */
+    int64_t max_missing;   /* max over samples of the local missing count              */
+    int64_t n_snp;         /* local SNP count                                          */
+    int32_t frac_bits;     /* in: < 0 = choose; out (after accumulate): chosen          */
+    int32_t frac_bits_d;   /* fixed point of the missing-pair denominator plane        */
+    int32_t digits;        /* out: digits (tensor passes) per table                    */
+    int32_t bayesian;      /* Eigenstrat only                                          */
 } snprel_plan;
 
 int snprel_plan_local(snprel_ctx *ctx, int estimator, snprel_plan *plan);
@@ -173,6 +186,8 @@ int snprel_reduce_buffer(snprel_ctx *ctx, int idx, void **dev_ptr,
  * snprel_ibs_* / snprel_king_* / snprel_indiv_beta calls above finish from the
  * reduced accumulators instead of accumulating again. */
 int snprel_mark_reduced(snprel_ctx *ctx);
+/* The plan (with the chosen frac_bits / digits) of the last covariance accumulate. */
+int snprel_last_plan(snprel_ctx *ctx, snprel_plan *plan);
 
 /* ---- introspection for benchmarks / tests ------------------------------ */
 

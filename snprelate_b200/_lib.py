@@ -24,9 +24,11 @@ class SNPRelError(RuntimeError):
 
 
 class Plan(C.Structure):
-    _fields_ = [("max_abs", C.c_double), ("sum_bound", C.c_double),
-                ("max_missing", C.c_int64), ("n_snp", C.c_int64),
-                ("frac_bits", C.c_int32), ("bayesian", C.c_int32)]
+    _fields_ = [("max_abs", C.c_double), ("sum_bound", C.c_double), ("err_weight", C.c_double),
+                ("scale", C.c_double), ("tol", C.c_double),
+                ("total_missing", C.c_int64), ("max_missing", C.c_int64), ("n_snp", C.c_int64),
+                ("frac_bits", C.c_int32), ("frac_bits_d", C.c_int32), ("digits", C.c_int32),
+                ("bayesian", C.c_int32)]
 
 
 def library_path() -> str:
@@ -71,6 +73,7 @@ def load_library():
         "snprel_reduce_buffer_count": [p],
         "snprel_reduce_buffer": [p, i32, C.POINTER(p), C.POINTER(i64), C.POINTER(i32)],
         "snprel_mark_reduced": [p],
+        "snprel_last_plan": [p, C.POINTER(Plan)],
         "snprel_last_hot_kernel": [p, C.POINTER(dbl), C.POINTER(i64), C.POINTER(dbl)],
         "snprel_time_accumulate": [p, i32, i32, C.POINTER(dbl)],
         "snprel_last_step_ms": [p, C.POINTER(dbl)],
@@ -101,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "snprel_ibs_num", "snprel_ibs_ave", "snprel_king_robust", "snprel_king_robust_counts",
     "snprel_king_homo", "snprel_indiv_beta", "snprel_indiv_beta_counts", "snprel_grm",
     "snprel_pca", "snprel_eigmix", "snprel_plan_local", "snprel_accumulate",
-    "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced",
+    "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced", "snprel_last_plan",
     "snprel_kernel_launches", "snprel_last_hot_kernel", "snprel_time_accumulate", "snprel_last_step_ms", "snprel_invalidate",
     "snprel_table_gram", "snprel_debug_flags",
 ]
@@ -279,9 +282,11 @@ class Context:
         return dict(eigenval=eigval, eigenvect=None if eigvec is None else eigvec.T, afreq=af, ibd=ibd)
 
     # ---- split accumulate / reduce / finish ----
-    def plan_local(self, est, bayesian=False):
+    def plan_local(self, est, bayesian=False, tol=0.0):
         pl = Plan()
         pl.frac_bits = -1
+        pl.frac_bits_d = -1
+        pl.tol = float(tol)
         pl.bayesian = int(bool(bayesian))
         self._ck(self.lib.snprel_plan_local(self.h, int(est), C.byref(pl)))
         return pl
@@ -296,6 +301,11 @@ class Context:
             self._ck(self.lib.snprel_reduce_buffer(self.h, i, C.byref(ptr), C.byref(cnt), C.byref(kind)))
             out.append((ptr.value, cnt.value, kind.value))
         return out
+
+    def last_plan(self):
+        pl = Plan()
+        self._ck(self.lib.snprel_last_plan(self.h, C.byref(pl)))
+        return pl
 
     def mark_reduced(self):
         self._ck(self.lib.snprel_mark_reduced(self.h))

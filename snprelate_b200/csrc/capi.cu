@@ -199,6 +199,9 @@ static void timed_plan(snprel_ctx *c, int est, snprel_plan *plan) {
     } else {
         plan->max_abs = 0;
         plan->sum_bound = 0;
+        plan->err_weight = 0;
+        plan->scale = 0;
+        plan->total_missing = 0;
         plan->max_missing = 0;
         plan->n_snp = c->n_snp;
     }
@@ -234,6 +237,12 @@ int snprel_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
 }
 int snprel_accumulate(snprel_ctx *c, int est, const snprel_plan *plan) {
     API_BEGIN(c) timed_accumulate(c, est, plan);
+    API_END(c)
+}
+int snprel_last_plan(snprel_ctx *c, snprel_plan *plan) {
+    API_BEGIN(c)
+    if (!plan) fail("snprel_last_plan: NULL plan");
+    *plan = c->plan;
     API_END(c)
 }
 int snprel_last_step_ms(snprel_ctx *c, double *ms) {
@@ -284,6 +293,7 @@ int snprel_time_accumulate(snprel_ctx *c, int est, int reps, double *ms) {
         c->planes_valid = false;
         snprel_plan plan{};
         plan.frac_bits = -1;
+        plan.frac_bits_d = -1;
         timed_plan(c, est, &plan);
         timed_accumulate(c, est, &plan);
         total += c->step_ms;

@@ -133,6 +133,14 @@ struct snprel_ctx {
     snprel::DevBuf<long long> iscalars;   // global int64 scalars (nLocus, ...)
     snprel_plan plan{};
     std::vector<snprel::ReduceBuf> reduce_list;
+    // persistent scratch of the accumulate step (no cudaMalloc / cudaFree in the hot path)
+    snprel::DevBuf<uint32_t> scr_tab;     // digit tables [npass][snp_cap]
+    snprel::DevBuf<int> scr_flags;        // [0] digit overflow, [1] pipeline error
+    snprel::DevBuf<double> scr_plan;      // plan statistics [3]
+    snprel::DevBuf<int2> scr_tiles;       // tile work list
+    snprel::DevBuf<int> scr_cnt;          // per-sample genotype sum / missing count [2][npad]
+    std::vector<int> host_cnt;
+    std::vector<int2> host_tiles;
 
     // hot-kernel bookkeeping for bench.py
     double hot_ms = 0;

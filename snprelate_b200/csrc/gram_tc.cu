@@ -159,6 +159,13 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
                  "r"(d)
                  : "memory");
 }
+// volatile so that the prefetch really is issued one stage ahead (a plain __ldg gets
+// sunk by the compiler to its first use, exposing the full L2 latency every stage)
+__device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t *p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ uint4 ld_nc_v4(const uint8_t *p) {
     uint4 r;
     asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -288,7 +295,7 @@ __global__ void __launch_bounds__(THREADS, 1) table_gram_kernel(const __grid_con
         uint4 na = ld_nc_v4(ap), nb0 = ld_nc_v4(bp), nb1 = ld_nc_v4(bp + 16);
         uint32_t nt[NP];
 #pragma unroll
-        for (int q = 0; q < NP; q++) nt[q] = __ldg(ta[q]);
+        for (int q = 0; q < NP; q++) nt[q] = ld_nc_u32(ta[q]);
 
         const uint32_t a_off = kg * A_LBO + (half * 4) * CORE_SBO + r * 16;
         const uint32_t b_off = MAXP * A_BYTES + kg * B_LBO + (half * 8) * CORE_SBO + r * 16;
@@ -309,7 +316,7 @@ __global__ void __launch_bounds__(THREADS, 1) table_gram_kernel(const __grid_con
 #pragma unroll
                 for (int q = 0; q < NP; q++) {
                     ta[q] += SK;
-                    nt[q] = __ldg(ta[q]);
+                    nt[q] = ld_nc_u32(ta[q]);
                 }
             }
             mbar_wait(empty_bar(s), phase ^ 1u, P.error_flag, 2);
@@ -382,17 +389,18 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     geno_pad_tail(c);
     const int64_t n = c->n_samp, npad = c->n_samp_pad;
     const int tiles_m = (int)((n + TM - 1) / TM), tiles_n = (int)((n + TN - 1) / TN);
-    std::vector<int2> tiles;
+    std::vector<int2> &tiles = c->host_tiles;
+    tiles.clear();
     for (int tm = 0; tm < tiles_m; tm++)
         for (int tn = 0; tn < tiles_n; tn++)
             if (!upper_only || (int64_t)tn * TN + TN - 1 >= (int64_t)tm * TM) tiles.push_back(make_int2(tm, tn));
-    DevBuf<int2> dtiles;
+    DevBuf<int2> &dtiles = c->scr_tiles;
     dtiles.alloc(tiles.size());
     CUDA_CHECK(cudaMemcpyAsync(dtiles.p, tiles.data(), tiles.size() * sizeof(int2),
                                cudaMemcpyHostToDevice, c->stream));
-    DevBuf<int> derr;
-    derr.alloc(1);
-    derr.zero(c->stream);
+    c->scr_flags.alloc(2);
+    int *derr = c->scr_flags.p + 1;
+    CUDA_CHECK(cudaMemsetAsync(derr, 0, sizeof(int), c->stream));
 
     const int stages_total = (int)(round_up(std::max<int64_t>(c->n_snp, 1), SK) / SK);
     // split the SNP range when the tile list alone cannot fill the SMs
@@ -435,7 +443,7 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
         P.stages_per_split = sps;
         P.upper_only = upper_only ? 1 : 0;
         P.flags = c->debug_flags;
-        P.error_flag = derr.p;
+        P.error_flag = derr;
         int np = 0;
         for (int j = i; j < npass && np < MAXP; j++) {
             if (used[j] || passes[j].tabB != passes[i].tabB) continue;
@@ -456,7 +464,7 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     }
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     int herr = 0;
-    CUDA_CHECK(cudaMemcpy(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost));
     if (herr) fail("table_gram_kernel: pipeline barrier %d timed out", herr);
 }
 

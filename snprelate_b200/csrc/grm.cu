@@ -32,13 +32,16 @@ constexpr uint32_t TABB_X = 0x00020100u;   // x channel: code -> {0,1,2,0}
 constexpr uint32_t TABB_M = 0x01000000u;   // m channel: code -> {0,0,0,1}
 constexpr int MAX_DIGITS = 8;
 
-enum { VEC_W = 0, VEC_D = 1, VEC_HET = 2, VEC_D2 = 3, NVEC = 4 };
+enum { VEC_W = 0, VEC_D = 1, VEC_HET = 2, VEC_D2 = 3, VEC_WLO = 4, NVEC = 5 };
+constexpr int W_EXTRA_BITS = 20;   // the per-sample W vector carries 20 more fractional bits than the passes
 // scalars[]: 0 = sum of d_l (EIGMIX SumDenominator / KING-homo sum p(1-p)), 1 = sum d2_l
 // iscalars[]: 0 = nLocus (GCTA), 1 = total missing genotypes (valid samples only)
 
 struct SnpTables {
     long long qU[4];   // fixed-point U
     long long qW[4];   // fixed-point W
+    long long qWx[4];  // fixed-point W with W_EXTRA_BITS more fractional bits (per-sample vector only)
+    double diag;       // sum over samples of U[g] (g - mu): this SNP's contribution to trace(C)
     long long qD;      // fixed-point d (GCTA: 0/1 unscaled; EIGMIX / KING-homo: 2^frac_bits scaled)
     long long qD2;     // KING-homo: (p(1-p))^2
     double d, d2;      // float64 d, d2 (for the global scalars)
@@ -47,8 +50,10 @@ struct SnpTables {
 
 // est: SNPREL_GRM_EIGENSTRAT / GCTA / CORR / EIGMIX, or SNPREL_EST_KING_HOMO
 __device__ __forceinline__ void snp_tables(const SnpStat st, int est, int bayesian, int frac_bits,
-                                           SnpTables &t) {
+                                           int frac_bits_d, SnpTables &t) {
     const double sc = exp2((double)frac_bits);
+    const double scd = exp2((double)frac_bits_d);
+    const double scx = exp2((double)(frac_bits + W_EXTRA_BITS));
     double mu = st.num > 0 ? (double)st.sum / (double)st.num : 0.0;   // DivideGeno, src/genPCA.cpp:98-142
     double w = 0, d = 0, d2 = 0;
     long long qD = 0, qD2 = 0;
@@ -56,13 +61,13 @@ __device__ __forceinline__ void snp_tables(const SnpStat st, int est, int bayesi
         w = 1.0;
         double af = 0.5 * mu;
         d = 4 * af * (1 - af);                    // src/genEIGMIX.cpp:116-119
-        qD = llrint(d * sc);
+        qD = llrint(d * scd);
     } else if (est == SNPREL_EST_KING_HOMO) {
         double p = st.num > 0 ? 0.5 * (double)st.sum / (double)st.num : 0.0;   // src/genKING.cpp:239-241
         d = p * (1 - p);
         d2 = d * d;
-        qD = llrint(d * sc);
-        qD2 = llrint(d2 * sc);
+        qD = llrint(d * scd);
+        qD2 = llrint(d2 * scd);
     } else {
         if (bayesian) {                           // src/genPCA.cpp:445-452
             double s = ((double)st.sum + 1.0) / (double)(2 * st.num + 2);
@@ -81,17 +86,23 @@ __device__ __forceinline__ void snp_tables(const SnpStat st, int est, int bayesi
     }
     t.maxU = 0;
     t.maxW = 0;
+    const int n2 = (st.sum - st.n1) / 2, n0 = st.num - st.n1 - n2;
+    const double cnt[3] = {(double)n0, (double)st.n1, (double)n2};
+    t.diag = 0;
 #pragma unroll
     for (int g = 0; g < 3; g++) {
         double u = (est == SNPREL_EST_KING_HOMO) ? 0.0 : w * ((double)g - mu);
         double ww = mu * u;
         t.qU[g] = llrint(u * sc);
         t.qW[g] = llrint(ww * sc);
+        t.qWx[g] = llrint(ww * scx);
         t.maxU = fmax(t.maxU, fabs(u));
         t.maxW = fmax(t.maxW, fabs(ww));
+        t.diag += cnt[g] * u * ((double)g - mu);
     }
     t.qU[3] = 0;
     t.qW[3] = 0;
+    t.qWx[3] = 0;
     t.qD = qD;
     t.qD2 = qD2;
     t.d = d;
@@ -105,28 +116,37 @@ __device__ __forceinline__ uint32_t digit_of(long long &q) {
 }
 
 // ---- plan statistics ---------------------------------------------------------
+// out[0] max |table value|, out[1] int64-range bound, out[2] total missing,
+// out[3] local share of the normaliser (trace(C) / nLocus / sum d / sum d2)
 __global__ void plan_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int64_t n_samp, int est,
-                            int bayesian, double *__restrict__ out /*[3]: max_abs, sum_bound, total_missing*/) {
-    double mx = 0, sb = 0, tm = 0;
+                            int bayesian, double *__restrict__ out) {
+    double mx = 0, sb = 0, tm = 0, sc = 0;
     for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n_snp;
          l += (int64_t)gridDim.x * blockDim.x) {
         SnpTables t;
-        snp_tables(st[l], est, bayesian, 0, t);
-        double dmax = (est == SNPREL_GRM_EIGMIX || est == SNPREL_EST_KING_HOMO) ? fmax(t.d, t.d2) : 0.0;
-        mx = fmax(mx, fmax(fmax(t.maxU, t.maxW), dmax));
+        snp_tables(st[l], est, bayesian, 0, 0, t);
+        const bool realD = (est == SNPREL_GRM_EIGMIX || est == SNPREL_EST_KING_HOMO);
+        double dmax = realD ? fmax(t.d, t.d2) : 0.0;
+        mx = fmax(mx, fmax(t.maxU, t.maxW));
         sb += 2 * t.maxU + 2 * t.maxW + 2 * dmax;
         tm += (double)(n_samp - st[l].num);
+        if (est == SNPREL_GRM_EIGENSTRAT) sc += t.diag;
+        else if (est == SNPREL_GRM_EIGMIX) sc += t.d;
+        else if (est == SNPREL_EST_KING_HOMO) sc += t.d2;
+        else sc += t.d;   // GCTA: number of polymorphic SNPs
     }
-    __shared__ double s0[256], s1[256], s2[256];
+    __shared__ double s0[256], s1[256], s2[256], s3[256];
     s0[threadIdx.x] = mx;
     s1[threadIdx.x] = sb;
     s2[threadIdx.x] = tm;
+    s3[threadIdx.x] = sc;
     __syncthreads();
     for (int o = blockDim.x / 2; o; o >>= 1) {
         if (threadIdx.x < o) {
             s0[threadIdx.x] = fmax(s0[threadIdx.x], s0[threadIdx.x + o]);
             s1[threadIdx.x] += s1[threadIdx.x + o];
             s2[threadIdx.x] += s2[threadIdx.x + o];
+            s3[threadIdx.x] += s3[threadIdx.x + o];
         }
         __syncthreads();
     }
@@ -134,13 +154,57 @@ __global__ void plan_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int64
         atomicMax(reinterpret_cast<unsigned long long *>(out), (unsigned long long)__double_as_longlong(s0[0]));
         atomicAdd(out + 1, s1[0]);
         atomicAdd(out + 2, s2[0]);
+        atomicAdd(out + 3, s3[0]);
+    }
+}
+
+// per-sample genotype sum and missing count (error weight of the fixed-point format)
+constexpr int SC_SNPS = 2048;
+__global__ void __launch_bounds__(128)
+sample_count_kernel(const uint8_t *__restrict__ geno, int64_t n_snp, int64_t row_bytes, int64_t npad,
+                    int *__restrict__ cnt /*[2][npad]: sum x, #missing*/) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= row_bytes) return;
+    const int64_t l0 = (int64_t)blockIdx.y * SC_SNPS;
+    const int nl = (int)min((int64_t)SC_SNPS, n_snp - l0);
+    const uint8_t *p = geno + l0 * row_bytes + b;
+    // byte-sliced counters: each 2-bit field of a byte counted in its own 8-bit lane
+    uint32_t c1 = 0, c2 = 0, c3 = 0;   // four 8-bit lanes each: #code1, #code2, #code3
+    int s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, s3[4] = {0, 0, 0, 0};
+    for (int s = 0; s < nl; s++) {
+        uint32_t v = p[(int64_t)s * row_bytes];
+        // spread the four 2-bit codes of the byte to the low bits of four byte lanes
+        uint32_t w = (v | (v << 6) | (v << 12) | (v << 18)) & 0x03030303u;
+        uint32_t lo = w & 0x01010101u, hi = (w >> 1) & 0x01010101u;
+        c1 += lo & ~hi;
+        c2 += hi & ~lo;
+        c3 += lo & hi;
+        if ((s & 127) == 127) {   // flush before an 8-bit lane can overflow
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                s1[k] += (c1 >> (8 * k)) & 255;
+                s2[k] += (c2 >> (8 * k)) & 255;
+                s3[k] += (c3 >> (8 * k)) & 255;
+            }
+            c1 = c2 = c3 = 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        s1[k] += (c1 >> (8 * k)) & 255;
+        s2[k] += (c2 >> (8 * k)) & 255;
+        s3[k] += (c3 >> (8 * k)) & 255;
+        int64_t i = b * 4 + k;
+        int sx = s1[k] + 2 * s2[k];
+        if (sx) atomicAdd(cnt + i, sx);
+        if (s3[k]) atomicAdd(cnt + npad + i, s3[k]);
     }
 }
 
 // ---- digit tables: tab[pass][snp] ------------------------------------------
 // pass order: U digits (nU), W digits (nW), D digits (nD), D2 digits (nD2)
 __global__ void tables_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int64_t cap, int est,
-                              int bayesian, int frac_bits, int nU, int nW, int nD, int nD2,
+                              int bayesian, int frac_bits, int frac_bits_d, int nU, int nW, int nD, int nD2,
                               uint32_t *__restrict__ tab, double *__restrict__ scalars,
                               long long *__restrict__ iscalars, int *__restrict__ overflow) {
     int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -148,7 +212,7 @@ __global__ void tables_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int
     long long poly = 0;
     if (l < n_snp) {
         SnpTables t;
-        snp_tables(st[l], est, bayesian, frac_bits, t);
+        snp_tables(st[l], est, bayesian, frac_bits, frac_bits_d, t);
         d = t.d;
         d2 = t.d2;
         poly = (est == SNPREL_GRM_GCTA || est == SNPREL_GRM_CORR) ? t.qD : 0;
@@ -203,23 +267,27 @@ __global__ void tables_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int
 constexpr int SS_SNPS = 512;   // SNPs per block
 __global__ void __launch_bounds__(128)
 sample_sum_kernel(const uint8_t *__restrict__ geno, const SnpStat *__restrict__ st, int64_t n_snp,
-                  int64_t row_bytes, int64_t npad, int est, int bayesian, int frac_bits,
+                  int64_t row_bytes, int64_t npad, int est, int bayesian, int frac_bits, int frac_bits_d,
                   long long *__restrict__ vec) {
-    __shared__ long long tW[SS_SNPS][4];
+    __shared__ long long tW[SS_SNPS][4];    // hi part of the extended-precision W (units 2^-frac_bits)
+    __shared__ int tWlo[SS_SNPS][4];        // lo part (W_EXTRA_BITS bits, non-negative)
     __shared__ long long tD[SS_SNPS], tD2[SS_SNPS];
     const int64_t l0 = (int64_t)blockIdx.y * SS_SNPS;
     const int nl = (int)min((int64_t)SS_SNPS, n_snp - l0);
     for (int s = threadIdx.x; s < nl; s += blockDim.x) {
         SnpTables t;
-        snp_tables(st[l0 + s], est, bayesian, frac_bits, t);
-        for (int g = 0; g < 4; g++) tW[s][g] = t.qW[g];
+        snp_tables(st[l0 + s], est, bayesian, frac_bits, frac_bits_d, t);
+        for (int g = 0; g < 4; g++) {
+            tW[s][g] = t.qWx[g] >> W_EXTRA_BITS;
+            tWlo[s][g] = (int)(t.qWx[g] & ((1ll << W_EXTRA_BITS) - 1));
+        }
         tD[s] = t.qD;
         tD2[s] = t.qD2;
     }
     __syncthreads();
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // byte column (4 samples)
     if (b >= row_bytes) return;
-    long long aw[4] = {0, 0, 0, 0}, ad[4] = {0, 0, 0, 0}, ad2[4] = {0, 0, 0, 0};
+    long long aw[4] = {0, 0, 0, 0}, awl[4] = {0, 0, 0, 0}, ad[4] = {0, 0, 0, 0}, ad2[4] = {0, 0, 0, 0};
     int ah[4] = {0, 0, 0, 0};
     const uint8_t *p = geno + l0 * row_bytes + b;
     for (int s = 0; s < nl; s++) {
@@ -229,6 +297,7 @@ sample_sum_kernel(const uint8_t *__restrict__ geno, const SnpStat *__restrict__ 
         for (int k = 0; k < 4; k++) {
             uint32_t code = (v >> (2 * k)) & 3;
             aw[k] += tW[s][code];
+            awl[k] += tWlo[s][code];
             if (code == 3) {
                 ad[k] += dd;
                 ad2[k] += dd2;
@@ -240,7 +309,9 @@ sample_sum_kernel(const uint8_t *__restrict__ geno, const SnpStat *__restrict__ 
     for (int k = 0; k < 4; k++) {
         int64_t i = b * 4 + k;
         unsigned long long *o = reinterpret_cast<unsigned long long *>(vec);
+        // W vector: hi part in units of 2^-frac_bits, lo part carries W_EXTRA_BITS more bits
         if (aw[k]) atomicAdd(o + VEC_W * npad + i, (unsigned long long)aw[k]);
+        if (awl[k]) atomicAdd(o + VEC_WLO * npad + i, (unsigned long long)awl[k]);
         if (ad[k]) atomicAdd(o + VEC_D * npad + i, (unsigned long long)ad[k]);
         if (ah[k]) atomicAdd(o + VEC_HET * npad + i, (unsigned long long)(long long)ah[k]);
         if (ad2[k]) atomicAdd(o + VEC_D2 * npad + i, (unsigned long long)ad2[k]);
@@ -248,85 +319,144 @@ sample_sum_kernel(const uint8_t *__restrict__ geno, const SnpStat *__restrict__ 
 }
 
 // ---- helpers ---------------------------------------------------------------
-static int digits_needed(double max_abs, int frac_bits) {
-    if (!(max_abs > 0)) return 1;
-    // |q| <= max_abs * 2^f + 0.5 must be representable with balanced digits:
-    // K digits cover |q| <= (2^(8K) - 1) / 2 - 128 ...  use a safe margin of one bit
-    double bits = std::log2(max_abs) + frac_bits + 2.0;
-    int k = (int)std::ceil(bits / 8.0);
-    return std::max(1, std::min(k, MAX_DIGITS));
+// largest frac_bits such that |round(max_abs * 2^f)| fits K balanced base-256 digits
+// (K digits cover [-128, 127] * (256^K - 1) / 255)
+static int frac_cap(double max_abs, int K) {
+    if (!(max_abs > 0)) return 60;
+    double lim = 127.0 * (std::pow(256.0, K) - 1.0) / 255.0 - 1.0;
+    return (int)std::floor(std::log2(lim / max_abs));
+}
+static int digits_for(double max_abs, int frac_bits) {
+    for (int K = 1; K <= MAX_DIGITS; K++)
+        if (frac_cap(max_abs, K) >= frac_bits) return K;
+    fail("fixed-point format needs more than %d digits (max |value| %.3g, %d fractional bits)", MAX_DIGITS,
+         max_abs, frac_bits);
 }
 
 void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
     if (!plan) fail("snprel_plan_local: NULL plan");
     ensure_stats(c);
-    DevBuf<double> out;
-    out.alloc(3);
+    const int64_t npad = c->n_samp_pad;
+    DevBuf<double> &out = c->scr_plan;
+    out.alloc(4);
     out.zero(c->stream);
+    c->scr_cnt.alloc((size_t)2 * npad);
+    c->scr_cnt.zero(c->stream);
     if (c->n_snp > 0) {
         int blocks = (int)std::min<int64_t>((c->n_snp + 255) / 256, 1024);
         plan_kernel<<<blocks, 256, 0, c->stream>>>(c->stat.p, c->n_snp, c->n_samp, est,
                                                    plan->bayesian, out.p);
         KERNEL_CHECK(c);
+        dim3 grid((unsigned)((c->row_bytes + 127) / 128), (unsigned)((c->n_snp + SC_SNPS - 1) / SC_SNPS));
+        sample_count_kernel<<<grid, 128, 0, c->stream>>>(c->geno2b.p, c->n_snp, c->row_bytes, npad,
+                                                         c->scr_cnt.p);
+        KERNEL_CHECK(c);
     }
-    double h[3];
+    double h[4];
+    c->host_cnt.resize((size_t)2 * npad);
     CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->host_cnt.data(), c->scr_cnt.p, (size_t)2 * npad * sizeof(int),
+                               cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    long long ew = 0, mm = 0;
+    for (int64_t i = 0; i < c->n_samp; i++) {
+        long long sx = c->host_cnt[i], ms = c->host_cnt[npad + i];
+        ew = std::max(ew, sx + ms);
+        mm = std::max(mm, ms);
+    }
     plan->max_abs = h[0];
     plan->sum_bound = h[1];
-    plan->max_missing = (int64_t)h[2];
+    plan->total_missing = (int64_t)h[2];
+    plan->scale = (est == SNPREL_GRM_EIGENSTRAT) ? h[3] / (double)std::max<int64_t>(c->n_samp - 1, 1)
+                  : (est == SNPREL_GRM_GCTA)     ? 2.0 * h[3]
+                                                 : h[3];
+    plan->err_weight = (est == SNPREL_EST_KING_HOMO) ? 0.0 : (double)ew;
+    plan->max_missing = mm;
     plan->n_snp = c->n_snp;
 }
 
-// choose frac_bits from the (global) plan statistics
-static int choose_frac_bits(const snprel_plan *plan) {
-    if (plan->frac_bits >= 0) return plan->frac_bits;
-    const int target = 40;
-    int head = 61 - (int)std::ceil(std::log2(std::max(plan->sum_bound, 1.0)));
-    int f = std::min(target, head);
-    if (f < 20) fail("fixed-point accumulator cannot hold this data set (sum bound %.3g)", plan->sum_bound);
-    return f;
+// Choose the fixed-point formats from the (global) plan statistics.
+//   numerator plane: quantisation error of an entry <= 2^-(f+1) * err_weight, wanted <= tol * scale
+//   denominator plane (EIGMIX / KING-homo): error <= 2^-(fd+1) * 2 max_missing, wanted <= tol * scale
+static void choose_format(int est, snprel_plan &plan, int &nU, int &nD) {
+    const double tol = (plan.tol > 0 ? plan.tol : 1e-10) * 0.9;   // 10 % left for float64 rounding in the epilogue
+    const bool homo = est == SNPREL_EST_KING_HOMO;
+    const int head = 61 - (int)std::ceil(std::log2(std::max(plan.sum_bound, 1.0)));   // int64 plane headroom
+    if (head < 16) fail("fixed-point accumulator cannot hold this data set (sum bound %.3g)", plan.sum_bound);
+    double scale = plan.scale;
+    if (est == SNPREL_GRM_GCTA) scale -= 4.0 * (double)plan.max_missing;   // 2 (nLocus - D_ij), D_ij <= 2 max_missing
+    if (est == SNPREL_GRM_EIGMIX) scale -= 2.0 * (double)plan.max_missing;
+    nU = 0;
+    if (!homo) {
+        int f = plan.frac_bits;
+        if (f < 0) {
+            int f_req = 24;
+            if (plan.err_weight > 0 && scale > 0)
+                f_req = (int)std::ceil(std::log2(plan.err_weight / (tol * scale))) - 1;
+            f_req = std::max(16, std::min(f_req, head));
+            nU = digits_for(plan.max_abs, f_req);
+            f = std::min(std::min(frac_cap(plan.max_abs, nU), head), 50);   // use every bit the digits offer
+        } else {
+            nU = digits_for(plan.max_abs, f);
+        }
+        plan.frac_bits = f;
+        plan.digits = nU;
+    } else {
+        plan.frac_bits = 0;
+        plan.digits = 0;
+    }
+    nD = 0;
+    plan.frac_bits_d = std::max(plan.frac_bits_d, 0);
+    if (plan.total_missing > 0) {
+        if (est == SNPREL_GRM_GCTA) {
+            nD = 1;               // d in {0,1}: exact integers
+            plan.frac_bits_d = 0;
+        } else if (est == SNPREL_GRM_EIGMIX || homo) {
+            double dmax = homo ? 0.25 : 1.0;
+            int fd_req = 24;
+            if (scale > 0)
+                fd_req = (int)std::ceil(std::log2(std::max(2.0 * (double)plan.max_missing, 1.0) / (tol * scale))) - 1;
+            fd_req = std::max(16, std::min(fd_req, head));
+            nD = digits_for(dmax, fd_req);
+            plan.frac_bits_d = std::min(std::min(frac_cap(dmax, nD), head), 50);
+        }
+    }
 }
 
 void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     if (est == SNPREL_GRM_CORR) est = SNPREL_GRM_GCTA;
     ensure_stats(c);
     snprel_plan plan = *plan_in;
-    const int f = choose_frac_bits(&plan);
-    plan.frac_bits = f;
-    const bool any_missing = plan.max_missing > 0;
     const bool homo = est == SNPREL_EST_KING_HOMO;
-    int nU = homo ? 0 : digits_needed(plan.max_abs, f);
+    int nU = 0, nD = 0;
+    choose_format(est, plan, nU, nD);
+    const int f = plan.frac_bits, fd = plan.frac_bits_d;
+    const bool any_missing = plan.total_missing > 0;
     int nW = (!homo && any_missing) ? nU : 0;
-    int nD = 0, nD2 = 0;
-    if (any_missing) {
-        if (est == SNPREL_GRM_GCTA) nD = 1;
-        if (est == SNPREL_GRM_EIGMIX) nD = digits_needed(1.0, f);
-        if (homo) nD = nD2 = digits_needed(0.25, f);
-    }
+    int nD2 = homo ? nD : 0;
     const int npass = nU + nW + nD + nD2;
     const int64_t cap = c->snp_cap, npad = c->n_samp_pad;
 
-    DevBuf<uint32_t> tab;
+    DevBuf<uint32_t> &tab = c->scr_tab;
     tab.alloc((size_t)std::max(npass, 1) * cap);
     tab.zero(c->stream);
     c->scalars.alloc(4);
     c->scalars.zero(c->stream);
     c->iscalars.alloc(4);
     c->iscalars.zero(c->stream);
-    DevBuf<int> ovf;
-    ovf.alloc(1);
+    DevBuf<int> &ovf = c->scr_flags;
+    ovf.alloc(2);
     ovf.zero(c->stream);
     if (c->n_snp > 0) {
         tables_kernel<<<(unsigned)((c->n_snp + 255) / 256), 256, 0, c->stream>>>(
-            c->stat.p, c->n_snp, cap, est, plan.bayesian, f, nU, nW, nD, nD2, tab.p, c->scalars.p,
+            c->stat.p, c->n_snp, cap, est, plan.bayesian, f, fd, nU, nW, nD, nD2, tab.p, c->scalars.p,
             c->iscalars.p, ovf.p);
         KERNEL_CHECK(c);
     }
     int hovf = 0;
     CUDA_CHECK(cudaMemcpyAsync(&hovf, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    if (hovf) fail("internal: fixed-point digit overflow (table %d, frac_bits %d)", hovf, f);
+    if (hovf) fail("internal: fixed-point digit overflow (table %d, frac_bits %d/%d)", hovf, f, fd);
 
     // per-sample vectors
     c->samp_sum.alloc((size_t)NVEC * npad);
@@ -335,7 +465,7 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     if (c->n_snp > 0) {
         dim3 grid((unsigned)((c->row_bytes + 127) / 128), (unsigned)((c->n_snp + SS_SNPS - 1) / SS_SNPS));
         sample_sum_kernel<<<grid, 128, 0, c->stream>>>(c->geno2b.p, c->stat.p, c->n_snp, c->row_bytes,
-                                                       npad, est, plan.bayesian, f, c->samp_sum.p);
+                                                       npad, est, plan.bayesian, f, fd, c->samp_sum.p);
         KERNEL_CHECK(c);
     }
 
@@ -386,13 +516,14 @@ __device__ __forceinline__ void store_sym2(double *out, int packed, int64_t n, i
     }
 }
 
-// numerator C_ij = (acc0[i][j] - vecW[i]) * 2^-f, into a full n x n matrix (upper triangle)
+// numerator C_ij = (acc0[i][j] - vecW_hi[i]) * 2^-f - vecW_lo[i] * 2^-(f+20), full n x n (upper triangle)
 __global__ void numerator_kernel(const long long *__restrict__ acc, const long long *__restrict__ vec,
-                                 double *__restrict__ out, double inv_scale, int64_t n, int64_t npad) {
+                                 double *__restrict__ out, double inv_scale, double inv_scale_lo, int64_t n,
+                                 int64_t npad) {
     int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= n || j < i) return;
     long long q = acc[i * npad + j] - vec[VEC_W * npad + i];
-    out[i * n + j] = (double)q * inv_scale;
+    out[i * n + j] = (double)q * inv_scale - (double)vec[VEC_WLO * npad + i] * inv_scale_lo;
 }
 
 // mode 0: Eigenstrat (scale = (n-1)/trace); 1: GCTA; 3: EIGMIX (mul = 1 ibd / 2 GRM)
@@ -461,6 +592,7 @@ static void need_grm_accum(snprel_ctx *c, int est, int bayesian) {
     if (c->accum_est == est && c->accum_reduced) return;
     snprel_plan plan{};
     plan.frac_bits = -1;
+    plan.frac_bits_d = -1;
     plan.bayesian = bayesian;
     grm_plan_local(c, est, &plan);
     grm_accumulate(c, est, &plan);
@@ -483,7 +615,8 @@ static void build_numerator(snprel_ctx *c, DevBuf<double> &num) {
     int64_t n = c->n_samp;
     num.alloc((size_t)n * n);
     numerator_kernel<<<tri_grid(n), 128, 0, c->stream>>>(c->acc.p, c->samp_sum.p, num.p,
-                                                         std::ldexp(1.0, -c->plan.frac_bits), n,
+                                                         std::ldexp(1.0, -c->plan.frac_bits),
+                                                         std::ldexp(1.0, -(c->plan.frac_bits + W_EXTRA_BITS)), n,
                                                          c->n_samp_pad);
     KERNEL_CHECK(c);
 }
@@ -522,7 +655,7 @@ static void grm_device(snprel_ctx *c, int method, int packed, int diagadj, doubl
     } else {
         grm_final_kernel<<<tri_grid(n), 128, 0, c->stream>>>(
             num.p, c->acc.p, c->samp_sum.p, o.p, packed, 3, 0, g.sum_den, 0,
-            std::ldexp(1.0, -c->plan.frac_bits), has_den, diagadj, mul, n, npad);
+            std::ldexp(1.0, -c->plan.frac_bits_d), has_den, diagadj, mul, n, npad);
     }
     KERNEL_CHECK(c);
 }
@@ -660,11 +793,12 @@ void king_homo_finish(snprel_ctx *c, double *k0, double *k1, int packed) {
     // float sums first (they own acc/samp_sum), then the integer counters (they own cnt)
     snprel_plan plan{};
     plan.frac_bits = -1;
+    plan.frac_bits_d = -1;
     grm_plan_local(c, SNPREL_EST_KING_HOMO, &plan);
     grm_accumulate(c, SNPREL_EST_KING_HOMO, &plan);
     Globals g = read_globals(c);
-    const int has_den = plan.max_missing > 0;
-    const int fb = c->plan.frac_bits;
+    const int has_den = plan.total_missing > 0;
+    const int fb = c->plan.frac_bits_d;
     bitcount_accumulate(c, SNPREL_EST_KING_ROBUST);
     DevBuf<double> o;
     size_t oc = out_count(n, packed);

@@ -55,18 +55,23 @@ def buffer_tensor(ptr, count, kind, device):
 
 def reduce_plan(plan, group=None, device=None):
     """All ranks must use one fixed-point format: max-reduce max_abs, sum-reduce
-    sum_bound / max_missing / n_snp of the per-rank plan statistics."""
+    the other per-rank plan statistics."""
     import torch
     import torch.distributed as dist
     dev = "cpu" if device is None else device
     mx = torch.tensor([plan.max_abs], dtype=torch.float64, device=dev)
-    sm = torch.tensor([plan.sum_bound, float(plan.max_missing), float(plan.n_snp)], dtype=torch.float64, device=dev)
+    # sums are conservative for the per-sample maxima (max of sums <= sum of maxima)
+    sm = torch.tensor([plan.sum_bound, plan.err_weight, plan.scale, float(plan.total_missing),
+                       float(plan.max_missing), float(plan.n_snp)], dtype=torch.float64, device=dev)
     dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
     dist.all_reduce(sm, op=dist.ReduceOp.SUM, group=group)
     plan.max_abs = float(mx[0])
     plan.sum_bound = float(sm[0])
-    plan.max_missing = int(sm[1])
-    plan.n_snp = int(sm[2])
+    plan.err_weight = float(sm[1])
+    plan.scale = float(sm[2])
+    plan.total_missing = int(sm[3])
+    plan.max_missing = int(sm[4])
+    plan.n_snp = int(sm[5])
     return plan
 
 

@@ -39,6 +39,9 @@ def _worker(rank, world, port, q):
     plan.max_abs = 10.0 + rank
     plan.sum_bound = 100.0 * (rank + 1)
     plan.max_missing = 5 + rank
+    plan.total_missing = 50 + rank
+    plan.err_weight = 7.0
+    plan.scale = 2.5
     plan.n_snp = 1000 * (rank + 1)
     plan = D.reduce_plan(plan, device=None)
     # three buffers of the three kinds the library exposes, as raw host pointers
@@ -47,7 +50,7 @@ def _worker(rank, world, port, q):
     c = np.array([0.5, 1.25]) * (rank + 1)
     bufs = [(a.ctypes.data, a.size, 0), (b.ctypes.data, b.size, 1), (c.ctypes.data, c.size, 2)]
     D.allreduce_buffers(bufs, device=None)
-    q.put((rank, plan.max_abs, plan.sum_bound, plan.max_missing, plan.n_snp, a.tolist(), b.tolist(), c.tolist()))
+    q.put((rank, plan.max_abs, plan.sum_bound, plan.max_missing, plan.n_snp, plan.total_missing, plan.err_weight, plan.scale, a.tolist(), b.tolist(), c.tolist()))
     dist.destroy_process_group()
 
 
@@ -64,8 +67,9 @@ def test_plan_and_buffer_reduction_world2():
         assert p.exitcode == 0
     exp_a = ((np.arange(6) * 1 - 3) + (np.arange(6) * 2 - 3)).tolist()
     exp_b = ((np.arange(4, dtype=np.uint64) + 4294967290) + (np.arange(4, dtype=np.uint64) + 4294967291)) % (1 << 32)
-    for rank, mx, sb, mm, ns, a, b, c in res:
+    for rank, mx, sb, mm, ns, tmiss, ew, sc, a, b, c in res:
         assert mx == 11.0 and sb == 300.0 and mm == 11 and ns == 3000
+        assert tmiss == 101 and ew == 14.0 and sc == 5.0
         assert a == exp_a
         assert b == exp_b.astype(np.uint32).tolist()
         assert c == [1.5, 3.75]

@@ -176,10 +176,10 @@ def test_table_gram_exact(ctx):
 
 def test_degenerate_inputs(ctx):
     g = O.synth_geno(64, 300, seed=4, miss_rate=0.0)
-    g[:, 5] = 3            # a sample with every genotype missing
     g[7, :] = 0            # monomorphic SNP
     g[8, :] = 3            # all-missing SNP
     g[9, :] = 2
+    g[:, 5] = 3            # a sample with every genotype missing
     load(ctx, g)
     assert np.array_equal(np.stack(ctx.ibs_num()), O.ibs_counts(g))
     ibs = ctx.ibs_ave()
