@@ -47,7 +47,14 @@ constexpr int THREADS = 32 + PROD_THREADS;
 constexpr int A_BYTES = TM * SK;   // one pass, one stage (16 KB)
 constexpr int B_BYTES = TN * SK;   // one stage (32 KB)
 constexpr int STAGE_BYTES = MAXP * A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024;
+// ring of packed (2-bit) genotype rows + digit tables, filled with cp.async PF_DEPTH stages ahead
+constexpr int PF_DEPTH = 2;
+constexpr int PF_A = PROD_THREADS * 16;      // one 16-byte A quad per producer thread
+constexpr int PF_B = PROD_THREADS * 16;      // two 16-byte B quads per producer thread (b0, b1)
+constexpr int PF_T = PROD_THREADS * 8;       // two 4-byte table words per producer thread
+constexpr int PF_BYTES = PF_A + 2 * PF_B + PF_T;
+constexpr int BAR_OFFSET = NSTAGE * STAGE_BYTES + PF_DEPTH * PF_BYTES;
+constexpr int SMEM_BYTES = BAR_OFFSET + 1024;
 constexpr int A_LBO = (TM / 16) * 128;   // byte stride between 8-SNP groups (K direction)
 constexpr int B_LBO = (TN / 16) * 128;
 constexpr int CORE_SBO = 128;            // byte stride between 16-sample cores (MN direction)
@@ -174,6 +181,28 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint8_t *p) {
     return r;
 }
 
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+
 // shared-memory matrix descriptor, MN-major, no swizzle (SWIZZLE_NONE / "interleave"):
 // core matrix = 8 K-rows x 16 bytes (16 consecutive samples), 128 contiguous bytes.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -214,14 +243,14 @@ __global__ void __launch_bounds__(THREADS, 1) table_gram_kernel(const __grid_con
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bar_base = smem_base + NSTAGE * STAGE_BYTES;
+    const uint32_t bar_base = smem_base + BAR_OFFSET;
     // barriers: full[NSTAGE], empty[NSTAGE], accum; then the TMEM address slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
     const uint32_t accum_bar = bar_base + 8u * (2 * NSTAGE);
     const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE + 1);
     volatile uint32_t *tmem_slot_ptr =
-        reinterpret_cast<volatile uint32_t *>(smem + NSTAGE * STAGE_BYTES + 8 * (2 * NSTAGE + 1));
+        reinterpret_cast<volatile uint32_t *>(smem + BAR_OFFSET + 8 * (2 * NSTAGE + 1));
 
     const int2 tile = P.tiles[blockIdx.x];
     const int st_begin = blockIdx.y * P.stages_per_split;
@@ -292,33 +321,46 @@ __global__ void __launch_bounds__(THREADS, 1) table_gram_kernel(const __grid_con
         for (int q = 0; q < NP; q++) ta[q] = P.tabA[q] + (long long)st_begin * SK + sl;
         uint32_t tb[1] = {P.tabB};
 
-        uint4 na = ld_nc_v4(ap), nb0 = ld_nc_v4(bp), nb1 = ld_nc_v4(bp + 16);
-        uint32_t nt[NP];
-#pragma unroll
-        for (int q = 0; q < NP; q++) nt[q] = ld_nc_u32(ta[q]);
-
         const uint32_t a_off = kg * A_LBO + (half * 4) * CORE_SBO + r * 16;
         const uint32_t b_off = MAXP * A_BYTES + kg * B_LBO + (half * 8) * CORE_SBO + r * 16;
 
+        // Packed genotypes and digit tables travel global -> shared with cp.async, PF_DEPTH
+        // stages ahead, each thread into its own slot of a small ring (structure-of-arrays so
+        // the 16-byte reads are conflict free).  cp.async groups retire in order, so waiting for
+        // the oldest group leaves the younger prefetches in flight -- register prefetch cannot do
+        // that: all loads of a thread share a handful of counting scoreboards, and the first use
+        // of an old load also waits for the youngest one.
+        const uint32_t pf_base = smem_base + NSTAGE * STAGE_BYTES;
+        auto prefetch = [&](int it) {
+            if (it < nst) {
+                const uint32_t slot = pf_base + (uint32_t)(it % PF_DEPTH) * PF_BYTES;
+                const long long off = (long long)it * stage_stride;
+                cp_async_16(slot + p * 16, ap + off);
+                cp_async_16(slot + PF_A + p * 16, bp + off);
+                cp_async_16(slot + PF_A + PF_B + p * 16, bp + off + 16);
+#pragma unroll
+                for (int q = 0; q < NP; q++)
+                    cp_async_4(slot + PF_A + 2 * PF_B + q * (PF_T / 2) + p * 4, ta[q] + (long long)it * SK);
+            }
+            cp_async_commit();   // always commit so that group counting stays uniform
+        };
+#pragma unroll
+        for (int d = 0; d < PF_DEPTH; d++) prefetch(d);
+
+#pragma unroll 1
         for (int it = 0; it < nst; it++) {
             const int s = it % NSTAGE;
             const uint32_t phase = (uint32_t)(it / NSTAGE) & 1u;
-            uint4 ca = na, cb0 = nb0, cb1 = nb1;
+            cp_async_wait<PF_DEPTH - 1>();   // this thread's copies for stage `it` have landed
+            const uint32_t slot = pf_base + (uint32_t)(it % PF_DEPTH) * PF_BYTES;
+            const uint4 ca = ld_shared_v4(slot + p * 16);
+            const uint4 cb0 = ld_shared_v4(slot + PF_A + p * 16);
+            const uint4 cb1 = ld_shared_v4(slot + PF_A + PF_B + p * 16);
             uint32_t ct[NP];
 #pragma unroll
-            for (int q = 0; q < NP; q++) ct[q] = nt[q];
-            if (it + 1 < nst) {   // prefetch the next stage's packed genotypes and tables
-                ap += stage_stride;
-                bp += stage_stride;
-                na = ld_nc_v4(ap);
-                nb0 = ld_nc_v4(bp);
-                nb1 = ld_nc_v4(bp + 16);
-#pragma unroll
-                for (int q = 0; q < NP; q++) {
-                    ta[q] += SK;
-                    nt[q] = ld_nc_u32(ta[q]);
-                }
-            }
+            for (int q = 0; q < NP; q++) ct[q] = ld_shared_u32(slot + PF_A + 2 * PF_B + q * (PF_T / 2) + p * 4);
+            prefetch(it + PF_DEPTH);         // refill the slot just read
+
             mbar_wait(empty_bar(s), phase ^ 1u, P.error_flag, 2);
             const uint32_t stage_addr = smem_base + s * STAGE_BYTES;
             const uint32_t aw[4] = {ca.x, ca.y, ca.z, ca.w};
@@ -338,6 +380,7 @@ __global__ void __launch_bounds__(THREADS, 1) table_gram_kernel(const __grid_con
             fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core
             mbar_arrive(full_bar(s));
         }
+        cp_async_wait<0>();
 
         // ===================== epilogue =====================
         mbar_wait(accum_bar, 0, P.error_flag, 3);

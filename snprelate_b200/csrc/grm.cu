@@ -386,6 +386,9 @@ static void choose_format(int est, snprel_plan &plan, int &nU, int &nD) {
     double scale = plan.scale;
     if (est == SNPREL_GRM_GCTA) scale -= 4.0 * (double)plan.max_missing;   // 2 (nLocus - D_ij), D_ij <= 2 max_missing
     if (est == SNPREL_GRM_EIGMIX) scale -= 2.0 * (double)plan.max_missing;
+    // the subtraction is a worst case (every missing SNP at full weight for both samples);
+    // never let it shrink the normaliser below 5 % of its complete-data value
+    scale = std::max(scale, 0.05 * plan.scale);
     nU = 0;
     if (!homo) {
         int f = plan.frac_bits;
@@ -393,9 +396,12 @@ static void choose_format(int est, snprel_plan &plan, int &nU, int &nD) {
             int f_req = 24;
             if (plan.err_weight > 0 && scale > 0)
                 f_req = (int)std::ceil(std::log2(plan.err_weight / (tol * scale))) - 1;
-            f_req = std::max(16, std::min(f_req, head));
+            f_req = std::max(16, std::min(f_req, std::min(head, 61 - W_EXTRA_BITS - (int)std::ceil(std::log2(std::max(plan.max_abs, 1.0))))));
             nU = digits_for(plan.max_abs, f_req);
-            f = std::min(std::min(frac_cap(plan.max_abs, nU), head), 50);   // use every bit the digits offer
+            // use every bit the digits offer; the extended-precision W vector needs
+            // max_abs * 2^(f + W_EXTRA_BITS) to stay inside int64
+            int wcap = 61 - W_EXTRA_BITS - (int)std::ceil(std::log2(std::max(plan.max_abs, 1.0)));
+            f = std::min(std::min(frac_cap(plan.max_abs, nU), head), wcap);
         } else {
             nU = digits_for(plan.max_abs, f);
         }
@@ -501,6 +507,7 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     c->reduce_list.push_back({c->samp_sum.p, (int64_t)c->samp_sum.n, 0});
     c->reduce_list.push_back({c->scalars.p, (int64_t)c->scalars.n, 2});
     c->reduce_list.push_back({c->iscalars.p, (int64_t)c->iscalars.n, 0});
+    c->reduce_list.push_back({c->scr_cnt.p, (int64_t)c->scr_cnt.n, 1});   // per-sample genotype sums / missing counts
 }
 
 // ---------------------------------------------------------------------------
@@ -518,10 +525,17 @@ __device__ __forceinline__ void store_sym2(double *out, int packed, int64_t n, i
 
 // numerator C_ij = (acc0[i][j] - vecW_hi[i]) * 2^-f - vecW_lo[i] * 2^-(f+20), full n x n (upper triangle)
 __global__ void numerator_kernel(const long long *__restrict__ acc, const long long *__restrict__ vec,
+                                 const int *__restrict__ nmiss, long long n_snp_total,
                                  double *__restrict__ out, double inv_scale, double inv_scale_lo, int64_t n,
                                  int64_t npad) {
     int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= n || j < i) return;
+    // a sample without a single valid genotype contributes exactly 0, as in the reference
+    // (its centred genotypes are all 0, src/genPCA.h:103)
+    if (nmiss[i] == n_snp_total || nmiss[j] == n_snp_total) {
+        out[i * n + j] = 0.0;
+        return;
+    }
     long long q = acc[i * npad + j] - vec[VEC_W * npad + i];
     out[i * n + j] = (double)q * inv_scale - (double)vec[VEC_WLO * npad + i] * inv_scale_lo;
 }
@@ -614,7 +628,8 @@ static Globals read_globals(snprel_ctx *c) {
 static void build_numerator(snprel_ctx *c, DevBuf<double> &num) {
     int64_t n = c->n_samp;
     num.alloc((size_t)n * n);
-    numerator_kernel<<<tri_grid(n), 128, 0, c->stream>>>(c->acc.p, c->samp_sum.p, num.p,
+    numerator_kernel<<<tri_grid(n), 128, 0, c->stream>>>(c->acc.p, c->samp_sum.p, c->scr_cnt.p + c->n_samp_pad,
+                                                         (long long)c->plan.n_snp, num.p,
                                                          std::ldexp(1.0, -c->plan.frac_bits),
                                                          std::ldexp(1.0, -(c->plan.frac_bits + W_EXTRA_BITS)), n,
                                                          c->n_samp_pad);
