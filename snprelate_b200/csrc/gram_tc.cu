@@ -18,9 +18,12 @@
 // hence bit-identical for any tiling, split or GPU count).
 //
 // Mapping onto sm_100a:
-//   * one CTA per (128 x 256 sample tile, SNP split); 9 warps.
-//   * warps 1..8 are producers: each thread reads 64 packed genotypes of one SNP
-//     with one 16-byte load, turns every 32-bit word (16 samples) into byte-permute
+//   * one CTA per (128 x 256 sample tile, SNP split); 10 warps.
+//   * warp 1 is the loader: per stage it issues six TMA box copies (16 bytes x 128 SNP rows
+//     each, cp.async.bulk.tensor.2d) of the packed 2-bit genotypes plus bulk copies of the
+//     digit tables into a small shared-memory ring, signalled through mbarrier complete_tx.
+//   * warps 2..9 are producers: each thread takes 64 packed genotypes of one SNP from
+//     the ring, turns every 32-bit word (16 samples) into byte-permute
 //     selectors (3 logic ops + 2 shifts) and emits int8 operand rows with PRMT
 //     against the 4-entry tables -- the "unpack, centre and scale on the fly" step.
 //     Operands are written MN-major (16 consecutive samples = one 16-byte core row),
@@ -30,6 +33,8 @@
 //     tcgen05.commit releases pipeline stages back to the producers through mbarriers.
 //   * after the last SNP stage the producer warps become the epilogue: tcgen05.ld the
 //     accumulators and issue the 64-bit atomics.
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace snprel {
@@ -43,16 +48,18 @@ constexpr int NSTAGE = 3;
 constexpr int MAXP = 2;            // passes per launch = TMEM accumulators
 constexpr int PROD_WARPS = 8;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
-constexpr int THREADS = 32 + PROD_THREADS;
+constexpr int FIRST_PROD_WARP = 2;                       // warp 0 = MMA issuer, warp 1 = TMA loader
+constexpr int THREADS = 32 * (FIRST_PROD_WARP + PROD_WARPS);
 constexpr int A_BYTES = TM * SK;   // one pass, one stage (16 KB)
 constexpr int B_BYTES = TN * SK;   // one stage (32 KB)
 constexpr int STAGE_BYTES = MAXP * A_BYTES + B_BYTES;
-// ring of packed (2-bit) genotype rows + digit tables, filled with cp.async PF_DEPTH stages ahead
+// ring of packed (2-bit) genotype boxes + digit tables, filled by TMA PF_DEPTH stages ahead:
+// six boxes of 16 bytes x SK rows (A quads 0-1, B quads 0-3), then MAXP tables of SK words
 constexpr int PF_DEPTH = 2;
-constexpr int PF_A = PROD_THREADS * 16;      // one 16-byte A quad per producer thread
-constexpr int PF_B = PROD_THREADS * 16;      // two 16-byte B quads per producer thread (b0, b1)
-constexpr int PF_T = PROD_THREADS * 8;       // two 4-byte table words per producer thread
-constexpr int PF_BYTES = PF_A + 2 * PF_B + PF_T;
+constexpr int PF_BOX = SK * 16;
+constexpr int PF_NBOX = (TM + TN) / 64;
+constexpr int PF_TAB = SK * 4;
+constexpr int PF_BYTES = PF_NBOX * PF_BOX + MAXP * PF_TAB;
 constexpr int BAR_OFFSET = NSTAGE * STAGE_BYTES + PF_DEPTH * PF_BYTES;
 constexpr int SMEM_BYTES = BAR_OFFSET + 1024;
 constexpr int A_LBO = (TM / 16) * 128;   // byte stride between 8-SNP groups (K direction)
@@ -77,6 +84,7 @@ struct Params {
     int stages_per_split;
     int upper_only;
     uint32_t flags;          // bit0: swap LBO/SBO in the descriptors (bring-up probe)
+    uint32_t sh32;           // always 32 (see mbar_arrive_after)
     int *error_flag;
 };
 
@@ -89,6 +97,16 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar)
+                 : "memory");
+}
+// Arrive whose ADDRESS is data-dependent on values just read from shared memory, so the
+// release of a ring slot cannot be issued before the ld.shared reading that slot have
+// returned (the TMA refill would otherwise race with loads still queued in the LSU).
+// `sh32` is a kernel parameter that is always 32: shr.u32 by 32 yields 0, which the
+// assembler cannot fold away.
+__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, uint32_t dep, uint32_t sh32) {
+    asm volatile("{\n .reg .b64 st;\n .reg .b32 z;\n shr.u32 z, %1, %2;\n add.u32 z, z, %0;\n"
+                 " mbarrier.arrive.shared::cta.b64 st, [z];\n}" ::"r"(bar), "r"(dep), "r"(sh32)
                  : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
@@ -181,16 +199,23 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint8_t *p) {
     return r;
 }
 
-__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar),
+                 "r"(bytes)
+                 : "memory");
 }
-__device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+// TMA: one 2-D box (16 bytes x SK rows) of the packed genotype matrix -> shared memory
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar)
+        : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+// bulk copy of a contiguous run (digit table of one stage)
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
     uint4 r;
@@ -239,18 +264,22 @@ __device__ __forceinline__ void expand_word(uint32_t x, const uint32_t (&tab)[NP
 }
 
 template <int NP>
-__global__ void __launch_bounds__(THREADS, 1) table_gram_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(THREADS, 1)
+table_gram_kernel(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_base + BAR_OFFSET;
-    // barriers: full[NSTAGE], empty[NSTAGE], accum; then the TMEM address slot
+    // barriers: full[NSTAGE], empty[NSTAGE], accum, pf_full[PF_DEPTH], pf_empty[PF_DEPTH]; then the TMEM slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
     const uint32_t accum_bar = bar_base + 8u * (2 * NSTAGE);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE + 1);
-    volatile uint32_t *tmem_slot_ptr =
-        reinterpret_cast<volatile uint32_t *>(smem + BAR_OFFSET + 8 * (2 * NSTAGE + 1));
+    auto pf_full = [&](int s) { return bar_base + 8u * (2 * NSTAGE + 1 + s); };
+    auto pf_empty = [&](int s) { return bar_base + 8u * (2 * NSTAGE + 1 + PF_DEPTH + s); };
+    constexpr int SLOT_IDX = 2 * NSTAGE + 1 + 2 * PF_DEPTH;
+    const uint32_t tmem_slot = bar_base + 8u * SLOT_IDX;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem + BAR_OFFSET + 8 * SLOT_IDX);
+    const uint32_t pf_base = smem_base + NSTAGE * STAGE_BYTES;
 
     const int2 tile = P.tiles[blockIdx.x];
     const int st_begin = blockIdx.y * P.stages_per_split;
@@ -265,6 +294,10 @@ __global__ void __launch_bounds__(THREADS, 1) table_gram_kernel(const __grid_con
                 mbar_init(empty_bar(s), 1);
             }
             mbar_init(accum_bar, 1);
+            for (int s = 0; s < PF_DEPTH; s++) {
+                mbar_init(pf_full(s), 1);
+                mbar_init(pf_empty(s), PROD_THREADS);
+            }
             fence_mbar_init();
         }
         __syncwarp();
@@ -306,60 +339,60 @@ __global__ void __launch_bounds__(THREADS, 1) table_gram_kernel(const __grid_con
         }
         if (lane == 0) umma_commit(accum_bar);
         __syncwarp();
+    } else if (warp == 1) {
+        // ===================== TMA loader =====================
+        if (lane == 0) {
+            const int ax = tile.x * (TM / 4), bx = tile.y * (TN / 4);
+            for (int it = 0; it < nst; it++) {
+                const int sl = it % PF_DEPTH;
+                const uint32_t ph = (uint32_t)(it / PF_DEPTH) & 1u;
+                mbar_wait(pf_empty(sl), ph ^ 1u, P.error_flag, 4);
+                const uint32_t slot = pf_base + (uint32_t)sl * PF_BYTES;
+                const uint32_t bar = pf_full(sl);
+                mbar_arrive_expect_tx(bar, PF_NBOX * PF_BOX + NP * PF_TAB);
+                const int y = (st_begin + it) * SK;
+#pragma unroll
+                for (int q = 0; q < TM / 64; q++) tma_load_2d(slot + q * PF_BOX, &tmap, ax + q * 16, y, bar);
+#pragma unroll
+                for (int q = 0; q < TN / 64; q++)
+                    tma_load_2d(slot + (TM / 64 + q) * PF_BOX, &tmap, bx + q * 16, y, bar);
+#pragma unroll
+                for (int q = 0; q < NP; q++)
+                    bulk_load(slot + PF_NBOX * PF_BOX + q * PF_TAB, P.tabA[q] + (long long)y, PF_TAB, bar);
+            }
+        }
+        __syncwarp();
     } else {
         // ===================== producers =====================
-        const int p = threadIdx.x - 32;
+        const int p = threadIdx.x - 32 * FIRST_PROD_WARP;
         const int sl = p & (SK - 1);   // SNP within the stage
         const int half = p >> 7;       // which 64-sample quad of A / which 128-sample half of B
         const int kg = sl >> 3, r = sl & 7;
-        const uint8_t *rowp = P.geno + ((long long)st_begin * SK + sl) * P.row_bytes;
-        const uint8_t *ap = rowp + (long long)tile.x * (TM / 4) + half * 16;
-        const uint8_t *bp = rowp + (long long)tile.y * (TN / 4) + half * 32;
-        const long long stage_stride = (long long)SK * P.row_bytes;
-        const uint32_t *ta[NP];
-#pragma unroll
-        for (int q = 0; q < NP; q++) ta[q] = P.tabA[q] + (long long)st_begin * SK + sl;
         uint32_t tb[1] = {P.tabB};
-
         const uint32_t a_off = kg * A_LBO + (half * 4) * CORE_SBO + r * 16;
         const uint32_t b_off = MAXP * A_BYTES + kg * B_LBO + (half * 8) * CORE_SBO + r * 16;
-
-        // Packed genotypes and digit tables travel global -> shared with cp.async, PF_DEPTH
-        // stages ahead, each thread into its own slot of a small ring (structure-of-arrays so
-        // the 16-byte reads are conflict free).  cp.async groups retire in order, so waiting for
-        // the oldest group leaves the younger prefetches in flight -- register prefetch cannot do
-        // that: all loads of a thread share a handful of counting scoreboards, and the first use
-        // of an old load also waits for the youngest one.
-        const uint32_t pf_base = smem_base + NSTAGE * STAGE_BYTES;
-        auto prefetch = [&](int it) {
-            if (it < nst) {
-                const uint32_t slot = pf_base + (uint32_t)(it % PF_DEPTH) * PF_BYTES;
-                const long long off = (long long)it * stage_stride;
-                cp_async_16(slot + p * 16, ap + off);
-                cp_async_16(slot + PF_A + p * 16, bp + off);
-                cp_async_16(slot + PF_A + PF_B + p * 16, bp + off + 16);
-#pragma unroll
-                for (int q = 0; q < NP; q++)
-                    cp_async_4(slot + PF_A + 2 * PF_B + q * (PF_T / 2) + p * 4, ta[q] + (long long)it * SK);
-            }
-            cp_async_commit();   // always commit so that group counting stays uniform
-        };
-#pragma unroll
-        for (int d = 0; d < PF_DEPTH; d++) prefetch(d);
+        // this thread's words inside a ring slot (16-byte box rows: conflict-free LDS.128)
+        const uint32_t pa = half * PF_BOX + sl * 16;
+        const uint32_t pb = (TM / 64 + 2 * half) * PF_BOX + sl * 16;
+        const uint32_t pt = PF_NBOX * PF_BOX + sl * 4;
 
 #pragma unroll 1
         for (int it = 0; it < nst; it++) {
             const int s = it % NSTAGE;
             const uint32_t phase = (uint32_t)(it / NSTAGE) & 1u;
-            cp_async_wait<PF_DEPTH - 1>();   // this thread's copies for stage `it` have landed
-            const uint32_t slot = pf_base + (uint32_t)(it % PF_DEPTH) * PF_BYTES;
-            const uint4 ca = ld_shared_v4(slot + p * 16);
-            const uint4 cb0 = ld_shared_v4(slot + PF_A + p * 16);
-            const uint4 cb1 = ld_shared_v4(slot + PF_A + PF_B + p * 16);
+            const int ps = it % PF_DEPTH;
+            mbar_wait(pf_full(ps), (uint32_t)(it / PF_DEPTH) & 1u, P.error_flag, 5);
+            const uint32_t slot = pf_base + (uint32_t)ps * PF_BYTES;
+            const uint4 ca = ld_shared_v4(slot + pa);
+            const uint4 cb0 = ld_shared_v4(slot + pb);
+            const uint4 cb1 = ld_shared_v4(slot + pb + PF_BOX);
             uint32_t ct[NP];
 #pragma unroll
-            for (int q = 0; q < NP; q++) ct[q] = ld_shared_u32(slot + PF_A + 2 * PF_B + q * (PF_T / 2) + p * 4);
-            prefetch(it + PF_DEPTH);         // refill the slot just read
+            for (int q = 0; q < NP; q++) ct[q] = ld_shared_u32(slot + pt + q * PF_TAB);
+            // the loader may refill this slot -- but only once every word above has really been read
+            mbar_arrive_after(pf_empty(ps), ca.x ^ ca.y ^ ca.z ^ ca.w ^ cb0.x ^ cb0.y ^ cb0.z ^ cb0.w ^ cb1.x ^ cb1.y ^
+                                                cb1.z ^ cb1.w ^ ct[0] ^ ct[NP - 1],
+                              P.sh32);
 
             mbar_wait(empty_bar(s), phase ^ 1u, P.error_flag, 2);
             const uint32_t stage_addr = smem_base + s * STAGE_BYTES;
@@ -380,13 +413,12 @@ __global__ void __launch_bounds__(THREADS, 1) table_gram_kernel(const __grid_con
             fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core
             mbar_arrive(full_bar(s));
         }
-        cp_async_wait<0>();
 
         // ===================== epilogue =====================
         mbar_wait(accum_bar, 0, P.error_flag, 3);
         tc_fence_after();
         const int quarter = warp & 3;            // TMEM lanes this warp may touch
-        const int colhalf = (warp - 1) >> 2;     // two warps share a lane quarter
+        const int colhalf = (warp - FIRST_PROD_WARP) >> 2;     // two warps share a lane quarter
         const int row = quarter * 32 + lane;
         const long long gi = (long long)tile.x * TM + (row & ~15) + core_pos_to_sample(row & 15);
 #pragma unroll 1
@@ -451,6 +483,7 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     int64_t splits = std::max<int64_t>(1, std::min<int64_t>((want + (int64_t)tiles.size() - 1) /
                                                                (int64_t)tiles.size(),
                                                            stages_total));
+    if (c->debug_flags & 2u) splits = 1;   // test hook: one CTA walks the whole SNP range
     splits = std::min<int64_t>(splits, 65535);
     int sps = (int)((stages_total + splits - 1) / splits);
     splits = (stages_total + sps - 1) / sps;
@@ -459,6 +492,31 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     if (sps > max_stages_i32) {
         sps = max_stages_i32;
         splits = (stages_total + sps - 1) / sps;
+    }
+
+    // tensor map over the packed genotype matrix: bytes x SNP rows, box = 16 bytes x SK rows
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) fail("cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    alignas(64) CUtensorMap tmap;
+    {
+        const int64_t rows = round_up(std::max<int64_t>(c->n_snp, 1), SK);
+        cuuint64_t gdim[2] = {(cuuint64_t)c->row_bytes, (cuuint64_t)rows};
+        cuuint64_t gstride[1] = {(cuuint64_t)c->row_bytes};
+        cuuint32_t box[2] = {16, (cuuint32_t)SK};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->geno2b.p, gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled failed (%d)", (int)r);
     }
 
     static bool attr_done = false;
@@ -486,6 +544,7 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
         P.stages_per_split = sps;
         P.upper_only = upper_only ? 1 : 0;
         P.flags = c->debug_flags;
+        P.sh32 = 32;
         P.error_flag = derr;
         int np = 0;
         for (int j = i; j < npass && np < MAXP; j++) {
@@ -499,9 +558,9 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
         P.npass = np;
         dim3 grid((unsigned)tiles.size(), (unsigned)splits);
         if (np == 2)
-            table_gram_kernel<2><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P);
+            table_gram_kernel<2><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
         else
-            table_gram_kernel<1><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P);
+            table_gram_kernel<1><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
         KERNEL_CHECK(c);
         c->hot_launches++;
     }

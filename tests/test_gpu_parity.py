@@ -174,6 +174,25 @@ def test_table_gram_exact(ctx):
         assert np.array_equal(ctx.table_gram(tA, tB), ref)
 
 
+def test_long_k_loop_single_cta():
+    """Hundreds of pipeline stages in ONE CTA (SNP splitting disabled): exercises every
+    ring-buffer phase flip of the TMA / producer / MMA pipeline, exact integers."""
+    rng = np.random.default_rng(5)
+    n, m = 300, 50000
+    g = O.synth_geno(n, m, seed=31, miss_rate=0.02)
+    c = S.Context(0)
+    c.debug_flags(2)
+    load(c, g)
+    tA = rng.integers(-128, 128, size=(m, 4)).astype(np.int8)
+    tB = np.array([0, 1, 2, 0], np.int8)
+    gi = g.astype(np.int64)
+    ref = np.take_along_axis(tA.astype(np.int64), gi, axis=1).T @ tB.astype(np.int64)[gi]
+    for _ in range(3):
+        assert np.array_equal(c.table_gram(tA, tB), ref)
+    assert relerr(c.grm("GCTA")[0], O.grm_gcta(g)) < TOL
+    c.close()
+
+
 def test_degenerate_inputs(ctx):
     g = O.synth_geno(64, 300, seed=4, miss_rate=0.0)
     g[7, :] = 0            # monomorphic SNP
