@@ -255,9 +255,9 @@ def run_ours(args):
         eig_ms = (time.perf_counter() - t0) * 1e3 - ms_per_step
 
     pl = ctx.last_plan()
-    passes = {"digits_per_table": int(pl.digits), "frac_bits": int(pl.frac_bits),
-              "tables": 2 if pl.total_missing > 0 else 1,
-              "tensor_passes_per_step": int(pl.digits) * (2 if pl.total_missing > 0 else 1)}
+    passes = {"digits_U": int(pl.digits), "digits_W": int(pl.digits_w), "frac_bits": int(pl.frac_bits),
+              "frac_bits_W": int(pl.frac_bits_w),
+              "tensor_passes_per_step": int(pl.digits) + int(pl.digits_w) + int(pl.digits_d)}
     pk, pk_kind = peaks()
     hot_per_step_ms = hot_ms / args.steps
     alg_flops = float(N_SAMP) * N_SAMP * N_SNP           # 2 flop per pair-SNP, symmetric half

@@ -154,22 +154,27 @@ int snprel_eigmix(snprel_ctx *ctx, int eigen_cnt, int diagadj, double *ibd,
  *
  * Format choice (grm.cu): every table value v is stored as round(v * 2^frac_bits) and
  * split into `digits` balanced base-256 digits (one int8 tensor pass each).  The
- * quantisation error of an output entry is at most 2^-(frac_bits+1) * err_weight, so
- * the library picks the fewest digits for which that bound is <= tol * scale, where
+ * quantisation error of an output entry is at most
+ *   2^-(frac_bits+1) * err_weight + 2^-(frac_bits_w+1) * max_missing,
+ * so the library picks the fewest passes for which that bound is <= tol * scale, where
  * scale is (a lower bound of) the estimator's normaliser (trace/(n-1), 2 nLocus,
  * sum 4p(1-p)).  tol defaults to 1e-10. */
 typedef struct snprel_plan {
-    double max_abs;        /* max |table value| over local SNPs                        */
+    double max_abs;        /* max |U table value| over local SNPs                      */
+    double max_abs_w;      /* max |W table value| (W = mu * U, the missing-data table) */
     double sum_bound;      /* sum over local SNPs of the per-SNP magnitude (int64 range) */
-    double err_weight;     /* max over samples of (sum of genotypes + #missing)        */
+    double err_weight;     /* max over samples of the sum of genotypes                 */
     double scale;          /* local share of the normaliser of the final matrix        */
     double tol;            /* in: relative tolerance target (<= 0: 1e-10)              */
     int64_t total_missing; /* missing genotypes among the selected samples             */
     int64_t max_missing;   /* max over samples of the local missing count              */
     int64_t n_snp;         /* local SNP count                                          */
     int32_t frac_bits;     /* in: < 0 = choose; out (after accumulate): chosen          */
+    int32_t frac_bits_w;   /* fixed point of the W table (<= frac_bits)                */
     int32_t frac_bits_d;   /* fixed point of the missing-pair denominator plane        */
-    int32_t digits;        /* out: digits (tensor passes) per table                    */
+    int32_t digits;        /* out: digits (tensor passes) of the U table               */
+    int32_t digits_w;      /* out: digits of the W table (0 without missing data)      */
+    int32_t digits_d;      /* out: digits of the denominator table                     */
     int32_t bayesian;      /* Eigenstrat only                                          */
 } snprel_plan;
 

@@ -24,10 +24,11 @@ class SNPRelError(RuntimeError):
 
 
 class Plan(C.Structure):
-    _fields_ = [("max_abs", C.c_double), ("sum_bound", C.c_double), ("err_weight", C.c_double),
-                ("scale", C.c_double), ("tol", C.c_double),
+    _fields_ = [("max_abs", C.c_double), ("max_abs_w", C.c_double), ("sum_bound", C.c_double),
+                ("err_weight", C.c_double), ("scale", C.c_double), ("tol", C.c_double),
                 ("total_missing", C.c_int64), ("max_missing", C.c_int64), ("n_snp", C.c_int64),
-                ("frac_bits", C.c_int32), ("frac_bits_d", C.c_int32), ("digits", C.c_int32),
+                ("frac_bits", C.c_int32), ("frac_bits_w", C.c_int32), ("frac_bits_d", C.c_int32),
+                ("digits", C.c_int32), ("digits_w", C.c_int32), ("digits_d", C.c_int32),
                 ("bayesian", C.c_int32)]
 
 
@@ -285,6 +286,7 @@ class Context:
     def plan_local(self, est, bayesian=False, tol=0.0):
         pl = Plan()
         pl.frac_bits = -1
+        pl.frac_bits_w = -1
         pl.frac_bits_d = -1
         pl.tol = float(tol)
         pl.bayesian = int(bool(bayesian))

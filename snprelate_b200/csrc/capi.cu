@@ -198,6 +198,7 @@ static void timed_plan(snprel_ctx *c, int est, snprel_plan *plan) {
         grm_plan_local(c, est == SNPREL_GRM_CORR ? SNPREL_GRM_GCTA : est, plan);
     } else {
         plan->max_abs = 0;
+        plan->max_abs_w = 0;
         plan->sum_bound = 0;
         plan->err_weight = 0;
         plan->scale = 0;
@@ -293,6 +294,7 @@ int snprel_time_accumulate(snprel_ctx *c, int est, int reps, double *ms) {
         c->planes_valid = false;
         snprel_plan plan{};
         plan.frac_bits = -1;
+        plan.frac_bits_w = -1;
         plan.frac_bits_d = -1;
         timed_plan(c, est, &plan);
         timed_accumulate(c, est, &plan);

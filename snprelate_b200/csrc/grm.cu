@@ -50,8 +50,9 @@ struct SnpTables {
 
 // est: SNPREL_GRM_EIGENSTRAT / GCTA / CORR / EIGMIX, or SNPREL_EST_KING_HOMO
 __device__ __forceinline__ void snp_tables(const SnpStat st, int est, int bayesian, int frac_bits,
-                                           int frac_bits_d, SnpTables &t) {
+                                           int frac_bits_w, int frac_bits_d, SnpTables &t) {
     const double sc = exp2((double)frac_bits);
+    const double scw = exp2((double)frac_bits_w);
     const double scd = exp2((double)frac_bits_d);
     const double scx = exp2((double)(frac_bits + W_EXTRA_BITS));
     double mu = st.num > 0 ? (double)st.sum / (double)st.num : 0.0;   // DivideGeno, src/genPCA.cpp:98-142
@@ -94,7 +95,7 @@ __device__ __forceinline__ void snp_tables(const SnpStat st, int est, int bayesi
         double u = (est == SNPREL_EST_KING_HOMO) ? 0.0 : w * ((double)g - mu);
         double ww = mu * u;
         t.qU[g] = llrint(u * sc);
-        t.qW[g] = llrint(ww * sc);
+        t.qW[g] = llrint(ww * scw);
         t.qWx[g] = llrint(ww * scx);
         t.maxU = fmax(t.maxU, fabs(u));
         t.maxW = fmax(t.maxW, fabs(ww));
@@ -120,14 +121,15 @@ __device__ __forceinline__ uint32_t digit_of(long long &q) {
 // out[3] local share of the normaliser (trace(C) / nLocus / sum d / sum d2)
 __global__ void plan_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int64_t n_samp, int est,
                             int bayesian, double *__restrict__ out) {
-    double mx = 0, sb = 0, tm = 0, sc = 0;
+    double mx = 0, mxw = 0, sb = 0, tm = 0, sc = 0;
     for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n_snp;
          l += (int64_t)gridDim.x * blockDim.x) {
         SnpTables t;
-        snp_tables(st[l], est, bayesian, 0, 0, t);
+        snp_tables(st[l], est, bayesian, 0, 0, 0, t);
         const bool realD = (est == SNPREL_GRM_EIGMIX || est == SNPREL_EST_KING_HOMO);
         double dmax = realD ? fmax(t.d, t.d2) : 0.0;
-        mx = fmax(mx, fmax(t.maxU, t.maxW));
+        mx = fmax(mx, t.maxU);
+        mxw = fmax(mxw, t.maxW);
         sb += 2 * t.maxU + 2 * t.maxW + 2 * dmax;
         tm += (double)(n_samp - st[l].num);
         if (est == SNPREL_GRM_EIGENSTRAT) sc += t.diag;
@@ -135,7 +137,8 @@ __global__ void plan_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int64
         else if (est == SNPREL_EST_KING_HOMO) sc += t.d2;
         else sc += t.d;   // GCTA: number of polymorphic SNPs
     }
-    __shared__ double s0[256], s1[256], s2[256], s3[256];
+    __shared__ double s0[256], s1[256], s2[256], s3[256], s4[256];
+    s4[threadIdx.x] = mxw;
     s0[threadIdx.x] = mx;
     s1[threadIdx.x] = sb;
     s2[threadIdx.x] = tm;
@@ -144,6 +147,7 @@ __global__ void plan_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int64
     for (int o = blockDim.x / 2; o; o >>= 1) {
         if (threadIdx.x < o) {
             s0[threadIdx.x] = fmax(s0[threadIdx.x], s0[threadIdx.x + o]);
+            s4[threadIdx.x] = fmax(s4[threadIdx.x], s4[threadIdx.x + o]);
             s1[threadIdx.x] += s1[threadIdx.x + o];
             s2[threadIdx.x] += s2[threadIdx.x + o];
             s3[threadIdx.x] += s3[threadIdx.x + o];
@@ -155,6 +159,7 @@ __global__ void plan_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int64
         atomicAdd(out + 1, s1[0]);
         atomicAdd(out + 2, s2[0]);
         atomicAdd(out + 3, s3[0]);
+        atomicMax(reinterpret_cast<unsigned long long *>(out + 4), (unsigned long long)__double_as_longlong(s4[0]));
     }
 }
 
@@ -204,7 +209,7 @@ sample_count_kernel(const uint8_t *__restrict__ geno, int64_t n_snp, int64_t row
 // ---- digit tables: tab[pass][snp] ------------------------------------------
 // pass order: U digits (nU), W digits (nW), D digits (nD), D2 digits (nD2)
 __global__ void tables_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int64_t cap, int est,
-                              int bayesian, int frac_bits, int frac_bits_d, int nU, int nW, int nD, int nD2,
+                              int bayesian, int frac_bits, int frac_bits_w, int frac_bits_d, int nU, int nW, int nD, int nD2,
                               uint32_t *__restrict__ tab, double *__restrict__ scalars,
                               long long *__restrict__ iscalars, int *__restrict__ overflow) {
     int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -212,7 +217,7 @@ __global__ void tables_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int
     long long poly = 0;
     if (l < n_snp) {
         SnpTables t;
-        snp_tables(st[l], est, bayesian, frac_bits, frac_bits_d, t);
+        snp_tables(st[l], est, bayesian, frac_bits, frac_bits_w, frac_bits_d, t);
         d = t.d;
         d2 = t.d2;
         poly = (est == SNPREL_GRM_GCTA || est == SNPREL_GRM_CORR) ? t.qD : 0;
@@ -267,7 +272,7 @@ __global__ void tables_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int
 constexpr int SS_SNPS = 512;   // SNPs per block
 __global__ void __launch_bounds__(128)
 sample_sum_kernel(const uint8_t *__restrict__ geno, const SnpStat *__restrict__ st, int64_t n_snp,
-                  int64_t row_bytes, int64_t npad, int est, int bayesian, int frac_bits, int frac_bits_d,
+                  int64_t row_bytes, int64_t npad, int est, int bayesian, int frac_bits, int frac_bits_w, int frac_bits_d,
                   long long *__restrict__ vec) {
     __shared__ long long tW[SS_SNPS][4];    // hi part of the extended-precision W (units 2^-frac_bits)
     __shared__ int tWlo[SS_SNPS][4];        // lo part (W_EXTRA_BITS bits, non-negative)
@@ -276,7 +281,7 @@ sample_sum_kernel(const uint8_t *__restrict__ geno, const SnpStat *__restrict__ 
     const int nl = (int)min((int64_t)SS_SNPS, n_snp - l0);
     for (int s = threadIdx.x; s < nl; s += blockDim.x) {
         SnpTables t;
-        snp_tables(st[l0 + s], est, bayesian, frac_bits, frac_bits_d, t);
+        snp_tables(st[l0 + s], est, bayesian, frac_bits, frac_bits_w, frac_bits_d, t);
         for (int g = 0; g < 4; g++) {
             tW[s][g] = t.qWx[g] >> W_EXTRA_BITS;
             tWlo[s][g] = (int)(t.qWx[g] & ((1ll << W_EXTRA_BITS) - 1));
@@ -338,7 +343,7 @@ void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
     ensure_stats(c);
     const int64_t npad = c->n_samp_pad;
     DevBuf<double> &out = c->scr_plan;
-    out.alloc(4);
+    out.alloc(5);
     out.zero(c->stream);
     c->scr_cnt.alloc((size_t)2 * npad);
     c->scr_cnt.zero(c->stream);
@@ -352,7 +357,7 @@ void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
                                                          c->scr_cnt.p);
         KERNEL_CHECK(c);
     }
-    double h[4];
+    double h[5];
     c->host_cnt.resize((size_t)2 * npad);
     CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaMemcpyAsync(c->host_cnt.data(), c->scr_cnt.p, (size_t)2 * npad * sizeof(int),
@@ -361,10 +366,11 @@ void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
     long long ew = 0, mm = 0;
     for (int64_t i = 0; i < c->n_samp; i++) {
         long long sx = c->host_cnt[i], ms = c->host_cnt[npad + i];
-        ew = std::max(ew, sx + ms);
+        ew = std::max(ew, sx);
         mm = std::max(mm, ms);
     }
     plan->max_abs = h[0];
+    plan->max_abs_w = h[4];
     plan->sum_bound = h[1];
     plan->total_missing = (int64_t)h[2];
     plan->scale = (est == SNPREL_GRM_EIGENSTRAT) ? h[3] / (double)std::max<int64_t>(c->n_samp - 1, 1)
@@ -376,11 +382,18 @@ void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
 }
 
 // Choose the fixed-point formats from the (global) plan statistics.
-//   numerator plane: quantisation error of an entry <= 2^-(f+1) * err_weight, wanted <= tol * scale
+//   numerator plane: quantisation error of an entry
+//        <= 2^-(f+1) * err_weight  (U table against the x channel)
+//         + 2^-(fw+1) * max_missing (W table against the m channel),   wanted <= tol * scale
 //   denominator plane (EIGMIX / KING-homo): error <= 2^-(fd+1) * 2 max_missing, wanted <= tol * scale
-static void choose_format(int est, snprel_plan &plan, int &nU, int &nD) {
+// Tensor passes run two at a time, so a table with n digits costs n/2 double launches plus
+// (n odd) one single launch that runs at ~0.8 of a double.
+static double launch_cost(int n) { return (n / 2) + (n % 2) * 0.8; }
+
+static void choose_format(int est, snprel_plan &plan, int &nU, int &nW, int &nD) {
     const double tol = (plan.tol > 0 ? plan.tol : 1e-10) * 0.9;   // 10 % left for float64 rounding in the epilogue
     const bool homo = est == SNPREL_EST_KING_HOMO;
+    const bool any_missing = plan.total_missing > 0;
     const int head = 61 - (int)std::ceil(std::log2(std::max(plan.sum_bound, 1.0)));   // int64 plane headroom
     if (head < 16) fail("fixed-point accumulator cannot hold this data set (sum bound %.3g)", plan.sum_bound);
     double scale = plan.scale;
@@ -389,31 +402,56 @@ static void choose_format(int est, snprel_plan &plan, int &nU, int &nD) {
     // the subtraction is a worst case (every missing SNP at full weight for both samples);
     // never let it shrink the normaliser below 5 % of its complete-data value
     scale = std::max(scale, 0.05 * plan.scale);
-    nU = 0;
+    const double budget = tol * std::max(scale, 1e-300);
+    // the extended-precision W vector needs max|W| * 2^(f + W_EXTRA_BITS) inside int64
+    const int wcap = 61 - W_EXTRA_BITS - (int)std::ceil(std::log2(std::max(std::max(plan.max_abs, plan.max_abs_w), 1.0)));
+    const int fmax = std::min(head, wcap);
+    nU = nW = 0;
     if (!homo) {
-        int f = plan.frac_bits;
-        if (f < 0) {
-            int f_req = 24;
-            if (plan.err_weight > 0 && scale > 0)
-                f_req = (int)std::ceil(std::log2(plan.err_weight / (tol * scale))) - 1;
-            f_req = std::max(16, std::min(f_req, std::min(head, 61 - W_EXTRA_BITS - (int)std::ceil(std::log2(std::max(plan.max_abs, 1.0))))));
-            nU = digits_for(plan.max_abs, f_req);
-            // use every bit the digits offer; the extended-precision W vector needs
-            // max_abs * 2^(f + W_EXTRA_BITS) to stay inside int64
-            int wcap = 61 - W_EXTRA_BITS - (int)std::ceil(std::log2(std::max(plan.max_abs, 1.0)));
-            f = std::min(std::min(frac_cap(plan.max_abs, nU), head), wcap);
+        if (plan.frac_bits >= 0) {           // caller-fixed format
+            nU = digits_for(plan.max_abs, plan.frac_bits);
+            if (any_missing) {
+                if (plan.frac_bits_w < 0 || plan.frac_bits_w > plan.frac_bits) plan.frac_bits_w = plan.frac_bits;
+                nW = digits_for(plan.max_abs_w, plan.frac_bits_w);
+            }
         } else {
-            nU = digits_for(plan.max_abs, f);
+            double best_cost = 1e30, best_err = 1e300;
+            int bU = MAX_DIGITS, bW = any_missing ? MAX_DIGITS : 0;
+            bool feasible = false;
+            for (int a = 1; a <= MAX_DIGITS; a++) {
+                int fa = std::min(frac_cap(plan.max_abs, a), fmax);
+                if (fa < 8) continue;
+                double ea = std::ldexp(plan.err_weight, -(fa + 1));
+                for (int b = any_missing ? 1 : 0; b <= (any_missing ? MAX_DIGITS : 0); b++) {
+                    int fb = b ? std::min(frac_cap(plan.max_abs_w, b), fa) : fa;
+                    if (b && fb < 8) continue;
+                    double err = ea + (b ? std::ldexp((double)plan.max_missing, -(fb + 1)) : 0.0);
+                    bool ok = err <= budget;
+                    double cost = launch_cost(a) + launch_cost(b);
+                    if ((ok && (!feasible || cost < best_cost - 1e-9 || (std::fabs(cost - best_cost) < 1e-9 && err < best_err))) ||
+                        (!ok && !feasible && err < best_err)) {
+                        best_cost = cost;
+                        best_err = err;
+                        bU = a;
+                        bW = b;
+                        feasible = feasible || ok;
+                    }
+                }
+            }
+            nU = bU;
+            nW = bW;
+            plan.frac_bits = std::min(frac_cap(plan.max_abs, nU), fmax);
+            plan.frac_bits_w = nW ? std::min(frac_cap(plan.max_abs_w, nW), plan.frac_bits) : plan.frac_bits;
         }
-        plan.frac_bits = f;
-        plan.digits = nU;
     } else {
         plan.frac_bits = 0;
-        plan.digits = 0;
+        plan.frac_bits_w = 0;
     }
+    plan.digits = nU;
+    plan.digits_w = nW;
     nD = 0;
     plan.frac_bits_d = std::max(plan.frac_bits_d, 0);
-    if (plan.total_missing > 0) {
+    if (any_missing) {
         if (est == SNPREL_GRM_GCTA) {
             nD = 1;               // d in {0,1}: exact integers
             plan.frac_bits_d = 0;
@@ -421,12 +459,13 @@ static void choose_format(int est, snprel_plan &plan, int &nU, int &nD) {
             double dmax = homo ? 0.25 : 1.0;
             int fd_req = 24;
             if (scale > 0)
-                fd_req = (int)std::ceil(std::log2(std::max(2.0 * (double)plan.max_missing, 1.0) / (tol * scale))) - 1;
+                fd_req = (int)std::ceil(std::log2(std::max(2.0 * (double)plan.max_missing, 1.0) / budget)) - 1;
             fd_req = std::max(16, std::min(fd_req, head));
             nD = digits_for(dmax, fd_req);
             plan.frac_bits_d = std::min(std::min(frac_cap(dmax, nD), head), 50);
         }
     }
+    plan.digits_d = nD;
 }
 
 void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
@@ -434,11 +473,9 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     ensure_stats(c);
     snprel_plan plan = *plan_in;
     const bool homo = est == SNPREL_EST_KING_HOMO;
-    int nU = 0, nD = 0;
-    choose_format(est, plan, nU, nD);
-    const int f = plan.frac_bits, fd = plan.frac_bits_d;
-    const bool any_missing = plan.total_missing > 0;
-    int nW = (!homo && any_missing) ? nU : 0;
+    int nU = 0, nW = 0, nD = 0;
+    choose_format(est, plan, nU, nW, nD);
+    const int f = plan.frac_bits, fw = plan.frac_bits_w, fd = plan.frac_bits_d;
     int nD2 = homo ? nD : 0;
     const int npass = nU + nW + nD + nD2;
     const int64_t cap = c->snp_cap, npad = c->n_samp_pad;
@@ -455,14 +492,14 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     ovf.zero(c->stream);
     if (c->n_snp > 0) {
         tables_kernel<<<(unsigned)((c->n_snp + 255) / 256), 256, 0, c->stream>>>(
-            c->stat.p, c->n_snp, cap, est, plan.bayesian, f, fd, nU, nW, nD, nD2, tab.p, c->scalars.p,
+            c->stat.p, c->n_snp, cap, est, plan.bayesian, f, fw, fd, nU, nW, nD, nD2, tab.p, c->scalars.p,
             c->iscalars.p, ovf.p);
         KERNEL_CHECK(c);
     }
     int hovf = 0;
     CUDA_CHECK(cudaMemcpyAsync(&hovf, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    if (hovf) fail("internal: fixed-point digit overflow (table %d, frac_bits %d/%d)", hovf, f, fd);
+    if (hovf) fail("internal: fixed-point digit overflow (table %d, frac_bits %d/%d/%d)", hovf, f, fw, fd);
 
     // per-sample vectors
     c->samp_sum.alloc((size_t)NVEC * npad);
@@ -471,7 +508,7 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     if (c->n_snp > 0) {
         dim3 grid((unsigned)((c->row_bytes + 127) / 128), (unsigned)((c->n_snp + SS_SNPS - 1) / SS_SNPS));
         sample_sum_kernel<<<grid, 128, 0, c->stream>>>(c->geno2b.p, c->stat.p, c->n_snp, c->row_bytes,
-                                                       npad, est, plan.bayesian, f, fd, c->samp_sum.p);
+                                                       npad, est, plan.bayesian, f, fw, fd, c->samp_sum.p);
         KERNEL_CHECK(c);
     }
 
@@ -484,7 +521,7 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     std::vector<GramPass> passes;
     int pass = 0;
     for (int k = 0; k < nU; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, TABB_X, 0, 8 * k});
-    for (int k = 0; k < nW; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, TABB_M, 0, 8 * k});
+    for (int k = 0; k < nW; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, TABB_M, 0, 8 * k + (f - fw)});
     for (int k = 0; k < nD; k++, pass++)
         passes.push_back({tab.p + (int64_t)pass * cap, TABB_M, homo ? 0 : 1, 8 * k});
     for (int k = 0; k < nD2; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, TABB_M, 1, 8 * k});
@@ -606,6 +643,7 @@ static void need_grm_accum(snprel_ctx *c, int est, int bayesian) {
     if (c->accum_est == est && c->accum_reduced) return;
     snprel_plan plan{};
     plan.frac_bits = -1;
+    plan.frac_bits_w = -1;
     plan.frac_bits_d = -1;
     plan.bayesian = bayesian;
     grm_plan_local(c, est, &plan);
@@ -808,6 +846,7 @@ void king_homo_finish(snprel_ctx *c, double *k0, double *k1, int packed) {
     // float sums first (they own acc/samp_sum), then the integer counters (they own cnt)
     snprel_plan plan{};
     plan.frac_bits = -1;
+    plan.frac_bits_w = -1;
     plan.frac_bits_d = -1;
     grm_plan_local(c, SNPREL_EST_KING_HOMO, &plan);
     grm_accumulate(c, SNPREL_EST_KING_HOMO, &plan);

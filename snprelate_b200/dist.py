@@ -59,13 +59,14 @@ def reduce_plan(plan, group=None, device=None):
     import torch
     import torch.distributed as dist
     dev = "cpu" if device is None else device
-    mx = torch.tensor([plan.max_abs], dtype=torch.float64, device=dev)
+    mx = torch.tensor([plan.max_abs, plan.max_abs_w], dtype=torch.float64, device=dev)
     # sums are conservative for the per-sample maxima (max of sums <= sum of maxima)
     sm = torch.tensor([plan.sum_bound, plan.err_weight, plan.scale, float(plan.total_missing),
                        float(plan.max_missing), float(plan.n_snp)], dtype=torch.float64, device=dev)
     dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
     dist.all_reduce(sm, op=dist.ReduceOp.SUM, group=group)
     plan.max_abs = float(mx[0])
+    plan.max_abs_w = float(mx[1])
     plan.sum_bound = float(sm[0])
     plan.err_weight = float(sm[1])
     plan.scale = float(sm[2])

@@ -19,7 +19,7 @@ for e in ests:
     hot, nl, units = ctx.last_hot_kernel()
     pl = ctx.last_plan() if ids[e] < 10 else None
     if pl is not None:
-        print(f"   plan: digits {pl.digits} frac_bits {pl.frac_bits}/{pl.frac_bits_d} max_abs {pl.max_abs:.3f} "
+        print(f"   plan: digits U{pl.digits}/W{pl.digits_w}/D{pl.digits_d} frac_bits {pl.frac_bits}/{pl.frac_bits_w}/{pl.frac_bits_d} max_abs {pl.max_abs:.3f}/{pl.max_abs_w:.3f} "
               f"err_weight {pl.err_weight:.4g} scale {pl.scale:.4g} sum_bound {pl.sum_bound:.4g} "
               f"missing {pl.total_missing} step {ctx.last_step_ms():.1f} ms")
     print(f"{e}: N={n} M={m} miss={miss} hot {hot:.1f} ms in {nl} launches, wall {wall*1e3:.1f} ms, "
