@@ -1,0 +1,203 @@
+// R-side binding of libsnprel_b200.so: drop-in bodies for the reference's .Call entry points
+// of the relatedness path.  SOURCE ONLY in this repository -- the build image has neither R nor
+// gdsfmt, so this file is not compiled here; it is written against the
+// reference's own headers (dGenGWAS.h) and is meant to replace the bodies of
+//   gnrGRM              src/genPCA.cpp:1614-1717      gnrIBSAve          src/genIBS.cpp:441-497
+//   gnrPCA (exact)      src/genPCA.cpp:1355-1452      gnrIBSNum          src/genIBS.cpp:500-550
+//   gnrEigMix           src/genEIGMIX.cpp:656-735     gnrIBD_KING_Robust src/genKING.cpp:576-679
+//   gnrGRM_avg_val      src/genPCA.cpp:1608           gnrIBD_KING_Homo   src/genKING.cpp:493-570
+//                                                     gnrIBD_Beta        src/genBeta.cpp:361-460
+// inside SNPRelate.so, keeping the workspace layer (gnrSetGenoSpace / gnrSelSNP_Base,
+// src/SNPRelate.cpp:76-214) and the R code untouched: every routine streams the SELECTED
+// genotypes through CdBaseWorkSpace::snpRead (src/dGenGWAS.h:94) into the device workspace and
+// returns R objects of exactly the reference's shape.
+#if defined(SNPREL_BUILD_R_SHIM)
+
+#include <vector>
+
+#include "dGenGWAS.h"          // the reference's workspace (GWAS::MCWorkingGeno, SEXP helpers)
+#include "snprel_b200.h"
+
+using namespace GWAS;
+
+namespace {
+
+struct Ctx {
+    snprel_ctx *h = nullptr;
+    Ctx() {
+        if (snprel_create(&h, 0) != 0) throw ErrCoreArray("%s", snprel_last_error(nullptr));
+    }
+    ~Ctx() { snprel_destroy(h); }
+    void ck(int rc) {
+        if (rc != 0) throw ErrCoreArray("%s", snprel_last_error(h));
+    }
+};
+
+// CGenoReadBySNP equivalent: selected SNPs x selected samples -> device, block by block
+void load_workspace(Ctx &c) {
+    CdBaseWorkSpace &sp = MCWorkingGeno.Space();
+    const int n = sp.SampleNum(), m = sp.SNPNum();
+    c.ck(snprel_geno_begin(c.h, n, m));
+    const int block = std::max(1, (64 << 20) / std::max(n, 1));
+    std::vector<C_UInt8> buf((size_t)block * n);
+    for (int st = 0; st < m; st += block) {
+        int cnt = std::min(block, m - st);
+        sp.snpRead(st, cnt, &buf[0], RDim_Sample_X_SNP);        // u8 [cnt][n], >2 = missing
+        c.ck(snprel_geno_push_u8(c.h, &buf[0], cnt));
+    }
+}
+
+SEXP sym_result(size_t n, bool packed) {
+    return packed ? NEW_NUMERIC(n * (n + 1) / 2) : Rf_allocMatrix(REALSXP, n, n);
+}
+
+double g_avg_val = 0;
+
+}  // namespace
+
+extern "C" {
+
+COREARRAY_DLL_EXPORT SEXP gnrGRM_avg_val() { return Rf_ScalarReal(g_avg_val); }
+
+COREARRAY_DLL_EXPORT SEXP gnrGRM(SEXP NumThread, SEXP Method, SEXP GDS, SEXP useMatrix, SEXP Verbose) {
+    const char *mt = CHAR(STRING_ELT(Method, 0));
+    COREARRAY_TRY
+        if (!Rf_isNull(GDS)) throw ErrCoreArray("GDS output is streamed by the host wrapper (INTEGRATION.md).");
+        int method = !strcmp(mt, "Eigenstrat") ? SNPREL_GRM_EIGENSTRAT : !strcmp(mt, "GCTA") ? SNPREL_GRM_GCTA
+                   : !strcmp(mt, "Corr") ? SNPREL_GRM_CORR : !strcmp(mt, "EIGMIX") ? SNPREL_GRM_EIGMIX
+                   : !strcmp(mt, "IndivBeta") ? SNPREL_GRM_INDIVBETA : -1;
+        if (method < 0) throw ErrCoreArray("Invalid 'method'!");
+        Ctx c;
+        load_workspace(c);
+        const size_t n = MCWorkingGeno.Space().SampleNum();
+        const bool packed = (Rf_asLogical(useMatrix) == TRUE) && method != SNPREL_GRM_CORR;
+        rv_ans = PROTECT(sym_result(n, packed));
+        c.ck(snprel_grm(c.h, method, REAL(rv_ans), packed, &g_avg_val));
+        UNPROTECT(1);
+    COREARRAY_CATCH
+}
+
+COREARRAY_DLL_EXPORT SEXP gnrPCA(SEXP EigenCnt, SEXP Algorithm, SEXP NumThread, SEXP ParamList, SEXP Verbose) {
+    COREARRAY_TRY
+        if (strcmp(CHAR(STRING_ELT(Algorithm, 0)), "exact") != 0)
+            throw ErrCoreArray("only the exact algorithm is accelerated");
+        Ctx c;
+        load_workspace(c);
+        const int n = MCWorkingGeno.Space().SampleNum();
+        int nEig = Rf_asInteger(EigenCnt);
+        if (nEig < 0) throw ErrCoreArray("Invalid 'eigen.cnt'.");
+        if (nEig > n) nEig = n;
+        const bool bayes = Rf_asLogical(RGetListElement(ParamList, "bayesian")) == TRUE;
+        const bool need = Rf_asLogical(RGetListElement(ParamList, "need.genmat")) == TRUE;
+        const bool only = Rf_asLogical(RGetListElement(ParamList, "genmat.only")) == TRUE;
+        PROTECT(rv_ans = NEW_LIST(5));
+        SEXP genmat = R_NilValue, eval = R_NilValue, evec = R_NilValue;
+        if (need) { genmat = PROTECT(Rf_allocMatrix(REALSXP, n, n)); SET_ELEMENT(rv_ans, 1, genmat); UNPROTECT(1); }
+        if (!only) {
+            eval = PROTECT(NEW_NUMERIC(n)); SET_ELEMENT(rv_ans, 2, eval); UNPROTECT(1);
+            evec = PROTECT(Rf_allocMatrix(REALSXP, n, nEig)); SET_ELEMENT(rv_ans, 3, evec); UNPROTECT(1);
+        }
+        double tx = 0, tv = 0;
+        c.ck(snprel_pca(c.h, nEig, bayes, need ? REAL(genmat) : NULL, &tx, &tv,
+                        only ? NULL : REAL(eval), only ? NULL : REAL(evec)));
+        SET_ELEMENT(rv_ans, 0, Rf_ScalarReal(tx));
+        SET_ELEMENT(rv_ans, 4, Rf_ScalarReal(tv));
+        UNPROTECT(1);
+    COREARRAY_CATCH
+}
+
+COREARRAY_DLL_EXPORT SEXP gnrEigMix(SEXP EigenCnt, SEXP NumThread, SEXP ParamList, SEXP Verbose) {
+    int diag_adj = Rf_asLogical(RGetListElement(ParamList, "diagadj"));
+    if (diag_adj == NA_LOGICAL) Rf_error("'diagadj' must be TRUE or FALSE.");
+    int need_ibd = Rf_asLogical(RGetListElement(ParamList, "ibdmat"));
+    if (need_ibd == NA_LOGICAL) Rf_error("'ibdmat' must be TRUE or FALSE.");
+    COREARRAY_TRY
+        Ctx c;
+        load_workspace(c);
+        const int n = MCWorkingGeno.Space().SampleNum();
+        int nEig = Rf_asInteger(EigenCnt);
+        if (nEig < 0 || nEig > n) nEig = n;
+        PROTECT(rv_ans = NEW_LIST(4));
+        SEXP af = PROTECT(NEW_NUMERIC(MCWorkingGeno.Space().SNPNum())); SET_ELEMENT(rv_ans, 2, af); UNPROTECT(1);
+        SEXP ibd = R_NilValue, eval = R_NilValue, evec = R_NilValue;
+        if (need_ibd) { ibd = PROTECT(Rf_allocMatrix(REALSXP, n, n)); SET_ELEMENT(rv_ans, 3, ibd); UNPROTECT(1); }
+        if (nEig > 0) {
+            eval = PROTECT(NEW_NUMERIC(n)); SET_ELEMENT(rv_ans, 0, eval); UNPROTECT(1);
+            evec = PROTECT(Rf_allocMatrix(REALSXP, n, nEig)); SET_ELEMENT(rv_ans, 1, evec); UNPROTECT(1);
+        }
+        c.ck(snprel_eigmix(c.h, nEig, diag_adj == TRUE, need_ibd ? REAL(ibd) : NULL, REAL(af),
+                           nEig > 0 ? REAL(eval) : NULL, nEig > 0 ? REAL(evec) : NULL));
+        UNPROTECT(1);
+    COREARRAY_CATCH
+}
+
+COREARRAY_DLL_EXPORT SEXP gnrIBSAve(SEXP NumThread, SEXP useMatrix, SEXP Verbose) {
+    COREARRAY_TRY
+        Ctx c;
+        load_workspace(c);
+        const size_t n = MCWorkingGeno.Space().SampleNum();
+        const bool packed = Rf_asLogical(useMatrix) == TRUE;
+        rv_ans = PROTECT(sym_result(n, packed));
+        c.ck(snprel_ibs_ave(c.h, REAL(rv_ans), packed));
+        UNPROTECT(1);
+    COREARRAY_CATCH
+}
+
+COREARRAY_DLL_EXPORT SEXP gnrIBSNum(SEXP NumThread, SEXP Verbose) {
+    COREARRAY_TRY
+        Ctx c;
+        load_workspace(c);
+        const int n = MCWorkingGeno.Space().SampleNum();
+        PROTECT(rv_ans = NEW_LIST(3));
+        SEXP m[3];
+        for (int k = 0; k < 3; k++) { m[k] = PROTECT(Rf_allocMatrix(INTSXP, n, n)); SET_ELEMENT(rv_ans, k, m[k]); UNPROTECT(1); }
+        c.ck(snprel_ibs_num(c.h, INTEGER(m[0]), INTEGER(m[1]), INTEGER(m[2])));
+        UNPROTECT(1);
+    COREARRAY_CATCH
+}
+
+COREARRAY_DLL_EXPORT SEXP gnrIBD_KING_Robust(SEXP FamilyID, SEXP NumThread, SEXP useMatrix, SEXP Verbose) {
+    COREARRAY_TRY
+        Ctx c;
+        load_workspace(c);
+        const size_t n = MCWorkingGeno.Space().SampleNum();
+        const bool packed = Rf_asLogical(useMatrix) == TRUE;
+        PROTECT(rv_ans = NEW_LIST(2));
+        SEXP a = PROTECT(sym_result(n, packed)); SET_ELEMENT(rv_ans, 0, a); UNPROTECT(1);
+        SEXP b = PROTECT(sym_result(n, packed)); SET_ELEMENT(rv_ans, 1, b); UNPROTECT(1);
+        // NA_INTEGER == INT32_MIN == SNPREL_NA_INT: the family vector passes through unchanged
+        c.ck(snprel_king_robust(c.h, INTEGER(FamilyID), REAL(a), REAL(b), packed));
+        UNPROTECT(1);
+    COREARRAY_CATCH
+}
+
+COREARRAY_DLL_EXPORT SEXP gnrIBD_KING_Homo(SEXP NumThread, SEXP useMatrix, SEXP Verbose) {
+    COREARRAY_TRY
+        Ctx c;
+        load_workspace(c);
+        const size_t n = MCWorkingGeno.Space().SampleNum();
+        const bool packed = Rf_asLogical(useMatrix) == TRUE;
+        PROTECT(rv_ans = NEW_LIST(2));
+        SEXP a = PROTECT(sym_result(n, packed)); SET_ELEMENT(rv_ans, 0, a); UNPROTECT(1);
+        SEXP b = PROTECT(sym_result(n, packed)); SET_ELEMENT(rv_ans, 1, b); UNPROTECT(1);
+        c.ck(snprel_king_homo(c.h, REAL(a), REAL(b), packed));
+        UNPROTECT(1);
+    COREARRAY_CATCH
+}
+
+COREARRAY_DLL_EXPORT SEXP gnrIBD_Beta(SEXP Inbreeding, SEXP NumThread, SEXP useMatrix, SEXP Verbose) {
+    int inbreeding = Rf_asLogical(Inbreeding);
+    if (inbreeding == NA_LOGICAL) Rf_error("'inbreeding' must be TRUE or FALSE.");
+    COREARRAY_TRY
+        Ctx c;
+        load_workspace(c);
+        const size_t n = MCWorkingGeno.Space().SampleNum();
+        const bool packed = Rf_asLogical(useMatrix) == TRUE;
+        rv_ans = PROTECT(sym_result(n, packed));
+        c.ck(snprel_indiv_beta(c.h, inbreeding == TRUE, REAL(rv_ans), packed, &g_avg_val));
+        UNPROTECT(1);
+    COREARRAY_CATCH
+}
+
+}  // extern "C"
+#endif  // SNPREL_BUILD_R_SHIM
