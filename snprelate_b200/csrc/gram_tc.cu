@@ -33,9 +33,8 @@
 //     tcgen05.commit releases pipeline stages back to the producers through mbarriers.
 //   * after the last SNP stage the producer warps become the epilogue: tcgen05.ld the
 //     accumulators and issue the 64-bit atomics.
-#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
-
 #include "common.cuh"
+#include "tc_ptx.cuh"   // CUtensorMap types; the encoder is fetched through cudaGetDriverEntryPoint
 
 namespace snprel {
 namespace tc {
@@ -88,179 +87,10 @@ struct Params {
     int *error_flag;
 };
 
-// ---- PTX wrappers -----------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar)
-                 : "memory");
-}
-// Arrive whose ADDRESS is data-dependent on values just read from shared memory, so the
-// release of a ring slot cannot be issued before the ld.shared reading that slot have
-// returned (the TMA refill would otherwise race with loads still queued in the LSU).
-// `sh32` is a kernel parameter that is always 32: shr.u32 by 32 yields 0, which the
-// assembler cannot fold away.
-__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, uint32_t dep, uint32_t sh32) {
-    asm volatile("{\n .reg .b64 st;\n .reg .b32 z;\n shr.u32 z, %1, %2;\n add.u32 z, z, %0;\n"
-                 " mbarrier.arrive.shared::cta.b64 st, [z];\n}" ::"r"(bar), "r"(dep), "r"(sh32)
-                 : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        " selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// bounded wait: a protocol bug must surface as an error, never as a hung GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *error_flag, int code) {
-    if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {   // ~2 s at 2 GHz
-            if (error_flag) atomicExch(error_flag, code);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void fence_proxy_async_smem() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem),
-                 "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                        uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
-        " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-          "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
-          "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
-          "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
-                                             uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c),
-                 "r"(d)
-                 : "memory");
-}
-// volatile so that the prefetch really is issued one stage ahead (a plain __ldg gets
-// sunk by the compiler to its first use, exposing the full L2 latency every stage)
-__device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t *p) {
-    uint32_t r;
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ uint4 ld_nc_v4(const uint8_t *p) {
-    uint4 r;
-    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
-
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar),
-                 "r"(bytes)
-                 : "memory");
-}
-// TMA: one 2-D box (16 bytes x SK rows) of the packed genotype matrix -> shared memory
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar)
-        : "memory");
-}
-// bulk copy of a contiguous run (digit table of one stage)
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
-    uint32_t r;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
-    return r;
-}
-
-// shared-memory matrix descriptor, MN-major, no swizzle (SWIZZLE_NONE / "interleave"):
-// core matrix = 8 K-rows x 16 bytes (16 consecutive samples), 128 contiguous bytes.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);   // bits 46-47: version 1 (sm_100)
-}
-
 // instruction descriptor for kind::i8: D=s32, A=s8, B=s8, both MN-major, M=128, N=256
 __device__ __forceinline__ uint32_t make_idesc() {
     return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TN >> 3) << 17) |
            ((uint32_t)(TM >> 4) << 24);
-}
-
-// position inside a 16-sample core row -> sample offset (the producer emits even
-// samples first: bytes [0,2,4,6 | 1,3,5,7 | 8,10,12,14 | 9,11,13,15])
-__device__ __forceinline__ int core_pos_to_sample(int pos) {
-    int grp = pos >> 2;
-    return ((grp >> 1) << 3) + (grp & 1) + ((pos & 3) << 1);
-}
-
-// expand one packed word (16 genotypes) against `np` tables and store the rows
-template <int NP>
-__device__ __forceinline__ void expand_word(uint32_t x, const uint32_t (&tab)[NP],
-                                            const uint32_t (&dst)[NP]) {
-    uint32_t e = x & 0x33333333u;           // even samples: selector nibbles 00gg
-    uint32_t o = (x >> 2) & 0x33333333u;    // odd samples
-    uint32_t eh = e >> 16, oh = o >> 16;
-#pragma unroll
-    for (int p = 0; p < NP; p++) {
-        uint32_t t = tab[p];
-        st_shared_v4(dst[p], __byte_perm(t, 0, e), __byte_perm(t, 0, o), __byte_perm(t, 0, eh),
-                     __byte_perm(t, 0, oh));
-    }
 }
 
 template <int NP>
@@ -461,6 +291,10 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
                  bool upper_only) {
     using namespace tc;
     if (npass <= 0) return;
+    if (!(c->debug_flags & 4u)) {   // default: CTA-pair (cta_group::2) kernel, gram_tc2.cu
+        gram_tc2_run(c, passes, npass, out_planes, upper_only);
+        return;
+    }
     geno_pad_tail(c);
     const int64_t n = c->n_samp, npad = c->n_samp_pad;
     const int tiles_m = (int)((n + TM - 1) / TM), tiles_n = (int)((n + TN - 1) / TN);

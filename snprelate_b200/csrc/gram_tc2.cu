@@ -1,0 +1,448 @@
+// K1, CTA-pair version: the same table Gram as gram_tc.cu, but a cluster of two CTAs (one
+// TPC, tcgen05 cta_group::2) owns a 256 x 256 sample tile.  CTA r of the pair expands A rows
+// [256 tm + 128 r, +128) for both passes and only ITS HALF of the B rows
+// [256 tn + 128 r, +128); one thread of CTA 0 issues tcgen05.mma.cta_group::2 (M=256, N=256,
+// K=32) which reads A and the B halves from both SMs' shared memory and accumulates 128 x 256
+// int32 per pass into each SM's TMEM.  Per CTA and stage this halves the B expansion work and
+// the B shared-memory traffic (48 KB written / 64 KB read by the tensor core instead of
+// 64 KB / 96 KB), which is what bounded the single-CTA kernel (profiles/r01_gram_tc_full.txt).
+//
+// Protocol differences to the single-CTA kernel:
+//   * stage-full barrier lives in CTA 0 and counts the producers of BOTH CTAs; CTA 1's
+//     producers arrive on it remotely (mapa + mbarrier.arrive.release.cluster);
+//   * tcgen05.commit multicasts the stage-empty / accumulator-ready arrivals to both CTAs;
+//   * TMEM is allocated / freed with cta_group::2 by warp 0 of each CTA, bracketed by cluster
+//     barriers.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace snprel {
+namespace tc2 {
+
+using namespace tc;
+
+constexpr int TM2 = 256;           // tile rows (A), 128 per CTA
+constexpr int TN2 = 256;           // tile cols (B), 128 per CTA
+constexpr int HM = 128, HN = 128;  // per-CTA halves
+constexpr int SK = 128;            // SNPs per stage
+constexpr int MMA_K = 32;
+constexpr int NSTAGE = 4;
+constexpr int MAXP = 2;
+constexpr int PROD_WARPS = 8;
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int FIRST_PROD_WARP = 2;
+constexpr int THREADS = 32 * (FIRST_PROD_WARP + PROD_WARPS);
+constexpr int A_BYTES = HM * SK;   // 16 KB per pass per stage
+constexpr int B_BYTES = HN * SK;   // 16 KB per stage
+constexpr int STAGE_BYTES = MAXP * A_BYTES + B_BYTES;   // 48 KB
+constexpr int PF_DEPTH = 3;
+constexpr int PF_BOX = SK * 16;
+constexpr int PF_NBOX = (HM + HN) / 64;                  // 2 A boxes + 2 B boxes
+constexpr int PF_TAB = SK * 4;
+constexpr int PF_BYTES = PF_NBOX * PF_BOX + MAXP * PF_TAB;   // 9 KB
+constexpr int BAR_OFFSET = NSTAGE * STAGE_BYTES + PF_DEPTH * PF_BYTES;
+constexpr int SMEM_BYTES = BAR_OFFSET + 1024;
+constexpr int LBO = (HM / 16) * 128;   // 8 cores per 8-SNP group (A and B halves alike)
+constexpr int SBO = 128;
+constexpr uint32_t TMEM_COLS = 512;
+
+struct Params {
+    const uint32_t *tabA[MAXP];
+    uint32_t tabB;
+    int npass;
+    int plane[MAXP];
+    int shift[MAXP];
+    long long *out;
+    long long ld;
+    long long plane_stride;
+    long long n_samp;
+    const int2 *tiles;       // (tile_m, tile_n) in units of 256 samples
+    int stages_total;
+    int stages_per_split;
+    int upper_only;
+    uint32_t sh32;
+    int *error_flag;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default .release.cta semantics as in CUTLASS' ClusterBarrier::arrive(cta_id): an explicit
+    // .release.cluster costs a MEMBAR.ALL.GPU + ERRBAR per thread and stage (33 % of all stall
+    // samples in profiles/r01 notes); the data being published is this CTA's own shared memory,
+    // already ordered for the async proxy by fence.proxy.async
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int *error_flag, int code) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            if (error_flag) atomicExch(error_flag, code);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
+    asm volatile(
+        "{\n .reg .b16 m;\n mov.b16 m, 3;\n"
+        " tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n}"
+        ::"r"(bar)
+        : "memory");
+}
+// D=s32, A=s8, B=s8, MN-major, M=256 (pair), N=256
+__device__ __forceinline__ uint32_t make_idesc2() {
+    return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TN2 >> 3) << 17) |
+           ((uint32_t)(TM2 >> 4) << 24);
+}
+
+template <int NP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + BAR_OFFSET;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
+    const uint32_t accum_bar = bar_base + 8u * (2 * NSTAGE);
+    auto pf_full = [&](int s) { return bar_base + 8u * (2 * NSTAGE + 1 + s); };
+    auto pf_empty = [&](int s) { return bar_base + 8u * (2 * NSTAGE + 1 + PF_DEPTH + s); };
+    constexpr int SLOT_IDX = 2 * NSTAGE + 1 + 2 * PF_DEPTH;
+    const uint32_t tmem_slot = bar_base + 8u * SLOT_IDX;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem + BAR_OFFSET + 8 * SLOT_IDX);
+    const uint32_t pf_base = smem_base + NSTAGE * STAGE_BYTES;
+
+    const int2 tile = P.tiles[blockIdx.x >> 1];
+    const int st_begin = blockIdx.y * P.stages_per_split;
+    const int st_end = min(P.stages_total, st_begin + P.stages_per_split);
+    const int nst = st_end - st_begin;   // identical in both CTAs of the pair
+    if (nst <= 0) return;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int s = 0; s < NSTAGE; s++) {
+                mbar_init(full_bar(s), 2 * PROD_THREADS);   // producers of both CTAs (used in CTA 0 only)
+                mbar_init(empty_bar(s), 1);
+            }
+            mbar_init(accum_bar, 1);
+            for (int s = 0; s < PF_DEPTH; s++) {
+                mbar_init(pf_full(s), 1);
+                mbar_init(pf_empty(s), PROD_THREADS);
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc2(tmem_slot, TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();          // peer barriers are initialised before anyone arrives remotely
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (rank == 0) {
+            const uint32_t idesc = make_idesc2();
+            for (int it = 0; it < nst; it++) {
+                const int s = it % NSTAGE;
+                const uint32_t phase = (uint32_t)(it / NSTAGE) & 1u;
+                mbar_wait_cluster(full_bar(s), phase, P.error_flag, 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t stage_addr = smem_base + s * STAGE_BYTES;
+#pragma unroll
+                    for (int j = 0; j < SK / MMA_K; j++) {
+                        uint64_t bdesc = make_desc(stage_addr + MAXP * A_BYTES + j * 4 * LBO, LBO, SBO);
+#pragma unroll
+                        for (int p = 0; p < NP; p++) {
+                            uint64_t adesc = make_desc(stage_addr + p * A_BYTES + j * 4 * LBO, LBO, SBO);
+                            umma2_i8(tmem_base + (uint32_t)(p * TN2), adesc, bdesc, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma2_commit_mc(empty_bar(s));
+                }
+                __syncwarp();
+            }
+            if (lane == 0) umma2_commit_mc(accum_bar);
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===================== TMA loader =====================
+        if (lane == 0) {
+            const int ax = (tile.x * TM2 + (int)rank * HM) / 4, bx = (tile.y * TN2 + (int)rank * HN) / 4;
+            for (int it = 0; it < nst; it++) {
+                const int sl = it % PF_DEPTH;
+                const uint32_t ph = (uint32_t)(it / PF_DEPTH) & 1u;
+                mbar_wait(pf_empty(sl), ph ^ 1u, P.error_flag, 4);
+                const uint32_t slot = pf_base + (uint32_t)sl * PF_BYTES;
+                const uint32_t bar = pf_full(sl);
+                mbar_arrive_expect_tx(bar, PF_NBOX * PF_BOX + NP * PF_TAB);
+                const int y = (st_begin + it) * SK;
+#pragma unroll
+                for (int q = 0; q < HM / 64; q++) tma_load_2d(slot + q * PF_BOX, &tmap, ax + q * 16, y, bar);
+#pragma unroll
+                for (int q = 0; q < HN / 64; q++) tma_load_2d(slot + (HM / 64 + q) * PF_BOX, &tmap, bx + q * 16, y, bar);
+#pragma unroll
+                for (int q = 0; q < NP; q++)
+                    bulk_load(slot + PF_NBOX * PF_BOX + q * PF_TAB, P.tabA[q] + (long long)y, PF_TAB, bar);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== producers =====================
+        const int p = threadIdx.x - 32 * FIRST_PROD_WARP;
+        const int sl = p & (SK - 1);   // SNP within the stage
+        const int half = p >> 7;       // which 64-sample quad of this CTA's A half and of its B half
+        const int kg = sl >> 3, r = sl & 7;
+        uint32_t tb[1] = {P.tabB};
+        const uint32_t a_off = kg * LBO + (half * 4) * SBO + r * 16;
+        const uint32_t b_off = MAXP * A_BYTES + a_off;
+        const uint32_t pa = half * PF_BOX + sl * 16;
+        const uint32_t pb = (HM / 64 + half) * PF_BOX + sl * 16;
+        const uint32_t pt = PF_NBOX * PF_BOX + sl * 4;
+        uint32_t full_remote[NSTAGE];
+#pragma unroll
+        for (int s = 0; s < NSTAGE; s++) full_remote[s] = mapa(full_bar(s), 0);   // leader's barrier
+
+#pragma unroll 1
+        for (int it = 0; it < nst; it++) {
+            const int s = it % NSTAGE;
+            const uint32_t phase = (uint32_t)(it / NSTAGE) & 1u;
+            const int ps = it % PF_DEPTH;
+            mbar_wait(pf_full(ps), (uint32_t)(it / PF_DEPTH) & 1u, P.error_flag, 5);
+            const uint32_t slot = pf_base + (uint32_t)ps * PF_BYTES;
+            const uint4 ca = ld_shared_v4(slot + pa);
+            const uint4 cb = ld_shared_v4(slot + pb);
+            uint32_t ct[NP];
+#pragma unroll
+            for (int q = 0; q < NP; q++) ct[q] = ld_shared_u32(slot + pt + q * PF_TAB);
+            mbar_arrive_after(pf_empty(ps), ca.x ^ ca.y ^ ca.z ^ ca.w ^ cb.x ^ cb.y ^ cb.z ^ cb.w ^ ct[0] ^ ct[NP - 1],
+                              P.sh32);
+
+            mbar_wait(empty_bar(s), phase ^ 1u, P.error_flag, 2);
+            const uint32_t stage_addr = smem_base + s * STAGE_BYTES;
+            const uint32_t aw[4] = {ca.x, ca.y, ca.z, ca.w};
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                uint32_t dst[NP];
+#pragma unroll
+                for (int q = 0; q < NP; q++) dst[q] = stage_addr + q * A_BYTES + a_off + w * SBO;
+                expand_word<NP>(aw[w], ct, dst);
+            }
+            const uint32_t bw[4] = {cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                uint32_t dst[1] = {stage_addr + b_off + w * SBO};
+                expand_word<1>(bw[w], tb, dst);
+            }
+            fence_proxy_async_smem();
+            // constant-index select keeps full_remote[] in registers
+            uint32_t fr = full_remote[0];
+#pragma unroll
+            for (int k = 1; k < NSTAGE; k++) fr = (s == k) ? full_remote[k] : fr;
+            mbar_arrive_cluster(fr);
+        }
+
+        // ===================== epilogue (each CTA drains its own 128 rows) =====================
+        mbar_wait(accum_bar, 0, P.error_flag, 3);
+        tc_fence_after();
+        const int quarter = warp & 3;
+        const int colhalf = (warp - FIRST_PROD_WARP) >> 2;
+        const int row = quarter * 32 + lane;
+        const long long gi = (long long)tile.x * TM2 + (long long)rank * HM + (row & ~15) + core_pos_to_sample(row & 15);
+#pragma unroll 1
+        for (int q = 0; q < NP; q++) {
+            long long *outp = P.out + (long long)P.plane[q] * P.plane_stride + gi * P.ld;
+            const long long mul = 1ll << P.shift[q];
+#pragma unroll 1
+            for (int cc = 0; cc < 4; cc++) {
+                const int col0 = colhalf * 128 + cc * 32;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(q * TN2 + col0), v);
+                if (gi < P.n_samp) {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) {
+                        int col = col0 + k;
+                        long long gj = (long long)tile.y * TN2 + (col & ~15) + core_pos_to_sample(col & 15);
+                        int val = (int)v[k];
+                        if (val != 0 && gj < P.n_samp && (!P.upper_only || gj >= gi))
+                            atomicAdd(reinterpret_cast<unsigned long long *>(outp + gj),
+                                      (unsigned long long)((long long)val * mul));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();          // both CTAs are done with TMEM and with each other's barriers
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace tc2
+
+// ---------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------
+// fraction of the SM-time of a launch that does useful work when `items` equal work items run
+// `slots` at a time (wave quantisation)
+static double wave_efficiency(int64_t items, int64_t slots) {
+    int64_t waves = (items + slots - 1) / slots;
+    return (double)items / (double)(waves * slots);
+}
+
+void gram_tc2_run(snprel_ctx *c, const GramPass *passes, int npass, long long *out_planes, bool upper_only) {
+    using namespace tc2;
+    if (npass <= 0) return;
+    geno_pad_tail(c);
+    const int64_t n = c->n_samp, npad = c->n_samp_pad;
+    const int nt = (int)((n + TM2 - 1) / TM2);
+    std::vector<int2> &tiles = c->host_tiles;
+    tiles.clear();
+    for (int tm = 0; tm < nt; tm++)
+        for (int tn = (upper_only ? tm : 0); tn < nt; tn++) tiles.push_back(make_int2(tm, tn));
+    DevBuf<int2> &dtiles = c->scr_tiles;
+    dtiles.alloc(tiles.size());
+    CUDA_CHECK(cudaMemcpyAsync(dtiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice,
+                               c->stream));
+    c->scr_flags.alloc(2);
+    int *derr = c->scr_flags.p + 1;
+    CUDA_CHECK(cudaMemsetAsync(derr, 0, sizeof(int), c->stream));
+
+    const int stages_total = (int)(round_up(std::max<int64_t>(c->n_snp, 1), SK) / SK);
+    // SNP splits: enough work items to fill the chip, chosen to minimise the wave-quantisation tail
+    const int64_t slots = std::max(1, c->num_sms / 2);   // concurrent CTA pairs
+    const int64_t ntile = (int64_t)tiles.size();
+    int64_t best = 1;
+    double best_eff = -1;
+    for (int64_t sp = 1; sp <= std::min<int64_t>(stages_total, 64); sp++) {
+        // each extra split costs an epilogue (~0.3 stage-equivalents of atomics per 256 stages)
+        double eff = wave_efficiency(ntile * sp, slots) * (1.0 - 0.002 * (double)(sp - 1));
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = sp;
+        }
+        if (ntile * sp >= 8 * slots && eff > 0.97) break;
+    }
+    int64_t splits = best;
+    if (c->debug_flags & 2u) splits = 1;   // test hook: one CTA pair walks the whole SNP range
+    int sps = (int)((stages_total + splits - 1) / splits);
+    const int max_stages_i32 = (int)((2147483647ll / 256) / SK);   // int32 accumulator headroom
+    sps = std::min(sps, max_stages_i32);
+    splits = (stages_total + sps - 1) / sps;
+    if (splits > 65535) fail("too many SNP splits");
+
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) fail("cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    alignas(64) CUtensorMap tmap;
+    {
+        const int64_t rows = round_up(std::max<int64_t>(c->n_snp, 1), SK);
+        cuuint64_t gdim[2] = {(cuuint64_t)c->row_bytes, (cuuint64_t)rows};
+        cuuint64_t gstride[1] = {(cuuint64_t)c->row_bytes};
+        cuuint32_t box[2] = {16, (cuuint32_t)SK};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->geno2b.p, gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
+
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_done = true;
+    }
+
+    std::vector<char> used((size_t)npass, 0);
+    for (int i = 0; i < npass; i++) {
+        if (used[i]) continue;
+        Params P{};
+        P.tabB = passes[i].tabB;
+        P.out = out_planes;
+        P.ld = npad;
+        P.plane_stride = npad * npad;
+        P.n_samp = n;
+        P.tiles = dtiles.p;
+        P.stages_total = stages_total;
+        P.stages_per_split = sps;
+        P.upper_only = upper_only ? 1 : 0;
+        P.sh32 = 32;
+        P.error_flag = derr;
+        int np = 0;
+        for (int j = i; j < npass && np < MAXP; j++) {
+            if (used[j] || passes[j].tabB != passes[i].tabB) continue;
+            P.tabA[np] = passes[j].tabA;
+            P.plane[np] = passes[j].plane;
+            P.shift[np] = passes[j].shift;
+            used[j] = 1;
+            np++;
+        }
+        P.npass = np;
+        dim3 grid((unsigned)(2 * tiles.size()), (unsigned)splits);
+        if (np == 2)
+            table_gram_kernel2<2><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
+        else
+            table_gram_kernel2<1><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
+        KERNEL_CHECK(c);
+        c->hot_launches++;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    int herr = 0;
+    CUDA_CHECK(cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (herr) fail("table_gram_kernel2: pipeline barrier %d timed out", herr);
+}
+
+}  // namespace snprel
