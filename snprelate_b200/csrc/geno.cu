@@ -52,6 +52,19 @@ __global__ void repack_2b_kernel(const uint8_t *__restrict__ src, uint8_t *__res
     dst[idx] = (uint8_t)v;
 }
 
+// bytes [pad_from, row_bytes) of every row: keep the valid genotypes of a partial byte, set the
+// rest (and every byte the host copy did not cover) to the missing code
+__global__ void fix_pad_kernel(uint8_t *__restrict__ dst, int64_t cnt, int64_t n_samp, int64_t pad_from,
+                               int64_t pad_bytes, int64_t copied, int64_t row_bytes) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cnt * pad_bytes) return;
+    int64_t r = idx / pad_bytes, b = pad_from + (idx - r * pad_bytes);
+    uint32_t v = 0xFF;
+    int64_t rem = n_samp - b * 4;   // valid genotypes in this byte
+    if (rem > 0 && b < copied) v = dst[r * row_bytes + b] | ((0xFFu << (2 * rem)) & 0xFF);
+    dst[r * row_bytes + b] = (uint8_t)v;
+}
+
 __global__ void unpack_u8_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
                                  int64_t cnt, int64_t n_samp, int64_t row_bytes) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -253,25 +266,20 @@ void geno_push_2b(snprel_ctx *c, const uint8_t *host, int64_t cnt, int64_t row_b
         fail("snprel_geno_push_2b: row_bytes %lld too small for %lld samples",
              (long long)row_bytes_in, (long long)c->n_samp);
     uint8_t *dst = c->geno2b.p + c->n_snp * c->row_bytes;
-    if (row_bytes_in == c->row_bytes && (c->n_samp % 4) == 0 && c->n_samp == c->n_samp_pad) {
-        CUDA_CHECK(cudaMemcpyAsync(dst, host, (size_t)cnt * row_bytes_in, cudaMemcpyHostToDevice,
-                                   c->stream));
-    } else {
-        const int64_t max_rows = std::max<int64_t>(1, (int64_t)(256ll << 20) / row_bytes_in);
-        c->stage_u8.alloc((size_t)std::min(cnt, max_rows) * row_bytes_in);
-        for (int64_t done = 0; done < cnt; done += max_rows) {
-            int64_t rows = std::min(max_rows, cnt - done);
-            CUDA_CHECK(cudaMemcpyAsync(c->stage_u8.p, host + done * row_bytes_in,
-                                       (size_t)rows * row_bytes_in, cudaMemcpyHostToDevice,
-                                       c->stream));
-            int64_t total = rows * c->row_bytes;
-            repack_2b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(
-                c->stage_u8.p, dst + done * c->row_bytes, rows, c->n_samp, row_bytes_in,
-                c->row_bytes);
-            KERNEL_CHECK(c);
-            CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        }
+    // one strided DMA straight into the padded device rows (no staging copy), then a small
+    // kernel rewrites the bytes at / beyond the last sample so that padding reads as missing
+    const int64_t w = (c->n_samp + 3) / 4;
+    CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)c->row_bytes, host, (size_t)row_bytes_in, (size_t)w, (size_t)cnt,
+                                 cudaMemcpyHostToDevice, c->stream));
+    const int64_t pad_from = c->n_samp / 4;              // first byte that holds any padding sample
+    const int64_t pad_bytes = c->row_bytes - pad_from;
+    if (pad_bytes > 0) {
+        int64_t total = cnt * pad_bytes;
+        fix_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(dst, cnt, c->n_samp, pad_from,
+                                                                              pad_bytes, w, c->row_bytes);
+        KERNEL_CHECK(c);
     }
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));   // the host block may be reused by the caller
     c->n_snp += cnt;
     invalidate(c);
 }
