@@ -15,7 +15,7 @@
 namespace snprel {
 
 constexpr int BT = 64;        // pairs tile edge
-constexpr int BKW = 8;        // 64-SNP words per pipeline stage
+constexpr int BKW = 9;        // 64-SNP words per pipeline stage (three carry-save groups of 3)
 constexpr int BTHREADS = 256;
 
 template <int EST> struct EstTraits;
@@ -32,32 +32,54 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// the bit streams whose populations are the estimator's counters, for 32 SNPs of one pair
 template <int EST>
-__device__ __forceinline__ void pair_update(uint32_t (&acc)[EstTraits<EST>::NC], uint32_t a1,
-                                            uint32_t a2, uint32_t b1, uint32_t b2) {
+__device__ __forceinline__ void pair_streams(uint32_t (&st)[EstTraits<EST>::NC], uint32_t a1, uint32_t a2,
+                                             uint32_t b1, uint32_t b2) {
     // validity: a genotype is missing iff (plane1, plane2) == (0, 1)
     uint32_t mask = (a1 | ~a2) & (b1 | ~b2);
     uint32_t x1 = a1 ^ b1, x2 = a2 ^ b2;
     if (EST == SNPREL_EST_IBS) {
-        acc[0] += __popc(x1 & x2 & mask);      // ibs0: (0,0) vs (1,1)
-        acc[1] += __popc(~(x1 | x2) & mask);   // ibs2: identical
-        acc[2] += __popc(mask);
+        st[0] = x1 & x2 & mask;        // ibs0: (0,0) vs (1,1)
+        st[1] = ~(x1 | x2) & mask;     // ibs2: identical
+        st[2] = mask;
     } else if (EST == SNPREL_EST_KING_ROBUST) {
-        acc[0] += __popc(x1 & x2 & mask);                 // ibs0
-        acc[1] += __popc(mask);                           // nLoci
-        acc[2] += __popc((x1 ^ x2) & mask);               // het: exactly one of the two is Aa
-        acc[3] += __popc(a1 & ~a2 & mask);                // N1_Aa (row sample)
-        acc[4] += __popc(b1 & ~b2 & mask);                // N2_Aa (column sample)
+        st[0] = x1 & x2 & mask;        // ibs0
+        st[1] = mask;                  // nLoci
+        st[2] = (x1 ^ x2) & mask;      // het: exactly one of the two is Aa
+        st[3] = a1 & ~a2 & mask;       // N1_Aa (row sample)
+        st[4] = b1 & ~b2 & mask;       // N2_Aa (column sample)
     } else {
         uint32_t het = (a1 ^ a2) | (b1 ^ b2);
-        acc[0] += __popc(het & mask);                     // either heterozygous
-        acc[1] += __popc(~(het | x1) & mask);             // same homozygote
-        acc[2] += __popc(mask);
+        st[0] = het & mask;            // either heterozygous
+        st[1] = ~(het | x1) & mask;    // same homozygote
+        st[2] = mask;
+    }
+}
+
+// POPC issues on the quarter-rate XU pipe and bounded the first version of this kernel (96 % busy,
+// profiles/r01_ibs_pair_count_full.txt).  Three words of every stream go through a carry-save
+// adder first (sum = a^b^c, carry = maj(a,b,c): two LOP3 on the full-rate ALU pipe), so three
+// populations cost two POPCs: pop(a)+pop(b)+pop(c) = pop(sum) + 2 pop(carry).
+template <int EST>
+__device__ __forceinline__ void pair_update3(uint32_t (&acc)[EstTraits<EST>::NC], const uint32_t (&a1)[3],
+                                             const uint32_t (&a2)[3], const uint32_t (&b1)[3],
+                                             const uint32_t (&b2)[3]) {
+    constexpr int NC = EstTraits<EST>::NC;
+    uint32_t s0[NC], s1[NC], s2[NC];
+    pair_streams<EST>(s0, a1[0], a2[0], b1[0], b2[0]);
+    pair_streams<EST>(s1, a1[1], a2[1], b1[1], b2[1]);
+    pair_streams<EST>(s2, a1[2], a2[2], b1[2], b2[2]);
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        uint32_t sum = s0[k] ^ s1[k] ^ s2[k];
+        uint32_t carry = (s0[k] & s1[k]) | (s2[k] & (s0[k] ^ s1[k]));
+        acc[k] += __popc(sum) + 2 * __popc(carry);
     }
 }
 
 template <int EST>
-__global__ void __launch_bounds__(BTHREADS)
+__global__ void __launch_bounds__(BTHREADS, EstTraits<EST>::NC <= 3 ? 2 : 1)
 pair_count_kernel(const uint4 *__restrict__ planes, uint32_t *__restrict__ cnt, int64_t n_pad,
                   int64_t n_words, int words_per_split) {
     constexpr int NC = EstTraits<EST>::NC;
@@ -81,15 +103,16 @@ pair_count_kernel(const uint4 *__restrict__ planes, uint32_t *__restrict__ cnt, 
             for (int k = 0; k < NC; k++) acc[r][q][k] = 0;
 
     auto load_stage = [&](int buf, int64_t w0) {
-        // BKW*BT = 512 uint4 per panel; 256 threads -> 2 per panel
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            int e = tid + h * BTHREADS;
+        // BKW*BT = 576 uint4 per panel; words past the end read as all-missing (plane1 = 0, plane2 = 1)
+        for (int e = tid; e < BKW * BT; e += BTHREADS) {
             int w = e >> 6, s = e & 63;
             int64_t gw = w0 + w;
             if (gw < w_end) {
                 cp_async16(&sA[buf][w][s], planes + gw * n_pad + i0 + s);
                 cp_async16(&sB[buf][w][s], planes + gw * n_pad + j0 + s);
+            } else {
+                sA[buf][w][s] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                sB[buf][w][s] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu);
             }
         }
     };
@@ -102,20 +125,35 @@ pair_count_kernel(const uint4 *__restrict__ planes, uint32_t *__restrict__ cnt, 
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        const int nw = (int)min((int64_t)BKW, w_end - w0);
-        for (int w = 0; w < nw; w++) {
-            uint4 a[4], b[4];
+#pragma unroll 1
+        for (int w = 0; w < BKW; w += 3) {
+            uint4 a[4][3];
 #pragma unroll
-            for (int r = 0; r < 4; r++) a[r] = sA[buf][w][ty + 16 * r];
+            for (int k = 0; k < 3; k++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) b[q] = sB[buf][w][tx + 16 * q];
+                for (int r = 0; r < 4; r++) a[r][k] = sA[buf][w + k][ty + 16 * r];
 #pragma unroll
-            for (int r = 0; r < 4; r++)
+            for (int q = 0; q < 4; q++) {
+                uint4 b[3];   // one column sample at a time keeps the live set under 128 registers
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    pair_update<EST>(acc[r][q], a[r].x, a[r].z, b[q].x, b[q].z);
-                    pair_update<EST>(acc[r][q], a[r].y, a[r].w, b[q].y, b[q].w);
+                for (int k = 0; k < 3; k++) b[k] = sB[buf][w + k][tx + 16 * q];
+                {   // low 32 SNPs of the three words
+                    const uint32_t b1[3] = {b[0].x, b[1].x, b[2].x}, b2[3] = {b[0].z, b[1].z, b[2].z};
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const uint32_t a1[3] = {a[r][0].x, a[r][1].x, a[r][2].x}, a2[3] = {a[r][0].z, a[r][1].z, a[r][2].z};
+                        pair_update3<EST>(acc[r][q], a1, a2, b1, b2);
+                    }
                 }
+                {   // high 32 SNPs
+                    const uint32_t b1[3] = {b[0].y, b[1].y, b[2].y}, b2[3] = {b[0].w, b[1].w, b[2].w};
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const uint32_t a1[3] = {a[r][0].y, a[r][1].y, a[r][2].y}, a2[3] = {a[r][0].w, a[r][1].w, a[r][2].w};
+                        pair_update3<EST>(acc[r][q], a1, a2, b1, b2);
+                    }
+                }
+            }
         }
         __syncthreads();
         buf ^= 1;
