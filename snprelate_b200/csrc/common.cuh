@@ -194,8 +194,6 @@ struct GramPass {
 };
 void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *out_planes,
                  bool upper_only);
-void gram_tc2_run(snprel_ctx *c, const GramPass *passes, int npass, long long *out_planes,
-                  bool upper_only);
 
 // grm.cu
 void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan);

@@ -35,23 +35,6 @@ __global__ void pack_u8_kernel(const uint8_t *__restrict__ src, uint8_t *__restr
     dst[idx] = (uint8_t)out;
 }
 
-// repack host 2-bit rows (row_bytes_in per SNP) into padded device rows
-__global__ void repack_2b_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
-                                 int64_t cnt, int64_t n_samp, int64_t row_bytes_in,
-                                 int64_t row_bytes) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t total = cnt * row_bytes;
-    if (idx >= total) return;
-    int64_t r = idx / row_bytes, b = idx - r * row_bytes;
-    uint32_t v = 0xFF;
-    if (b * 4 < n_samp) {
-        v = src[r * row_bytes_in + b];
-        int64_t rem = n_samp - b * 4;   // valid genotypes in this byte
-        if (rem < 4) v |= (0xFFu << (2 * rem)) & 0xFF;
-    }
-    dst[idx] = (uint8_t)v;
-}
-
 // bytes [pad_from, row_bytes) of every row: keep the valid genotypes of a partial byte, set the
 // rest (and every byte the host copy did not cover) to the missing code
 __global__ void fix_pad_kernel(uint8_t *__restrict__ dst, int64_t cnt, int64_t n_samp, int64_t pad_from,

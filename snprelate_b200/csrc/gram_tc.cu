@@ -1,106 +1,170 @@
 // K1: the tcgen05 "table Gram" -- the tensor-core hot loop that replaces
-// CProdMat_AlgArith::MulAdd (src/genPCA.cpp:229-312) together with its block
-// preparation (TransposeGenotype / GenoSub / GenoMul, src/genPCA.h:93-108,
-// src/genPCA.cpp:315-368) and the missing-pair denominator loops
-// (src/genPCA.cpp:1201-1224, src/genEIGMIX.cpp:113-138).
+// CProdMat_AlgArith::MulAdd (src/genPCA.cpp:229-312) together with its block preparation
+// (TransposeGenotype / GenoSub / GenoMul, src/genPCA.h:93-108, src/genPCA.cpp:315-368) and the
+// missing-pair denominator loops (src/genPCA.cpp:1201-1224, src/genEIGMIX.cpp:113-138).
 //
-// It computes, for up to two "passes" p that share one B table,
+// For up to two "passes" p that share one B table it computes
 //
 //     Acc_p[i][j] = sum over SNPs l of  tabA_p[l][g_il] * tabB[g_jl]      (exact, int32)
 //
-// where g is the 2-bit genotype code, tabA_p[l] is a per-SNP table of four int8
-// digits and tabB a table of four small int8 values, and adds Acc_p << shift_p into
-// an int64 fixed-point output plane with 64-bit atomics.  The per-SNP real weights
-// (1/(p(1-p)), 2p, 4p(1-p) ...) live in the digits of tabA: grm.cu slices each
-// table value into balanced base-256 digits, one pass per digit, so the sum over
-// passes reproduces the float64 result to a proven bound while every tensor-core
-// product and every accumulation is exact integer arithmetic (order independent,
-// hence bit-identical for any tiling, split or GPU count).
+// where g is the 2-bit genotype code, tabA_p[l] a per-SNP table of four int8 digits and tabB a
+// table of four small int8 values, and adds Acc_p << shift_p into an int64 fixed-point plane
+// with 64-bit atomics.  The per-SNP real weights (1/(p(1-p)), 2p, 4p(1-p) ...) live in the digits
+// of tabA: grm.cu slices each table value into balanced base-256 digits, one pass per digit, so
+// the sum over passes reproduces the float64 result to a proven bound while every tensor-core
+// product and every accumulation is exact integer arithmetic (order independent, hence
+// bit-identical for any tiling, split or GPU count).
 //
-// Mapping onto sm_100a:
-//   * one CTA per (128 x 256 sample tile, SNP split); 10 warps.
-//   * warp 1 is the loader: per stage it issues six TMA box copies (16 bytes x 128 SNP rows
-//     each, cp.async.bulk.tensor.2d) of the packed 2-bit genotypes plus bulk copies of the
-//     digit tables into a small shared-memory ring, signalled through mbarrier complete_tx.
-//   * warps 2..9 are producers: each thread takes 64 packed genotypes of one SNP from
-//     the ring, turns every 32-bit word (16 samples) into byte-permute
-//     selectors (3 logic ops + 2 shifts) and emits int8 operand rows with PRMT
-//     against the 4-entry tables -- the "unpack, centre and scale on the fly" step.
-//     Operands are written MN-major (16 consecutive samples = one 16-byte core row),
-//     the layout in which a packed genotype word expands without any transpose.
-//   * warp 0 issues tcgen05.mma.kind::i8 (M=128, N=256, K=32) from shared-memory
-//     descriptors into two 128x256 int32 accumulators that fill the 512 TMEM columns;
-//     tcgen05.commit releases pipeline stages back to the producers through mbarriers.
-//   * after the last SNP stage the producer warps become the epilogue: tcgen05.ld the
-//     accumulators and issue the 64-bit atomics.
+// Mapping onto sm_100a: a cluster of two CTAs (one TPC, tcgen05 cta_group::2) owns a 256 x 256
+// sample tile (upper triangle only) and an SNP split; 10 warps per CTA, 1 CTA per SM.
+//   * warp 1, one lane -- TMA loader: per 128-SNP stage four cp.async.bulk.tensor.2d boxes
+//     (16 bytes x 128 SNP rows) of the packed 2-bit genotypes plus cp.async.bulk copies of the
+//     digit tables into a 3-deep shared-memory ring, mbarrier complete_tx.
+//   * warps 2..9 -- producers: each thread takes 64 packed genotypes of one SNP for this CTA's
+//     128 A rows and for ITS HALF (128) of the B rows, turns every 32-bit word (16 samples) into
+//     byte-permute selectors (3 logic ops + 2 shifts) and emits int8 operand rows with PRMT
+//     against the 4-entry tables -- the fused "unpack, centre and scale" step.  Operands are
+//     written MN-major (16 consecutive samples = one 16-byte core-matrix row), the layout in
+//     which a packed SNP-major genotype word expands without any transpose.
+//   * warp 0 of CTA 0, one lane -- MMA issuer: tcgen05.mma.cta_group::2.kind::i8 (M=256, N=256,
+//     K=32) reads A and the B halves from both SMs' shared memory and accumulates 128 x 256 int32
+//     per pass into each SM's TMEM (2 passes = all 512 columns); tcgen05.commit multicasts the
+//     stage-empty / accumulator-ready arrivals to both CTAs.
+//   * the stage-full barrier lives in CTA 0 and counts the producers of BOTH CTAs; CTA 1's
+//     producers arrive on it remotely (mapa + mbarrier.arrive on the cluster address).
+//   * after the last stage the producer warps become the epilogue: tcgen05.ld their 128 rows and
+//     issue the 64-bit atomics.
+// History (profiles/): a single-CTA 128 x 256 version was bounded by shared-memory traffic
+// (64 KB written + 96 KB read by the tensor core per stage); the pair halves the B expansion and
+// the B traffic per CTA (48 KB + 64 KB).
 #include "common.cuh"
-#include "tc_ptx.cuh"   // CUtensorMap types; the encoder is fetched through cudaGetDriverEntryPoint
+#include "tc_ptx.cuh"
 
 namespace snprel {
-namespace tc {
+namespace tc2 {
 
-constexpr int TM = 128;            // A rows (samples) per tile
-constexpr int TN = 256;            // B rows (samples) per tile
-constexpr int SK = 128;            // SNPs per pipeline stage
-constexpr int MMA_K = 32;          // SNPs per tcgen05.mma (int8)
-constexpr int NSTAGE = 3;
-constexpr int MAXP = 2;            // passes per launch = TMEM accumulators
+using namespace tc;
+
+constexpr int TM2 = 256;           // tile rows (A), 128 per CTA
+constexpr int TN2 = 256;           // tile cols (B), 128 per CTA
+constexpr int HM = 128, HN = 128;  // per-CTA halves
+constexpr int SK = 128;            // SNPs per stage
+constexpr int MMA_K = 32;
+constexpr int NSTAGE = 4;
+constexpr int MAXP = 2;
 constexpr int PROD_WARPS = 8;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
-constexpr int FIRST_PROD_WARP = 2;                       // warp 0 = MMA issuer, warp 1 = TMA loader
+constexpr int FIRST_PROD_WARP = 2;
 constexpr int THREADS = 32 * (FIRST_PROD_WARP + PROD_WARPS);
-constexpr int A_BYTES = TM * SK;   // one pass, one stage (16 KB)
-constexpr int B_BYTES = TN * SK;   // one stage (32 KB)
-constexpr int STAGE_BYTES = MAXP * A_BYTES + B_BYTES;
-// ring of packed (2-bit) genotype boxes + digit tables, filled by TMA PF_DEPTH stages ahead:
-// six boxes of 16 bytes x SK rows (A quads 0-1, B quads 0-3), then MAXP tables of SK words
-constexpr int PF_DEPTH = 2;
+constexpr int A_BYTES = HM * SK;   // 16 KB per pass per stage
+constexpr int B_BYTES = HN * SK;   // 16 KB per stage
+constexpr int STAGE_BYTES = MAXP * A_BYTES + B_BYTES;   // 48 KB
+constexpr int PF_DEPTH = 3;
 constexpr int PF_BOX = SK * 16;
-constexpr int PF_NBOX = (TM + TN) / 64;
+constexpr int PF_NBOX = (HM + HN) / 64;                  // 2 A boxes + 2 B boxes
 constexpr int PF_TAB = SK * 4;
-constexpr int PF_BYTES = PF_NBOX * PF_BOX + MAXP * PF_TAB;
+constexpr int PF_BYTES = PF_NBOX * PF_BOX + MAXP * PF_TAB;   // 9 KB
 constexpr int BAR_OFFSET = NSTAGE * STAGE_BYTES + PF_DEPTH * PF_BYTES;
 constexpr int SMEM_BYTES = BAR_OFFSET + 1024;
-constexpr int A_LBO = (TM / 16) * 128;   // byte stride between 8-SNP groups (K direction)
-constexpr int B_LBO = (TN / 16) * 128;
-constexpr int CORE_SBO = 128;            // byte stride between 16-sample cores (MN direction)
+constexpr int LBO = (HM / 16) * 128;   // 8 cores per 8-SNP group (A and B halves alike)
+constexpr int SBO = 128;
 constexpr uint32_t TMEM_COLS = 512;
 
 struct Params {
-    const uint8_t *geno;
-    long long row_bytes;
     const uint32_t *tabA[MAXP];
     uint32_t tabB;
     int npass;
     int plane[MAXP];
     int shift[MAXP];
     long long *out;
-    long long ld;            // leading dimension of an output plane (n_samp_pad)
-    long long plane_stride;  // elements per plane
+    long long ld;
+    long long plane_stride;
     long long n_samp;
-    const int2 *tiles;       // (tile_m, tile_n) work list
+    const int2 *tiles;       // (tile_m, tile_n) in units of 256 samples
     int stages_total;
     int stages_per_split;
     int upper_only;
-    uint32_t flags;          // bit0: swap LBO/SBO in the descriptors (bring-up probe)
-    uint32_t sh32;           // always 32 (see mbar_arrive_after)
+    uint32_t sh32;
     int *error_flag;
 };
 
-// instruction descriptor for kind::i8: D=s32, A=s8, B=s8, both MN-major, M=128, N=256
-__device__ __forceinline__ uint32_t make_idesc() {
-    return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TN >> 3) << 17) |
-           ((uint32_t)(TM >> 4) << 24);
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default .release.cta semantics as in CUTLASS' ClusterBarrier::arrive(cta_id): an explicit
+    // .release.cluster costs a MEMBAR.ALL.GPU + ERRBAR per thread and stage (33 % of all stall
+    // samples in profiles/r01 notes); the data being published is this CTA's own shared memory,
+    // already ordered for the async proxy by fence.proxy.async
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int *error_flag, int code) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            if (error_flag) atomicExch(error_flag, code);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
+    asm volatile(
+        "{\n .reg .b16 m;\n mov.b16 m, 3;\n"
+        " tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n}"
+        ::"r"(bar)
+        : "memory");
+}
+// D=s32, A=s8, B=s8, MN-major, M=256 (pair), N=256
+__device__ __forceinline__ uint32_t make_idesc2() {
+    return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TN2 >> 3) << 17) |
+           ((uint32_t)(TM2 >> 4) << 24);
 }
 
 template <int NP>
-__global__ void __launch_bounds__(THREADS, 1)
-table_gram_kernel(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_base + BAR_OFFSET;
-    // barriers: full[NSTAGE], empty[NSTAGE], accum, pf_full[PF_DEPTH], pf_empty[PF_DEPTH]; then the TMEM slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
     const uint32_t accum_bar = bar_base + 8u * (2 * NSTAGE);
@@ -111,16 +175,16 @@ table_gram_kernel(const __grid_constant__ Params P, const __grid_constant__ CUte
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem + BAR_OFFSET + 8 * SLOT_IDX);
     const uint32_t pf_base = smem_base + NSTAGE * STAGE_BYTES;
 
-    const int2 tile = P.tiles[blockIdx.x];
+    const int2 tile = P.tiles[blockIdx.x >> 1];
     const int st_begin = blockIdx.y * P.stages_per_split;
     const int st_end = min(P.stages_total, st_begin + P.stages_per_split);
-    const int nst = st_end - st_begin;
+    const int nst = st_end - st_begin;   // identical in both CTAs of the pair
     if (nst <= 0) return;
 
     if (warp == 0) {
         if (lane == 0) {
             for (int s = 0; s < NSTAGE; s++) {
-                mbar_init(full_bar(s), PROD_THREADS);
+                mbar_init(full_bar(s), 2 * PROD_THREADS);   // producers of both CTAs (used in CTA 0 only)
                 mbar_init(empty_bar(s), 1);
             }
             mbar_init(accum_bar, 1);
@@ -131,48 +195,45 @@ table_gram_kernel(const __grid_constant__ Params P, const __grid_constant__ CUte
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_alloc2(tmem_slot, TMEM_COLS);
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync();          // peer barriers are initialised before anyone arrives remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
-        // ===================== MMA issuer =====================
-        const uint32_t idesc = make_idesc();
-        const bool swap = (P.flags & 1u) != 0;
-        const uint32_t a_lbo = swap ? CORE_SBO : A_LBO, a_sbo = swap ? A_LBO : CORE_SBO;
-        const uint32_t b_lbo = swap ? CORE_SBO : B_LBO, b_sbo = swap ? B_LBO : CORE_SBO;
-        for (int it = 0; it < nst; it++) {
-            const int s = it % NSTAGE;
-            const uint32_t phase = (uint32_t)(it / NSTAGE) & 1u;
-            mbar_wait(full_bar(s), phase, P.error_flag, 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t stage_addr = smem_base + s * STAGE_BYTES;
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (rank == 0) {
+            const uint32_t idesc = make_idesc2();
+            for (int it = 0; it < nst; it++) {
+                const int s = it % NSTAGE;
+                const uint32_t phase = (uint32_t)(it / NSTAGE) & 1u;
+                mbar_wait_cluster(full_bar(s), phase, P.error_flag, 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t stage_addr = smem_base + s * STAGE_BYTES;
 #pragma unroll
-                for (int j = 0; j < SK / MMA_K; j++) {
-                    // K step j covers 4 groups of 8 SNPs
-                    uint64_t bdesc = make_desc(stage_addr + MAXP * A_BYTES + j * 4 * B_LBO, b_lbo, b_sbo);
+                    for (int j = 0; j < SK / MMA_K; j++) {
+                        uint64_t bdesc = make_desc(stage_addr + MAXP * A_BYTES + j * 4 * LBO, LBO, SBO);
 #pragma unroll
-                    for (int p = 0; p < NP; p++) {
-                        uint64_t adesc =
-                            make_desc(stage_addr + p * A_BYTES + j * 4 * A_LBO, a_lbo, a_sbo);
-                        umma_i8(tmem_base + (uint32_t)(p * TN), adesc, bdesc, idesc,
-                                (it > 0 || j > 0) ? 1u : 0u);
+                        for (int p = 0; p < NP; p++) {
+                            uint64_t adesc = make_desc(stage_addr + p * A_BYTES + j * 4 * LBO, LBO, SBO);
+                            umma2_i8(tmem_base + (uint32_t)(p * TN2), adesc, bdesc, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                        }
                     }
+                    umma2_commit_mc(empty_bar(s));
                 }
-                umma_commit(empty_bar(s));   // frees the stage once these MMAs have read it
+                __syncwarp();
             }
+            if (lane == 0) umma2_commit_mc(accum_bar);
             __syncwarp();
         }
-        if (lane == 0) umma_commit(accum_bar);
-        __syncwarp();
     } else if (warp == 1) {
         // ===================== TMA loader =====================
         if (lane == 0) {
-            const int ax = tile.x * (TM / 4), bx = tile.y * (TN / 4);
+            const int ax = (tile.x * TM2 + (int)rank * HM) / 4, bx = (tile.y * TN2 + (int)rank * HN) / 4;
             for (int it = 0; it < nst; it++) {
                 const int sl = it % PF_DEPTH;
                 const uint32_t ph = (uint32_t)(it / PF_DEPTH) & 1u;
@@ -182,10 +243,9 @@ table_gram_kernel(const __grid_constant__ Params P, const __grid_constant__ CUte
                 mbar_arrive_expect_tx(bar, PF_NBOX * PF_BOX + NP * PF_TAB);
                 const int y = (st_begin + it) * SK;
 #pragma unroll
-                for (int q = 0; q < TM / 64; q++) tma_load_2d(slot + q * PF_BOX, &tmap, ax + q * 16, y, bar);
+                for (int q = 0; q < HM / 64; q++) tma_load_2d(slot + q * PF_BOX, &tmap, ax + q * 16, y, bar);
 #pragma unroll
-                for (int q = 0; q < TN / 64; q++)
-                    tma_load_2d(slot + (TM / 64 + q) * PF_BOX, &tmap, bx + q * 16, y, bar);
+                for (int q = 0; q < HN / 64; q++) tma_load_2d(slot + (HM / 64 + q) * PF_BOX, &tmap, bx + q * 16, y, bar);
 #pragma unroll
                 for (int q = 0; q < NP; q++)
                     bulk_load(slot + PF_NBOX * PF_BOX + q * PF_TAB, P.tabA[q] + (long long)y, PF_TAB, bar);
@@ -196,15 +256,17 @@ table_gram_kernel(const __grid_constant__ Params P, const __grid_constant__ CUte
         // ===================== producers =====================
         const int p = threadIdx.x - 32 * FIRST_PROD_WARP;
         const int sl = p & (SK - 1);   // SNP within the stage
-        const int half = p >> 7;       // which 64-sample quad of A / which 128-sample half of B
+        const int half = p >> 7;       // which 64-sample quad of this CTA's A half and of its B half
         const int kg = sl >> 3, r = sl & 7;
         uint32_t tb[1] = {P.tabB};
-        const uint32_t a_off = kg * A_LBO + (half * 4) * CORE_SBO + r * 16;
-        const uint32_t b_off = MAXP * A_BYTES + kg * B_LBO + (half * 8) * CORE_SBO + r * 16;
-        // this thread's words inside a ring slot (16-byte box rows: conflict-free LDS.128)
+        const uint32_t a_off = kg * LBO + (half * 4) * SBO + r * 16;
+        const uint32_t b_off = MAXP * A_BYTES + a_off;
         const uint32_t pa = half * PF_BOX + sl * 16;
-        const uint32_t pb = (TM / 64 + 2 * half) * PF_BOX + sl * 16;
+        const uint32_t pb = (HM / 64 + half) * PF_BOX + sl * 16;
         const uint32_t pt = PF_NBOX * PF_BOX + sl * 4;
+        uint32_t full_remote[NSTAGE];
+#pragma unroll
+        for (int s = 0; s < NSTAGE; s++) full_remote[s] = mapa(full_bar(s), 0);   // leader's barrier
 
 #pragma unroll 1
         for (int it = 0; it < nst; it++) {
@@ -214,14 +276,11 @@ table_gram_kernel(const __grid_constant__ Params P, const __grid_constant__ CUte
             mbar_wait(pf_full(ps), (uint32_t)(it / PF_DEPTH) & 1u, P.error_flag, 5);
             const uint32_t slot = pf_base + (uint32_t)ps * PF_BYTES;
             const uint4 ca = ld_shared_v4(slot + pa);
-            const uint4 cb0 = ld_shared_v4(slot + pb);
-            const uint4 cb1 = ld_shared_v4(slot + pb + PF_BOX);
+            const uint4 cb = ld_shared_v4(slot + pb);
             uint32_t ct[NP];
 #pragma unroll
             for (int q = 0; q < NP; q++) ct[q] = ld_shared_u32(slot + pt + q * PF_TAB);
-            // the loader may refill this slot -- but only once every word above has really been read
-            mbar_arrive_after(pf_empty(ps), ca.x ^ ca.y ^ ca.z ^ ca.w ^ cb0.x ^ cb0.y ^ cb0.z ^ cb0.w ^ cb1.x ^ cb1.y ^
-                                                cb1.z ^ cb1.w ^ ct[0] ^ ct[NP - 1],
+            mbar_arrive_after(pf_empty(ps), ca.x ^ ca.y ^ ca.z ^ ca.w ^ cb.x ^ cb.y ^ cb.z ^ cb.w ^ ct[0] ^ ct[NP - 1],
                               P.sh32);
 
             mbar_wait(empty_bar(s), phase ^ 1u, P.error_flag, 2);
@@ -231,26 +290,30 @@ table_gram_kernel(const __grid_constant__ Params P, const __grid_constant__ CUte
             for (int w = 0; w < 4; w++) {
                 uint32_t dst[NP];
 #pragma unroll
-                for (int q = 0; q < NP; q++) dst[q] = stage_addr + q * A_BYTES + a_off + w * CORE_SBO;
+                for (int q = 0; q < NP; q++) dst[q] = stage_addr + q * A_BYTES + a_off + w * SBO;
                 expand_word<NP>(aw[w], ct, dst);
             }
-            const uint32_t bw[8] = {cb0.x, cb0.y, cb0.z, cb0.w, cb1.x, cb1.y, cb1.z, cb1.w};
+            const uint32_t bw[4] = {cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
-            for (int w = 0; w < 8; w++) {
-                uint32_t dst[1] = {stage_addr + b_off + w * CORE_SBO};
+            for (int w = 0; w < 4; w++) {
+                uint32_t dst[1] = {stage_addr + b_off + w * SBO};
                 expand_word<1>(bw[w], tb, dst);
             }
-            fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core
-            mbar_arrive(full_bar(s));
+            fence_proxy_async_smem();
+            // constant-index select keeps full_remote[] in registers
+            uint32_t fr = full_remote[0];
+#pragma unroll
+            for (int k = 1; k < NSTAGE; k++) fr = (s == k) ? full_remote[k] : fr;
+            mbar_arrive_cluster(fr);
         }
 
-        // ===================== epilogue =====================
+        // ===================== epilogue (each CTA drains its own 128 rows) =====================
         mbar_wait(accum_bar, 0, P.error_flag, 3);
         tc_fence_after();
-        const int quarter = warp & 3;            // TMEM lanes this warp may touch
-        const int colhalf = (warp - FIRST_PROD_WARP) >> 2;     // two warps share a lane quarter
+        const int quarter = warp & 3;
+        const int colhalf = (warp - FIRST_PROD_WARP) >> 2;
         const int row = quarter * 32 + lane;
-        const long long gi = (long long)tile.x * TM + (row & ~15) + core_pos_to_sample(row & 15);
+        const long long gi = (long long)tile.x * TM2 + (long long)rank * HM + (row & ~15) + core_pos_to_sample(row & 15);
 #pragma unroll 1
         for (int q = 0; q < NP; q++) {
             long long *outp = P.out + (long long)P.plane[q] * P.plane_stride + gi * P.ld;
@@ -259,12 +322,12 @@ table_gram_kernel(const __grid_constant__ Params P, const __grid_constant__ CUte
             for (int cc = 0; cc < 4; cc++) {
                 const int col0 = colhalf * 128 + cc * 32;
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(q * TN + col0), v);
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(q * TN2 + col0), v);
                 if (gi < P.n_samp) {
 #pragma unroll
                     for (int k = 0; k < 32; k++) {
                         int col = col0 + k;
-                        long long gj = (long long)tile.y * TN + (col & ~15) + core_pos_to_sample(col & 15);
+                        long long gj = (long long)tile.y * TN2 + (col & ~15) + core_pos_to_sample(col & 15);
                         int val = (int)v[k];
                         if (val != 0 && gj < P.n_samp && (!P.upper_only || gj >= gi))
                             atomicAdd(reinterpret_cast<unsigned long long *>(outp + gj),
@@ -276,59 +339,66 @@ table_gram_kernel(const __grid_constant__ Params P, const __grid_constant__ CUte
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync();          // both CTAs are done with TMEM and with each other's barriers
     if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc2(tmem_base, TMEM_COLS);
     }
 }
 
-}  // namespace tc
+}  // namespace tc2
 
 // ---------------------------------------------------------------------------
-// host driver: group passes that share a B table into launches of <= 2
+// host driver
 // ---------------------------------------------------------------------------
-void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *out_planes,
-                 bool upper_only) {
-    using namespace tc;
+// fraction of the SM-time of a launch that does useful work when `items` equal work items run
+// `slots` at a time (wave quantisation)
+static double wave_efficiency(int64_t items, int64_t slots) {
+    int64_t waves = (items + slots - 1) / slots;
+    return (double)items / (double)(waves * slots);
+}
+
+void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *out_planes, bool upper_only) {
+    using namespace tc2;
     if (npass <= 0) return;
-    if (!(c->debug_flags & 4u)) {   // default: CTA-pair (cta_group::2) kernel, gram_tc2.cu
-        gram_tc2_run(c, passes, npass, out_planes, upper_only);
-        return;
-    }
     geno_pad_tail(c);
     const int64_t n = c->n_samp, npad = c->n_samp_pad;
-    const int tiles_m = (int)((n + TM - 1) / TM), tiles_n = (int)((n + TN - 1) / TN);
+    const int nt = (int)((n + TM2 - 1) / TM2);
     std::vector<int2> &tiles = c->host_tiles;
     tiles.clear();
-    for (int tm = 0; tm < tiles_m; tm++)
-        for (int tn = 0; tn < tiles_n; tn++)
-            if (!upper_only || (int64_t)tn * TN + TN - 1 >= (int64_t)tm * TM) tiles.push_back(make_int2(tm, tn));
+    for (int tm = 0; tm < nt; tm++)
+        for (int tn = (upper_only ? tm : 0); tn < nt; tn++) tiles.push_back(make_int2(tm, tn));
     DevBuf<int2> &dtiles = c->scr_tiles;
     dtiles.alloc(tiles.size());
-    CUDA_CHECK(cudaMemcpyAsync(dtiles.p, tiles.data(), tiles.size() * sizeof(int2),
-                               cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(dtiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice,
+                               c->stream));
     c->scr_flags.alloc(2);
     int *derr = c->scr_flags.p + 1;
     CUDA_CHECK(cudaMemsetAsync(derr, 0, sizeof(int), c->stream));
 
     const int stages_total = (int)(round_up(std::max<int64_t>(c->n_snp, 1), SK) / SK);
-    // split the SNP range when the tile list alone cannot fill the SMs
-    int64_t want = (int64_t)c->num_sms * 2;
-    int64_t splits = std::max<int64_t>(1, std::min<int64_t>((want + (int64_t)tiles.size() - 1) /
-                                                               (int64_t)tiles.size(),
-                                                           stages_total));
-    if (c->debug_flags & 2u) splits = 1;   // test hook: one CTA walks the whole SNP range
-    splits = std::min<int64_t>(splits, 65535);
-    int sps = (int)((stages_total + splits - 1) / splits);
-    splits = (stages_total + sps - 1) / sps;
-    // int32 accumulator headroom: |digit| <= 128, |tabB| <= 2  ->  256 per SNP
-    const int max_stages_i32 = (int)((2147483647ll / 256) / SK);
-    if (sps > max_stages_i32) {
-        sps = max_stages_i32;
-        splits = (stages_total + sps - 1) / sps;
+    // SNP splits: enough work items to fill the chip, chosen to minimise the wave-quantisation tail
+    const int64_t slots = std::max(1, c->num_sms / 2);   // concurrent CTA pairs
+    const int64_t ntile = (int64_t)tiles.size();
+    int64_t best = 1;
+    double best_eff = -1;
+    for (int64_t sp = 1; sp <= std::min<int64_t>(stages_total, 64); sp++) {
+        // each extra split costs an epilogue (~0.3 stage-equivalents of atomics per 256 stages)
+        double eff = wave_efficiency(ntile * sp, slots) * (1.0 - 0.002 * (double)(sp - 1));
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = sp;
+        }
+        if (ntile * sp >= 8 * slots && eff > 0.97) break;
     }
+    int64_t splits = best;
+    if (c->debug_flags & 2u) splits = 1;   // test hook: one CTA pair walks the whole SNP range
+    int sps = (int)((stages_total + splits - 1) / splits);
+    const int max_stages_i32 = (int)((2147483647ll / 256) / SK);   // int32 accumulator headroom
+    sps = std::min(sps, max_stages_i32);
+    splits = (stages_total + sps - 1) / sps;
+    if (splits > 65535) fail("too many SNP splits");
 
-    // tensor map over the packed genotype matrix: bytes x SNP rows, box = 16 bytes x SK rows
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -355,10 +425,8 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
 
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        SMEM_BYTES));
-        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        SMEM_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_done = true;
     }
 
@@ -366,8 +434,6 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     for (int i = 0; i < npass; i++) {
         if (used[i]) continue;
         Params P{};
-        P.geno = c->geno2b.p;
-        P.row_bytes = c->row_bytes;
         P.tabB = passes[i].tabB;
         P.out = out_planes;
         P.ld = npad;
@@ -377,7 +443,6 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
         P.stages_total = stages_total;
         P.stages_per_split = sps;
         P.upper_only = upper_only ? 1 : 0;
-        P.flags = c->debug_flags;
         P.sh32 = 32;
         P.error_flag = derr;
         int np = 0;
@@ -390,18 +455,18 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
             np++;
         }
         P.npass = np;
-        dim3 grid((unsigned)tiles.size(), (unsigned)splits);
+        dim3 grid((unsigned)(2 * tiles.size()), (unsigned)splits);
         if (np == 2)
-            table_gram_kernel<2><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
+            table_gram_kernel2<2><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
         else
-            table_gram_kernel<1><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
+            table_gram_kernel2<1><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
         KERNEL_CHECK(c);
         c->hot_launches++;
     }
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     int herr = 0;
     CUDA_CHECK(cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost));
-    if (herr) fail("table_gram_kernel: pipeline barrier %d timed out", herr);
+    if (herr) fail("table_gram_kernel2: pipeline barrier %d timed out", herr);
 }
 
 }  // namespace snprel
