@@ -194,6 +194,20 @@ int snprel_mark_reduced(snprel_ctx *ctx);
 /* The plan (with the chosen frac_bits / digits) of the last covariance accumulate. */
 int snprel_last_plan(snprel_ctx *ctx, snprel_plan *plan);
 
+/* ---- row windows: N x N outputs that do not fit in HBM (or are tiled across GPUs) ---- */
+
+/* Restrict the accumulators and the results of the following estimator calls to output rows
+ * [row0, row0 + rows) (both multiples of 256; rows == 0 restores the whole matrix).  Inside a
+ * window snprel_grm (Eigenstrat / GCTA / EIGMIX), snprel_ibs_ave, snprel_king_robust and
+ * snprel_king_homo require packed != 0 and write only the window's slice of the row-packed
+ * upper triangle -- entries idx(row0,row0) .. idx(r1-1, n-1), contiguous in CdMatTri order
+ * (src/dGenGWAS.h:556-561); snprel_ibs_num writes three packed int32 slices.  The host walks the
+ * windows (one GPU: sequentially; several GPUs holding the same genotypes: windows dealt
+ * round-robin, no collective) and concatenates the slices. */
+int snprel_set_row_window(snprel_ctx *ctx, int64_t row0, int64_t rows);
+/* Number of packed entries the current window produces. */
+int snprel_window_count(snprel_ctx *ctx, int64_t *count);
+
 /* ---- introspection for benchmarks / tests ------------------------------ */
 
 /* Number of kernels this library launched on the context so far. */

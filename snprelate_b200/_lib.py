@@ -75,6 +75,8 @@ def load_library():
         "snprel_reduce_buffer": [p, i32, C.POINTER(p), C.POINTER(i64), C.POINTER(i32)],
         "snprel_mark_reduced": [p],
         "snprel_last_plan": [p, C.POINTER(Plan)],
+        "snprel_set_row_window": [p, i64, i64],
+        "snprel_window_count": [p, C.POINTER(i64)],
         "snprel_last_hot_kernel": [p, C.POINTER(dbl), C.POINTER(i64), C.POINTER(dbl)],
         "snprel_time_accumulate": [p, i32, i32, C.POINTER(dbl)],
         "snprel_last_step_ms": [p, C.POINTER(dbl)],
@@ -105,7 +107,7 @@ EXPORTED_SYMBOLS = [
     "snprel_ibs_num", "snprel_ibs_ave", "snprel_king_robust", "snprel_king_robust_counts",
     "snprel_king_homo", "snprel_indiv_beta", "snprel_indiv_beta_counts", "snprel_grm",
     "snprel_pca", "snprel_eigmix", "snprel_plan_local", "snprel_accumulate",
-    "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced", "snprel_last_plan",
+    "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced", "snprel_last_plan", "snprel_set_row_window", "snprel_window_count",
     "snprel_kernel_launches", "snprel_last_hot_kernel", "snprel_time_accumulate", "snprel_last_step_ms", "snprel_invalidate",
     "snprel_table_gram", "snprel_debug_flags",
 ]
@@ -201,13 +203,36 @@ class Context:
         return sel.astype(bool), nrm.value
 
     # ---- estimators ----
+    # ---- row windows ----
+    def set_row_window(self, row0=0, rows=0):
+        self._ck(self.lib.snprel_set_row_window(self.h, int(row0), int(rows)))
+        self._win = rows > 0
+
+    def window_count(self):
+        cnt = C.c_int64()
+        self._ck(self.lib.snprel_window_count(self.h, C.byref(cnt)))
+        return cnt.value
+
+    def windows(self, rows):
+        """Iterate (row0, rows) windows of height `rows` (multiple of 256) over all samples."""
+        n, _ = self.geno_dim()
+        for r0 in range(0, n, rows):
+            yield r0, rows
+
     def _out(self, packed):
+        if getattr(self, "_win", False):
+            if not packed:
+                raise SNPRelError("a row window returns the packed upper triangle only (useMatrix)")
+            return np.empty(self.window_count())
         n, _ = self.geno_dim()
         return np.empty(n * (n + 1) // 2) if packed else np.empty((n, n))
 
     def ibs_num(self):
         n, _ = self.geno_dim()
-        o = [np.empty((n, n), dtype=np.int32) for _ in range(3)]
+        if getattr(self, "_win", False):
+            o = [np.empty(self.window_count(), dtype=np.int32) for _ in range(3)]
+        else:
+            o = [np.empty((n, n), dtype=np.int32) for _ in range(3)]
         self._ck(self.lib.snprel_ibs_num(self.h, _ptr(o[0]), _ptr(o[1]), _ptr(o[2])))
         return o
 

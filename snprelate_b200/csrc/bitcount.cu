@@ -81,9 +81,9 @@ __device__ __forceinline__ void pair_update3(uint32_t (&acc)[EstTraits<EST>::NC]
 template <int EST>
 __global__ void __launch_bounds__(BTHREADS, EstTraits<EST>::NC <= 3 ? 2 : 1)
 pair_count_kernel(const uint4 *__restrict__ planes, uint32_t *__restrict__ cnt, int64_t n_pad,
-                  int64_t n_words, int words_per_split) {
+                  int64_t n_words, int words_per_split, RowWin win) {
     constexpr int NC = EstTraits<EST>::NC;
-    const int ti = blockIdx.y, tj = blockIdx.x;
+    const int ti = blockIdx.y + (int)(win.r0 / BT), tj = blockIdx.x;
     if (ti > tj) return;   // upper block triangle only
     __shared__ uint4 sA[2][BKW][BT];
     __shared__ uint4 sB[2][BKW][BT];
@@ -160,7 +160,7 @@ pair_count_kernel(const uint4 *__restrict__ planes, uint32_t *__restrict__ cnt, 
     }
     cp_async_wait<0>();
 
-    const int64_t plane = n_pad * n_pad;
+    const int64_t plane = win.rows * n_pad;
 #pragma unroll
     for (int r = 0; r < 4; r++)
 #pragma unroll
@@ -169,26 +169,28 @@ pair_count_kernel(const uint4 *__restrict__ planes, uint32_t *__restrict__ cnt, 
             if (j < i) continue;   // only the upper triangle is kept (CdMatTri)
 #pragma unroll
             for (int k = 0; k < NC; k++)
-                if (acc[r][q][k]) atomicAdd(cnt + k * plane + i * n_pad + j, acc[r][q][k]);
+                if (acc[r][q][k]) atomicAdd(cnt + k * plane + (i - win.r0) * n_pad + j, acc[r][q][k]);
         }
 }
 
 template <int EST>
 static void launch_pair_count(snprel_ctx *c) {
     const int64_t npad = c->n_samp_pad;
+    const RowWin win = row_window(c);
     const int64_t tiles = (c->n_samp + BT - 1) / BT;
+    const int64_t wtiles = (win.r1 - win.r0 + BT - 1) / BT;          // tile rows of the window
     const int64_t n_words = c->plane_words;
     // split the SNP words when the tile grid alone cannot fill the chip
-    int64_t ntile = tiles * (tiles + 1) / 2;
+    int64_t ntile = std::max<int64_t>(1, wtiles * (2 * (tiles - win.r0 / BT) - wtiles + 1) / 2);
     int64_t want = (int64_t)c->num_sms * 4;
     int64_t splits = std::max<int64_t>(1, std::min<int64_t>((want + ntile - 1) / ntile,
                                                            (n_words + BKW - 1) / BKW));
     splits = std::min<int64_t>(splits, 65535);
     int64_t wps = round_up((n_words + splits - 1) / splits, BKW);
     splits = (n_words + wps - 1) / wps;
-    dim3 grid((unsigned)tiles, (unsigned)tiles, (unsigned)splits);
+    dim3 grid((unsigned)tiles, (unsigned)wtiles, (unsigned)splits);
     pair_count_kernel<EST><<<grid, BTHREADS, 0, c->stream>>>(c->planes.p, c->cnt.p, npad, n_words,
-                                                            (int)wps);
+                                                            (int)wps, win);
     KERNEL_CHECK(c);
 }
 
@@ -197,7 +199,7 @@ void bitcount_accumulate(snprel_ctx *c, int est) {
     int nc = est == SNPREL_EST_KING_ROBUST ? 5 : 3;
     if (est == SNPREL_EST_KING_ROBUST && c->n_snp >= 1073741824ll)
         fail("The number of SNPs should be less than 1,073,741,824.");   // src/genKING.cpp:598
-    c->cnt.alloc((size_t)nc * c->n_samp_pad * c->n_samp_pad);
+    c->cnt.alloc((size_t)nc * row_window(c).rows * c->n_samp_pad);
     c->cnt_planes = nc;
     c->cnt.zero(c->stream);
     CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
@@ -214,6 +216,7 @@ void bitcount_accumulate(snprel_ctx *c, int est) {
     c->hot_ms = ms;
     c->hot_launches = 1;
     c->hot_units = 0.5 * (double)c->n_samp * (double)c->n_samp * (double)c->n_snp;
+    c->accum_win_r0 = row_window(c).r0;
     c->accum_est = est;
     c->accum_reduced = false;
     c->reduce_list.clear();
@@ -227,9 +230,9 @@ void bitcount_accumulate(snprel_ctx *c, int est) {
 // out index helpers: full symmetric n x n (column-major == row-major) or the
 // row-packed upper triangle idx(r,c) = c + r(2n-r-1)/2 (src/dGenGWAS.h:556-561)
 __device__ __forceinline__ void store_sym(double *out, int packed, int64_t n, int64_t i,
-                                          int64_t j, double v) {
+                                          int64_t j, double v, long long pbase = 0) {
     if (packed) {
-        out[j + i * (2 * n - i - 1) / 2] = v;
+        out[tri_idx(n, i, j) - pbase] = v;
     } else {
         out[i * n + j] = v;
         out[j * n + i] = v;
@@ -238,41 +241,49 @@ __device__ __forceinline__ void store_sym(double *out, int packed, int64_t n, in
 
 __global__ void ibs_num_kernel(const uint32_t *__restrict__ cnt, int32_t *__restrict__ o0,
                                int32_t *__restrict__ o1, int32_t *__restrict__ o2, int64_t n,
-                               int64_t npad) {
-    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+                               int64_t npad, RowWin win, int packed) {
+    int64_t i = win.r0 + blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= n || j < i) return;
-    int64_t plane = npad * npad, k = i * npad + j;
+    int64_t plane = win.rows * npad, k = (i - win.r0) * npad + j;
     uint32_t n0 = cnt[k], n2 = cnt[plane + k], nm = cnt[2 * plane + k];
     uint32_t n1 = nm - n0 - n2;
-    o0[i * n + j] = o0[j * n + i] = (int32_t)n0;
-    o1[i * n + j] = o1[j * n + i] = (int32_t)n1;
-    o2[i * n + j] = o2[j * n + i] = (int32_t)n2;
+    if (packed) {
+        long long t = tri_idx(n, i, j) - win.pbase;
+        o0[t] = (int32_t)n0;
+        o1[t] = (int32_t)n1;
+        o2[t] = (int32_t)n2;
+    } else {
+        o0[i * n + j] = o0[j * n + i] = (int32_t)n0;
+        o1[i * n + j] = o1[j * n + i] = (int32_t)n1;
+        o2[i * n + j] = o2[j * n + i] = (int32_t)n2;
+    }
 }
 
 __global__ void ibs_ave_kernel(const uint32_t *__restrict__ cnt, double *__restrict__ out,
-                               int packed, int64_t n, int64_t npad) {
-    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+                               int packed, int64_t n, int64_t npad, RowWin win) {
+    int64_t i = win.r0 + blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= n || j < i) return;
-    int64_t plane = npad * npad, k = i * npad + j;
+    int64_t plane = win.rows * npad, k = (i - win.r0) * npad + j;
     uint32_t n0 = cnt[k], n2 = cnt[plane + k], nm = cnt[2 * plane + k];
     uint32_t n1 = nm - n0 - n2;
     // (0.5*IBS1 + IBS2) / (IBS0 + IBS1 + IBS2), src/genIBS.cpp:472-473
     double v = (0.5 * (double)n1 + (double)n2) / (double)(n0 + n1 + n2);
-    store_sym(out, packed, n, i, j, v);
+    store_sym(out, packed, n, i, j, v, win.pbase);
 }
 
 __global__ void king_robust_kernel(const uint32_t *__restrict__ cnt,
                                    const int32_t *__restrict__ fam, double *__restrict__ oibs0,
-                                   double *__restrict__ okin, int packed, int64_t n, int64_t npad) {
-    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+                                   double *__restrict__ okin, int packed, int64_t n, int64_t npad,
+                                   RowWin win) {
+    int64_t i = win.r0 + blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= n || j < i) return;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     if (i == j) {   // src/genKING.cpp:628
-        store_sym(oibs0, packed, n, i, j, 0.0);
-        store_sym(okin, packed, n, i, j, 0.5);
+        store_sym(oibs0, packed, n, i, j, 0.0, win.pbase);
+        store_sym(okin, packed, n, i, j, 0.5, win.pbase);
         return;
     }
-    int64_t plane = npad * npad, k = i * npad + j;
+    int64_t plane = win.rows * npad, k = (i - win.r0) * npad + j;
     uint32_t ibs0 = cnt[k], nloci = cnt[plane + k], het = cnt[2 * plane + k];
     uint32_t n1 = cnt[3 * plane + k], n2 = cnt[4 * plane + k];
     uint32_t sumsq = het + 4u * ibs0;   // sum (g_i - g_j)^2, src/genKING.cpp:421
@@ -284,8 +295,8 @@ __global__ void king_robust_kernel(const uint32_t *__restrict__ cnt,
     else
         v = 0.5 - (double)sumsq / (4.0 * (double)min(n1, n2));
     if (!isfinite(v)) v = nan;
-    store_sym(oibs0, packed, n, i, j, r0);
-    store_sym(okin, packed, n, i, j, v);
+    store_sym(oibs0, packed, n, i, j, r0, win.pbase);
+    store_sym(okin, packed, n, i, j, v, win.pbase);
 }
 
 // copy counter planes to full symmetric int32 matrices (row = first sample)
@@ -360,11 +371,24 @@ __global__ void beta_final_kernel(const double *__restrict__ raw, double *__rest
 }
 
 static void need_accum(snprel_ctx *c, int est) {
-    if (c->accum_est == est && c->accum_reduced) return;   // reduced across ranks already
+    if (c->accum_est == est && c->accum_reduced && c->accum_win_r0 == row_window(c).r0) return;   // reduced across ranks already
     bitcount_accumulate(c, est);
 }
 
 static dim3 tri_grid(int64_t n) { return dim3((unsigned)n, (unsigned)((n + 127) / 128)); }
+// rows of the current window x column chunks
+static dim3 win_grid(snprel_ctx *c) {
+    RowWin w = row_window(c);
+    return dim3((unsigned)(w.r1 - w.r0), (unsigned)((c->n_samp + 127) / 128));
+}
+static void need_packed_in_window(snprel_ctx *c, int packed, const char *who) {
+    if (!full_window(c) && !packed) fail("%s: a row window returns the packed upper triangle only (useMatrix)", who);
+}
+static size_t win_out_count(snprel_ctx *c, int packed) {
+    if (!full_window(c)) return window_packed_count(c);
+    int64_t n = c->n_samp;
+    return packed ? (size_t)n * (n + 1) / 2 : (size_t)n * n;
+}
 
 static void check_grid_rows(int64_t n) {
     if (n > 2147483647ll) fail("too many samples for the epilogue grid");
@@ -385,30 +409,34 @@ void ibs_num_finish(snprel_ctx *c, int32_t *i0, int32_t *i1, int32_t *i2) {
     need_accum(c, SNPREL_EST_IBS);
     int64_t n = c->n_samp;
     check_grid_rows(n);
+    const int packed = full_window(c) ? 0 : 1;   // a row window yields packed int32 slices
+    const size_t oc = win_out_count(c, packed);
     DevBuf<int32_t> o;
-    o.alloc((size_t)3 * n * n);
-    ibs_num_kernel<<<tri_grid(n), 128, 0, c->stream>>>(c->cnt.p, o.p, o.p + n * n, o.p + 2 * n * n,
-                                                       n, c->n_samp_pad);
+    o.alloc(3 * oc);
+    ibs_num_kernel<<<win_grid(c), 128, 0, c->stream>>>(c->cnt.p, o.p, o.p + oc, o.p + 2 * oc, n, c->n_samp_pad,
+                                                       row_window(c), packed);
     KERNEL_CHECK(c);
-    d2h(c, i0, o.p, (size_t)n * n);
-    d2h(c, i1, o.p + n * n, (size_t)n * n);
-    d2h(c, i2, o.p + 2 * n * n, (size_t)n * n);
+    d2h(c, i0, o.p, oc);
+    d2h(c, i1, o.p + oc, oc);
+    d2h(c, i2, o.p + 2 * oc, oc);
 }
 
 void ibs_ave_finish(snprel_ctx *c, double *out, int packed) {
     if (!out) fail("snprel_ibs_ave: NULL output");
+    need_packed_in_window(c, packed, "snprel_ibs_ave");
     need_accum(c, SNPREL_EST_IBS);
     int64_t n = c->n_samp;
     check_grid_rows(n);
     DevBuf<double> o;
-    o.alloc(out_count(n, packed));
-    ibs_ave_kernel<<<tri_grid(n), 128, 0, c->stream>>>(c->cnt.p, o.p, packed, n, c->n_samp_pad);
+    o.alloc(win_out_count(c, packed));
+    ibs_ave_kernel<<<win_grid(c), 128, 0, c->stream>>>(c->cnt.p, o.p, packed, n, c->n_samp_pad, row_window(c));
     KERNEL_CHECK(c);
-    d2h(c, out, o.p, out_count(n, packed));
+    d2h(c, out, o.p, win_out_count(c, packed));
 }
 
 void king_robust_finish(snprel_ctx *c, const int32_t *fam, double *ibs0, double *kin, int packed) {
     if (!ibs0 || !kin) fail("snprel_king_robust: NULL output");
+    need_packed_in_window(c, packed, "snprel_king_robust");
     need_accum(c, SNPREL_EST_KING_ROBUST);
     int64_t n = c->n_samp;
     check_grid_rows(n);
@@ -419,10 +447,10 @@ void king_robust_finish(snprel_ctx *c, const int32_t *fam, double *ibs0, double 
                                    c->stream));
     }
     DevBuf<double> o;
-    size_t oc = out_count(n, packed);
+    size_t oc = win_out_count(c, packed);
     o.alloc(2 * oc);
-    king_robust_kernel<<<tri_grid(n), 128, 0, c->stream>>>(c->cnt.p, fam ? dfam.p : nullptr, o.p,
-                                                           o.p + oc, packed, n, c->n_samp_pad);
+    king_robust_kernel<<<win_grid(c), 128, 0, c->stream>>>(c->cnt.p, fam ? dfam.p : nullptr, o.p, o.p + oc,
+                                                           packed, n, c->n_samp_pad, row_window(c));
     KERNEL_CHECK(c);
     d2h(c, ibs0, o.p, oc);
     d2h(c, kin, o.p + oc, oc);
@@ -430,6 +458,7 @@ void king_robust_finish(snprel_ctx *c, const int32_t *fam, double *ibs0, double 
 
 static void counts_finish(snprel_ctx *c, int est, int np, int32_t *out) {
     if (!out) fail("NULL output");
+    if (!full_window(c)) fail("raw counter matrices are not available inside a row window");
     need_accum(c, est);
     int64_t n = c->n_samp;
     check_grid_rows(n);
@@ -450,6 +479,7 @@ void beta_counts_finish(snprel_ctx *c, int32_t *out2) { counts_finish(c, SNPREL_
 void indiv_beta_finish(snprel_ctx *c, int inbreeding, int grm_flavour, double *out, int packed,
                        double *avg_out) {
     if (!out) fail("snprel_indiv_beta: NULL output");
+    if (!full_window(c)) fail("snprel_indiv_beta: needs the whole matrix (global average), not a row window");
     need_accum(c, SNPREL_EST_BETA);
     int64_t n = c->n_samp;
     check_grid_rows(n);

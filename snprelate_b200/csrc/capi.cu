@@ -275,6 +275,24 @@ int snprel_mark_reduced(snprel_ctx *c) {
     API_END(c)
 }
 
+int snprel_set_row_window(snprel_ctx *c, int64_t row0, int64_t rows) {
+    API_BEGIN(c)
+    if (c->n_samp <= 0) fail("snprel_set_row_window: no genotype workspace");
+    if (rows < 0 || row0 < 0 || (row0 % 256) || (rows % 256)) fail("snprel_set_row_window: row0 and rows must be non-negative multiples of 256");
+    if (rows > 0 && row0 >= c->n_samp) fail("snprel_set_row_window: window starts past the last sample");
+    c->win_r0 = rows > 0 ? row0 : 0;
+    c->win_rows = rows;
+    c->accum_est = -1;
+    c->accum_reduced = false;
+    API_END(c)
+}
+int snprel_window_count(snprel_ctx *c, int64_t *count) {
+    API_BEGIN(c)
+    if (c->n_samp <= 0) fail("snprel_window_count: no genotype workspace");
+    if (count) *count = (int64_t)window_packed_count(c);
+    API_END(c)
+}
+
 // ---- introspection -----------------------------------------------------------
 int64_t snprel_kernel_launches(snprel_ctx *c) { return c ? c->launches : 0; }
 int snprel_last_hot_kernel(snprel_ctx *c, double *ms, int64_t *launches, double *units) {

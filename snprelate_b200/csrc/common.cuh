@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -83,6 +84,20 @@ struct SnpStat {
     int32_t pad;
 };
 
+// Row window of the N x N output that the accumulators currently cover.  The default window
+// is the whole matrix; for N where N^2 accumulators do not fit in HBM the host walks windows of
+// 256-aligned rows and receives each window's slice of the row-packed upper triangle
+// (rows r0..r0+rows are contiguous there, CdMatTri order src/dGenGWAS.h:556-561).
+struct RowWin {
+    long long r0;      // first row (multiple of 256)
+    long long rows;    // window height in rows (multiple of 256)
+    long long r1;      // min(r0 + rows, n_samp): end of the valid rows
+    long long pbase;   // packed index of (r0, r0)
+};
+__host__ __device__ inline long long tri_idx(long long n, long long i, long long j) {
+    return j + i * (2 * n - i - 1) / 2;
+}
+
 struct ReduceBuf {
     void *ptr;
     int64_t count;
@@ -120,8 +135,10 @@ struct snprel_ctx {
     bool planes_valid = false;
 
     // accumulators
+    int64_t win_r0 = 0, win_rows = 0;   // row window (win_rows == 0: whole matrix)
     int accum_est = -1;          // estimator the accumulators belong to
     bool accum_reduced = false;  // true after snprel_mark_reduced
+    int64_t accum_win_r0 = 0;    // first row of the window the accumulators were built for
     snprel::DevBuf<uint32_t> cnt;         // packed-bit counters [ncnt][npad][npad]
     int cnt_planes = 0;
     snprel::DevBuf<double> cnt_f64;       // KING-homo f64 pair sums [2][npad][npad]
@@ -139,6 +156,7 @@ struct snprel_ctx {
     snprel::DevBuf<double> scr_plan;      // plan statistics [3]
     snprel::DevBuf<int2> scr_tiles;       // tile work list
     snprel::DevBuf<int> scr_cnt;          // per-sample genotype sum / missing count [2][npad]
+    snprel::DevBuf<double> scr_part;      // per-block float64 partial sums of the tables kernel
     std::vector<int> host_cnt;
     std::vector<int2> host_tiles;
 
@@ -153,6 +171,22 @@ struct snprel_ctx {
 namespace snprel {
 
 inline void count_launch(snprel_ctx *c, int64_t n = 1) { c->launches += n; }
+
+inline RowWin row_window(const snprel_ctx *c) {
+    RowWin w;
+    w.r0 = c->win_rows > 0 ? c->win_r0 : 0;
+    w.rows = c->win_rows > 0 ? c->win_rows : c->n_samp_pad;
+    if (w.r0 + w.rows > c->n_samp_pad) w.rows = c->n_samp_pad - w.r0;
+    w.r1 = std::min<long long>(w.r0 + w.rows, c->n_samp);
+    w.pbase = tri_idx(c->n_samp, w.r0, w.r0);
+    return w;
+}
+inline bool full_window(const snprel_ctx *c) { return c->win_rows <= 0; }
+// number of packed upper-triangle entries in the window's rows
+inline size_t window_packed_count(const snprel_ctx *c) {
+    RowWin w = row_window(c);
+    return (size_t)(tri_idx(c->n_samp, w.r1 - 1, c->n_samp - 1) + 1 - w.pbase);
+}
 
 #define KERNEL_CHECK(ctx)                                   \
     do {                                                    \

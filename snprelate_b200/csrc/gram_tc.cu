@@ -80,6 +80,7 @@ struct Params {
     long long ld;
     long long plane_stride;
     long long n_samp;
+    long long row0;          // first row of the output window (planes hold rows row0 ..)
     const int2 *tiles;       // (tile_m, tile_n) in units of 256 samples
     int stages_total;
     int stages_per_split;
@@ -316,7 +317,7 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
         const long long gi = (long long)tile.x * TM2 + (long long)rank * HM + (row & ~15) + core_pos_to_sample(row & 15);
 #pragma unroll 1
         for (int q = 0; q < NP; q++) {
-            long long *outp = P.out + (long long)P.plane[q] * P.plane_stride + gi * P.ld;
+            long long *outp = P.out + (long long)P.plane[q] * P.plane_stride + (gi - P.row0) * P.ld;
             const long long mul = 1ll << P.shift[q];
 #pragma unroll 1
             for (int cc = 0; cc < 4; cc++) {
@@ -364,10 +365,12 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     geno_pad_tail(c);
     const int64_t n = c->n_samp, npad = c->n_samp_pad;
     const int nt = (int)((n + TM2 - 1) / TM2);
+    const RowWin win = row_window(c);
     std::vector<int2> &tiles = c->host_tiles;
     tiles.clear();
-    for (int tm = 0; tm < nt; tm++)
+    for (int tm = (int)(win.r0 / TM2); tm < nt && (long long)tm * TM2 < win.r1; tm++)
         for (int tn = (upper_only ? tm : 0); tn < nt; tn++) tiles.push_back(make_int2(tm, tn));
+    if (tiles.empty()) return;
     DevBuf<int2> &dtiles = c->scr_tiles;
     dtiles.alloc(tiles.size());
     CUDA_CHECK(cudaMemcpyAsync(dtiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice,
@@ -437,7 +440,8 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
         P.tabB = passes[i].tabB;
         P.out = out_planes;
         P.ld = npad;
-        P.plane_stride = npad * npad;
+        P.plane_stride = win.rows * npad;
+        P.row0 = win.r0;
         P.n_samp = n;
         P.tiles = dtiles.p;
         P.stages_total = stages_total;

@@ -210,7 +210,7 @@ sample_count_kernel(const uint8_t *__restrict__ geno, int64_t n_snp, int64_t row
 // pass order: U digits (nU), W digits (nW), D digits (nD), D2 digits (nD2)
 __global__ void tables_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int64_t cap, int est,
                               int bayesian, int frac_bits, int frac_bits_w, int frac_bits_d, int nU, int nW, int nD, int nD2,
-                              uint32_t *__restrict__ tab, double *__restrict__ scalars,
+                              uint32_t *__restrict__ tab, double *__restrict__ scalars /*[gridDim.x][2] partials*/,
                               long long *__restrict__ iscalars, int *__restrict__ overflow) {
     int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double d = 0, d2 = 0;
@@ -262,8 +262,9 @@ __global__ void tables_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        atomicAdd(scalars + 0, s0[0]);
-        atomicAdd(scalars + 1, s1[0]);
+        // float64 block partials are summed in block order by the host (run-to-run deterministic)
+        scalars[2 * blockIdx.x + 0] = s0[0];
+        scalars[2 * blockIdx.x + 1] = s1[0];
         atomicAdd(reinterpret_cast<unsigned long long *>(iscalars), (unsigned long long)s2[0]);
     }
 }
@@ -490,15 +491,27 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     DevBuf<int> &ovf = c->scr_flags;
     ovf.alloc(2);
     ovf.zero(c->stream);
+    const unsigned tblocks = (unsigned)((c->n_snp + 255) / 256);
+    c->scr_part.alloc((size_t)std::max(tblocks, 1u) * 2);
     if (c->n_snp > 0) {
-        tables_kernel<<<(unsigned)((c->n_snp + 255) / 256), 256, 0, c->stream>>>(
-            c->stat.p, c->n_snp, cap, est, plan.bayesian, f, fw, fd, nU, nW, nD, nD2, tab.p, c->scalars.p,
-            c->iscalars.p, ovf.p);
+        tables_kernel<<<tblocks, 256, 0, c->stream>>>(c->stat.p, c->n_snp, cap, est, plan.bayesian, f, fw, fd, nU, nW,
+                                                      nD, nD2, tab.p, c->scr_part.p, c->iscalars.p, ovf.p);
         KERNEL_CHECK(c);
     }
     int hovf = 0;
+    std::vector<double> part((size_t)tblocks * 2);
     CUDA_CHECK(cudaMemcpyAsync(&hovf, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (tblocks)
+        CUDA_CHECK(cudaMemcpyAsync(part.data(), c->scr_part.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                                   c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    double hsc[4] = {0, 0, 0, 0};
+    for (unsigned b = 0; b < tblocks; b++) {
+        hsc[0] += part[2 * b];
+        hsc[1] += part[2 * b + 1];
+    }
+    CUDA_CHECK(cudaMemcpyAsync(c->scalars.p, hsc, sizeof(hsc), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));   // hsc lives on this stack frame
     if (hovf) fail("internal: fixed-point digit overflow (table %d, frac_bits %d/%d/%d)", hovf, f, fw, fd);
 
     // per-sample vectors
@@ -514,7 +527,7 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
 
     // Gram planes: 0 = numerator, 1 = missing-pair denominator (or KING-homo d), 2 = KING-homo d2
     const int nplanes = homo ? 2 : ((nD > 0) ? 2 : 1);
-    c->acc.alloc((size_t)nplanes * npad * npad);
+    c->acc.alloc((size_t)nplanes * row_window(c).rows * npad);
     c->acc.zero(c->stream);
     c->acc_planes = nplanes;
 
@@ -537,6 +550,7 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     c->hot_units = 0.5 * (double)c->n_samp * (double)c->n_samp * (double)c->n_snp;
 
     c->plan = plan;
+    c->accum_win_r0 = row_window(c).r0;
     c->accum_est = est;
     c->accum_reduced = false;
     c->reduce_list.clear();
@@ -564,17 +578,18 @@ __device__ __forceinline__ void store_sym2(double *out, int packed, int64_t n, i
 __global__ void numerator_kernel(const long long *__restrict__ acc, const long long *__restrict__ vec,
                                  const int *__restrict__ nmiss, long long n_snp_total,
                                  double *__restrict__ out, double inv_scale, double inv_scale_lo, int64_t n,
-                                 int64_t npad) {
-    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+                                 int64_t npad, RowWin win) {
+    int64_t i = win.r0 + blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= n || j < i) return;
+    const int64_t li = i - win.r0;   // row inside the window
     // a sample without a single valid genotype contributes exactly 0, as in the reference
     // (its centred genotypes are all 0, src/genPCA.h:103)
     if (nmiss[i] == n_snp_total || nmiss[j] == n_snp_total) {
-        out[i * n + j] = 0.0;
+        out[li * n + j] = 0.0;
         return;
     }
-    long long q = acc[i * npad + j] - vec[VEC_W * npad + i];
-    out[i * n + j] = (double)q * inv_scale - (double)vec[VEC_WLO * npad + i] * inv_scale_lo;
+    long long q = acc[li * npad + j] - vec[VEC_W * npad + i];
+    out[li * n + j] = (double)q * inv_scale - (double)vec[VEC_WLO * npad + i] * inv_scale_lo;
 }
 
 // mode 0: Eigenstrat (scale = (n-1)/trace); 1: GCTA; 3: EIGMIX (mul = 1 ibd / 2 GRM)
@@ -582,17 +597,18 @@ __global__ void grm_final_kernel(const double *__restrict__ num, const long long
                                  const long long *__restrict__ vec, double *__restrict__ out, int packed,
                                  int mode, double scale, double sum_den, long long nlocus,
                                  double inv_fix, int has_den, int diagadj, double mul, int64_t n,
-                                 int64_t npad) {
-    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+                                 int64_t npad, RowWin win) {
+    int64_t i = win.r0 + blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= n || j < i) return;
-    double c = num[i * n + j];
+    const int64_t li = i - win.r0;
+    double c = num[li * n + j];
     double v;
     if (mode == 0) {
         v = c * scale;
     } else {
         long long dq = 0;
         if (has_den)
-            dq = vec[VEC_D * npad + i] + vec[VEC_D * npad + j] - acc[npad * npad + i * npad + j];
+            dq = vec[VEC_D * npad + i] + vec[VEC_D * npad + j] - acc[win.rows * npad + li * npad + j];
         if (mode == 1) {
             v = c / (double)(2 * (nlocus - dq));      // src/genPCA.cpp:1233-1236
         } else {
@@ -600,7 +616,10 @@ __global__ void grm_final_kernel(const double *__restrict__ num, const long long
             v = c / (sum_den - (double)dq * inv_fix) * mul;                // :153-155, :645-652
         }
     }
-    store_sym2(out, packed, n, i, j, v);
+    if (packed)
+        out[tri_idx(n, i, j) - win.pbase] = v;
+    else
+        store_sym2(out, 0, n, i, j, v);
 }
 
 __global__ void diag_kernel(const double *__restrict__ m, double *__restrict__ d, int64_t n) {
@@ -640,7 +659,7 @@ static void d2h(snprel_ctx *c, T *host, const T *dev, size_t count) {
 
 static void need_grm_accum(snprel_ctx *c, int est, int bayesian) {
     if (est == SNPREL_GRM_CORR) est = SNPREL_GRM_GCTA;
-    if (c->accum_est == est && c->accum_reduced) return;
+    if (c->accum_est == est && c->accum_reduced && c->accum_win_r0 == row_window(c).r0) return;
     snprel_plan plan{};
     plan.frac_bits = -1;
     plan.frac_bits_w = -1;
@@ -663,14 +682,25 @@ static Globals read_globals(snprel_ctx *c) {
 }
 
 // numerator into dev buffer `num` (n x n, upper triangle valid)
+static dim3 win_grid(snprel_ctx *c) {
+    RowWin w = row_window(c);
+    return dim3((unsigned)(w.r1 - w.r0), (unsigned)((c->n_samp + 127) / 128));
+}
+static size_t win_out_count(snprel_ctx *c, int packed) {
+    if (!full_window(c)) return window_packed_count(c);
+    return out_count(c->n_samp, packed);
+}
+
+// numerator rows of the current window: [r1 - r0][n]
 static void build_numerator(snprel_ctx *c, DevBuf<double> &num) {
     int64_t n = c->n_samp;
-    num.alloc((size_t)n * n);
-    numerator_kernel<<<tri_grid(n), 128, 0, c->stream>>>(c->acc.p, c->samp_sum.p, c->scr_cnt.p + c->n_samp_pad,
+    RowWin w = row_window(c);
+    num.alloc((size_t)(w.r1 - w.r0) * n);
+    numerator_kernel<<<win_grid(c), 128, 0, c->stream>>>(c->acc.p, c->samp_sum.p, c->scr_cnt.p + c->n_samp_pad,
                                                          (long long)c->plan.n_snp, num.p,
                                                          std::ldexp(1.0, -c->plan.frac_bits),
                                                          std::ldexp(1.0, -(c->plan.frac_bits + W_EXTRA_BITS)), n,
-                                                         c->n_samp_pad);
+                                                         c->n_samp_pad, w);
     KERNEL_CHECK(c);
 }
 
@@ -690,25 +720,30 @@ static double trace_of(snprel_ctx *c, const double *m, int64_t n) {
 static void grm_device(snprel_ctx *c, int method, int packed, int diagadj, double mul, DevBuf<double> &o,
                        double *trace_xtx) {
     int64_t n = c->n_samp, npad = c->n_samp_pad;
+    const RowWin w = row_window(c);
+    if (!full_window(c) && !packed) fail("a row window returns the packed upper triangle only (useMatrix)");
     DevBuf<double> num;
     build_numerator(c, num);
     Globals g = read_globals(c);
     const int has_den = c->acc_planes > 1;
-    o.alloc(out_count(n, packed));
+    o.alloc(win_out_count(c, packed));
     if (method == SNPREL_GRM_EIGENSTRAT) {
-        double tr = trace_of(c, num.p, n);
+        // whole matrix: trace of the computed numerator (CdMatTri::Trace, src/genPCA.cpp:1387);
+        // row window: the diagonal lives in other windows, so use the same trace evaluated from
+        // the per-SNP genotype counts by the plan kernel (equal up to float64 rounding)
+        double tr = full_window(c) ? trace_of(c, num.p, n) : c->plan.scale * (double)std::max<int64_t>(n - 1, 1);
         if (trace_xtx) *trace_xtx = tr;
-        grm_final_kernel<<<tri_grid(n), 128, 0, c->stream>>>(num.p, c->acc.p, c->samp_sum.p, o.p, packed,
+        grm_final_kernel<<<win_grid(c), 128, 0, c->stream>>>(num.p, c->acc.p, c->samp_sum.p, o.p, packed,
                                                              0, (double)(n - 1) / tr, 0, 0, 0, 0, 0, 1, n,
-                                                             npad);
+                                                             npad, w);
     } else if (method == SNPREL_GRM_GCTA || method == SNPREL_GRM_CORR) {
-        grm_final_kernel<<<tri_grid(n), 128, 0, c->stream>>>(num.p, c->acc.p, c->samp_sum.p, o.p, packed,
+        grm_final_kernel<<<win_grid(c), 128, 0, c->stream>>>(num.p, c->acc.p, c->samp_sum.p, o.p, packed,
                                                              1, 0, 0, g.nlocus, 1.0, has_den, 0, 1, n,
-                                                             npad);
+                                                             npad, w);
     } else {
-        grm_final_kernel<<<tri_grid(n), 128, 0, c->stream>>>(
+        grm_final_kernel<<<win_grid(c), 128, 0, c->stream>>>(
             num.p, c->acc.p, c->samp_sum.p, o.p, packed, 3, 0, g.sum_den, 0,
-            std::ldexp(1.0, -c->plan.frac_bits_d), has_den, diagadj, mul, n, npad);
+            std::ldexp(1.0, -c->plan.frac_bits_d), has_den, diagadj, mul, n, npad, w);
     }
     KERNEL_CHECK(c);
 }
@@ -716,6 +751,7 @@ static void grm_device(snprel_ctx *c, int method, int packed, int diagadj, doubl
 void grm_finish(snprel_ctx *c, int method, double *out, int packed) {
     if (!out) fail("snprel_grm: NULL output");
     int64_t n = c->n_samp;
+    if (!full_window(c) && method == SNPREL_GRM_CORR) fail("method \"Corr\" needs the whole matrix, not a row window");
     need_grm_accum(c, method, 0);
     DevBuf<double> o;
     if (method == SNPREL_GRM_CORR) {
@@ -730,7 +766,7 @@ void grm_finish(snprel_ctx *c, int method, double *out, int packed) {
         return;
     }
     grm_device(c, method, packed, 0, method == SNPREL_GRM_EIGMIX ? 2.0 : 1.0, o, nullptr);
-    d2h(c, out, o.p, out_count(n, packed));
+    d2h(c, out, o.p, win_out_count(c, packed));
 }
 
 // top-k eigenpairs of the symmetric matrix `m` (upper triangle valid), descending:
@@ -784,6 +820,7 @@ static void eigen_topk(snprel_ctx *c, const double *m_upper, int64_t n, int k, d
 void pca_finish(snprel_ctx *c, int eigen_cnt, int bayesian, double *genmat, double *trace_xtx,
                 double *trace_val, double *eigval, double *eigvec) {
     if (eigen_cnt < 0) fail("Invalid 'eigen.cnt'.");   // src/genPCA.cpp:1423-1424
+    if (!full_window(c)) fail("snprel_pca needs the whole matrix, not a row window");
     int64_t n = c->n_samp;
     need_grm_accum(c, SNPREL_GRM_EIGENSTRAT, bayesian);
     DevBuf<double> o;
@@ -798,6 +835,7 @@ void pca_finish(snprel_ctx *c, int eigen_cnt, int bayesian, double *genmat, doub
 void eigmix_finish(snprel_ctx *c, int eigen_cnt, int diagadj, double *ibd, double *afreq, double *eigval,
                    double *eigvec) {
     int64_t n = c->n_samp;
+    if (!full_window(c)) fail("snprel_eigmix needs the whole matrix, not a row window (use snprel_grm EIGMIX)");
     need_grm_accum(c, SNPREL_GRM_EIGMIX, 0);
     if (eigen_cnt < 0 || eigen_cnt > n) eigen_cnt = (int)n;   // src/genEIGMIX.cpp:675-676
     DevBuf<double> o;
@@ -817,16 +855,17 @@ void eigmix_finish(snprel_ctx *c, int eigen_cnt, int diagadj, double *ibd, doubl
 __global__ void king_homo_kernel(const uint32_t *__restrict__ cnt, const long long *__restrict__ acc,
                                  const long long *__restrict__ vec, double *__restrict__ k0o,
                                  double *__restrict__ k1o, int packed, double s1, double s2,
-                                 double inv_fix, int has_den, int64_t n, int64_t npad) {
-    int64_t i = blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+                                 double inv_fix, int has_den, int64_t n, int64_t npad, RowWin win) {
+    int64_t i = win.r0 + blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= n || j < i) return;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    double *k0p = packed ? k0o - win.pbase : k0o, *k1p = packed ? k1o - win.pbase : k1o;
     if (i == j) {   // src/genKING.cpp:524
-        store_sym2(k0o, packed, n, i, j, 0.0);
-        store_sym2(k1o, packed, n, i, j, 0.0);
+        store_sym2(k0p, packed, n, i, j, 0.0);
+        store_sym2(k1p, packed, n, i, j, 0.0);
         return;
     }
-    int64_t plane = npad * npad, k = i * npad + j;
+    int64_t plane = win.rows * npad, k = (i - win.r0) * npad + j;
     double ibs0 = (double)cnt[k], sumsq = (double)(cnt[2 * plane + k] + 4u * cnt[k]);
     double a1 = s1, a2 = s2;
     if (has_den) {
@@ -838,8 +877,8 @@ __global__ void king_homo_kernel(const uint32_t *__restrict__ cnt, const long lo
     double theta = 0.5 - sumsq / (8 * a1);          // src/genKING.cpp:527-529
     double k0 = ibs0 / (2 * a2);
     double k1 = 2 - 2 * k0 - 4 * theta;
-    store_sym2(k0o, packed, n, i, j, isfinite(k0) ? k0 : nan);
-    store_sym2(k1o, packed, n, i, j, isfinite(k1) ? k1 : nan);
+    store_sym2(k0p, packed, n, i, j, isfinite(k0) ? k0 : nan);
+    store_sym2(k1p, packed, n, i, j, isfinite(k1) ? k1 : nan);
 }
 
 void king_homo_finish(snprel_ctx *c, double *k0, double *k1, int packed) {
@@ -856,12 +895,14 @@ void king_homo_finish(snprel_ctx *c, double *k0, double *k1, int packed) {
     const int has_den = plan.total_missing > 0;
     const int fb = c->plan.frac_bits_d;
     bitcount_accumulate(c, SNPREL_EST_KING_ROBUST);
+    if (!full_window(c) && !packed) fail("snprel_king_homo: a row window returns the packed upper triangle only");
     DevBuf<double> o;
-    size_t oc = out_count(n, packed);
+    size_t oc = win_out_count(c, packed);
     o.alloc(2 * oc);
-    king_homo_kernel<<<tri_grid(n), 128, 0, c->stream>>>(c->cnt.p, c->acc.p, c->samp_sum.p, o.p, o.p + oc,
+    king_homo_kernel<<<win_grid(c), 128, 0, c->stream>>>(c->cnt.p, c->acc.p, c->samp_sum.p, o.p, o.p + oc,
                                                          packed, g.sum_den, g.sum_den2,
-                                                         std::ldexp(1.0, -fb), has_den, n, c->n_samp_pad);
+                                                         std::ldexp(1.0, -fb), has_den, n, c->n_samp_pad,
+                                                         row_window(c));
     KERNEL_CHECK(c);
     d2h(c, k0, o.p, oc);
     d2h(c, k1, o.p + oc, oc);
