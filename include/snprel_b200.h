@@ -207,6 +207,8 @@ int snprel_last_plan(snprel_ctx *ctx, snprel_plan *plan);
 int snprel_set_row_window(snprel_ctx *ctx, int64_t row0, int64_t rows);
 /* Number of packed entries the current window produces. */
 int snprel_window_count(snprel_ctx *ctx, int64_t *count);
+/* Free / total device memory in bytes (cudaMemGetInfo): the host sizes row windows with it. */
+int snprel_mem_info(snprel_ctx *ctx, int64_t *free_bytes, int64_t *total_bytes);
 
 /* ---- introspection for benchmarks / tests ------------------------------ */
 

@@ -77,6 +77,7 @@ def load_library():
         "snprel_last_plan": [p, C.POINTER(Plan)],
         "snprel_set_row_window": [p, i64, i64],
         "snprel_window_count": [p, C.POINTER(i64)],
+        "snprel_mem_info": [p, C.POINTER(i64), C.POINTER(i64)],
         "snprel_last_hot_kernel": [p, C.POINTER(dbl), C.POINTER(i64), C.POINTER(dbl)],
         "snprel_time_accumulate": [p, i32, i32, C.POINTER(dbl)],
         "snprel_last_step_ms": [p, C.POINTER(dbl)],
@@ -107,7 +108,7 @@ EXPORTED_SYMBOLS = [
     "snprel_ibs_num", "snprel_ibs_ave", "snprel_king_robust", "snprel_king_robust_counts",
     "snprel_king_homo", "snprel_indiv_beta", "snprel_indiv_beta_counts", "snprel_grm",
     "snprel_pca", "snprel_eigmix", "snprel_plan_local", "snprel_accumulate",
-    "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced", "snprel_last_plan", "snprel_set_row_window", "snprel_window_count",
+    "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced", "snprel_last_plan", "snprel_set_row_window", "snprel_window_count", "snprel_mem_info",
     "snprel_kernel_launches", "snprel_last_hot_kernel", "snprel_time_accumulate", "snprel_last_step_ms", "snprel_invalidate",
     "snprel_table_gram", "snprel_debug_flags",
 ]
@@ -212,6 +213,46 @@ class Context:
         cnt = C.c_int64()
         self._ck(self.lib.snprel_window_count(self.h, C.byref(cnt)))
         return cnt.value
+
+    def mem_info(self):
+        f, t = C.c_int64(), C.c_int64()
+        self._ck(self.lib.snprel_mem_info(self.h, C.byref(f), C.byref(t)))
+        return f.value, t.value
+
+    def auto_window_rows(self, bytes_per_pair):
+        """0 when whole-matrix accumulators (bytes_per_pair per pair, padded square) fit
+        comfortably in free HBM, else a window height (multiple of 256) that uses about a
+        quarter of it."""
+        n, _ = self.geno_dim()
+        npad = (n + 255) // 256 * 256
+        free, _ = self.mem_info()
+        if bytes_per_pair * npad * npad <= 0.5 * free:
+            return 0
+        rows = int(0.25 * free / (bytes_per_pair * npad)) // 256 * 256
+        return max(256, rows)
+
+    def packed_by_windows(self, fn, rows, rank=0, world=1):
+        """Run fn() (an estimator call with packed=True) over row windows of height `rows`
+        and concatenate the packed slices.  With world > 1 this rank only computes windows
+        rank, rank + world, ... and returns a list of (packed_offset, slice[s]) -- the N x N
+        output tiled across GPUs that all hold the same genotypes, no collective."""
+        n, _ = self.geno_dim()
+        parts, offs, off = [], [], 0
+        try:
+            for k, (r0, h) in enumerate(self.windows(rows)):
+                self.set_row_window(r0, h)
+                cnt = self.window_count()
+                if k % world == rank:
+                    parts.append(fn())
+                    offs.append(off)
+                off += cnt
+        finally:
+            self.set_row_window(0, 0)
+        if world > 1:
+            return list(zip(offs, parts))
+        if isinstance(parts[0], (tuple, list)):
+            return tuple(np.concatenate([p[i] for p in parts]) for i in range(len(parts[0])))
+        return np.concatenate(parts)
 
     def windows(self, rows):
         """Iterate (row0, rows) windows of height `rows` (multiple of 256) over all samples."""

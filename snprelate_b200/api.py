@@ -137,7 +137,11 @@ def snpgdsGRM(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_mo
     ws = _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, missing_rate,
                      num_thread, verbose, device)
     with ws["ctx"] as ctx:
-        grm, avg = ctx.grm(method, packed=bool(useMatrix))
+        rows = ctx.auto_window_rows(16) if (useMatrix and method in ("GCTA", "EIGMIX", "Eigenstrat")) else 0
+        if rows:      # N^2 int64 planes do not fit: walk row windows, packed slices concatenated
+            grm, avg = ctx.packed_by_windows(lambda: ctx.grm(method, packed=True)[0], rows), 0.0
+        else:
+            grm, avg = ctx.grm(method, packed=bool(useMatrix))
     if useMatrix and method != "Corr":
         grm = _newmat(ws["n_samp"], grm)
     if not with_id:
@@ -194,7 +198,9 @@ def snpgdsIBS(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_mo
     ws = _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, missing_rate,
                      num_thread, verbose, device)
     with ws["ctx"] as ctx:
-        ibs = ctx.ibs_ave(packed=bool(useMatrix))
+        rows = ctx.auto_window_rows(12) if useMatrix else 0      # TIBS: 12 bytes per pair
+        ibs = (ctx.packed_by_windows(lambda: ctx.ibs_ave(packed=True), rows) if rows
+               else ctx.ibs_ave(packed=bool(useMatrix)))
     if useMatrix:
         ibs = _newmat(ws["n_samp"], ibs)
     return {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "ibs": ibs}
@@ -241,7 +247,9 @@ def snpgdsIBDKING(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remov
             a, b = ctx.king_homo(packed=bool(useMatrix))
             names = ("k0", "k1")
         else:
-            a, b = ctx.king_robust(fam, packed=bool(useMatrix))
+            rows = ctx.auto_window_rows(20) if useMatrix else 0  # TS_KINGRobust: 20 bytes per pair
+            a, b = (ctx.packed_by_windows(lambda: ctx.king_robust(fam, packed=True), rows) if rows
+                    else ctx.king_robust(fam, packed=bool(useMatrix)))
             names = ("IBS0", "kinship")
     if useMatrix:
         a, b = _newmat(ws["n_samp"], a), _newmat(ws["n_samp"], b)

@@ -286,6 +286,14 @@ int snprel_set_row_window(snprel_ctx *c, int64_t row0, int64_t rows) {
     c->accum_reduced = false;
     API_END(c)
 }
+int snprel_mem_info(snprel_ctx *c, int64_t *free_bytes, int64_t *total_bytes) {
+    API_BEGIN(c)
+    size_t f = 0, t = 0;
+    CUDA_CHECK(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    API_END(c)
+}
 int snprel_window_count(snprel_ctx *c, int64_t *count) {
     API_BEGIN(c)
     if (c->n_samp <= 0) fail("snprel_window_count: no genotype workspace");
