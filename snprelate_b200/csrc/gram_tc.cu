@@ -58,13 +58,15 @@ constexpr int FIRST_PROD_WARP = 2;
 constexpr int THREADS = 32 * (FIRST_PROD_WARP + PROD_WARPS);
 constexpr int A_BYTES = HM * SK;   // 16 KB per pass per stage
 constexpr int B_BYTES = HN * SK;   // 16 KB per stage
-constexpr int STAGE_BYTES = MAXP * A_BYTES + B_BYTES;   // 48 KB
-constexpr int PF_DEPTH = 3;
+// A launch fills the two TMEM accumulators either with two passes over one B tile (NP=2, NB=1)
+// or with ONE pass over two B tiles (NP=1, NB=2: a 256 x 512 tile, so that the odd pass of a
+// table costs half a launch instead of ~0.8).  Either way a stage holds three 16 KB operands.
+constexpr int STAGE_BYTES = 3 * A_BYTES;   // 48 KB
 constexpr int PF_BOX = SK * 16;
-constexpr int PF_NBOX = (HM + HN) / 64;                  // 2 A boxes + 2 B boxes
 constexpr int PF_TAB = SK * 4;
-constexpr int PF_BYTES = PF_NBOX * PF_BOX + MAXP * PF_TAB;   // 9 KB
-constexpr int BAR_OFFSET = NSTAGE * STAGE_BYTES + PF_DEPTH * PF_BYTES;
+constexpr int PF_MAX_DEPTH = 3;
+constexpr int PF_RING_BYTES = 27648;       // 3 x (4 boxes + 2 tables) or 2 x (6 boxes + 1 table)
+constexpr int BAR_OFFSET = NSTAGE * STAGE_BYTES + PF_RING_BYTES;
 constexpr int SMEM_BYTES = BAR_OFFSET + 1024;
 constexpr int LBO = (HM / 16) * 128;   // 8 cores per 8-SNP group (A and B halves alike)
 constexpr int SBO = 128;
@@ -158,9 +160,14 @@ __device__ __forceinline__ uint32_t make_idesc2() {
            ((uint32_t)(TM2 >> 4) << 24);
 }
 
-template <int NP>
+template <int NP, int NB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap tmap) {
+    static_assert(NP * NB == 2, "two TMEM accumulators of 256 columns");
+    constexpr int PF_DEPTH = NB == 1 ? 3 : 2;
+    constexpr int PF_NBOX = 2 + 2 * NB;                       // A quads 0-1, then two quads per B tile
+    constexpr int PF_BYTES = PF_NBOX * PF_BOX + NP * PF_TAB;
+    static_assert(PF_DEPTH * PF_BYTES <= PF_RING_BYTES, "ring does not fit");
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -170,8 +177,8 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
     auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
     const uint32_t accum_bar = bar_base + 8u * (2 * NSTAGE);
     auto pf_full = [&](int s) { return bar_base + 8u * (2 * NSTAGE + 1 + s); };
-    auto pf_empty = [&](int s) { return bar_base + 8u * (2 * NSTAGE + 1 + PF_DEPTH + s); };
-    constexpr int SLOT_IDX = 2 * NSTAGE + 1 + 2 * PF_DEPTH;
+    auto pf_empty = [&](int s) { return bar_base + 8u * (2 * NSTAGE + 1 + PF_MAX_DEPTH + s); };
+    constexpr int SLOT_IDX = 2 * NSTAGE + 1 + 2 * PF_MAX_DEPTH;
     const uint32_t tmem_slot = bar_base + 8u * SLOT_IDX;
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem + BAR_OFFSET + 8 * SLOT_IDX);
     const uint32_t pf_base = smem_base + NSTAGE * STAGE_BYTES;
@@ -217,11 +224,15 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
                     const uint32_t stage_addr = smem_base + s * STAGE_BYTES;
 #pragma unroll
                     for (int j = 0; j < SK / MMA_K; j++) {
-                        uint64_t bdesc = make_desc(stage_addr + MAXP * A_BYTES + j * 4 * LBO, LBO, SBO);
 #pragma unroll
-                        for (int p = 0; p < NP; p++) {
-                            uint64_t adesc = make_desc(stage_addr + p * A_BYTES + j * 4 * LBO, LBO, SBO);
-                            umma2_i8(tmem_base + (uint32_t)(p * TN2), adesc, bdesc, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                        for (int b = 0; b < NB; b++) {
+                            uint64_t bdesc = make_desc(stage_addr + (NP + b) * A_BYTES + j * 4 * LBO, LBO, SBO);
+#pragma unroll
+                            for (int p = 0; p < NP; p++) {
+                                uint64_t adesc = make_desc(stage_addr + p * A_BYTES + j * 4 * LBO, LBO, SBO);
+                                umma2_i8(tmem_base + (uint32_t)((p * NB + b) * TN2), adesc, bdesc, idesc,
+                                         (it > 0 || j > 0) ? 1u : 0u);
+                            }
                         }
                     }
                     umma2_commit_mc(empty_bar(s));
@@ -234,7 +245,7 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
     } else if (warp == 1) {
         // ===================== TMA loader =====================
         if (lane == 0) {
-            const int ax = (tile.x * TM2 + (int)rank * HM) / 4, bx = (tile.y * TN2 + (int)rank * HN) / 4;
+            const int ax = (tile.x * TM2 + (int)rank * HM) / 4;
             for (int it = 0; it < nst; it++) {
                 const int sl = it % PF_DEPTH;
                 const uint32_t ph = (uint32_t)(it / PF_DEPTH) & 1u;
@@ -246,7 +257,14 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
 #pragma unroll
                 for (int q = 0; q < HM / 64; q++) tma_load_2d(slot + q * PF_BOX, &tmap, ax + q * 16, y, bar);
 #pragma unroll
-                for (int q = 0; q < HN / 64; q++) tma_load_2d(slot + (HM / 64 + q) * PF_BOX, &tmap, bx + q * 16, y, bar);
+                for (int b = 0; b < NB; b++) {
+                    // columns beyond the padded matrix are out of bounds for the tensor map and arrive
+                    // as zeros (code 0 against tabB[0] = 0 in every channel): they contribute nothing
+                    const int bx = ((tile.y * NB + b) * TN2 + (int)rank * HN) / 4;
+#pragma unroll
+                    for (int q = 0; q < HN / 64; q++)
+                        tma_load_2d(slot + (2 + 2 * b + q) * PF_BOX, &tmap, bx + q * 16, y, bar);
+                }
 #pragma unroll
                 for (int q = 0; q < NP; q++)
                     bulk_load(slot + PF_NBOX * PF_BOX + q * PF_TAB, P.tabA[q] + (long long)y, PF_TAB, bar);
@@ -261,9 +279,9 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
         const int kg = sl >> 3, r = sl & 7;
         uint32_t tb[1] = {P.tabB};
         const uint32_t a_off = kg * LBO + (half * 4) * SBO + r * 16;
-        const uint32_t b_off = MAXP * A_BYTES + a_off;
+        const uint32_t b_off = NP * A_BYTES + a_off;
         const uint32_t pa = half * PF_BOX + sl * 16;
-        const uint32_t pb = (HM / 64 + half) * PF_BOX + sl * 16;
+        const uint32_t pb = (2 + half) * PF_BOX + sl * 16;
         const uint32_t pt = PF_NBOX * PF_BOX + sl * 4;
         uint32_t full_remote[NSTAGE];
 #pragma unroll
@@ -277,12 +295,16 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
             mbar_wait(pf_full(ps), (uint32_t)(it / PF_DEPTH) & 1u, P.error_flag, 5);
             const uint32_t slot = pf_base + (uint32_t)ps * PF_BYTES;
             const uint4 ca = ld_shared_v4(slot + pa);
-            const uint4 cb = ld_shared_v4(slot + pb);
+            uint4 cb[NB];
+#pragma unroll
+            for (int b = 0; b < NB; b++) cb[b] = ld_shared_v4(slot + pb + 2 * b * PF_BOX);
             uint32_t ct[NP];
 #pragma unroll
             for (int q = 0; q < NP; q++) ct[q] = ld_shared_u32(slot + pt + q * PF_TAB);
-            mbar_arrive_after(pf_empty(ps), ca.x ^ ca.y ^ ca.z ^ ca.w ^ cb.x ^ cb.y ^ cb.z ^ cb.w ^ ct[0] ^ ct[NP - 1],
-                              P.sh32);
+            uint32_t dep = ca.x ^ ca.y ^ ca.z ^ ca.w ^ ct[0] ^ ct[NP - 1];
+#pragma unroll
+            for (int b = 0; b < NB; b++) dep ^= cb[b].x ^ cb[b].y ^ cb[b].z ^ cb[b].w;
+            mbar_arrive_after(pf_empty(ps), dep, P.sh32);
 
             mbar_wait(empty_bar(s), phase ^ 1u, P.error_flag, 2);
             const uint32_t stage_addr = smem_base + s * STAGE_BYTES;
@@ -294,11 +316,14 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
                 for (int q = 0; q < NP; q++) dst[q] = stage_addr + q * A_BYTES + a_off + w * SBO;
                 expand_word<NP>(aw[w], ct, dst);
             }
-            const uint32_t bw[4] = {cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
-            for (int w = 0; w < 4; w++) {
-                uint32_t dst[1] = {stage_addr + b_off + w * SBO};
-                expand_word<1>(bw[w], tb, dst);
+            for (int b = 0; b < NB; b++) {
+                const uint32_t bw[4] = {cb[b].x, cb[b].y, cb[b].z, cb[b].w};
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    uint32_t dst[1] = {stage_addr + b_off + b * B_BYTES + w * SBO};
+                    expand_word<1>(bw[w], tb, dst);
+                }
             }
             fence_proxy_async_smem();
             // constant-index select keeps full_remote[] in registers
@@ -316,19 +341,20 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
         const int row = quarter * 32 + lane;
         const long long gi = (long long)tile.x * TM2 + (long long)rank * HM + (row & ~15) + core_pos_to_sample(row & 15);
 #pragma unroll 1
-        for (int q = 0; q < NP; q++) {
+        for (int a = 0; a < 2; a++) {        // accumulator a = pass (a / NB), B tile (a % NB)
+            const int q = a / NB, bt = a % NB;
             long long *outp = P.out + (long long)P.plane[q] * P.plane_stride + (gi - P.row0) * P.ld;
             const long long mul = 1ll << P.shift[q];
 #pragma unroll 1
             for (int cc = 0; cc < 4; cc++) {
                 const int col0 = colhalf * 128 + cc * 32;
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(q * TN2 + col0), v);
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * TN2 + col0), v);
                 if (gi < P.n_samp) {
 #pragma unroll
                     for (int k = 0; k < 32; k++) {
                         int col = col0 + k;
-                        long long gj = (long long)tile.y * TN2 + (col & ~15) + core_pos_to_sample(col & 15);
+                        long long gj = ((long long)tile.y * NB + bt) * TN2 + (col & ~15) + core_pos_to_sample(col & 15);
                         int val = (int)v[k];
                         if (val != 0 && gj < P.n_samp && (!P.upper_only || gj >= gi))
                             atomicAdd(reinterpret_cast<unsigned long long *>(outp + gj),
@@ -359,6 +385,30 @@ static double wave_efficiency(int64_t items, int64_t slots) {
     return (double)items / (double)(waves * slots);
 }
 
+// SNP splits for `ntile` tiles: enough work items to fill the chip, chosen to minimise the
+// wave-quantisation tail (74 CTA pairs run at a time)
+static void choose_splits(snprel_ctx *c, int64_t ntile, int stages_total, int SK, int &sps, int64_t &splits) {
+    const int64_t slots = std::max(1, c->num_sms / 2);
+    int64_t best = 1;
+    double best_eff = -1;
+    for (int64_t sp = 1; sp <= std::min<int64_t>(stages_total, 64); sp++) {
+        // each extra split costs one more epilogue of 64-bit atomics per tile
+        double eff = wave_efficiency(ntile * sp, slots) * (1.0 - 0.002 * (double)(sp - 1));
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = sp;
+        }
+        if (ntile * sp >= 8 * slots && eff > 0.97) break;
+    }
+    splits = best;
+    if (c->debug_flags & 2u) splits = 1;   // test hook: one CTA pair walks the whole SNP range
+    sps = (int)((stages_total + splits - 1) / splits);
+    const int max_stages_i32 = (int)((2147483647ll / 256) / SK);   // int32 accumulator headroom
+    sps = std::min(sps, max_stages_i32);
+    splits = (stages_total + sps - 1) / sps;
+    if (splits > 65535) fail("too many SNP splits");
+}
+
 void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *out_planes, bool upper_only) {
     using namespace tc2;
     if (npass <= 0) return;
@@ -366,11 +416,16 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     const int64_t n = c->n_samp, npad = c->n_samp_pad;
     const int nt = (int)((n + TM2 - 1) / TM2);
     const RowWin win = row_window(c);
+    // two work lists: 256 x 256 tiles for two-pass launches, 256 x 512 tiles for one-pass launches
     std::vector<int2> &tiles = c->host_tiles;
     tiles.clear();
     for (int tm = (int)(win.r0 / TM2); tm < nt && (long long)tm * TM2 < win.r1; tm++)
         for (int tn = (upper_only ? tm : 0); tn < nt; tn++) tiles.push_back(make_int2(tm, tn));
-    if (tiles.empty()) return;
+    const size_t n1 = tiles.size();
+    for (int tm = (int)(win.r0 / TM2); tm < nt && (long long)tm * TM2 < win.r1; tm++)
+        for (int tn2 = (upper_only ? tm / 2 : 0); 2 * tn2 < nt; tn2++) tiles.push_back(make_int2(tm, tn2));
+    const size_t n2 = tiles.size() - n1;
+    if (n1 == 0) return;
     DevBuf<int2> &dtiles = c->scr_tiles;
     dtiles.alloc(tiles.size());
     CUDA_CHECK(cudaMemcpyAsync(dtiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice,
@@ -380,27 +435,10 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     CUDA_CHECK(cudaMemsetAsync(derr, 0, sizeof(int), c->stream));
 
     const int stages_total = (int)(round_up(std::max<int64_t>(c->n_snp, 1), SK) / SK);
-    // SNP splits: enough work items to fill the chip, chosen to minimise the wave-quantisation tail
-    const int64_t slots = std::max(1, c->num_sms / 2);   // concurrent CTA pairs
-    const int64_t ntile = (int64_t)tiles.size();
-    int64_t best = 1;
-    double best_eff = -1;
-    for (int64_t sp = 1; sp <= std::min<int64_t>(stages_total, 64); sp++) {
-        // each extra split costs an epilogue (~0.3 stage-equivalents of atomics per 256 stages)
-        double eff = wave_efficiency(ntile * sp, slots) * (1.0 - 0.002 * (double)(sp - 1));
-        if (eff > best_eff + 1e-9) {
-            best_eff = eff;
-            best = sp;
-        }
-        if (ntile * sp >= 8 * slots && eff > 0.97) break;
-    }
-    int64_t splits = best;
-    if (c->debug_flags & 2u) splits = 1;   // test hook: one CTA pair walks the whole SNP range
-    int sps = (int)((stages_total + splits - 1) / splits);
-    const int max_stages_i32 = (int)((2147483647ll / 256) / SK);   // int32 accumulator headroom
-    sps = std::min(sps, max_stages_i32);
-    splits = (stages_total + sps - 1) / sps;
-    if (splits > 65535) fail("too many SNP splits");
+    int sps1 = 1, sps2 = 1;
+    int64_t splits1 = 1, splits2 = 1;
+    choose_splits(c, (int64_t)n1, stages_total, SK, sps1, splits1);
+    choose_splits(c, (int64_t)n2, stages_total, SK, sps2, splits2);
 
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -428,8 +466,8 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
 
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel2<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel2<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_done = true;
     }
 
@@ -443,9 +481,7 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
         P.plane_stride = win.rows * npad;
         P.row0 = win.r0;
         P.n_samp = n;
-        P.tiles = dtiles.p;
         P.stages_total = stages_total;
-        P.stages_per_split = sps;
         P.upper_only = upper_only ? 1 : 0;
         P.sh32 = 32;
         P.error_flag = derr;
@@ -459,11 +495,17 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
             np++;
         }
         P.npass = np;
-        dim3 grid((unsigned)(2 * tiles.size()), (unsigned)splits);
-        if (np == 2)
-            table_gram_kernel2<2><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
-        else
-            table_gram_kernel2<1><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
+        if (np == 2) {
+            P.tiles = dtiles.p;
+            P.stages_per_split = sps1;
+            dim3 grid((unsigned)(2 * n1), (unsigned)splits1);
+            table_gram_kernel2<2, 1><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
+        } else {
+            P.tiles = dtiles.p + n1;
+            P.stages_per_split = sps2;
+            dim3 grid((unsigned)(2 * n2), (unsigned)splits2);
+            table_gram_kernel2<1, 2><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
+        }
         KERNEL_CHECK(c);
         c->hot_launches++;
     }
