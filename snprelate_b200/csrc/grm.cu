@@ -795,22 +795,28 @@ static void eigen_topk(snprel_ctx *c, const double *m_upper, int64_t n, int k, d
     cusolverDnHandle_t h;
     if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) fail("cusolverDnCreate failed");
     cusolverDnSetStream(h, c->stream);
-    // full divide-and-conquer decomposition and keep the first k columns: on B200 syevd takes
-    // 1.8 s for n = 10 000 (float64) while syevdx with an index range (bisection + inverse
-    // iteration) took 9-18 s for k = 32
-    int lwork = 0;
+    // full divide-and-conquer decomposition (64-bit API, the routine torch.linalg.eigh uses:
+    // 1.8 s for n = 10 000 in float64 on B200) and keep the first k columns.  The legacy
+    // cusolverDnDsyevd took 26 s and syevdx with an index range 9-18 s for the same matrix.
     DevBuf<int> info;
     info.alloc(1);
-    cusolverStatus_t st = cusolverDnDsyevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n,
-                                                     a.p, (int)n, w.p, &lwork);
+    cusolverDnParams_t params = nullptr;
+    cusolverDnCreateParams(&params);
+    size_t wdev = 0, whost = 0;
+    cusolverStatus_t st = cusolverDnXsyevd_bufferSize(h, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER,
+                                                     (int64_t)n, CUDA_R_64F, a.p, (int64_t)n, CUDA_R_64F, w.p,
+                                                     CUDA_R_64F, &wdev, &whost);
     if (st != CUSOLVER_STATUS_SUCCESS) {
+        cusolverDnDestroyParams(params);
         cusolverDnDestroy(h);
-        fail("cusolverDnDsyevd_bufferSize failed (%d)", (int)st);
+        fail("cusolverDnXsyevd_bufferSize failed (%d)", (int)st);
     }
-    DevBuf<double> work;
-    work.alloc((size_t)lwork);
-    st = cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, a.p, (int)n, w.p, work.p,
-                          lwork, info.p);
+    DevBuf<uint8_t> work;
+    work.alloc(std::max<size_t>(wdev, 1));
+    std::vector<uint8_t> hwork(std::max<size_t>(whost, 1));
+    st = cusolverDnXsyevd(h, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int64_t)n, CUDA_R_64F, a.p,
+                          (int64_t)n, CUDA_R_64F, w.p, CUDA_R_64F, work.p, wdev, hwork.data(), whost, info.p);
+    cusolverDnDestroyParams(params);
     int hinfo = 0;
     CUDA_CHECK(cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
