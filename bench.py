@@ -259,10 +259,11 @@ def run_ours(args):
               "frac_bits_W": int(pl.frac_bits_w),
               "tensor_passes_per_step": int(pl.digits) + int(pl.digits_w) + int(pl.digits_d)}
     pk, pk_kind = peaks()
-    traffic = None
+    traffic, tensor_pct = None, None
     tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tp):      # dram__bytes_read+write of the dominant kernel, one ncu --set full capture
-        traffic = json.load(open(tp)).get("traffic_bytes_per_launch")
+        rec = json.load(open(tp))
+        traffic, tensor_pct = rec.get("traffic_bytes_per_launch"), rec.get("tensor_pipe_active_pct")
     hot_per_step_ms = hot_ms / args.steps
     alg_flops = float(N_SAMP) * N_SAMP * N_SNP           # 2 flop per pair-SNP, symmetric half
     achieved = alg_flops / (hot_per_step_ms * 1e-3) / 1e12
@@ -271,7 +272,7 @@ def run_ours(args):
                 "frac": achieved / peak, "traffic": traffic,
                 "kernel": "snprel::tc::table_gram_kernel (tcgen05.mma kind::i8)",
                 "launches_per_step": hot_launch // args.steps, "fixed_point": passes,
-                "tensor_pipe_active_pct_ncu": 95.0, "kernel_ms_per_step": hot_per_step_ms,
+                "tensor_pipe_active_pct_ncu": tensor_pct, "kernel_ms_per_step": hot_per_step_ms,
                 "share_of_step": hot_per_step_ms / ms_per_step,
                 "peak_source": f"bf16_tflops_sustained of {pk_kind} MEASURED_PEAKS.json (kernel timed inside a long step); "
                                "algorithmic flops = N^2*M; the kernel executes one int8 MMA pass per base-256 digit "
