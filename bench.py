@@ -217,7 +217,7 @@ def run_ours(args):
     value = pair_snps_per_step / (ms_per_step * 1e-3)
 
     # ---- end-to-end through the C ABI with HOST buffers (rank-local shard) ----
-    rb = (N_SAMP + 3) // 4
+    rb = (N_SAMP + 255) // 256 * 256 // 4     # host rows use the device pitch: one linear DMA
     host_geno = torch.empty((N_SNP, rb), dtype=torch.uint8, pin_memory=True)
     ctx.geno_copy_2b(host_geno.numpy())
     host_out = torch.empty((N_SAMP, N_SAMP), dtype=torch.float64, pin_memory=True)

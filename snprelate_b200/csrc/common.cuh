@@ -117,6 +117,7 @@ struct snprel_ctx {
     int64_t launches = 0;
     uint32_t debug_flags = 0;
     int num_sms = 148;
+    bool gram_attr_done = false;   // cudaFuncSetAttribute(max dynamic smem) done on this device
 
     // workspace
     int64_t n_samp = 0;        // N

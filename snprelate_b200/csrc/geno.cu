@@ -252,14 +252,17 @@ void geno_push_2b(snprel_ctx *c, const uint8_t *host, int64_t cnt, int64_t row_b
     // one strided DMA straight into the padded device rows (no staging copy), then a small
     // kernel rewrites the bytes at / beyond the last sample so that padding reads as missing
     const int64_t w = (c->n_samp + 3) / 4;
-    CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)c->row_bytes, host, (size_t)row_bytes_in, (size_t)w, (size_t)cnt,
-                                 cudaMemcpyHostToDevice, c->stream));
+    if (row_bytes_in == c->row_bytes)   // host rows already have the device pitch: one linear copy
+        CUDA_CHECK(cudaMemcpyAsync(dst, host, (size_t)cnt * c->row_bytes, cudaMemcpyHostToDevice, c->stream));
+    else
+        CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)c->row_bytes, host, (size_t)row_bytes_in, (size_t)w, (size_t)cnt,
+                                     cudaMemcpyHostToDevice, c->stream));
     const int64_t pad_from = c->n_samp / 4;              // first byte that holds any padding sample
     const int64_t pad_bytes = c->row_bytes - pad_from;
     if (pad_bytes > 0) {
         int64_t total = cnt * pad_bytes;
-        fix_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(dst, cnt, c->n_samp, pad_from,
-                                                                              pad_bytes, w, c->row_bytes);
+        fix_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(
+            dst, cnt, c->n_samp, pad_from, pad_bytes, row_bytes_in == c->row_bytes ? c->row_bytes : w, c->row_bytes);
         KERNEL_CHECK(c);
     }
     CUDA_CHECK(cudaStreamSynchronize(c->stream));   // the host block may be reused by the caller

@@ -464,11 +464,10 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
         if (r != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled failed (%d)", (int)r);
     }
 
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!c->gram_attr_done) {   // per device: a process may hold contexts on several GPUs
         CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel2<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel2<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_done = true;
+        c->gram_attr_done = true;
     }
 
     std::vector<char> used((size_t)npass, 0);
