@@ -79,3 +79,50 @@ def test_two_rank_snp_sharding_matches_single_gpu():
         assert np.array_equal(res[rank]["ibs"], O.ibs_counts(g))
     for k in ref:
         assert np.array_equal(res[0][k], res[1][k])
+
+
+def _tile_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import snprelate_b200 as S
+    from oracle import snprel_oracle as O
+    torch.cuda.set_device(rank)
+    n, m = 1100, 4000
+    g = O.synth_geno(n, m, seed=41, miss_rate=0.01)
+    ctx = S.Context(rank)
+    ctx.geno_begin(n, m)          # every rank holds ALL genotypes; the N x N output is dealt out
+    ctx.geno_push_u8(g)
+    parts = ctx.packed_by_windows(lambda: ctx.grm("GCTA", packed=True)[0], 256, rank=rank, world=world)
+    ibs = ctx.packed_by_windows(lambda: ctx.ibs_ave(packed=True), 256, rank=rank, world=world)
+    q.put((rank, parts, ibs))
+
+
+def test_output_tiled_across_two_gpus():
+    """N x N output tiled across GPUs (second mode): each rank computes
+    every second 256-row window of the packed triangle, no collective; the union of the slices
+    is the single-GPU result."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    from oracle import snprel_oracle as O
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    procs = [ctxm.Process(target=_tile_worker, args=(r, 2, 0, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    n = 1100
+    g = O.synth_geno(n, 4000, seed=41, miss_rate=0.01)
+    grm = np.full(n * (n + 1) // 2, np.nan)
+    ibs = np.full(n * (n + 1) // 2, np.nan)
+    for rank, parts, ib in res:
+        for off, sl in parts:
+            grm[off:off + len(sl)] = sl
+        for off, sl in ib:
+            ibs[off:off + len(sl)] = sl
+    ref = O.to_packed_upper(O.grm_gcta(g))
+    assert np.max(np.abs(grm - ref) / np.maximum(np.abs(ref), 1)) < 1e-10
+    assert np.array_equal(ibs, O.to_packed_upper(O.ibs_ave(O.ibs_counts(g))))

@@ -174,6 +174,22 @@ def test_table_gram_exact(ctx):
         assert np.array_equal(ctx.table_gram(tA, tB), ref)
 
 
+def test_rare_alleles_need_more_digits(ctx):
+    """Singletons / doubletons give weights 1/(p(1-p)) in the thousands: the format chooser
+    must add digits (tensor passes) instead of losing precision."""
+    n, m = 1500, 3000
+    g = O.synth_geno(n, m, seed=23, miss_rate=0.01, maf_lo=0.0004, maf_hi=0.02)
+    keep = O.select_snp_base(g, True, float("nan"), float("nan"))
+    g = np.ascontiguousarray(g[keep])
+    load(ctx, g)
+    got = ctx.grm("GCTA")[0]
+    pl = ctx.last_plan()
+    assert pl.max_abs > 500 and pl.digits >= 6, (pl.max_abs, pl.digits)
+    assert relerr(got, O.grm_gcta(g)) < TOL
+    assert relerr(ctx.grm("Eigenstrat")[0], O.grm_eigenstrat(g)) < TOL
+    assert relerr(ctx.grm("EIGMIX")[0], O.grm_eigmix(g)) < TOL
+
+
 def test_long_k_loop_single_cta():
     """Hundreds of pipeline stages in ONE CTA (SNP splitting disabled): exercises every
     ring-buffer phase flip of the TMA / producer / MMA pipeline, exact integers."""
