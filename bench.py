@@ -270,7 +270,7 @@ def run_ours(args):
     peak = pk.get("bf16_tflops_sustained", 1400.0)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "kernel": "snprel::tc::table_gram_kernel (tcgen05.mma kind::i8)",
+                "kernel": "snprel::tc2::table_gram_kernel2 (tcgen05.mma.cta_group::2.kind::i8, CTA pairs)",
                 "launches_per_step": hot_launch // args.steps, "fixed_point": passes,
                 "tensor_pipe_active_pct_ncu": tensor_pct, "kernel_ms_per_step": hot_per_step_ms,
                 "share_of_step": hot_per_step_ms / ms_per_step,
