@@ -90,6 +90,12 @@ int snprel_snp_ratefreq(snprel_ctx *ctx, double *af, double *maf, double *mr);
 int snprel_select_snp_base(snprel_ctx *ctx, int remove_mono, double maf,
                            double missrate, uint8_t *out_sel,
                            int64_t *n_removed);
+/* gnrSelSNP_Base_Ex -> CdBaseWorkSpace::Select_SNP_Base_Ex
+ * (src/dGenGWAS.cpp:399-470): the same filter with the MAF taken from
+ * caller-supplied allele frequencies afreq[n_snp]; non-finite = dropped. */
+int snprel_select_snp_base_ex(snprel_ctx *ctx, const double *afreq,
+                              int remove_mono, double maf, double missrate,
+                              uint8_t *out_sel, int64_t *n_removed);
 
 /* ---- packed-bit estimators (integer, bit exact) ----------------------- */
 
@@ -97,6 +103,21 @@ int snprel_select_snp_base(snprel_ctx *ctx, int remove_mono, double maf,
 int snprel_ibs_num(snprel_ctx *ctx, int32_t *ibs0, int32_t *ibs1, int32_t *ibs2);
 /* gnrIBSAve (src/genIBS.cpp:441-497). */
 int snprel_ibs_ave(snprel_ctx *ctx, double *out, int packed);
+/* gnrIBD_PLINK (src/genIBS.cpp:558-639): PLINK method-of-moments k0, k1 from the
+ * IBS counters.  afreq_in (nullable, double[n_snp]): user allele frequencies
+ * (NaN or outside [0,1] = SNP ignored, no finite-sample correction factor, as
+ * R/IBD.R:51-52 + src/genIBD.cpp:253-338); NULL = frequencies and correction
+ * from the genotype counts.  afreq_out (nullable) receives the frequencies used. */
+int snprel_ibd_mom(snprel_ctx *ctx, const double *afreq_in, int kinship_constraint,
+                   int packed, double *k0, double *k1, double *afreq_out);
+/* The same in two steps, for SNP-sharded ranks: sums6 = the five un-normalised
+ * expectation sums {a00,a01,a02,a11,a12} + nValid over this context's SNPs (add
+ * them across ranks), then the pair epilogue on the (reduced) IBS counters. */
+int snprel_ibd_mom_sums(snprel_ctx *ctx, const double *afreq_in, double *sums6,
+                        double *afreq_out);
+int snprel_ibd_mom_from_sums(snprel_ctx *ctx, const double *sums6,
+                             int kinship_constraint, int packed, double *k0,
+                             double *k1);
 /* gnrIBD_KING_Robust (src/genKING.cpp:576-679).  family_id: int[n_samp], same
  * id (and not SNPREL_NA_INT) = within-family estimator; NULL = all unrelated. */
 int snprel_king_robust(snprel_ctx *ctx, const int32_t *family_id, double *ibs0,

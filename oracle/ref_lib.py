@@ -103,6 +103,18 @@ class RefWorkspace:
         _ck(_lib().ref_king_homo(int(nthread), _p(a), _p(b)))
         return a, b
 
+    def ibd_mom(self, nthread=1, allele_freq=None, kinship_constraint=False):
+        """gnrIBD_PLINK (src/genIBS.cpp:558-639) -> (k0, k1, afreq)."""
+        m, n = self.dims()
+        k0, k1, af = np.empty((n, n)), np.empty((n, n)), np.empty(m)
+        afin = None
+        if allele_freq is not None:
+            afin = np.ascontiguousarray(allele_freq, dtype=np.float64)
+            assert afin.shape == (m,)
+        _ck(_lib().ref_ibd_mom(int(nthread), _p(afin) if afin is not None else None,
+                               int(kinship_constraint), _p(k0), _p(k1), _p(af)))
+        return k0, k1, af
+
     def indiv_beta(self, nthread=1, inbreeding=True):
         n = self.dims()[1]
         o = np.empty((n, n))

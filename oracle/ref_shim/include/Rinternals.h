@@ -76,6 +76,9 @@ void R_CheckUserInterrupt(void);
 #define R_FINITE(x) R_finite(x)
 #define ISNA(x) ((x) != (x))
 #define ISNAN(x) ((x) != (x))
+/* the shim driver always passes vectors of the requested type already */
+#define AS_INTEGER(x) (x)
+#define AS_NUMERIC(x) (x)
 #define NEW_NUMERIC(n) Rf_allocVector(REALSXP, n)
 #define NEW_INTEGER(n) Rf_allocVector(INTSXP, n)
 #define NEW_LOGICAL(n) Rf_allocVector(LGLSXP, n)

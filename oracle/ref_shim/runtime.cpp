@@ -241,12 +241,6 @@ void GDS_SetError(const char *msg) { g_err = msg ? msg : ""; }
 const char *GDS_GetError(void) { return g_err.c_str(); }
 }  // extern "C"
 
-// gnrIBD_PLINK (not on the accelerated path) references two genIBD.cpp functions
-namespace IBD {
-void Init_EPrIBD_IBS(const double *, double *, bool, long) { throw ErrCoreArray("shim: PLINK MoM is not built"); }
-void Est_PLINK_Kinship(int, int, int, double &, double &, bool) { throw ErrCoreArray("shim: PLINK MoM is not built"); }
-}
-
 // ------------------------------------------------------------------ driver
 extern "C" {
 SEXP gnrGRM(SEXP, SEXP, SEXP, SEXP, SEXP);
@@ -256,6 +250,7 @@ SEXP gnrIBSAve(SEXP, SEXP, SEXP);
 SEXP gnrIBSNum(SEXP, SEXP);
 SEXP gnrIBD_KING_Robust(SEXP, SEXP, SEXP, SEXP);
 SEXP gnrIBD_KING_Homo(SEXP, SEXP, SEXP);
+SEXP gnrIBD_PLINK(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 SEXP gnrIBD_Beta(SEXP, SEXP, SEXP, SEXP);
 }
 
@@ -378,6 +373,18 @@ int ref_king_homo(int nthread, double *k0, double *k1) {
     SEXP r = gnrIBD_KING_Homo(Rf_ScalarInteger(nthread), Rf_ScalarLogical(0), Rf_ScalarLogical(0));
     copy_real(VECTOR_ELT(r, 0), k0);
     copy_real(VECTOR_ELT(r, 1), k1);
+    REF_CATCH
+}
+int ref_ibd_mom(int nthread, const double *afreq_in, int constraint, double *k0, double *k1, double *afreq) {
+    REF_TRY
+    const int m = GWAS::MCWorkingGeno.Space().SNPNum();
+    SEXP af = Rf_allocVector(REALSXP, afreq_in ? m : 0);
+    if (afreq_in) memcpy(REAL(af), afreq_in, sizeof(double) * (size_t)m);
+    SEXP r = gnrIBD_PLINK(Rf_ScalarInteger(nthread), af, Rf_ScalarLogical(afreq_in != nullptr),
+                          Rf_ScalarLogical(constraint), Rf_ScalarLogical(0), Rf_ScalarLogical(0));
+    copy_real(VECTOR_ELT(r, 0), k0);
+    copy_real(VECTOR_ELT(r, 1), k1);
+    copy_real(VECTOR_ELT(r, 2), afreq);
     REF_CATCH
 }
 int ref_indiv_beta(int nthread, int inbreeding, double *out) {

@@ -374,6 +374,114 @@ def grm_indivbeta(counts):
 # ---------------------------------------------------------------------------
 
 
+def ibd_mom_tables(geno, allele_freq=None):
+    """IBD::Init_EPrIBD_IBS (src/genIBD.cpp:253-338): expected P(IBS i | IBD j)
+    averaged over SNPs, sequential f64 sums in SNP order.  Without allele_freq
+    the frequency is that of the A allele from the genotype counts and PLINK's
+    finite-sample correction factor is applied; with allele_freq the counts are
+    zero and no correction is used (src/genIBS.cpp:585-587).
+    Returns (E[3,3], afreq[nsnp])."""
+    nsnp = geno.shape[0]
+    if allele_freq is None:
+        aa = (geno == 2).sum(axis=1).astype(np.int64)
+        ab = (geno == 1).sum(axis=1).astype(np.int64)
+        bb = (geno == 0).sum(axis=1).astype(np.int64)
+    else:
+        aa = ab = bb = np.zeros(nsnp, dtype=np.int64)
+    e = np.zeros((3, 3))
+    afreq = np.empty(nsnp)
+    nvalid = 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for i in range(nsnp):
+            n = 2 * int(aa[i] + ab[i] + bb[i])
+            p = (2.0 * aa[i] + ab[i]) / n if n > 0 else np.nan
+            if allele_freq is not None:
+                p = float(allele_freq[i])
+                if np.isfinite(p) and (p < 0 or p > 1):
+                    p = np.nan
+            afreq[i] = p
+            q = 1 - p
+            na = np.float64(n)
+            x = np.float64(2 * aa[i] + ab[i])
+            y = np.float64(2 * bb[i] + ab[i])
+            if allele_freq is None:
+                f3 = (na / (na - 1)) * (na / (na - 2)) * (na / (na - 3))
+                a00 = 2*p*p*q*q * ((x-1)/x * (y-1)/y * f3)
+                a01 = (4*p*p*p*q * ((x-1)/x * (x-2)/x * f3)
+                       + 4*p*q*q*q * ((y-1)/y * (y-2)/y * f3))
+                a02 = (q*q*q*q * ((y-1)/y * (y-2)/y * (y-3)/y * f3)
+                       + p*p*p*p * ((x-1)/x * (x-2)/x * (x-3)/x * f3)
+                       + 4*p*p*q*q * ((x-1)/x * (y-1)/y * f3))
+                f2 = na / (na - 1) * na / (na - 2)
+                a11 = (2*p*p*q * ((x-1)/x * na/(na-1) * na/(na-2))
+                       + 2*p*q*q * ((y-1)/y * na/(na-1) * na/(na-2)))
+                a12 = (p*p*p * ((x-1)/x * (x-2)/x * na/(na-1) * na/(na-2))
+                       + q*q*q * ((y-1)/y * (y-2)/y * na/(na-1) * na/(na-2))
+                       + p*p*q * ((x-1)/x * na/(na-1) * na/(na-2))
+                       + p*q*q * ((y-1)/y * na/(na-1) * na/(na-2)))
+                del f2
+            else:
+                a00 = 2*p*p*q*q
+                a01 = 4*p*p*p*q + 4*p*q*q*q
+                a02 = q*q*q*q + p*p*p*p + 4*p*p*q*q
+                a11 = 2*p*p*q + 2*p*q*q
+                a12 = p*p*p + q*q*q + p*p*q + p*q*q
+            if all(np.isfinite(v) for v in (a00, a01, a02, a11, a12)):
+                e[0, 0] += a00
+                e[0, 1] += a01
+                e[0, 2] += a02
+                e[1, 1] += a11
+                e[1, 2] += a12
+                nvalid += 1
+        nv = np.float64(nvalid)
+        e[0, 0] /= nv
+        e[0, 1] /= nv
+        e[0, 2] /= nv
+        e[1, 1] /= nv
+        e[1, 2] /= nv
+    e[2, 2] = 1.0
+    return e, afreq
+
+
+def ibd_mom(counts, e, kinship_constraint=False):
+    """IBD::Est_PLINK_Kinship over all pairs (src/genIBD.cpp:341-383) as
+    gnrIBD_PLINK applies it (src/genIBS.cpp:591-607): diagonal k0 = k1 = 0.
+    counts = int [3, n, n] IBS0/1/2.  Returns (k0, k1) f64 [n, n]."""
+    c = counts.astype(np.float64)
+    ntot = (counts[0] + counts[1] + counts[2]).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        e00, e01, e11 = e[0, 0] * ntot, e[0, 1] * ntot, e[1, 1] * ntot
+        e02, e12, e22 = e[0, 2] * ntot, e[1, 2] * ntot, e[2, 2] * ntot
+        k0 = c[0] / e00
+        k1 = (c[1] - k0 * e01) / e11
+        k2 = (c[2] - k0 * e02 - k1 * e12) / e22
+        # the six sequential clamps, each seeing the previous one's result
+        m = k0 > 1
+        k0 = np.where(m, 1.0, k0); k1 = np.where(m, 0.0, k1); k2 = np.where(m, 0.0, k2)
+        m = k1 > 1
+        k1 = np.where(m, 1.0, k1); k0 = np.where(m, 0.0, k0); k2 = np.where(m, 0.0, k2)
+        m = k2 > 1
+        k2 = np.where(m, 1.0, k2); k0 = np.where(m, 0.0, k0); k1 = np.where(m, 0.0, k1)
+        m = k0 < 0
+        s = k1 + k2
+        k1 = np.where(m, k1 / s, k1); k2 = np.where(m, k2 / s, k2); k0 = np.where(m, 0.0, k0)
+        m = k1 < 0
+        s = k0 + k2
+        k0 = np.where(m, k0 / s, k0); k2 = np.where(m, k2 / s, k2); k1 = np.where(m, 0.0, k1)
+        m = k2 < 0
+        s = k0 + k1
+        k0 = np.where(m, k0 / s, k0); k1 = np.where(m, k1 / s, k1); k2 = np.where(m, 0.0, k2)
+        if kinship_constraint:
+            k2 = 1 - k0 - k1
+            pihat = k1 / 2 + k2
+            m = pihat * pihat < k2
+            k0 = np.where(m, (1 - pihat) * (1 - pihat), k0)
+            k1 = np.where(m, 2 * pihat * (1 - pihat), k1)
+    np.fill_diagonal(k0, 0.0)
+    np.fill_diagonal(k1, 0.0)
+    return k0, k1
+
+
 def to_packed_upper(m):
     """Row-packed upper triangle: idx(r,c) = c + r(2N-r-1)/2, r <= c."""
     n = m.shape[0]

@@ -1,6 +1,6 @@
 """snprelate_b200 -- B200-native (sm_100a) implementation of SNPRelate's pairwise
 N x N relatedness-matrix path (snpgdsGRM / snpgdsPCA / snpgdsEIGMIX / snpgdsIBS /
-snpgdsIBSNum / snpgdsIBDKING / snpgdsIndivBeta).
+snpgdsIBSNum / snpgdsIBDMoM / snpgdsIBDKING / snpgdsIndivBeta).
 
 The product is ``libsnprel_b200.so`` (hand-written CUDA behind a C ABI, see
 ``include/snprel_b200.h``).  This package is the thin host layer that mirrors the
@@ -17,6 +17,7 @@ from .api import (  # noqa: F401
     snpgdsEIGMIX,
     snpgdsIBS,
     snpgdsIBSNum,
+    snpgdsIBDMoM,
     snpgdsIBDKING,
     snpgdsIndivBeta,
     snpgdsSNPRateFreq,
@@ -24,6 +25,6 @@ from .api import (  # noqa: F401
 
 __all__ = [
     "SNPRelError", "Context", "load_library", "library_path", "GenotypeData",
-    "snpgdsGRM", "snpgdsPCA", "snpgdsEIGMIX", "snpgdsIBS", "snpgdsIBSNum",
+    "snpgdsGRM", "snpgdsPCA", "snpgdsEIGMIX", "snpgdsIBS", "snpgdsIBSNum", "snpgdsIBDMoM",
     "snpgdsIBDKING", "snpgdsIndivBeta", "snpgdsSNPRateFreq",
 ]

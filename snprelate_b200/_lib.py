@@ -59,8 +59,12 @@ def load_library():
         "snprel_geno_copy_2b": [p, p, i64],
         "snprel_snp_ratefreq": [p, p, p, p],
         "snprel_select_snp_base": [p, i32, dbl, dbl, p, C.POINTER(i64)],
+        "snprel_select_snp_base_ex": [p, p, i32, dbl, dbl, p, C.POINTER(i64)],
         "snprel_ibs_num": [p, p, p, p],
         "snprel_ibs_ave": [p, p, i32],
+        "snprel_ibd_mom": [p, p, i32, i32, p, p, p],
+        "snprel_ibd_mom_sums": [p, p, p, p],
+        "snprel_ibd_mom_from_sums": [p, p, i32, i32, p, p],
         "snprel_king_robust": [p, p, p, p, i32],
         "snprel_king_robust_counts": [p, p],
         "snprel_king_homo": [p, p, p, i32],
@@ -104,8 +108,8 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "snprel_create", "snprel_destroy", "snprel_last_error", "snprel_version",
     "snprel_geno_begin", "snprel_geno_push_u8", "snprel_geno_push_2b", "snprel_geno_synth",
-    "snprel_geno_dim", "snprel_geno_copy_u8", "snprel_geno_copy_2b", "snprel_snp_ratefreq", "snprel_select_snp_base",
-    "snprel_ibs_num", "snprel_ibs_ave", "snprel_king_robust", "snprel_king_robust_counts",
+    "snprel_geno_dim", "snprel_geno_copy_u8", "snprel_geno_copy_2b", "snprel_snp_ratefreq", "snprel_select_snp_base", "snprel_select_snp_base_ex",
+    "snprel_ibs_num", "snprel_ibs_ave", "snprel_ibd_mom", "snprel_ibd_mom_sums", "snprel_ibd_mom_from_sums", "snprel_king_robust", "snprel_king_robust_counts",
     "snprel_king_homo", "snprel_indiv_beta", "snprel_indiv_beta_counts", "snprel_grm",
     "snprel_pca", "snprel_eigmix", "snprel_plan_local", "snprel_accumulate",
     "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced", "snprel_last_plan", "snprel_set_row_window", "snprel_window_count", "snprel_mem_info",
@@ -195,12 +199,17 @@ class Context:
         self._ck(self.lib.snprel_snp_ratefreq(self.h, _ptr(af), _ptr(maf), _ptr(mr)))
         return af, maf, mr
 
-    def select_snp_base(self, remove_mono=True, maf=-1.0, missrate=2.0):
+    def select_snp_base(self, remove_mono=True, maf=-1.0, missrate=2.0, allele_freq=None):
         _, m = self.geno_dim()
         sel = np.empty(m, dtype=np.uint8)
         nrm = C.c_int64()
-        self._ck(self.lib.snprel_select_snp_base(self.h, int(bool(remove_mono)), float(maf), float(missrate),
-                                                 _ptr(sel), C.byref(nrm)))
+        if allele_freq is None:
+            self._ck(self.lib.snprel_select_snp_base(self.h, int(bool(remove_mono)), float(maf), float(missrate),
+                                                     _ptr(sel), C.byref(nrm)))
+        else:
+            af = self._afreq_in(allele_freq)
+            self._ck(self.lib.snprel_select_snp_base_ex(self.h, _ptr(af), int(bool(remove_mono)), float(maf),
+                                                        float(missrate), _ptr(sel), C.byref(nrm)))
         return sel.astype(bool), nrm.value
 
     # ---- estimators ----
@@ -281,6 +290,36 @@ class Context:
         o = self._out(packed)
         self._ck(self.lib.snprel_ibs_ave(self.h, _ptr(o), int(packed)))
         return o
+
+    def _afreq_in(self, allele_freq):
+        if allele_freq is None:
+            return None
+        af = np.ascontiguousarray(allele_freq, dtype=np.float64)
+        if af.shape != (self.geno_dim()[1],):
+            raise SNPRelError("allele_freq must have one entry per SNP")
+        return af
+
+    def ibd_mom(self, allele_freq=None, kinship_constraint=False, packed=False):
+        """PLINK method of moments -> (k0, k1, afreq)."""
+        k0, k1 = self._out(packed), self._out(packed)
+        af = np.empty(self.geno_dim()[1], dtype=np.float64)
+        afin = self._afreq_in(allele_freq)
+        self._ck(self.lib.snprel_ibd_mom(self.h, _ptr(afin), int(bool(kinship_constraint)), int(packed),
+                                         _ptr(k0), _ptr(k1), _ptr(af)))
+        return k0, k1, af
+
+    def ibd_mom_sums(self, allele_freq=None):
+        sums = np.empty(6, dtype=np.float64)
+        af = np.empty(self.geno_dim()[1], dtype=np.float64)
+        self._ck(self.lib.snprel_ibd_mom_sums(self.h, _ptr(self._afreq_in(allele_freq)), _ptr(sums), _ptr(af)))
+        return sums, af
+
+    def ibd_mom_from_sums(self, sums, kinship_constraint=False, packed=False):
+        k0, k1 = self._out(packed), self._out(packed)
+        sums = np.ascontiguousarray(sums, dtype=np.float64)
+        self._ck(self.lib.snprel_ibd_mom_from_sums(self.h, _ptr(sums), int(bool(kinship_constraint)),
+                                                   int(packed), _ptr(k0), _ptr(k1)))
+        return k0, k1
 
     def king_robust(self, family_id=None, packed=False):
         a, b = self._out(packed), self._out(packed)

@@ -61,7 +61,7 @@ class GenotypeData:
 
 
 def _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, missing_rate,
-                num_thread, verbose, device=0, ctx=None):
+                num_thread, verbose, device=0, ctx=None, allele_freq=None):
     """.InitFile2 (R/Internal.R:166-484): select, load the workspace, QC-filter."""
     if not isinstance(gdsobj, GenotypeData):
         raise SNPRelError("'gdsobj' should be a GenotypeData object")
@@ -80,6 +80,18 @@ def _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, m
         sample_ids = gdsobj.sample_id[samp_mask]
     # SNPs (R/Internal.R:316-422)
     snp_mask = np.ones(gdsobj.n_snp, dtype=bool)
+    if allele_freq is not None:
+        allele_freq = np.asarray(allele_freq)
+        if allele_freq.ndim != 1 or not np.issubdtype(allele_freq.dtype, np.number):
+            raise SNPRelError("'allele.freq' should be a numeric vector or NULL.")
+        allele_freq = allele_freq.astype(np.float64)
+        if snp_id is not None:
+            if len(allele_freq) != len(snp_id):
+                raise SNPRelError("'length(allele.freq)' should be 'length(snp.id)'.")
+            # re-order to file order of the selected SNPs (R/Internal.R:355-356)
+            pos = {v: k for k, v in enumerate(np.asarray(snp_id).tolist())}
+        elif len(allele_freq) != gdsobj.n_snp:
+            raise SNPRelError("'length(allele.freq)' should be the number of SNPs.")
     if snp_id is not None:
         snp_id = np.asarray(snp_id)
         snp_mask = np.isin(gdsobj.snp_id, snp_id)
@@ -94,6 +106,11 @@ def _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, m
             snp_mask &= (gdsobj.chromosome == autosome_only)
     snp_idx = np.nonzero(snp_mask)[0]
     snp_ids = gdsobj.snp_id[snp_idx]
+    if allele_freq is not None:
+        if snp_id is not None:
+            allele_freq = allele_freq[[pos[v] for v in snp_ids.tolist()]]
+        else:
+            allele_freq = allele_freq[snp_idx]
 
     # gnrSetGenoSpace: stream blocks to the device
     ctx = ctx or Context(device)
@@ -107,15 +124,17 @@ def _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, m
     if remove_monosnp or math.isfinite(maf) or math.isfinite(missing_rate):
         t_maf = maf if math.isfinite(maf) else -1.0
         t_mr = missing_rate if math.isfinite(missing_rate) else 2.0
-        sel, nrm = ctx.select_snp_base(remove_monosnp, t_maf, t_mr)
+        sel, nrm = ctx.select_snp_base(remove_monosnp, t_maf, t_mr, allele_freq)
         snp_ids = snp_ids[sel]
+        if allele_freq is not None:
+            allele_freq = allele_freq[sel]
         if verbose:
             print(f"Excluding {nrm} SNP{'s' if nrm != 1 else ''} (monomorphic: {remove_monosnp}, "
                   f"MAF: {maf}, missing rate: {missing_rate})")
     n, m = ctx.geno_dim()
     if verbose:
         print(f"    # of samples: {n}\n    # of SNPs: {m}")
-    return dict(ctx=ctx, sample_id=sample_ids, snp_id=snp_ids, n_snp=m, n_samp=n)
+    return dict(ctx=ctx, sample_id=sample_ids, snp_id=snp_ids, n_snp=m, n_samp=n, allele_freq=allele_freq)
 
 
 def _newmat(n, packed_values):
@@ -204,6 +223,34 @@ def snpgdsIBS(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_mo
     if useMatrix:
         ibs = _newmat(ws["n_samp"], ibs)
     return {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "ibs": ibs}
+
+
+def snpgdsIBDMoM(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_monosnp=True,
+                 maf=float("nan"), missing_rate=0.01, allele_freq=None, kinship=False,
+                 kinship_constraint=False, num_thread=1, useMatrix=False, verbose=False, device=0):
+    """R/IBD.R:22-70 -> gnrIBD_PLINK (src/genIBS.cpp:558-639): PLINK method of moments."""
+    ws = _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, missing_rate,
+                     num_thread, verbose, device, allele_freq=allele_freq)
+    for name, v in (("kinship", kinship), ("kinship.constraint", kinship_constraint), ("useMatrix", useMatrix)):
+        if not isinstance(v, (bool, np.bool_)):
+            raise SNPRelError(f"'{name}' should be a logical value.")
+    with ws["ctx"] as ctx:
+        rows = ctx.auto_window_rows(12) if useMatrix else 0
+        if rows:
+            sums, afreq = ctx.ibd_mom_sums(ws["allele_freq"])
+            k0, k1 = ctx.packed_by_windows(
+                lambda: ctx.ibd_mom_from_sums(sums, kinship_constraint, packed=True), rows)
+        else:
+            k0, k1, afreq = ctx.ibd_mom(ws["allele_freq"], kinship_constraint, packed=bool(useMatrix))
+    afreq = afreq.copy()
+    afreq[afreq < 0] = np.nan
+    ans = {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "afreq": afreq, "k0": k0, "k1": k1}
+    if kinship:
+        ans["kinship"] = 0.5 * (1 - k0 - k1) + 0.25 * k1
+    if useMatrix:
+        for key in ("k0", "k1") + (("kinship",) if kinship else ()):
+            ans[key] = _newmat(ws["n_samp"], ans[key])
+    return ans
 
 
 def snpgdsIBSNum(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_monosnp=True,

@@ -299,6 +299,47 @@ __global__ void king_robust_kernel(const uint32_t *__restrict__ cnt,
     store_sym(okin, packed, n, i, j, v, win.pbase);
 }
 
+// IBD::Est_PLINK_Kinship (src/genIBD.cpp:341-383) per pair on the IBS counters; the diagonal is
+// k0 = k1 = 0 (src/genIBS.cpp:596,614).  e = {E00, E01, E02, E11, E12} (E22 = 1).
+struct MomTab { double e00, e01, e02, e11, e12; };
+
+__global__ void ibd_mom_kernel(const uint32_t *__restrict__ cnt, double *__restrict__ ok0,
+                               double *__restrict__ ok1, MomTab t, int constraint, int packed,
+                               int64_t n, int64_t npad, RowWin win) {
+    int64_t i = win.r0 + blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= n || j < i) return;
+    if (i == j) {
+        store_sym(ok0, packed, n, i, j, 0.0, win.pbase);
+        store_sym(ok1, packed, n, i, j, 0.0, win.pbase);
+        return;
+    }
+    int64_t plane = win.rows * npad, k = (i - win.r0) * npad + j;
+    uint32_t n0 = cnt[k], n2 = cnt[plane + k], nm = cnt[2 * plane + k];
+    uint32_t n1 = nm - n0 - n2;
+    double tot = (double)(int)nm;
+    double e00 = t.e00 * tot, e01 = t.e01 * tot, e11 = t.e11 * tot;
+    double e02 = t.e02 * tot, e12 = t.e12 * tot, e22 = 1.0 * tot;
+    double k0 = __ddiv_rn((double)n0, e00);
+    double k1 = __ddiv_rn(__dsub_rn((double)n1, __dmul_rn(k0, e01)), e11);
+    double k2 = __ddiv_rn(__dsub_rn(__dsub_rn((double)n2, __dmul_rn(k0, e02)), __dmul_rn(k1, e12)), e22);
+    if (k0 > 1) { k0 = 1; k1 = k2 = 0; }
+    if (k1 > 1) { k1 = 1; k0 = k2 = 0; }
+    if (k2 > 1) { k2 = 1; k0 = k1 = 0; }
+    if (k0 < 0) { double S = k1 + k2; k1 /= S; k2 /= S; k0 = 0; }
+    if (k1 < 0) { double S = k0 + k2; k0 /= S; k2 /= S; k1 = 0; }
+    if (k2 < 0) { double S = k0 + k1; k0 /= S; k1 /= S; k2 = 0; }
+    if (constraint) {
+        k2 = __dsub_rn(__dsub_rn(1.0, k0), k1);
+        double pihat = __dadd_rn(k1 / 2, k2);
+        if (__dmul_rn(pihat, pihat) < k2) {
+            k0 = __dmul_rn(1 - pihat, 1 - pihat);
+            k1 = __dmul_rn(__dmul_rn(2.0, pihat), 1 - pihat);
+        }
+    }
+    store_sym(ok0, packed, n, i, j, k0, win.pbase);
+    store_sym(ok1, packed, n, i, j, k1, win.pbase);
+}
+
 // copy counter planes to full symmetric int32 matrices (row = first sample)
 __global__ void counts_sym_kernel(const uint32_t *__restrict__ cnt, int32_t *__restrict__ out,
                                   int est, int nplanes_out, int64_t n, int64_t npad) {
@@ -454,6 +495,25 @@ void king_robust_finish(snprel_ctx *c, const int32_t *fam, double *ibs0, double 
     KERNEL_CHECK(c);
     d2h(c, ibs0, o.p, oc);
     d2h(c, kin, o.p + oc, oc);
+}
+
+// gnrIBD_PLINK (src/genIBS.cpp:558-639) from the IBS counters and the summed per-SNP terms
+void ibd_mom_finish(snprel_ctx *c, const double *sums, int constraint, double *k0, double *k1, int packed) {
+    if (!sums || !k0 || !k1) fail("snprel_ibd_mom: NULL argument");
+    need_packed_in_window(c, packed, "snprel_ibd_mom");
+    need_accum(c, SNPREL_EST_IBS);
+    int64_t n = c->n_samp;
+    check_grid_rows(n);
+    const double nv = sums[5];
+    MomTab t = {sums[0] / nv, sums[1] / nv, sums[2] / nv, sums[3] / nv, sums[4] / nv};
+    DevBuf<double> o;
+    size_t oc = win_out_count(c, packed);
+    o.alloc(2 * oc);
+    ibd_mom_kernel<<<win_grid(c), 128, 0, c->stream>>>(c->cnt.p, o.p, o.p + oc, t, constraint, packed, n,
+                                                        c->n_samp_pad, row_window(c));
+    KERNEL_CHECK(c);
+    d2h(c, k0, o.p, oc);
+    d2h(c, k1, o.p + oc, oc);
 }
 
 static void counts_finish(snprel_ctx *c, int est, int np, int32_t *out) {

@@ -127,7 +127,14 @@ int snprel_snp_ratefreq(snprel_ctx *c, double *af, double *maf, double *mr) {
 }
 int snprel_select_snp_base(snprel_ctx *c, int remove_mono, double maf, double missrate,
                            uint8_t *out_sel, int64_t *n_removed) {
-    API_BEGIN(c) select_snp_base(c, remove_mono, maf, missrate, out_sel, n_removed);
+    API_BEGIN(c) select_snp_base(c, nullptr, remove_mono, maf, missrate, out_sel, n_removed);
+    API_END(c)
+}
+int snprel_select_snp_base_ex(snprel_ctx *c, const double *afreq, int remove_mono, double maf, double missrate,
+                              uint8_t *out_sel, int64_t *n_removed) {
+    API_BEGIN(c)
+    if (!afreq) fail("snprel_select_snp_base_ex: NULL allele frequencies");
+    select_snp_base(c, afreq, remove_mono, maf, missrate, out_sel, n_removed);
     API_END(c)
 }
 
@@ -138,6 +145,23 @@ int snprel_ibs_num(snprel_ctx *c, int32_t *i0, int32_t *i1, int32_t *i2) {
 }
 int snprel_ibs_ave(snprel_ctx *c, double *out, int packed) {
     API_BEGIN(c) ibs_ave_finish(c, out, packed);
+    API_END(c)
+}
+int snprel_ibd_mom_sums(snprel_ctx *c, const double *afreq_in, double *sums6, double *afreq_out) {
+    API_BEGIN(c) ibd_mom_sums(c, afreq_in, sums6, afreq_out);
+    API_END(c)
+}
+int snprel_ibd_mom_from_sums(snprel_ctx *c, const double *sums6, int constraint, int packed, double *k0,
+                             double *k1) {
+    API_BEGIN(c) ibd_mom_finish(c, sums6, constraint, k0, k1, packed);
+    API_END(c)
+}
+int snprel_ibd_mom(snprel_ctx *c, const double *afreq_in, int constraint, int packed, double *k0, double *k1,
+                   double *afreq_out) {
+    API_BEGIN(c)
+    double sums[6];
+    ibd_mom_sums(c, afreq_in, sums, afreq_out);
+    ibd_mom_finish(c, sums, constraint, k0, k1, packed);
     API_END(c)
 }
 int snprel_king_robust(snprel_ctx *c, const int32_t *fam, double *ibs0, double *kin, int packed) {

@@ -206,7 +206,7 @@ void geno_copy_2b(snprel_ctx *c, uint8_t *out, int64_t row_bytes);
 void geno_pad_tail(snprel_ctx *c);
 void ensure_stats(snprel_ctx *c);
 void snp_ratefreq(snprel_ctx *c, double *af, double *maf, double *mr);
-void select_snp_base(snprel_ctx *c, int remove_mono, double maf, double missrate,
+void select_snp_base(snprel_ctx *c, const double *afreq, int remove_mono, double maf, double missrate,
                      uint8_t *out_sel, int64_t *n_removed);
 void ensure_planes(snprel_ctx *c);
 
@@ -214,6 +214,8 @@ void ensure_planes(snprel_ctx *c);
 void bitcount_accumulate(snprel_ctx *c, int estimator);
 void ibs_num_finish(snprel_ctx *c, int32_t *i0, int32_t *i1, int32_t *i2);
 void ibs_ave_finish(snprel_ctx *c, double *out, int packed);
+void ibd_mom_sums(snprel_ctx *c, const double *afreq_in, double *sums, double *afreq_out);
+void ibd_mom_finish(snprel_ctx *c, const double *sums, int constraint, double *k0, double *k1, int packed);
 void king_robust_finish(snprel_ctx *c, const int32_t *fam, double *ibs0, double *kin, int packed);
 void king_robust_counts_finish(snprel_ctx *c, int32_t *out5);
 void beta_counts_finish(snprel_ctx *c, int32_t *out2);

@@ -8,6 +8,7 @@
 // all-missing rows to a multiple of 128.  N*M/4 bytes -- a 10k x 1M data set is
 // 2.5 GB, 500k x 800k is 100 GB (fits one 180 GB B200).
 #include "common.cuh"
+#include <cmath>
 
 namespace snprel {
 
@@ -366,8 +367,67 @@ void snp_ratefreq(snprel_ctx *c, double *af, double *maf, double *mr) {
     }
 }
 
-// Select_SNP_Base (src/dGenGWAS.cpp:361-397)
-void select_snp_base(snprel_ctx *c, int remove_mono, double maf, double missrate,
+// IBD::Init_EPrIBD_IBS (src/genIBD.cpp:253-338): per-SNP expected P(IBS i | IBD j) terms summed
+// in SNP order (the reference's own summation order; an O(M) host loop over the device-computed
+// per-SNP counts).  sums = {a00, a01, a02, a11, a12, nValid}, not yet divided by nValid so that
+// SNP-sharded ranks can add them.  afreq_in != NULL: use those frequencies, no finite-sample
+// correction (src/genIBS.cpp:585-587; the AA/AB/BB counts are zero in that mode).
+void ibd_mom_sums(snprel_ctx *c, const double *afreq_in, double *sums, double *afreq_out) {
+    if (!sums) fail("snprel_ibd_mom_sums: NULL output");
+    std::vector<SnpStat> h = stats_to_host(c);
+    const double nan = __builtin_nan("");
+    double e00 = 0, e01 = 0, e02 = 0, e11 = 0, e12 = 0;
+    int64_t nvalid = 0;
+    for (int64_t l = 0; l < c->n_snp; l++) {
+        long AA = 0, AB = 0, BB = 0;
+        if (!afreq_in) {
+            AB = h[l].n1;
+            AA = (h[l].sum - h[l].n1) / 2;
+            BB = h[l].num - AA - AB;
+        }
+        long n = 2 * (AA + AB + BB);
+        double p = (n > 0) ? ((double)(2 * AA + AB) / n) : nan;
+        if (afreq_in) {
+            p = afreq_in[l];
+            if (std::isfinite(p) && (p < 0 || p > 1)) p = nan;
+        }
+        if (afreq_out) afreq_out[l] = p;
+        double q = 1 - p, Na = (double)n;
+        double x = (double)(2 * AA + AB), y = (double)(2 * BB + AB);
+        double a00, a01, a02, a11, a12;
+        if (!afreq_in) {
+            a00 = 2*p*p*q*q * ((x-1)/x * (y-1)/y * (Na/(Na-1)) * (Na/(Na-2)) * (Na/(Na-3)));
+            a01 = 4*p*p*p*q * ((x-1)/x * (x-2)/x * (Na/(Na-1)) * (Na/(Na-2)) * (Na/(Na-3))) +
+                  4*p*q*q*q * ((y-1)/y * (y-2)/y * (Na/(Na-1)) * (Na/(Na-2)) * (Na/(Na-3)));
+            a02 = q*q*q*q * ((y-1)/y * (y-2)/y * (y-3)/y * (Na/(Na-1)) * (Na/(Na-2)) * (Na/(Na-3))) +
+                  p*p*p*p * ((x-1)/x * (x-2)/x * (x-3)/x * (Na/(Na-1)) * (Na/(Na-2)) * (Na/(Na-3))) +
+                  4*p*p*q*q * ((x-1)/x * (y-1)/y * (Na/(Na-1)) * (Na/(Na-2)) * (Na/(Na-3)));
+            a11 = 2*p*p*q * ((x-1)/x * Na/(Na-1) * Na/(Na-2)) +
+                  2*p*q*q * ((y-1)/y * Na/(Na-1) * Na/(Na-2));
+            a12 = p*p*p * ((x-1)/x * (x-2)/x * Na/(Na-1) * Na/(Na-2)) +
+                  q*q*q * ((y-1)/y * (y-2)/y * Na/(Na-1) * Na/(Na-2)) +
+                  p*p*q * ((x-1)/x * Na/(Na-1) * Na/(Na-2)) +
+                  p*q*q * ((y-1)/y * Na/(Na-1) * Na/(Na-2));
+        } else {
+            a00 = 2*p*p*q*q;
+            a01 = 4*p*p*p*q + 4*p*q*q*q;
+            a02 = q*q*q*q + p*p*p*p + 4*p*p*q*q;
+            a11 = 2*p*p*q + 2*p*q*q;
+            a12 = p*p*p + q*q*q + p*p*q + p*q*q;
+        }
+        if (std::isfinite(a00) && std::isfinite(a01) && std::isfinite(a02) && std::isfinite(a11) &&
+            std::isfinite(a12)) {
+            e00 += a00; e01 += a01; e02 += a02; e11 += a11; e12 += a12;
+            nvalid++;
+        }
+    }
+    sums[0] = e00; sums[1] = e01; sums[2] = e02; sums[3] = e11; sums[4] = e12;
+    sums[5] = (double)nvalid;
+}
+
+// Select_SNP_Base (src/dGenGWAS.cpp:361-397); with afreq != NULL Select_SNP_Base_Ex
+// (src/dGenGWAS.cpp:399-470): MAF from the caller's frequencies, non-finite = dropped.
+void select_snp_base(snprel_ctx *c, const double *afreq, int remove_mono, double maf, double missrate,
                      uint8_t *out_sel, int64_t *n_removed) {
     std::vector<SnpStat> h = stats_to_host(c);
     std::vector<int64_t> keep;
@@ -375,8 +435,8 @@ void select_snp_base(snprel_ctx *c, int remove_mono, double maf, double missrate
     for (int64_t l = 0; l < c->n_snp; l++) {
         int num = h[l].num, sum = h[l].sum;
         bool flag = false;
-        if (num > 0) {
-            double f = (double)sum / (2 * num);
+        if (afreq ? std::isfinite(afreq[l]) : num > 0) {
+            double f = afreq ? afreq[l] : (double)sum / (2 * num);
             double m = f < 1 - f ? f : 1 - f;
             double r = 1 - ((double)num) / (double)c->n_samp;
             flag = true;

@@ -6,7 +6,7 @@
 //   gnrPCA (exact)      src/genPCA.cpp:1355-1452      gnrIBSNum          src/genIBS.cpp:500-550
 //   gnrEigMix           src/genEIGMIX.cpp:656-735     gnrIBD_KING_Robust src/genKING.cpp:576-679
 //   gnrGRM_avg_val      src/genPCA.cpp:1608           gnrIBD_KING_Homo   src/genKING.cpp:493-570
-//                                                     gnrIBD_Beta        src/genBeta.cpp:361-460
+//   gnrIBD_PLINK        src/genIBS.cpp:558-639        gnrIBD_Beta        src/genBeta.cpp:361-460
 // inside SNPRelate.so, keeping the workspace layer (gnrSetGenoSpace / gnrSelSNP_Base,
 // src/SNPRelate.cpp:76-214) and the R code untouched: every routine streams the SELECTED
 // genotypes through CdBaseWorkSpace::snpRead (src/dGenGWAS.h:94) into the device workspace and
@@ -140,6 +140,26 @@ COREARRAY_DLL_EXPORT SEXP gnrIBSAve(SEXP NumThread, SEXP useMatrix, SEXP Verbose
         rv_ans = PROTECT(sym_result(n, packed));
         c.ck(snprel_ibs_ave(c.h, REAL(rv_ans), packed));
         UNPROTECT(1);
+    COREARRAY_CATCH
+}
+
+COREARRAY_DLL_EXPORT SEXP gnrIBD_PLINK(SEXP NumThread, SEXP AlleleFreq, SEXP UseSpecificAFreq,
+                                       SEXP KinshipConstrict, SEXP useMatrix, SEXP Verbose) {
+    COREARRAY_TRY
+        Ctx c;
+        load_workspace(c);
+        const size_t n = MCWorkingGeno.Space().SampleNum();
+        const bool packed = Rf_asLogical(useMatrix) == TRUE;
+        SEXP k0 = PROTECT(sym_result(n, packed));
+        SEXP k1 = PROTECT(sym_result(n, packed));
+        SEXP afreq = PROTECT(NEW_NUMERIC(MCWorkingGeno.Space().SNPNum()));
+        c.ck(snprel_ibd_mom(c.h, Rf_asLogical(UseSpecificAFreq) == TRUE ? REAL(AlleleFreq) : NULL,
+                            Rf_asLogical(KinshipConstrict) == TRUE, packed, REAL(k0), REAL(k1), REAL(afreq)));
+        PROTECT(rv_ans = NEW_LIST(3));
+        SET_ELEMENT(rv_ans, 0, k0);
+        SET_ELEMENT(rv_ans, 1, k1);
+        SET_ELEMENT(rv_ans, 2, afreq);
+        UNPROTECT(4);
     COREARRAY_CATCH
 }
 

@@ -99,3 +99,18 @@ def accumulate_sharded(ctx, est, bayesian=False, group=None, device=None):
         torch.cuda.synchronize(device)
     ctx.mark_reduced()
     return plan
+
+
+def ibd_mom_sharded(ctx, allele_freq=None, kinship_constraint=False, packed=False, group=None, device=None):
+    """PLINK method of moments over SNP-sharded ranks: the IBS counters and the six
+    per-SNP expectation sums (src/genIBD.cpp:253-338) are both plain sums over SNPs.
+    `allele_freq` is this rank's slice.  Returns (k0, k1, afreq of the local shard)."""
+    import torch
+    import torch.distributed as dist
+    from ._lib import EST_IBS
+    accumulate_sharded(ctx, EST_IBS, group=group, device=device)
+    sums, afreq = ctx.ibd_mom_sums(allele_freq)
+    t = torch.from_numpy(sums).to("cpu" if device is None else device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    k0, k1 = ctx.ibd_mom_from_sums(t.cpu().numpy(), kinship_constraint, packed)
+    return k0, k1, afreq

@@ -50,6 +50,9 @@ def _worker(rank, world, port, q):
     torch.cuda.synchronize()
     ctx.mark_reduced()
     out["ibs"] = np.stack(ctx.ibs_num())
+    ctx.geno_begin(n, hi - lo)
+    ctx.geno_push_u8(g[lo:hi])
+    out["mom"] = D.ibd_mom_sharded(ctx, kinship_constraint=True, device=dev)[:2]
     q.put((rank, out))
     tdist.destroy_process_group()
 
@@ -77,6 +80,9 @@ def test_two_rank_snp_sharding_matches_single_gpu():
             err = np.max(np.abs(res[rank][k] - r) / np.maximum(np.abs(r), 1))
             assert err < 1e-10, (rank, k, err)
         assert np.array_equal(res[rank]["ibs"], O.ibs_counts(g))
+        e, _ = O.ibd_mom_tables(g)
+        r0, r1 = O.ibd_mom(O.ibs_counts(g), e, True)
+        assert np.max(np.abs(res[rank]["mom"][0] - r0)) < 1e-13 and np.max(np.abs(res[rank]["mom"][1] - r1)) < 1e-13
     for k in ref:
         assert np.array_equal(res[0][k], res[1][k])
 

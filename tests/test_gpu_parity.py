@@ -48,6 +48,54 @@ def test_ibs_golden(gds, hapmap, goldens):          # test_rel.R:103-129
     assert np.array_equal(rp["ibs"]["x"], O.to_packed_upper(r["ibs"]))
 
 
+def test_plink_mom_golden(gds, hapmap, goldens):    # test_rel.R:197-227
+    samp = hapmap["sample_id"][:90]
+    r = S.snpgdsIBDMoM(gds, sample_id=samp, missing_rate=float("nan"), kinship=True)
+    assert np.array_equal(r["afreq"], goldens["mom_afreq"])
+    assert np.max(np.abs(r["k0"] - goldens["mom_k0"])) < 1e-14
+    assert np.max(np.abs(r["k1"] - goldens["mom_k1"])) < 1e-14
+    assert np.array_equal(r["kinship"], 0.5 * (1 - r["k0"] - r["k1"]) + 0.25 * r["k1"])
+    rp = S.snpgdsIBDMoM(gds, sample_id=samp, missing_rate=float("nan"), useMatrix=True)
+    assert np.array_equal(rp["k0"]["x"], O.to_packed_upper(r["k0"]))
+    assert np.array_equal(rp["k1"]["x"], O.to_packed_upper(r["k1"]))
+
+
+def test_plink_mom_vs_oracle(ctx, gds, hapmap):
+    """Counts-derived and caller-supplied allele frequencies, kinship constraint, row windows."""
+    g = O.synth_geno(300, 2500, seed=23, miss_rate=0.04, maf_lo=0.01)
+    load(ctx, g)
+    cnt = O.ibs_counts(g)
+    _, af0 = O.ibd_mom_tables(g)
+    user = af0.copy()
+    user[5] = np.nan
+    user[11] = -0.25
+    for afin in (None, user):
+        for kc in (False, True):
+            k0, k1, af = ctx.ibd_mom(afin, kc)
+            e, raf = O.ibd_mom_tables(g, afin)
+            r0, r1 = O.ibd_mom(cnt, e, kc)
+            assert np.array_equal(af, raf, equal_nan=True)
+            assert np.nanmax(np.abs(k0 - r0)) < 1e-13 and np.nanmax(np.abs(k1 - r1)) < 1e-13
+            assert np.array_equal(np.isnan(k0), np.isnan(r0))
+    sums, _ = ctx.ibd_mom_sums()
+    full = ctx.ibd_mom_from_sums(sums, True, packed=True)
+    win = ctx.packed_by_windows(lambda: ctx.ibd_mom_from_sums(sums, True, packed=True), 256)
+    assert np.array_equal(win[0], full[0]) and np.array_equal(win[1], full[1])
+    # allele.freq through the R-level wrapper: selection uses the supplied frequencies
+    samp = hapmap["sample_id"][:60]
+    base = S.snpgdsIBDMoM(gds, sample_id=samp, missing_rate=float("nan"))
+    af_all = np.full(gds.n_snp, np.nan)
+    af_all[np.isin(gds.snp_id, base["snp.id"])] = base["afreq"]
+    r = S.snpgdsIBDMoM(gds, sample_id=samp, missing_rate=float("nan"), allele_freq=af_all)
+    assert np.array_equal(r["snp.id"], base["snp.id"]) and np.array_equal(r["afreq"], base["afreq"])
+    gsel, _ = hapmap_subset(hapmap, 60)
+    e, _ = O.ibd_mom_tables(gsel, base["afreq"])
+    r0, r1 = O.ibd_mom(O.ibs_counts(gsel), e)
+    assert np.max(np.abs(r["k0"] - r0)) < 1e-13 and np.max(np.abs(r["k1"] - r1)) < 1e-13
+    with pytest.raises(S.SNPRelError, match="allele.freq"):
+        S.snpgdsIBDMoM(gds, sample_id=samp, allele_freq=np.zeros(5))
+
+
 def test_pca_golden(gds, hapmap, goldens):          # test_rel.R:133-195
     samp = hapmap["sample_id"][:90]
     r = S.snpgdsPCA(gds, sample_id=samp, missing_rate=float("nan"), need_genmat=True, eigen_cnt=8)

@@ -25,6 +25,15 @@ def test_ibs_golden(hapmap, goldens):
     assert np.max(np.abs(O.ibs_ave(c) - goldens["ibs"])) == 0.0
 
 
+def test_plink_mom_golden(hapmap, goldens):          # test_rel.R:197-227
+    g, _ = hapmap_subset(hapmap, 90)
+    e, af = O.ibd_mom_tables(g)
+    k0, k1 = O.ibd_mom(O.ibs_counts(g), e)
+    assert np.array_equal(af, goldens["mom_afreq"])
+    assert np.max(np.abs(k0 - goldens["mom_k0"])) < 1e-14
+    assert np.max(np.abs(k1 - goldens["mom_k1"])) < 1e-14
+
+
 def test_pca_genmat_golden(hapmap, goldens):
     g, _ = hapmap_subset(hapmap, 90)
     genmat, _, _ = O.pca_genmat(g)

@@ -42,6 +42,24 @@ def test_integer_estimators(data):
         assert np.max(np.abs(w.indiv_beta(2, inb) - O.indiv_beta(O.beta_counts(data), inb)[0])) < 1e-12
 
 
+def test_plink_mom(data):
+    """gnrIBD_PLINK with counts-derived and caller-supplied frequencies, with and
+    without the kinship constraint (src/genIBS.cpp:558-639, src/genIBD.cpp:253-383)."""
+    w = R.RefWorkspace(data)
+    cnt = O.ibs_counts(data)
+    _, af0 = O.ibd_mom_tables(data)
+    user = af0.copy()
+    user[3] = np.nan
+    user[7] = 1.5
+    for afin in (None, user):
+        for kc in (False, True):
+            k0, k1, af = w.ibd_mom(2, afin, kc)
+            e, raf = O.ibd_mom_tables(data, afin)
+            r0, r1 = O.ibd_mom(cnt, e, kc)
+            assert np.array_equal(np.isnan(af), np.isnan(raf)) and np.nanmax(np.abs(af - raf)) == 0
+            assert np.nanmax(np.abs(k0 - r0)) < 1e-13 and np.nanmax(np.abs(k1 - r1)) < 1e-13
+
+
 def test_pca_eigmix_and_selection(data):
     w = R.RefWorkspace(data)
     r = w.pca(2, False, 6)
@@ -64,3 +82,6 @@ def test_reference_reproduces_its_own_goldens(hapmap, goldens):
     assert np.max(np.abs(w.pca(2)["genmat"] - goldens["pca_genmat"])) < 1e-12
     assert np.max(np.abs(w.eigmix(2, True)[0] - goldens["eigmix_ibd"])) < 1e-12
     assert np.max(np.abs(w.indiv_beta(2, True) - goldens["beta"])) < 1e-12
+    k0, k1, af = w.ibd_mom(2)
+    assert np.max(np.abs(k0 - goldens["mom_k0"])) < 1e-14 and np.max(np.abs(k1 - goldens["mom_k1"])) < 1e-14
+    assert np.array_equal(af, goldens["mom_afreq"])
