@@ -495,6 +495,28 @@ def merge_grm(grms, weights):
     return sum(wi * g for wi, g in zip(w, grms))
 
 
+def merge_grm_indivbeta(grms, avg_vals, weights):
+    """gnrGRMMerge, ":method = IndivBeta" branch (src/genPCA.cpp:1737-1822): undo each
+    file's min-based normalisation through its off-diagonal mean M_b and stored
+    avg_val, average, then re-normalise against the new minimum.
+    Returns (grm, grm_avg_value)."""
+    n = grms[0].shape[0]
+    off = ~np.eye(n, dtype=bool)
+    acc = np.zeros((n, n))
+    for g, av, w in zip(grms, avg_vals, weights):
+        mb = g[off].sum() / (float(n) * (n - 1)) * 0.5
+        inv = 1 / (1 - mb)
+        m = (g * 0.5 - mb) * inv * (1 - av) + av
+        d = (np.diag(g) - 1 - mb) * inv * (1 - av) + av
+        m[np.arange(n), np.arange(n)] = d
+        acc += m * w
+    avg = acc[off].sum() / (float(n) * (n - 1))
+    mn = acc.min()
+    out = (acc - mn) * (2 / (1 - mn))
+    out[np.arange(n), np.arange(n)] = np.diag(out) * 0.5 + 1
+    return out, avg
+
+
 # ---------------------------------------------------------------------------
 # Synthetic genotypes (SURVEY.md section 8d): counter-based, any shard is
 # reproducible without communication.  The CUDA generator uses the same mixer.

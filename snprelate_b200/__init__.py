@@ -18,6 +18,7 @@ from .api import (  # noqa: F401
     snpgdsIBS,
     snpgdsIBSNum,
     snpgdsIBDMoM,
+    snpgdsMergeGRM,
     snpgdsIBDKING,
     snpgdsIndivBeta,
     snpgdsSNPRateFreq,
@@ -25,6 +26,6 @@ from .api import (  # noqa: F401
 
 __all__ = [
     "SNPRelError", "Context", "load_library", "library_path", "GenotypeData",
-    "snpgdsGRM", "snpgdsPCA", "snpgdsEIGMIX", "snpgdsIBS", "snpgdsIBSNum", "snpgdsIBDMoM",
+    "snpgdsGRM", "snpgdsPCA", "snpgdsEIGMIX", "snpgdsIBS", "snpgdsIBSNum", "snpgdsIBDMoM", "snpgdsMergeGRM",
     "snpgdsIBDKING", "snpgdsIndivBeta", "snpgdsSNPRateFreq",
 ]

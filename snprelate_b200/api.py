@@ -145,8 +145,11 @@ def _newmat(n, packed_values):
 
 def snpgdsGRM(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_monosnp=True,
               maf=float("nan"), missing_rate=0.01,
-              method="GCTA", num_thread=1, useMatrix=False, with_id=True, verbose=False, device=0):
-    """R/IBD.R:543-615 -> gnrGRM (src/genPCA.cpp:1614-1717)."""
+              method="GCTA", num_thread=1, useMatrix=False, out_fn=None, out_prec="double",
+              with_id=True, verbose=False, device=0, window_rows=None):
+    """R/IBD.R:543-615 -> gnrGRM (src/genPCA.cpp:1614-1717).  With out_fn the matrix is
+    streamed to a SNPRELATE_OUTPUT container (grmfile.py; grm_save_to_gds,
+    src/genPCA.cpp:1571-1584) band by band and nothing is returned."""
     methods = ("GCTA", "Eigenstrat", "EIGMIX", "Weighted", "Corr", "IndivBeta")
     if method not in methods:
         raise SNPRelError("'arg' should be one of " + ", ".join(f'"{m}"' for m in methods))
@@ -155,8 +158,29 @@ def snpgdsGRM(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_mo
         method = "EIGMIX"
     ws = _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, missing_rate,
                      num_thread, verbose, device)
+    windowed = method in ("GCTA", "EIGMIX", "Eigenstrat")
+    if out_fn is not None:
+        if not isinstance(out_fn, str):
+            raise SNPRelError("'out.fn' should be a file name")
+        from .grmfile import GrmWriter
+        writer = GrmWriter(out_fn, ["snpgdsGRM", f":method = {method}"], ws["sample_id"], ws["snp_id"], out_prec)
+        with ws["ctx"] as ctx:
+            rows = window_rows or (ctx.auto_window_rows(16) if windowed else 0)
+            avg = None
+            if rows and windowed:
+                try:
+                    for r0, h in ctx.windows(rows):
+                        ctx.set_row_window(r0, h)
+                        writer.write_band(r0, ctx.grm(method, packed=True)[0])
+                finally:
+                    ctx.set_row_window(0, 0)
+            else:
+                grm, avg = ctx.grm(method, packed=False)
+                writer.write_full(grm)
+        writer.close(avg if method == "IndivBeta" else None)
+        return None
     with ws["ctx"] as ctx:
-        rows = ctx.auto_window_rows(16) if (useMatrix and method in ("GCTA", "EIGMIX", "Eigenstrat")) else 0
+        rows = (window_rows or ctx.auto_window_rows(16)) if (useMatrix and windowed) else 0
         if rows:      # N^2 int64 planes do not fit: walk row windows, packed slices concatenated
             grm, avg = ctx.packed_by_windows(lambda: ctx.grm(method, packed=True)[0], rows), 0.0
         else:
@@ -169,6 +193,13 @@ def snpgdsGRM(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_mo
     if method == "IndivBeta":
         rv["avg_val"] = avg           # R/IBD.R:605-606
     return rv
+
+
+def snpgdsMergeGRM(filelist, out_fn=None, out_prec="double", weight=None, verbose=False):
+    """R/IBD.R:624-748 -> gnrGRMMerge (src/genPCA.cpp:1721-1857) over the containers written
+    by snpgdsGRM(out_fn=...)."""
+    from .grmfile import merge_grm_files
+    return merge_grm_files(filelist, out_fn, out_prec, weight, verbose)
 
 
 def snpgdsPCA(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_monosnp=True,

@@ -156,6 +156,34 @@ def test_grm_merge_identity(gds, hapmap):           # test_GRM.R:15-49
     assert relerr(merged, full) < TOL
 
 
+def test_grm_files_merge(gds, hapmap, tmp_path):     # test_GRM.R:15-90 (GCTA and IndivBeta)
+    """snpgdsGRM(out.fn=) streams the matrix to a SNPRELATE_OUTPUT container (in row bands for
+    the windowed estimators) and snpgdsMergeGRM of three SNP subsets reproduces the GRM of
+    the union."""
+    from snprelate_b200.grmfile import GrmFile
+    _, idx = hapmap_subset(hapmap, 279, missing_rate=0.0)
+    ids = hapmap["snp_id"][idx]
+    parts = [ids[:1000], ids[1000:3000], ids[3000:]]
+    for method in ("GCTA", "IndivBeta"):
+        names = [str(tmp_path / f"{method}{k}.grm") for k in range(3)]
+        for nm, p in zip(names, parts):
+            assert S.snpgdsGRM(gds, snp_id=p, method=method, out_fn=nm, window_rows=256) is None
+        out = str(tmp_path / f"{method}.grm")
+        S.snpgdsMergeGRM(names, out)
+        full = S.snpgdsGRM(gds, snp_id=ids, method=method)
+        f = GrmFile(out)
+        assert relerr(np.array(f.grm), full["grm"]) < TOL, method
+        assert np.array_equal(f.snp_id, ids) and np.array_equal(f.sample_id, hapmap["sample_id"])
+        one = GrmFile(names[0])
+        direct = S.snpgdsGRM(gds, snp_id=parts[0], method=method)
+        assert np.array_equal(np.array(one.grm), direct["grm"])      # band writes == direct matrix
+        if method == "IndivBeta":
+            assert one.avg_val == direct["avg_val"]
+            assert abs(f.avg_val - full["avg_val"]) < 1e-12
+    S.snpgdsGRM(gds, snp_id=parts[0], method="GCTA", out_fn=str(tmp_path / "s.grm"), out_prec="single")
+    assert GrmFile(str(tmp_path / "s.grm")).grm.dtype == np.float32
+
+
 # ---------------------------------------------------------------- synthetic vs oracle
 
 @pytest.mark.parametrize("n,m,miss", [(4, 1, 0.0), (17, 33, 0.1), (130, 129, 0.0), (257, 1000, 0.02),
