@@ -223,19 +223,32 @@ def run_ours(args):
     host_out = torch.empty((N_SAMP, N_SAMP), dtype=torch.float64, pin_memory=True)
     e2e_steps = max(1, min(args.steps, 3))
 
+    e2e_parts = {"geno_begin": 0.0, "push_2b": 0.0, "accumulate_allreduce": 0.0, "pca_finish_d2h": 0.0}
+    hg, ho = host_geno.numpy(), host_out.numpy()
+
     def e2e_step():
+        ta = time.perf_counter()
         ctx.geno_begin(N_SAMP, N_SNP)
-        ctx.geno_push_2b(host_geno.numpy())
+        tb = time.perf_counter()
+        ctx.geno_push_2b(hg)
+        tc = time.perf_counter()
         if world > 1:
             D.accumulate_sharded(ctx, est, device=dev)
-        ctx.pca(genmat_only=True, genmat_out=host_out.numpy())
+        td = time.perf_counter()
+        ctx.pca(genmat_only=True, genmat_out=ho)
+        te = time.perf_counter()
+        for k, v in zip(e2e_parts, (tb - ta, tc - tb, td - tc, te - td)):
+            e2e_parts[k] += v * 1e3
     e2e_step()
+    for k in e2e_parts:
+        e2e_parts[k] = 0.0
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_parts = {k: round(v / e2e_steps, 2) for k, v in e2e_parts.items()}
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
@@ -296,7 +309,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_geno.numel()) * world,
                 "d2h_bytes_per_step": int(host_out.numel()) * 8,
                 "call": "snprel_geno_begin + snprel_geno_push_2b (pinned host 2-bit rows) + snprel_pca (genmat to host)",
-                "ms_per_step": e2e_s * 1e3},
+                "ms_per_step": e2e_s * 1e3, "ms_parts": e2e_parts},
         "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
         "roofline": roofline, "cpu_baseline": cpu,
         "clocks": sampler.summary() if sampler else None,

@@ -350,12 +350,20 @@ class Context:
         self._ck(self.lib.snprel_indiv_beta_counts(self.h, _ptr(o)))
         return o
 
-    def grm(self, method="GCTA", packed=False):
+    def grm(self, method="GCTA", packed=False, out=None):
+        """`out`: caller buffer (e.g. pinned host memory) of at least the result's size."""
         if method not in GRM_METHODS:
             raise SNPRelError("Invalid 'method'!")
         if method == "Corr":
             packed = False
-        o = self._out(packed)
+        if out is None:
+            o = self._out(packed)
+        else:
+            n, _ = self.geno_dim()
+            need = self.window_count() if getattr(self, "_win", False) else (n * (n + 1) // 2 if packed else n * n)
+            if out.dtype != np.float64 or not out.flags.c_contiguous or out.size < need:
+                raise SNPRelError("grm: 'out' must be a C-contiguous float64 buffer of the result's size")
+            o = out.reshape(-1)[:need] if (packed or getattr(self, "_win", False)) else out.reshape(-1)[:need].reshape(n, n)
         avg = C.c_double()
         self._ck(self.lib.snprel_grm(self.h, GRM_METHODS[method], _ptr(o), int(packed), C.byref(avg)))
         return o, avg.value

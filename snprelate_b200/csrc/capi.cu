@@ -277,10 +277,7 @@ int snprel_last_step_ms(snprel_ctx *c, double *ms) {
 }
 int snprel_invalidate(snprel_ctx *c) {
     API_BEGIN(c)
-    c->stat_valid = false;
-    c->planes_valid = false;
-    c->accum_est = -1;
-    c->accum_reduced = false;
+    drop_derived(c);
     API_END(c)
 }
 int snprel_reduce_buffer_count(snprel_ctx *c) { return c ? (int)c->reduce_list.size() : 0; }
@@ -296,6 +293,8 @@ int snprel_mark_reduced(snprel_ctx *c) {
     API_BEGIN(c)
     if (c->accum_est < 0) fail("snprel_mark_reduced: nothing accumulated");
     c->accum_reduced = true;
+    // the per-sample vectors and scalars were summed in place together with the planes
+    if (c->prep_cache.version == c->geno_version) c->prep_cache.reduced = true;
     API_END(c)
 }
 
@@ -340,8 +339,7 @@ int snprel_time_accumulate(snprel_ctx *c, int est, int reps, double *ms) {
     double total = 0;
     for (int r = 0; r < reps; r++) {
         // everything derived from the resident 2-bit matrix is recomputed inside the timed region
-        c->stat_valid = false;
-        c->planes_valid = false;
+        drop_derived(c);
         snprel_plan plan{};
         plan.frac_bits = -1;
         plan.frac_bits_w = -1;

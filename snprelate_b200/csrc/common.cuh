@@ -161,6 +161,21 @@ struct snprel_ctx {
     std::vector<int> host_cnt;
     std::vector<int2> host_tiles;
 
+    // window-invariant products of the covariance path, kept across row windows (tiled N x N
+    // output: every window re-uses the plan statistics, digit tables and per-sample vectors).
+    // geno_version changes whenever the resident 2-bit matrix (or anything derived) is dropped.
+    uint64_t geno_version = 1;
+    struct PlanCache {
+        uint64_t version = 0;
+        int est = -1, bayesian = 0;
+        snprel_plan stats{};
+    } plan_cache;
+    struct PrepCache {
+        uint64_t version = 0;
+        int est = -1, bayesian = 0, f = 0, fw = 0, fd = 0, nU = 0, nW = 0, nD = 0, nD2 = 0;
+        bool reduced = false;   // the per-sample vectors / scalars already hold the all-reduced sums
+    } prep_cache;
+
     // hot-kernel bookkeeping for bench.py
     double hot_ms = 0;
     int64_t hot_launches = 0;
@@ -172,6 +187,15 @@ struct snprel_ctx {
 namespace snprel {
 
 inline void count_launch(snprel_ctx *c, int64_t n = 1) { c->launches += n; }
+
+// everything derived from the resident 2-bit matrix is stale
+inline void drop_derived(snprel_ctx *c) {
+    c->stat_valid = false;
+    c->planes_valid = false;
+    c->accum_est = -1;
+    c->accum_reduced = false;
+    c->geno_version++;
+}
 
 inline RowWin row_window(const snprel_ctx *c) {
     RowWin w;

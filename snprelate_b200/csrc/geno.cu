@@ -199,10 +199,7 @@ void geno_begin(snprel_ctx *c, int64_t n_samp, int64_t cap) {
     c->geno2b.release();
     c->geno2b.alloc((size_t)c->snp_cap * c->row_bytes);
     c->stat.alloc(c->snp_cap);
-    c->stat_valid = false;
-    c->planes_valid = false;
-    c->accum_est = -1;
-    c->accum_reduced = false;
+    drop_derived(c);
 }
 
 static void need_room(snprel_ctx *c, int64_t cnt, const char *who) {
@@ -213,12 +210,7 @@ static void need_room(snprel_ctx *c, int64_t cnt, const char *who) {
              (long long)cnt, (long long)c->snp_cap);
 }
 
-static void invalidate(snprel_ctx *c) {
-    c->stat_valid = false;
-    c->planes_valid = false;
-    c->accum_est = -1;
-    c->accum_reduced = false;
-}
+static void invalidate(snprel_ctx *c) { drop_derived(c); }
 
 void geno_push_u8(snprel_ctx *c, const uint8_t *host, int64_t cnt) {
     need_room(c, cnt, "snprel_geno_push_u8");

@@ -350,25 +350,47 @@ static int digits_for(double max_abs, int frac_bits) {
          max_abs, frac_bits);
 }
 
+// scr_cnt[2][npad]: this rank's per-sample genotype sums and missing counts
+static void sample_counts(snprel_ctx *c) {
+    const int64_t npad = c->n_samp_pad;
+    c->scr_cnt.alloc((size_t)2 * npad);
+    c->scr_cnt.zero(c->stream);
+    if (c->n_snp > 0) {
+        dim3 grid((unsigned)((c->row_bytes + 127) / 128), (unsigned)((c->n_snp + SC_SNPS - 1) / SC_SNPS));
+        sample_count_kernel<<<grid, 128, 0, c->stream>>>(c->geno2b.p, c->n_snp, c->row_bytes, npad, c->scr_cnt.p);
+        KERNEL_CHECK(c);
+    }
+}
+
 void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
     if (!plan) fail("snprel_plan_local: NULL plan");
+    {   // same genotypes, same estimator: the statistics do not depend on the row window
+        const snprel_ctx::PlanCache &pc = c->plan_cache;
+        if (pc.version == c->geno_version && pc.est == est && pc.bayesian == plan->bayesian) {
+            const snprel_plan &s = pc.stats;
+            plan->max_abs = s.max_abs;
+            plan->max_abs_w = s.max_abs_w;
+            plan->sum_bound = s.sum_bound;
+            plan->total_missing = s.total_missing;
+            plan->scale = s.scale;
+            plan->err_weight = s.err_weight;
+            plan->max_missing = s.max_missing;
+            plan->n_snp = s.n_snp;
+            return;
+        }
+    }
     ensure_stats(c);
     const int64_t npad = c->n_samp_pad;
     DevBuf<double> &out = c->scr_plan;
     out.alloc(5);
     out.zero(c->stream);
-    c->scr_cnt.alloc((size_t)2 * npad);
-    c->scr_cnt.zero(c->stream);
     if (c->n_snp > 0) {
         int blocks = (int)std::min<int64_t>((c->n_snp + 255) / 256, 1024);
         plan_kernel<<<blocks, 256, 0, c->stream>>>(c->stat.p, c->n_snp, c->n_samp, est,
                                                    plan->bayesian, out.p);
         KERNEL_CHECK(c);
-        dim3 grid((unsigned)((c->row_bytes + 127) / 128), (unsigned)((c->n_snp + SC_SNPS - 1) / SC_SNPS));
-        sample_count_kernel<<<grid, 128, 0, c->stream>>>(c->geno2b.p, c->n_snp, c->row_bytes, npad,
-                                                         c->scr_cnt.p);
-        KERNEL_CHECK(c);
     }
+    sample_counts(c);
     double h[5];
     c->host_cnt.resize((size_t)2 * npad);
     CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
@@ -391,6 +413,10 @@ void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
     plan->err_weight = (est == SNPREL_EST_KING_HOMO) ? 0.0 : (double)ew;
     plan->max_missing = mm;
     plan->n_snp = c->n_snp;
+    c->plan_cache.version = c->geno_version;
+    c->plan_cache.est = est;
+    c->plan_cache.bayesian = plan->bayesian;
+    c->plan_cache.stats = *plan;
 }
 
 // Choose the fixed-point formats from the (global) plan statistics.
@@ -492,48 +518,71 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     const int npass = nU + nW + nD + nD2;
     const int64_t cap = c->snp_cap, npad = c->n_samp_pad;
 
+    // Digit tables, per-sample vectors and global scalars depend on the genotypes and the
+    // fixed-point format only, not on the row window: a tiled N x N run builds them once.
+    snprel_ctx::PrepCache &pc = c->prep_cache;
+    const bool prep_hit = pc.version == c->geno_version && pc.est == est && pc.bayesian == plan.bayesian &&
+                          pc.f == f && pc.fw == fw && pc.fd == fd && pc.nU == nU && pc.nW == nW && pc.nD == nD &&
+                          pc.nD2 == nD2 && c->scr_tab.p && c->samp_sum.p && c->scr_cnt.p;
     DevBuf<uint32_t> &tab = c->scr_tab;
-    tab.alloc((size_t)std::max(npass, 1) * cap);
-    tab.zero(c->stream);
-    c->scalars.alloc(4);
-    c->scalars.zero(c->stream);
-    c->iscalars.alloc(4);
-    c->iscalars.zero(c->stream);
-    DevBuf<int> &ovf = c->scr_flags;
-    ovf.alloc(2);
-    ovf.zero(c->stream);
-    const unsigned tblocks = (unsigned)((c->n_snp + 255) / 256);
-    c->scr_part.alloc((size_t)std::max(tblocks, 1u) * 2);
-    if (c->n_snp > 0) {
-        tables_kernel<<<tblocks, 256, 0, c->stream>>>(c->stat.p, c->n_snp, cap, est, plan.bayesian, f, fw, fd, nU, nW,
-                                                      nD, nD2, tab.p, c->scr_part.p, c->iscalars.p, ovf.p);
-        KERNEL_CHECK(c);
-    }
-    int hovf = 0;
-    std::vector<double> part((size_t)tblocks * 2);
-    CUDA_CHECK(cudaMemcpyAsync(&hovf, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    if (tblocks)
-        CUDA_CHECK(cudaMemcpyAsync(part.data(), c->scr_part.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost,
-                                   c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    double hsc[4] = {0, 0, 0, 0};
-    for (unsigned b = 0; b < tblocks; b++) {
-        hsc[0] += part[2 * b];
-        hsc[1] += part[2 * b + 1];
-    }
-    CUDA_CHECK(cudaMemcpyAsync(c->scalars.p, hsc, sizeof(hsc), cudaMemcpyHostToDevice, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));   // hsc lives on this stack frame
-    if (hovf) fail("internal: fixed-point digit overflow (table %d, frac_bits %d/%d/%d)", hovf, f, fw, fd);
+    if (!prep_hit) {
+        // scr_cnt was summed over the ranks together with an earlier format's vectors while the
+        // cached plan statistics kept it from being rebuilt: restore this rank's own counts
+        if (pc.reduced && pc.version == c->geno_version) sample_counts(c);
+        pc.version = 0;
+        tab.alloc((size_t)std::max(npass, 1) * cap);
+        tab.zero(c->stream);
+        c->scalars.alloc(4);
+        c->scalars.zero(c->stream);
+        c->iscalars.alloc(4);
+        c->iscalars.zero(c->stream);
+        DevBuf<int> &ovf = c->scr_flags;
+        ovf.alloc(2);
+        ovf.zero(c->stream);
+        const unsigned tblocks = (unsigned)((c->n_snp + 255) / 256);
+        c->scr_part.alloc((size_t)std::max(tblocks, 1u) * 2);
+        if (c->n_snp > 0) {
+            tables_kernel<<<tblocks, 256, 0, c->stream>>>(c->stat.p, c->n_snp, cap, est, plan.bayesian, f, fw, fd, nU,
+                                                          nW, nD, nD2, tab.p, c->scr_part.p, c->iscalars.p, ovf.p);
+            KERNEL_CHECK(c);
+        }
+        int hovf = 0;
+        std::vector<double> part((size_t)tblocks * 2);
+        CUDA_CHECK(cudaMemcpyAsync(&hovf, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        if (tblocks)
+            CUDA_CHECK(cudaMemcpyAsync(part.data(), c->scr_part.p, part.size() * sizeof(double),
+                                       cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        double hsc[4] = {0, 0, 0, 0};
+        for (unsigned b = 0; b < tblocks; b++) {
+            hsc[0] += part[2 * b];
+            hsc[1] += part[2 * b + 1];
+        }
+        CUDA_CHECK(cudaMemcpyAsync(c->scalars.p, hsc, sizeof(hsc), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));   // hsc lives on this stack frame
+        if (hovf) fail("internal: fixed-point digit overflow (table %d, frac_bits %d/%d/%d)", hovf, f, fw, fd);
 
-    // per-sample vectors
-    c->samp_sum.alloc((size_t)NVEC * npad);
-    c->samp_sum.zero(c->stream);
-    c->samp_vecs = NVEC;
-    if (c->n_snp > 0) {
-        dim3 grid((unsigned)((c->row_bytes + 127) / 128), (unsigned)((c->n_snp + SS_SNPS - 1) / SS_SNPS));
-        sample_sum_kernel<<<grid, 128, 0, c->stream>>>(c->geno2b.p, c->stat.p, c->n_snp, c->row_bytes,
-                                                       npad, est, plan.bayesian, f, fw, fd, c->samp_sum.p);
-        KERNEL_CHECK(c);
+        // per-sample vectors
+        c->samp_sum.alloc((size_t)NVEC * npad);
+        c->samp_sum.zero(c->stream);
+        c->samp_vecs = NVEC;
+        if (c->n_snp > 0) {
+            dim3 grid((unsigned)((c->row_bytes + 127) / 128), (unsigned)((c->n_snp + SS_SNPS - 1) / SS_SNPS));
+            sample_sum_kernel<<<grid, 128, 0, c->stream>>>(c->geno2b.p, c->stat.p, c->n_snp, c->row_bytes, npad, est,
+                                                           plan.bayesian, f, fw, fd, c->samp_sum.p);
+            KERNEL_CHECK(c);
+        }
+        pc.version = c->geno_version;
+        pc.est = est;
+        pc.bayesian = plan.bayesian;
+        pc.f = f;
+        pc.fw = fw;
+        pc.fd = fd;
+        pc.nU = nU;
+        pc.nW = nW;
+        pc.nD = nD;
+        pc.nD2 = nD2;
+        pc.reduced = false;
     }
 
     // Gram planes: 0 = numerator, 1 = missing-pair denominator (or KING-homo d), 2 = KING-homo d2
@@ -566,10 +615,12 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     c->accum_reduced = false;
     c->reduce_list.clear();
     c->reduce_list.push_back({c->acc.p, (int64_t)c->acc.n, 0});
-    c->reduce_list.push_back({c->samp_sum.p, (int64_t)c->samp_sum.n, 0});
-    c->reduce_list.push_back({c->scalars.p, (int64_t)c->scalars.n, 2});
-    c->reduce_list.push_back({c->iscalars.p, (int64_t)c->iscalars.n, 0});
-    c->reduce_list.push_back({c->scr_cnt.p, (int64_t)c->scr_cnt.n, 1});   // per-sample genotype sums / missing counts
+    if (!pc.reduced) {   // (kept from an earlier window: already summed over the ranks)
+        c->reduce_list.push_back({c->samp_sum.p, (int64_t)c->samp_sum.n, 0});
+        c->reduce_list.push_back({c->scalars.p, (int64_t)c->scalars.n, 2});
+        c->reduce_list.push_back({c->iscalars.p, (int64_t)c->iscalars.n, 0});
+        c->reduce_list.push_back({c->scr_cnt.p, (int64_t)c->scr_cnt.n, 1});   // per-sample genotype sums / missing counts
+    }
 }
 
 // ---------------------------------------------------------------------------
