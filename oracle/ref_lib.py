@@ -120,3 +120,55 @@ class RefWorkspace:
         o = np.empty((n, n))
         _ck(_lib().ref_indiv_beta(int(nthread), int(inbreeding), _p(o)))
         return o
+
+    # ---- PCA / EIGMIX loadings and correlations ----
+    def pca_corr(self, eigenvect, nthread=1):
+        """gnrPCACorr (src/genPCA.cpp:1456-1485) -> [k, nsnp]."""
+        m, n = self.dims()
+        v = np.asfortranarray(eigenvect, dtype=np.float64)
+        k = v.shape[1]
+        out = np.empty((m, k))
+        _ck(_lib().ref_pca_corr(int(nthread), k, _p(v), _p(out)))
+        return out.T
+
+    def pca_snp_loading(self, eigenval, eigenvect, trace_xtx, bayesian=False, nthread=1):
+        """gnrPCASNPLoading (src/genPCA.cpp:1489-1540) -> (loading [k, nsnp], avgfreq, scale)."""
+        m, n = self.dims()
+        v = np.asfortranarray(eigenvect, dtype=np.float64)
+        k = v.shape[1]
+        ev = np.ascontiguousarray(eigenval[:k], dtype=np.float64)
+        load, af, sc = np.empty((m, k)), np.empty(m), np.empty(m)
+        _ck(_lib().ref_pca_snp_loading(int(nthread), k, _p(ev), _p(v), C.c_double(trace_xtx), int(bayesian),
+                                       _p(load), _p(af), _p(sc)))
+        return load.T, af, sc
+
+    def pca_samp_loading(self, loadings, avgfreq, scale, nthread=1):
+        """gnrPCASampLoading (src/genPCA.cpp:1542-1563): loadings [k, nsnp] -> [n, k]."""
+        m, n = self.dims()
+        ld = np.ascontiguousarray(np.asarray(loadings, dtype=np.float64).T)     # [nsnp][k] == k x nsnp column-major
+        k = ld.shape[1]
+        out = np.empty((k, n))
+        _ck(_lib().ref_pca_samp_loading(int(nthread), k, _p(ld), _p(np.ascontiguousarray(avgfreq, dtype=np.float64)),
+                                        _p(np.ascontiguousarray(scale, dtype=np.float64)), _p(out)))
+        return out.T
+
+    def eigmix_snp_loading(self, eigenval, eigenvect, afreq, nthread=1):
+        """gnrEigMixSNPLoading (src/genEIGMIX.cpp:739-775) -> [k, nsnp]."""
+        m, n = self.dims()
+        v = np.asfortranarray(eigenvect, dtype=np.float64)
+        k = v.shape[1]
+        ev = np.ascontiguousarray(eigenval[:k], dtype=np.float64)
+        load = np.empty((m, k))
+        _ck(_lib().ref_eigmix_snp_loading(int(nthread), k, _p(ev), _p(v),
+                                          _p(np.ascontiguousarray(afreq, dtype=np.float64)), _p(load)))
+        return load.T
+
+    def eigmix_samp_loading(self, loadings, afreq, nthread=1):
+        """gnrEigMixSampLoading (src/genEIGMIX.cpp:777-803): loadings [k, nsnp] -> [n, k]."""
+        m, n = self.dims()
+        ld = np.ascontiguousarray(np.asarray(loadings, dtype=np.float64).T)
+        k = ld.shape[1]
+        out = np.empty((k, n))
+        _ck(_lib().ref_eigmix_samp_loading(int(nthread), k, _p(ld), _p(np.ascontiguousarray(afreq, dtype=np.float64)),
+                                           _p(out)))
+        return out.T

@@ -252,6 +252,11 @@ SEXP gnrIBD_KING_Robust(SEXP, SEXP, SEXP, SEXP);
 SEXP gnrIBD_KING_Homo(SEXP, SEXP, SEXP);
 SEXP gnrIBD_PLINK(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 SEXP gnrIBD_Beta(SEXP, SEXP, SEXP, SEXP);
+SEXP gnrPCACorr(SEXP, SEXP, SEXP, SEXP, SEXP);
+SEXP gnrPCASNPLoading(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+SEXP gnrPCASampLoading(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+SEXP gnrEigMixSNPLoading(SEXP, SEXP, SEXP, SEXP, SEXP);
+SEXP gnrEigMixSampLoading(SEXP, SEXP, SEXP, SEXP);
 }
 
 static MemGeno g_geno;
@@ -385,6 +390,62 @@ int ref_ibd_mom(int nthread, const double *afreq_in, int constraint, double *k0,
     copy_real(VECTOR_ELT(r, 0), k0);
     copy_real(VECTOR_ELT(r, 1), k1);
     copy_real(VECTOR_ELT(r, 2), afreq);
+    REF_CATCH
+}
+static SEXP real_matrix(const double *src, int nr, int nc) {
+    SEXP m = Rf_allocMatrix(REALSXP, nr, nc);
+    memcpy(REAL(m), src, sizeof(double) * (size_t)nr * nc);
+    return m;
+}
+static SEXP real_vector(const double *src, int n) {
+    SEXP v = Rf_allocVector(REALSXP, n);
+    memcpy(REAL(v), src, sizeof(double) * (size_t)n);
+    return v;
+}
+// gnrPCACorr (src/genPCA.cpp:1456-1485): eigvect n x k column-major -> corr k x nsnp
+int ref_pca_corr(int nthread, int k, const double *eigvect, double *out) {
+    REF_TRY
+    const int n = GWAS::MCWorkingGeno.Space().SampleNum();
+    copy_real(gnrPCACorr(Rf_ScalarInteger(k), real_matrix(eigvect, n, k), Rf_ScalarInteger(nthread), R_NilValue,
+                         Rf_ScalarLogical(0)), out);
+    REF_CATCH
+}
+// gnrPCASNPLoading (src/genPCA.cpp:1489-1540) -> loading k x nsnp, avgfreq, scale
+int ref_pca_snp_loading(int nthread, int k, const double *eigval, const double *eigvect, double trace_xtx,
+                        int bayesian, double *loading, double *avgfreq, double *scale) {
+    REF_TRY
+    const int n = GWAS::MCWorkingGeno.Space().SampleNum();
+    SEXP r = gnrPCASNPLoading(real_vector(eigval, k), real_matrix(eigvect, n, k), Rf_ScalarReal(trace_xtx),
+                              Rf_ScalarInteger(nthread), Rf_ScalarLogical(bayesian), Rf_ScalarLogical(0));
+    copy_real(VECTOR_ELT(r, 0), loading);
+    copy_real(VECTOR_ELT(r, 1), avgfreq);
+    copy_real(VECTOR_ELT(r, 2), scale);
+    REF_CATCH
+}
+// gnrPCASampLoading (src/genPCA.cpp:1542-1563): loadings k x nsnp -> n x k
+int ref_pca_samp_loading(int nthread, int k, const double *loadings, const double *avgfreq, const double *scale,
+                         double *out) {
+    REF_TRY
+    const int m = GWAS::MCWorkingGeno.Space().SNPNum();
+    copy_real(gnrPCASampLoading(Rf_ScalarInteger(k), real_matrix(loadings, k, m), real_vector(avgfreq, m),
+                                real_vector(scale, m), Rf_ScalarInteger(nthread), Rf_ScalarLogical(0)), out);
+    REF_CATCH
+}
+// gnrEigMixSNPLoading (src/genEIGMIX.cpp:739-775)
+int ref_eigmix_snp_loading(int nthread, int k, const double *eigval, const double *eigvect, const double *afreq,
+                           double *loading) {
+    REF_TRY
+    const int n = GWAS::MCWorkingGeno.Space().SampleNum(), m = GWAS::MCWorkingGeno.Space().SNPNum();
+    copy_real(gnrEigMixSNPLoading(real_vector(eigval, k), real_matrix(eigvect, n, k), real_vector(afreq, m),
+                                  Rf_ScalarInteger(nthread), Rf_ScalarLogical(0)), loading);
+    REF_CATCH
+}
+// gnrEigMixSampLoading (src/genEIGMIX.cpp:777-803)
+int ref_eigmix_samp_loading(int nthread, int k, const double *loadings, const double *afreq, double *out) {
+    REF_TRY
+    const int m = GWAS::MCWorkingGeno.Space().SNPNum();
+    copy_real(gnrEigMixSampLoading(real_matrix(loadings, k, m), real_vector(afreq, m), Rf_ScalarInteger(nthread),
+                                   Rf_ScalarLogical(0)), out);
     REF_CATCH
 }
 int ref_indiv_beta(int nthread, int inbreeding, double *out) {

@@ -126,6 +126,75 @@ def pca_eigen(genmat, eigen_cnt):
     return -w[:k], v[:, :k]
 
 
+# ---------------------------------------------------------------------------
+# SNP loadings, sample loadings (projection) and SNP-PC correlations
+# (the tall-skinny products either side of the eigen step)
+# ---------------------------------------------------------------------------
+
+
+def pca_snp_loading(geno, eigenval, eigenvect, trace_xtx, bayesian=False):
+    """gnrPCASNPLoading + CPCA_SNPLoad::thread_loading (src/genPCA.cpp:1489-1540,
+    938-1040): eigenvectors scaled by sqrt(((n-1)/TraceXTX)/eigenval_k), then
+    loading[k, l] = sum_j (g_jl - avg_l) scale_l v_jk over non-missing genotypes.
+    Returns (loading [k, nsnp], avgfreq [nsnp], scale [nsnp])."""
+    n = geno.shape[1]
+    k = eigenvect.shape[1]
+    v = eigenvect * np.sqrt(((n - 1) / trace_xtx) / np.asarray(eigenval[:k], dtype=np.float64))[None, :]
+    s, num, avg = _avg_geno(geno)
+    if bayesian:                                  # :963-966
+        p = (s + 1.0) / (2 * num + 2)
+        scale = np.where(num > 0, 1.0 / np.sqrt(p * (1 - p)), 0.0)
+    else:
+        scale = np.where(num > 0, _rsqrt_prod(avg), 0.0)
+    z = np.where(geno <= 2, (geno.astype(np.float64) - avg[:, None]) * scale[:, None], 0.0)
+    return (z @ v).T, avg, scale
+
+
+def pca_samp_loading(geno, loadings, avgfreq, scale):
+    """gnrPCASampLoading + CPCA_SampleLoad::thread_loading (src/genPCA.cpp:1542-1563,
+    1042-1123): out[i, k] = sum_l (g_il - avgfreq_l) scale_l loadings[k, l].  `loadings`
+    is what R passes: snploading * sqrt(((n0-1)/TraceXTX)/eigenval) (R/PCA.R:274-281)."""
+    z = np.where(geno <= 2, (geno.astype(np.float64) - avgfreq[:, None]) * scale[:, None], 0.0)
+    return z.T @ np.asarray(loadings, dtype=np.float64).T
+
+
+def pca_corr(geno, eigenvect):
+    """gnrPCACorr + CPCA_SNPCorr::SNP_PC_Corr (src/genPCA.cpp:1456-1485, 809-936):
+    Pearson correlation between each SNP's genotypes and each eigenvector over the
+    SNP's non-missing samples; NaN when fewer than 2 samples or a zero variance.
+    Returns [k, nsnp]."""
+    valid = (geno <= 2).astype(np.float64)
+    y = np.where(geno <= 2, geno, 0).astype(np.float64)
+    v = np.asarray(eigenvect, dtype=np.float64)
+    m = valid.sum(axis=1)[:, None]
+    XY, X, XX = y @ v, valid @ v, valid @ (v * v)
+    Y, YY = y.sum(axis=1)[:, None], (y * y).sum(axis=1)[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        c1, c2 = XX - X * X / m, YY - Y * Y / m
+        val = c1 * c2
+        out = np.where((m > 1) & (val > 0), (XY - X * Y / m) / np.sqrt(np.where(val > 0, val, 1.0)), np.nan)
+    return out.T
+
+
+def _eigmix_z(geno, afreq):
+    """(g - 2 af_l) / sqrt(sum_l 4 af_l (1 - af_l)), missing -> 0 (src/genEIGMIX.cpp:455-478,508-513)."""
+    afreq = np.asarray(afreq, dtype=np.float64)
+    sc = 1.0 / np.sqrt(np.sum(4 * afreq * (1 - afreq)))
+    return np.where(geno <= 2, (geno.astype(np.float64) - 2 * afreq[:, None]) * sc, 0.0)
+
+
+def eigmix_snp_loading(geno, eigenval, eigenvect, afreq):
+    """gnrEigMixSNPLoading + CEigMix_SNPLoad (src/genEIGMIX.cpp:739-775, 445-530) -> [k, nsnp]."""
+    k = eigenvect.shape[1]
+    v = eigenvect * np.sqrt(1.0 / np.asarray(eigenval[:k], dtype=np.float64))[None, :]
+    return (_eigmix_z(geno, afreq) @ v).T
+
+
+def eigmix_samp_loading(geno, loadings, afreq):
+    """gnrEigMixSampLoading + CEigMix_SampleLoad (src/genEIGMIX.cpp:777-803, 534-640) -> [n, k]."""
+    return _eigmix_z(geno, afreq).T @ np.asarray(loadings, dtype=np.float64).T
+
+
 def _missing_pair_denom(geno, d):
     """Denom[i,j] = sum_l d_l [i missing or j missing]
     (src/genPCA.cpp:1201-1224, src/genEIGMIX.cpp:113-138)."""

@@ -118,6 +118,15 @@ EXPORTED_SYMBOLS = [
 ]
 
 
+def window_owner(k: int, world: int) -> int:
+    """Rank that computes row window k when the N x N output is tiled across `world` GPUs.
+    Windows shrink with k (upper triangle), so they are dealt in boustrophedon order
+    (0..w-1, w-1..0, ...): every rank's share of the pairs is within a fraction of a window of
+    1/world, where plain round-robin always hands rank 0 the largest window of each round."""
+    r = k % (2 * world)
+    return r if r < world else 2 * world - 1 - r
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -242,8 +251,8 @@ class Context:
 
     def packed_by_windows(self, fn, rows, rank=0, world=1):
         """Run fn() (an estimator call with packed=True) over row windows of height `rows`
-        and concatenate the packed slices.  With world > 1 this rank only computes windows
-        rank, rank + world, ... and returns a list of (packed_offset, slice[s]) -- the N x N
+        and concatenate the packed slices.  With world > 1 this rank only computes the windows
+        window_owner() deals to it and returns a list of (packed_offset, slice[s]) -- the N x N
         output tiled across GPUs that all hold the same genotypes, no collective."""
         n, _ = self.geno_dim()
         parts, offs, off = [], [], 0
@@ -251,7 +260,7 @@ class Context:
             for k, (r0, h) in enumerate(self.windows(rows)):
                 self.set_row_window(r0, h)
                 cnt = self.window_count()
-                if k % world == rank:
+                if window_owner(k, world) == rank:
                     parts.append(fn())
                     offs.append(off)
                 off += cnt

@@ -305,6 +305,10 @@ int snprel_set_row_window(snprel_ctx *c, int64_t row0, int64_t rows) {
     if (rows > 0 && row0 >= c->n_samp) fail("snprel_set_row_window: window starts past the last sample");
     c->win_r0 = rows > 0 ? row0 : 0;
     c->win_rows = rows;
+    if (rows == 0) {   // back to the whole matrix: the per-window epilogue scratch is not needed
+        c->scr_num.release();
+        c->scr_out.release();
+    }
     c->accum_est = -1;
     c->accum_reduced = false;
     API_END(c)

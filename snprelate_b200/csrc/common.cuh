@@ -158,6 +158,7 @@ struct snprel_ctx {
     snprel::DevBuf<int2> scr_tiles;       // tile work list
     snprel::DevBuf<int> scr_cnt;          // per-sample genotype sum / missing count [2][npad]
     snprel::DevBuf<double> scr_part;      // per-block float64 partial sums of the tables kernel
+    snprel::DevBuf<double> scr_num, scr_out;   // epilogue scratch kept across row windows
     std::vector<int> host_cnt;
     std::vector<int2> host_tiles;
 

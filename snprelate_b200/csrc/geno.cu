@@ -197,6 +197,8 @@ void geno_begin(snprel_ctx *c, int64_t n_samp, int64_t cap) {
     c->snp_cap = round_up(cap > 0 ? cap : 1, SNP_PAD);
     c->n_snp = 0;
     c->geno2b.release();
+    c->scr_num.release();
+    c->scr_out.release();
     c->geno2b.alloc((size_t)c->snp_cap * c->row_bytes);
     c->stat.alloc(c->snp_cap);
     drop_derived(c);

@@ -784,7 +784,10 @@ static void grm_device(snprel_ctx *c, int method, int packed, int diagadj, doubl
     int64_t n = c->n_samp, npad = c->n_samp_pad;
     const RowWin w = row_window(c);
     if (!full_window(c) && !packed) fail("a row window returns the packed upper triangle only (useMatrix)");
-    DevBuf<double> num;
+    // row windows come in long runs of equal-or-shrinking size: keep the scratch between them
+    // (a cudaMalloc + cudaFree of several GB per window costs more than the epilogue itself)
+    DevBuf<double> num_local;
+    DevBuf<double> &num = full_window(c) ? num_local : c->scr_num;
     build_numerator(c, num);
     Globals g = read_globals(c);
     const int has_den = c->acc_planes > 1;
@@ -815,7 +818,8 @@ void grm_finish(snprel_ctx *c, int method, double *out, int packed) {
     int64_t n = c->n_samp;
     if (!full_window(c) && method == SNPREL_GRM_CORR) fail("method \"Corr\" needs the whole matrix, not a row window");
     need_grm_accum(c, method, 0);
-    DevBuf<double> o;
+    DevBuf<double> o_local;
+    DevBuf<double> &o = full_window(c) ? o_local : c->scr_out;
     if (method == SNPREL_GRM_CORR) {
         grm_device(c, SNPREL_GRM_GCTA, 0, 0, 1, o, nullptr);
         DevBuf<double> d;

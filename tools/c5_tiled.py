@@ -1,6 +1,6 @@
 """BASELINE config 5 (snpgdsGRM GCTA, 500k samples x 800k SNPs, N x N output tiled across GPUs)
 or any other tiled run: every rank holds the whole 2-bit matrix (100 GB at C5), the row windows of
-the N x N output are dealt round-robin to the ranks, no collective.  On one GPU `--world 8 --rank r`
+the N x N output are dealt to the ranks in boustrophedon order, no collective.  On one GPU `--world 8 --rank r`
 runs exactly the share rank r of an 8-GPU job would run (same windows, same time), so the
 8-GPU time can be measured at 1/8 of the GPU-minutes; under torchrun rank / world come from the
 environment and the job time is the max over ranks.
@@ -15,6 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import snprelate_b200 as S
+from snprelate_b200._lib import window_owner
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=500000)
@@ -44,7 +45,7 @@ t_synth = time.perf_counter() - t0
 free0, total = ctx.mem_info()
 
 wins = list(ctx.windows(args.rows))
-mine = wins[args.rank::args.world]
+mine = [w for k, w in enumerate(wins) if window_owner(k, args.world) == args.rank]
 if args.max_windows:
     mine = mine[:args.max_windows]
 max_cnt = 0
@@ -110,7 +111,7 @@ if args.rank == 0:
     total_pairs = n * (n + 1) / 2
     print(json.dumps({
         "workload": f"snpgdsGRM {args.method}, synthetic {n} samples x {m} SNPs, missing {args.miss}, "
-                    f"N x N output tiled in {args.rows}-row windows dealt round-robin to {args.world} rank(s)",
+                    f"N x N output tiled in {args.rows}-row windows dealt boustrophedon to {args.world} rank(s)",
         "rank": args.rank, "world": args.world, "torchrun": dist, "windows_this_rank": len(mine), "windows_total": len(wins),
         "synth_s": round(t_synth, 2), "job_s": round(t_job_max, 3), "hot_kernel_s": round(hot_ms / 1e3, 3),
         "pairs_this_job": pairs_all, "share_of_all_pairs": pairs_all / total_pairs,
