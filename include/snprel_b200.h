@@ -161,6 +161,40 @@ int snprel_pca(snprel_ctx *ctx, int eigen_cnt, int bayesian, double *genmat,
 int snprel_eigmix(snprel_ctx *ctx, int eigen_cnt, int diagadj, double *ibd,
                   double *afreq, double *eigval, double *eigvec);
 
+/* ---- loadings, projection of new samples, SNP-PC correlation ----------
+ * The tall-skinny float64 products either side of the eigen-decomposition
+ * (csrc/project.cu).  Matrix layouts are the reference's R layouts: an
+ * "n x k column-major" eigenvector matrix is eigvect[i + kk * n]; a
+ * "k x n_snp column-major" loading / correlation matrix is m[kk + l * k]. */
+
+/* gnrPCASNPLoading (src/genPCA.cpp:1489-1540, CPCA_SNPLoad :938-1040): SNP loadings of the
+ * workspace's samples against the top k eigenpairs of snprel_pca.  eigval[k], eigvect n x k,
+ * trace_xtx and bayesian as returned by / passed to snprel_pca.  loading: k x n_snp;
+ * avgfreq[n_snp] (mean genotype) and scale[n_snp] (nullable) are what
+ * snprel_pca_samp_loading needs later. */
+int snprel_pca_snp_loading(snprel_ctx *ctx, int k, const double *eigval,
+                           const double *eigvect, double trace_xtx, int bayesian,
+                           double *loading, double *avgfreq, double *scale);
+/* gnrPCASampLoading (src/genPCA.cpp:1542-1563, CPCA_SampleLoad :1042-1123): project the
+ * workspace's samples (typically NEW samples over the loading's SNPs) onto k components.
+ * loadings: k x n_snp, already scaled by sqrt(((n0-1)/TraceXTX)/eigenval) as R/PCA.R:274-277
+ * does; out: n_samp x k column-major. */
+int snprel_pca_samp_loading(snprel_ctx *ctx, int k, const double *loadings,
+                            const double *avgfreq, const double *scale, double *out);
+/* gnrPCACorr (src/genPCA.cpp:1456-1485, CPCA_SNPCorr :809-936): Pearson correlation between
+ * every SNP and each of k eigenvectors (n x k) over the SNP's non-missing samples; NaN when
+ * undefined.  out: k x n_snp. */
+int snprel_pca_corr(snprel_ctx *ctx, int k, const double *eigvect, double *out);
+/* gnrEigMixSNPLoading (src/genEIGMIX.cpp:739-775, CEigMix_SNPLoad :445-530); afreq[n_snp]
+ * as returned by snprel_eigmix. */
+int snprel_eigmix_snp_loading(snprel_ctx *ctx, int k, const double *eigval,
+                              const double *eigvect, const double *afreq,
+                              double *loading);
+/* gnrEigMixSampLoading (src/genEIGMIX.cpp:777-803, CEigMix_SampleLoad :534-640); loadings
+ * k x n_snp scaled by sqrt(1/eigenval) (R/PCA.R:296-297); out n_samp x k. */
+int snprel_eigmix_samp_loading(snprel_ctx *ctx, int k, const double *loadings,
+                               const double *afreq, double *out);
+
 /* ---- split accumulate / reduce / finish (multi-GPU SNP sharding) ------- */
 
 #define SNPREL_EST_IBS          10

@@ -1,6 +1,7 @@
 """snprelate_b200 -- B200-native (sm_100a) implementation of SNPRelate's pairwise
 N x N relatedness-matrix path (snpgdsGRM / snpgdsPCA / snpgdsEIGMIX / snpgdsIBS /
-snpgdsIBSNum / snpgdsIBDMoM / snpgdsIBDKING / snpgdsIndivBeta).
+snpgdsIBSNum / snpgdsIBDMoM / snpgdsIBDKING / snpgdsIndivBeta, plus the loadings /
+projection / SNP-PC correlation steps around the eigen-decomposition).
 
 The product is ``libsnprel_b200.so`` (hand-written CUDA behind a C ABI, see
 ``include/snprel_b200.h``).  This package is the thin host layer that mirrors the
@@ -15,6 +16,9 @@ from .api import (  # noqa: F401
     snpgdsGRM,
     snpgdsPCA,
     snpgdsEIGMIX,
+    snpgdsPCACorr,
+    snpgdsPCASNPLoading,
+    snpgdsPCASampLoading,
     snpgdsIBS,
     snpgdsIBSNum,
     snpgdsIBDMoM,
@@ -26,6 +30,6 @@ from .api import (  # noqa: F401
 
 __all__ = [
     "SNPRelError", "Context", "load_library", "library_path", "GenotypeData",
-    "snpgdsGRM", "snpgdsPCA", "snpgdsEIGMIX", "snpgdsIBS", "snpgdsIBSNum", "snpgdsIBDMoM", "snpgdsMergeGRM",
+    "snpgdsGRM", "snpgdsPCA", "snpgdsEIGMIX", "snpgdsPCACorr", "snpgdsPCASNPLoading", "snpgdsPCASampLoading", "snpgdsIBS", "snpgdsIBSNum", "snpgdsIBDMoM", "snpgdsMergeGRM",
     "snpgdsIBDKING", "snpgdsIndivBeta", "snpgdsSNPRateFreq",
 ]

@@ -73,6 +73,11 @@ def load_library():
         "snprel_grm": [p, i32, p, i32, C.POINTER(dbl)],
         "snprel_pca": [p, i32, i32, p, C.POINTER(dbl), C.POINTER(dbl), p, p],
         "snprel_eigmix": [p, i32, i32, p, p, p, p],
+        "snprel_pca_snp_loading": [p, i32, p, p, dbl, i32, p, p, p],
+        "snprel_pca_samp_loading": [p, i32, p, p, p, p],
+        "snprel_pca_corr": [p, i32, p, p],
+        "snprel_eigmix_snp_loading": [p, i32, p, p, p, p],
+        "snprel_eigmix_samp_loading": [p, i32, p, p, p],
         "snprel_plan_local": [p, i32, C.POINTER(Plan)],
         "snprel_accumulate": [p, i32, C.POINTER(Plan)],
         "snprel_reduce_buffer_count": [p],
@@ -111,7 +116,8 @@ EXPORTED_SYMBOLS = [
     "snprel_geno_dim", "snprel_geno_copy_u8", "snprel_geno_copy_2b", "snprel_snp_ratefreq", "snprel_select_snp_base", "snprel_select_snp_base_ex",
     "snprel_ibs_num", "snprel_ibs_ave", "snprel_ibd_mom", "snprel_ibd_mom_sums", "snprel_ibd_mom_from_sums", "snprel_king_robust", "snprel_king_robust_counts",
     "snprel_king_homo", "snprel_indiv_beta", "snprel_indiv_beta_counts", "snprel_grm",
-    "snprel_pca", "snprel_eigmix", "snprel_plan_local", "snprel_accumulate",
+    "snprel_pca", "snprel_eigmix", "snprel_pca_snp_loading", "snprel_pca_samp_loading", "snprel_pca_corr",
+    "snprel_eigmix_snp_loading", "snprel_eigmix_samp_loading", "snprel_plan_local", "snprel_accumulate",
     "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced", "snprel_last_plan", "snprel_set_row_window", "snprel_window_count", "snprel_mem_info",
     "snprel_kernel_launches", "snprel_last_hot_kernel", "snprel_time_accumulate", "snprel_last_step_ms", "snprel_invalidate",
     "snprel_table_gram", "snprel_debug_flags",
@@ -278,13 +284,20 @@ class Context:
         for r0 in range(0, n, rows):
             yield r0, rows
 
-    def _out(self, packed):
-        if getattr(self, "_win", False):
-            if not packed:
-                raise SNPRelError("a row window returns the packed upper triangle only (useMatrix)")
-            return np.empty(self.window_count())
+    def _out(self, packed, out=None):
+        """Result buffer: a fresh array, or a view of the caller's `out` (C-contiguous float64,
+        e.g. pinned host memory re-used across row windows)."""
+        win = getattr(self, "_win", False)
+        if win and not packed:
+            raise SNPRelError("a row window returns the packed upper triangle only (useMatrix)")
         n, _ = self.geno_dim()
-        return np.empty(n * (n + 1) // 2) if packed else np.empty((n, n))
+        need = self.window_count() if win else (n * (n + 1) // 2 if packed else n * n)
+        if out is None:
+            return np.empty(need) if (win or packed) else np.empty((n, n))
+        if out.dtype != np.float64 or not out.flags.c_contiguous or out.size < need:
+            raise SNPRelError("'out' must be a C-contiguous float64 buffer of at least the result's size")
+        o = out.reshape(-1)[:need]
+        return o if (win or packed) else o.reshape(n, n)
 
     def ibs_num(self):
         n, _ = self.geno_dim()
@@ -295,8 +308,8 @@ class Context:
         self._ck(self.lib.snprel_ibs_num(self.h, _ptr(o[0]), _ptr(o[1]), _ptr(o[2])))
         return o
 
-    def ibs_ave(self, packed=False):
-        o = self._out(packed)
+    def ibs_ave(self, packed=False, out=None):
+        o = self._out(packed, out)
         self._ck(self.lib.snprel_ibs_ave(self.h, _ptr(o), int(packed)))
         return o
 
@@ -330,8 +343,9 @@ class Context:
                                                    int(packed), _ptr(k0), _ptr(k1)))
         return k0, k1
 
-    def king_robust(self, family_id=None, packed=False):
-        a, b = self._out(packed), self._out(packed)
+    def king_robust(self, family_id=None, packed=False, out=None):
+        """`out`: optional pair of caller buffers (IBS0, kinship)."""
+        a, b = self._out(packed, None if out is None else out[0]), self._out(packed, None if out is None else out[1])
         fam = None if family_id is None else np.ascontiguousarray(family_id, dtype=np.int32)
         self._ck(self.lib.snprel_king_robust(self.h, _ptr(fam), _ptr(a), _ptr(b), int(packed)))
         return a, b
@@ -365,14 +379,7 @@ class Context:
             raise SNPRelError("Invalid 'method'!")
         if method == "Corr":
             packed = False
-        if out is None:
-            o = self._out(packed)
-        else:
-            n, _ = self.geno_dim()
-            need = self.window_count() if getattr(self, "_win", False) else (n * (n + 1) // 2 if packed else n * n)
-            if out.dtype != np.float64 or not out.flags.c_contiguous or out.size < need:
-                raise SNPRelError("grm: 'out' must be a C-contiguous float64 buffer of the result's size")
-            o = out.reshape(-1)[:need] if (packed or getattr(self, "_win", False)) else out.reshape(-1)[:need].reshape(n, n)
+        o = self._out(packed, out)
         avg = C.c_double()
         self._ck(self.lib.snprel_grm(self.h, GRM_METHODS[method], _ptr(o), int(packed), C.byref(avg)))
         return o, avg.value
@@ -403,6 +410,74 @@ class Context:
         self._ck(self.lib.snprel_eigmix(self.h, k, int(bool(diagadj)), _ptr(ibd), _ptr(af), _ptr(eigval),
                                         _ptr(eigvec)))
         return dict(eigenval=eigval, eigenvect=None if eigvec is None else eigvec.T, afreq=af, ibd=ibd)
+
+    # ---- loadings / projection / correlation (matrices in the reference's R layouts) ----
+    @staticmethod
+    def _colmajor(a, name):
+        a = np.asarray(a, dtype=np.float64)
+        if a.ndim != 2:
+            raise SNPRelError(f"{name} must be a matrix")
+        return np.asfortranarray(a)
+
+    def pca_snp_loading(self, eigenval, eigenvect, trace_xtx, bayesian=False):
+        """-> (snploading [k, n_snp], avgfreq [n_snp], scale [n_snp])."""
+        n, m = self.geno_dim()
+        v = self._colmajor(eigenvect, "eigenvect")
+        if v.shape[0] != n:
+            raise SNPRelError("the number of samples should be equal to the number of rows in 'eigenvect'.")
+        k = v.shape[1]
+        ev = np.ascontiguousarray(np.asarray(eigenval, dtype=np.float64)[:k])
+        load, af, sc = np.empty((m, k)), np.empty(m), np.empty(m)
+        self._ck(self.lib.snprel_pca_snp_loading(self.h, k, _ptr(ev), _ptr(v), float(trace_xtx), int(bool(bayesian)),
+                                                 _ptr(load), _ptr(af), _ptr(sc)))
+        return load.T, af, sc
+
+    def pca_samp_loading(self, loadings, avgfreq, scale):
+        """loadings [k, n_snp] (pre-scaled) -> eigenvect [n_samp, k]."""
+        n, m = self.geno_dim()
+        ld = self._colmajor(loadings, "loadings")          # k x n_snp column-major == [n_snp][k]
+        if ld.shape[1] != m:
+            raise SNPRelError("the number of SNPs should be equal to the number of columns in 'snploading'.")
+        k = ld.shape[0]
+        af = np.ascontiguousarray(avgfreq, dtype=np.float64)
+        sc = np.ascontiguousarray(scale, dtype=np.float64)
+        if af.shape != (m,) or sc.shape != (m,):
+            raise SNPRelError("'avgfreq' and 'scale' must have one entry per SNP")
+        out = np.empty((k, n))
+        self._ck(self.lib.snprel_pca_samp_loading(self.h, k, _ptr(ld), _ptr(af), _ptr(sc), _ptr(out)))
+        return out.T
+
+    def pca_corr(self, eigenvect):
+        """-> snpcorr [k, n_snp]."""
+        n, m = self.geno_dim()
+        v = self._colmajor(eigenvect, "eigenvect")
+        if v.shape[0] != n:
+            raise SNPRelError("the number of samples should be equal to the number of rows in 'eigenvect'.")
+        k = v.shape[1]
+        out = np.empty((m, k))
+        self._ck(self.lib.snprel_pca_corr(self.h, k, _ptr(v), _ptr(out)))
+        return out.T
+
+    def eigmix_snp_loading(self, eigenval, eigenvect, afreq):
+        n, m = self.geno_dim()
+        v = self._colmajor(eigenvect, "eigenvect")
+        if v.shape[0] != n:
+            raise SNPRelError("the number of samples should be equal to the number of rows in 'eigenvect'.")
+        k = v.shape[1]
+        ev = np.ascontiguousarray(np.asarray(eigenval, dtype=np.float64)[:k])
+        load = np.empty((m, k))
+        self._ck(self.lib.snprel_eigmix_snp_loading(self.h, k, _ptr(ev), _ptr(v), _ptr(self._afreq_in(afreq)), _ptr(load)))
+        return load.T
+
+    def eigmix_samp_loading(self, loadings, afreq):
+        n, m = self.geno_dim()
+        ld = self._colmajor(loadings, "loadings")
+        if ld.shape[1] != m:
+            raise SNPRelError("the number of SNPs should be equal to the number of columns in 'snploading'.")
+        k = ld.shape[0]
+        out = np.empty((k, n))
+        self._ck(self.lib.snprel_eigmix_samp_loading(self.h, k, _ptr(ld), _ptr(self._afreq_in(afreq)), _ptr(out)))
+        return out.T
 
     # ---- split accumulate / reduce / finish ----
     def plan_local(self, est, bayesian=False, tol=0.0):

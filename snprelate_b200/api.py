@@ -224,7 +224,8 @@ def snpgdsPCA(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_mo
     return {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "eigenval": eigenval,
             "eigenvect": r["eigenvect"],
             "varprop": None if eigenval is None else eigenval / r["TraceVal"],
-            "TraceXTX": r["TraceXTX"], "Bayesian": bayesian, "genmat": r["genmat"]}
+            "TraceXTX": r["TraceXTX"], "Bayesian": bayesian, "genmat": r["genmat"],
+            "class": "snpgdsPCAClass"}
 
 
 def snpgdsEIGMIX(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_monosnp=True,
@@ -238,7 +239,93 @@ def snpgdsEIGMIX(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove
     with ws["ctx"] as ctx:
         r = ctx.eigmix(eigen_cnt, diagadj, ibdmat)
     return {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "eigenval": r["eigenval"],
-            "eigenvect": r["eigenvect"], "afreq": r["afreq"], "ibd": r["ibd"], "diagadj": diagadj}
+            "eigenvect": r["eigenvect"], "afreq": r["afreq"], "ibd": r["ibd"], "diagadj": diagadj,
+            "class": "snpgdsEigMixClass"}
+
+
+def _init_file(gdsobj, sample_id, snp_id, device=0):
+    """.InitFile (R/Internal.R:56-163): selection only, no QC filter."""
+    return _init_file2(gdsobj, sample_id, snp_id, False, False, float("nan"), float("nan"), 1, False, device)
+
+
+def snpgdsPCACorr(pcaobj, gdsobj, snp_id=None, eig_which=None, num_thread=1, with_id=True, outgds=None,
+                  verbose=False, device=0):
+    """R/PCA.R:99-175 -> gnrPCACorr (src/genPCA.cpp:1456-1485).  `eig_which` is 1-based like
+    the reference's eig.which.  pcaobj: a snpgdsPCA / snpgdsEIGMIX result, or a
+    (sample_id, eigenvect) pair standing in for a matrix with sample-id row names."""
+    if isinstance(pcaobj, dict) and pcaobj.get("class") in ("snpgdsPCAClass", "snpgdsEigMixClass"):
+        sampid, eigenvect = pcaobj["sample.id"], pcaobj["eigenvect"]
+    elif isinstance(pcaobj, (tuple, list)) and len(pcaobj) == 2:
+        sampid, eigenvect = pcaobj
+        if sampid is None:
+            raise SNPRelError("'rownames(pcaobj)' should be sample id.")
+    else:
+        raise SNPRelError("'pcaobj' should be a snpgdsPCA / snpgdsEIGMIX result or (sample.id, eigenvect)")
+    if outgds is not None:
+        raise SNPRelError("'outgds' (packedreal16 GDS output) is not supported; use the returned matrix")
+    eigenvect = np.asarray(eigenvect, dtype=np.float64)
+    ws = _init_file(gdsobj, sampid, snp_id, device)
+    if len(sampid) != eigenvect.shape[0]:
+        raise SNPRelError("Internal error: the number of samples should be equal to the number of rows in 'eigenvect'.")
+    if eig_which is None:
+        idx = np.arange(eigenvect.shape[1])
+    else:
+        idx = np.asarray(eig_which, dtype=np.int64).reshape(-1) - 1
+        if idx.size == 0 or idx.min() < 0 or idx.max() >= eigenvect.shape[1]:
+            raise SNPRelError("'eig.which' is out of range")
+    with ws["ctx"] as ctx:
+        corr = ctx.pca_corr(eigenvect[:, idx])
+    if with_id:
+        return {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "snpcorr": corr}
+    return corr
+
+
+def snpgdsPCASNPLoading(pcaobj, gdsobj, num_thread=1, verbose=False, device=0):
+    """R/PCA.R:184-229 -> gnrPCASNPLoading (src/genPCA.cpp:1489-1540) or, for a snpgdsEIGMIX
+    result, gnrEigMixSNPLoading (src/genEIGMIX.cpp:739-775)."""
+    cls = pcaobj.get("class") if isinstance(pcaobj, dict) else None
+    if cls not in ("snpgdsPCAClass", "snpgdsEigMixClass"):
+        raise SNPRelError("'pcaobj' should be a snpgdsPCA or snpgdsEIGMIX result")
+    if pcaobj.get("eigenval") is None or pcaobj.get("eigenvect") is None:
+        raise SNPRelError("'pcaobj' has no eigenvalues / eigenvectors")
+    ws = _init_file(gdsobj, pcaobj["sample.id"], pcaobj["snp.id"], device)
+    k = pcaobj["eigenvect"].shape[1]
+    with ws["ctx"] as ctx:
+        if cls == "snpgdsPCAClass":
+            load, avg, scale = ctx.pca_snp_loading(pcaobj["eigenval"], pcaobj["eigenvect"], pcaobj["TraceXTX"],
+                                                   pcaobj["Bayesian"])
+            return {"sample.id": pcaobj["sample.id"], "snp.id": pcaobj["snp.id"], "eigenval": pcaobj["eigenval"],
+                    "snploading": load, "TraceXTX": pcaobj["TraceXTX"], "Bayesian": pcaobj["Bayesian"],
+                    "avgfreq": avg, "scale": scale, "class": "snpgdsPCASNPLoadingClass"}
+        if pcaobj.get("diagadj"):
+            raise SNPRelError("Please run `snpgdsEIGMIX(, diagadj=FALSE)` for projecting new samples.")
+        load = ctx.eigmix_snp_loading(pcaobj["eigenval"][:k], pcaobj["eigenvect"], pcaobj["afreq"])
+        return {"sample.id": pcaobj["sample.id"], "snp.id": pcaobj["snp.id"], "eigenval": pcaobj["eigenval"],
+                "snploading": load, "afreq": pcaobj["afreq"], "class": "snpgdsEigMixSNPLoadingClass"}
+
+
+def snpgdsPCASampLoading(loadobj, gdsobj, sample_id=None, num_thread=1, verbose=False, device=0):
+    """R/PCA.R:238-303 -> gnrPCASampLoading (src/genPCA.cpp:1542-1563) / gnrEigMixSampLoading
+    (src/genEIGMIX.cpp:777-803): project (new) samples onto the components of `loadobj`."""
+    cls = loadobj.get("class") if isinstance(loadobj, dict) else None
+    if cls not in ("snpgdsPCASNPLoadingClass", "snpgdsEigMixSNPLoadingClass"):
+        raise SNPRelError("'loadobj' should be a snpgdsPCASNPLoading result")
+    ws = _init_file(gdsobj, sample_id, loadobj["snp.id"], device)
+    load = np.asarray(loadobj["snploading"], dtype=np.float64)
+    eigcnt = load.shape[0]
+    nan = np.full(ws["n_samp"], np.nan)
+    with ws["ctx"] as ctx:
+        if cls == "snpgdsPCASNPLoadingClass":
+            ss = (len(loadobj["sample.id"]) - 1) / loadobj["TraceXTX"]              # R/PCA.R:274-277
+            sload = load * np.sqrt(ss / np.asarray(loadobj["eigenval"][:eigcnt]))[:, None]
+            mm = ctx.pca_samp_loading(sload, loadobj["avgfreq"], loadobj["scale"])
+            return {"sample.id": ws["sample_id"], "snp.id": loadobj["snp.id"], "eigenval": nan, "eigenvect": mm,
+                    "varprop": nan.copy(), "TraceXTX": loadobj["TraceXTX"], "Bayesian": loadobj["Bayesian"],
+                    "genmat": None, "class": "snpgdsPCAClass"}
+        sload = load * np.sqrt(1.0 / np.asarray(loadobj["eigenval"][:eigcnt]))[:, None]       # R/PCA.R:296-297
+        mm = ctx.eigmix_samp_loading(sload, loadobj["afreq"])
+        return {"sample.id": ws["sample_id"], "snp.id": loadobj["snp.id"], "eigenval": nan, "eigenvect": mm,
+                "afreq": loadobj["afreq"], "class": "snpgdsEigMixClass"}
 
 
 def snpgdsIBS(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_monosnp=True,

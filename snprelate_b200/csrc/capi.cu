@@ -213,6 +213,31 @@ int snprel_eigmix(snprel_ctx *c, int eigen_cnt, int diagadj, double *ibd, double
     API_END(c)
 }
 
+// ---- loadings / projection / SNP-PC correlation -------------------------------
+int snprel_pca_snp_loading(snprel_ctx *c, int k, const double *eigval, const double *eigvect, double trace_xtx,
+                           int bayesian, double *loading, double *avgfreq, double *scale) {
+    API_BEGIN(c) pca_snp_loading(c, k, eigval, eigvect, trace_xtx, bayesian, loading, avgfreq, scale);
+    API_END(c)
+}
+int snprel_pca_samp_loading(snprel_ctx *c, int k, const double *loadings, const double *avgfreq, const double *scale,
+                            double *out) {
+    API_BEGIN(c) pca_samp_loading(c, k, loadings, avgfreq, scale, out);
+    API_END(c)
+}
+int snprel_pca_corr(snprel_ctx *c, int k, const double *eigvect, double *out) {
+    API_BEGIN(c) pca_corr(c, k, eigvect, out);
+    API_END(c)
+}
+int snprel_eigmix_snp_loading(snprel_ctx *c, int k, const double *eigval, const double *eigvect, const double *afreq,
+                              double *loading) {
+    API_BEGIN(c) eigmix_snp_loading(c, k, eigval, eigvect, afreq, loading);
+    API_END(c)
+}
+int snprel_eigmix_samp_loading(snprel_ctx *c, int k, const double *loadings, const double *afreq, double *out) {
+    API_BEGIN(c) eigmix_samp_loading(c, k, loadings, afreq, out);
+    API_END(c)
+}
+
 // ---- split accumulate / reduce / finish -------------------------------------
 static bool is_cov(int est) { return est >= SNPREL_GRM_EIGENSTRAT && est <= SNPREL_GRM_EIGMIX; }
 

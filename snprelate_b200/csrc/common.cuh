@@ -104,6 +104,17 @@ struct ReduceBuf {
     int kind;   // 0 int64, 1 uint32, 2 float64
 };
 
+
+// project.cu
+void pca_snp_loading(snprel_ctx *c, int k, const double *eigval, const double *eigvect, double trace_xtx,
+                     int bayesian, double *loading, double *avgfreq, double *scale);
+void pca_samp_loading(snprel_ctx *c, int k, const double *loadings, const double *avgfreq, const double *scale,
+                      double *out);
+void pca_corr(snprel_ctx *c, int k, const double *eigvect, double *out);
+void eigmix_snp_loading(snprel_ctx *c, int k, const double *eigval, const double *eigvect, const double *afreq,
+                        double *loading);
+void eigmix_samp_loading(snprel_ctx *c, int k, const double *loadings, const double *afreq, double *out);
+
 }  // namespace snprel
 
 // ---------------------------------------------------------------------------
@@ -267,5 +278,16 @@ void eigmix_finish(snprel_ctx *c, int eigen_cnt, int diagadj, double *ibd, doubl
                    double *eigval, double *eigvec);
 void king_homo_finish(snprel_ctx *c, double *k0, double *k1, int packed);
 void table_gram_debug(snprel_ctx *c, const int8_t *tabA, const int8_t *tabB, int64_t *out);
+
+
+// project.cu
+void pca_snp_loading(snprel_ctx *c, int k, const double *eigval, const double *eigvect, double trace_xtx,
+                     int bayesian, double *loading, double *avgfreq, double *scale);
+void pca_samp_loading(snprel_ctx *c, int k, const double *loadings, const double *avgfreq, const double *scale,
+                      double *out);
+void pca_corr(snprel_ctx *c, int k, const double *eigvect, double *out);
+void eigmix_snp_loading(snprel_ctx *c, int k, const double *eigval, const double *eigvect, const double *afreq,
+                        double *loading);
+void eigmix_samp_loading(snprel_ctx *c, int k, const double *loadings, const double *afreq, double *out);
 
 }  // namespace snprel

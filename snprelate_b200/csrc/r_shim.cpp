@@ -7,6 +7,9 @@
 //   gnrEigMix           src/genEIGMIX.cpp:656-735     gnrIBD_KING_Robust src/genKING.cpp:576-679
 //   gnrGRM_avg_val      src/genPCA.cpp:1608           gnrIBD_KING_Homo   src/genKING.cpp:493-570
 //   gnrIBD_PLINK        src/genIBS.cpp:558-639        gnrIBD_Beta        src/genBeta.cpp:361-460
+//   gnrPCACorr          src/genPCA.cpp:1456-1485      gnrPCASNPLoading   src/genPCA.cpp:1489-1540
+//   gnrPCASampLoading   src/genPCA.cpp:1542-1563      gnrEigMixSNPLoading / gnrEigMixSampLoading
+//                                                     src/genEIGMIX.cpp:739-803
 // inside SNPRelate.so, keeping the workspace layer (gnrSetGenoSpace / gnrSelSNP_Base,
 // src/SNPRelate.cpp:76-214) and the R code untouched: every routine streams the SELECTED
 // genotypes through CdBaseWorkSpace::snpRead (src/dGenGWAS.h:94) into the device workspace and
@@ -215,6 +218,72 @@ COREARRAY_DLL_EXPORT SEXP gnrIBD_Beta(SEXP Inbreeding, SEXP NumThread, SEXP useM
         const bool packed = Rf_asLogical(useMatrix) == TRUE;
         rv_ans = PROTECT(sym_result(n, packed));
         c.ck(snprel_indiv_beta(c.h, inbreeding == TRUE, REAL(rv_ans), packed, &g_avg_val));
+        UNPROTECT(1);
+    COREARRAY_CATCH
+}
+
+// ---- loadings / projection / SNP-PC correlation (csrc/project.cu) ----
+
+COREARRAY_DLL_EXPORT SEXP gnrPCACorr(SEXP LenEig, SEXP EigenVect, SEXP NumThread, SEXP GDSNode, SEXP Verbose) {
+    const int nEig = Rf_asInteger(LenEig);
+    COREARRAY_TRY
+        if (!Rf_isNull(GDSNode)) throw ErrCoreArray("GDS output is written by the host wrapper (INTEGRATION.md).");
+        Ctx c;
+        load_workspace(c);
+        rv_ans = PROTECT(Rf_allocMatrix(REALSXP, nEig, MCWorkingGeno.Space().SNPNum()));
+        c.ck(snprel_pca_corr(c.h, nEig, REAL(EigenVect), REAL(rv_ans)));
+        UNPROTECT(1);
+    COREARRAY_CATCH
+}
+
+COREARRAY_DLL_EXPORT SEXP gnrPCASNPLoading(SEXP EigenVal, SEXP EigenVect, SEXP TraceXTX, SEXP NumThread,
+                                           SEXP Bayesian, SEXP Verbose) {
+    const int LenEig = INTEGER(GET_DIM(EigenVect))[1];
+    COREARRAY_TRY
+        Ctx c;
+        load_workspace(c);
+        const size_t m = MCWorkingGeno.Space().SNPNum();
+        PROTECT(rv_ans = NEW_LIST(3));
+        SEXP loading = PROTECT(Rf_allocMatrix(REALSXP, LenEig, m)); SET_ELEMENT(rv_ans, 0, loading); UNPROTECT(1);
+        SEXP afreq = PROTECT(NEW_NUMERIC(m)); SET_ELEMENT(rv_ans, 1, afreq); UNPROTECT(1);
+        SEXP scale = PROTECT(NEW_NUMERIC(m)); SET_ELEMENT(rv_ans, 2, scale); UNPROTECT(1);
+        c.ck(snprel_pca_snp_loading(c.h, LenEig, REAL(EigenVal), REAL(EigenVect), Rf_asReal(TraceXTX),
+                                    Rf_asLogical(Bayesian) == TRUE, REAL(loading), REAL(afreq), REAL(scale)));
+        UNPROTECT(1);
+    COREARRAY_CATCH
+}
+
+COREARRAY_DLL_EXPORT SEXP gnrPCASampLoading(SEXP EigenCnt, SEXP SNPLoadings, SEXP AvgFreq, SEXP Scale,
+                                            SEXP NumThread, SEXP Verbose) {
+    COREARRAY_TRY
+        Ctx c;
+        load_workspace(c);
+        rv_ans = PROTECT(Rf_allocMatrix(REALSXP, MCWorkingGeno.Space().SampleNum(), Rf_asInteger(EigenCnt)));
+        c.ck(snprel_pca_samp_loading(c.h, Rf_asInteger(EigenCnt), REAL(SNPLoadings), REAL(AvgFreq), REAL(Scale),
+                                     REAL(rv_ans)));
+        UNPROTECT(1);
+    COREARRAY_CATCH
+}
+
+COREARRAY_DLL_EXPORT SEXP gnrEigMixSNPLoading(SEXP EigenVal, SEXP EigenVect, SEXP AFreq, SEXP NumThread,
+                                              SEXP Verbose) {
+    const int LenEig = INTEGER(GET_DIM(EigenVect))[1];
+    COREARRAY_TRY
+        Ctx c;
+        load_workspace(c);
+        rv_ans = PROTECT(Rf_allocMatrix(REALSXP, LenEig, MCWorkingGeno.Space().SNPNum()));
+        c.ck(snprel_eigmix_snp_loading(c.h, LenEig, REAL(EigenVal), REAL(EigenVect), REAL(AFreq), REAL(rv_ans)));
+        UNPROTECT(1);
+    COREARRAY_CATCH
+}
+
+COREARRAY_DLL_EXPORT SEXP gnrEigMixSampLoading(SEXP SNPLoadings, SEXP AFreq, SEXP NumThread, SEXP Verbose) {
+    const int EigenCnt = INTEGER(GET_DIM(SNPLoadings))[0];
+    COREARRAY_TRY
+        Ctx c;
+        load_workspace(c);
+        rv_ans = PROTECT(Rf_allocMatrix(REALSXP, MCWorkingGeno.Space().SampleNum(), EigenCnt));
+        c.ck(snprel_eigmix_samp_loading(c.h, EigenCnt, REAL(SNPLoadings), REAL(AFreq), REAL(rv_ans)));
         UNPROTECT(1);
     COREARRAY_CATCH
 }

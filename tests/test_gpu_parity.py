@@ -109,6 +109,63 @@ def test_pca_golden(gds, hapmap, goldens):          # test_rel.R:133-195
     assert abs(r["varprop"][0] - r["eigenval"][0] / np.trace(r["genmat"])) < 1e-12
 
 
+def _sign_free(got, ref, tol):
+    return min(np.nanmax(np.abs(got - ref)), np.nanmax(np.abs(-got - ref))) <= tol and \
+        np.array_equal(np.isnan(got), np.isnan(ref))
+
+
+def test_pca_loadings_golden(gds, hapmap, goldens):          # test_rel.R:144-160
+    samp = hapmap["sample_id"]
+    pca = S.snpgdsPCA(gds, sample_id=samp[:90], missing_rate=float("nan"), need_genmat=True, eigen_cnt=8)
+    corr = S.snpgdsPCACorr(pca, gds, eig_which=[1, 2])["snpcorr"]
+    assert corr.shape == (2, 9088)
+    for k in range(2):              # goldens are rounded (3 / 3 / 4 decimals), eigenvector signs are free
+        assert _sign_free(corr[k], goldens["pca_corr"][k], 0.5e-3 + 1e-9), k
+    sl = S.snpgdsPCASNPLoading(pca, gds)
+    assert sl["snploading"].shape == (8, 8695)
+    for k in range(8):
+        assert _sign_free(sl["snploading"][k], goldens["pca_snploading"][k], 0.5e-3 + 1e-9), k
+    pr = S.snpgdsPCASampLoading(sl, gds, sample_id=samp[:100])
+    assert pr["eigenvect"].shape == (100, 8) and np.all(np.isnan(pr["eigenval"]))
+    for k in range(8):
+        assert _sign_free(pr["eigenvect"][:, k], goldens["pca_samploading"][:, k], 0.5e-4 + 1e-9), k
+    # and to float64 accuracy against the oracle fed with the device's own eigenpairs
+    g, idx = hapmap_subset(hapmap, 90)
+    load, avg, scale = O.pca_snp_loading(g, pca["eigenval"], pca["eigenvect"], pca["TraceXTX"])
+    assert relerr(sl["snploading"], load) < TOL and np.array_equal(sl["avgfreq"], avg) and relerr(sl["scale"], scale) < 1e-14
+    # projecting the training samples reproduces their eigenvectors (the identity the method rests on)
+    back = S.snpgdsPCASampLoading(sl, gds, sample_id=samp[:90])["eigenvect"]
+    assert np.max(np.abs(back - pca["eigenvect"])) < 1e-8
+
+
+@pytest.mark.parametrize("n,m,k,miss", [(300, 3001, 5, 0.03), (257, 1200, 40, 0.0), (130, 77, 1, 0.2)])
+def test_loadings_vs_oracle(ctx, n, m, k, miss):
+    """SNP loadings, projection of new samples, SNP-PC correlation and the EIGMIX flavours against
+    the oracle on ragged sizes (k > 32 takes two column panels), with missing data."""
+    g = O.synth_geno(n, m, seed=n + m, miss_rate=miss, maf_lo=0.01)
+    new = O.synth_geno(91, m, seed=5, miss_rate=miss, maf_lo=0.01)
+    genmat, tr, _ = O.pca_genmat(g)
+    val, vec = O.pca_eigen(genmat, k)
+    load(ctx, g)
+    for bayes in (False, True):
+        got, avg, scale = ctx.pca_snp_loading(val, vec, tr, bayes)
+        ref, ravg, rscale = O.pca_snp_loading(g, val, vec, tr, bayes)
+        assert relerr(got, ref) < TOL and np.array_equal(avg, ravg) and relerr(scale, rscale) < 1e-14
+    corr, rcorr = ctx.pca_corr(vec), O.pca_corr(g, vec)
+    assert np.array_equal(np.isnan(corr), np.isnan(rcorr)) and np.nanmax(np.abs(corr - rcorr)) < 1e-9
+    ibd, af = O.eigmix_ibd(g, diagadj=False)
+    ev, evec = O.pca_eigen(ibd, k)
+    el = ctx.eigmix_snp_loading(ev, evec, af)
+    assert relerr(el, O.eigmix_snp_loading(g, ev, evec, af)) < TOL
+    sload = ref * np.sqrt(((n - 1) / tr) / val[:k])[:, None]
+    esl = el * np.sqrt(1.0 / np.abs(ev[:k]))[:, None]
+    load(ctx, new)
+    assert relerr(ctx.pca_samp_loading(sload, ravg, rscale), O.pca_samp_loading(new, sload, ravg, rscale)) < TOL
+    assert relerr(ctx.eigmix_samp_loading(esl, af), O.eigmix_samp_loading(new, esl, af)) < TOL
+    with pytest.raises(S.SNPRelError, match="number of samples"):
+        ctx.pca_corr(vec)           # 91 samples in the workspace, n rows in vec
+
+
 def test_king_golden(gds, hapmap, goldens):         # test_rel.R:237-283
     samp = hapmap["sample_id"][:60]
     r = S.snpgdsIBDKING(gds, sample_id=samp, missing_rate=float("nan"), type="KING-robust")

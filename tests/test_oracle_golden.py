@@ -94,3 +94,28 @@ def test_synth_reproducible():
     assert set(np.unique(a)) <= {0, 1, 2, 3}
     frac_missing = (O.synth_geno(256, 2000, seed=3) == 3).mean()
     assert 0.003 < frac_missing < 0.007
+
+
+def _sign_free_rounded(got, gold, digits):
+    """the goldens are round(x, digits) of vectors whose sign LAPACK leaves free"""
+    tol = 0.5 * 10.0 ** (-digits) + 1e-9
+    a = np.nanmax(np.abs(got - gold))
+    b = np.nanmax(np.abs(-got - gold))
+    return min(a, b) <= tol and np.array_equal(np.isnan(got), np.isnan(gold))
+
+
+def test_pca_loadings_and_corr_golden(hapmap, goldens):          # test_rel.R:20-41,144-160
+    g, idx = hapmap_subset(hapmap, 90)
+    genmat, tr, _ = O.pca_genmat(g)
+    val, vec = O.pca_eigen(genmat, 8)
+    load, avg, scale = O.pca_snp_loading(g, val, vec, tr)
+    for k in range(8):
+        assert _sign_free_rounded(load[k], goldens["pca_snploading"][k], 3), k
+    g100 = np.ascontiguousarray(hapmap["geno"][:, :100][idx])     # snpgdsPCASampLoading(sample.id = first 100)
+    sload = load * np.sqrt(((90 - 1) / tr) / val[:8])[:, None]    # R/PCA.R:274-277
+    sl = O.pca_samp_loading(g100, sload, avg, scale)
+    for k in range(8):
+        assert _sign_free_rounded(sl[:, k], goldens["pca_samploading"][:, k], 4), k
+    corr = O.pca_corr(np.ascontiguousarray(hapmap["geno"][:, :90]), vec[:, :2])    # snp.id = NULL: all 9088 SNPs
+    for k in range(2):
+        assert _sign_free_rounded(corr[k], goldens["pca_corr"][k], 3), k

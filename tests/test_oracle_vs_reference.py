@@ -85,3 +85,28 @@ def test_reference_reproduces_its_own_goldens(hapmap, goldens):
     k0, k1, af = w.ibd_mom(2)
     assert np.max(np.abs(k0 - goldens["mom_k0"])) < 1e-14 and np.max(np.abs(k1 - goldens["mom_k1"])) < 1e-14
     assert np.array_equal(af, goldens["mom_afreq"])
+
+
+def test_loadings_projection_and_correlation(data):
+    """gnrPCASNPLoading / gnrPCASampLoading / gnrPCACorr / gnrEigMixSNPLoading / gnrEigMixSampLoading
+     with missing data, Bayesian scaling and 1 vs 3 threads."""
+    genmat, tr, _ = O.pca_genmat(data)
+    val, vec = O.pca_eigen(genmat, 6)
+    new = O.synth_geno(61, data.shape[0], seed=99, miss_rate=0.04, maf_lo=0.005)      # samples to project
+    w = R.RefWorkspace(data)
+    for bayes in (False, True):
+        load, avg, scale = O.pca_snp_loading(data, val, vec, tr, bayes)
+        rl, ra, rs = w.pca_snp_loading(val, vec, tr, bayes, nthread=1)
+        assert np.max(np.abs(rl - load)) < 1e-12 and np.array_equal(ra, avg) and np.max(np.abs(rs - scale)) < 1e-13
+        assert np.max(np.abs(w.pca_snp_loading(val, vec, tr, bayes, nthread=3)[0] - rl)) < 1e-13
+    corr, rc = O.pca_corr(data, vec[:, :3]), w.pca_corr(vec[:, :3])
+    assert np.array_equal(np.isnan(corr), np.isnan(rc)) and np.nanmax(np.abs(corr - rc)) < 1e-12
+    sload = load * np.sqrt(((data.shape[1] - 1) / tr) / val[:6])[:, None]
+    ibd, af = O.eigmix_ibd(data, diagadj=False)
+    ev, evec = O.pca_eigen(ibd, 5)
+    el = O.eigmix_snp_loading(data, ev, evec, af)
+    assert np.max(np.abs(w.eigmix_snp_loading(ev, evec, af) - el)) < 1e-13
+    w2 = R.RefWorkspace(new)
+    assert np.max(np.abs(w2.pca_samp_loading(sload, avg, scale) - O.pca_samp_loading(new, sload, avg, scale))) < 1e-11
+    esl = el * np.sqrt(1.0 / ev[:5])[:, None]
+    assert np.max(np.abs(w2.eigmix_samp_loading(esl, af) - O.eigmix_samp_loading(new, esl, af))) < 1e-12
