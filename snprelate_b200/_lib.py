@@ -93,6 +93,7 @@ def load_library():
         "snprel_invalidate": [p],
         "snprel_table_gram": [p, p, p, p],
         "snprel_debug_flags": [p, u32],
+        "snprel_set_count_engine": [p, i32],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -120,7 +121,7 @@ EXPORTED_SYMBOLS = [
     "snprel_eigmix_snp_loading", "snprel_eigmix_samp_loading", "snprel_plan_local", "snprel_accumulate",
     "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced", "snprel_last_plan", "snprel_set_row_window", "snprel_window_count", "snprel_mem_info",
     "snprel_kernel_launches", "snprel_last_hot_kernel", "snprel_time_accumulate", "snprel_last_step_ms", "snprel_invalidate",
-    "snprel_table_gram", "snprel_debug_flags",
+    "snprel_table_gram", "snprel_debug_flags", "snprel_set_count_engine",
 ]
 
 
@@ -540,6 +541,12 @@ class Context:
         out = np.empty((n, n), dtype=np.int64)
         self._ck(self.lib.snprel_table_gram(self.h, _ptr(tabA), _ptr(tabB), _ptr(out)))
         return out
+
+    def set_count_engine(self, engine):
+        """'bits' (default: packed-bit XOR/AND/popcount kernels) or 'tensor' (same exact counters
+        from the tensor pipe) for IBS / KING-robust / IndivBeta / PLINK-MoM."""
+        code = {"bits": 0, "tensor": 1}.get(engine, engine)
+        self._ck(self.lib.snprel_set_count_engine(self.h, int(code)))
 
     def debug_flags(self, flags):
         self._ck(self.lib.snprel_debug_flags(self.h, int(flags)))

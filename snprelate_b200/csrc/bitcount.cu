@@ -194,11 +194,26 @@ static void launch_pair_count(snprel_ctx *c) {
     KERNEL_CHECK(c);
 }
 
+static void finish_accumulate(snprel_ctx *c, int est) {
+    c->accum_win_r0 = row_window(c).r0;
+    c->accum_est = est;
+    c->accum_reduced = false;
+    c->reduce_list.clear();
+    c->reduce_list.push_back({c->cnt.p, (int64_t)c->cnt.n, 1});
+}
+
 void bitcount_accumulate(snprel_ctx *c, int est) {
-    ensure_planes(c);
-    int nc = est == SNPREL_EST_KING_ROBUST ? 5 : 3;
+    if (est != SNPREL_EST_IBS && est != SNPREL_EST_KING_ROBUST && est != SNPREL_EST_BETA)
+        fail("internal: bad packed-bit estimator %d", est);
     if (est == SNPREL_EST_KING_ROBUST && c->n_snp >= 1073741824ll)
         fail("The number of SNPs should be less than 1,073,741,824.");   // src/genKING.cpp:598
+    if (c->count_engine == 1) {   // same counters from the tensor pipe (grm.cu), opt-in
+        tensor_count_accumulate(c, est);
+        finish_accumulate(c, est);
+        return;
+    }
+    ensure_planes(c);
+    int nc = est == SNPREL_EST_KING_ROBUST ? 5 : 3;
     c->cnt.alloc((size_t)nc * row_window(c).rows * c->n_samp_pad);
     c->cnt_planes = nc;
     c->cnt.zero(c->stream);
@@ -216,11 +231,7 @@ void bitcount_accumulate(snprel_ctx *c, int est) {
     c->hot_ms = ms;
     c->hot_launches = 1;
     c->hot_units = 0.5 * (double)c->n_samp * (double)c->n_samp * (double)c->n_snp;
-    c->accum_win_r0 = row_window(c).r0;
-    c->accum_est = est;
-    c->accum_reduced = false;
-    c->reduce_list.clear();
-    c->reduce_list.push_back({c->cnt.p, (int64_t)c->cnt.n, 1});
+    finish_accumulate(c, est);
 }
 
 // ---------------------------------------------------------------------------

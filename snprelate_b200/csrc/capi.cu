@@ -384,6 +384,14 @@ int snprel_table_gram(snprel_ctx *c, const int8_t *tabA, const int8_t *tabB, int
     API_BEGIN(c) table_gram_debug(c, tabA, tabB, out);
     API_END(c)
 }
+int snprel_set_count_engine(snprel_ctx *c, int engine) {
+    API_BEGIN(c)
+    if (engine != 0 && engine != 1) fail("snprel_set_count_engine: 0 (packed-bit kernels) or 1 (tensor pipe)");
+    c->count_engine = engine;
+    c->accum_est = -1;
+    c->accum_reduced = false;
+    API_END(c)
+}
 int snprel_debug_flags(snprel_ctx *c, uint32_t flags) {
     API_BEGIN(c) c->debug_flags = flags;
     API_END(c)

@@ -170,6 +170,8 @@ struct snprel_ctx {
     snprel::DevBuf<int> scr_cnt;          // per-sample genotype sum / missing count [2][npad]
     snprel::DevBuf<double> scr_part;      // per-block float64 partial sums of the tables kernel
     snprel::DevBuf<double> scr_num, scr_out;   // epilogue scratch kept across row windows
+    snprel::DevBuf<uint32_t> scr_ctab;    // constant tables of the tensor count engine
+    int count_engine = 0;                 // 0: packed-bit pair kernels (default), 1: tensor pipe
     std::vector<int> host_cnt;
     std::vector<int2> host_tiles;
 
@@ -278,6 +280,7 @@ void eigmix_finish(snprel_ctx *c, int eigen_cnt, int diagadj, double *ibd, doubl
                    double *eigval, double *eigvec);
 void king_homo_finish(snprel_ctx *c, double *k0, double *k1, int packed);
 void table_gram_debug(snprel_ctx *c, const int8_t *tabA, const int8_t *tabB, int64_t *out);
+void tensor_count_accumulate(snprel_ctx *c, int est);
 
 
 // project.cu

@@ -222,6 +222,15 @@ static void need_ws(snprel_ctx *c, int k, const char *who) {
 // src[row * rs + col * cs] * colscale[col]
 static void upload_panel(snprel_ctx *c, DevBuf<double> &dev, const double *src, int64_t rows, int64_t rows_pad,
                          int k, int kp, int64_t rs, int64_t cs, const double *colscale) {
+    if (cs == 1 && rs == kp && k == kp && !colscale) {   // already in the device layout: no host staging
+        dev.alloc((size_t)rows_pad * kp);
+        if (rows_pad > rows)
+            CUDA_CHECK(cudaMemsetAsync(dev.p + (size_t)rows * kp, 0, (size_t)(rows_pad - rows) * kp * sizeof(double),
+                                       c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(dev.p, src, (size_t)rows * kp * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        return;
+    }
     std::vector<double> h((size_t)rows_pad * kp, 0.0);
     if (cs == 1) {   // source rows are contiguous (loadings [n_snp][k]): walk both sides linearly
         for (int64_t r = 0; r < rows; r++)

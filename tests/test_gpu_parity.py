@@ -243,6 +243,29 @@ def test_grm_files_merge(gds, hapmap, tmp_path):     # test_GRM.R:15-90 (GCTA an
 
 # ---------------------------------------------------------------- synthetic vs oracle
 
+@pytest.mark.parametrize("n,m,miss", [(300, 1000, 0.02), (513, 4099, 0.0), (70, 130, 0.3)])
+def test_tensor_count_engine_bit_identical(n, m, miss):
+    """The opt-in tensor-pipe engine (snprel_set_count_engine) reproduces the packed-bit kernels'
+    uint32 counters exactly, hence every estimator built on them, also inside row windows."""
+    g = O.synth_geno(n, m, seed=n, miss_rate=miss, maf_lo=0.01)
+    with S.Context(0) as c:
+        load(c, g)
+        c.set_count_engine("tensor")
+        assert np.array_equal(np.stack(c.ibs_num()), O.ibs_counts(g))
+        assert np.array_equal(c.king_robust_counts(), O.king_robust_counts(g))
+        tb = c.indiv_beta_counts()
+        ob = O.beta_counts(g)
+        assert np.array_equal(tb, ob)
+        t_ibs, t_king, t_beta = c.ibs_ave(packed=True), c.king_robust(packed=True), c.indiv_beta()[0]
+        if n > 256:
+            win = c.packed_by_windows(lambda: c.king_robust(packed=True), 256)
+            assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(win, t_king))
+        c.set_count_engine("bits")
+        assert np.array_equal(c.ibs_ave(packed=True), t_ibs, equal_nan=True)
+        assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(c.king_robust(packed=True), t_king))
+        assert np.array_equal(c.indiv_beta()[0], t_beta, equal_nan=True)
+
+
 @pytest.mark.parametrize("n,m,miss", [(4, 1, 0.0), (17, 33, 0.1), (130, 129, 0.0), (257, 1000, 0.02),
                                       (513, 777, 0.3), (1000, 4099, 0.005)])
 def test_counts_bit_exact(ctx, n, m, miss):

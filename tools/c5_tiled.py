@@ -5,7 +5,7 @@ runs exactly the share rank r of an 8-GPU job would run (same windows, same time
 8-GPU time can be measured at 1/8 of the GPU-minutes; under torchrun rank / world come from the
 environment and the job time is the max over ranks.
 
-    python tools/c5_tiled.py [--n 500000] [--m 800000] [--rows 2048] [--world 8] [--rank 0]
+    python tools/c5_tiled.py [--samples 500000] [--snps 800000] [--rows 2048] [--world 8] [--rank 0]
                              [--method GCTA] [--max-windows K]
 Prints one JSON line (rank 0).  Each window's packed slice is copied to a reused pinned host
 buffer (the D2H is inside the timed region); nothing is kept -- the full C5 output is 1 TB.
@@ -18,8 +18,8 @@ import snprelate_b200 as S
 from snprelate_b200._lib import window_owner
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=500000)
-ap.add_argument("--m", type=int, default=800000)
+ap.add_argument("--samples", dest="n", type=int, default=500000)
+ap.add_argument("--snps", dest="m", type=int, default=800000)
 ap.add_argument("--rows", type=int, default=2048)
 ap.add_argument("--world", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
 ap.add_argument("--rank", type=int, default=int(os.environ.get("RANK", "0")))
