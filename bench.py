@@ -261,11 +261,15 @@ def run_ours(args):
         return
 
     # ---- top-32 eigenvectors of the covariance (config 2; cuSOLVER, outside the metric) ----
-    eig_ms = None
+    eig_ms, eig_info = None, None
     if world == 1 and not args.no_eigen:
         t0 = time.perf_counter()
         ctx.pca(eigen_cnt=32)
         eig_ms = (time.perf_counter() - t0) * 1e3 - ms_per_step
+        es, er, eg = ctx.last_eigen_info()
+        eig_info = {"solver": "chebyshev-filtered subspace iteration (cuBLAS/cuSOLVER calls)" if es == 1
+                    else "dense cusolverDnXsyevd", "filter_rounds": er, "block_products": eg,
+                    "phase_ms": {k: round(v, 1) for k, v in ctx.eigen_phase_ms.items()}}
 
     pl = ctx.last_plan()
     passes = {"digits_U": int(pl.digits), "digits_W": int(pl.digits_w), "frac_bits": int(pl.frac_bits),
@@ -313,7 +317,7 @@ def run_ours(args):
         "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
         "roofline": roofline, "cpu_baseline": cpu,
         "clocks": sampler.summary() if sampler else None,
-        "eigen_top32_ms": eig_ms,
+        "eigen_top32_ms": eig_ms, "eigen_top32": eig_info,
     }
     print(json.dumps(out))
     if world > 1:

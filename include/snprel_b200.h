@@ -167,6 +167,17 @@ int snprel_pca(snprel_ctx *ctx, int eigen_cnt, int bayesian, double *genmat,
 int snprel_eigmix(snprel_ctx *ctx, int eigen_cnt, int diagadj, double *ibd,
                   double *afreq, double *eigval, double *eigvec);
 
+/* The eigen step of snprel_pca / snprel_eigmix (CalcEigen, LAPACK dspevx on -C,
+ * src/genPCA.cpp:1262-1346) runs in csrc/eigen.cu: a Chebyshev-filtered subspace iteration
+ * built from cuBLAS / cuSOLVER calls when eigen_cnt << n_samp (n_samp >= 2048, 8 eigen_cnt <=
+ * n_samp), otherwise (or if its residuals stall above 1e-10) a full cusolverDnXsyevd.  What the
+ * last solve did: solver 0 = dense, 1 = filtered subspace iteration; its filter rounds and the
+ * number of n x n by n x b block products; phase_ms[3] (nullable): milliseconds spent in the
+ * filter, the orthonormalisation and the Rayleigh-Ritz steps.  snprel_debug_flags bit 4 forces
+ * the dense solver. */
+int snprel_last_eigen_info(snprel_ctx *ctx, int *solver, int *rounds, int *block_gemms,
+                           double *phase_ms);
+
 /* ---- loadings, projection of new samples, SNP-PC correlation ----------
  * The tall-skinny float64 products either side of the eigen-decomposition
  * (csrc/project.cu).  Matrix layouts are the reference's R layouts: an

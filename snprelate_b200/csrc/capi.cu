@@ -78,6 +78,7 @@ void snprel_destroy(snprel_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    eigen_release(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->evs0) cudaEventDestroy(c->evs0);
@@ -382,6 +383,15 @@ int snprel_time_accumulate(snprel_ctx *c, int est, int reps, double *ms) {
 }
 int snprel_table_gram(snprel_ctx *c, const int8_t *tabA, const int8_t *tabB, int64_t *out) {
     API_BEGIN(c) table_gram_debug(c, tabA, tabB, out);
+    API_END(c)
+}
+int snprel_last_eigen_info(snprel_ctx *c, int *solver, int *rounds, int *block_gemms, double *phase_ms) {
+    API_BEGIN(c)
+    if (solver) *solver = c->eig_solver;
+    if (rounds) *rounds = c->eig_rounds;
+    if (block_gemms) *block_gemms = c->eig_gemms;
+    if (phase_ms)
+        for (int i = 0; i < 3; i++) phase_ms[i] = c->eig_phase_ms[i];
     API_END(c)
 }
 int snprel_set_count_engine(snprel_ctx *c, int engine) {

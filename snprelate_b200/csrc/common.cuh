@@ -190,6 +190,12 @@ struct snprel_ctx {
         bool reduced = false;   // the per-sample vectors / scalars already hold the all-reduced sums
     } prep_cache;
 
+    // eigen step (eigen.cu): persistent cuBLAS / cuSOLVER handles and what the last solve did
+    void *eig_handles = nullptr;
+    int eig_solver = 0;          // 0 dense (Xsyevd), 1 Chebyshev-filtered subspace iteration
+    int eig_rounds = 0, eig_gemms = 0;
+    double eig_phase_ms[3] = {0, 0, 0};   // filter, orthonormalisation, Rayleigh-Ritz
+
     // hot-kernel bookkeeping for bench.py
     double hot_ms = 0;
     int64_t hot_launches = 0;
@@ -281,6 +287,10 @@ void eigmix_finish(snprel_ctx *c, int eigen_cnt, int diagadj, double *ibd, doubl
 void king_homo_finish(snprel_ctx *c, double *k0, double *k1, int packed);
 void table_gram_debug(snprel_ctx *c, const int8_t *tabA, const int8_t *tabB, int64_t *out);
 void tensor_count_accumulate(snprel_ctx *c, int est);
+
+// eigen.cu
+void eigen_topk(snprel_ctx *c, const double *m_upper, int64_t n, int k, double *eigval, double *eigvec);
+void eigen_release(snprel_ctx *c);
 
 
 // project.cu

@@ -20,8 +20,6 @@
 // EIGMIX: sum 4p(1-p) over SNPs with i or j missing) use
 //     D_ij = r_i + r_j - sum_l d_l m_il m_jl,   r_i = sum_l d_l m_il,
 // i.e. one more table Gram (channel m on both sides) and a per-sample vector.
-#include <cusolverDn.h>
-
 #include <cmath>
 
 #include "common.cuh"
@@ -833,60 +831,6 @@ void grm_finish(snprel_ctx *c, int method, double *out, int packed) {
     }
     grm_device(c, method, packed, 0, method == SNPREL_GRM_EIGMIX ? 2.0 : 1.0, o, nullptr);
     d2h(c, out, o.p, win_out_count(c, packed));
-}
-
-// top-k eigenpairs of the symmetric matrix `m` (upper triangle valid), descending:
-// the reference runs LAPACK dspevx on -C and negates back (src/genPCA.cpp:1262-1346);
-// here cuSOLVER syevd on -C (a library call is fine for the O(N^3) eigen step).
-static void eigen_topk(snprel_ctx *c, const double *m_upper, int64_t n, int k, double *eigval,
-                       double *eigvec) {
-    if (k <= 0) return;
-    if (k > n) k = (int)n;
-    DevBuf<double> a, w;
-    a.alloc((size_t)n * n);
-    w.alloc((size_t)n);
-    symmetrize_neg_kernel<<<tri_grid(n), 128, 0, c->stream>>>(m_upper, a.p, -1.0, n);
-    KERNEL_CHECK(c);
-    cusolverDnHandle_t h;
-    if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) fail("cusolverDnCreate failed");
-    cusolverDnSetStream(h, c->stream);
-    // full divide-and-conquer decomposition (64-bit API, the routine torch.linalg.eigh uses:
-    // 1.8 s for n = 10 000 in float64 on B200) and keep the first k columns.  The legacy
-    // cusolverDnDsyevd took 26 s and syevdx with an index range 9-18 s for the same matrix.
-    DevBuf<int> info;
-    info.alloc(1);
-    cusolverDnParams_t params = nullptr;
-    cusolverDnCreateParams(&params);
-    size_t wdev = 0, whost = 0;
-    cusolverStatus_t st = cusolverDnXsyevd_bufferSize(h, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER,
-                                                     (int64_t)n, CUDA_R_64F, a.p, (int64_t)n, CUDA_R_64F, w.p,
-                                                     CUDA_R_64F, &wdev, &whost);
-    if (st != CUSOLVER_STATUS_SUCCESS) {
-        cusolverDnDestroyParams(params);
-        cusolverDnDestroy(h);
-        fail("cusolverDnXsyevd_bufferSize failed (%d)", (int)st);
-    }
-    DevBuf<uint8_t> work;
-    work.alloc(std::max<size_t>(wdev, 1));
-    std::vector<uint8_t> hwork(std::max<size_t>(whost, 1));
-    st = cusolverDnXsyevd(h, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int64_t)n, CUDA_R_64F, a.p,
-                          (int64_t)n, CUDA_R_64F, w.p, CUDA_R_64F, work.p, wdev, hwork.data(), whost, info.p);
-    cusolverDnDestroyParams(params);
-    int hinfo = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    cusolverDnDestroy(h);
-    if (st != CUSOLVER_STATUS_SUCCESS || hinfo != 0)
-        fail("eigen-decomposition error (%d), infinite or missing values in the genetic covariance matrix!",
-             hinfo);   // wording follows src/genPCA.cpp:1330-1334
-    std::vector<double> hw((size_t)n);
-    d2h(c, hw.data(), w.p, (size_t)n);
-    const double nan = __builtin_nan("");
-    if (eigval) {
-        for (int i = 0; i < k; i++) eigval[i] = -hw[i];
-        for (int64_t i = k; i < n; i++) eigval[i] = nan;   // src/genPCA.cpp:1339-1341
-    }
-    if (eigvec) d2h(c, eigvec, a.p, (size_t)n * k);
 }
 
 void pca_finish(snprel_ctx *c, int eigen_cnt, int bayesian, double *genmat, double *trace_xtx,

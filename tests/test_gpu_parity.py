@@ -166,6 +166,53 @@ def test_loadings_vs_oracle(ctx, n, m, k, miss):
         ctx.pca_corr(vec)           # 91 samples in the workspace, n rows in vec
 
 
+def _two_populations(n, m, seed):
+    """genotypes of two diverged populations (a few dominant eigenvalues on top of the noise bulk)"""
+    rng = np.random.default_rng(seed)
+    p0 = rng.uniform(0.1, 0.9, m)
+    pops = rng.integers(0, 3, n)
+    shift = rng.normal(0, 0.08, (3, m))
+    g = np.empty((m, n), dtype=np.uint8)
+    for q in range(3):
+        idx = np.nonzero(pops == q)[0]
+        p = np.clip(p0 + shift[q], 0.02, 0.98)
+        g[:, idx] = (rng.random((m, idx.size)) < p[:, None]).astype(np.uint8) + (rng.random((m, idx.size)) < p[:, None])
+    g[rng.random((m, n)) < 0.003] = 3
+    return g
+
+
+@pytest.mark.parametrize("structured", [True, False])
+def test_filtered_subspace_eigen_solver(ctx, structured):
+    """The Chebyshev-filtered subspace iteration of the eigen step (csrc/eigen.cu, n >= 2048) against
+    the dense cuSOLVER decomposition and the oracle: eigenvalues to 1e-9, eigenvectors to 1e-6 up to
+    sign (BASELINE tolerance) -- with population structure and on a structure-free matrix whose
+    wanted eigenvalues sit at the edge of the noise bulk."""
+    n, m, k = 2304, 6000, 16
+    g = _two_populations(n, m, 11) if structured else O.synth_geno(n, m, seed=21, miss_rate=0.002)
+    load(ctx, g)
+    r1 = ctx.pca(eigen_cnt=k, need_genmat=True)
+    solver, rounds, gemms = ctx.last_eigen_info()
+    assert solver == 1 and rounds >= 1 and gemms > 0, (solver, rounds, gemms)
+    ctx.debug_flags(4)                       # dense solver
+    try:
+        r0 = ctx.pca(eigen_cnt=k)
+        assert ctx.last_eigen_info()[0] == 0
+    finally:
+        ctx.debug_flags(0)
+    val, vec = O.pca_eigen(r1["genmat"], k)
+    assert np.max(np.abs(r1["eigenval"][:k] - val)) < 1e-9 * val[0]
+    assert np.max(np.abs(r0["eigenval"][:k] - val)) < 1e-9 * val[0]
+    assert np.all(np.isnan(r1["eigenval"][k:]))
+    for v1 in (r1["eigenvect"], r0["eigenvect"]):
+        # the defining property, independent of how close neighbouring eigenvalues are
+        assert np.max(np.abs(r1["genmat"] @ v1 - v1 * val[None, :])) < 1e-9 * val[0]
+        assert np.max(np.abs(v1.T @ v1 - np.eye(k))) < 1e-10
+    gaps = np.minimum(np.abs(np.diff(val, prepend=np.inf)), np.abs(np.diff(val, append=val[-1] - 1)))[: k - 1]
+    for i in np.nonzero(gaps > 1e-3 * val[0])[0]:      # isolated eigenvalues: the vectors themselves agree
+        d = min(np.max(np.abs(r1["eigenvect"][:, i] - vec[:, i])), np.max(np.abs(r1["eigenvect"][:, i] + vec[:, i])))
+        assert d < 1e-6, (i, d)
+
+
 def test_king_golden(gds, hapmap, goldens):         # test_rel.R:237-283
     samp = hapmap["sample_id"][:60]
     r = S.snpgdsIBDKING(gds, sample_id=samp, missing_rate=float("nan"), type="KING-robust")
