@@ -12,20 +12,32 @@ import os
 
 import numpy as np
 
-_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libsnprelate_ref.so")
-_LIB = None
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+_PATH = os.path.join(_DIR, "libsnprelate_ref.so")
+# the product's R binding (r_shim.cpp) behind the same driver functions, see oracle/Makefile
+RSHIM_PATH = os.path.join(_DIR, "libsnprelate_b200_rshim.so")
+_LIBS = {}
+_CURRENT = None
 
 
 def available() -> bool:
     return os.path.exists(_PATH)
 
 
+def rshim_available() -> bool:
+    return os.path.exists(RSHIM_PATH)
+
+
+def _load(path):
+    if path not in _LIBS:
+        lib = C.CDLL(path)
+        lib.ref_error.restype = C.c_char_p
+        _LIBS[path] = lib
+    return _LIBS[path]
+
+
 def _lib():
-    global _LIB
-    if _LIB is None:
-        _LIB = C.CDLL(_PATH)
-        _LIB.ref_error.restype = C.c_char_p
-    return _LIB
+    return _CURRENT if _CURRENT is not None else _load(_PATH)
 
 
 def _ck(rc):
@@ -41,7 +53,12 @@ class RefWorkspace:
     """Drives the reference like R does: set the genotype space, optionally
     gnrSelSNP_Base, then the gnr* estimators."""
 
-    def __init__(self, geno: np.ndarray):
+    def __init__(self, geno: np.ndarray, lib_path: str = None):
+        """lib_path: the shared library whose gnr* entry points are driven (default: the reference's
+        own sources; RSHIM_PATH: the product's R binding).  One library is current at a time, like
+        the process-global workspace it owns."""
+        global _CURRENT
+        _CURRENT = _load(lib_path or _PATH)
         g = np.ascontiguousarray(geno, dtype=np.uint8)
         self.nsnp, self.nsamp = g.shape
         _ck(_lib().ref_set_geno(_p(g), C.c_int(g.shape[0]), C.c_int(g.shape[1])))
