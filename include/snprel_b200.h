@@ -173,7 +173,7 @@ int snprel_eigmix(snprel_ctx *ctx, int eigen_cnt, int diagadj, double *ibd,
  * n_samp), otherwise (or if its residuals stall above 1e-10) a full cusolverDnXsyevd.  What the
  * last solve did: solver 0 = dense, 1 = filtered subspace iteration; its filter rounds and the
  * number of n x n by n x b block products; phase_ms[3] (nullable): milliseconds spent in the
- * filter, the orthonormalisation and the Rayleigh-Ritz steps.  snprel_debug_flags bit 4 forces
+ * filter, the orthonormalisation and the Rayleigh-Ritz steps.  snprel_debug_flags(ctx, 4) forces
  * the dense solver. */
 int snprel_last_eigen_info(snprel_ctx *ctx, int *solver, int *rounds, int *block_gemms,
                            double *phase_ms);
@@ -305,7 +305,8 @@ int snprel_invalidate(snprel_ctx *ctx);
  * (n_samp x n_samp row-major, all entries). */
 int snprel_table_gram(snprel_ctx *ctx, const int8_t *tabA /*[n_snp][4]*/,
                       const int8_t *tabB /*[4]*/, int64_t *out);
-/* Same product on the CUDA-core fp64 reference kernel (device cross-check). */
+/* Test hooks (OR of): 2 = one CTA pair walks the whole SNP range of a tile (no SNP splits),
+ * 4 = always use the dense eigen solver. */
 int snprel_debug_flags(snprel_ctx *ctx, uint32_t flags);
 
 #ifdef __cplusplus

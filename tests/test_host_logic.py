@@ -53,3 +53,35 @@ def test_family_codes():
     assert fam[1] == api.NA_INT and fam[3] == api.NA_INT
     with pytest.raises(S.SNPRelError, match="length"):
         api._family_codes(["x"], None, None, ws)
+
+
+def test_loading_and_correlation_argument_checks():
+    """snpgdsPCACorr / snpgdsPCASNPLoading / snpgdsPCASampLoading refuse malformed inputs before any
+    device call (R/PCA.R:99-303)."""
+    gds = _gds()
+    with pytest.raises(S.SNPRelError, match="pcaobj"):
+        S.snpgdsPCASNPLoading({"eigenvect": np.zeros((6, 2))}, gds)
+    with pytest.raises(S.SNPRelError, match="pcaobj"):
+        S.snpgdsPCACorr(np.zeros((6, 2)), gds)
+    with pytest.raises(S.SNPRelError, match="sample id"):
+        S.snpgdsPCACorr((None, np.zeros((6, 2))), gds)
+    pca = {"class": "snpgdsPCAClass", "sample.id": [f"s{i}" for i in range(6)], "snp.id": np.arange(1, 13),
+           "eigenval": None, "eigenvect": None}
+    with pytest.raises(S.SNPRelError, match="eigenvalues"):
+        S.snpgdsPCASNPLoading(pca, gds)
+    with pytest.raises(S.SNPRelError, match="outgds"):
+        S.snpgdsPCACorr(dict(pca, eigenvect=np.zeros((6, 2))), gds, outgds="x.gds")
+    with pytest.raises(S.SNPRelError, match="loadobj"):
+        S.snpgdsPCASampLoading({"class": "snpgdsPCAClass"}, gds)
+    # unknown sample ids are reported by the shared selection code before the device is touched
+    with pytest.raises(S.SNPRelError, match="Some of sample.id do not exist!"):
+        S.snpgdsPCACorr((["s0", "zz"], np.zeros((2, 1))), gds)
+
+
+def test_window_owner_is_a_permutation_per_round():
+    from snprelate_b200._lib import window_owner
+    for world in (1, 2, 5, 8):
+        for base in range(0, 6 * world, 2 * world):
+            fwd = [window_owner(base + i, world) for i in range(world)]
+            back = [window_owner(base + world + i, world) for i in range(world)]
+            assert fwd == list(range(world)) and back == list(range(world))[::-1]
