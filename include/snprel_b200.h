@@ -306,7 +306,8 @@ int snprel_invalidate(snprel_ctx *ctx);
 int snprel_table_gram(snprel_ctx *ctx, const int8_t *tabA /*[n_snp][4]*/,
                       const int8_t *tabB /*[4]*/, int64_t *out);
 /* Test hooks (OR of): 2 = one CTA pair walks the whole SNP range of a tile (no SNP splits),
- * 4 = always use the dense eigen solver. */
+ * 4 = always use the dense eigen solver, 8 = experimental: issue the tensor-pass launches of a
+ * step on two streams (they only meet in commutative atomics) so that wave tails overlap. */
 int snprel_debug_flags(snprel_ctx *ctx, uint32_t flags);
 
 #ifdef __cplusplus

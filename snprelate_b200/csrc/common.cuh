@@ -124,6 +124,8 @@ struct snprel_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs0 = nullptr, evs1 = nullptr;
+    cudaStream_t aux_stream[2] = {nullptr, nullptr};   // experimental concurrent pass launches (gram_tc.cu)
+    cudaEvent_t aux_event[2] = {nullptr, nullptr}, aux_fork = nullptr;
     std::string err;
     int64_t launches = 0;
     uint32_t debug_flags = 0;

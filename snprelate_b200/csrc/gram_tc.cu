@@ -470,6 +470,24 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
         c->gram_attr_done = true;
     }
 
+    // Experimental (snprel_debug_flags 8, off by default, not yet measured): the launches of one
+    // step only meet in the int64 planes through commutative 64-bit atomics, so they need no
+    // ordering among themselves; issued on alternating streams the first wave of launch k+1 can
+    // fill the SMs that the last, partial wave of launch k leaves idle (820 tiles on 74 CTA-pair
+    // slots = 11.08 waves).
+    const bool overlap = (c->debug_flags & 8u) != 0;
+    if (overlap && !c->aux_stream[0]) {
+        for (int k = 0; k < 2; k++) {
+            CUDA_CHECK(cudaStreamCreateWithFlags(&c->aux_stream[k], cudaStreamNonBlocking));
+            CUDA_CHECK(cudaEventCreateWithFlags(&c->aux_event[k], cudaEventDisableTiming));
+        }
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming));
+    }
+    if (overlap) {   // fork: the auxiliary streams start after everything queued on the main stream
+        CUDA_CHECK(cudaEventRecord(c->aux_fork, c->stream));
+        for (int k = 0; k < 2; k++) CUDA_CHECK(cudaStreamWaitEvent(c->aux_stream[k], c->aux_fork, 0));
+    }
+    int launch_no = 0;
     std::vector<char> used((size_t)npass, 0);
     for (int i = 0; i < npass; i++) {
         if (used[i]) continue;
@@ -494,19 +512,27 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
             np++;
         }
         P.npass = np;
+        cudaStream_t st = overlap ? c->aux_stream[launch_no & 1] : c->stream;
+        launch_no++;
         if (np == 2) {
             P.tiles = dtiles.p;
             P.stages_per_split = sps1;
             dim3 grid((unsigned)(2 * n1), (unsigned)splits1);
-            table_gram_kernel2<2, 1><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
+            table_gram_kernel2<2, 1><<<grid, THREADS, SMEM_BYTES, st>>>(P, tmap);
         } else {
             P.tiles = dtiles.p + n1;
             P.stages_per_split = sps2;
             dim3 grid((unsigned)(2 * n2), (unsigned)splits2);
-            table_gram_kernel2<1, 2><<<grid, THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
+            table_gram_kernel2<1, 2><<<grid, THREADS, SMEM_BYTES, st>>>(P, tmap);
         }
         KERNEL_CHECK(c);
         c->hot_launches++;
+    }
+    if (overlap) {   // join: the main stream continues after both auxiliary streams
+        for (int k = 0; k < 2; k++) {
+            CUDA_CHECK(cudaEventRecord(c->aux_event[k], c->aux_stream[k]));
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->aux_event[k], 0));
+        }
     }
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     int herr = 0;
