@@ -25,12 +25,20 @@ using namespace GWAS;
 
 namespace {
 
+// One device context per R process, created at the first estimator call and re-used: it is the
+// counterpart of the reference's process-global GWAS::MCWorkingGeno (src/dGenGWAS.cpp:2000) and
+// saves a CUDA stream / event / buffer set-up per .Call.  Every routine re-loads the SELECTED
+// genotypes, because gnrSetGenoSpace / gnrSelSNP_Base may have changed the selection in between.
 struct Ctx {
     snprel_ctx *h = nullptr;
     Ctx() {
-        if (snprel_create(&h, 0) != 0) throw ErrCoreArray("%s", snprel_last_error(nullptr));
+        static snprel_ctx *shared = nullptr;
+        if (!shared && snprel_create(&shared, 0) != 0) {
+            shared = nullptr;
+            throw ErrCoreArray("%s", snprel_last_error(nullptr));
+        }
+        h = shared;
     }
-    ~Ctx() { snprel_destroy(h); }
     void ck(int rc) {
         if (rc != 0) throw ErrCoreArray("%s", snprel_last_error(h));
     }
