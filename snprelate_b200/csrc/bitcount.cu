@@ -32,27 +32,45 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
-// the bit streams whose populations are the estimator's counters, for 32 SNPs of one pair
+// the bit streams whose populations are the estimator's counters, for 32 SNPs of one pair.
+// vb = validity of the column sample (b1 | ~b2), hb = its heterozygosity (b1 & ~b2): both depend on
+// the column word only and are computed once per word, outside the loop over the four row samples,
+// so that the pair's mask is ONE three-input LOP3, (a1 | ~a2) & vb.
+// one three-input logic op with an explicit truth table (index bit = a<<2 | b<<1 | c); spelled in
+// PTX because nvcc re-associates C-level boolean expressions into a form that needs 8.3 LOP3 per word
+// pair where 7 suffice (profiles/r01_pair_count_sass_mix.md)
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return r;
+}
+constexpr int TA = 0xF0, TB = 0xCC, TC = 0xAA;   // truth-table columns of the three inputs
+
 template <int EST>
 __device__ __forceinline__ void pair_streams(uint32_t (&st)[EstTraits<EST>::NC], uint32_t a1, uint32_t a2,
-                                             uint32_t b1, uint32_t b2) {
+                                             uint32_t b1, uint32_t b2, uint32_t vb, uint32_t hb) {
     // validity: a genotype is missing iff (plane1, plane2) == (0, 1)
-    uint32_t mask = (a1 | ~a2) & (b1 | ~b2);
-    uint32_t x1 = a1 ^ b1, x2 = a2 ^ b2;
+    const uint32_t mask = lop3<(TA | (~TB & 0xFF)) & TC>(a1, a2, vb);            // (a1 | ~a2) & vb
     if (EST == SNPREL_EST_IBS) {
-        st[0] = x1 & x2 & mask;        // ibs0: (0,0) vs (1,1)
-        st[1] = ~(x1 | x2) & mask;     // ibs2: identical
+        const uint32_t t = lop3<(TA ^ TB) & TC>(a1, b1, mask);                   // plane 1 differs, both valid
+        st[0] = lop3<TA & (TB ^ TC)>(t, a2, b2);                                 // ibs0: (0,0) vs (1,1)
+        const uint32_t u = lop3<(~(TA ^ TB) & 0xFF) & TC>(a1, b1, mask);         // plane 1 equal, both valid
+        st[1] = lop3<TA & (~(TB ^ TC) & 0xFF)>(u, a2, b2);                       // ibs2: identical
         st[2] = mask;
     } else if (EST == SNPREL_EST_KING_ROBUST) {
-        st[0] = x1 & x2 & mask;        // ibs0
-        st[1] = mask;                  // nLoci
-        st[2] = (x1 ^ x2) & mask;      // het: exactly one of the two is Aa
-        st[3] = a1 & ~a2 & mask;       // N1_Aa (row sample)
-        st[4] = b1 & ~b2 & mask;       // N2_Aa (column sample)
+        const uint32_t t = lop3<(TA ^ TB) & TC>(a1, b1, mask);
+        st[0] = lop3<TA & (TB ^ TC)>(t, a2, b2);                                 // ibs0
+        st[1] = mask;                                                            // nLoci
+        const uint32_t pa = lop3<TA ^ TB ^ TC>(a1, a2, b1);
+        st[2] = lop3<(TA ^ TB) & TC>(pa, b2, mask);                              // het: exactly one of the two is Aa
+        st[3] = lop3<TA & (~TB & 0xFF) & TC>(a1, a2, vb);                        // N1_Aa (row sample)
+        st[4] = lop3<TA & (TB | (~TC & 0xFF))>(hb, a1, a2);                      // N2_Aa (column sample)
     } else {
-        uint32_t het = (a1 ^ a2) | (b1 ^ b2);
-        st[0] = het & mask;            // either heterozygous
-        st[1] = ~(het | x1) & mask;    // same homozygote
+        const uint32_t h1 = lop3<(TA ^ TB) | TC>(a1, a2, hb);                    // either heterozygous
+        st[0] = h1 & mask;
+        const uint32_t v = mask & ~h1;
+        st[1] = lop3<TA & (~(TB ^ TC) & 0xFF)>(v, a1, b1);                       // same homozygote
         st[2] = mask;
     }
 }
@@ -64,17 +82,22 @@ __device__ __forceinline__ void pair_streams(uint32_t (&st)[EstTraits<EST>::NC],
 template <int EST>
 __device__ __forceinline__ void pair_update3(uint32_t (&acc)[EstTraits<EST>::NC], const uint32_t (&a1)[3],
                                              const uint32_t (&a2)[3], const uint32_t (&b1)[3],
-                                             const uint32_t (&b2)[3]) {
+                                             const uint32_t (&b2)[3], const uint32_t (&vb)[3],
+                                             const uint32_t (&hb)[3]) {
     constexpr int NC = EstTraits<EST>::NC;
     uint32_t s0[NC], s1[NC], s2[NC];
-    pair_streams<EST>(s0, a1[0], a2[0], b1[0], b2[0]);
-    pair_streams<EST>(s1, a1[1], a2[1], b1[1], b2[1]);
-    pair_streams<EST>(s2, a1[2], a2[2], b1[2], b2[2]);
+    pair_streams<EST>(s0, a1[0], a2[0], b1[0], b2[0], vb[0], hb[0]);
+    pair_streams<EST>(s1, a1[1], a2[1], b1[1], b2[1], vb[1], hb[1]);
+    pair_streams<EST>(s2, a1[2], a2[2], b1[2], b2[2], vb[2], hb[2]);
 #pragma unroll
     for (int k = 0; k < NC; k++) {
         uint32_t sum = s0[k] ^ s1[k] ^ s2[k];
         uint32_t carry = (s0[k] & s1[k]) | (s2[k] & (s0[k] ^ s1[k]));
-        acc[k] += __popc(sum) + 2 * __popc(carry);
+        // acc += pop(sum) + 2 pop(carry) as two IMADs: the FMA pipe is idle in this kernel while the
+        // ALU pipe (LOP3, IADD3) is the bound (profiles/r01_pair_count_sass_mix.md)
+        uint32_t t;
+        asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(t) : "r"((uint32_t)__popc(carry)), "r"(acc[k]));
+        asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(acc[k]) : "r"((uint32_t)__popc(sum)), "r"(t));
     }
 }
 
@@ -139,18 +162,22 @@ pair_count_kernel(const uint4 *__restrict__ planes, uint32_t *__restrict__ cnt, 
                 for (int k = 0; k < 3; k++) b[k] = sB[buf][w + k][tx + 16 * q];
                 {   // low 32 SNPs of the three words
                     const uint32_t b1[3] = {b[0].x, b[1].x, b[2].x}, b2[3] = {b[0].z, b[1].z, b[2].z};
+                    const uint32_t vb[3] = {b1[0] | ~b2[0], b1[1] | ~b2[1], b1[2] | ~b2[2]};
+                    const uint32_t hb[3] = {b1[0] & ~b2[0], b1[1] & ~b2[1], b1[2] & ~b2[2]};
 #pragma unroll
                     for (int r = 0; r < 4; r++) {
                         const uint32_t a1[3] = {a[r][0].x, a[r][1].x, a[r][2].x}, a2[3] = {a[r][0].z, a[r][1].z, a[r][2].z};
-                        pair_update3<EST>(acc[r][q], a1, a2, b1, b2);
+                        pair_update3<EST>(acc[r][q], a1, a2, b1, b2, vb, hb);
                     }
                 }
                 {   // high 32 SNPs
                     const uint32_t b1[3] = {b[0].y, b[1].y, b[2].y}, b2[3] = {b[0].w, b[1].w, b[2].w};
+                    const uint32_t vb[3] = {b1[0] | ~b2[0], b1[1] | ~b2[1], b1[2] | ~b2[2]};
+                    const uint32_t hb[3] = {b1[0] & ~b2[0], b1[1] & ~b2[1], b1[2] & ~b2[2]};
 #pragma unroll
                     for (int r = 0; r < 4; r++) {
                         const uint32_t a1[3] = {a[r][0].y, a[r][1].y, a[r][2].y}, a2[3] = {a[r][0].w, a[r][1].w, a[r][2].w};
-                        pair_update3<EST>(acc[r][q], a1, a2, b1, b2);
+                        pair_update3<EST>(acc[r][q], a1, a2, b1, b2, vb, hb);
                     }
                 }
             }
