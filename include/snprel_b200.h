@@ -167,6 +167,15 @@ int snprel_pca(snprel_ctx *ctx, int eigen_cnt, int bayesian, double *genmat,
 int snprel_eigmix(snprel_ctx *ctx, int eigen_cnt, int diagadj, double *ibd,
                   double *afreq, double *eigval, double *eigvec);
 
+/* Rounding of the fixed-point U table of the covariance estimators (EXPERIMENTAL, default 0).
+ * 0: round to nearest; the format is chosen from the worst-case error bound
+ *    2^-(frac_bits+1) * err_weight (proven <= tol for every entry).
+ * 1: unbiased randomised rounding, one draw per (SNP, genotype) table entry; the format is chosen
+ *    from the Hoeffding bound 2^-frac_bits * sqrt(err_weight * ln(2 #pairs / 1e-12)), which holds
+ *    for all entries simultaneously with probability 1 - 1e-12 over the draws and needs one digit
+ *    (tensor pass) less at config-2 size.  All ranks of a multi-GPU run must use the same mode. */
+int snprel_set_rounding(snprel_ctx *ctx, int mode);
+
 /* The eigen step of snprel_pca / snprel_eigmix (CalcEigen, LAPACK dspevx on -C,
  * src/genPCA.cpp:1262-1346) runs in csrc/eigen.cu: a Chebyshev-filtered subspace iteration
  * built from cuBLAS / cuSOLVER calls when eigen_cnt << n_samp (n_samp >= 2048, 8 eigen_cnt <=

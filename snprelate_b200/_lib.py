@@ -94,6 +94,7 @@ def load_library():
         "snprel_table_gram": [p, p, p, p],
         "snprel_debug_flags": [p, u32],
         "snprel_set_count_engine": [p, i32],
+        "snprel_set_rounding": [p, i32],
         "snprel_last_eigen_info": [p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(dbl)],
     }
     for name, args in sig.items():
@@ -122,7 +123,7 @@ EXPORTED_SYMBOLS = [
     "snprel_eigmix_snp_loading", "snprel_eigmix_samp_loading", "snprel_plan_local", "snprel_accumulate",
     "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced", "snprel_last_plan", "snprel_set_row_window", "snprel_window_count", "snprel_mem_info",
     "snprel_kernel_launches", "snprel_last_hot_kernel", "snprel_time_accumulate", "snprel_last_step_ms", "snprel_invalidate",
-    "snprel_table_gram", "snprel_debug_flags", "snprel_set_count_engine", "snprel_last_eigen_info",
+    "snprel_table_gram", "snprel_debug_flags", "snprel_set_count_engine", "snprel_last_eigen_info", "snprel_set_rounding",
 ]
 
 
@@ -551,6 +552,12 @@ class Context:
         self._ck(self.lib.snprel_last_eigen_info(self.h, C.byref(a), C.byref(b), C.byref(g), ph))
         self.eigen_phase_ms = {"filter": ph[0], "orthonormalise": ph[1], "rayleigh_ritz": ph[2]}
         return a.value, b.value, g.value
+
+    def set_rounding(self, mode):
+        """'nearest' (default, worst-case error bound) or 'random' (experimental: unbiased randomised
+        rounding of the U table + Hoeffding bound, one tensor pass fewer at config-2 size)."""
+        code = {"nearest": 0, "random": 1}.get(mode, mode)
+        self._ck(self.lib.snprel_set_rounding(self.h, int(code)))
 
     def set_count_engine(self, engine):
         """'bits' (default: packed-bit XOR/AND/popcount kernels) or 'tensor' (same exact counters

@@ -390,6 +390,14 @@ int snprel_table_gram(snprel_ctx *c, const int8_t *tabA, const int8_t *tabB, int
     API_BEGIN(c) table_gram_debug(c, tabA, tabB, out);
     API_END(c)
 }
+int snprel_set_rounding(snprel_ctx *c, int mode) {
+    API_BEGIN(c)
+    if (mode != 0 && mode != 1) fail("snprel_set_rounding: 0 (round to nearest, worst-case bound) or 1 (randomised, Hoeffding bound)");
+    c->round_mode = mode;
+    c->accum_est = -1;
+    c->accum_reduced = false;
+    API_END(c)
+}
 int snprel_last_eigen_info(snprel_ctx *c, int *solver, int *rounds, int *block_gemms, double *phase_ms) {
     API_BEGIN(c)
     if (solver) *solver = c->eig_solver;

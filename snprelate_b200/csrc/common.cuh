@@ -174,6 +174,7 @@ struct snprel_ctx {
     snprel::DevBuf<double> scr_num, scr_out;   // epilogue scratch kept across row windows
     snprel::DevBuf<uint32_t> scr_ctab;    // constant tables of the tensor count engine
     int count_engine = 0;                 // 0: packed-bit pair kernels (default), 1: tensor pipe
+    int round_mode = 0;                   // 0: round to nearest + worst-case bound (default), 1: randomised + Hoeffding
     std::vector<int> host_cnt;
     std::vector<int2> host_tiles;
 
@@ -188,7 +189,7 @@ struct snprel_ctx {
     } plan_cache;
     struct PrepCache {
         uint64_t version = 0;
-        int est = -1, bayesian = 0, f = 0, fw = 0, fd = 0, nU = 0, nW = 0, nD = 0, nD2 = 0;
+        int est = -1, bayesian = 0, f = 0, fw = 0, fd = 0, nU = 0, nW = 0, nD = 0, nD2 = 0, round_mode = 0;
         bool reduced = false;   // the per-sample vectors / scalars already hold the all-reduced sums
     } prep_cache;
 

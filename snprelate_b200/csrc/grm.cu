@@ -47,8 +47,22 @@ struct SnpTables {
 };
 
 // est: SNPREL_GRM_EIGENSTRAT / GCTA / CORR / EIGMIX, or SNPREL_EST_KING_HOMO
+// uniform [0, 1) draw of table entry (SNP l, genotype g): randomised rounding (snprel_set_rounding)
+__device__ __forceinline__ double dither_u01(uint64_t seed, long long l, int g) {
+    uint64_t x = seed ^ ((uint64_t)l * 4u + (uint64_t)g) * 0xD1342543DE82EF95ull;
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// dither != 0: the U table is rounded at random, floor(v 2^f + u) with u ~ U[0, 1) drawn per
+// (global SNP index snp_index, genotype) -- unbiased and independent across SNPs, which is what the
+// Hoeffding bound of choose_format relies on; 0: round to nearest (the default, worst-case bound)
 __device__ __forceinline__ void snp_tables(const SnpStat st, int est, int bayesian, int frac_bits,
-                                           int frac_bits_w, int frac_bits_d, SnpTables &t) {
+                                           int frac_bits_w, int frac_bits_d, SnpTables &t,
+                                           long long snp_index = 0, uint64_t dither = 0) {
     const double sc = exp2((double)frac_bits);
     const double scw = exp2((double)frac_bits_w);
     const double scd = exp2((double)frac_bits_d);
@@ -92,7 +106,7 @@ __device__ __forceinline__ void snp_tables(const SnpStat st, int est, int bayesi
     for (int g = 0; g < 3; g++) {
         double u = (est == SNPREL_EST_KING_HOMO) ? 0.0 : w * ((double)g - mu);
         double ww = mu * u;
-        t.qU[g] = llrint(u * sc);
+        t.qU[g] = dither ? (long long)floor(u * sc + dither_u01(dither, snp_index, g)) : llrint(u * sc);
         t.qW[g] = llrint(ww * scw);
         t.qWx[g] = llrint(ww * scx);
         t.maxU = fmax(t.maxU, fabs(u));
@@ -209,13 +223,13 @@ sample_count_kernel(const uint8_t *__restrict__ geno, int64_t n_snp, int64_t row
 __global__ void tables_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int64_t cap, int est,
                               int bayesian, int frac_bits, int frac_bits_w, int frac_bits_d, int nU, int nW, int nD, int nD2,
                               uint32_t *__restrict__ tab, double *__restrict__ scalars /*[gridDim.x][2] partials*/,
-                              long long *__restrict__ iscalars, int *__restrict__ overflow) {
+                              long long *__restrict__ iscalars, int *__restrict__ overflow, uint64_t dither) {
     int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double d = 0, d2 = 0;
     long long poly = 0;
     if (l < n_snp) {
         SnpTables t;
-        snp_tables(st[l], est, bayesian, frac_bits, frac_bits_w, frac_bits_d, t);
+        snp_tables(st[l], est, bayesian, frac_bits, frac_bits_w, frac_bits_d, t, (long long)l, dither);
         d = t.d;
         d2 = t.d2;
         poly = (est == SNPREL_GRM_GCTA || est == SNPREL_GRM_CORR) ? t.qD : 0;
@@ -426,7 +440,20 @@ void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
 // (n odd) one single launch that runs at ~0.8 of a double.
 static double launch_cost(int n) { return (n / 2) + (n % 2) * 0.8; }
 
-static void choose_format(int est, snprel_plan &plan, int &nU, int &nW, int &nD) {
+// round_mode 1 (snprel_set_rounding): the U table is rounded at random, so for a fixed pair (i, j)
+// the error sum_l e_l[g_il] x_jl is a sum of independent zero-mean terms of width x_jl 2^-f, and by
+// Hoeffding it exceeds 2^-f sqrt(1/2 sum_l x_jl^2 ln(2/delta)) with probability < delta; delta is
+// 1e-12 divided by the number of pairs (union bound) and sum x^2 <= 2 sum x = 2 err_weight.  This
+// replaces the worst-case 2^-(f+1) err_weight and saves one tensor pass per table at C2
+// (tools/fixed_point_model.py: actual error 1.8e-11, bound 6.5e-11 with U in 4 digits).
+static double u_table_error(const snprel_plan &plan, int fa, int round_mode, double n_samp) {
+    if (round_mode != 1) return std::ldexp(plan.err_weight, -(fa + 1));
+    const double pairs = std::max(1.0, 0.5 * n_samp * (n_samp + 1.0));
+    return std::ldexp(std::sqrt(0.5 * 2.0 * plan.err_weight * std::log(2.0 * pairs / 1e-12)), -fa);
+}
+
+static void choose_format(int est, snprel_plan &plan, int &nU, int &nW, int &nD, int round_mode = 0,
+                          double n_samp = 0) {
     const double tol = (plan.tol > 0 ? plan.tol : 1e-10) * 0.9;   // 10 % left for float64 rounding in the epilogue
     const bool homo = est == SNPREL_EST_KING_HOMO;
     const bool any_missing = plan.total_missing > 0;
@@ -457,7 +484,7 @@ static void choose_format(int est, snprel_plan &plan, int &nU, int &nW, int &nD)
             for (int a = 1; a <= MAX_DIGITS; a++) {
                 int fa = std::min(frac_cap(plan.max_abs, a), fmax);
                 if (fa < 8) continue;
-                double ea = std::ldexp(plan.err_weight, -(fa + 1));
+                double ea = u_table_error(plan, fa, round_mode, n_samp);
                 for (int b = any_missing ? 1 : 0; b <= (any_missing ? MAX_DIGITS : 0); b++) {
                     int fb = b ? std::min(frac_cap(plan.max_abs_w, b), fa) : fa;
                     if (b && fb < 8) continue;
@@ -510,7 +537,7 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     snprel_plan plan = *plan_in;
     const bool homo = est == SNPREL_EST_KING_HOMO;
     int nU = 0, nW = 0, nD = 0;
-    choose_format(est, plan, nU, nW, nD);
+    choose_format(est, plan, nU, nW, nD, c->round_mode, (double)c->n_samp);
     const int f = plan.frac_bits, fw = plan.frac_bits_w, fd = plan.frac_bits_d;
     int nD2 = homo ? nD : 0;
     const int npass = nU + nW + nD + nD2;
@@ -520,6 +547,7 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     // fixed-point format only, not on the row window: a tiled N x N run builds them once.
     snprel_ctx::PrepCache &pc = c->prep_cache;
     const bool prep_hit = pc.version == c->geno_version && pc.est == est && pc.bayesian == plan.bayesian &&
+                          pc.round_mode == c->round_mode &&
                           pc.f == f && pc.fw == fw && pc.fd == fd && pc.nU == nU && pc.nW == nW && pc.nD == nD &&
                           pc.nD2 == nD2 && c->scr_tab.p && c->samp_sum.p && c->scr_cnt.p;
     DevBuf<uint32_t> &tab = c->scr_tab;
@@ -540,8 +568,11 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
         const unsigned tblocks = (unsigned)((c->n_snp + 255) / 256);
         c->scr_part.alloc((size_t)std::max(tblocks, 1u) * 2);
         if (c->n_snp > 0) {
+            // (the draw is keyed by the LOCAL SNP index: shards of a multi-GPU run use different SNPs, so
+            //  different local indices on different ranks still give independent draws per SNP)
+            const uint64_t dither = (c->round_mode == 1 && !homo) ? (0xD17E5ull + (uint64_t)c->device * 0x9E3779B97F4A7C15ull) | 1ull : 0ull;
             tables_kernel<<<tblocks, 256, 0, c->stream>>>(c->stat.p, c->n_snp, cap, est, plan.bayesian, f, fw, fd, nU,
-                                                          nW, nD, nD2, tab.p, c->scr_part.p, c->iscalars.p, ovf.p);
+                                                          nW, nD, nD2, tab.p, c->scr_part.p, c->iscalars.p, ovf.p, dither);
             KERNEL_CHECK(c);
         }
         int hovf = 0;
@@ -580,6 +611,7 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
         pc.nW = nW;
         pc.nD = nD;
         pc.nD2 = nD2;
+        pc.round_mode = c->round_mode;
         pc.reduced = false;
     }
 

@@ -82,8 +82,12 @@ def table_gram(qtab3, nd, bvals):
     return big, ovf
 
 
-def run(name, T3, f, nT, Bv, D3, fw, nD, ew, maxmiss):
-    qT = np.rint(T3 * 2.0 ** f).astype(np.int64)
+def run(name, T3, f, nT, Bv, D3, fw, nD, ew, maxmiss, dither=False, s2=None):
+    if dither:   # unbiased randomised rounding, one draw per table entry: floor(v 2^f + u), u ~ U[0, 1)
+        rng = np.random.default_rng(7)
+        qT = np.floor(T3 * 2.0 ** f + rng.random(T3.shape)).astype(np.int64)
+    else:
+        qT = np.rint(T3 * 2.0 ** f).astype(np.int64)
     qD = np.rint(D3 * 2.0 ** fw).astype(np.int64)
     main, o1 = table_gram(qT, nT, Bv)
     corr, o2 = table_gram(qD, nD, mis)
@@ -91,6 +95,8 @@ def run(name, T3, f, nT, Bv, D3, fw, nD, ew, maxmiss):
     C = np.array(main, dtype=np.float64) / 2.0 ** f + np.array(corr, dtype=np.float64) / 2.0 ** fw - vecD[:, None]
     err = np.max(np.abs(C - Cref)) / scale
     bound = (2.0 ** -(f + 1) * ew + 2.0 ** -(fw + 1) * maxmiss) / scale
+    if dither:   # Hoeffding over the rounding draws, union bound over 1e4^2 pairs, failure probability 1e-12
+        bound = (2.0 ** -f * np.sqrt(0.5 * s2 * np.log(2 * 1e8 / 1e-12)) + 2.0 ** -(fw + 1) * maxmiss) / scale
     print(f"{name}: digits {nT}+{nD} (f={f}, fw={fw}) overflow={o1 or o2}  max |err|/scale = {err:.2e}   proven bound {bound:.2e}")
 
 
@@ -126,4 +132,9 @@ fD = int(np.floor(np.log2((127 * (256.0 ** 3 - 1) / 255 - 1) / np.max(np.abs(D3)
 print(f"   scheme B tables: s in [{s.min():.0f}, {s.max():.0f}], max|T| {np.max(np.abs(T3)):.3f}, max|D| {np.max(np.abs(D3)):.2e}, "
       f"err weight {ewB:.3g} (A: {ewA:.3g}), max missing {maxmiss:.0f}")
 run("B (proposed)", T3, fT, 5, Bv, D3, fD, 3, ewB, maxmiss)
+fU4 = int(np.floor(np.log2((127 * (256.0 ** 4 - 1) / 255 - 1) / np.max(np.abs(U)))))
+fT4 = int(np.floor(np.log2((127 * (256.0 ** 4 - 1) / 255 - 1) / np.max(np.abs(T3)))))
+print("   randomised rounding of the main table (probabilistic bound, failure probability 1e-12):")
+run("A', U 4 digits dithered", U, fU4, 4, x, W3, 28, 4, ewA, maxmiss, True, float(np.max((x * x).sum(axis=0))))
+run("B', T 4 digits dithered", T3, fT4, 4, Bv, D3, fD, 3, ewB, maxmiss, True, float(np.max((Bv * Bv).sum(axis=0))))
 print(f"   ({time.time() - t0:.0f} s)   target: 1e-10")
