@@ -136,7 +136,7 @@ int snprel_indiv_beta_counts(snprel_ctx *ctx, int32_t *out2);
 
 /* Engine of the pair counters above: 0 (default) = packed-bit XOR/AND/popcount kernels
  * (csrc/bitcount.cu, the reference's formulation); 1 = the same uint32 counters as exact
- * {-1,0,1}-table Grams on the tensor pipe (csrc/grm.cu:tensor_count_accumulate), bit-identical
+ * {-1,0,1}-table Grams on the tensor pipe (csrc/count_tc.cu:tensor_count_accumulate), bit-identical
  * and several times faster because the bit kernels are bound by the integer ALU. */
 int snprel_set_count_engine(snprel_ctx *ctx, int engine);
 

@@ -234,7 +234,7 @@ void bitcount_accumulate(snprel_ctx *c, int est) {
         fail("internal: bad packed-bit estimator %d", est);
     if (est == SNPREL_EST_KING_ROBUST && c->n_snp >= 1073741824ll)
         fail("The number of SNPs should be less than 1,073,741,824.");   // src/genKING.cpp:598
-    if (c->count_engine == 1) {   // same counters from the tensor pipe (grm.cu), opt-in
+    if (c->count_engine == 1) {   // same counters from the tensor pipe (count_tc.cu), opt-in
         tensor_count_accumulate(c, est);
         finish_accumulate(c, est);
         return;
