@@ -63,6 +63,14 @@ int snprel_geno_push_u8(snprel_ctx *ctx, const uint8_t *geno, int64_t cnt);
  * code 3 = missing; GDS dBit2 encoding) with `row_bytes` bytes per SNP row. */
 int snprel_geno_push_2b(snprel_ctx *ctx, const uint8_t *packed, int64_t cnt,
                         int64_t row_bytes);
+/* Append `cnt` SNPs straight from the payload of an uncompressed GDS dBit2 genotype node
+ * (sample.order layout): one continuous LSB-first 2-bit stream, sample fastest, with NO per-row
+ * padding, so rows are not byte aligned when n_samp % 4 != 0 (what CdSNPWorkSpace::snpRead
+ * decodes through gdsfmt, src/dGenGWAS.cpp:677-733).  `stream` points to the first byte of the
+ * payload, `first_genotype` = index (in genotypes) of the first genotype of the first SNP to push,
+ * i.e. first_snp * n_samp.  EXPERIMENTAL: written at the end of round 1, not yet run on a GPU. */
+int snprel_geno_push_bitstream(snprel_ctx *ctx, const uint8_t *stream,
+                               int64_t first_genotype, int64_t cnt);
 /* Fill the workspace with `n_snp` synthetic SNPs on the device (counter-based
  * generator; SNP l uses global index snp_start+l so SNP shards of one data
  * set can be generated independently).  Benchmark / test input only. */

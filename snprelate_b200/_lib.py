@@ -53,6 +53,7 @@ def load_library():
         "snprel_geno_begin": [p, i64, i64],
         "snprel_geno_push_u8": [p, p, i64],
         "snprel_geno_push_2b": [p, p, i64, i64],
+        "snprel_geno_push_bitstream": [p, p, i64, i64],
         "snprel_geno_synth": [p, i64, u64, dbl, dbl, dbl, i64],
         "snprel_geno_dim": [p, C.POINTER(i64), C.POINTER(i64)],
         "snprel_geno_copy_u8": [p, p],
@@ -115,7 +116,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "snprel_create", "snprel_destroy", "snprel_last_error", "snprel_version",
-    "snprel_geno_begin", "snprel_geno_push_u8", "snprel_geno_push_2b", "snprel_geno_synth",
+    "snprel_geno_begin", "snprel_geno_push_u8", "snprel_geno_push_2b", "snprel_geno_push_bitstream", "snprel_geno_synth",
     "snprel_geno_dim", "snprel_geno_copy_u8", "snprel_geno_copy_2b", "snprel_snp_ratefreq", "snprel_select_snp_base", "snprel_select_snp_base_ex",
     "snprel_ibs_num", "snprel_ibs_ave", "snprel_ibd_mom", "snprel_ibd_mom_sums", "snprel_ibd_mom_from_sums", "snprel_king_robust", "snprel_king_robust_counts",
     "snprel_king_homo", "snprel_indiv_beta", "snprel_indiv_beta_counts", "snprel_grm",
@@ -187,6 +188,14 @@ class Context:
     def geno_push_2b(self, packed):
         packed = np.ascontiguousarray(packed, dtype=np.uint8)
         self._ck(self.lib.snprel_geno_push_2b(self.h, _ptr(packed), packed.shape[0], packed.shape[1]))
+
+    def geno_push_bitstream(self, stream, first_snp, cnt):
+        """GDS dBit2 payload (continuous 2-bit stream, no row padding) -> `cnt` SNPs from `first_snp`."""
+        stream = np.ascontiguousarray(stream, dtype=np.uint8).reshape(-1)
+        n, _ = self.geno_dim()
+        if (int(first_snp) + int(cnt)) * n * 2 > stream.size * 8:
+            raise SNPRelError("geno_push_bitstream: the stream is shorter than the requested SNP range")
+        self._ck(self.lib.snprel_geno_push_bitstream(self.h, _ptr(stream), int(first_snp) * n, int(cnt)))
 
     def geno_synth(self, n_snp, seed=20261017, maf_lo=0.05, maf_hi=0.5, miss_rate=0.005, snp_start=0):
         self._ck(self.lib.snprel_geno_synth(self.h, int(n_snp), int(seed), float(maf_lo), float(maf_hi),

@@ -107,6 +107,10 @@ int snprel_geno_push_2b(snprel_ctx *c, const uint8_t *packed, int64_t cnt, int64
     API_BEGIN(c) geno_push_2b(c, packed, cnt, row_bytes);
     API_END(c)
 }
+int snprel_geno_push_bitstream(snprel_ctx *c, const uint8_t *stream, int64_t first_genotype, int64_t cnt) {
+    API_BEGIN(c) geno_push_bitstream(c, stream, first_genotype, cnt);
+    API_END(c)
+}
 int snprel_geno_synth(snprel_ctx *c, int64_t n_snp, uint64_t seed, double maf_lo, double maf_hi,
                       double miss_rate, int64_t snp_start) {
     API_BEGIN(c) geno_synth(c, n_snp, seed, maf_lo, maf_hi, miss_rate, snp_start);

@@ -246,6 +246,7 @@ inline size_t window_packed_count(const snprel_ctx *c) {
 void geno_begin(snprel_ctx *c, int64_t n_samp, int64_t cap);
 void geno_push_u8(snprel_ctx *c, const uint8_t *host, int64_t cnt);
 void geno_push_2b(snprel_ctx *c, const uint8_t *host, int64_t cnt, int64_t row_bytes);
+void geno_push_bitstream(snprel_ctx *c, const uint8_t *host, int64_t first_genotype, int64_t cnt);
 void geno_synth(snprel_ctx *c, int64_t n_snp, uint64_t seed, double maf_lo, double maf_hi,
                 double miss_rate, int64_t snp_start);
 void geno_copy_u8(snprel_ctx *c, uint8_t *out);

@@ -265,6 +265,53 @@ void geno_push_2b(snprel_ctx *c, const uint8_t *host, int64_t cnt, int64_t row_b
     invalidate(c);
 }
 
+// GDS dBit2 payload (uncompressed genotype node of a SNP GDS file with sample.order): ONE continuous
+// LSB-first 2-bit stream, sample fastest, with no per-row padding -- rows are not byte aligned when
+// n_samp is not a multiple of 4.  Repack to the padded device rows.
+__global__ void repack_bits_kernel(const uint8_t *__restrict__ stream, int64_t bit0, uint8_t *__restrict__ dst,
+                                   int64_t cnt, int64_t n_samp, int64_t row_bytes) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cnt * row_bytes) return;
+    int64_t r = idx / row_bytes, b = idx - r * row_bytes;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int64_t i = b * 4 + k;
+        uint32_t g = 3;
+        if (i < n_samp) {
+            int64_t pos = bit0 + (r * n_samp + i) * 2;     // even: a genotype never straddles a byte
+            g = (stream[pos >> 3] >> (pos & 7)) & 3u;
+        }
+        out |= g << (2 * k);
+    }
+    dst[idx] = (uint8_t)out;
+}
+
+void geno_push_bitstream(snprel_ctx *c, const uint8_t *host, int64_t first_genotype, int64_t cnt) {
+    need_room(c, cnt, "snprel_geno_push_bitstream");
+    if (cnt == 0) return;
+    if (!host) fail("snprel_geno_push_bitstream: NULL stream");
+    if (first_genotype < 0) fail("snprel_geno_push_bitstream: negative offset");
+    // stage the covering byte range of a bounded number of rows at a time
+    const int64_t max_rows = std::max<int64_t>(1, (int64_t)(256ll << 20) * 4 / c->n_samp);
+    for (int64_t done = 0; done < cnt; done += max_rows) {
+        const int64_t rows = std::min(max_rows, cnt - done);
+        const int64_t g0 = first_genotype + done * c->n_samp;          // first genotype of this chunk
+        const int64_t byte0 = g0 / 4, byte1 = (g0 + rows * c->n_samp + 3) / 4;
+        c->stage_u8.alloc((size_t)(byte1 - byte0));
+        CUDA_CHECK(cudaMemcpyAsync(c->stage_u8.p, host + byte0, (size_t)(byte1 - byte0), cudaMemcpyHostToDevice,
+                                   c->stream));
+        const int64_t total = rows * c->row_bytes;
+        repack_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(
+            c->stage_u8.p, (g0 - byte0 * 4) * 2, c->geno2b.p + (c->n_snp + done) * c->row_bytes, rows, c->n_samp,
+            c->row_bytes);
+        KERNEL_CHECK(c);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));   // staging buffer is reused
+    }
+    c->n_snp += cnt;
+    invalidate(c);
+}
+
 void geno_synth(snprel_ctx *c, int64_t n_snp, uint64_t seed, double maf_lo, double maf_hi,
                 double miss_rate, int64_t snp_start) {
     need_room(c, n_snp, "snprel_geno_synth");

@@ -74,3 +74,17 @@ def test_two_stream_launches_are_bit_identical():
         c.invalidate()
         e0, _ = c.grm("EIGMIX")
         assert np.array_equal(a, b) and np.array_equal(e, e0)
+
+
+def test_gds_bitstream_ingest(hapmap):
+    """The fixture's genotype node is a continuous dBit2 stream of 279-sample rows (279 % 4 = 3)."""
+    g = hapmap["geno"]                                  # [9088, 279] codes 0..3
+    flat = g.reshape(-1).astype(np.uint8)
+    pad = (-flat.size) % 4
+    q = np.concatenate([flat, np.zeros(pad, np.uint8)]).reshape(-1, 4)
+    stream = (q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).astype(np.uint8)
+    with S.Context(0) as c:
+        c.geno_begin(g.shape[1], g.shape[0])
+        c.geno_push_bitstream(stream, 0, 5000)
+        c.geno_push_bitstream(stream, 5000, g.shape[0] - 5000)      # second chunk starts mid-byte
+        assert np.array_equal(c.geno_copy_u8(), g)
