@@ -33,8 +33,13 @@ N_SAMP = 10000
 N_SNP = 1000000
 MISS = 0.005
 SEED = 20261017
-# bounded CPU sample of the same workload (same generator, same MAF / missing rate)
-CPU_N, CPU_M = 2048, 16384
+# bounded CPU sample of the same workload (same generator, same MAF / missing rate): the
+# cpu_baseline leg of our own line times CPU_N x CPU_M once; the reference arm (--impl reference)
+# times REF_N samples x up to REF_M SNPs per step (N=4096, M=65536), with M
+# cut back so that the K timed steps fit REF_BUDGET_S seconds -- the size really run is what the line's
+# config reports
+CPU_N, CPU_M = 4096, 16384
+REF_N, REF_M, REF_M_MIN, REF_BUDGET_S = 4096, 65536, 8192, 150.0
 
 
 def peaks():
@@ -110,25 +115,35 @@ def run_reference(args):
         return
     from oracle import ref_lib as R
     threads = os.cpu_count() or 1
-    kind = "reference" if R.available() else "unavailable"
-    if kind == "unavailable":
+    if not R.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsnprelate_ref.so not built"}))
         return
-    for _ in range(args.warmup):
-        cpu_reference_rate(threads, 1024, 4096)
+    # warm-up steps (thread pool, page cache) on a small block; the last one calibrates the rate
+    rate = None
+    for _ in range(max(args.warmup, 1)):
+        rate, _ = cpu_reference_rate(threads, REF_N, REF_M_MIN)
+    per_step_budget = REF_BUDGET_S / max(args.steps, 1)
+    m = int(rate * per_step_budget / (0.5 * REF_N * REF_N)) // 4096 * 4096
+    m = max(REF_M_MIN, min(REF_M, m))
     times = []
     for _ in range(args.steps):
-        rate, dt = cpu_reference_rate(threads)
+        _, dt = cpu_reference_rate(threads, REF_N, m)
         times.append(dt)
     dt = sum(times) / len(times)
-    value = 0.5 * CPU_N * CPU_N * CPU_M / dt
+    value = 0.5 * REF_N * REF_N * m / dt
     sample = (f"reference src/genPCA.cpp CExactPCA (gnrPCA genmat.only) compiled -O3 -march=x86-64-v3, "
-              f"{threads} threads, {CPU_N} samples x {CPU_M} SNPs of the same synthetic generator")
+              f"{threads} threads, {REF_N} samples x {m} SNPs of the same synthetic generator per step "
+              f"(BASELINE.md section 3 size {REF_N} x {REF_M}, SNP count cut to fit {REF_BUDGET_S:.0f} s for {args.steps} steps)")
+    cfg = workload_config(args.gpus)
+    cfg.update({"workload": f"snpgdsPCA covariance (Eigenstrat), CPU sample of the synthetic workload: {REF_N} samples x {m} SNPs, "
+                            f"2-bit source data, missing rate {MISS}, MAF U(0.05,0.5)",
+                "n_samp": REF_N, "n_snp_per_gpu": m, "n_snp_total": m, "sharding": "host threads (reference pthread pool)",
+                "l2": "n/a (CPU)", "full_workload": f"{N_SAMP} samples x {N_SNP} SNPs per GPU (infeasible on the CPU: rate-vs-rate comparison)"})
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -185,6 +200,8 @@ def run_ours(args):
         ev1.record()
         torch.cuda.synchronize()
         ms += ev0.elapsed_time(ev1)
+        ctx.mark_reduced()
+        ms += ctx.time_finish(est)     # int64 planes -> final float64 matrix ("final N x N complete")
         return ms
 
     for _ in range(args.warmup):
@@ -225,6 +242,7 @@ def run_ours(args):
 
     e2e_parts = {"geno_begin": 0.0, "push_2b": 0.0, "accumulate_allreduce": 0.0, "pca_finish_d2h": 0.0}
     hg, ho = host_geno.numpy(), host_out.numpy()
+    e2e_last = {}
 
     def e2e_step():
         ta = time.perf_counter()
@@ -235,7 +253,7 @@ def run_ours(args):
         if world > 1:
             D.accumulate_sharded(ctx, est, device=dev)
         td = time.perf_counter()
-        ctx.pca(genmat_only=True, genmat_out=ho)
+        e2e_last.update(ctx.pca(genmat_only=True, genmat_out=ho))
         te = time.perf_counter()
         for k, v in zip(e2e_parts, (tb - ta, tc - tb, td - tc, te - td)):
             e2e_parts[k] += v * 1e3
@@ -255,6 +273,26 @@ def run_ours(args):
     e2e_s = float(t[0])
     e2e_value = pair_snps_per_step / e2e_s
 
+    # ---- parity of the FINISHED matrix (after the all-reduce at N > 1): entries at scattered sample
+    # indices spanning the first, a middle and the last tile row against the oracle evaluated on those
+    # samples' columns.  Every rank restates its own SNP shard on the CPU; the partial sums are added.
+    from oracle import snprel_oracle as O          # checker only: never on the timed path
+    PAR_K = 64
+    idx = O.scattered_samples(N_SAMP, PAR_K, seed=5)
+    sub = O.synth_geno(0, N_SNP, seed=SEED, miss_rate=MISS, snp_start=rank * N_SNP, samples=idx)
+    af, _, _ = ctx.snp_ratefreq()                   # this shard's all-sample allele frequencies (device statistics)
+    cov = torch.from_numpy(O.subset_entries(sub, af, "cov")).to(dev)
+    if world > 1:
+        tdist.all_reduce(cov, op=tdist.ReduceOp.SUM)
+    ref = cov.cpu().numpy() * ((N_SAMP - 1) / e2e_last["TraceXTX"])
+    got = ho[np.ix_(idx, idx)]
+    perr = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)))
+    sym = bool(np.array_equal(got, got.T))
+    parity = {"checked": int(got.size), "samples": int(PAR_K), "max_rel_err": perr, "tol": 1e-10,
+              "symmetric": sym, "ok": bool(perr < 1e-10 and sym),
+              "what": "genmat entries of the last end-to-end step (all-reduced at N > 1) at 64 scattered samples "
+                      "(first / middle / last 256-sample tile rows) vs oracle on those samples' columns of every shard"}
+
     if rank != 0:
         if world > 1:
             tdist.destroy_process_group()
@@ -263,13 +301,22 @@ def run_ours(args):
     # ---- top-32 eigenvectors of the covariance (config 2; cuSOLVER, outside the metric) ----
     eig_ms, eig_info = None, None
     if world == 1 and not args.no_eigen:
-        t0 = time.perf_counter()
-        ctx.pca(eigen_cnt=32)
-        eig_ms = (time.perf_counter() - t0) * 1e3 - ms_per_step
+        eig_calls = []
+        for _ in range(2):          # the first call pays the cuSOLVER / cuBLAS initialisation
+            t0 = time.perf_counter()
+            r = ctx.pca(eigen_cnt=32)
+            eig_calls.append((time.perf_counter() - t0) * 1e3 - ms_per_step)   # pca() re-runs the accumulation
+        eig_ms = eig_calls[1]
         es, er, eg = ctx.last_eigen_info()
+        # a-posteriori check against the covariance the e2e leg returned: residual and orthonormality
+        V, lam = np.ascontiguousarray(r["eigenvect"]), r["eigenval"][:32]
+        resid = float(np.max(np.linalg.norm(ho @ V - V * lam[None, :], axis=0)) / abs(lam[0]))
+        ortho = float(np.max(np.abs(V.T @ V - np.eye(V.shape[1]))))
         eig_info = {"solver": "chebyshev-filtered subspace iteration (cuBLAS/cuSOLVER calls)" if es == 1
                     else "dense cusolverDnXsyevd", "filter_rounds": er, "block_products": eg,
-                    "phase_ms": {k: round(v, 1) for k, v in ctx.eigen_phase_ms.items()}}
+                    "phase_ms": {k: round(v, 1) for k, v in ctx.eigen_phase_ms.items()},
+                    "first_call_ms": eig_calls[0], "warm_call_ms": eig_calls[1],
+                    "max_residual_over_lambda1": resid, "max_orthonormality_defect": ortho}
 
     pl = ctx.last_plan()
     passes = {"digits_U": int(pl.digits), "digits_W": int(pl.digits_w), "frac_bits": int(pl.frac_bits),
@@ -315,13 +362,15 @@ def run_ours(args):
                 "call": "snprel_geno_begin + snprel_geno_push_2b (pinned host 2-bit rows) + snprel_pca (genmat to host)",
                 "ms_per_step": e2e_s * 1e3, "ms_parts": e2e_parts},
         "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
-        "roofline": roofline, "cpu_baseline": cpu,
+        "parity": parity, "roofline": roofline, "cpu_baseline": cpu,
         "clocks": sampler.summary() if sampler else None,
         "eigen_top32_ms": eig_ms, "eigen_top32": eig_info,
     }
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
     if world > 1:
         tdist.destroy_process_group()
+    if not parity["ok"]:
+        raise SystemExit(3)
 
 
 def main():

@@ -312,6 +312,13 @@ int snprel_last_hot_kernel(snprel_ctx *ctx, double *ms, int64_t *launches,
  * the average device time per repetition in ms, measured with CUDA events on the
  * library's stream (bench.py `value`). */
 int snprel_time_accumulate(snprel_ctx *ctx, int estimator, int reps, double *ms);
+/* Covariance estimators: run the device epilogue (int64 planes -> final float64 matrix,
+ * left on the device) for the accumulators at hand -- after snprel_accumulate, or after the
+ * all-reduce + snprel_mark_reduced of a sharded run -- and return its device time in ms (also
+ * added to snprel_last_step_ms).  snprel_time_accumulate includes it: the metric runs up to
+ * "final N x N complete" (the reference's gnrGRM / gnrPCA end with the same normalisation loop,
+ * src/genPCA.cpp:1381-1390, :1233-1236). */
+int snprel_time_finish(snprel_ctx *ctx, int estimator, double *ms);
 /* Device time (ms, CUDA events) of the last snprel_plan_local + snprel_accumulate pair. */
 int snprel_last_step_ms(snprel_ctx *ctx, double *ms);
 /* Drop everything derived from the resident 2-bit matrix (per-SNP statistics, bit

@@ -587,6 +587,47 @@ def merge_grm_indivbeta(grms, avg_vals, weights):
 
 
 # ---------------------------------------------------------------------------
+# Entries of the covariance-type matrices for a SUBSET of the samples, given the per-SNP
+# statistics over ALL samples (full-size parity checks: the sub-matrix of scattered samples
+# costs O(k^2 M) instead of O(N^2 M)).  Same formulas as cov_eigenstrat / grm_gcta above.
+# ---------------------------------------------------------------------------
+def subset_entries(sub, afreq, method="GCTA", n_total=None, trace=None):
+    """sub: uint8 [nsnp, k] genotypes of k samples of a larger data set; afreq: [nsnp]
+    allele frequency of every SNP over ALL samples (sum / (2 num), src/genPCA.cpp:84-142).
+    GCTA: G_ij = sum_l z_il z_jl / (2 (nLocus - Denom_ij)) (src/genPCA.cpp:1201-1236);
+    Eigenstrat: cov_ij (n_total - 1) / trace with the all-sample trace (src/genPCA.cpp:1381-1390)."""
+    af = np.asarray(afreq, dtype=np.float64)
+    mu = 2.0 * af
+    poly = (af > 0) & (af < 1)
+    w = np.where(poly, 1.0 / np.where(poly, af * (1 - af), 1.0), 0.0)
+    valid = sub <= 2
+    z = np.where(valid, (sub - mu[:, None]) * np.sqrt(w)[:, None], 0.0)
+    cov = _zzt(z.T.copy()) if z.shape[1] > 64 else z.T @ z
+    if method == "cov":              # un-normalised Z Z^T: shards of a multi-GPU run add these
+        return cov
+    if method == "Eigenstrat":
+        return cov * ((n_total - 1) / trace)
+    if method != "GCTA":
+        raise ValueError(method)
+    mm = (~valid).astype(np.float64)
+    miss = mm * poly[:, None]
+    den = miss.sum(0)[:, None] + miss.sum(0)[None, :] - miss.T @ mm
+    return cov / (2.0 * (poly.sum() - den))
+
+
+def scattered_samples(n, k, seed=1):
+    """k distinct sample indices spanning the first, a middle and the last 256-sample tile row
+    (plus the very first and last sample), sorted."""
+    rng = np.random.default_rng(seed)
+    pick = {0, n - 1}
+    zones = [(0, min(256, n)), (max(0, n // 2 - 128), min(n, n // 2 + 128)), (max(0, n - 256), n)]
+    while len(pick) < min(k, n):
+        lo, hi = zones[len(pick) % 3] if len(pick) < k - k // 4 else (0, n)
+        pick.add(int(rng.integers(lo, hi)))
+    return np.array(sorted(pick), dtype=np.int64)
+
+
+# ---------------------------------------------------------------------------
 # Synthetic genotypes (SURVEY.md section 8d): counter-based, any shard is
 # reproducible without communication.  The CUDA generator uses the same mixer.
 # ---------------------------------------------------------------------------
@@ -603,10 +644,13 @@ def _splitmix64(x):
 
 
 def synth_geno(nsamp, nsnp, seed=20261017, maf_lo=0.05, maf_hi=0.5,
-               miss_rate=0.005, snp_start=0):
+               miss_rate=0.005, snp_start=0, samples=None):
     """uint8 [nsnp, nsamp] with p_l ~ U(maf_lo, maf_hi), g ~ Binomial(2, p_l),
     missing (code 3) with probability miss_rate.  Bit-identical to the device
-    generator in snprelate_b200/csrc (same 64-bit mixer, same thresholds)."""
+    generator in snprelate_b200/csrc (same 64-bit mixer, same thresholds).
+    `samples`: optional array of sample indices -- only those columns of the
+    (arbitrarily large) data set are generated, in the given order (the generator is
+    counter-based per (SNP, sample), so scattered samples cost nothing)."""
     with np.errstate(over="ignore"):
         l = (np.arange(nsnp, dtype=np.uint64) + np.uint64(snp_start))
         seed = np.uint64(seed)
@@ -618,7 +662,7 @@ def synth_geno(nsamp, nsnp, seed=20261017, maf_lo=0.05, maf_hi=0.5,
         th0 = np.minimum(np.floor(t0 * 4294967296.0), 4294967295.0).astype(np.uint64)
         th1 = np.minimum(np.floor(t1 * 4294967296.0), 4294967295.0).astype(np.uint64)
         thm = np.uint64(min(int(miss_rate * 4294967296.0), 4294967295))
-        i = np.arange(nsamp, dtype=np.uint64)
+        i = np.arange(nsamp, dtype=np.uint64) if samples is None else np.asarray(samples, dtype=np.uint64)
         key = _splitmix64((hp[:, None] + i[None, :] * np.uint64(0x9E3779B97F4A7C15)) & _M64)
         r = key >> np.uint64(32)
         rm = key & np.uint64(0xFFFFFFFF)

@@ -90,6 +90,7 @@ def load_library():
         "snprel_mem_info": [p, C.POINTER(i64), C.POINTER(i64)],
         "snprel_last_hot_kernel": [p, C.POINTER(dbl), C.POINTER(i64), C.POINTER(dbl)],
         "snprel_time_accumulate": [p, i32, i32, C.POINTER(dbl)],
+        "snprel_time_finish": [p, i32, C.POINTER(dbl)],
         "snprel_last_step_ms": [p, C.POINTER(dbl)],
         "snprel_invalidate": [p],
         "snprel_table_gram": [p, p, p, p],
@@ -123,7 +124,7 @@ EXPORTED_SYMBOLS = [
     "snprel_pca", "snprel_eigmix", "snprel_pca_snp_loading", "snprel_pca_samp_loading", "snprel_pca_corr",
     "snprel_eigmix_snp_loading", "snprel_eigmix_samp_loading", "snprel_plan_local", "snprel_accumulate",
     "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced", "snprel_last_plan", "snprel_set_row_window", "snprel_window_count", "snprel_mem_info",
-    "snprel_kernel_launches", "snprel_last_hot_kernel", "snprel_time_accumulate", "snprel_last_step_ms", "snprel_invalidate",
+    "snprel_kernel_launches", "snprel_last_hot_kernel", "snprel_time_accumulate", "snprel_time_finish", "snprel_last_step_ms", "snprel_invalidate",
     "snprel_table_gram", "snprel_debug_flags", "snprel_set_count_engine", "snprel_last_eigen_info", "snprel_set_rounding",
 ]
 
@@ -533,6 +534,12 @@ class Context:
     def time_accumulate(self, est, reps=1):
         ms = C.c_double()
         self._ck(self.lib.snprel_time_accumulate(self.h, int(est), int(reps), C.byref(ms)))
+        return ms.value
+
+    def time_finish(self, est):
+        """Device epilogue of the accumulators at hand (result stays on the device); ms."""
+        ms = C.c_double()
+        self._ck(self.lib.snprel_time_finish(self.h, int(est), C.byref(ms)))
         return ms.value
 
     def last_step_ms(self):

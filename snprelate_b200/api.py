@@ -189,7 +189,7 @@ def snpgdsGRM(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_mo
         grm = _newmat(ws["n_samp"], grm)
     if not with_id:
         return grm
-    rv = {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "method": mtxt, "grm": grm}
+    rv = {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "method": method, "grm": grm}   # the mapped method, R/IBD.R:603-604
     if method == "IndivBeta":
         rv["avg_val"] = avg           # R/IBD.R:605-606
     return rv
@@ -388,9 +388,13 @@ def _family_codes(family_id, gdsobj, sample_id, ws):
     family_id = list(family_id)
     if len(family_id) != ws["n_samp"]:
         raise SNPRelError("'length(family.id)' should be the number of samples.")
-    if sample_id is not None:          # re-index to file order (R/IBD.R:356-357)
-        order = {s: k for k, s in enumerate(np.asarray(sample_id).tolist())}
-        family_id = [family_id[order[s]] for s in ws["sample_id"].tolist()]
+    if sample_id is not None:
+        # exactly the reference's re-indexing, family.id[match(sample.id, ws$sample.id)] (R/IBD.R:356-357):
+        # entry k becomes the family of the sample at the WORKSPACE position of sample.id[k].  (For a
+        # sample.id that is not in file order this is the inverse of the permutation one would expect;
+        # a drop-in replacement has to pick the same pairs as "within family", so it is mirrored as is.)
+        pos = {s: k for k, s in enumerate(ws["sample_id"].tolist())}
+        family_id = [family_id[pos[s]] for s in np.asarray(sample_id).tolist()]
     levels = sorted({f for f in family_id if f is not None and f != "" and f == f})
     code = {f: k + 1 for k, f in enumerate(levels)}
     return np.array([code.get(f, NA_INT) if (f is not None and f != "" and f == f) else NA_INT

@@ -223,6 +223,7 @@ static void launch_pair_count(snprel_ctx *c) {
 
 static void finish_accumulate(snprel_ctx *c, int est) {
     c->accum_win_r0 = row_window(c).r0;
+    c->accum_win_rows = row_window(c).rows;
     c->accum_est = est;
     c->accum_reduced = false;
     c->reduce_list.clear();
@@ -450,7 +451,8 @@ __global__ void beta_final_kernel(const double *__restrict__ raw, double *__rest
 }
 
 static void need_accum(snprel_ctx *c, int est) {
-    if (c->accum_est == est && c->accum_reduced && c->accum_win_r0 == row_window(c).r0) return;   // reduced across ranks already
+    const RowWin w = row_window(c);   // reduced across ranks already, for this very window
+    if (c->accum_est == est && c->accum_reduced && c->accum_win_r0 == w.r0 && c->accum_win_rows == w.rows) return;
     bitcount_accumulate(c, est);
 }
 

@@ -289,6 +289,25 @@ static void timed_accumulate(snprel_ctx *c, int est, const snprel_plan *plan) {
     c->plan_ms = 0;
 }
 
+// device epilogue (int64 planes -> float64 result in c->scr_out); adds its time to step_ms
+static void timed_finish(snprel_ctx *c, int est) {
+    CUDA_CHECK(cudaEventRecord(c->evs0, c->stream));
+    grm_finish_device(c, est);
+    CUDA_CHECK(cudaEventRecord(c->evs1, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, c->evs0, c->evs1));
+    c->finish_ms = ms;
+    c->step_ms += ms;
+}
+
+int snprel_time_finish(snprel_ctx *c, int est, double *ms) {
+    API_BEGIN(c)
+    if (!is_cov(est)) fail("snprel_time_finish: covariance estimators only");
+    timed_finish(c, est);
+    if (ms) *ms = c->finish_ms;
+    API_END(c)
+}
 int snprel_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
     API_BEGIN(c)
     if (!plan) fail("snprel_plan_local: NULL plan");
@@ -340,10 +359,6 @@ int snprel_set_row_window(snprel_ctx *c, int64_t row0, int64_t rows) {
     if (rows > 0 && row0 >= c->n_samp) fail("snprel_set_row_window: window starts past the last sample");
     c->win_r0 = rows > 0 ? row0 : 0;
     c->win_rows = rows;
-    if (rows == 0) {   // back to the whole matrix: the per-window epilogue scratch is not needed
-        c->scr_num.release();
-        c->scr_out.release();
-    }
     c->accum_est = -1;
     c->accum_reduced = false;
     API_END(c)
@@ -385,6 +400,7 @@ int snprel_time_accumulate(snprel_ctx *c, int est, int reps, double *ms) {
         plan.frac_bits_d = -1;
         timed_plan(c, est, &plan);
         timed_accumulate(c, est, &plan);
+        if (is_cov(est)) timed_finish(c, est);   // ... up to "final N x N complete" 
         total += c->step_ms;
     }
     if (ms) *ms = total / reps;

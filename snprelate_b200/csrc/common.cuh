@@ -153,6 +153,8 @@ struct snprel_ctx {
     int accum_est = -1;          // estimator the accumulators belong to
     bool accum_reduced = false;  // true after snprel_mark_reduced
     int64_t accum_win_r0 = 0;    // first row of the window the accumulators were built for
+    int64_t accum_win_rows = 0;  // ... and its height
+    int accum_bayesian = 0;      // covariance accumulators: the Bayesian-normalisation flag they were built with
     snprel::DevBuf<uint32_t> cnt;         // packed-bit counters [ncnt][npad][npad]
     int cnt_planes = 0;
     snprel::DevBuf<double> cnt_f64;       // KING-homo f64 pair sums [2][npad][npad]
@@ -171,8 +173,11 @@ struct snprel_ctx {
     snprel::DevBuf<int2> scr_tiles;       // tile work list
     snprel::DevBuf<int> scr_cnt;          // per-sample genotype sum / missing count [2][npad]
     snprel::DevBuf<double> scr_part;      // per-block float64 partial sums of the tables kernel
-    snprel::DevBuf<double> scr_num, scr_out;   // epilogue scratch kept across row windows
+    snprel::DevBuf<double> scr_out;       // device result of the last epilogue (kept across calls and row windows)
+    snprel::DevBuf<double> scr_diag;      // diagonal staging of the trace
+    std::vector<double> host_diag;
     snprel::DevBuf<uint32_t> scr_ctab;    // constant tables of the tensor count engine
+    snprel::DevBuf<long long> scr_cacc;   // int64 planes of the tensor count engine (acc belongs to the covariance path)
     int count_engine = 0;                 // 0: packed-bit pair kernels (default), 1: tensor pipe
     int round_mode = 0;                   // 0: round to nearest + worst-case bound (default), 1: randomised + Hoeffding
     std::vector<int> host_cnt;
@@ -205,6 +210,7 @@ struct snprel_ctx {
     double hot_units = 0;
     double step_ms = 0;          // whole plan + accumulate (CUDA events)
     double plan_ms = 0;
+    double finish_ms = 0;        // device epilogue of the last snprel_time_accumulate / snprel_time_finish
 };
 
 namespace snprel {
@@ -284,6 +290,7 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
 void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan);
 void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan);
 void grm_finish(snprel_ctx *c, int method, double *out, int packed);
+void grm_finish_device(snprel_ctx *c, int est);
 void pca_finish(snprel_ctx *c, int eigen_cnt, int bayesian, double *genmat, double *trace_xtx,
                 double *trace_val, double *eigval, double *eigvec);
 void eigmix_finish(snprel_ctx *c, int eigen_cnt, int diagadj, double *ibd, double *afreq,

@@ -87,10 +87,10 @@ void tensor_count_accumulate(snprel_ctx *c, int est) {
             if (kinds[t] == kind) return (const uint32_t *)(tab.p + (int64_t)t * cap);
         return (const uint32_t *)nullptr;
     };
-    c->acc.alloc((size_t)np * win.rows * npad);
-    c->acc.zero(c->stream);
-    c->acc_planes = np;
-    c->prep_cache.version = 0;   // (acc is shared with the covariance path)
+    // own planes: KING-homo keeps its two float-sum Gram planes in c->acc while these counters run
+    DevBuf<long long> &cacc = c->scr_cacc;
+    cacc.alloc((size_t)np * win.rows * npad);
+    cacc.zero(c->stream);
     std::vector<GramPass> passes;
     for (int p = 0; p < np; p++) passes.push_back({tab_of(cp[p].a), cp[p].b, p, 0});
     c->cnt.alloc((size_t)nc * win.rows * npad);
@@ -98,9 +98,9 @@ void tensor_count_accumulate(snprel_ctx *c, int est) {
     c->cnt.zero(c->stream);
     c->hot_launches = 0;
     CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
-    gram_tc_run(c, passes.data(), np, c->acc.p, true);
+    gram_tc_run(c, passes.data(), np, cacc.p, true);
     dim3 grid((unsigned)(win.r1 - win.r0), (unsigned)((c->n_samp + 127) / 128));
-    counts_from_planes_kernel<<<grid, 128, 0, c->stream>>>(c->acc.p, c->cnt.p, est, c->n_samp, npad, win);
+    counts_from_planes_kernel<<<grid, 128, 0, c->stream>>>(cacc.p, c->cnt.p, est, c->n_samp, npad, win);
     KERNEL_CHECK(c);
     CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));

@@ -196,10 +196,12 @@ void geno_begin(snprel_ctx *c, int64_t n_samp, int64_t cap) {
     c->row_bytes = c->n_samp_pad / 4;
     c->snp_cap = round_up(cap > 0 ? cap : 1, SNP_PAD);
     c->n_snp = 0;
-    c->geno2b.release();
-    c->scr_num.release();
-    c->scr_out.release();
-    c->geno2b.alloc((size_t)c->snp_cap * c->row_bytes);
+    // same or smaller workspace: keep the allocation (a cudaFree + cudaMalloc of a few GB costs
+    // 3-13 ms per call); a much smaller one gives the memory back
+    const size_t need = (size_t)c->snp_cap * c->row_bytes;
+    if (c->geno2b.n > 2 * need + (64u << 20)) c->geno2b.release();
+    if (c->scr_out.n > 2 * (size_t)c->n_samp_pad * c->n_samp_pad) c->scr_out.release();
+    c->geno2b.alloc(need);
     c->stat.alloc(c->snp_cap);
     drop_derived(c);
 }

@@ -641,6 +641,8 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
 
     c->plan = plan;
     c->accum_win_r0 = row_window(c).r0;
+    c->accum_win_rows = row_window(c).rows;
+    c->accum_bayesian = plan.bayesian ? 1 : 0;
     c->accum_est = est;
     c->accum_reduced = false;
     c->reduce_list.clear();
@@ -666,52 +668,78 @@ __device__ __forceinline__ void store_sym2(double *out, int packed, int64_t n, i
     }
 }
 
-// numerator C_ij = (acc0[i][j] - vecW_hi[i]) * 2^-f - vecW_lo[i] * 2^-(f+20), full n x n (upper triangle)
-__global__ void numerator_kernel(const long long *__restrict__ acc, const long long *__restrict__ vec,
-                                 const int *__restrict__ nmiss, long long n_snp_total,
-                                 double *__restrict__ out, double inv_scale, double inv_scale_lo, int64_t n,
-                                 int64_t npad, RowWin win) {
-    int64_t i = win.r0 + blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
-    if (j >= n || j < i) return;
-    const int64_t li = i - win.r0;   // row inside the window
+// ---- fused epilogue: int64 planes -> float64 result in its final layout, one pass -------------
+// numerator C_ij = (acc0[i][j] - vecW_hi[i]) * 2^-f - vecW_lo[i] * 2^-(f+20), then the estimator's
+// normalisation.  mode 0: Eigenstrat (scale = (n-1)/trace); 1: GCTA; 3: EIGMIX (mul = 1 ibd / 2 GRM)
+struct FinalArgs {
+    const long long *acc;     // [planes][win.rows][npad]
+    const long long *vec;     // [NVEC][npad]
+    const int *nmiss;         // [npad] missing genotypes per sample
+    long long n_snp_total;
+    double inv_scale, inv_scale_lo;   // 2^-f, 2^-(f + W_EXTRA_BITS)
+    int mode, has_den, diagadj;
+    double scale, sum_den, inv_fix, mul;
+    long long nlocus;
+    int64_t n, npad;
+    RowWin win;
+};
+
+__device__ __forceinline__ double grm_numerator(const FinalArgs &a, int64_t i, int64_t j) {
     // a sample without a single valid genotype contributes exactly 0, as in the reference
     // (its centred genotypes are all 0, src/genPCA.h:103)
-    if (nmiss[i] == n_snp_total || nmiss[j] == n_snp_total) {
-        out[li * n + j] = 0.0;
-        return;
-    }
-    long long q = acc[li * npad + j] - vec[VEC_W * npad + i];
-    out[li * n + j] = (double)q * inv_scale - (double)vec[VEC_WLO * npad + i] * inv_scale_lo;
+    if (a.nmiss[i] == a.n_snp_total || a.nmiss[j] == a.n_snp_total) return 0.0;
+    const long long q = a.acc[(i - a.win.r0) * a.npad + j] - a.vec[VEC_W * a.npad + i];
+    return (double)q * a.inv_scale - (double)a.vec[VEC_WLO * a.npad + i] * a.inv_scale_lo;
 }
 
-// mode 0: Eigenstrat (scale = (n-1)/trace); 1: GCTA; 3: EIGMIX (mul = 1 ibd / 2 GRM)
-__global__ void grm_final_kernel(const double *__restrict__ num, const long long *__restrict__ acc,
-                                 const long long *__restrict__ vec, double *__restrict__ out, int packed,
-                                 int mode, double scale, double sum_den, long long nlocus,
-                                 double inv_fix, int has_den, int diagadj, double mul, int64_t n,
-                                 int64_t npad, RowWin win) {
-    int64_t i = win.r0 + blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
-    if (j >= n || j < i) return;
-    const int64_t li = i - win.r0;
-    double c = num[li * n + j];
-    double v;
-    if (mode == 0) {
-        v = c * scale;
-    } else {
-        long long dq = 0;
-        if (has_den)
-            dq = vec[VEC_D * npad + i] + vec[VEC_D * npad + j] - acc[win.rows * npad + li * npad + j];
-        if (mode == 1) {
-            v = c / (double)(2 * (nlocus - dq));      // src/genPCA.cpp:1233-1236
-        } else {
-            if (diagadj && i == j) c -= (double)vec[VEC_HET * npad + i];   // src/genEIGMIX.cpp:147-151
-            v = c / (sum_den - (double)dq * inv_fix) * mul;                // :153-155, :645-652
+__device__ __forceinline__ double grm_entry(const FinalArgs &a, int64_t i, int64_t j) {   // i <= j
+    double c = grm_numerator(a, i, j);
+    if (a.mode == 0) return c * a.scale;
+    long long dq = 0;
+    if (a.has_den)
+        dq = a.vec[VEC_D * a.npad + i] + a.vec[VEC_D * a.npad + j] -
+             a.acc[a.win.rows * a.npad + (i - a.win.r0) * a.npad + j];
+    if (a.mode == 1) return c / (double)(2 * (a.nlocus - dq));      // src/genPCA.cpp:1233-1236
+    if (a.diagadj && i == j) c -= (double)a.vec[VEC_HET * a.npad + i];   // src/genEIGMIX.cpp:147-151
+    return c / (a.sum_den - (double)dq * a.inv_fix) * a.mul;            // :153-155, :645-652
+}
+
+// packed slice of the window's rows (row-packed upper triangle, CdMatTri order)
+__global__ void grm_final_packed_kernel(const FinalArgs a, double *__restrict__ out) {
+    const int64_t i = a.win.r0 + blockIdx.x, j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= a.n || j < i) return;
+    out[tri_idx(a.n, i, j) - a.win.pbase] = grm_entry(a, i, j);
+}
+
+// full symmetric n x n: 32 x 32 tiles of the upper triangle, the mirror image goes through shared
+// memory so that both the direct and the transposed store are coalesced
+__global__ void __launch_bounds__(256) grm_final_full_kernel(const FinalArgs a, double *__restrict__ out) {
+    __shared__ double t[32][33];
+    const int64_t bi = blockIdx.y, bj = blockIdx.x;
+    if (bj < bi) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int64_t i = bi * 32 + ty + 8 * r, j = bj * 32 + tx;
+        double v = 0.0;
+        if (i < a.n && j < a.n && j >= i) {
+            v = grm_entry(a, i, j);
+            out[i * a.n + j] = v;
         }
+        t[ty + 8 * r][tx] = v;
     }
-    if (packed)
-        out[tri_idx(n, i, j) - win.pbase] = v;
-    else
-        store_sym2(out, 0, n, i, j, v);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int64_t j = bj * 32 + ty + 8 * r, i = bi * 32 + tx;   // out[j][i] = entry (i, j)
+        if (i < a.n && j < a.n && j > i) out[j * a.n + i] = t[tx][ty + 8 * r];
+    }
+}
+
+// numerators of the diagonal (trace of the covariance, CdMatTri::Trace src/genPCA.cpp:1387)
+__global__ void diag_numerator_kernel(const FinalArgs a, double *__restrict__ d) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) d[i] = grm_numerator(a, i, i);
 }
 
 __global__ void diag_kernel(const double *__restrict__ m, double *__restrict__ d, int64_t n) {
@@ -751,7 +779,14 @@ static void d2h(snprel_ctx *c, T *host, const T *dev, size_t count) {
 
 static void need_grm_accum(snprel_ctx *c, int est, int bayesian) {
     if (est == SNPREL_GRM_CORR) est = SNPREL_GRM_GCTA;
-    if (c->accum_est == est && c->accum_reduced && c->accum_win_r0 == row_window(c).r0) return;
+    const RowWin w = row_window(c);
+    if (c->accum_est == est && c->accum_reduced && c->accum_win_r0 == w.r0 && c->accum_win_rows == w.rows) {
+        // accumulators already summed over the ranks: they must have been built for this request
+        if (c->accum_bayesian != (bayesian ? 1 : 0))
+            fail("the reduced accumulators were built with bayesian = %s; accumulate again with the flag you finish with",
+                 c->accum_bayesian ? "TRUE" : "FALSE");
+        return;
+    }
     snprel_plan plan{};
     plan.frac_bits = -1;
     plan.frac_bits_w = -1;
@@ -773,7 +808,6 @@ static Globals read_globals(snprel_ctx *c) {
     return Globals{hs[0], hs[1], hi[0]};
 }
 
-// numerator into dev buffer `num` (n x n, upper triangle valid)
 static dim3 win_grid(snprel_ctx *c) {
     RowWin w = row_window(c);
     return dim3((unsigned)(w.r1 - w.r0), (unsigned)((c->n_samp + 127) / 128));
@@ -783,64 +817,85 @@ static size_t win_out_count(snprel_ctx *c, int packed) {
     return out_count(c->n_samp, packed);
 }
 
-// numerator rows of the current window: [r1 - r0][n]
-static void build_numerator(snprel_ctx *c, DevBuf<double> &num) {
-    int64_t n = c->n_samp;
-    RowWin w = row_window(c);
-    num.alloc((size_t)(w.r1 - w.r0) * n);
-    numerator_kernel<<<win_grid(c), 128, 0, c->stream>>>(c->acc.p, c->samp_sum.p, c->scr_cnt.p + c->n_samp_pad,
-                                                         (long long)c->plan.n_snp, num.p,
-                                                         std::ldexp(1.0, -c->plan.frac_bits),
-                                                         std::ldexp(1.0, -(c->plan.frac_bits + W_EXTRA_BITS)), n,
-                                                         c->n_samp_pad, w);
-    KERNEL_CHECK(c);
-}
-
-static double trace_of(snprel_ctx *c, const double *m, int64_t n) {
-    DevBuf<double> d;
-    d.alloc((size_t)n);
-    diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(m, d.p, n);
-    KERNEL_CHECK(c);
-    std::vector<double> h((size_t)n);
-    d2h(c, h.data(), d.p, (size_t)n);
+// sum of n device doubles in index order on the host (the reference's CdMatTri::Trace order);
+// the staging buffers are persistent
+static double host_sum(snprel_ctx *c, const double *dev, int64_t n) {
+    c->host_diag.resize((size_t)n);
+    d2h(c, c->host_diag.data(), dev, (size_t)n);
     double t = 0;
-    for (int64_t i = 0; i < n; i++) t += h[i];   // CdMatTri::Trace order
+    for (int64_t i = 0; i < n; i++) t += c->host_diag[i];
     return t;
 }
 
-// device-side result of the covariance family: full symmetric/packed matrix in `o`
-static void grm_device(snprel_ctx *c, int method, int packed, int diagadj, double mul, DevBuf<double> &o,
-                       double *trace_xtx) {
-    int64_t n = c->n_samp, npad = c->n_samp_pad;
-    const RowWin w = row_window(c);
+static double trace_of(snprel_ctx *c, const double *m, int64_t n) {
+    c->scr_diag.alloc((size_t)n);
+    diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(m, c->scr_diag.p, n);
+    KERNEL_CHECK(c);
+    return host_sum(c, c->scr_diag.p, n);
+}
+
+// device-side result of the covariance family: full symmetric / packed matrix in c->scr_out
+// (persistent: a cudaMalloc + cudaFree of the 800 MB result per call cost more than the whole
+// epilogue -- and up to 0.5 s on a cold driver)
+static void grm_device(snprel_ctx *c, int method, int packed, int diagadj, double mul, double *trace_xtx) {
+    const int64_t n = c->n_samp;
     if (!full_window(c) && !packed) fail("a row window returns the packed upper triangle only (useMatrix)");
-    // row windows come in long runs of equal-or-shrinking size: keep the scratch between them
-    // (a cudaMalloc + cudaFree of several GB per window costs more than the epilogue itself)
-    DevBuf<double> num_local;
-    DevBuf<double> &num = full_window(c) ? num_local : c->scr_num;
-    build_numerator(c, num);
-    Globals g = read_globals(c);
-    const int has_den = c->acc_planes > 1;
+    DevBuf<double> &o = c->scr_out;
     o.alloc(win_out_count(c, packed));
+    FinalArgs a{};
+    a.acc = c->acc.p;
+    a.vec = c->samp_sum.p;
+    a.nmiss = c->scr_cnt.p + c->n_samp_pad;
+    a.n_snp_total = (long long)c->plan.n_snp;
+    a.inv_scale = std::ldexp(1.0, -c->plan.frac_bits);
+    a.inv_scale_lo = std::ldexp(1.0, -(c->plan.frac_bits + W_EXTRA_BITS));
+    a.has_den = c->acc_planes > 1;
+    a.diagadj = diagadj;
+    a.mul = mul;
+    a.n = n;
+    a.npad = c->n_samp_pad;
+    a.win = row_window(c);
     if (method == SNPREL_GRM_EIGENSTRAT) {
         // whole matrix: trace of the computed numerator (CdMatTri::Trace, src/genPCA.cpp:1387);
         // row window: the diagonal lives in other windows, so use the same trace evaluated from
         // the per-SNP genotype counts by the plan kernel (equal up to float64 rounding)
-        double tr = full_window(c) ? trace_of(c, num.p, n) : c->plan.scale * (double)std::max<int64_t>(n - 1, 1);
+        double tr;
+        if (full_window(c)) {
+            c->scr_diag.alloc((size_t)n);
+            diag_numerator_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(a, c->scr_diag.p);
+            KERNEL_CHECK(c);
+            tr = host_sum(c, c->scr_diag.p, n);
+        } else {
+            tr = c->plan.scale * (double)std::max<int64_t>(n - 1, 1);
+        }
         if (trace_xtx) *trace_xtx = tr;
-        grm_final_kernel<<<win_grid(c), 128, 0, c->stream>>>(num.p, c->acc.p, c->samp_sum.p, o.p, packed,
-                                                             0, (double)(n - 1) / tr, 0, 0, 0, 0, 0, 1, n,
-                                                             npad, w);
+        a.mode = 0;
+        a.scale = (double)(n - 1) / tr;
     } else if (method == SNPREL_GRM_GCTA || method == SNPREL_GRM_CORR) {
-        grm_final_kernel<<<win_grid(c), 128, 0, c->stream>>>(num.p, c->acc.p, c->samp_sum.p, o.p, packed,
-                                                             1, 0, 0, g.nlocus, 1.0, has_den, 0, 1, n,
-                                                             npad, w);
+        Globals g = read_globals(c);
+        a.mode = 1;
+        a.nlocus = g.nlocus;
     } else {
-        grm_final_kernel<<<win_grid(c), 128, 0, c->stream>>>(
-            num.p, c->acc.p, c->samp_sum.p, o.p, packed, 3, 0, g.sum_den, 0,
-            std::ldexp(1.0, -c->plan.frac_bits_d), has_den, diagadj, mul, n, npad, w);
+        Globals g = read_globals(c);
+        a.mode = 3;
+        a.sum_den = g.sum_den;
+        a.inv_fix = std::ldexp(1.0, -c->plan.frac_bits_d);
+    }
+    if (packed) {
+        grm_final_packed_kernel<<<win_grid(c), 128, 0, c->stream>>>(a, o.p);
+    } else {
+        const unsigned nb = (unsigned)((n + 31) / 32);
+        grm_final_full_kernel<<<dim3(nb, nb), 256, 0, c->stream>>>(a, o.p);
     }
     KERNEL_CHECK(c);
+}
+
+// device epilogue of the accumulators at hand, result left in c->scr_out (bench timing:
+// SURVEY section 8d counts the step up to "final N x N complete")
+void grm_finish_device(snprel_ctx *c, int est) {
+    if (est == SNPREL_GRM_CORR) est = SNPREL_GRM_GCTA;
+    if (c->accum_est != est) fail("snprel_time_finish: no accumulators for estimator %d", est);
+    grm_device(c, est, full_window(c) ? 0 : 1, 0, est == SNPREL_GRM_EIGMIX ? 2.0 : 1.0, nullptr);
 }
 
 void grm_finish(snprel_ctx *c, int method, double *out, int packed) {
@@ -848,20 +903,18 @@ void grm_finish(snprel_ctx *c, int method, double *out, int packed) {
     int64_t n = c->n_samp;
     if (!full_window(c) && method == SNPREL_GRM_CORR) fail("method \"Corr\" needs the whole matrix, not a row window");
     need_grm_accum(c, method, 0);
-    DevBuf<double> o_local;
-    DevBuf<double> &o = full_window(c) ? o_local : c->scr_out;
+    DevBuf<double> &o = c->scr_out;
     if (method == SNPREL_GRM_CORR) {
-        grm_device(c, SNPREL_GRM_GCTA, 0, 0, 1, o, nullptr);
-        DevBuf<double> d;
-        d.alloc((size_t)n);
-        diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(o.p, d.p, n);
+        grm_device(c, SNPREL_GRM_GCTA, 0, 0, 1, nullptr);
+        c->scr_diag.alloc((size_t)n);
+        diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(o.p, c->scr_diag.p, n);
         KERNEL_CHECK(c);
-        corr_kernel<<<tri_grid(n), 128, 0, c->stream>>>(o.p, d.p, n);
+        corr_kernel<<<tri_grid(n), 128, 0, c->stream>>>(o.p, c->scr_diag.p, n);
         KERNEL_CHECK(c);
         d2h(c, out, o.p, (size_t)n * n);
         return;
     }
-    grm_device(c, method, packed, 0, method == SNPREL_GRM_EIGMIX ? 2.0 : 1.0, o, nullptr);
+    grm_device(c, method, packed, 0, method == SNPREL_GRM_EIGMIX ? 2.0 : 1.0, nullptr);
     d2h(c, out, o.p, win_out_count(c, packed));
 }
 
@@ -871,12 +924,14 @@ void pca_finish(snprel_ctx *c, int eigen_cnt, int bayesian, double *genmat, doub
     if (!full_window(c)) fail("snprel_pca needs the whole matrix, not a row window");
     int64_t n = c->n_samp;
     need_grm_accum(c, SNPREL_GRM_EIGENSTRAT, bayesian);
-    DevBuf<double> o;
+    DevBuf<double> &o = c->scr_out;
     double tx = 0;
-    grm_device(c, SNPREL_GRM_EIGENSTRAT, 0, 0, 1, o, &tx);
+    grm_device(c, SNPREL_GRM_EIGENSTRAT, 0, 0, 1, &tx);
     if (trace_xtx) *trace_xtx = tx;
+    // the big copy first: the 80 KB diagonal for TraceVal rides behind it on the same stream
+    if (genmat) CUDA_CHECK(cudaMemcpyAsync(genmat, o.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (trace_val) *trace_val = trace_of(c, o.p, n);
-    if (genmat) d2h(c, genmat, o.p, (size_t)n * n);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (eigval || eigvec) eigen_topk(c, o.p, n, eigen_cnt, eigval, eigvec);
 }
 
@@ -886,8 +941,8 @@ void eigmix_finish(snprel_ctx *c, int eigen_cnt, int diagadj, double *ibd, doubl
     if (!full_window(c)) fail("snprel_eigmix needs the whole matrix, not a row window (use snprel_grm EIGMIX)");
     need_grm_accum(c, SNPREL_GRM_EIGMIX, 0);
     if (eigen_cnt < 0 || eigen_cnt > n) eigen_cnt = (int)n;   // src/genEIGMIX.cpp:675-676
-    DevBuf<double> o;
-    grm_device(c, SNPREL_GRM_EIGMIX, 0, diagadj, 1.0, o, nullptr);
+    DevBuf<double> &o = c->scr_out;
+    grm_device(c, SNPREL_GRM_EIGMIX, 0, diagadj, 1.0, nullptr);
     if (ibd) d2h(c, ibd, o.p, (size_t)n * n);
     if (afreq) {   // af = 0.5 * avg_geno (src/genEIGMIX.cpp:116-118)
         std::vector<SnpStat> h((size_t)c->n_snp);

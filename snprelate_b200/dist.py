@@ -53,27 +53,75 @@ def buffer_tensor(ptr, count, kind, device):
     return torch.as_tensor(_DevArray(ptr, count, typestr), device=device)
 
 
+_PLAN_MAX = ("max_abs", "max_abs_w")
+# sums are conservative for the per-sample maxima (max of sums <= sum of maxima)
+_PLAN_SUM = ("sum_bound", "err_weight", "scale", "total_missing", "max_missing", "n_snp")
+_PLAN_INT = ("total_missing", "max_missing", "n_snp")
+
+
+def _plan_vectors(plan):
+    return ([float(getattr(plan, k)) for k in _PLAN_MAX], [float(getattr(plan, k)) for k in _PLAN_SUM])
+
+
+def _plan_store(plan, mx, sm):
+    for k, v in zip(_PLAN_MAX, mx):
+        setattr(plan, k, float(v))
+    for k, v in zip(_PLAN_SUM, sm):
+        setattr(plan, k, int(v) if k in _PLAN_INT else float(v))
+    return plan
+
+
 def reduce_plan(plan, group=None, device=None):
     """All ranks must use one fixed-point format: max-reduce max_abs, sum-reduce
     the other per-rank plan statistics."""
     import torch
     import torch.distributed as dist
     dev = "cpu" if device is None else device
-    mx = torch.tensor([plan.max_abs, plan.max_abs_w], dtype=torch.float64, device=dev)
-    # sums are conservative for the per-sample maxima (max of sums <= sum of maxima)
-    sm = torch.tensor([plan.sum_bound, plan.err_weight, plan.scale, float(plan.total_missing),
-                       float(plan.max_missing), float(plan.n_snp)], dtype=torch.float64, device=dev)
+    mxl, sml = _plan_vectors(plan)
+    mx = torch.tensor(mxl, dtype=torch.float64, device=dev)
+    sm = torch.tensor(sml, dtype=torch.float64, device=dev)
     dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
     dist.all_reduce(sm, op=dist.ReduceOp.SUM, group=group)
-    plan.max_abs = float(mx[0])
-    plan.max_abs_w = float(mx[1])
-    plan.sum_bound = float(sm[0])
-    plan.err_weight = float(sm[1])
-    plan.scale = float(sm[2])
-    plan.total_missing = int(sm[3])
-    plan.max_missing = int(sm[4])
-    plan.n_snp = int(sm[5])
-    return plan
+    return _plan_store(plan, mx.tolist(), sm.tolist())
+
+
+def merge_plans(plans):
+    """The same merge as reduce_plan for plans held by ONE process (several contexts, e.g. one per
+    GPU of the box driven from a single host thread): every plan receives the merged statistics."""
+    vec = [_plan_vectors(p) for p in plans]
+    mx = [max(v[0][k] for v in vec) for k in range(len(_PLAN_MAX))]
+    sm = [sum(v[1][k] for v in vec) for k in range(len(_PLAN_SUM))]
+    for p in plans:
+        _plan_store(p, mx, sm)
+    return plans
+
+
+def accumulate_in_process(contexts, est, bayesian=False):
+    """SNP-sharded accumulation over contexts of ONE process (each holding its own SNP range, on
+    the same or on different GPUs): plan -> merged format -> local accumulate -> the partial
+    buffers are summed into every context (device-to-device adds through torch views of the
+    library's buffers) -> mark reduced.  The algebra is exactly accumulate_sharded's, without a
+    process group; afterwards any context's finish calls return the global result."""
+    import torch
+    plans = merge_plans([c.plan_local(est, bayesian) for c in contexts])
+    for c, p in zip(contexts, plans):
+        c.accumulate(est, p)
+    bufs = [c.reduce_buffers() for c in contexts]
+    devs = [torch.device("cuda", c.device) for c in contexts]
+    for k in range(len(bufs[0])):
+        ts = [buffer_tensor(b[k][0], b[k][1], b[k][2], d) for b, d in zip(bufs, devs)]
+        if ts[0].numel() == 0:
+            continue
+        total = ts[0].clone()
+        for t in ts[1:]:
+            total += t.to(devs[0])
+        for t, d in zip(ts, devs):
+            t.copy_(total.to(d))
+    for d in set(devs):
+        torch.cuda.synchronize(d)
+    for c in contexts:
+        c.mark_reduced()
+    return plans[0]
 
 
 def allreduce_buffers(buffers, group=None, device=None, dst=None):

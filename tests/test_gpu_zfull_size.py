@@ -1,5 +1,6 @@
 """BASELINE config-2 size (10 000 samples x 1 000 000 SNPs, the bench workload) through the C ABI:
-entries of the first samples against the oracle evaluated on those samples' columns (the per-SNP
+entries at SCATTERED sample indices (first / middle / last 256-sample tile rows, so the tile-index
+arithmetic of every tile row and the ragged last tile are covered) against the oracle evaluated on those samples' columns (the per-SNP
 statistics over ALL samples come from the device, themselves checked against the generator), plus
 size-independent properties of the whole matrix.  The same checks run at configs 3-5 in
 tools/config_run.py and tools/c5_tiled.py (results in profiles/).  Sorted last: ~1 minute."""
@@ -11,7 +12,8 @@ from oracle import snprel_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-N, M, K, SEED, MISS = 10000, 1000000, 12, 20261017, 0.005
+N, M, K, SEED, MISS = 10000, 1000000, 48, 20261017, 0.005
+IDX = O.scattered_samples(N, K, seed=11)
 
 
 @pytest.fixture(scope="module")
@@ -19,15 +21,15 @@ def ws():
     ctx = S.Context(0)
     ctx.geno_begin(N, M)
     ctx.geno_synth(M, seed=SEED, miss_rate=MISS)
-    sub = O.synth_geno(K, M, seed=SEED, miss_rate=MISS)          # samples 0..K-1 of the same data set
+    sub = O.synth_geno(0, M, seed=SEED, miss_rate=MISS, samples=IDX)   # K scattered samples of the same data set
     yield ctx, sub
     ctx.close()
 
 
 def test_generator_and_snp_statistics(ws):
     ctx, sub = ws
-    back = ctx.geno_copy_2b()[:, : (K + 3) // 4]
-    codes = np.stack([(back >> (2 * k)) & 3 for k in range(4)], axis=-1).reshape(M, -1)[:, :K]
+    back = ctx.geno_copy_2b()
+    codes = (back[:, IDX // 4] >> (2 * (IDX % 4)).astype(np.uint8)[None, :]) & 3
     assert np.array_equal(codes, np.minimum(sub, 3))              # device generator == oracle generator
     af, maf, mr = ctx.snp_ratefreq()
     assert np.all((af > 0.02) & (af < 0.55)) and abs(float(mr.mean()) - MISS) < 2e-4
@@ -43,15 +45,9 @@ def test_gcta_grm_full_size(ws):
     off_mean = (float(grm.sum()) - float(d.sum())) / (N * (N - 1.0))
     assert abs(off_mean + 1.0 / (N - 1)) < 1e-5                   # centred genotypes: rows sum to ~0
     af, _, _ = ctx.snp_ratefreq()
-    mu = 2 * af
-    poly = (af > 0) & (af < 1)
-    w = np.where(poly, 1.0 / np.where(poly, af * (1 - af), 1.0), 0.0)
-    z = np.where(sub <= 2, (sub - mu[:, None]) * np.sqrt(w)[:, None], 0.0)
-    mm = (sub > 2).astype(np.float64)
-    miss = mm * poly[:, None]
-    den = miss.sum(0)[:, None] + miss.sum(0)[None, :] - miss.T @ mm
-    ref = (z.T @ z) / (2.0 * (poly.sum() - den))
-    got = grm[:K, :K]
+    ref = O.subset_entries(sub, af, "GCTA")
+    got = grm[np.ix_(IDX, IDX)]
+    assert IDX[0] == 0 and IDX[-1] == N - 1 and np.sum((IDX > 4000) & (IDX < 6000)) >= 8
     assert float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0))) < 1e-10
     pl = ctx.last_plan()
     assert pl.digits + pl.digits_w + pl.digits_d <= 10            # the fixed-point plan of DESIGN.md section 3
@@ -61,7 +57,35 @@ def test_ibs_counts_full_size(ws):
     ctx, sub = ws
     i0, i1, i2 = ctx.ibs_num()
     ref = O.ibs_counts(sub)
-    assert np.array_equal(np.stack([i0[:K, :K], i1[:K, :K], i2[:K, :K]]), ref)          # bit exact
+    ix = np.ix_(IDX, IDX)
+    assert np.array_equal(np.stack([i0[ix], i1[ix], i2[ix]]), ref)                      # bit exact
     tot = (i0.astype(np.int64) + i1 + i2)
     assert np.array_equal(tot, tot.T) and int(tot.max()) <= M
     assert np.array_equal(np.diag(i2), np.diag(tot))              # a sample is IBS2 with itself wherever it is valid
+
+
+def test_pca_genmat_and_top32_eigenvectors_full_size(ws):
+    """Config 2 proper: snpgdsPCA covariance + top-32 eigenvectors.  genmat at the scattered samples vs the
+    oracle (1e-10); eigenvectors vs scipy.linalg.eigh of the device genmat (north star: 1e-6, up to sign)."""
+    import scipy.linalg as sla
+    ctx, sub = ws
+    r = ctx.pca(eigen_cnt=32, need_genmat=True)
+    gm = r["genmat"]
+    af, _, _ = ctx.snp_ratefreq()
+    ref = O.subset_entries(sub, af, "Eigenstrat", n_total=N, trace=r["TraceXTX"])
+    got = gm[np.ix_(IDX, IDX)]
+    assert float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0))) < 1e-10
+    assert abs(float(np.trace(gm)) - (N - 1)) < 1e-6 * N and abs(r["TraceVal"] - float(np.trace(gm))) < 1e-6
+    w, v = sla.eigh(gm, subset_by_index=[N - 33, N - 1])          # one more: the gap below the 32nd
+    w, v = w[::-1], v[:, ::-1]
+    assert np.max(np.abs(r["eigenval"][:32] - w[:32]) / w[:32]) < 1e-9
+    V = r["eigenvect"]
+    for k in range(32):
+        sgn = 1.0 if float(V[:, k] @ v[:, k]) >= 0 else -1.0
+        # an eigenvector is conditioned by the gap to its neighbours (both solvers stop at residuals of
+        # ~1e-11 |C|): 1e-6 wherever the gap allows it, which it does for all 32 here
+        gap = min(w[k - 1] - w[k] if k else np.inf, w[k] - w[k + 1])
+        tol = max(1e-6, 1e-10 * w[0] / gap)
+        assert float(np.max(np.abs(sgn * V[:, k] - v[:, k]))) < tol, (k, gap, tol)
+    resid = np.linalg.norm(gm @ V - V * r["eigenval"][None, :32], axis=0)
+    assert float(resid.max()) < 1e-9 * w[0]

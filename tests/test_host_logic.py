@@ -55,6 +55,19 @@ def test_family_codes():
         api._family_codes(["x"], None, None, ws)
 
 
+def test_family_codes_follow_the_reference_reindexing():
+    """R/IBD.R:356-357: family.id <- family.id[match(sample.id, ws$sample.id)].  With a sample.id that is
+    a 3-cycle of the file order the reference picks family.id at the WORKSPACE position of each requested
+    sample (not the inverse permutation); the mirror must pick the same entries."""
+    ws = dict(n_samp=3, sample_id=np.array(["a", "b", "c"]))           # workspace = file order
+    sample_id = ["b", "c", "a"]                                        # a 3-cycle, not an involution
+    family = ["F1", "F2", "F3"]
+    # R: match(c("b","c","a"), c("a","b","c")) = (2, 3, 1)  ->  family.id[c(2, 3, 1)] = F2, F3, F1
+    fam = api._family_codes(family, None, sample_id, ws)
+    lv = {"F1": 1, "F2": 2, "F3": 3}
+    assert fam.tolist() == [lv["F2"], lv["F3"], lv["F1"]]
+
+
 def test_loading_and_correlation_argument_checks():
     """snpgdsPCACorr / snpgdsPCASNPLoading / snpgdsPCASampLoading refuse malformed inputs before any
     device call (R/PCA.R:99-303)."""

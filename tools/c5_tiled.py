@@ -26,7 +26,8 @@ ap.add_argument("--rank", type=int, default=int(os.environ.get("RANK", "0")))
 ap.add_argument("--method", default="GCTA")
 ap.add_argument("--miss", type=float, default=0.005)
 ap.add_argument("--max-windows", type=int, default=0, help="stop after K of this rank's windows (0 = all)")
-ap.add_argument("--check", type=int, default=16, help="oracle check on the first K samples of window 0 (rank 0)")
+ap.add_argument("--check", type=int, default=48, help="oracle check on K scattered samples (first / middle / last tile rows); "
+                "every rank checks the entries of its own windows")
 args = ap.parse_args()
 
 dist = "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1
@@ -60,7 +61,9 @@ if dist:
 torch.cuda.synchronize()
 t_start = time.perf_counter()
 per_win, hot_ms, launches0, pairs = [], 0.0, ctx.kernel_launches(), 0
-first = None
+from oracle import snprel_oracle as O          # checker only (not on the timed path's arithmetic)
+idx = O.scattered_samples(n, args.check, seed=7) if args.check > 0 else np.zeros(0, dtype=np.int64)
+got_rows = []                                  # (position a in idx, entries (idx[a], idx[a:]) of the packed slice)
 for k, (r0, h) in enumerate(mine):
     tw = time.perf_counter()
     ctx.set_row_window(r0, h)
@@ -69,8 +72,11 @@ for k, (r0, h) in enumerate(mine):
     hot_ms += ctx.last_hot_kernel()[0]
     pairs += cnt
     per_win.append(round((time.perf_counter() - tw) * 1e3, 1))
-    if first is None and r0 == 0:
-        first = out[: min(cnt, 4 * n)].copy()      # rows 0..3 of the packed triangle
+    pbase = r0 * (2 * n - r0 - 1) // 2 + r0         # packed index of (r0, r0)
+    for a, i in enumerate(idx):
+        if r0 <= i < min(r0 + h, n):
+            base = int(i) * (2 * n - int(i) - 1) // 2 - pbase
+            got_rows.append((a, out[base + idx[a:]].copy()))
 torch.cuda.synchronize()
 t_job = time.perf_counter() - t_start
 if dist:
@@ -86,26 +92,26 @@ ctx.set_row_window(0, 0)
 pl = ctx.last_plan()
 
 check = None
-if args.rank == 0 and first is not None and args.check > 0:
-    # oracle (checker only) on the first rows against the device's own all-sample SNP statistics
-    from oracle import snprel_oracle as O
-    k = min(args.check, n)
-    sub = O.synth_geno(k, m, seed=20261017, miss_rate=args.miss)           # samples 0..k-1, all SNPs
+if len(idx):
+    # oracle on the scattered samples' columns against the device's own all-sample SNP statistics;
+    # every rank checks the rows that fell into its windows, the verdict is the max over ranks
+    sub = O.synth_geno(0, m, seed=20261017, miss_rate=args.miss, samples=idx)
     af, _, _ = ctx.snp_ratefreq()
-    mu = 2 * af
-    poly = (af > 0) & (af < 1)
-    w = np.where(poly, 1.0 / np.where(poly, af * (1 - af), 1.0), 0.0)
-    z = np.where(sub <= 2, (sub - mu[:, None]) * np.sqrt(w)[:, None], 0.0)
-    mm = (sub > 2).astype(np.float64)
-    miss = mm * poly[:, None]
-    den = miss.sum(0)[:, None] + miss.sum(0)[None, :] - miss.T @ mm
-    ref = (z.T @ z) / (2.0 * (poly.sum() - den))
-    err = 0.0
-    for i in range(min(k, 4)):
-        base = i * n - i * (i - 1) // 2                 # packed index of (i, i)
-        got = first[base: base + (k - i)]
-        err = max(err, float(np.max(np.abs(got - ref[i, i:k]) / np.maximum(np.abs(ref[i, i:k]), 1.0))))
-    check = {"rows": min(k, 4), "cols": k, "max_rel_err": err}
+    ref = O.subset_entries(sub, af, "GCTA")
+    err, cnt_chk = 0.0, 0
+    for a, vals in got_rows:
+        r = ref[a, a:]
+        err = max(err, float(np.max(np.abs(vals - r) / np.maximum(np.abs(r), 1.0))))
+        cnt_chk += len(r)
+    if dist:
+        tt = torch.tensor([err, -float(cnt_chk)], dtype=torch.float64, device="cuda")
+        td.all_reduce(tt, op=td.ReduceOp.MAX)
+        err = float(tt[0])
+        cc = torch.tensor([float(cnt_chk)], dtype=torch.float64, device="cuda")
+        td.all_reduce(cc)
+        cnt_chk = int(cc[0])
+    check = {"scattered_samples": int(len(idx)), "entries_checked": int(cnt_chk), "max_rel_err": err,
+             "first_last_sample": [int(idx[0]), int(idx[-1])], "ok": bool(err < 1e-10)}
 
 if args.rank == 0:
     total_pairs = n * (n + 1) / 2
