@@ -241,18 +241,19 @@ int snprel_eigmix_samp_loading(snprel_ctx *ctx, int k, const double *loadings,
  * the fixed-point format, so the host max-reduces max_abs and sum-reduces the other
  * statistics before snprel_accumulate (see snprelate_b200/dist.py).
  *
- * Format choice (grm.cu): every table value v is stored as round(v * 2^frac_bits) and
- * split into `digits` balanced base-256 digits (one int8 tensor pass each).  The
+ * Format choice (grm.cu): every row-table value v is stored as round(v * 2^frac_bits) and
+ * split into `digits` balanced base-256 digits (one int8 tensor pass each) and multiplied
+ * with a per-SNP INTEGER column table B_l (main passes) or the missing indicator.  The
  * quantisation error of an output entry is at most
  *   2^-(frac_bits+1) * err_weight + 2^-(frac_bits_w+1) * max_missing,
  * so the library picks the fewest passes for which that bound is <= tol * scale, where
  * scale is (a lower bound of) the estimator's normaliser (trace/(n-1), 2 nLocus,
  * sum 4p(1-p)).  tol defaults to 1e-10. */
 typedef struct snprel_plan {
-    double max_abs;        /* max |U table value| over local SNPs                      */
-    double max_abs_w;      /* max |W table value| (W = mu * U, the missing-data table) */
+    double max_abs;        /* max |T| over local SNPs, T = U / s the row table of the main passes */
+    double max_abs_w;      /* max |R|, R = (mu - t/s) U the row table of the missing-data passes  */
     double sum_bound;      /* sum over local SNPs of the per-SNP magnitude (int64 range) */
-    double err_weight;     /* max over samples of the sum of genotypes                 */
+    double err_weight;     /* max over samples of sum_l |B_l[g]|, B_l = s g - t the integer column table */
     double scale;          /* local share of the normaliser of the final matrix        */
     double tol;            /* in: relative tolerance target (<= 0: 1e-10)              */
     int64_t total_missing; /* missing genotypes among the selected samples             */
@@ -265,6 +266,7 @@ typedef struct snprel_plan {
     int32_t digits_w;      /* out: digits of the W table (0 without missing data)      */
     int32_t digits_d;      /* out: digits of the denominator table                     */
     int32_t bayesian;      /* Eigenstrat only                                          */
+    int32_t frac_bits_v;   /* out: fixed point of the per-sample vector sum_l R_l[g_il] */
 } snprel_plan;
 
 int snprel_plan_local(snprel_ctx *ctx, int estimator, snprel_plan *plan);

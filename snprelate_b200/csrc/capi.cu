@@ -79,11 +79,6 @@ void snprel_destroy(snprel_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     eigen_release(c);
-    for (int k = 0; k < 2; k++) {
-        if (c->aux_event[k]) cudaEventDestroy(c->aux_event[k]);
-        if (c->aux_stream[k]) cudaStreamDestroy(c->aux_stream[k]);
-    }
-    if (c->aux_fork) cudaEventDestroy(c->aux_fork);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->evs0) cudaEventDestroy(c->evs0);

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -124,8 +125,6 @@ struct snprel_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs0 = nullptr, evs1 = nullptr;
-    cudaStream_t aux_stream[2] = {nullptr, nullptr};   // experimental concurrent pass launches (gram_tc.cu)
-    cudaEvent_t aux_event[2] = {nullptr, nullptr}, aux_fork = nullptr;
     std::string err;
     int64_t launches = 0;
     uint32_t debug_flags = 0;
@@ -170,8 +169,21 @@ struct snprel_ctx {
     snprel::DevBuf<uint32_t> scr_tab;     // digit tables [npass][snp_cap]
     snprel::DevBuf<int> scr_flags;        // [0] digit overflow, [1] pipeline error
     snprel::DevBuf<double> scr_plan;      // plan statistics [3]
-    snprel::DevBuf<int2> scr_tiles;       // tile work list
-    snprel::DevBuf<int> scr_cnt;          // per-sample genotype sum / missing count [2][npad]
+    snprel::DevBuf<uint8_t> scr_items, scr_passes;   // K1 work items / pass descriptors
+    struct ConstTab {
+        uint32_t word = 0;
+        snprel::DevBuf<uint32_t> buf;
+    };
+    std::vector<std::unique_ptr<ConstTab>> const_tabs;   // constant per-SNP tables (gram_const_table)
+    snprel::DevBuf<int> scr_cnt;          // per-sample heterozygote / missing counts [2][npad]
+    snprel::DevBuf<long long> scr_ew;     // per-sample error weight sum_l |B_l[g_il]| [npad]
+    snprel::DevBuf<int> scr_chunk;        // per GRAM_CHUNK SNPs: max over samples of the chunk's error weight
+    snprel::DevBuf<int2> scr_coltab;      // per-SNP integer column table (s_l, t_l), B_l[g] = s_l g - t_l
+    snprel::DevBuf<uint32_t> scr_tabb;    // [2][snp_cap]: B_l as int8 bytes by genotype code, and |B_l|
+    uint64_t coltab_version = 0;
+    int coltab_est = -1, coltab_bayesian = 0;
+    std::vector<long long> host_ew;
+    std::vector<int64_t> chunk_bound;     // host copy of scr_chunk (int32 accumulator headroom of K1)
     snprel::DevBuf<double> scr_part;      // per-block float64 partial sums of the tables kernel
     snprel::DevBuf<double> scr_out;       // device result of the last epilogue (kept across calls and row windows)
     snprel::DevBuf<double> scr_diag;      // diagonal staging of the trace
@@ -181,7 +193,6 @@ struct snprel_ctx {
     int count_engine = 0;                 // 0: packed-bit pair kernels (default), 1: tensor pipe
     int round_mode = 0;                   // 0: round to nearest + worst-case bound (default), 1: randomised + Hoeffding
     std::vector<int> host_cnt;
-    std::vector<int2> host_tiles;
 
     // window-invariant products of the covariance path, kept across row windows (tiled N x N
     // output: every window re-uses the plan statistics, digit tables and per-sample vectors).
@@ -194,7 +205,7 @@ struct snprel_ctx {
     } plan_cache;
     struct PrepCache {
         uint64_t version = 0;
-        int est = -1, bayesian = 0, f = 0, fw = 0, fd = 0, nU = 0, nW = 0, nD = 0, nD2 = 0, round_mode = 0;
+        int est = -1, bayesian = 0, f = 0, fw = 0, fd = 0, fv = 0, nU = 0, nW = 0, nD = 0, nD2 = 0, round_mode = 0;
         bool reduced = false;   // the per-sample vectors / scalars already hold the all-reduced sums
     } prep_cache;
 
@@ -207,6 +218,7 @@ struct snprel_ctx {
     // hot-kernel bookkeeping for bench.py
     double hot_ms = 0;
     int64_t hot_launches = 0;
+    int64_t hot_items = 0;       // work items (CTA pairs) of the last table-Gram launch
     double hot_units = 0;
     double step_ms = 0;          // whole plan + accumulate (CUDA events)
     double plan_ms = 0;
@@ -277,12 +289,18 @@ void indiv_beta_finish(snprel_ctx *c, int inbreeding, int grm_flavour, double *o
                        double *avg_out);
 
 // gram_tc.cu
+constexpr int GRAM_CHUNK = 512;   // SNPs per chunk of the |B| bounds below
 struct GramPass {
-    const uint32_t *tabA;   // device [snp_cap] : 4 int8 digits per SNP (byte g = genotype code g)
-    uint32_t tabB;          // 4 int8 values (byte g = genotype code g)
+    const uint32_t *tabA;   // device [snp_cap]: 4 int8 digits per SNP (byte g = genotype code g)
+    const uint32_t *tabB;   // device [snp_cap]: 4 int8 column values per SNP (gram_const_table for a constant table)
     int plane;              // output plane
     int shift;              // contribution = acc << shift
+    int b_abs_max;          // max |tabB entry|: int32 accumulator headroom
+    // optional, per GRAM_CHUNK SNPs: bound on sum_l |tabB_l[g_jl]| over the chunk for ANY sample j
+    // (tighter than b_abs_max x GRAM_CHUNK; lets a long SNP range stay in one int32 accumulation)
+    const std::vector<int64_t> *b_chunk_bound;
 };
+const uint32_t *gram_const_table(snprel_ctx *c, uint32_t word);
 void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *out_planes,
                  bool upper_only);
 

@@ -92,7 +92,7 @@ void tensor_count_accumulate(snprel_ctx *c, int est) {
     cacc.alloc((size_t)np * win.rows * npad);
     cacc.zero(c->stream);
     std::vector<GramPass> passes;
-    for (int p = 0; p < np; p++) passes.push_back({tab_of(cp[p].a), cp[p].b, p, 0});
+    for (int p = 0; p < np; p++) passes.push_back({tab_of(cp[p].a), gram_const_table(c, cp[p].b), p, 0, 1, nullptr});
     c->cnt.alloc((size_t)nc * win.rows * npad);
     c->cnt_planes = nc;
     c->cnt.zero(c->stream);

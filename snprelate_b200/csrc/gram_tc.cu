@@ -51,41 +51,56 @@ constexpr int HM = 128, HN = 128;  // per-CTA halves
 constexpr int SK = 128;            // SNPs per stage
 constexpr int MMA_K = 32;
 constexpr int NSTAGE = 4;
-constexpr int MAXP = 2;
 constexpr int PROD_WARPS = 8;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int FIRST_PROD_WARP = 2;
 constexpr int THREADS = 32 * (FIRST_PROD_WARP + PROD_WARPS);
 constexpr int A_BYTES = HM * SK;   // 16 KB per pass per stage
 constexpr int B_BYTES = HN * SK;   // 16 KB per stage
-// A launch fills the two TMEM accumulators either with two passes over one B tile (NP=2, NB=1)
+// An item fills the two TMEM accumulators either with two passes over one B tile (NP=2, NB=1)
 // or with ONE pass over two B tiles (NP=1, NB=2: a 256 x 512 tile, so that the odd pass of a
-// table costs half a launch instead of ~0.8).  Either way a stage holds three 16 KB operands.
+// table costs half an item instead of ~0.8).  Either way a stage holds three 16 KB operands.
 constexpr int STAGE_BYTES = 3 * A_BYTES;   // 48 KB
 constexpr int PF_BOX = SK * 16;
 constexpr int PF_TAB = SK * 4;
 constexpr int PF_MAX_DEPTH = 3;
-constexpr int PF_RING_BYTES = 27648;       // 3 x (4 boxes + 2 tables) or 2 x (6 boxes + 1 table)
+constexpr int PF_RING_BYTES = 29184;       // 3 x (4 boxes + 2 A tables + 1 B table) or 2 x (6 boxes + 1 + 1)
 constexpr int BAR_OFFSET = NSTAGE * STAGE_BYTES + PF_RING_BYTES;
 constexpr int SMEM_BYTES = BAR_OFFSET + 1024;
 constexpr int LBO = (HM / 16) * 128;   // 8 cores per 8-SNP group (A and B halves alike)
 constexpr int SBO = 128;
 constexpr uint32_t TMEM_COLS = 512;
 
+// one digit pass: per-SNP A table (4 int8 digits by genotype code) against a per-SNP B table
+struct PassDesc {
+    const uint32_t *tabA;
+    const uint32_t *tabB;
+    int plane;   // output plane
+    int shift;   // contribution = acc << shift
+};
+
+// One work item = one CTA pair: a 256-row tile x one or two 256-column B tiles x an SNP range.
+// All items of a step go out in ONE launch (heterogeneous grid); the hardware block scheduler
+// deals them to the 74 CTA-pair slots in list order, so the host orders them for L2 locality
+// (tile-major, super-tile raster) and puts the small ones last (wave tail).
+struct Item {
+    int tm;              // A tile row, units of 256 samples
+    int tn;              // first B tile column, units of 256 samples
+    int st_begin, st_end;
+    short ncols[2];      // MMA N of each B tile: 0 (absent / below the diagonal), 128 or 256
+    short mode;          // 0: NP=2 passes x NB=1 B tile; 1: NP=1 pass x NB=2 B tiles
+    short pad;
+    int pass[2];
+};
+
 struct Params {
-    const uint32_t *tabA[MAXP];
-    uint32_t tabB;
-    int npass;
-    int plane[MAXP];
-    int shift[MAXP];
+    const Item *items;
+    const PassDesc *passes;
     long long *out;
     long long ld;
     long long plane_stride;
     long long n_samp;
     long long row0;          // first row of the output window (planes hold rows row0 ..)
-    const int2 *tiles;       // (tile_m, tile_n) in units of 256 samples
-    int stages_total;
-    int stages_per_split;
     int upper_only;
     uint32_t sh32;
     int *error_flag;
@@ -154,21 +169,20 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
         ::"r"(bar)
         : "memory");
 }
-// D=s32, A=s8, B=s8, MN-major, M=256 (pair), N=256
-__device__ __forceinline__ uint32_t make_idesc2() {
-    return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TN2 >> 3) << 17) |
+// D=s32, A=s8, B=s8, MN-major, M=256 (pair), N = ncols (32 .. 256)
+__device__ __forceinline__ uint32_t make_idesc2(int ncols) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(ncols >> 3) << 17) |
            ((uint32_t)(TM2 >> 4) << 24);
 }
 
 template <int NP, int NB>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap tmap) {
+__device__ __forceinline__ void gram_item(const Params &P, const Item &item, const CUtensorMap *tmap, uint8_t *smem) {
     static_assert(NP * NB == 2, "two TMEM accumulators of 256 columns");
     constexpr int PF_DEPTH = NB == 1 ? 3 : 2;
     constexpr int PF_NBOX = 2 + 2 * NB;                       // A quads 0-1, then two quads per B tile
-    constexpr int PF_BYTES = PF_NBOX * PF_BOX + NP * PF_TAB;
+    constexpr int PF_BYTES = PF_NBOX * PF_BOX + (NP + 1) * PF_TAB;   // boxes, NP A tables, the B table
     static_assert(PF_DEPTH * PF_BYTES <= PF_RING_BYTES, "ring does not fit");
-    extern __shared__ __align__(1024) uint8_t smem[];
+    static_assert(PF_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const uint32_t smem_base = smem_u32(smem);
@@ -183,11 +197,15 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem + BAR_OFFSET + 8 * SLOT_IDX);
     const uint32_t pf_base = smem_base + NSTAGE * STAGE_BYTES;
 
-    const int2 tile = P.tiles[blockIdx.x >> 1];
-    const int st_begin = blockIdx.y * P.stages_per_split;
-    const int st_end = min(P.stages_total, st_begin + P.stages_per_split);
-    const int nst = st_end - st_begin;   // identical in both CTAs of the pair
+    const int st_begin = item.st_begin;
+    const int nst = item.st_end - item.st_begin;   // identical in both CTAs of the pair
     if (nst <= 0) return;
+    int ncols[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) ncols[b] = item.ncols[b];
+    PassDesc pd[NP];
+#pragma unroll
+    for (int q = 0; q < NP; q++) pd[q] = P.passes[item.pass[q]];
 
     if (warp == 0) {
         if (lane == 0) {
@@ -214,7 +232,9 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
     if (warp == 0) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (rank == 0) {
-            const uint32_t idesc = make_idesc2();
+            uint32_t idesc[NB];
+#pragma unroll
+            for (int b = 0; b < NB; b++) idesc[b] = make_idesc2(ncols[b]);
             for (int it = 0; it < nst; it++) {
                 const int s = it % NSTAGE;
                 const uint32_t phase = (uint32_t)(it / NSTAGE) & 1u;
@@ -226,11 +246,12 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
                     for (int j = 0; j < SK / MMA_K; j++) {
 #pragma unroll
                         for (int b = 0; b < NB; b++) {
+                            if (ncols[b] == 0) continue;
                             uint64_t bdesc = make_desc(stage_addr + (NP + b) * A_BYTES + j * 4 * LBO, LBO, SBO);
 #pragma unroll
                             for (int p = 0; p < NP; p++) {
                                 uint64_t adesc = make_desc(stage_addr + p * A_BYTES + j * 4 * LBO, LBO, SBO);
-                                umma2_i8(tmem_base + (uint32_t)((p * NB + b) * TN2), adesc, bdesc, idesc,
+                                umma2_i8(tmem_base + (uint32_t)((p * NB + b) * TN2), adesc, bdesc, idesc[b],
                                          (it > 0 || j > 0) ? 1u : 0u);
                             }
                         }
@@ -245,29 +266,36 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
     } else if (warp == 1) {
         // ===================== TMA loader =====================
         if (lane == 0) {
-            const int ax = (tile.x * TM2 + (int)rank * HM) / 4;
+            const int ax = (item.tm * TM2 + (int)rank * HM) / 4;
+            uint32_t tx_bytes = 2 * PF_BOX + (NP + 1) * PF_TAB;
+#pragma unroll
+            for (int b = 0; b < NB; b++) tx_bytes += ncols[b] ? 2 * PF_BOX : 0;
             for (int it = 0; it < nst; it++) {
                 const int sl = it % PF_DEPTH;
                 const uint32_t ph = (uint32_t)(it / PF_DEPTH) & 1u;
                 mbar_wait(pf_empty(sl), ph ^ 1u, P.error_flag, 4);
                 const uint32_t slot = pf_base + (uint32_t)sl * PF_BYTES;
                 const uint32_t bar = pf_full(sl);
-                mbar_arrive_expect_tx(bar, PF_NBOX * PF_BOX + NP * PF_TAB);
+                mbar_arrive_expect_tx(bar, tx_bytes);
                 const int y = (st_begin + it) * SK;
 #pragma unroll
-                for (int q = 0; q < HM / 64; q++) tma_load_2d(slot + q * PF_BOX, &tmap, ax + q * 16, y, bar);
+                for (int q = 0; q < HM / 64; q++) tma_load_2d(slot + q * PF_BOX, tmap, ax + q * 16, y, bar);
 #pragma unroll
                 for (int b = 0; b < NB; b++) {
-                    // columns beyond the padded matrix are out of bounds for the tensor map and arrive
-                    // as zeros (code 0 against tabB[0] = 0 in every channel): they contribute nothing
-                    const int bx = ((tile.y * NB + b) * TN2 + (int)rank * HN) / 4;
+                    if (ncols[b] == 0) continue;
+                    // this CTA's half of the B tile's ncols columns starts at sample rank * ncols / 2 of the
+                    // tile, wherever that falls inside a 16-byte group: box coordinates are free.  Columns
+                    // beyond the padded matrix are out of bounds for the tensor map and arrive as zeros
+                    // (code 0); the epilogue drops them.
+                    const int bx = ((item.tn + b) * TN2 + (int)rank * (ncols[b] >> 1)) / 4;
 #pragma unroll
                     for (int q = 0; q < HN / 64; q++)
-                        tma_load_2d(slot + (2 + 2 * b + q) * PF_BOX, &tmap, bx + q * 16, y, bar);
+                        tma_load_2d(slot + (2 + 2 * b + q) * PF_BOX, tmap, bx + q * 16, y, bar);
                 }
 #pragma unroll
                 for (int q = 0; q < NP; q++)
-                    bulk_load(slot + PF_NBOX * PF_BOX + q * PF_TAB, P.tabA[q] + (long long)y, PF_TAB, bar);
+                    bulk_load(slot + PF_NBOX * PF_BOX + q * PF_TAB, pd[q].tabA + (long long)y, PF_TAB, bar);
+                bulk_load(slot + PF_NBOX * PF_BOX + NP * PF_TAB, pd[0].tabB + (long long)y, PF_TAB, bar);
             }
         }
         __syncwarp();
@@ -277,12 +305,14 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
         const int sl = p & (SK - 1);   // SNP within the stage
         const int half = p >> 7;       // which 64-sample quad of this CTA's A half and of its B half
         const int kg = sl >> 3, r = sl & 7;
-        uint32_t tb[1] = {P.tabB};
         const uint32_t a_off = kg * LBO + (half * 4) * SBO + r * 16;
         const uint32_t b_off = NP * A_BYTES + a_off;
         const uint32_t pa = half * PF_BOX + sl * 16;
         const uint32_t pb = (2 + half) * PF_BOX + sl * 16;
         const uint32_t pt = PF_NBOX * PF_BOX + sl * 4;
+        int bwords[NB];                // 16-sample words of B tile b this thread expands (0..4)
+#pragma unroll
+        for (int b = 0; b < NB; b++) bwords[b] = min(4, max(0, (ncols[b] >> 5) - 4 * half));
         uint32_t full_remote[NSTAGE];
 #pragma unroll
         for (int s = 0; s < NSTAGE; s++) full_remote[s] = mapa(full_bar(s), 0);   // leader's barrier
@@ -297,11 +327,12 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
             const uint4 ca = ld_shared_v4(slot + pa);
             uint4 cb[NB];
 #pragma unroll
-            for (int b = 0; b < NB; b++) cb[b] = ld_shared_v4(slot + pb + 2 * b * PF_BOX);
+            for (int b = 0; b < NB; b++) cb[b] = bwords[b] ? ld_shared_v4(slot + pb + 2 * b * PF_BOX) : make_uint4(0, 0, 0, 0);
             uint32_t ct[NP];
 #pragma unroll
             for (int q = 0; q < NP; q++) ct[q] = ld_shared_u32(slot + pt + q * PF_TAB);
-            uint32_t dep = ca.x ^ ca.y ^ ca.z ^ ca.w ^ ct[0] ^ ct[NP - 1];
+            uint32_t tb[1] = {ld_shared_u32(slot + pt + NP * PF_TAB)};
+            uint32_t dep = ca.x ^ ca.y ^ ca.z ^ ca.w ^ ct[0] ^ ct[NP - 1] ^ tb[0];
 #pragma unroll
             for (int b = 0; b < NB; b++) dep ^= cb[b].x ^ cb[b].y ^ cb[b].z ^ cb[b].w;
             mbar_arrive_after(pf_empty(ps), dep, P.sh32);
@@ -321,8 +352,10 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
                 const uint32_t bw[4] = {cb[b].x, cb[b].y, cb[b].z, cb[b].w};
 #pragma unroll
                 for (int w = 0; w < 4; w++) {
-                    uint32_t dst[1] = {stage_addr + b_off + b * B_BYTES + w * SBO};
-                    expand_word<1>(bw[w], tb, dst);
+                    if (w < bwords[b]) {
+                        uint32_t dst[1] = {stage_addr + b_off + b * B_BYTES + w * SBO};
+                        expand_word<1>(bw[w], tb, dst);
+                    }
                 }
             }
             fence_proxy_async_smem();
@@ -339,26 +372,53 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
         const int quarter = warp & 3;
         const int colhalf = (warp - FIRST_PROD_WARP) >> 2;
         const int row = quarter * 32 + lane;
-        const long long gi = (long long)tile.x * TM2 + (long long)rank * HM + (row & ~15) + core_pos_to_sample(row & 15);
-#pragma unroll 1
-        for (int a = 0; a < 2; a++) {        // accumulator a = pass (a / NB), B tile (a % NB)
-            const int q = a / NB, bt = a % NB;
-            long long *outp = P.out + (long long)P.plane[q] * P.plane_stride + (gi - P.row0) * P.ld;
-            const long long mul = 1ll << P.shift[q];
+        const long long gi = (long long)item.tm * TM2 + (long long)rank * HM + (row & ~15) + core_pos_to_sample(row & 15);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        // two digit passes that feed the same plane leave as ONE 64-bit atomic per entry
+        const bool combine = NP == 2 && pd[0].plane == pd[NP - 1].plane;
+        if (combine) {
+            long long *outp = P.out + (long long)pd[0].plane * P.plane_stride + (gi - P.row0) * P.ld;
+            const long long mul0 = 1ll << pd[0].shift, mul1 = 1ll << pd[NP - 1].shift;
 #pragma unroll 1
             for (int cc = 0; cc < 4; cc++) {
-                const int col0 = colhalf * 128 + cc * 32;
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * TN2 + col0), v);
+                const int col0 = (2 * cc + colhalf) * 32;
+                if (col0 >= ncols[0]) break;
+                uint32_t v0[32], v1[32];
+                tmem_ld32(lane_base + (uint32_t)col0, v0);
+                tmem_ld32(lane_base + (uint32_t)(TN2 + col0), v1);
                 if (gi < P.n_samp) {
 #pragma unroll
                     for (int k = 0; k < 32; k++) {
-                        int col = col0 + k;
-                        long long gj = ((long long)tile.y * NB + bt) * TN2 + (col & ~15) + core_pos_to_sample(col & 15);
-                        int val = (int)v[k];
+                        const int col = col0 + k;
+                        const long long gj = (long long)item.tn * TN2 + (col & ~15) + core_pos_to_sample(col & 15);
+                        const long long val = (long long)(int)v0[k] * mul0 + (long long)(int)v1[k] * mul1;
                         if (val != 0 && gj < P.n_samp && (!P.upper_only || gj >= gi))
-                            atomicAdd(reinterpret_cast<unsigned long long *>(outp + gj),
-                                      (unsigned long long)((long long)val * mul));
+                            atomicAdd(reinterpret_cast<unsigned long long *>(outp + gj), (unsigned long long)val);
+                    }
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int a = 0; a < 2; a++) {        // accumulator a = pass (a / NB), B tile (a % NB)
+                const int q = a / NB, bt = a % NB;
+                long long *outp = P.out + (long long)pd[q].plane * P.plane_stride + (gi - P.row0) * P.ld;
+                const long long mul = 1ll << pd[q].shift;
+#pragma unroll 1
+                for (int cc = 0; cc < 4; cc++) {
+                    const int col0 = (2 * cc + colhalf) * 32;
+                    if (col0 >= ncols[bt]) break;
+                    uint32_t v[32];
+                    tmem_ld32(lane_base + (uint32_t)(a * TN2 + col0), v);
+                    if (gi < P.n_samp) {
+#pragma unroll
+                        for (int k = 0; k < 32; k++) {
+                            const int col = col0 + k;
+                            const long long gj = ((long long)item.tn + bt) * TN2 + (col & ~15) + core_pos_to_sample(col & 15);
+                            const int val = (int)v[k];
+                            if (val != 0 && gj < P.n_samp && (!P.upper_only || gj >= gi))
+                                atomicAdd(reinterpret_cast<unsigned long long *>(outp + gj),
+                                          (unsigned long long)((long long)val * mul));
+                        }
                     }
                 }
             }
@@ -373,40 +433,46 @@ table_gram_kernel2(const __grid_constant__ Params P, const __grid_constant__ CUt
     }
 }
 
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+table_gram_kernel3(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const Item item = P.items[blockIdx.x >> 1];
+    if (item.mode == 0)
+        gram_item<2, 1>(P, item, &tmap, smem);
+    else
+        gram_item<1, 2>(P, item, &tmap, smem);
+}
+
 }  // namespace tc2
 
 // ---------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------
-// fraction of the SM-time of a launch that does useful work when `items` equal work items run
-// `slots` at a time (wave quantisation)
-static double wave_efficiency(int64_t items, int64_t slots) {
-    int64_t waves = (items + slots - 1) / slots;
-    return (double)items / (double)(waves * slots);
+// device array of snp_cap copies of one table word (constant tables: the x / m channels, the
+// {-1,0,1} tables of the tensor count engine), built once per (word, capacity)
+__global__ void fill_table_kernel(uint32_t *__restrict__ p, int64_t n, uint32_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+const uint32_t *gram_const_table(snprel_ctx *c, uint32_t word) {
+    for (auto &t : c->const_tabs)
+        if (t->word == word && (int64_t)t->buf.n >= c->snp_cap) return t->buf.p;
+    std::unique_ptr<snprel_ctx::ConstTab> t(new snprel_ctx::ConstTab());
+    t->word = word;
+    t->buf.alloc((size_t)c->snp_cap);
+    fill_table_kernel<<<(unsigned)((c->snp_cap + 255) / 256), 256, 0, c->stream>>>(t->buf.p, c->snp_cap, word);
+    KERNEL_CHECK(c);
+    c->const_tabs.push_back(std::move(t));
+    return c->const_tabs.back()->buf.p;
 }
 
-// SNP splits for `ntile` tiles: enough work items to fill the chip, chosen to minimise the
-// wave-quantisation tail (74 CTA pairs run at a time)
-static void choose_splits(snprel_ctx *c, int64_t ntile, int stages_total, int SK, int &sps, int64_t &splits) {
-    const int64_t slots = std::max(1, c->num_sms / 2);
-    int64_t best = 1;
-    double best_eff = -1;
-    for (int64_t sp = 1; sp <= std::min<int64_t>(stages_total, 64); sp++) {
-        // each extra split costs one more epilogue of 64-bit atomics per tile
-        double eff = wave_efficiency(ntile * sp, slots) * (1.0 - 0.002 * (double)(sp - 1));
-        if (eff > best_eff + 1e-9) {
-            best_eff = eff;
-            best = sp;
-        }
-        if (ntile * sp >= 8 * slots && eff > 0.97) break;
-    }
-    splits = best;
-    if (c->debug_flags & 2u) splits = 1;   // test hook: one CTA pair walks the whole SNP range
-    sps = (int)((stages_total + splits - 1) / splits);
-    const int max_stages_i32 = (int)((2147483647ll / 256) / SK);   // int32 accumulator headroom
-    sps = std::min(sps, max_stages_i32);
-    splits = (stages_total + sps - 1) / sps;
-    if (splits > 65535) fail("too many SNP splits");
+// MMA N for a B tile with `nvalid` live columns: 128 or 256.  (The instruction set lists every
+// multiple of 32 from 32 for M = 256 / cta_group::2 / kind::i8, but with this MN-major operand
+// layout N = 32 and N = 64 raise "illegal instruction" on the B200 -- measured in round 2 -- so the
+// ragged last tile column only drops to half width.)
+static int tile_ncols(int64_t nvalid) {
+    if (nvalid <= 0) return 0;
+    return nvalid <= 128 ? 128 : 256;
 }
 
 void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *out_planes, bool upper_only) {
@@ -416,29 +482,144 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     const int64_t n = c->n_samp, npad = c->n_samp_pad;
     const int nt = (int)((n + TM2 - 1) / TM2);
     const RowWin win = row_window(c);
-    // two work lists: 256 x 256 tiles for two-pass launches, 256 x 512 tiles for one-pass launches
-    std::vector<int2> &tiles = c->host_tiles;
-    tiles.clear();
-    for (int tm = (int)(win.r0 / TM2); tm < nt && (long long)tm * TM2 < win.r1; tm++)
-        for (int tn = (upper_only ? tm : 0); tn < nt; tn++) tiles.push_back(make_int2(tm, tn));
-    const size_t n1 = tiles.size();
-    for (int tm = (int)(win.r0 / TM2); tm < nt && (long long)tm * TM2 < win.r1; tm++)
-        for (int tn2 = (upper_only ? tm / 2 : 0); 2 * tn2 < nt; tn2++) tiles.push_back(make_int2(tm, tn2));
-    const size_t n2 = tiles.size() - n1;
-    if (n1 == 0) return;
-    DevBuf<int2> &dtiles = c->scr_tiles;
-    dtiles.alloc(tiles.size());
-    CUDA_CHECK(cudaMemcpyAsync(dtiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice,
-                               c->stream));
+    const int tm_lo = (int)(win.r0 / TM2), tm_hi = (int)std::min<int64_t>(nt, (win.r1 + TM2 - 1) / TM2);
+    if (tm_hi <= tm_lo) return;
+    const int stages_total = (int)(round_up(std::max<int64_t>(c->n_snp, 1), SK) / SK);
+    const int64_t slots = std::max(1, c->num_sms / 2);
+
+    // ---- pass groups: two passes that share a B table fill the two accumulators of a 256 x 256
+    // tile (mode 0); a pass left over runs alone over 256 x 512 tiles (mode 1)
+    struct Group { int mode; int pass[2]; };
+    std::vector<Group> groups;
+    std::vector<PassDesc> pd((size_t)npass);
+    for (int i = 0; i < npass; i++) pd[i] = PassDesc{passes[i].tabA, passes[i].tabB, passes[i].plane, passes[i].shift};
+    {
+        std::vector<char> used((size_t)npass, 0);
+        for (int i = 0; i < npass; i++) {
+            if (used[i]) continue;
+            used[i] = 1;
+            int mate = -1;
+            for (int j = i + 1; j < npass && mate < 0; j++)   // same plane first: their atomics are combined
+                if (!used[j] && passes[j].tabB == passes[i].tabB && passes[j].plane == passes[i].plane) mate = j;
+            for (int j = i + 1; j < npass && mate < 0; j++)
+                if (!used[j] && passes[j].tabB == passes[i].tabB) mate = j;
+            if (mate >= 0) {
+                used[mate] = 1;
+                groups.push_back({0, {i, mate}});
+            } else {
+                groups.push_back({1, {i, i}});
+            }
+        }
+    }
+
+    // ---- SNP segments per group.  (a) int32 accumulator headroom: |digit| <= 128 and a bound on
+    // sum_l |B_l[g_jl]| per 512-SNP chunk (measured by the caller, or max|B| x 512);  (b) enough
+    // items to fill the chip when the tile grid alone is small.
+    int64_t base_items = 0;
+    for (int tm = tm_lo; tm < tm_hi; tm++) {
+        const int ncol = nt - (upper_only ? tm : 0);
+        for (auto &g : groups) base_items += g.mode == 0 ? ncol : (ncol + 1) / 2;
+    }
+    int parts = 1;
+    if (!(c->debug_flags & 2u) && base_items < 8 * slots)
+        parts = (int)std::min<int64_t>(std::min<int64_t>((8 * slots + base_items - 1) / base_items, 64),
+                                       std::max(1, stages_total / 4));
+    std::vector<std::vector<int>> cuts(groups.size());   // stage boundaries, ascending, first 0, last stages_total
+    const int CH = GRAM_CHUNK / SK;                        // stages per bound chunk
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+        const GramPass &ps = passes[groups[gi].pass[0]];
+        std::vector<int> &cu = cuts[gi];
+        cu.push_back(0);
+        std::vector<int> want;                             // wished part boundaries, multiples of a chunk
+        for (int k = 1; k < parts; k++) {
+            const int bnd = (int)((long long)k * stages_total / parts) / CH * CH;
+            if (bnd > 0 && bnd < stages_total && (want.empty() || bnd > want.back())) want.push_back(bnd);
+        }
+        size_t wi = 0;
+        long long acc = 0;
+        for (int st = 0; st < stages_total; st += CH) {
+            const size_t ck = (size_t)(st / CH);
+            long long cb = (ps.b_chunk_bound && ck < ps.b_chunk_bound->size())
+                               ? std::min<long long>((*ps.b_chunk_bound)[ck], (long long)ps.b_abs_max * GRAM_CHUNK)
+                               : (long long)ps.b_abs_max * GRAM_CHUNK;
+            cb *= 128;
+            if (cb > 2147483647ll) fail("internal: one SNP chunk overflows the int32 accumulator");
+            const bool part_cut = wi < want.size() && st >= want[wi];
+            if (st > cu.back() && (acc + cb > 2147483647ll || part_cut)) {
+                cu.push_back(st);
+                acc = 0;
+            }
+            while (wi < want.size() && st >= want[wi]) wi++;
+            acc += cb;
+        }
+        cu.push_back(stages_total);
+    }
+
+    // ---- the item list: tile-major (all pass groups of a tile are neighbours, so the co-resident
+    // CTA pairs share genotype panels in L2), tiles in a super-tile raster
+    std::vector<Item> items;
+    auto width = [&](int t) { return tile_ncols(std::min<int64_t>(TN2, n - (int64_t)t * TN2)); };
+    auto emit = [&](int tm, int tn) {
+        const int first_col = upper_only ? tm : 0;
+        for (size_t gi = 0; gi < groups.size(); gi++) {
+            const Group &g = groups[gi];
+            Item it{};
+            it.tm = tm;
+            it.mode = (short)g.mode;
+            it.pass[0] = g.pass[0];
+            it.pass[1] = g.pass[1];
+            if (g.mode == 0) {
+                it.tn = tn;
+                it.ncols[0] = (short)width(tn);
+                it.ncols[1] = 0;
+            } else {
+                const int tn2 = tn / 2;
+                if (tn != std::max(2 * tn2, first_col)) continue;   // the pair is emitted at its first live column
+                it.tn = 2 * tn2;
+                it.ncols[0] = (short)(2 * tn2 >= first_col ? width(2 * tn2) : 0);
+                it.ncols[1] = (short)(2 * tn2 + 1 < nt ? width(2 * tn2 + 1) : 0);
+            }
+            for (size_t k = 0; k + 1 < cuts[gi].size(); k++) {
+                it.st_begin = cuts[gi][k];
+                it.st_end = cuts[gi][k + 1];
+                items.push_back(it);
+            }
+        }
+    };
+    constexpr int RB = 8, CB = 8;
+    for (int rb = tm_lo / RB * RB; rb < tm_hi; rb += RB)
+        for (int cb = (upper_only ? rb / CB * CB : 0); cb < nt; cb += CB)
+            for (int tm = std::max(rb, tm_lo); tm < std::min(rb + RB, tm_hi); tm++)
+                for (int tn = std::max(cb, upper_only ? tm : 0); tn < std::min(cb + CB, nt); tn++) emit(tm, tn);
+    if (items.empty()) return;
+    // wave tail: the items that start last are cut in four, so the chip drains in quarter steps
+    if (!(c->debug_flags & 2u) && parts == 1 && (int64_t)items.size() > 4 * slots) {
+        const size_t ntail = (size_t)(slots + slots / 2);
+        std::vector<Item> tail(items.end() - ntail, items.end());
+        items.resize(items.size() - ntail);
+        for (const Item &it : tail) {
+            const int len = it.st_end - it.st_begin;
+            if (len < 64) {
+                items.push_back(it);
+                continue;
+            }
+            for (int q = 0; q < 4; q++) {
+                Item sub = it;
+                sub.st_begin = it.st_begin + (int)((long long)len * q / 4);
+                sub.st_end = it.st_begin + (int)((long long)len * (q + 1) / 4);
+                items.push_back(sub);
+            }
+        }
+    }
+    if (items.size() > 0x3fffffffull) fail("too many work items");
+
+    c->scr_items.alloc(items.size() * sizeof(Item));
+    c->scr_passes.alloc(pd.size() * sizeof(PassDesc));
+    CUDA_CHECK(cudaMemcpyAsync(c->scr_items.p, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->scr_passes.p, pd.data(), pd.size() * sizeof(PassDesc), cudaMemcpyHostToDevice, c->stream));
     c->scr_flags.alloc(2);
     int *derr = c->scr_flags.p + 1;
     CUDA_CHECK(cudaMemsetAsync(derr, 0, sizeof(int), c->stream));
-
-    const int stages_total = (int)(round_up(std::max<int64_t>(c->n_snp, 1), SK) / SK);
-    int sps1 = 1, sps2 = 1;
-    int64_t splits1 = 1, splits2 = 1;
-    choose_splits(c, (int64_t)n1, stages_total, SK, sps1, splits1);
-    choose_splits(c, (int64_t)n2, stages_total, SK, sps2, splits2);
 
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -465,79 +646,29 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     }
 
     if (!c->gram_attr_done) {   // per device: a process may hold contexts on several GPUs
-        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel2<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel2<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         c->gram_attr_done = true;
     }
 
-    // Experimental (snprel_debug_flags 8, off by default, not yet measured): the launches of one
-    // step only meet in the int64 planes through commutative 64-bit atomics, so they need no
-    // ordering among themselves; issued on alternating streams the first wave of launch k+1 can
-    // fill the SMs that the last, partial wave of launch k leaves idle (820 tiles on 74 CTA-pair
-    // slots = 11.08 waves).
-    const bool overlap = (c->debug_flags & 8u) != 0;
-    if (overlap && !c->aux_stream[0]) {
-        for (int k = 0; k < 2; k++) {
-            CUDA_CHECK(cudaStreamCreateWithFlags(&c->aux_stream[k], cudaStreamNonBlocking));
-            CUDA_CHECK(cudaEventCreateWithFlags(&c->aux_event[k], cudaEventDisableTiming));
-        }
-        CUDA_CHECK(cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming));
-    }
-    if (overlap) {   // fork: the auxiliary streams start after everything queued on the main stream
-        CUDA_CHECK(cudaEventRecord(c->aux_fork, c->stream));
-        for (int k = 0; k < 2; k++) CUDA_CHECK(cudaStreamWaitEvent(c->aux_stream[k], c->aux_fork, 0));
-    }
-    int launch_no = 0;
-    std::vector<char> used((size_t)npass, 0);
-    for (int i = 0; i < npass; i++) {
-        if (used[i]) continue;
-        Params P{};
-        P.tabB = passes[i].tabB;
-        P.out = out_planes;
-        P.ld = npad;
-        P.plane_stride = win.rows * npad;
-        P.row0 = win.r0;
-        P.n_samp = n;
-        P.stages_total = stages_total;
-        P.upper_only = upper_only ? 1 : 0;
-        P.sh32 = 32;
-        P.error_flag = derr;
-        int np = 0;
-        for (int j = i; j < npass && np < MAXP; j++) {
-            if (used[j] || passes[j].tabB != passes[i].tabB) continue;
-            P.tabA[np] = passes[j].tabA;
-            P.plane[np] = passes[j].plane;
-            P.shift[np] = passes[j].shift;
-            used[j] = 1;
-            np++;
-        }
-        P.npass = np;
-        cudaStream_t st = overlap ? c->aux_stream[launch_no & 1] : c->stream;
-        launch_no++;
-        if (np == 2) {
-            P.tiles = dtiles.p;
-            P.stages_per_split = sps1;
-            dim3 grid((unsigned)(2 * n1), (unsigned)splits1);
-            table_gram_kernel2<2, 1><<<grid, THREADS, SMEM_BYTES, st>>>(P, tmap);
-        } else {
-            P.tiles = dtiles.p + n1;
-            P.stages_per_split = sps2;
-            dim3 grid((unsigned)(2 * n2), (unsigned)splits2);
-            table_gram_kernel2<1, 2><<<grid, THREADS, SMEM_BYTES, st>>>(P, tmap);
-        }
-        KERNEL_CHECK(c);
-        c->hot_launches++;
-    }
-    if (overlap) {   // join: the main stream continues after both auxiliary streams
-        for (int k = 0; k < 2; k++) {
-            CUDA_CHECK(cudaEventRecord(c->aux_event[k], c->aux_stream[k]));
-            CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->aux_event[k], 0));
-        }
-    }
+    Params P{};
+    P.items = reinterpret_cast<const Item *>(c->scr_items.p);
+    P.passes = reinterpret_cast<const PassDesc *>(c->scr_passes.p);
+    P.out = out_planes;
+    P.ld = npad;
+    P.plane_stride = win.rows * npad;
+    P.row0 = win.r0;
+    P.n_samp = n;
+    P.upper_only = upper_only ? 1 : 0;
+    P.sh32 = 32;
+    P.error_flag = derr;
+    table_gram_kernel3<<<dim3((unsigned)(2 * items.size())), THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
+    KERNEL_CHECK(c);
+    c->hot_launches++;
+    c->hot_items = (int64_t)items.size();
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     int herr = 0;
     CUDA_CHECK(cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost));
-    if (herr) fail("table_gram_kernel2: pipeline barrier %d timed out", herr);
+    if (herr) fail("table_gram_kernel3: pipeline barrier %d timed out", herr);
 }
 
 }  // namespace snprel

@@ -4,20 +4,27 @@
 //   EIGMIX             CEigMix_AlgArith::Run         src/genEIGMIX.cpp:60-156,645-735
 //   KING-homo sums     CKINGHomo                     src/genKING.cpp:69-266,493-570
 //
-// Algebra.  With x = genotype (0 when missing), m = missing indicator, mu_l the mean
-// genotype of SNP l over non-missing samples and w_l the per-SNP weight
-// (1/(p(1-p)) for Eigenstrat/GCTA, 1 for EIGMIX), the reference accumulates
-//     C_ij = sum_l w_l (x_il - mu_l (1-m_il)) (x_jl - mu_l (1-m_jl)).
-// Define the per-SNP 4-entry tables over the genotype code g (0,1,2,3=missing)
-//     U_l[g] = w_l (g - mu_l)  (U_l[3] = 0),      W_l[g] = mu_l U_l[g].
-// Then  C_ij = sum_l U_l[g_il] x_jl  -  sum_l W_l[g_il]  +  sum_l W_l[g_il] m_jl.
-// The first and third sums are table Grams against the small-integer channels x and
-// m; the middle one is a per-sample vector.  Tables are quantised to fixed point
-// (2^-frac_bits) and split into balanced base-256 digits, one int8 tensor-core pass
-// per digit; the quantisation error of an entry is bounded by
-// 2^-(frac_bits+1) * (2 #SNP + #missing) and everything after quantisation is exact
-// integer arithmetic.  Denominators (GCTA: #polymorphic SNPs with i or j missing;
-// EIGMIX: sum 4p(1-p) over SNPs with i or j missing) use
+// Algebra.  With g the genotype code, v = valid and m = missing indicators, mu_l the mean
+// genotype of SNP l over non-missing samples and w_l the per-SNP weight (1/(p(1-p)) for
+// Eigenstrat/GCTA, 1 for EIGMIX), the reference accumulates
+//     C_ij = sum_l w_l z_il z_jl,     z_il = (g_il - mu_l) v_il.
+// Per SNP pick integers s_l >= 1, t_l >= 0 with the INTEGER column table
+//     B_l[g] = s_l g - t_l  (|B_l[g]| <= 127, B_l[missing] = 0),      delta_l = mu_l - t_l / s_l,
+// so that z_jl = B_l[g_jl] / s_l - delta_l v_jl exactly.  With the real row tables
+//     U_l[g] = w_l (g - mu_l) (0 for missing),   T_l = U_l / s_l,   R_l = delta_l U_l
+// this gives
+//     C_ij = sum_l T_l[g_il] B_l[g_jl]  -  sum_l R_l[g_il]  +  sum_l R_l[g_il] m_jl.
+// The first and third sums are table Grams (real row table against a small-integer column
+// channel: B_l, resp. the missing indicator); the middle one is a per-sample vector.  s_l follows
+// the magnitude of U_l (the row tables of all SNPs get the same dynamic range) and t_l / s_l is
+// the best rational approximation of mu_l in a window of s, which makes R two orders of
+// magnitude smaller than the plain choice s = 1, t = 0 (R = mu U) and saves one digit pass.
+// Row tables are quantised to fixed point (2^-frac_bits) and split into balanced base-256
+// digits, one int8 tensor-core pass per digit; the quantisation error of an entry is bounded by
+//     2^-(f+1) max_j sum_l |B_l[g_jl]|  +  2^-(fw+1) max_j #missing_j
+// (both maxima are MEASURED by sample_stats_kernel) and everything after quantisation is exact
+// integer arithmetic.  Denominators (GCTA: #polymorphic SNPs with i or j missing; EIGMIX: sum
+// 4p(1-p) over SNPs with i or j missing) use
 //     D_ij = r_i + r_j - sum_l d_l m_il m_jl,   r_i = sum_l d_l m_il,
 // i.e. one more table Gram (channel m on both sides) and a per-sample vector.
 #include <cmath>
@@ -26,27 +33,27 @@
 
 namespace snprel {
 
-constexpr uint32_t TABB_X = 0x00020100u;   // x channel: code -> {0,1,2,0}
 constexpr uint32_t TABB_M = 0x01000000u;   // m channel: code -> {0,0,0,1}
 constexpr int MAX_DIGITS = 8;
 
 enum { VEC_W = 0, VEC_D = 1, VEC_HET = 2, VEC_D2 = 3, VEC_WLO = 4, NVEC = 5 };
-constexpr int W_EXTRA_BITS = 20;   // the per-sample W vector carries 20 more fractional bits than the passes
+constexpr int LIMB = 20;           // the per-sample vector is accumulated in 20-bit limbs of int32
+// VEC_W is in units of 2^-(frac_bits_v - 20), VEC_WLO in 2^-frac_bits_v
 // scalars[]: 0 = sum of d_l (EIGMIX SumDenominator / KING-homo sum p(1-p)), 1 = sum d2_l
-// iscalars[]: 0 = nLocus (GCTA), 1 = total missing genotypes (valid samples only)
+// iscalars[]: 0 = nLocus (GCTA), 2 = low limb and 3 = upper limbs of sum_l qb_l (constant of the vector)
 
 struct SnpTables {
-    long long qU[4];   // fixed-point U
-    long long qW[4];   // fixed-point W
-    long long qWx[4];  // fixed-point W with W_EXTRA_BITS more fractional bits (per-sample vector only)
+    long long qU[4];   // fixed-point T = U / s (row table of the main passes)
+    long long qW[4];   // fixed-point R = delta U (row table of the missing-data passes)
+    long long qa, qb;  // the per-sample vector in linear form: R[g] = a g - b, fixed point 2^-frac_bits_v
     double diag;       // sum over samples of U[g] (g - mu): this SNP's contribution to trace(C)
     long long qD;      // fixed-point d (GCTA: 0/1 unscaled; EIGMIX / KING-homo: 2^frac_bits scaled)
     long long qD2;     // KING-homo: (p(1-p))^2
     double d, d2;      // float64 d, d2 (for the global scalars)
-    double maxU, maxW;
+    double maxU, maxW; // max |T|, max |R|
+    int maxB;          // max |B_l[g]|
 };
 
-// est: SNPREL_GRM_EIGENSTRAT / GCTA / CORR / EIGMIX, or SNPREL_EST_KING_HOMO
 // uniform [0, 1) draw of table entry (SNP l, genotype g): randomised rounding (snprel_set_rounding)
 __device__ __forceinline__ double dither_u01(uint64_t seed, long long l, int g) {
     uint64_t x = seed ^ ((uint64_t)l * 4u + (uint64_t)g) * 0xD1342543DE82EF95ull;
@@ -57,46 +64,97 @@ __device__ __forceinline__ double dither_u01(uint64_t seed, long long l, int g) 
     return (double)(x >> 11) * (1.0 / 9007199254740992.0);
 }
 
-// dither != 0: the U table is rounded at random, floor(v 2^f + u) with u ~ U[0, 1) drawn per
-// (global SNP index snp_index, genotype) -- unbiased and independent across SNPs, which is what the
-// Hoeffding bound of choose_format relies on; 0: round to nearest (the default, worst-case bound)
-__device__ __forceinline__ void snp_tables(const SnpStat st, int est, int bayesian, int frac_bits,
-                                           int frac_bits_w, int frac_bits_d, SnpTables &t,
-                                           long long snp_index = 0, uint64_t dither = 0) {
-    const double sc = exp2((double)frac_bits);
-    const double scw = exp2((double)frac_bits_w);
-    const double scd = exp2((double)frac_bits_d);
-    const double scx = exp2((double)(frac_bits + W_EXTRA_BITS));
-    double mu = st.num > 0 ? (double)st.sum / (double)st.num : 0.0;   // DivideGeno, src/genPCA.cpp:98-142
-    double w = 0, d = 0, d2 = 0;
-    long long qD = 0, qD2 = 0;
+// mean, weight and denominators of one SNP.  est: SNPREL_GRM_EIGENSTRAT / GCTA / EIGMIX or
+// SNPREL_EST_KING_HOMO
+struct SnpCoef {
+    double mu, w, d, d2;
+    long long qD;   // GCTA: polymorphic flag
+};
+__device__ __forceinline__ SnpCoef snp_coef(const SnpStat st, int est, int bayesian) {
+    SnpCoef k;
+    k.mu = st.num > 0 ? (double)st.sum / (double)st.num : 0.0;   // DivideGeno, src/genPCA.cpp:98-142
+    k.w = 0;
+    k.d = 0;
+    k.d2 = 0;
+    k.qD = 0;
     if (est == SNPREL_GRM_EIGMIX) {
-        w = 1.0;
-        double af = 0.5 * mu;
-        d = 4 * af * (1 - af);                    // src/genEIGMIX.cpp:116-119
-        qD = llrint(d * scd);
+        k.w = 1.0;
+        double af = 0.5 * k.mu;
+        k.d = 4 * af * (1 - af);                  // src/genEIGMIX.cpp:116-119
     } else if (est == SNPREL_EST_KING_HOMO) {
         double p = st.num > 0 ? 0.5 * (double)st.sum / (double)st.num : 0.0;   // src/genKING.cpp:239-241
-        d = p * (1 - p);
-        d2 = d * d;
-        qD = llrint(d * scd);
-        qD2 = llrint(d2 * scd);
+        k.d = p * (1 - p);
+        k.d2 = k.d * k.d;
     } else {
         if (bayesian) {                           // src/genPCA.cpp:445-452
             double s = ((double)st.sum + 1.0) / (double)(2 * st.num + 2);
             double r = 1.0 / sqrt(s * (1 - s));
-            w = r * r;
+            k.w = r * r;
         } else {                                  // rsqrt_prod, src/genPCA.cpp:145-181
-            double s = mu * 0.5;
+            double s = k.mu * 0.5;
             if (0 < s && s < 1) {
                 double r = 1.0 / sqrt(s * (1 - s));
-                w = r * r;
+                k.w = r * r;
             }
         }
         bool poly = (0 < st.sum) && (st.sum < 2 * st.num);   // src/genPCA.cpp:1206
-        d = poly ? 1.0 : 0.0;
-        qD = poly ? 1 : 0;
+        k.d = poly ? 1.0 : 0.0;
+        k.qD = poly ? 1 : 0;
     }
+    return k;
+}
+
+// ---- per-SNP integer column tables ---------------------------------------------
+// coltab[l] = (s_l, t_l); tabB[l] = bytes (B[0], B[1], B[2], 0); tabBabs[l] = their magnitudes.
+// A pure function of the SNP's own counts, so every rank of a sharded run picks the same table
+// for the same SNP without communication.
+__global__ void coltab_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int est, int bayesian,
+                              int2 *__restrict__ coltab, uint32_t *__restrict__ tabB, uint32_t *__restrict__ tabBabs) {
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_snp) return;
+    const SnpCoef k = snp_coef(st[l], est, bayesian);
+    int s = 1, t = 0;
+    if (est != SNPREL_EST_KING_HOMO && k.w > 0 && st[l].num > 0) {
+        const double mu = k.mu;
+        const double umax = k.w * fmax(mu, 2.0 - mu);
+        const double uref = est == SNPREL_GRM_EIGMIX ? 2.0 : 40.0;   // |U| at MAF 0.05: s saturates there
+        const double s_hi = fmin(floor(127.0 / fmax(2.0 - mu, 1e-9)), 127.0);   // 2 s - t <= 127 with t ~ s mu
+        // (s >= 24 keeps the residual R = delta U of the common SNPs, whose |U| is small, below ~0.1)
+        const double s_tgt = fmin(s_hi, fmax(24.0, 127.0 * umax / uref));
+        double best_e = 1e300;
+        t = (int)rint(mu);
+        for (int q = 0; q <= 30; q++) {      // the s in [0.7, 1] s_tgt whose t / s approximates mu best
+            const double sc = fmax(1.0, floor(s_tgt * (0.7 + 0.01 * q)));
+            const double tc = rint(sc * mu);
+            if (2 * sc - tc > 127.0 || tc > 127.0) continue;
+            const double e = fabs(mu - tc / sc);
+            if (e < best_e) {
+                best_e = e;
+                s = (int)sc;
+                t = (int)tc;
+            }
+        }
+    }
+    coltab[l] = make_int2(s, t);
+    const int b0 = -t, b1 = s - t, b2 = 2 * s - t;
+    tabB[l] = (uint32_t)(b0 & 255) | ((uint32_t)(b1 & 255) << 8) | ((uint32_t)(b2 & 255) << 16);
+    tabBabs[l] = (uint32_t)abs(b0) | ((uint32_t)abs(b1) << 8) | ((uint32_t)abs(b2) << 16);
+}
+
+// dither != 0: the T table is rounded at random, floor(v 2^f + u) with u ~ U[0, 1) drawn per
+// (global SNP index snp_index, genotype) -- unbiased and independent across SNPs, which is what the
+// Hoeffding bound of choose_format relies on; 0: round to nearest (the default, worst-case bound)
+__device__ __forceinline__ void snp_tables(const SnpStat st, int est, int bayesian, int2 ct, int frac_bits,
+                                           int frac_bits_w, int frac_bits_d, int frac_bits_v, SnpTables &t,
+                                           long long snp_index = 0, uint64_t dither = 0) {
+    const double sc = exp2((double)frac_bits);
+    const double scw = exp2((double)frac_bits_w);
+    const double scd = exp2((double)frac_bits_d);
+    const double scv = exp2((double)frac_bits_v);
+    const SnpCoef k = snp_coef(st, est, bayesian);
+    const double mu = k.mu, w = k.w;
+    const double inv_s = 1.0 / (double)ct.x;
+    const double delta = mu - (double)ct.y * inv_s;
     t.maxU = 0;
     t.maxW = 0;
     const int n2 = (st.sum - st.n1) / 2, n0 = st.num - st.n1 - n2;
@@ -104,22 +162,25 @@ __device__ __forceinline__ void snp_tables(const SnpStat st, int est, int bayesi
     t.diag = 0;
 #pragma unroll
     for (int g = 0; g < 3; g++) {
-        double u = (est == SNPREL_EST_KING_HOMO) ? 0.0 : w * ((double)g - mu);
-        double ww = mu * u;
-        t.qU[g] = dither ? (long long)floor(u * sc + dither_u01(dither, snp_index, g)) : llrint(u * sc);
-        t.qW[g] = llrint(ww * scw);
-        t.qWx[g] = llrint(ww * scx);
-        t.maxU = fmax(t.maxU, fabs(u));
-        t.maxW = fmax(t.maxW, fabs(ww));
+        const double u = (est == SNPREL_EST_KING_HOMO) ? 0.0 : w * ((double)g - mu);
+        const double tt = u * inv_s, rr = delta * u;
+        t.qU[g] = dither ? (long long)floor(tt * sc + dither_u01(dither, snp_index, g)) : llrint(tt * sc);
+        t.qW[g] = llrint(rr * scw);
+        t.maxU = fmax(t.maxU, fabs(tt));
+        t.maxW = fmax(t.maxW, fabs(rr));
         t.diag += cnt[g] * u * ((double)g - mu);
     }
     t.qU[3] = 0;
     t.qW[3] = 0;
-    t.qWx[3] = 0;
-    t.qD = qD;
-    t.qD2 = qD2;
-    t.d = d;
-    t.d2 = d2;
+    const double a = (est == SNPREL_EST_KING_HOMO) ? 0.0 : delta * w;
+    t.qa = llrint(a * scv);
+    t.qb = llrint(a * mu * scv);
+    t.maxB = max(ct.y, max(abs(ct.x - ct.y), 2 * ct.x - ct.y));
+    const bool realD = est == SNPREL_GRM_EIGMIX || est == SNPREL_EST_KING_HOMO;
+    t.qD = realD ? llrint(k.d * scd) : k.qD;
+    t.qD2 = est == SNPREL_EST_KING_HOMO ? llrint(k.d2 * scd) : 0;
+    t.d = k.d;
+    t.d2 = k.d2;
 }
 
 __device__ __forceinline__ uint32_t digit_of(long long &q) {
@@ -129,20 +190,20 @@ __device__ __forceinline__ uint32_t digit_of(long long &q) {
 }
 
 // ---- plan statistics ---------------------------------------------------------
-// out[0] max |table value|, out[1] int64-range bound, out[2] total missing,
-// out[3] local share of the normaliser (trace(C) / nLocus / sum d / sum d2)
-__global__ void plan_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int64_t n_samp, int est,
-                            int bayesian, double *__restrict__ out) {
+// out[0] max |T|, out[1] int64-range bound, out[2] total missing,
+// out[3] local share of the normaliser (trace(C) / nLocus / sum d / sum d2), out[4] max |R|
+__global__ void plan_kernel(const SnpStat *__restrict__ st, const int2 *__restrict__ coltab, int64_t n_snp,
+                            int64_t n_samp, int est, int bayesian, double *__restrict__ out) {
     double mx = 0, mxw = 0, sb = 0, tm = 0, sc = 0;
     for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n_snp;
          l += (int64_t)gridDim.x * blockDim.x) {
         SnpTables t;
-        snp_tables(st[l], est, bayesian, 0, 0, 0, t);
+        snp_tables(st[l], est, bayesian, coltab[l], 0, 0, 0, 0, t);
         const bool realD = (est == SNPREL_GRM_EIGMIX || est == SNPREL_EST_KING_HOMO);
         double dmax = realD ? fmax(t.d, t.d2) : 0.0;
         mx = fmax(mx, t.maxU);
         mxw = fmax(mxw, t.maxW);
-        sb += 2 * t.maxU + 2 * t.maxW + 2 * dmax;
+        sb += (double)t.maxB * t.maxU + 2 * t.maxW + 2 * dmax;
         tm += (double)(n_samp - st[l].num);
         if (est == SNPREL_GRM_EIGENSTRAT) sc += t.diag;
         else if (est == SNPREL_GRM_EIGMIX) sc += t.d;
@@ -175,63 +236,137 @@ __global__ void plan_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int64
     }
 }
 
-// per-sample genotype sum and missing count (error weight of the fixed-point format)
-constexpr int SC_SNPS = 2048;
-__global__ void __launch_bounds__(128)
-sample_count_kernel(const uint8_t *__restrict__ geno, int64_t n_snp, int64_t row_bytes, int64_t npad,
-                    int *__restrict__ cnt /*[2][npad]: sum x, #missing*/) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= row_bytes) return;
-    const int64_t l0 = (int64_t)blockIdx.y * SC_SNPS;
-    const int nl = (int)min((int64_t)SC_SNPS, n_snp - l0);
-    const uint8_t *p = geno + l0 * row_bytes + b;
-    // byte-sliced counters: each 2-bit field of a byte counted in its own 8-bit lane
-    uint32_t c1 = 0, c2 = 0, c3 = 0;   // four 8-bit lanes each: #code1, #code2, #code3
-    int s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, s3[4] = {0, 0, 0, 0};
-    for (int s = 0; s < nl; s++) {
-        uint32_t v = p[(int64_t)s * row_bytes];
-        // spread the four 2-bit codes of the byte to the low bits of four byte lanes
-        uint32_t w = (v | (v << 6) | (v << 12) | (v << 18)) & 0x03030303u;
-        uint32_t lo = w & 0x01010101u, hi = (w >> 1) & 0x01010101u;
-        c1 += lo & ~hi;
-        c2 += hi & ~lo;
-        c3 += lo & hi;
-        if ((s & 127) == 127) {   // flush before an 8-bit lane can overflow
+// ---- per-sample statistics in one pass over the 2-bit matrix -----------------
+//   ew[i]      = sum_l |B_l[g_il]|     (error weight of the main passes; int64)
+//   cnt[0][i]  = #heterozygous, cnt[1][i] = #missing
+//   chunk_ew[y] = max over samples of the sum over SNP chunk y (int32 accumulator headroom of K1)
+// One thread per 32-bit word column (16 samples), one block row per GRAM_CHUNK SNPs.  |B| comes from a
+// byte-permute of the SNP's magnitude table (the selector trick of K1's producers) and is summed
+// in 16-bit lanes (512 x 127 < 2^16); the two indicator counts use bit-sliced vertical counters
+// (3 rows in 2-bit fields -> 15 in 4-bit fields -> 255 in bytes -> 16-bit lanes).
+constexpr int SS_THREADS = 128;
+__global__ void __launch_bounds__(SS_THREADS)
+sample_stats_kernel(const uint32_t *__restrict__ geno, const uint32_t *__restrict__ tabBabs, int64_t n_snp,
+                    int64_t row_words, int64_t npad, long long *__restrict__ ew, int *__restrict__ cnt,
+                    int *__restrict__ chunk_ew) {
+    __shared__ uint32_t tab[GRAM_CHUNK + 4];
+    __shared__ int smax[SS_THREADS / 32];
+    const int64_t l0 = (int64_t)blockIdx.y * GRAM_CHUNK;
+    const int nl = (int)min((int64_t)GRAM_CHUNK, n_snp - l0);
+    for (int s = threadIdx.x; s < GRAM_CHUNK + 4; s += blockDim.x) tab[s] = s < nl ? tabBabs[l0 + s] : 0u;
+    __syncthreads();
+    const int64_t wc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = wc < row_words;
+    const uint32_t *p = geno + l0 * row_words + (live ? wc : 0);
+    uint32_t e16[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // |B| sums: selector q -> e16[2q] (bytes 0,2), e16[2q+1] (bytes 1,3)
+    uint32_t m16[8] = {0, 0, 0, 0, 0, 0, 0, 0}, h16[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t m8[4] = {0, 0, 0, 0}, h8[4] = {0, 0, 0, 0};
+    int in8 = 0;
+    for (int r0 = 0; r0 < nl; r0 += 15) {
+        uint32_t m4a = 0, m4b = 0, h4a = 0, h4b = 0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                s1[k] += (c1 >> (8 * k)) & 255;
-                s2[k] += (c2 >> (8 * k)) & 255;
-                s3[k] += (c3 >> (8 * k)) & 255;
+        for (int g5 = 0; g5 < 5; g5++) {
+            uint32_t m2 = 0, h2 = 0;
+            uint32_t w[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const int row = r0 + 3 * g5 + r;
+                w[r] = (live && row < nl) ? __ldg(p + (int64_t)row * row_words) : 0u;   // beyond the chunk: code 0 against a zero table
             }
-            c1 = c2 = c3 = 0;
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const int row = min(r0 + 3 * g5 + r, GRAM_CHUNK + 3);
+                const uint32_t x = w[r], t = tab[row];
+                const uint32_t hi = x >> 1;
+                m2 += x & hi & 0x55555555u;
+                h2 += x & ~hi & 0x55555555u;
+                const uint32_t e = x & 0x33333333u, o = hi >> 1 & 0x33333333u;
+                const uint32_t sel[4] = {e, o, e >> 16, o >> 16};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t v = __byte_perm(t, 0, sel[q]);
+                    e16[2 * q] += __byte_perm(v, 0, 0x4240);
+                    e16[2 * q + 1] += __byte_perm(v, 0, 0x4341);
+                }
+            }
+            m4a += m2 & 0x33333333u;
+            m4b += (m2 >> 2) & 0x33333333u;
+            h4a += h2 & 0x33333333u;
+            h4b += (h2 >> 2) & 0x33333333u;
+        }
+        m8[0] += m4a & 0x0F0F0F0Fu;
+        m8[1] += (m4a >> 4) & 0x0F0F0F0Fu;
+        m8[2] += m4b & 0x0F0F0F0Fu;
+        m8[3] += (m4b >> 4) & 0x0F0F0F0Fu;
+        h8[0] += h4a & 0x0F0F0F0Fu;
+        h8[1] += (h4a >> 4) & 0x0F0F0F0Fu;
+        h8[2] += h4b & 0x0F0F0F0Fu;
+        h8[3] += (h4b >> 4) & 0x0F0F0F0Fu;
+        if (++in8 == 17 || r0 + 15 >= nl) {      // 17 x 15 = 255 rows: bytes are about to overflow
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                m16[2 * q] += m8[q] & 0x00FF00FFu;
+                m16[2 * q + 1] += (m8[q] >> 8) & 0x00FF00FFu;
+                h16[2 * q] += h8[q] & 0x00FF00FFu;
+                h16[2 * q + 1] += (h8[q] >> 8) & 0x00FF00FFu;
+                m8[q] = 0;
+                h8[q] = 0;
+            }
+            in8 = 0;
+        }
+    }
+    // sample positions.  |B| lanes: selector q = (e, o, e>>16, o>>16) covers samples 2j + (q & 1) + 8 (q >> 1),
+    // j = byte index 0..3; e16[2q] holds bytes 0 and 2, e16[2q+1] bytes 1 and 3.
+    // indicator lanes: m8[0] samples 0,4,8,12; m8[1] 2,6,10,14; m8[2] 1,5,9,13; m8[3] 3,7,11,15 (byte index b);
+    // m16[2q] holds bytes 0 and 2 of m8[q], m16[2q+1] bytes 1 and 3.
+    int best = 0;
+    if (live) {
+        const int64_t s0 = wc * 16;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+#pragma unroll
+            for (int hb = 0; hb < 2; hb++) {
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    const int byte = hb + 2 * half;                     // byte index inside the 32-bit word
+                    const int ev = (int)((e16[2 * q + hb] >> (16 * half)) & 0xFFFFu);
+                    const int es = 2 * byte + (q & 1) + 8 * (q >> 1);
+                    best = max(best, ev);
+                    if (ev) atomicAdd(reinterpret_cast<unsigned long long *>(ew) + s0 + es, (unsigned long long)ev);
+                    const int ms = (q == 0 ? 0 : q == 1 ? 2 : q == 2 ? 1 : 3) + 4 * byte;
+                    const int mv = (int)((m16[2 * q + hb] >> (16 * half)) & 0xFFFFu);
+                    const int hv = (int)((h16[2 * q + hb] >> (16 * half)) & 0xFFFFu);
+                    if (hv) atomicAdd(cnt + s0 + ms, hv);
+                    if (mv) atomicAdd(cnt + npad + s0 + ms, mv);
+                }
+            }
         }
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        s1[k] += (c1 >> (8 * k)) & 255;
-        s2[k] += (c2 >> (8 * k)) & 255;
-        s3[k] += (c3 >> (8 * k)) & 255;
-        int64_t i = b * 4 + k;
-        int sx = s1[k] + 2 * s2[k];
-        if (sx) atomicAdd(cnt + i, sx);
-        if (s3[k]) atomicAdd(cnt + npad + i, s3[k]);
+    for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < SS_THREADS / 32; k++) best = max(best, smax[k]);
+        if (best) atomicMax(chunk_ew + blockIdx.y, best);
     }
 }
 
 // ---- digit tables: tab[pass][snp] ------------------------------------------
-// pass order: U digits (nU), W digits (nW), D digits (nD), D2 digits (nD2)
-__global__ void tables_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int64_t cap, int est,
-                              int bayesian, int frac_bits, int frac_bits_w, int frac_bits_d, int nU, int nW, int nD, int nD2,
+// pass order: T digits (nU), R digits (nW), D digits (nD), D2 digits (nD2)
+__global__ void tables_kernel(const SnpStat *__restrict__ st, const int2 *__restrict__ coltab, int64_t n_snp, int64_t cap, int est,
+                              int bayesian, int frac_bits, int frac_bits_w, int frac_bits_d, int frac_bits_v, int nU, int nW, int nD, int nD2,
                               uint32_t *__restrict__ tab, double *__restrict__ scalars /*[gridDim.x][2] partials*/,
                               long long *__restrict__ iscalars, int *__restrict__ overflow, uint64_t dither) {
     int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double d = 0, d2 = 0;
-    long long poly = 0;
+    long long poly = 0, qb = 0;
     if (l < n_snp) {
         SnpTables t;
-        snp_tables(st[l], est, bayesian, frac_bits, frac_bits_w, frac_bits_d, t, (long long)l, dither);
+        snp_tables(st[l], est, bayesian, coltab[l], frac_bits, frac_bits_w, frac_bits_d, frac_bits_v, t, (long long)l, dither);
         d = t.d;
         d2 = t.d2;
+        qb = t.qb;
         poly = (est == SNPREL_GRM_GCTA || est == SNPREL_GRM_CORR) ? t.qD : 0;
         int pass = 0;
         long long q[4];
@@ -260,16 +395,20 @@ __global__ void tables_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int
     }
     // global scalars: deterministic per-block tree, then one atomic per block
     __shared__ double s0[256], s1[256];
-    __shared__ long long s2[256];
+    __shared__ long long s2[256], s3[256], s4[256];
     s0[threadIdx.x] = d;
     s1[threadIdx.x] = d2;
     s2[threadIdx.x] = poly;
+    s3[threadIdx.x] = qb & ((1ll << LIMB) - 1);     // the constant of the per-sample vector, in two limbs
+    s4[threadIdx.x] = qb >> LIMB;
     __syncthreads();
     for (int o = blockDim.x / 2; o; o >>= 1) {
         if (threadIdx.x < o) {
             s0[threadIdx.x] += s0[threadIdx.x + o];
             s1[threadIdx.x] += s1[threadIdx.x + o];
             s2[threadIdx.x] += s2[threadIdx.x + o];
+            s3[threadIdx.x] += s3[threadIdx.x + o];
+            s4[threadIdx.x] += s4[threadIdx.x + o];
         }
         __syncthreads();
     }
@@ -278,73 +417,116 @@ __global__ void tables_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int
         scalars[2 * blockIdx.x + 0] = s0[0];
         scalars[2 * blockIdx.x + 1] = s1[0];
         atomicAdd(reinterpret_cast<unsigned long long *>(iscalars), (unsigned long long)s2[0]);
+        atomicAdd(reinterpret_cast<unsigned long long *>(iscalars) + 2, (unsigned long long)s3[0]);
+        atomicAdd(reinterpret_cast<unsigned long long *>(iscalars) + 3, (unsigned long long)s4[0]);
     }
 }
 
-// ---- per-sample sums: vec[v][i] = sum_l T_v,l[g_il]  (exact int64) ---------
-constexpr int SS_SNPS = 512;   // SNPs per block
-__global__ void __launch_bounds__(128)
-sample_sum_kernel(const uint8_t *__restrict__ geno, const SnpStat *__restrict__ st, int64_t n_snp,
-                  int64_t row_bytes, int64_t npad, int est, int bayesian, int frac_bits, int frac_bits_w, int frac_bits_d,
-                  long long *__restrict__ vec) {
-    __shared__ long long tW[SS_SNPS][4];    // hi part of the extended-precision W (units 2^-frac_bits)
-    __shared__ int tWlo[SS_SNPS][4];        // lo part (W_EXTRA_BITS bits, non-negative)
-    __shared__ long long tD[SS_SNPS], tD2[SS_SNPS];
-    const int64_t l0 = (int64_t)blockIdx.y * SS_SNPS;
-    const int nl = (int)min((int64_t)SS_SNPS, n_snp - l0);
-    for (int s = threadIdx.x; s < nl; s += blockDim.x) {
-        SnpTables t;
-        snp_tables(st[l0 + s], est, bayesian, frac_bits, frac_bits_w, frac_bits_d, t);
-        for (int g = 0; g < 4; g++) {
-            tW[s][g] = t.qWx[g] >> W_EXTRA_BITS;
-            tWlo[s][g] = (int)(t.qWx[g] & ((1ll << W_EXTRA_BITS) - 1));
+// ---- per-sample vectors (exact int64) ----------------------------------------
+//   V_i = sum_l R_l[g_il] = sum_l (a_l x_il + b_l m_il) - sum_l b_l     (R_l[g] = a_l g - b_l for valid g)
+//   VEC_WLO[i] = low 20-bit limb sums (units 2^-fv), VEC_W[i] = upper limbs (units 2^-(fv-20));
+//   the constant sum_l b_l goes to iscalars[2..3] (tables_kernel);
+//   VEC_D[i] = sum_l qD_l m_il, VEC_D2[i] = sum_l qD2_l m_il  (missing-pair denominators).
+// A block owns 32 word columns (512 samples) and SV_ROWS SNP rows; its four warps take every fourth
+// row.  a_l x_il runs as one IMAD per 20-bit limb into int32 registers (512 rows x 2 x 2^20 < 2^31);
+// the sparse m terms take a divergent slow path with 64-bit shared-memory atomics.
+constexpr int SV_ROWS = 2048, SV_THREADS = 128;
+template <int NL>
+__global__ void __launch_bounds__(SV_THREADS)
+sample_vec_kernel(const uint32_t *__restrict__ geno, const SnpStat *__restrict__ st, const int2 *__restrict__ coltab,
+                  int64_t n_snp, int64_t n_samp, int64_t row_words, int64_t npad, int est, int bayesian, int frac_bits_d,
+                  int frac_bits_v, long long *__restrict__ vec) {
+    __shared__ int tA[GRAM_CHUNK][NL];
+    __shared__ long long tB[GRAM_CHUNK], tD[GRAM_CHUNK], tD2[GRAM_CHUNK];
+    __shared__ unsigned long long sv[4][512];      // VEC_W, VEC_WLO, VEC_D, VEC_D2 of the block's 512 samples
+    for (int k = threadIdx.x; k < 4 * 512; k += blockDim.x) (&sv[0][0])[k] = 0ull;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t wc = (int64_t)blockIdx.x * 32 + lane;
+    const bool live = wc < row_words;
+    // padding samples (code 3 in every row) would send their lanes down the slow path for every SNP
+    uint32_t real = 0;
+    for (int k = 0; k < 16; k++)
+        if (wc * 16 + k < n_samp) real |= 1u << (2 * k);
+    int acc[16][NL];
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+#pragma unroll
+        for (int j = 0; j < NL; j++) acc[k][j] = 0;
+    const int64_t lb = (int64_t)blockIdx.y * SV_ROWS;
+    for (int64_t l0 = lb; l0 < min(lb + (int64_t)SV_ROWS, n_snp); l0 += GRAM_CHUNK) {
+        const int nl = (int)min((int64_t)GRAM_CHUNK, n_snp - l0);
+        __syncthreads();
+        for (int s = threadIdx.x; s < nl; s += blockDim.x) {
+            SnpTables t;
+            snp_tables(st[l0 + s], est, bayesian, coltab[l0 + s], 0, 0, frac_bits_d, frac_bits_v, t);
+            long long qa = t.qa;
+#pragma unroll
+            for (int j = 0; j < NL; j++) {      // low limbs unsigned 20 bits, the top one signed
+                tA[s][j] = j + 1 < NL ? (int)(qa & ((1ll << LIMB) - 1)) : (int)qa;
+                qa >>= LIMB;
+            }
+            tB[s] = t.qb;
+            tD[s] = t.qD;
+            tD2[s] = t.qD2;
         }
-        tD[s] = t.qD;
-        tD2[s] = t.qD2;
-    }
-    __syncthreads();
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // byte column (4 samples)
-    if (b >= row_bytes) return;
-    long long aw[4] = {0, 0, 0, 0}, awl[4] = {0, 0, 0, 0}, ad[4] = {0, 0, 0, 0}, ad2[4] = {0, 0, 0, 0};
-    int ah[4] = {0, 0, 0, 0};
-    const uint8_t *p = geno + l0 * row_bytes + b;
-    // eight independent byte loads in flight per thread: the serial load -> table lookup -> add
-    // chain was latency bound (12.6 ms for 2.5 GB in profiles/r01_launches_pca.csv)
-    constexpr int UNR = 8;
-    for (int s0 = 0; s0 < nl; s0 += UNR) {
-        uint32_t vv[UNR];
+        __syncthreads();
+        const uint32_t *p = geno + l0 * row_words + (live ? wc : 0);
+        for (int r = warp; r < nl; r += 4 * 4) {
+            uint32_t wv[4];
 #pragma unroll
-        for (int u = 0; u < UNR; u++) vv[u] = (s0 + u < nl) ? p[(int64_t)(s0 + u) * row_bytes] : 0xFFu;
+            for (int u = 0; u < 4; u++) wv[u] = (live && r + 4 * u < nl) ? __ldg(p + (int64_t)(r + 4 * u) * row_words) : 0u;
 #pragma unroll
-        for (int u = 0; u < UNR; u++) {
-            const int s = min(s0 + u, nl - 1);
-            const bool live = s0 + u < nl;
-            const uint32_t v = vv[u];
-            long long dd = live ? tD[s] : 0, dd2 = live ? tD2[s] : 0;
+            for (int u = 0; u < 4; u++) {
+                const int row = r + 4 * u;
+                if (row >= nl) break;
+                const uint32_t x = wv[u];
+                const uint32_t m3 = x & (x >> 1) & 0x55555555u;
+                const uint32_t xv = x & ~(m3 * 3u);            // missing -> 0
+                int a[NL];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                uint32_t code = (v >> (2 * k)) & 3;   // a dead slot reads as missing: table entry 3 is 0
-                aw[k] += tW[s][code];
-                awl[k] += tWlo[s][code];
-                if (code == 3) {
-                    ad[k] += dd;
-                    ad2[k] += dd2;
+                for (int j = 0; j < NL; j++) a[j] = tA[row][j];
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const int g = (int)((xv >> (2 * k)) & 3u);
+#pragma unroll
+                    for (int j = 0; j < NL; j++) acc[k][j] += g * a[j];
                 }
-                ah[k] += (code == 1);
+                uint32_t mm = live ? (m3 & real) : 0u;
+                while (mm) {                                    // sparse: b_l, d_l, d2_l of the missing genotypes
+                    const int k = (__ffs(mm) - 1) >> 1;
+                    mm &= mm - 1;
+                    const int sidx = lane * 16 + k;
+                    const long long qb = tB[row];
+                    atomicAdd(&sv[1][sidx], (unsigned long long)(qb & ((1ll << LIMB) - 1)));
+                    atomicAdd(&sv[0][sidx], (unsigned long long)(qb >> LIMB));
+                    if (tD[row]) atomicAdd(&sv[2][sidx], (unsigned long long)tD[row]);
+                    if (tD2[row]) atomicAdd(&sv[3][sidx], (unsigned long long)tD2[row]);
+                }
             }
         }
     }
+    // limb sums of this warp -> the block's per-sample sums
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int64_t i = b * 4 + k;
-        unsigned long long *o = reinterpret_cast<unsigned long long *>(vec);
-        // W vector: hi part in units of 2^-frac_bits, lo part carries W_EXTRA_BITS more bits
-        if (aw[k]) atomicAdd(o + VEC_W * npad + i, (unsigned long long)aw[k]);
-        if (awl[k]) atomicAdd(o + VEC_WLO * npad + i, (unsigned long long)awl[k]);
-        if (ad[k]) atomicAdd(o + VEC_D * npad + i, (unsigned long long)ad[k]);
-        if (ah[k]) atomicAdd(o + VEC_HET * npad + i, (unsigned long long)(long long)ah[k]);
-        if (ad2[k]) atomicAdd(o + VEC_D2 * npad + i, (unsigned long long)ad2[k]);
+    for (int k = 0; k < 16; k++) {
+        long long hi = 0;
+#pragma unroll
+        for (int j = NL - 1; j >= 1; j--) hi = (hi << LIMB) + (long long)acc[k][j];
+        if (acc[k][0]) atomicAdd(&sv[1][lane * 16 + k], (unsigned long long)(long long)acc[k][0]);
+        if (hi) atomicAdd(&sv[0][lane * 16 + k], (unsigned long long)hi);
     }
+    __syncthreads();
+    const int vmap[4] = {VEC_W, VEC_WLO, VEC_D, VEC_D2};
+    for (int k = threadIdx.x; k < 4 * 512; k += blockDim.x) {
+        const int v = k >> 9, sidx = k & 511;
+        const int64_t i = (int64_t)blockIdx.x * 512 + sidx;
+        const unsigned long long val = sv[v][sidx];
+        if (val && i < npad) atomicAdd(reinterpret_cast<unsigned long long *>(vec) + (int64_t)vmap[v] * npad + i, val);
+    }
+}
+
+__global__ void het_to_vec_kernel(const int *__restrict__ cnt, long long *__restrict__ vec, int64_t npad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npad) vec[VEC_HET * npad + i] = cnt[i];
 }
 
 // ---- helpers ---------------------------------------------------------------
@@ -362,14 +544,40 @@ static int digits_for(double max_abs, int frac_bits) {
          max_abs, frac_bits);
 }
 
-// scr_cnt[2][npad]: this rank's per-sample genotype sums and missing counts
-static void sample_counts(snprel_ctx *c) {
+// per-SNP column tables of the current genotypes / estimator
+static void ensure_coltab(snprel_ctx *c, int est, int bayesian) {
+    ensure_stats(c);
+    if (c->coltab_version == c->geno_version && c->coltab_est == est && c->coltab_bayesian == bayesian) return;
+    c->scr_coltab.alloc((size_t)c->snp_cap);
+    c->scr_tabb.alloc((size_t)2 * c->snp_cap);
+    c->scr_tabb.zero(c->stream);               // padding rows: all-zero tables
+    if (c->n_snp > 0) {
+        coltab_kernel<<<(unsigned)((c->n_snp + 255) / 256), 256, 0, c->stream>>>(
+            c->stat.p, c->n_snp, est, bayesian, c->scr_coltab.p, c->scr_tabb.p, c->scr_tabb.p + c->snp_cap);
+        KERNEL_CHECK(c);
+    }
+    c->coltab_version = c->geno_version;
+    c->coltab_est = est;
+    c->coltab_bayesian = bayesian;
+}
+
+// scr_ew[npad], scr_cnt[2][npad], scr_chunk[nchunk]: this rank's per-sample error weights, het / missing
+// counts and the per-chunk maxima of the error weight
+static void sample_stats(snprel_ctx *c) {
     const int64_t npad = c->n_samp_pad;
+    const int64_t nchunk = (c->snp_cap + GRAM_CHUNK - 1) / GRAM_CHUNK;
     c->scr_cnt.alloc((size_t)2 * npad);
     c->scr_cnt.zero(c->stream);
+    c->scr_ew.alloc((size_t)npad);
+    c->scr_ew.zero(c->stream);
+    c->scr_chunk.alloc((size_t)nchunk);
+    c->scr_chunk.zero(c->stream);
     if (c->n_snp > 0) {
-        dim3 grid((unsigned)((c->row_bytes + 127) / 128), (unsigned)((c->n_snp + SC_SNPS - 1) / SC_SNPS));
-        sample_count_kernel<<<grid, 128, 0, c->stream>>>(c->geno2b.p, c->n_snp, c->row_bytes, npad, c->scr_cnt.p);
+        const int64_t row_words = c->row_bytes / 4;
+        dim3 grid((unsigned)((row_words + SS_THREADS - 1) / SS_THREADS), (unsigned)((c->n_snp + GRAM_CHUNK - 1) / GRAM_CHUNK));
+        sample_stats_kernel<<<grid, SS_THREADS, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(c->geno2b.p),
+                                                               c->scr_tabb.p + c->snp_cap, c->n_snp, row_words, npad,
+                                                               c->scr_ew.p, c->scr_cnt.p, c->scr_chunk.p);
         KERNEL_CHECK(c);
     }
 }
@@ -391,30 +599,37 @@ void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
             return;
         }
     }
-    ensure_stats(c);
+    ensure_coltab(c, est, plan->bayesian);
     const int64_t npad = c->n_samp_pad;
     DevBuf<double> &out = c->scr_plan;
     out.alloc(5);
     out.zero(c->stream);
     if (c->n_snp > 0) {
         int blocks = (int)std::min<int64_t>((c->n_snp + 255) / 256, 1024);
-        plan_kernel<<<blocks, 256, 0, c->stream>>>(c->stat.p, c->n_snp, c->n_samp, est,
+        plan_kernel<<<blocks, 256, 0, c->stream>>>(c->stat.p, c->scr_coltab.p, c->n_snp, c->n_samp, est,
                                                    plan->bayesian, out.p);
         KERNEL_CHECK(c);
     }
-    sample_counts(c);
+    sample_stats(c);
     double h[5];
-    c->host_cnt.resize((size_t)2 * npad);
+    c->host_cnt.resize((size_t)npad);
+    c->host_ew.resize((size_t)npad);
+    const size_t nchunk = (size_t)((c->n_snp + GRAM_CHUNK - 1) / GRAM_CHUNK);
+    std::vector<int> hchunk(nchunk);
     CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaMemcpyAsync(c->host_cnt.data(), c->scr_cnt.p, (size_t)2 * npad * sizeof(int),
+    CUDA_CHECK(cudaMemcpyAsync(c->host_cnt.data(), c->scr_cnt.p + npad, (size_t)npad * sizeof(int),
                                cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->host_ew.data(), c->scr_ew.p, (size_t)npad * sizeof(long long),
+                               cudaMemcpyDeviceToHost, c->stream));
+    if (nchunk)
+        CUDA_CHECK(cudaMemcpyAsync(hchunk.data(), c->scr_chunk.p, nchunk * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     long long ew = 0, mm = 0;
     for (int64_t i = 0; i < c->n_samp; i++) {
-        long long sx = c->host_cnt[i], ms = c->host_cnt[npad + i];
-        ew = std::max(ew, sx);
-        mm = std::max(mm, ms);
+        ew = std::max(ew, c->host_ew[i]);
+        mm = std::max<long long>(mm, c->host_cnt[i]);
     }
+    c->chunk_bound.assign(hchunk.begin(), hchunk.end());
     plan->max_abs = h[0];
     plan->max_abs_w = h[4];
     plan->sum_bound = h[1];
@@ -433,28 +648,26 @@ void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
 
 // Choose the fixed-point formats from the (global) plan statistics.
 //   numerator plane: quantisation error of an entry
-//        <= 2^-(f+1) * err_weight  (U table against the x channel)
-//         + 2^-(fw+1) * max_missing (W table against the m channel),   wanted <= tol * scale
+//        <= 2^-(f+1) * err_weight  (T table against the integer column table B)
+//         + 2^-(fw+1) * max_missing (R table against the m channel),   wanted <= tol * scale
 //   denominator plane (EIGMIX / KING-homo): error <= 2^-(fd+1) * 2 max_missing, wanted <= tol * scale
-// Tensor passes run two at a time, so a table with n digits costs n/2 double launches plus
-// (n odd) one single launch that runs at ~0.8 of a double.
-static double launch_cost(int n) { return (n / 2) + (n % 2) * 0.8; }
+// Items run two passes at a time; a table with an odd digit count sends its last digit through
+// 256 x 512 items (one pass, two column tiles) at the same cost per pass.
+static double launch_cost(int n) { return (double)n; }
 
-// round_mode 1 (snprel_set_rounding): the U table is rounded at random, so for a fixed pair (i, j)
-// the error sum_l e_l[g_il] x_jl is a sum of independent zero-mean terms of width x_jl 2^-f, and by
-// Hoeffding it exceeds 2^-f sqrt(1/2 sum_l x_jl^2 ln(2/delta)) with probability < delta; delta is
-// 1e-12 divided by the number of pairs (union bound) and sum x^2 <= 2 sum x = 2 err_weight.  This
-// replaces the worst-case 2^-(f+1) err_weight and saves one tensor pass per table at C2
-// (tools/fixed_point_model.py: actual error 1.8e-11, bound 6.5e-11 with U in 4 digits).
+// round_mode 1 (snprel_set_rounding): the T table is rounded at random, so for a fixed pair (i, j)
+// the error sum_l e_l[g_il] B_l[g_jl] is a sum of independent zero-mean terms of width |B| 2^-f, and by
+// Hoeffding it exceeds 2^-f sqrt(1/2 sum_l B^2 ln(2/delta)) with probability < delta; delta is
+// 1e-12 divided by the number of pairs (union bound) and sum B^2 <= 127 sum |B| = 127 err_weight.
 static double u_table_error(const snprel_plan &plan, int fa, int round_mode, double n_samp) {
     if (round_mode != 1) return std::ldexp(plan.err_weight, -(fa + 1));
     const double pairs = std::max(1.0, 0.5 * n_samp * (n_samp + 1.0));
-    return std::ldexp(std::sqrt(0.5 * 2.0 * plan.err_weight * std::log(2.0 * pairs / 1e-12)), -fa);
+    return std::ldexp(std::sqrt(0.5 * 127.0 * plan.err_weight * std::log(2.0 * pairs / 1e-12)), -fa);
 }
 
 static void choose_format(int est, snprel_plan &plan, int &nU, int &nW, int &nD, int round_mode = 0,
                           double n_samp = 0) {
-    const double tol = (plan.tol > 0 ? plan.tol : 1e-10) * 0.9;   // 10 % left for float64 rounding in the epilogue
+    const double tol = (plan.tol > 0 ? plan.tol : 1e-10) * 0.9;   // 10 % left for the per-sample vector and float64 rounding in the epilogue
     const bool homo = est == SNPREL_EST_KING_HOMO;
     const bool any_missing = plan.total_missing > 0;
     const int head = 61 - (int)std::ceil(std::log2(std::max(plan.sum_bound, 1.0)));   // int64 plane headroom
@@ -466,9 +679,7 @@ static void choose_format(int est, snprel_plan &plan, int &nU, int &nW, int &nD,
     // never let it shrink the normaliser below 5 % of its complete-data value
     scale = std::max(scale, 0.05 * plan.scale);
     const double budget = tol * std::max(scale, 1e-300);
-    // the extended-precision W vector needs max|W| * 2^(f + W_EXTRA_BITS) inside int64
-    const int wcap = 61 - W_EXTRA_BITS - (int)std::ceil(std::log2(std::max(std::max(plan.max_abs, plan.max_abs_w), 1.0)));
-    const int fmax = std::min(head, wcap);
+    const int fmax = head;
     nU = nW = 0;
     if (!homo) {
         if (plan.frac_bits >= 0) {           // caller-fixed format
@@ -512,6 +723,13 @@ static void choose_format(int est, snprel_plan &plan, int &nU, int &nW, int &nD,
     }
     plan.digits = nU;
     plan.digits_w = nW;
+    // the per-sample vector: 1.5 n_snp 2^-fv (rounding of a_l x and b_l, x <= 2) <= 5 % of the budget
+    {
+        const double need = 1.5 * (double)std::max<int64_t>(plan.n_snp, 1) / (0.05 * budget / 0.9);
+        int fv = (int)std::ceil(std::log2(std::max(need, 2.0)));
+        const int lim = 57 - (int)std::ceil(std::log2(std::max(2.0 * plan.max_abs_w, 1e-300)));   // |qa|, |qb| < 2^58: three limbs
+        plan.frac_bits_v = std::max(8, std::min(std::min(fv, lim), 60));
+    }
     nD = 0;
     plan.frac_bits_d = std::max(plan.frac_bits_d, 0);
     if (any_missing) {
@@ -533,12 +751,12 @@ static void choose_format(int est, snprel_plan &plan, int &nU, int &nW, int &nD,
 
 void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     if (est == SNPREL_GRM_CORR) est = SNPREL_GRM_GCTA;
-    ensure_stats(c);
     snprel_plan plan = *plan_in;
+    ensure_coltab(c, est, plan.bayesian);
     const bool homo = est == SNPREL_EST_KING_HOMO;
     int nU = 0, nW = 0, nD = 0;
     choose_format(est, plan, nU, nW, nD, c->round_mode, (double)c->n_samp);
-    const int f = plan.frac_bits, fw = plan.frac_bits_w, fd = plan.frac_bits_d;
+    const int f = plan.frac_bits, fw = plan.frac_bits_w, fd = plan.frac_bits_d, fv = plan.frac_bits_v;
     int nD2 = homo ? nD : 0;
     const int npass = nU + nW + nD + nD2;
     const int64_t cap = c->snp_cap, npad = c->n_samp_pad;
@@ -547,14 +765,15 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     // fixed-point format only, not on the row window: a tiled N x N run builds them once.
     snprel_ctx::PrepCache &pc = c->prep_cache;
     const bool prep_hit = pc.version == c->geno_version && pc.est == est && pc.bayesian == plan.bayesian &&
-                          pc.round_mode == c->round_mode &&
+                          pc.round_mode == c->round_mode && pc.fv == fv &&
                           pc.f == f && pc.fw == fw && pc.fd == fd && pc.nU == nU && pc.nW == nW && pc.nD == nD &&
                           pc.nD2 == nD2 && c->scr_tab.p && c->samp_sum.p && c->scr_cnt.p;
     DevBuf<uint32_t> &tab = c->scr_tab;
     if (!prep_hit) {
         // scr_cnt was summed over the ranks together with an earlier format's vectors while the
         // cached plan statistics kept it from being rebuilt: restore this rank's own counts
-        if (pc.reduced && pc.version == c->geno_version) sample_counts(c);
+        if ((pc.reduced && pc.version == c->geno_version) || !c->scr_cnt.p || c->plan_cache.version != c->geno_version)
+            sample_stats(c);
         pc.version = 0;
         tab.alloc((size_t)std::max(npass, 1) * cap);
         tab.zero(c->stream);
@@ -571,7 +790,7 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
             // (the draw is keyed by the LOCAL SNP index: shards of a multi-GPU run use different SNPs, so
             //  different local indices on different ranks still give independent draws per SNP)
             const uint64_t dither = (c->round_mode == 1 && !homo) ? (0xD17E5ull + (uint64_t)c->device * 0x9E3779B97F4A7C15ull) | 1ull : 0ull;
-            tables_kernel<<<tblocks, 256, 0, c->stream>>>(c->stat.p, c->n_snp, cap, est, plan.bayesian, f, fw, fd, nU,
+            tables_kernel<<<tblocks, 256, 0, c->stream>>>(c->stat.p, c->scr_coltab.p, c->n_snp, cap, est, plan.bayesian, f, fw, fd, fv, nU,
                                                           nW, nD, nD2, tab.p, c->scr_part.p, c->iscalars.p, ovf.p, dither);
             KERNEL_CHECK(c);
         }
@@ -596,9 +815,19 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
         c->samp_sum.zero(c->stream);
         c->samp_vecs = NVEC;
         if (c->n_snp > 0) {
-            dim3 grid((unsigned)((c->row_bytes + 127) / 128), (unsigned)((c->n_snp + SS_SNPS - 1) / SS_SNPS));
-            sample_sum_kernel<<<grid, 128, 0, c->stream>>>(c->geno2b.p, c->stat.p, c->n_snp, c->row_bytes, npad, est,
-                                                           plan.bayesian, f, fw, fd, c->samp_sum.p);
+            const int64_t row_words = c->row_bytes / 4;
+            dim3 grid((unsigned)((row_words + 31) / 32), (unsigned)((c->n_snp + SV_ROWS - 1) / SV_ROWS));
+            // |qa| < 2^(fv + 1) max|R|: two 20-bit limbs up to 2^39, three up to 2^59
+            const double qbits = (double)fv + 1.0 + std::log2(std::max(plan.max_abs_w, 1e-300));
+            const uint32_t *g32 = reinterpret_cast<const uint32_t *>(c->geno2b.p);
+            if (qbits < 38.0)
+                sample_vec_kernel<2><<<grid, SV_THREADS, 0, c->stream>>>(g32, c->stat.p, c->scr_coltab.p, c->n_snp, c->n_samp, row_words,
+                                                                        npad, est, plan.bayesian, fd, fv, c->samp_sum.p);
+            else
+                sample_vec_kernel<3><<<grid, SV_THREADS, 0, c->stream>>>(g32, c->stat.p, c->scr_coltab.p, c->n_snp, c->n_samp, row_words,
+                                                                        npad, est, plan.bayesian, fd, fv, c->samp_sum.p);
+            KERNEL_CHECK(c);
+            het_to_vec_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, c->stream>>>(c->scr_cnt.p, c->samp_sum.p, npad);
             KERNEL_CHECK(c);
         }
         pc.version = c->geno_version;
@@ -607,6 +836,7 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
         pc.f = f;
         pc.fw = fw;
         pc.fd = fd;
+        pc.fv = fv;
         pc.nU = nU;
         pc.nW = nW;
         pc.nD = nD;
@@ -621,13 +851,18 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     c->acc.zero(c->stream);
     c->acc_planes = nplanes;
 
+    // int32 headroom of the main passes: |digit| <= 128 against the measured per-chunk column weights
+    const uint32_t *tabB = c->scr_tabb.p;
+    const uint32_t *tabM = gram_const_table(c, TABB_M);
+    const std::vector<int64_t> *cb = c->chunk_bound.size() == (size_t)((c->n_snp + GRAM_CHUNK - 1) / GRAM_CHUNK)
+                                         ? &c->chunk_bound : nullptr;
     std::vector<GramPass> passes;
     int pass = 0;
-    for (int k = 0; k < nU; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, TABB_X, 0, 8 * k});
-    for (int k = 0; k < nW; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, TABB_M, 0, 8 * k + (f - fw)});
+    for (int k = 0; k < nU; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, tabB, 0, 8 * k, 127, cb});
+    for (int k = 0; k < nW; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, tabM, 0, 8 * k + (f - fw), 1, nullptr});
     for (int k = 0; k < nD; k++, pass++)
-        passes.push_back({tab.p + (int64_t)pass * cap, TABB_M, homo ? 0 : 1, 8 * k});
-    for (int k = 0; k < nD2; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, TABB_M, 1, 8 * k});
+        passes.push_back({tab.p + (int64_t)pass * cap, tabM, homo ? 0 : 1, 8 * k, 1, nullptr});
+    for (int k = 0; k < nD2; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, tabM, 1, 8 * k, 1, nullptr});
 
     c->hot_launches = 0;
     CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
@@ -651,7 +886,7 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
         c->reduce_list.push_back({c->samp_sum.p, (int64_t)c->samp_sum.n, 0});
         c->reduce_list.push_back({c->scalars.p, (int64_t)c->scalars.n, 2});
         c->reduce_list.push_back({c->iscalars.p, (int64_t)c->iscalars.n, 0});
-        c->reduce_list.push_back({c->scr_cnt.p, (int64_t)c->scr_cnt.n, 1});   // per-sample genotype sums / missing counts
+        c->reduce_list.push_back({c->scr_cnt.p, (int64_t)c->scr_cnt.n, 1});   // per-sample het / missing counts
     }
 }
 
@@ -669,14 +904,16 @@ __device__ __forceinline__ void store_sym2(double *out, int packed, int64_t n, i
 }
 
 // ---- fused epilogue: int64 planes -> float64 result in its final layout, one pass -------------
-// numerator C_ij = (acc0[i][j] - vecW_hi[i]) * 2^-f - vecW_lo[i] * 2^-(f+20), then the estimator's
-// normalisation.  mode 0: Eigenstrat (scale = (n-1)/trace); 1: GCTA; 3: EIGMIX (mul = 1 ibd / 2 GRM)
+// numerator C_ij = acc0[i][j] 2^-f - V_i (the per-sample vector in its own fixed point), then the
+// estimator's normalisation.  mode 0: Eigenstrat (scale = (n-1)/trace); 1: GCTA; 3: EIGMIX (mul = 1 ibd / 2 GRM)
 struct FinalArgs {
     const long long *acc;     // [planes][win.rows][npad]
     const long long *vec;     // [NVEC][npad]
     const int *nmiss;         // [npad] missing genotypes per sample
     long long n_snp_total;
-    double inv_scale, inv_scale_lo;   // 2^-f, 2^-(f + W_EXTRA_BITS)
+    double inv_scale;                 // 2^-f
+    double inv_v_hi, inv_v_lo;        // per-sample vector: 2^-(fv - 20) for VEC_W, 2^-fv for VEC_WLO
+    long long sb_hi, sb_lo;           // its constant sum_l b_l in the same two units
     int mode, has_den, diagadj;
     double scale, sum_den, inv_fix, mul;
     long long nlocus;
@@ -688,8 +925,9 @@ __device__ __forceinline__ double grm_numerator(const FinalArgs &a, int64_t i, i
     // a sample without a single valid genotype contributes exactly 0, as in the reference
     // (its centred genotypes are all 0, src/genPCA.h:103)
     if (a.nmiss[i] == a.n_snp_total || a.nmiss[j] == a.n_snp_total) return 0.0;
-    const long long q = a.acc[(i - a.win.r0) * a.npad + j] - a.vec[VEC_W * a.npad + i];
-    return (double)q * a.inv_scale - (double)a.vec[VEC_WLO * a.npad + i] * a.inv_scale_lo;
+    // C_ij = sum T B + sum R m  -  V_i,   V_i = (VEC_W - sb_hi) 2^-(fv-20) + (VEC_WLO - sb_lo) 2^-fv
+    const long long hi = a.vec[VEC_W * a.npad + i] - a.sb_hi, lo = a.vec[VEC_WLO * a.npad + i] - a.sb_lo;
+    return (double)a.acc[(i - a.win.r0) * a.npad + j] * a.inv_scale - ((double)hi * a.inv_v_hi + (double)lo * a.inv_v_lo);
 }
 
 __device__ __forceinline__ double grm_entry(const FinalArgs &a, int64_t i, int64_t j) {   // i <= j
@@ -798,14 +1036,14 @@ static void need_grm_accum(snprel_ctx *c, int est, int bayesian) {
 
 struct Globals {
     double sum_den, sum_den2;
-    long long nlocus;
+    long long nlocus, sb_lo, sb_hi;
 };
 static Globals read_globals(snprel_ctx *c) {
     double hs[4];
     long long hi[4];
     d2h(c, hs, c->scalars.p, 4);
     d2h(c, hi, c->iscalars.p, 4);
-    return Globals{hs[0], hs[1], hi[0]};
+    return Globals{hs[0], hs[1], hi[0], hi[2], hi[3]};
 }
 
 static dim3 win_grid(snprel_ctx *c) {
@@ -847,8 +1085,12 @@ static void grm_device(snprel_ctx *c, int method, int packed, int diagadj, doubl
     a.vec = c->samp_sum.p;
     a.nmiss = c->scr_cnt.p + c->n_samp_pad;
     a.n_snp_total = (long long)c->plan.n_snp;
+    const Globals g = read_globals(c);
     a.inv_scale = std::ldexp(1.0, -c->plan.frac_bits);
-    a.inv_scale_lo = std::ldexp(1.0, -(c->plan.frac_bits + W_EXTRA_BITS));
+    a.inv_v_hi = std::ldexp(1.0, -(c->plan.frac_bits_v - LIMB));
+    a.inv_v_lo = std::ldexp(1.0, -c->plan.frac_bits_v);
+    a.sb_hi = g.sb_hi;
+    a.sb_lo = g.sb_lo;
     a.has_den = c->acc_planes > 1;
     a.diagadj = diagadj;
     a.mul = mul;
@@ -872,11 +1114,9 @@ static void grm_device(snprel_ctx *c, int method, int packed, int diagadj, doubl
         a.mode = 0;
         a.scale = (double)(n - 1) / tr;
     } else if (method == SNPREL_GRM_GCTA || method == SNPREL_GRM_CORR) {
-        Globals g = read_globals(c);
         a.mode = 1;
         a.nlocus = g.nlocus;
     } else {
-        Globals g = read_globals(c);
         a.mode = 3;
         a.sum_den = g.sum_den;
         a.inv_fix = std::ldexp(1.0, -c->plan.frac_bits_d);
@@ -1027,7 +1267,9 @@ void table_gram_debug(snprel_ctx *c, const int8_t *tabA, const int8_t *tabB, int
     DevBuf<long long> acc;
     acc.alloc((size_t)npad * npad);
     acc.zero(c->stream);
-    GramPass p{tab.p, tb, 0, 0};
+    int bmax = 0;
+    for (int g = 0; g < 4; g++) bmax = std::max(bmax, std::abs((int)tabB[g]));
+    GramPass p{tab.p, gram_const_table(c, tb), 0, 0, std::max(bmax, 1), nullptr};
     c->hot_launches = 0;
     gram_tc_run(c, &p, 1, acc.p, false);
     CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)n * 8, acc.p, (size_t)npad * 8, (size_t)n * 8, (size_t)n,

@@ -2,8 +2,8 @@
 evaluate format changes before touching the kernel.  Two schemes on the bench generator
 (MAF ~ U(0.05, 0.5), 0.5 % missing), Eigenstrat weights:
 
-  A (shipped)  C = sum U[g_i] x_j - sum W[g_i] + sum W[g_i] m_j,            U 5 digits, W 4 digits
-  B (proposed) C = sum T[g_i] B_l[g_j] - sum D[g_i] + sum D[g_i] m_j        T 5 digits, D 3 digits
+  A (round 1)  C = sum U[g_i] x_j - sum W[g_i] + sum W[g_i] m_j,            U 5 digits, W 4 digits
+  B (shipped since round 2) C = sum T[g_i] B_l[g_j] - sum D[g_i] + sum D[g_i] m_j        T 5 digits, D 3 digits
                with per-SNP integer column tables B_l[g] = s_l g - t_l (|B| <= 127, 0 for missing),
                T = U / s_l, D = (mu_l - t_l / s_l) U: the centring of the column sample moves into
                the main passes and the missing-data pass only carries the rational-approximation
@@ -105,12 +105,13 @@ t0 = time.time()
 W3 = mu[:, None] * U
 ewA = float(np.max(x.sum(axis=0)))
 maxmiss = float(np.max(mis.sum(axis=0)))
-run("A (shipped) ", U, 33, 5, x, W3, 28, 4, ewA, maxmiss)
+run("A (round 1) ", U, 33, 5, x, W3, 28, 4, ewA, maxmiss)
 
 # scheme B: per-SNP (s, t): equalise |T| = |U| / s and pick the s in a window that best approximates mu by t / s
 umax = np.max(np.abs(U), axis=1)
 s_hi = np.minimum(np.floor(127.0 / np.maximum(2.0 - mu, 1e-9)), 127.0)     # 2 s - t <= 127 with t ~ s mu
-s_tgt = np.minimum(s_hi, np.maximum(8.0, 127.0 * umax / umax.max()))
+UREF = 40.0          # shipped rule (grm.cu:coltab_kernel): |U| at MAF 0.05, a constant, so that every rank of a sharded run picks the same table
+s_tgt = np.minimum(s_hi, np.maximum(24.0, 127.0 * umax / UREF))
 best_s = np.zeros(m)
 best_t = np.zeros(m)
 best_e = np.full(m, np.inf)
@@ -131,7 +132,7 @@ fT = int(np.floor(np.log2((127 * (256.0 ** 5 - 1) / 255 - 1) / np.max(np.abs(T3)
 fD = int(np.floor(np.log2((127 * (256.0 ** 3 - 1) / 255 - 1) / np.max(np.abs(D3)))))
 print(f"   scheme B tables: s in [{s.min():.0f}, {s.max():.0f}], max|T| {np.max(np.abs(T3)):.3f}, max|D| {np.max(np.abs(D3)):.2e}, "
       f"err weight {ewB:.3g} (A: {ewA:.3g}), max missing {maxmiss:.0f}")
-run("B (proposed)", T3, fT, 5, Bv, D3, fD, 3, ewB, maxmiss)
+run("B (shipped) ", T3, fT, 5, Bv, D3, fD, 3, ewB, maxmiss)
 fU4 = int(np.floor(np.log2((127 * (256.0 ** 4 - 1) / 255 - 1) / np.max(np.abs(U)))))
 fT4 = int(np.floor(np.log2((127 * (256.0 ** 4 - 1) / 255 - 1) / np.max(np.abs(T3)))))
 print("   randomised rounding of the main table (probabilistic bound, failure probability 1e-12):")
