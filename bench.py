@@ -157,6 +157,70 @@ def workload_config(gpus):
             "l2": "inputs (2.56 GB of 2-bit genotypes per GPU) are larger than the 126 MB L2"}
 
 
+
+# ---- optional legs (never change the headline): BASELINE.json's other configs under the driver's clock ----
+X_N, X_M = 16384, 262144          # pair-counter legs at --gpus 1 (< 2 s each)
+PAIR_ALU_OPS = {"ibs": 7.27, "king": 10.83, "beta": 8.19}      # ALU-pipe ops per 32-SNP word pair (profiles/r01_pair_count_sass_mix.md)
+PAIR_POPC = {"ibs": 2.0, "king": 3.33, "beta": 2.0}
+
+
+def measured_peaks_r02():
+    p = os.path.join(ROOT, "profiles", "peaks_r02.json")
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
+def pair_counter_legs(local, clocks_mhz):
+    """snpgdsIBS / KING-robust / IndivBeta counters on X_N x X_M synthetic genotypes, packed-bit kernels
+    (default engine) and the tensor engine, each checked bit for bit against the oracle at scattered samples."""
+    import numpy as np
+    import snprelate_b200 as S
+    from snprelate_b200._lib import EST_IBS, EST_KING_ROBUST, EST_BETA
+    from oracle import snprel_oracle as O          # checker only
+    pk = measured_peaks_r02()
+    out = {"n_samp": X_N, "n_snp": X_M, "miss_rate": MISS,
+           "note": "device time of planes + pair kernel from resident 2-bit genotypes (snprel_time_accumulate); "
+                   "alu_frac = ALU-pipe instructions issued / measured LOP3 issue peak (profiles/peaks_r02.json) at the max clock"}
+    idx = O.scattered_samples(X_N, 24, seed=7)
+    sub = O.synth_geno(0, X_M, seed=SEED + 1, miss_rate=MISS, samples=idx)
+    refs = {"ibs": O.ibs_counts(sub), "king": O.king_robust_counts(sub), "beta": O.beta_counts(sub)}
+    ix = np.ix_(idx, idx)
+    with S.Context(local) as c:
+        c.geno_begin(X_N, X_M)
+        c.geno_synth(X_M, seed=SEED + 1, miss_rate=MISS)
+        for name, est in (("ibs", EST_IBS), ("king", EST_KING_ROBUST), ("beta", EST_BETA)):
+            leg = {}
+            for engine in ("bits", "tensor"):
+                c.set_count_engine(engine)
+                ms = min(c.time_accumulate(est, 1) for _ in range(2))
+                hot, nl, units = c.last_hot_kernel()
+                if name == "ibs":
+                    got = np.stack([a[ix] for a in c.ibs_num()])
+                elif name == "king":
+                    got = c.king_robust_counts()[:, idx][:, :, idx]
+                else:
+                    got = c.indiv_beta_counts()[:, idx][:, :, idx]
+                iu = np.triu_indices(len(idx))
+                exact = bool(np.array_equal(got[(slice(None),) + iu], np.asarray(refs[name])[(slice(None),) + iu]))
+                rec = {"ms": ms, "kernel_ms": hot, "pair_snps_per_s": units / (ms * 1e-3), "bit_exact_vs_oracle": exact,
+                       "checked_pairs": int(len(iu[0]))}
+                if engine == "bits":
+                    # algorithmic HBM bytes: 2-bit genotypes in, bit planes out and in again, counters out
+                    planes = {"ibs": 3, "king": 5, "beta": 2}[name]
+                    alg = 3 * X_N * X_M / 4 + planes * 4 * X_N * (X_N + 1) / 2
+                    rec["algorithmic_hbm_gbs"] = alg / (ms * 1e-3) / 1e9
+                    wp_per_s = units / 32.0 / (hot * 1e-3)
+                    rec["alu_ops_per_word_pair"] = PAIR_ALU_OPS[name]
+                    if pk and "alu_lop3" in pk:
+                        rec["alu_frac_of_measured_lop3_peak"] = wp_per_s * PAIR_ALU_OPS[name] / pk["alu_lop3"]["thread_inst_per_s"]
+                        rec["popc_frac_of_measured_popc_peak"] = wp_per_s * PAIR_POPC[name] / pk["alu_popc"]["thread_inst_per_s"]
+                leg[engine] = rec
+                if not exact:
+                    raise SystemExit(f"extra leg {name}/{engine}: counters differ from the oracle")
+            out[name] = leg
+        c.set_count_engine("bits")
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -293,6 +357,24 @@ def run_ours(args):
               "what": "genmat entries of the last end-to-end step (all-reduced at N > 1) at 64 scattered samples "
                       "(first / middle / last 256-sample tile rows) vs oracle on those samples' columns of every shard"}
 
+
+    # ---- extra: the FIXED config-2 problem (N_SAMP x N_SNP in total) split over the ranks by SNP block ----
+    strong = None
+    if world > 1 and not args.no_extra:
+        lo, hi = D.shard_range(N_SNP, rank, world)
+        ctx.geno_begin(N_SAMP, hi - lo)
+        ctx.geno_synth(hi - lo, seed=SEED, miss_rate=MISS, snp_start=lo)
+        sms = []
+        for _ in range(4):
+            barrier()
+            sms.append(step())
+        t = torch.tensor(sms[1:], dtype=torch.float64, device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        sm = float(t.mean())
+        strong = {"workload": f"config 2 as ONE fixed problem: {N_SAMP} samples x {N_SNP} SNPs split into {world} SNP blocks",
+                  "ms_per_step": sm, "value": 0.5 * N_SAMP * N_SAMP * N_SNP / (sm * 1e-3), "unit": UNIT, "scaling": "strong",
+                  "steps": 3, "warmup": 1}
+
     if rank != 0:
         if world > 1:
             tdist.destroy_process_group()
@@ -324,7 +406,7 @@ def run_ours(args):
               "tensor_passes_per_step": int(pl.digits) + int(pl.digits_w) + int(pl.digits_d)}
     pk, pk_kind = peaks()
     traffic, tensor_pct = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tp):      # dram__bytes_read+write of the dominant kernel, one ncu --set full capture
         rec = json.load(open(tp))
         traffic, tensor_pct = rec.get("traffic_bytes_per_launch"), rec.get("tensor_pipe_active_pct")
@@ -334,7 +416,7 @@ def run_ours(args):
     peak = pk.get("bf16_tflops_sustained", 1400.0)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "kernel": "snprel::tc2::table_gram_kernel2 (tcgen05.mma.cta_group::2.kind::i8, CTA pairs)",
+                "kernel": "snprel::tc2::table_gram_kernel3 (tcgen05.mma.cta_group::2.kind::i8, CTA pairs, one launch per step)",
                 "launches_per_step": hot_launch // args.steps, "fixed_point": passes,
                 "tensor_pipe_active_pct_ncu": tensor_pct, "kernel_ms_per_step": hot_per_step_ms,
                 "share_of_step": hot_per_step_ms / ms_per_step,
@@ -352,6 +434,23 @@ def run_ours(args):
                    "sample": f"reference CExactPCA (oracle/_ref) on {CPU_N} samples x {CPU_M} SNPs of the same "
                              f"generator, {dt:.2f} s"}
 
+    extra = {}
+    if strong:
+        extra["strong"] = strong
+    if world == 1 and not args.no_extra:
+        ctx.close()
+        extra["pair_counters"] = pair_counter_legs(local, None)
+    pk2 = measured_peaks_r02()
+    if pk2 and "int8_tcgen05_random_operands_sustained" in pk2:
+        # executed int8 work of K1 (full 256 x 256 tiles of the upper triangle x digit passes) against the
+        # measured sustained tcgen05 int8 issue peak of this chip under its power cap
+        nt = (N_SAMP + 255) // 256
+        exec_ops = 2.0 * (nt * (nt + 1) // 2) * 65536.0 * N_SNP * passes["tensor_passes_per_step"]
+        i8 = pk2["int8_tcgen05_random_operands_sustained"]["tops"]
+        roofline["executed_int8_tops"] = exec_ops / (hot_per_step_ms * 1e-3) / 1e12
+        roofline["int8_peak_measured_tops"] = i8
+        roofline["executed_frac_of_int8_peak"] = roofline["executed_int8_tops"] / i8
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -364,7 +463,7 @@ def run_ours(args):
         "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
         "parity": parity, "roofline": roofline, "cpu_baseline": cpu,
         "clocks": sampler.summary() if sampler else None,
-        "eigen_top32_ms": eig_ms, "eigen_top32": eig_info,
+        "eigen_top32_ms": eig_ms, "eigen_top32": eig_info, "extra": extra or None,
     }
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -381,6 +480,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-eigen", action="store_true", help="skip the top-32 eigen step")
+    ap.add_argument("--no-extra", action="store_true", help="skip the optional legs (pair counters at 1 GPU, strong scaling at N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

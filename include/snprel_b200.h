@@ -229,6 +229,17 @@ int snprel_eigmix_snp_loading(snprel_ctx *ctx, int k, const double *eigval,
 int snprel_eigmix_samp_loading(snprel_ctx *ctx, int k, const double *loadings,
                                const double *afreq, double *out);
 
+/* gnrPCA algorithm "randomized" (src/genPCA.cpp:1436-1442, CRandomPCA :469-796).
+ * aux_mat: the R vector rnorm(aux.dim * n.samp) (R/PCA.R:56), i.e. G_0 as a column-major
+ * n_samp x aux_dim matrix; not modified (the reference overwrites it).  Outputs, as the three list
+ * elements of the reference: sigma[n_samp] singular values of T (zero padded), vt = the rows of
+ * V_T^T, row-major [aux_dim * (iter_num + 1)][n_samp] (rows beyond min(hsize, n_samp) are zero), and
+ * 2 * TraceXTX.  R/PCA.R:80-89 turns them into eigenval / eigenvect / varprop.  Leading singular
+ * values / vectors agree with the reference run with num.thread = 1 (subspace angle < 1e-6); the
+ * trailing directions of the ill-conditioned Krylov basis are not comparable between LAPACKs. */
+int snprel_pca_randomized(snprel_ctx *ctx, const double *aux_mat, int aux_dim, int iter_num,
+                          double *sigma, double *vt, double *trace_xtx2);
+
 /* ---- split accumulate / reduce / finish (multi-GPU SNP sharding) ------- */
 
 #define SNPREL_EST_IBS          10

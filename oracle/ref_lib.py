@@ -89,6 +89,17 @@ class RefWorkspace:
         _ck(_lib().ref_pca(int(nthread), int(bayesian), int(eigen_cnt), _p(genmat), C.byref(tr), _p(ev), _p(evec)))
         return dict(genmat=genmat, TraceXTX=tr.value, eigenval=ev, eigenvect=None if evec is None else evec.T)
 
+    def pca_randomized(self, aux_mat, aux_dim, iter_num=10, nthread=1):
+        """gnrPCA algorithm "randomized" (src/genPCA.cpp:1436-1442, CRandomPCA :469-796)
+        -> (sigma [nsamp], V^T [hsize, nsamp], 2 TraceXTX)."""
+        n = self.dims()[1]
+        hsize = aux_dim * (iter_num + 1)
+        aux = np.ascontiguousarray(aux_mat, dtype=np.float64).copy()     # overwritten by the reference
+        sigma, vt = np.empty(n), np.empty((n, hsize))                    # R matrix hsize x n, column major
+        tr = C.c_double()
+        _ck(_lib().ref_pca_randomized(int(nthread), _p(aux), int(aux_dim), int(iter_num), _p(sigma), _p(vt), C.byref(tr)))
+        return sigma, vt.T.copy(), tr.value
+
     def eigmix(self, nthread=1, diagadj=True):
         nsnp, n = self.dims()
         ibd, af = np.empty((n, n)), np.empty(nsnp)

@@ -340,6 +340,22 @@ int ref_pca(int nthread, int bayesian, int eigen_cnt, double *genmat, double *tr
     }
     REF_CATCH
 }
+// gnrPCA "randomized" (src/genPCA.cpp:1436-1442): aux.mat [aux.dim * n.samp] is overwritten
+int ref_pca_randomized(int nthread, double *aux_mat, int aux_dim, int iter_num, double *sigma, double *vt,
+                       double *trace2) {
+    REF_TRY
+    const int n = GWAS::MCWorkingGeno.Space().SampleNum();
+    SEXP aux = Rf_allocVector(REALSXP, (R_xlen_t)aux_dim * n);
+    memcpy(REAL(aux), aux_mat, sizeof(double) * (size_t)aux_dim * n);
+    SEXP param = named_list({{"aux.mat", aux}, {"aux.dim", Rf_ScalarInteger(aux_dim)},
+                             {"iter.num", Rf_ScalarInteger(iter_num)}});
+    SEXP r = gnrPCA(Rf_ScalarInteger(1), Rf_mkString("randomized"), Rf_ScalarInteger(nthread), param,
+                    Rf_ScalarLogical(0));
+    if (sigma) copy_real(VECTOR_ELT(r, 0), sigma);
+    if (vt) copy_real(VECTOR_ELT(r, 1), vt);
+    if (trace2) *trace2 = REAL(VECTOR_ELT(r, 2))[0];
+    REF_CATCH
+}
 int ref_eigmix(int nthread, int diagadj, double *ibd, double *afreq) {
     REF_TRY
     SEXP param = named_list({{"diagadj", Rf_ScalarLogical(diagadj)}, {"ibdmat", Rf_ScalarLogical(1)}});

@@ -117,6 +117,46 @@ def pca_genmat(geno, bayesian=False):
     return c, tr, np.trace(c)
 
 
+def pca_randomized(geno, aux_mat, aux_dim, iter_num=10):
+    """CRandomPCA::Run (src/genPCA.cpp:684-790), the randomized algorithm of gnrPCA (:1436-1442).
+    aux_mat: the R vector rnorm(aux.dim * n.samp) (R/PCA.R:56), read by the reference as the
+    column-major nSamp x AuxDim matrix G_0 (AuxMat[j * nSamp + i], :535-563).
+      Y[l][g] = (g - avg_l) / sqrt(2 p_l (1 - p_l)), 0 for missing / monomorphic      (:497-517)
+      H_it = Y G_it,  G_{it+1} = Y^T H_it / nSNP,  it = 0 .. iter_num                  (:710-742)
+      V^T = right singular vectors of MatH [hsize x nSNP] (dgesvd "N","O", :642-662,752)
+      T = V^T Y [hsize x nSamp]  (:619-640,763-768),  sigma, V_T^T = svd(T)             (:778-779)
+    Returns (sigma padded with zeros to nSamp, V_T^T [min(hsize, nSamp), nSamp], 2 TraceXTX) -- the
+    three list elements gnrPCA hands back (:781-793)."""
+    geno = np.asarray(geno)
+    m, n = geno.shape
+    s, num, avg = _avg_geno(geno)
+    p = avg * 0.5
+    ok = (p > 0) & (p < 1)
+    sc = np.where(ok, 1.0 / np.sqrt(np.where(ok, 2 * p * (1 - p), 1.0)), 0.0)
+    y = np.where(geno <= 2, (geno.astype(np.float64) - avg[:, None]) * sc[:, None], 0.0)      # [nSNP, nSamp]
+    trace = float((y * y).sum())
+    g = np.asarray(aux_mat, dtype=np.float64).reshape(aux_dim, n).T.copy()                    # [nSamp, AuxDim]
+    hs = []
+    for it in range(iter_num + 1):
+        h = y @ g
+        hs.append(h)
+        if it < iter_num:
+            g = (y.T @ h) / m
+    math = np.hstack(hs)                                                                      # [nSNP, hsize]
+    u, _, _ = np.linalg.svd(math, full_matrices=False)        # columns = rows of the reference's V^T
+    t = u.T @ y
+    _, sig, vt = np.linalg.svd(t, full_matrices=False)
+    sigma = np.zeros(n)
+    sigma[:len(sig)] = sig
+    return sigma, vt, 2.0 * trace
+
+
+def pca_randomized_result(sigma, vt, trace2, n_samp, eigen_cnt):
+    """R/PCA.R:80-89: varprop = 2 d^2 / TraceXTX, eigenval = (n - 1) varprop, eigenvect = t(V[1:eigen.cnt, ])."""
+    vp = 2.0 * np.asarray(sigma) ** 2 / trace2
+    return dict(eigenval=(n_samp - 1) * vp, eigenvect=np.asarray(vt)[:eigen_cnt].T.copy(), varprop=vp, TraceXTX=trace2)
+
+
 def pca_eigen(genmat, eigen_cnt):
     """CalcEigen on -C (src/genPCA.cpp:1262-1346): top-k eigenpairs, descending.
     The reference's own tests pin eigenvectors only through rounded loadings,

@@ -77,6 +77,7 @@ def load_library():
         "snprel_pca_snp_loading": [p, i32, p, p, dbl, i32, p, p, p],
         "snprel_pca_samp_loading": [p, i32, p, p, p, p],
         "snprel_pca_corr": [p, i32, p, p],
+        "snprel_pca_randomized": [p, p, i32, i32, p, p, p],
         "snprel_eigmix_snp_loading": [p, i32, p, p, p, p],
         "snprel_eigmix_samp_loading": [p, i32, p, p, p],
         "snprel_plan_local": [p, i32, C.POINTER(Plan)],
@@ -121,7 +122,7 @@ EXPORTED_SYMBOLS = [
     "snprel_geno_dim", "snprel_geno_copy_u8", "snprel_geno_copy_2b", "snprel_snp_ratefreq", "snprel_select_snp_base", "snprel_select_snp_base_ex",
     "snprel_ibs_num", "snprel_ibs_ave", "snprel_ibd_mom", "snprel_ibd_mom_sums", "snprel_ibd_mom_from_sums", "snprel_king_robust", "snprel_king_robust_counts",
     "snprel_king_homo", "snprel_indiv_beta", "snprel_indiv_beta_counts", "snprel_grm",
-    "snprel_pca", "snprel_eigmix", "snprel_pca_snp_loading", "snprel_pca_samp_loading", "snprel_pca_corr",
+    "snprel_pca", "snprel_eigmix", "snprel_pca_snp_loading", "snprel_pca_samp_loading", "snprel_pca_corr", "snprel_pca_randomized",
     "snprel_eigmix_snp_loading", "snprel_eigmix_samp_loading", "snprel_plan_local", "snprel_accumulate",
     "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced", "snprel_last_plan", "snprel_set_row_window", "snprel_window_count", "snprel_mem_info",
     "snprel_kernel_launches", "snprel_last_hot_kernel", "snprel_time_accumulate", "snprel_time_finish", "snprel_last_step_ms", "snprel_invalidate",
@@ -459,6 +460,19 @@ class Context:
         out = np.empty((k, n))
         self._ck(self.lib.snprel_pca_samp_loading(self.h, k, _ptr(ld), _ptr(af), _ptr(sc), _ptr(out)))
         return out.T
+
+    def pca_randomized(self, aux_mat, aux_dim, iter_num=10):
+        """gnrPCA "randomized" -> (sigma [n], V^T [aux_dim * (iter_num + 1), n], 2 TraceXTX)."""
+        n, _ = self.geno_dim()
+        aux = np.ascontiguousarray(aux_mat, dtype=np.float64).reshape(-1)
+        if aux.size != aux_dim * n:
+            raise SNPRelError("aux_mat must hold aux_dim * n_samp values")
+        hsize = aux_dim * (iter_num + 1)
+        sigma, vt = np.empty(n), np.empty((hsize, n))
+        tr = C.c_double()
+        self._ck(self.lib.snprel_pca_randomized(self.h, _ptr(aux), int(aux_dim), int(iter_num), _ptr(sigma), _ptr(vt),
+                                                C.byref(tr)))
+        return sigma, vt, tr.value
 
     def pca_corr(self, eigenvect):
         """-> snpcorr [k, n_snp]."""

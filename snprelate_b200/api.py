@@ -203,13 +203,16 @@ def snpgdsMergeGRM(filelist, out_fn=None, out_prec="double", weight=None, verbos
 
 
 def snpgdsPCA(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_monosnp=True,
-              maf=float("nan"), missing_rate=0.01, algorithm="exact", eigen_cnt=32, num_thread=1,
+              maf=float("nan"), missing_rate=0.01, algorithm="exact", eigen_cnt=None, num_thread=1,
               bayesian=False, need_genmat=False, genmat_only=False, eigen_method="DSPEVX",
-              verbose=False, device=0):
-    """R/PCA.R:22-91 -> gnrPCA "exact" (src/genPCA.cpp:1355-1452)."""
-    if algorithm != "exact":
-        raise SNPRelError("only algorithm='exact' is on the accelerated path "
-                          "(randomized PCA is out of scope, SURVEY.md section 2)")
+              aux_dim=None, iter_num=10, aux_mat=None, verbose=False, device=0):
+    """R/PCA.R:22-91 -> gnrPCA "exact" / "randomized" (src/genPCA.cpp:1355-1452).  eigen_cnt
+    defaults to 32 (exact) or 16 (randomized) when None; aux_dim to 2 * eigen_cnt.  `aux_mat`
+    stands in for R's rnorm(aux.dim * n.samp) (R/PCA.R:56): pass it for a reproducible run."""
+    if algorithm not in ("exact", "randomized"):
+        raise SNPRelError("'arg' should be one of \"exact\", \"randomized\"")      # match.arg
+    if eigen_cnt is None:
+        eigen_cnt = 16 if algorithm == "randomized" else 32
     if eigen_method not in ("DSPEVX", "DSPEV"):
         raise SNPRelError("Unknown 'eigen.method'.")
     ws = _init_file2(gdsobj, sample_id, snp_id, autosome_only, remove_monosnp, maf, missing_rate,
@@ -218,6 +221,18 @@ def snpgdsPCA(gdsobj, sample_id=None, snp_id=None, autosome_only=True, remove_mo
         need_genmat = True
     if eigen_cnt <= 0:
         eigen_cnt = ws["n_samp"]
+    if algorithm == "randomized":
+        n = ws["n_samp"]
+        if aux_dim is None:
+            aux_dim = 2 * eigen_cnt
+        if aux_mat is None:
+            aux_mat = np.random.default_rng().standard_normal(aux_dim * n)
+        with ws["ctx"] as ctx:
+            d, h, tr2 = ctx.pca_randomized(aux_mat, aux_dim, iter_num)
+        vp = 2.0 * d ** 2 / tr2                                            # R/PCA.R:82-87
+        return {"sample.id": ws["sample_id"], "snp.id": ws["snp_id"], "eigenval": (n - 1) * vp,
+                "eigenvect": np.ascontiguousarray(h[:eigen_cnt].T), "varprop": vp, "TraceXTX": tr2,
+                "Bayesian": False, "class": "snpgdsPCAClass"}
     with ws["ctx"] as ctx:
         r = ctx.pca(eigen_cnt, bayesian, need_genmat, genmat_only)
     eigenval = r["eigenval"]

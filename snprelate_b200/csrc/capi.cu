@@ -233,6 +233,11 @@ int snprel_pca_corr(snprel_ctx *c, int k, const double *eigvect, double *out) {
     API_BEGIN(c) pca_corr(c, k, eigvect, out);
     API_END(c)
 }
+int snprel_pca_randomized(snprel_ctx *c, const double *aux_mat, int aux_dim, int iter_num, double *sigma, double *vt,
+                          double *trace_xtx2) {
+    API_BEGIN(c) pca_randomized(c, aux_mat, aux_dim, iter_num, sigma, vt, trace_xtx2);
+    API_END(c)
+}
 int snprel_eigmix_snp_loading(snprel_ctx *c, int k, const double *eigval, const double *eigvect, const double *afreq,
                               double *loading) {
     API_BEGIN(c) eigmix_snp_loading(c, k, eigval, eigvect, afreq, loading);

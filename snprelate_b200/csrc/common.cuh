@@ -115,6 +115,8 @@ void pca_corr(snprel_ctx *c, int k, const double *eigvect, double *out);
 void eigmix_snp_loading(snprel_ctx *c, int k, const double *eigval, const double *eigvect, const double *afreq,
                         double *loading);
 void eigmix_samp_loading(snprel_ctx *c, int k, const double *loadings, const double *afreq, double *out);
+void pca_randomized(snprel_ctx *c, const double *aux_mat, int aux_dim, int iter_num, double *sigma, double *vt,
+                    double *trace_xtx2);
 
 }  // namespace snprel
 
@@ -320,6 +322,11 @@ void tensor_count_accumulate(snprel_ctx *c, int est);
 // eigen.cu
 void eigen_topk(snprel_ctx *c, const double *m_upper, int64_t n, int k, double *eigval, double *eigvec);
 void eigen_release(snprel_ctx *c);
+// small dense helpers on the context's cuBLAS / cuSOLVER handles (column-major, float64)
+void la_transpose(snprel_ctx *c, int64_t m, int64_t n, const double *A, int64_t lda, double *B, int64_t ldb);   // B [m x n] = A^T, A [n x m]
+void la_orthonormalise(snprel_ctx *c, double *A, int64_t m, int n);   // A [m x n], m >= n, lda = m  <-  Q of its Householder QR
+// thin SVD of A [m x n], m >= n, lda = m (destroyed): S -> host [n]; U [m x n] and / or VT [n x n] on the device (may be NULL)
+void la_svd_tall(snprel_ctx *c, double *A, int64_t m, int n, double *S_host, double *U, double *VT);
 
 
 // project.cu
@@ -331,5 +338,7 @@ void pca_corr(snprel_ctx *c, int k, const double *eigvect, double *out);
 void eigmix_snp_loading(snprel_ctx *c, int k, const double *eigval, const double *eigvect, const double *afreq,
                         double *loading);
 void eigmix_samp_loading(snprel_ctx *c, int k, const double *loadings, const double *afreq, double *out);
+void pca_randomized(snprel_ctx *c, const double *aux_mat, int aux_dim, int iter_num, double *sigma, double *vt,
+                    double *trace_xtx2);
 
 }  // namespace snprel

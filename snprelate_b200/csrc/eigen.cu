@@ -462,4 +462,52 @@ void eigen_topk(snprel_ctx *c, const double *m_upper, int64_t n, int k, double *
     }
 }
 
+// ---------------------------------------------------------------------------
+// dense helpers for the randomized PCA (project.cu): library calls on small / tall-skinny operands
+// ---------------------------------------------------------------------------
+void la_transpose(snprel_ctx *c, int64_t m, int64_t n, const double *A, int64_t lda, double *B, int64_t ldb) {
+    Handles &h = handles(c);
+    const double one = 1.0, zero = 0.0;
+    CUBLAS_CHECK(cublasDgeam(h.blas, CUBLAS_OP_T, CUBLAS_OP_N, (int)m, (int)n, &one, A, (int)lda, &zero, B, (int)ldb, B, (int)ldb));
+}
+
+void la_orthonormalise(snprel_ctx *c, double *A, int64_t m, int n) {
+    Handles &h = handles(c);
+    if (m > 2147483647ll) fail("la_orthonormalise: too many rows");
+    DevBuf<double> tau, work;
+    DevBuf<int> info;
+    tau.alloc((size_t)n);
+    info.alloc(1);
+    int lw_qr = 0, lw_org = 0;
+    CUSOLVER_CHECK(cusolverDnDgeqrf_bufferSize(h.sol, (int)m, n, A, (int)m, &lw_qr));
+    CUSOLVER_CHECK(cusolverDnDorgqr_bufferSize(h.sol, (int)m, n, n, A, (int)m, tau.p, &lw_org));
+    const int lwork = std::max(lw_qr, lw_org);
+    work.alloc((size_t)lwork);
+    CUSOLVER_CHECK(cusolverDnDgeqrf(h.sol, (int)m, n, A, (int)m, tau.p, work.p, lwork, info.p));
+    CUSOLVER_CHECK(cusolverDnDorgqr(h.sol, (int)m, n, n, A, (int)m, tau.p, work.p, lwork, info.p));
+    int hinfo = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (hinfo != 0) fail("cusolverDnDgeqrf / Dorgqr failed (info %d)", hinfo);
+}
+
+void la_svd_tall(snprel_ctx *c, double *A, int64_t m, int n, double *S_host, double *U, double *VT) {
+    Handles &h = handles(c);
+    if (m < n) fail("la_svd_tall: needs m >= n");
+    DevBuf<double> S, work;
+    DevBuf<int> info;
+    S.alloc((size_t)n);
+    info.alloc(1);
+    int lwork = 0;
+    CUSOLVER_CHECK(cusolverDnDgesvd_bufferSize(h.sol, (int)m, n, &lwork));
+    work.alloc((size_t)std::max(lwork, 1));
+    CUSOLVER_CHECK(cusolverDnDgesvd(h.sol, U ? 'S' : 'N', VT ? 'S' : 'N', (int)m, n, A, (int)m, S.p, U, (int)m, VT, n,
+                                    work.p, lwork, nullptr, info.p));
+    int hinfo = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(S_host, S.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (hinfo != 0) fail("cusolverDnDgesvd failed (info %d)", hinfo);
+}
+
 }  // namespace snprel

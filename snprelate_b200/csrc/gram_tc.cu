@@ -17,9 +17,11 @@
 //
 // Mapping onto sm_100a: a cluster of two CTAs (one TPC, tcgen05 cta_group::2) owns a 256 x 256
 // sample tile (upper triangle only) and an SNP split; 10 warps per CTA, 1 CTA per SM.
-//   * warp 1, one lane -- TMA loader: per 128-SNP stage four cp.async.bulk.tensor.2d boxes
-//     (16 bytes x 128 SNP rows) of the packed 2-bit genotypes plus cp.async.bulk copies of the
-//     digit tables into a 3-deep shared-memory ring, mbarrier complete_tx.
+//   * warp 1, one lane -- TMA loader: per 128-SNP stage two cp.async.bulk.tensor.2d boxes
+//     (32 bytes = 128 samples x 128 SNP rows, 32-byte swizzle) of the packed 2-bit genotypes plus
+//     cp.async.bulk copies of the digit tables into a 3-deep shared-memory ring, mbarrier
+//     complete_tx.  (Round 1 used four 16-byte boxes: every 32-byte L2 sector was fetched twice;
+//     the wider box cut the L2->SM sectors by 40 % and the kernel time by 3.7 %, profiles/r02_notes.md.)
 //   * warps 2..9 -- producers: each thread takes 64 packed genotypes of one SNP for this CTA's
 //     128 A rows and for ITS HALF (128) of the B rows, turns every 32-bit word (16 samples) into
 //     byte-permute selectors (3 logic ops + 2 shifts) and emits int8 operand rows with PRMT
@@ -103,6 +105,7 @@ struct Params {
     long long row0;          // first row of the output window (planes hold rows row0 ..)
     int upper_only;
     uint32_t sh32;
+    int box32;               // genotype boxes are 32 bytes wide with the 32-byte TMA swizzle (else 16 bytes, plain)
     int *error_flag;
 };
 
@@ -182,7 +185,7 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
     constexpr int PF_NBOX = 2 + 2 * NB;                       // A quads 0-1, then two quads per B tile
     constexpr int PF_BYTES = PF_NBOX * PF_BOX + (NP + 1) * PF_TAB;   // boxes, NP A tables, the B table
     static_assert(PF_DEPTH * PF_BYTES <= PF_RING_BYTES, "ring does not fit");
-    static_assert(PF_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
+    static_assert(PF_BYTES % 256 == 0, "TMA destinations are 128-byte aligned; the 32-byte swizzle pattern repeats every 256");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const uint32_t smem_base = smem_u32(smem);
@@ -278,8 +281,12 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
                 const uint32_t bar = pf_full(sl);
                 mbar_arrive_expect_tx(bar, tx_bytes);
                 const int y = (st_begin + it) * SK;
+                if (P.box32) {
+                    tma_load_2d(slot, tmap, ax, y, bar);
+                } else {
 #pragma unroll
-                for (int q = 0; q < HM / 64; q++) tma_load_2d(slot + q * PF_BOX, tmap, ax + q * 16, y, bar);
+                    for (int q = 0; q < HM / 64; q++) tma_load_2d(slot + q * PF_BOX, tmap, ax + q * 16, y, bar);
+                }
 #pragma unroll
                 for (int b = 0; b < NB; b++) {
                     if (ncols[b] == 0) continue;
@@ -288,9 +295,13 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
                     // beyond the padded matrix are out of bounds for the tensor map and arrive as zeros
                     // (code 0); the epilogue drops them.
                     const int bx = ((item.tn + b) * TN2 + (int)rank * (ncols[b] >> 1)) / 4;
+                    if (P.box32) {
+                        tma_load_2d(slot + (2 + 2 * b) * PF_BOX, tmap, bx, y, bar);
+                    } else {
 #pragma unroll
-                    for (int q = 0; q < HN / 64; q++)
-                        tma_load_2d(slot + (2 + 2 * b + q) * PF_BOX, tmap, bx + q * 16, y, bar);
+                        for (int q = 0; q < HN / 64; q++)
+                            tma_load_2d(slot + (2 + 2 * b + q) * PF_BOX, tmap, bx + q * 16, y, bar);
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < NP; q++)
@@ -307,8 +318,12 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
         const int kg = sl >> 3, r = sl & 7;
         const uint32_t a_off = kg * LBO + (half * 4) * SBO + r * 16;
         const uint32_t b_off = NP * A_BYTES + a_off;
-        const uint32_t pa = half * PF_BOX + sl * 16;
-        const uint32_t pb = (2 + half) * PF_BOX + sl * 16;
+        // 16-byte boxes: [quad][SNP][16 B].  32-byte boxes: [SNP][32 B] with the 32-byte swizzle (address
+        // bit 4 ^= bit 7; the slots are 256-byte aligned), which keeps the LDS.128 of eight consecutive
+        // SNPs on eight different 16-byte bank groups.
+        const uint32_t sw = (uint32_t)(half ^ ((sl >> 2) & 1)) * 16u;
+        const uint32_t pa = P.box32 ? (uint32_t)sl * 32u + sw : half * PF_BOX + sl * 16;
+        const uint32_t pb = P.box32 ? 2 * PF_BOX + (uint32_t)sl * 32u + sw : (2 + half) * PF_BOX + sl * 16;
         const uint32_t pt = PF_NBOX * PF_BOX + sl * 4;
         int bwords[NB];                // 16-sample words of B tile b this thread expands (0..4)
 #pragma unroll
@@ -559,9 +574,11 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     // CTA pairs share genotype panels in L2), tiles in a super-tile raster
     std::vector<Item> items;
     auto width = [&](int t) { return tile_ncols(std::min<int64_t>(TN2, n - (int64_t)t * TN2)); };
+    int only_group = -1;
     auto emit = [&](int tm, int tn) {
         const int first_col = upper_only ? tm : 0;
         for (size_t gi = 0; gi < groups.size(); gi++) {
+            if (only_group >= 0 && (int)gi != only_group) continue;
             const Group &g = groups[gi];
             Item it{};
             it.tm = tm;
@@ -587,10 +604,22 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
         }
     };
     constexpr int RB = 8, CB = 8;
-    for (int rb = tm_lo / RB * RB; rb < tm_hi; rb += RB)
-        for (int cb = (upper_only ? rb / CB * CB : 0); cb < nt; cb += CB)
-            for (int tm = std::max(rb, tm_lo); tm < std::min(rb + RB, tm_hi); tm++)
-                for (int tn = std::max(cb, upper_only ? tm : 0); tn < std::min(cb + CB, nt); tn++) emit(tm, tn);
+    const size_t g_lo = 0, g_hi = groups.size();
+    auto raster = [&]() {
+        for (int rb = tm_lo / RB * RB; rb < tm_hi; rb += RB)
+            for (int cb = (upper_only ? rb / CB * CB : 0); cb < nt; cb += CB)
+                for (int tm = std::max(rb, tm_lo); tm < std::min(rb + RB, tm_hi); tm++)
+                    for (int tn = std::max(cb, upper_only ? tm : 0); tn < std::min(cb + CB, nt); tn++) emit(tm, tn);
+    };
+    if (c->debug_flags & 128u) {      // experiment: group-major (all tiles of one pass group, then the next)
+        for (size_t g = g_lo; g < g_hi; g++) {
+            only_group = (int)g;
+            raster();
+        }
+        only_group = -1;
+    } else {
+        raster();
+    }
     if (items.empty()) return;
     // wave tail: the items that start last are cut in four, so the chip drains in quarter steps
     if (!(c->debug_flags & 2u) && parts == 1 && (int64_t)items.size() > 4 * slots) {
@@ -633,15 +662,19 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
         encode = reinterpret_cast<EncodeFn>(fn);
     }
     alignas(64) CUtensorMap tmap;
+    const bool box32 = (c->debug_flags & 16u) == 0;   // flag 16: the round-1 16-byte boxes (A/B experiments)
     {
         const int64_t rows = round_up(std::max<int64_t>(c->n_snp, 1), SK);
         cuuint64_t gdim[2] = {(cuuint64_t)c->row_bytes, (cuuint64_t)rows};
         cuuint64_t gstride[1] = {(cuuint64_t)c->row_bytes};
-        cuuint32_t box[2] = {16, (cuuint32_t)SK};
+        cuuint32_t box[2] = {box32 ? 32u : 16u, (cuuint32_t)SK};
         cuuint32_t estr[2] = {1, 1};
+        const CUtensorMapL2promotion promo = (c->debug_flags & 32u)   ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                             : (c->debug_flags & 64u) ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                                      : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
         CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->geno2b.p, gdim, gstride, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, box32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                            promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled failed (%d)", (int)r);
     }
 
@@ -660,6 +693,7 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     P.n_samp = n;
     P.upper_only = upper_only ? 1 : 0;
     P.sh32 = 32;
+    P.box32 = box32 ? 1 : 0;
     P.error_flag = derr;
     table_gram_kernel3<<<dim3((unsigned)(2 * items.size())), THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
     KERNEL_CHECK(c);

@@ -64,7 +64,7 @@ __device__ __forceinline__ void stage_fma(const double (&As)[PJ_STEP][PJ_ROWS], 
 __global__ void __launch_bounds__(PJ_ROWS)
 snp_project_kernel(const uint8_t *__restrict__ geno, int64_t row_bytes, int64_t n_snp, int64_t npad, int mode,
                    const double2 *__restrict__ ab, const double *__restrict__ Vt, int kp, int k_out,
-                   double *__restrict__ out) {
+                   double *__restrict__ out, int64_t ld_out) {
     __shared__ __align__(16) double As[PJ_STEP][PJ_ROWS];
     __shared__ __align__(16) double Bs[PJ_STEP][PJ_COLS];
     const int t = threadIdx.x, ty = t >> 3, tx = t & 7;
@@ -104,7 +104,7 @@ snp_project_kernel(const uint8_t *__restrict__ geno, int64_t row_bytes, int64_t 
 #pragma unroll
         for (int cc = 0; cc < 4; cc++) {
             const int kk = k0 + tx * 4 + cc;
-            if (kk < k_out) out[lr * k_out + kk] = acc[r][cc];
+            if (kk < k_out) out[lr * ld_out + kk] = acc[r][cc];
         }
     }
 }
@@ -112,7 +112,7 @@ snp_project_kernel(const uint8_t *__restrict__ geno, int64_t row_bytes, int64_t 
 // part[z][k][i] = sum over the z-th SNP range of z_il Lt[l][k];  Lt is [round_up(n_snp,32)][kp], zero padded
 __global__ void __launch_bounds__(PJ_ROWS)
 samp_project_kernel(const uint8_t *__restrict__ geno, int64_t row_bytes, int64_t n_snp, int64_t npad,
-                    const double2 *__restrict__ ab, const double *__restrict__ Lt, int kp, int64_t snps_per_split,
+                    const double2 *__restrict__ ab, const double *__restrict__ Lt, int64_t kp, int64_t snps_per_split,
                     double *__restrict__ part) {
     __shared__ __align__(16) double As[PJ_STEP][PJ_ROWS];
     __shared__ __align__(16) double Bs[PJ_STEP][PJ_COLS];
@@ -253,12 +253,12 @@ static void upload_panel(snprel_ctx *c, DevBuf<double> &dev, const double *src, 
 }
 
 static void run_snp_project(snprel_ctx *c, int mode, const double2 *ab, const double *Vt, int kp, int k,
-                            double *out_dev) {
+                            double *out_dev, int64_t ld_out = 0) {
     if (c->n_snp == 0) return;
     dim3 grid((unsigned)((c->n_snp + PJ_ROWS - 1) / PJ_ROWS), (unsigned)(kp / PJ_COLS));
     CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
     snp_project_kernel<<<grid, PJ_ROWS, 0, c->stream>>>(c->geno2b.p, c->row_bytes, c->n_snp, c->n_samp_pad, mode, ab,
-                                                        Vt, kp, k, out_dev);
+                                                        Vt, kp, k, out_dev, ld_out > 0 ? ld_out : (int64_t)k);
     KERNEL_CHECK(c);
     CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -414,6 +414,185 @@ void eigmix_samp_loading(snprel_ctx *c, int k, const double *loadings, const dou
     DevBuf<double2> ab;
     upload_ab(c, ab, afreq, 2.0, nullptr, eigmix_afreq_scale(afreq, c->n_snp));
     run_samp_project(c, ab.p, loadings, k, out);
+}
+
+// ---------------------------------------------------------------------------
+// Randomized PCA: CRandomPCA (src/genPCA.cpp:469-796), gnrPCA algorithm "randomized" (:1436-1442)
+//   Y[l][g] = (g - avg_l) * s_l,  s_l = 1 / sqrt(2 p_l (1 - p_l)) (0 outside (0,1)), missing -> 0   (:497-517)
+//   H_it = Y G_it  (snp_project),   G_{it+1} = Y^T H_it / nSNP  (samp_project),  it = 0 .. iter_num  (:710-742)
+//   V^T  = orthonormal basis of the row space of MatH [hsize x nSNP]                                  (:752)
+//   T    = V^T Y [hsize x nSamp] (samp_project with hsize columns), sigma / right vectors = svd(T)    (:763-779)
+// The reference takes V^T from a LAPACK SVD of MatH; T's singular values and right singular vectors
+// only depend on the row SPACE of MatH (any other orthonormal basis is Q V^T with Q orthogonal, and
+// svd(Q T) has the same sigma and right vectors), so a Householder QR of MatH^T (cuSOLVER geqrf + orgqr)
+// serves; the two tall products run on the float64 projection kernels above, straight from the
+// resident 2-bit matrix.  Single-thread semantics of the reference (its multi-threaded G update
+// re-adds the per-thread partials of earlier blocks, :727-735).
+// ---------------------------------------------------------------------------
+__global__ void rand_scale_kernel(const SnpStat *__restrict__ st, int64_t n_snp, double2 *__restrict__ ab,
+                                  double *__restrict__ trace_part) {
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double tr = 0;
+    if (l < n_snp) {
+        const SnpStat s = st[l];
+        double avg = 0, scale = 0;
+        if (s.num > 0) {
+            avg = (double)s.sum / (double)s.num;
+            const double p = avg * 0.5;
+            scale = (0.0 < p && p < 1.0) ? 1.0 / sqrt(__dmul_rn(__dmul_rn(2.0, p), 1.0 - p)) : 0.0;
+        }
+        ab[l] = make_double2(avg, scale);
+        double tab[3];
+        z_table(0, make_double2(avg, scale), tab);
+        const int n2 = (s.sum - s.n1) / 2, n0 = s.num - s.n1 - n2;
+        tr = (double)n0 * tab[0] * tab[0] + (double)s.n1 * tab[1] * tab[1] + (double)n2 * tab[2] * tab[2];
+    }
+    __shared__ double sh[256];
+    sh[threadIdx.x] = tr;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) trace_part[blockIdx.x] = sh[0];
+}
+
+// G[i][kk] = mul * sum_z part[z][kk][i] (z ascending), written in the dense-operand layout [npad][kp]
+__global__ void samp_reduce_panel_kernel(const double *__restrict__ part, int splits, int64_t kp_total, int64_t npad,
+                                         int k_out, int64_t n, double mul, double *__restrict__ G, int kp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int kk = blockIdx.y;
+    if (i >= n || kk >= k_out) return;
+    double s = 0;
+    for (int z = 0; z < splits; z++) s += part[((int64_t)z * kp_total + kk) * npad + i];
+    G[i * kp + kk] = s * mul;
+}
+
+// part / splits for a device-side sample projection of k columns
+struct SampPlan { int kp; int64_t splits, sps; };
+static SampPlan samp_plan(snprel_ctx *c, int k) {
+    const int64_t npad = c->n_samp_pad, m = c->n_snp;
+    SampPlan p;
+    p.kp = (int)round_up(k, PJ_COLS);
+    const int64_t row_tiles = npad / PJ_ROWS, col_tiles = p.kp / PJ_COLS;
+    int64_t splits = std::max<int64_t>(1, ((int64_t)c->num_sms * 4 + row_tiles * col_tiles - 1) / (row_tiles * col_tiles));
+    splits = std::min<int64_t>(splits, std::max<int64_t>(1, (m + 1023) / 1024));
+    p.sps = round_up((std::max<int64_t>(m, 1) + splits - 1) / splits, PJ_STEP);
+    p.splits = std::max<int64_t>(1, (m + p.sps - 1) / p.sps);
+    return p;
+}
+
+void pca_randomized(snprel_ctx *c, const double *aux_mat, int aux_dim, int iter_num, double *sigma, double *vt,
+                    double *trace_xtx2) {
+    if (c->n_samp <= 0 || c->n_snp <= 0) fail("snprel_pca_randomized: no genotype workspace");
+    if (!aux_mat || aux_dim <= 0) fail("snprel_pca_randomized: 'aux.mat' / 'aux.dim' are required");
+    if (iter_num < 0) fail("snprel_pca_randomized: invalid 'iter.num'");
+    ensure_stats(c);
+    geno_pad_tail(c);
+    const int64_t n = c->n_samp, npad = c->n_samp_pad, m = c->n_snp;
+    const int64_t hsize = (int64_t)aux_dim * (iter_num + 1);
+    if (hsize > m) fail("snprel_pca_randomized: aux.dim * (iter.num + 1) = %lld exceeds the number of SNPs (%lld)",
+                        (long long)hsize, (long long)m);
+    const int kp = (int)round_up(aux_dim, PJ_COLS);
+    const int64_t ld = round_up(hsize, PJ_COLS) + PJ_COLS;     // row pitch of MatH: a 32-column panel read never leaves the row
+    const int64_t m32 = round_up(m, PJ_STEP);
+
+    // Y lookup tables and TraceXTX
+    DevBuf<double2> ab;
+    DevBuf<double> tpart;
+    const unsigned tb = (unsigned)((m + 255) / 256);
+    ab.alloc((size_t)m);
+    tpart.alloc(tb);
+    rand_scale_kernel<<<tb, 256, 0, c->stream>>>(c->stat.p, m, ab.p, tpart.p);
+    KERNEL_CHECK(c);
+    {
+        std::vector<double> h(tb);
+        CUDA_CHECK(cudaMemcpyAsync(h.data(), tpart.p, tb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        double tr = 0;
+        for (unsigned b = 0; b < tb; b++) tr += h[b];
+        if (trace_xtx2) *trace_xtx2 = 2.0 * tr;     // :792
+    }
+
+    // power iteration
+    DevBuf<double> G, H, part;
+    upload_panel(c, G, aux_mat, n, npad, aux_dim, kp, 1, n, nullptr);      // G_0[i][j] = aux.mat[j * nSamp + i]
+    H.alloc((size_t)m32 * ld);
+    H.zero(c->stream);
+    const SampPlan sp = samp_plan(c, aux_dim);
+    part.alloc((size_t)sp.splits * sp.kp * npad);
+    for (int it = 0; it <= iter_num; it++) {
+        run_snp_project(c, 0, ab.p, G.p, kp, aux_dim, H.p + (int64_t)it * aux_dim, ld);
+        if (it == iter_num) break;
+        dim3 grid((unsigned)(npad / PJ_ROWS), (unsigned)(sp.kp / PJ_COLS), (unsigned)sp.splits);
+        samp_project_kernel<<<grid, PJ_ROWS, 0, c->stream>>>(c->geno2b.p, c->row_bytes, m, npad, ab.p,
+                                                             H.p + (int64_t)it * aux_dim, ld, sp.sps, part.p);
+        KERNEL_CHECK(c);
+        dim3 rgrid((unsigned)((n + 255) / 256), (unsigned)aux_dim);
+        samp_reduce_panel_kernel<<<rgrid, 256, 0, c->stream>>>(part.p, (int)sp.splits, sp.kp, npad, aux_dim, n,
+                                                              1.0 / (double)m, G.p, kp);
+        KERNEL_CHECK(c);
+    }
+    part.release();
+
+    // orthonormal basis of the row space of MatH: Householder QR of MatH^T [nSNP x hsize]
+    {
+        DevBuf<double> Q;
+        Q.alloc((size_t)m * hsize);
+        la_transpose(c, m, hsize, H.p, ld, Q.p, m);            // H is column-major [ld x nSNP]
+        la_orthonormalise(c, Q.p, m, (int)hsize);
+        la_transpose(c, hsize, m, Q.p, m, H.p, ld);            // rows 0 .. hsize-1 of H <- Q^T
+    }
+
+    // T = Q^T Y  [hsize x nSamp]
+    const SampPlan st = samp_plan(c, (int)hsize);
+    part.alloc((size_t)st.splits * st.kp * npad);
+    DevBuf<double> T;
+    T.alloc((size_t)hsize * n);
+    {
+        dim3 grid((unsigned)(npad / PJ_ROWS), (unsigned)(st.kp / PJ_COLS), (unsigned)st.splits);
+        CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+        samp_project_kernel<<<grid, PJ_ROWS, 0, c->stream>>>(c->geno2b.p, c->row_bytes, m, npad, ab.p, H.p, ld, st.sps, part.p);
+        KERNEL_CHECK(c);
+        CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
+        dim3 rgrid((unsigned)((n + 255) / 256), (unsigned)hsize);
+        samp_reduce_kernel<<<rgrid, 256, 0, c->stream>>>(part.p, (int)st.splits, st.kp, npad, (int)hsize, n, T.p);
+        KERNEL_CHECK(c);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->hot_ms = ms;
+        c->hot_launches = 1;
+        c->hot_units = (double)n * (double)m * (double)hsize;
+    }
+    part.release();
+    H.release();
+
+    // sigma and the right singular vectors of T.  T.p holds T row-major [hsize][n] = T^T column-major [n x hsize].
+    const int64_t r = std::min<int64_t>(hsize, n);
+    std::vector<double> hs((size_t)r);
+    if (sigma) std::fill(sigma, sigma + n, 0.0);           // vector<double> sigma(nSamp), :777
+    if (vt) std::fill(vt, vt + hsize * n, 0.0);
+    if (n >= hsize) {
+        DevBuf<double> U;
+        U.alloc((size_t)n * hsize);
+        la_svd_tall(c, T.p, n, (int)hsize, hs.data(), U.p, nullptr);         // T^T = U S W^T: the columns of U
+        if (vt) CUDA_CHECK(cudaMemcpyAsync(vt, U.p, (size_t)n * hsize * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    } else {
+        DevBuf<double> Tc, VT;
+        Tc.alloc((size_t)hsize * n);
+        VT.alloc((size_t)n * n);
+        la_transpose(c, hsize, n, T.p, n, Tc.p, hsize);                      // T column-major [hsize x n]
+        la_svd_tall(c, Tc.p, hsize, (int)n, hs.data(), nullptr, VT.p);       // T = A S V^T: the rows of V^T
+        std::vector<double> hv((size_t)n * n);
+        CUDA_CHECK(cudaMemcpyAsync(hv.data(), VT.p, hv.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (vt)
+            for (int64_t h = 0; h < n; h++)
+                for (int64_t i = 0; i < n; i++) vt[h * n + i] = hv[(size_t)(h + i * n)];
+    }
+    if (sigma) std::copy(hs.begin(), hs.end(), sigma);
 }
 
 }  // namespace snprel

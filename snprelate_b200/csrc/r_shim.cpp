@@ -1,9 +1,10 @@
 // R-side binding of libsnprel_b200.so: drop-in bodies for the reference's .Call entry points
-// of the relatedness path.  SOURCE ONLY in this repository -- the build image has neither R nor
-// gdsfmt, so this file is not compiled here; it is written against the
-// reference's own headers (dGenGWAS.h) and is meant to replace the bodies of
+// of the relatedness path.  The build image has neither R nor gdsfmt; oracle/Makefile compiles this
+// file against the reference's own workspace layer (dGenGWAS.h / dGenGWAS.cpp, unmodified) and a
+// stand-in for the R / gdsfmt headers (oracle/ref_shim) into oracle/_ref/libsnprelate_b200_rshim.so,
+// which tests/test_gpu_rshim.py drives on the GPU.  It replaces the bodies of
 //   gnrGRM              src/genPCA.cpp:1614-1717      gnrIBSAve          src/genIBS.cpp:441-497
-//   gnrPCA (exact)      src/genPCA.cpp:1355-1452      gnrIBSNum          src/genIBS.cpp:500-550
+//   gnrPCA (both algs)  src/genPCA.cpp:1355-1452      gnrIBSNum          src/genIBS.cpp:500-550
 //   gnrEigMix           src/genEIGMIX.cpp:656-735     gnrIBD_KING_Robust src/genKING.cpp:576-679
 //   gnrGRM_avg_val      src/genPCA.cpp:1608           gnrIBD_KING_Homo   src/genKING.cpp:493-570
 //   gnrIBD_PLINK        src/genIBS.cpp:558-639        gnrIBD_Beta        src/genBeta.cpp:361-460
@@ -90,11 +91,30 @@ COREARRAY_DLL_EXPORT SEXP gnrGRM(SEXP NumThread, SEXP Method, SEXP GDS, SEXP use
 
 COREARRAY_DLL_EXPORT SEXP gnrPCA(SEXP EigenCnt, SEXP Algorithm, SEXP NumThread, SEXP ParamList, SEXP Verbose) {
     COREARRAY_TRY
-        if (strcmp(CHAR(STRING_ELT(Algorithm, 0)), "exact") != 0)
-            throw ErrCoreArray("only the exact algorithm is accelerated");
+        const char *alg = CHAR(STRING_ELT(Algorithm, 0));
+        if (strcmp(alg, "exact") != 0 && strcmp(alg, "randomized") != 0) throw "Invalid 'algorithm'.";
         Ctx c;
         load_workspace(c);
         const int n = MCWorkingGeno.Space().SampleNum();
+        if (strcmp(alg, "randomized") == 0) {
+            // src/genPCA.cpp:1436-1442, :781-793: list(sigma[n], V^T [hsize x n], 2 TraceXTX)
+            const int aux_dim = Rf_asInteger(RGetListElement(ParamList, "aux.dim"));
+            const int iter_num = Rf_asInteger(RGetListElement(ParamList, "iter.num"));
+            const size_t hsize = (size_t)aux_dim * (size_t)(iter_num + 1);
+            std::vector<double> vt(hsize * (size_t)n);
+            PROTECT(rv_ans = NEW_LIST(3));
+            SEXP d = PROTECT(NEW_NUMERIC(n)); SET_ELEMENT(rv_ans, 0, d); UNPROTECT(1);
+            SEXP h = PROTECT(Rf_allocMatrix(REALSXP, (int)hsize, n)); SET_ELEMENT(rv_ans, 1, h); UNPROTECT(1);
+            double tr2 = 0;
+            c.ck(snprel_pca_randomized(c.h, REAL(RGetListElement(ParamList, "aux.mat")), aux_dim, iter_num, REAL(d),
+                                       vt.data(), &tr2));
+            double *ph = REAL(h);      // R matrix hsize x n, column major
+            for (size_t r = 0; r < hsize; r++)
+                for (size_t i = 0; i < (size_t)n; i++) ph[r + i * hsize] = vt[r * (size_t)n + i];
+            SET_ELEMENT(rv_ans, 2, Rf_ScalarReal(tr2));
+            UNPROTECT(1);
+            return rv_ans;
+        }
         int nEig = Rf_asInteger(EigenCnt);
         if (nEig < 0) throw ErrCoreArray("Invalid 'eigen.cnt'.");
         if (nEig > n) nEig = n;

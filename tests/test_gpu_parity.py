@@ -542,3 +542,46 @@ def test_gds_bitstream_ingest(hapmap):
         c.geno_push_bitstream(stream, 0, 5000)
         c.geno_push_bitstream(stream, 5000, g.shape[0] - 5000)      # second chunk starts mid-byte
         assert np.array_equal(c.geno_copy_u8(), g)
+
+
+def _leading_subspace_ok(sig, vt, rsig, rvt, k):
+    assert np.max(np.abs(sig[:k] - rsig[:k]) / rsig[:k]) < 1e-7
+    assert np.max(1 - np.abs(np.sum(vt[:k] * rvt[:k], axis=1))) < 1e-10       # |cos| of each leading vector pair
+    # subspace angle of the whole leading block (north star: 1e-6 on the top-k eigenvectors)
+    s = np.linalg.svd(vt[:k] @ rvt[:k].T, compute_uv=False)
+    assert np.max(np.sqrt(np.maximum(0, 1 - s ** 2))) < 1e-6
+
+
+@pytest.mark.parametrize("n,m,aux_dim,it", [(300, 4000, 16, 10), (700, 9000, 8, 4), (120, 2500, 16, 10)])
+def test_randomized_pca_vs_oracle(n, m, aux_dim, it):
+    """snprel_pca_randomized against the oracle's restatement of CRandomPCA (pinned to the reference
+    itself, num.thread = 1, in tests/test_oracle_vs_reference.py).  The third case has
+    hsize = aux_dim (it + 1) > n_samp: the wide branch of the final SVD."""
+    g = O.synth_geno(n, m, seed=41, miss_rate=0.02)
+    aux = np.random.default_rng(n).standard_normal(aux_dim * n)
+    rsig, rvt, rtr = O.pca_randomized(g, aux, aux_dim, it)
+    with S.Context(0) as c:
+        c.geno_begin(n, m)
+        c.geno_push_u8(g)
+        sig, vt, tr = c.pca_randomized(aux, aux_dim, it)
+    assert abs(tr - rtr) <= 1e-12 * rtr
+    assert vt.shape == (aux_dim * (it + 1), n) and sig.shape == (n,)
+    r = min(n, aux_dim * (it + 1))
+    assert np.all(sig[r:] == 0) and np.all(vt[r:] == 0)
+    assert np.max(np.abs(vt[:r] @ vt[:r].T - np.eye(r))) < 1e-10               # orthonormal rows
+    _leading_subspace_ok(sig, vt, rsig, rvt, 6)
+
+
+def test_randomized_pca_through_the_api(gds, hapmap):
+    """snpgdsPCA(algorithm="randomized") (R/PCA.R:54-62,80-89): same result object as the exact
+    algorithm, leading components close to it."""
+    n = 279
+    aux = np.random.default_rng(1).standard_normal(32 * n)
+    r = S.snpgdsPCA(gds, algorithm="randomized", aux_mat=aux)
+    e = S.snpgdsPCA(gds, algorithm="exact", eigen_cnt=16)
+    assert r["eigenvect"].shape == (n, 16) and r["eigenval"].shape == (n,) and r["Bayesian"] is False
+    assert np.max(np.abs(r["eigenval"][:4] - e["eigenval"][:4]) / e["eigenval"][:4]) < 1e-6
+    assert np.max(1 - np.abs(np.sum(r["eigenvect"][:, :4] * e["eigenvect"][:, :4], axis=0))) < 1e-6
+    assert abs(r["TraceXTX"] - 2.0 * 0.5 * e["TraceXTX"]) / e["TraceXTX"] < 1e-12   # 2 x sum y^2 with y = z / sqrt(2)
+    with pytest.raises(S.SNPRelError):
+        S.snpgdsPCA(gds, algorithm="fast")

@@ -77,3 +77,16 @@ def test_workspace_selection_is_honoured(data):
     sub = np.ascontiguousarray(data[keep])
     assert relerr(w.grm("GCTA"), O.grm_gcta(sub)) < TOL
     assert np.array_equal(np.stack(w.ibs_num()), O.ibs_counts(sub))
+
+
+def test_randomized_pca_through_the_r_entry_point(data):
+    """gnrPCA(algorithm = "randomized") of the binding: list(sigma, V^T [hsize x n], 2 TraceXTX)."""
+    n = data.shape[1]
+    aux_dim, it = 8, 6
+    aux = np.random.default_rng(5).standard_normal(aux_dim * n)
+    w = R.RefWorkspace(data, R.RSHIM_PATH)
+    sig, vt, tr = w.pca_randomized(aux, aux_dim, it)
+    rsig, rvt, rtr = O.pca_randomized(data, aux, aux_dim, it)
+    assert abs(tr - rtr) <= 1e-12 * rtr and vt.shape == (aux_dim * (it + 1), n)
+    assert np.max(np.abs(sig[:4] - rsig[:4]) / rsig[:4]) < 1e-7
+    assert np.max(1 - np.abs(np.sum(vt[:4] * rvt[:4], axis=1))) < 1e-10

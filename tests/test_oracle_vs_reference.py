@@ -110,3 +110,27 @@ def test_loadings_projection_and_correlation(data):
     assert np.max(np.abs(w2.pca_samp_loading(sload, avg, scale) - O.pca_samp_loading(new, sload, avg, scale))) < 1e-11
     esl = el * np.sqrt(1.0 / ev[:5])[:, None]
     assert np.max(np.abs(w2.eigmix_samp_loading(esl, af) - O.eigmix_samp_loading(new, esl, af))) < 1e-12
+
+
+def test_randomized_pca(data):
+    """gnrPCA algorithm "randomized" (CRandomPCA, src/genPCA.cpp:469-796) with num.thread = 1.
+    (With several threads the reference re-adds the per-thread partial matrices AuxMat_mc of every
+    earlier block -- they are cleared once per iteration, :722-735 -- so its multi-threaded result
+    weights the SNP blocks unevenly; the single-threaded result is the algorithm as written.)
+    The dominant subspace is well conditioned, the trailing directions of the Krylov basis are not:
+    compare the leading singular values / vectors."""
+    rng = np.random.default_rng(3)
+    aux_dim, it, k = 16, 10, 8
+    n = data.shape[1]
+    aux = rng.standard_normal(aux_dim * n)
+    sig, vt, tr = O.pca_randomized(data, aux, aux_dim, it)
+    w = R.RefWorkspace(data)
+    rsig, rvt, rtr = w.pca_randomized(aux, aux_dim, it, nthread=1)
+    assert abs(tr - rtr) <= 1e-12 * rtr
+    assert rvt.shape == (aux_dim * (it + 1), n)
+    assert np.max(np.abs(sig[:k] - rsig[:k]) / rsig[:k]) < 1e-8
+    assert np.max(1 - np.abs(np.sum(vt[:k] * rvt[:k], axis=1))) < 1e-10
+    # and it approximates the exact decomposition (R/PCA.R:80-89)
+    res = O.pca_randomized_result(sig, vt, tr, n, k)
+    ev, evec = O.pca_eigen(O.pca_genmat(data)[0], k)
+    assert np.max(np.abs(res["eigenval"][:k] - ev[:k]) / ev[:k]) < 1e-3
