@@ -49,6 +49,8 @@ void snprel_destroy(snprel_ctx *ctx);
 const char *snprel_last_error(snprel_ctx *ctx);
 /* Library version string. */
 const char *snprel_version(void);
+/* Number of CUDA devices visible to the process (0 when there is none). */
+int snprel_device_count(void);
 
 /* ---- genotype workspace  (gnrSetGenoSpace, src/SNPRelate.cpp:76-114;
  *      CGenoReadBySNP block iterator, src/dGenGWAS.cpp:1218-1397) ---------- */
@@ -346,6 +348,41 @@ int snprel_table_gram(snprel_ctx *ctx, const int8_t *tabA /*[n_snp][4]*/,
  * 4 = always use the dense eigen solver, 8 = experimental: issue the tensor-pass launches of a
  * step on two streams (they only meet in commutative atomics) so that wave tails overlap. */
 int snprel_debug_flags(snprel_ctx *ctx, uint32_t flags);
+
+/* ---- several GPUs of one box behind one handle (single host process) --------------------
+ * What an R session needs to spread gnrGRM / gnrPCA / gnrIBSNum / gnrIBD_KING_Robust ... over the
+ * eight B200s of a box (north star: "partition across the 8 GPUs by SNP block, each GPU
+ * accumulating a partial N x N matrix with one all-reduce over NVLink at the end"): device r owns
+ * the r-th contiguous SNP range (what CGenoReadBySNP hands out block by block,
+ * src/dGenGWAS.cpp:1218-1397, is routed by SNP index), every device accumulates its partial planes
+ * on its own host thread with one agreed fixed-point format, and a hand-written peer-memory
+ * reduction over NVLink (reduce-scatter by peer loads, then the finishing device pulls the
+ * reduced slices; upper-triangle columns only) leaves the global accumulators on device `root`.
+ * The finishing calls of this header (snprel_grm, snprel_pca, snprel_ibs_num, snprel_king_robust,
+ * snprel_indiv_beta, ...) are then made on snprel_multi_ctx(m, root).  Per-SNP outputs (afreq of
+ * snprel_eigmix, snprel_snp_ratefreq) of a context cover that device's SNP range only; ranges are
+ * consecutive, in device order.  `devices` may repeat a GPU (tests on a one-GPU box). */
+typedef struct snprel_multi snprel_multi;
+int snprel_multi_create(const int *devices, int n_dev, snprel_multi **out);
+void snprel_multi_destroy(snprel_multi *m);
+const char *snprel_multi_last_error(snprel_multi *m);
+int snprel_multi_device_count(snprel_multi *m);
+snprel_ctx *snprel_multi_ctx(snprel_multi *m, int i);
+/* gnrSetGenoSpace + the block reader, routed: same meaning as the single-device calls */
+int snprel_multi_geno_begin(snprel_multi *m, int64_t n_samp, int64_t snp_capacity);
+int snprel_multi_geno_push_u8(snprel_multi *m, const uint8_t *geno, int64_t cnt);
+int snprel_multi_geno_push_2b(snprel_multi *m, const uint8_t *packed, int64_t cnt, int64_t row_bytes);
+int snprel_multi_geno_synth(snprel_multi *m, int64_t n_snp, uint64_t seed, double maf_lo, double maf_hi,
+                            double miss_rate, int64_t snp_start);
+int snprel_multi_set_row_window(snprel_multi *m, int64_t row0, int64_t rows);
+int snprel_multi_set_count_engine(snprel_multi *m, int engine);
+/* plan (all devices) -> merged format -> accumulate (all devices) -> peer reduction -> mark reduced.
+ * est: SNPREL_GRM_EIGENSTRAT / GCTA / CORR / EIGMIX or SNPREL_EST_IBS / KING_ROBUST / BETA.
+ * root: device index (position in `devices`) that receives the reduced N x N planes; -1: every device
+ * (an all-reduce).  The small per-sample buffers always go to every device. */
+int snprel_multi_accumulate(snprel_multi *m, int est, int bayesian, int root);
+/* duration (ms) and link traffic (bytes) of the last peer reduction */
+int snprel_multi_last_reduce(snprel_multi *m, double *ms, int64_t *bytes);
 
 #ifdef __cplusplus
 }

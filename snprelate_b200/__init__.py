@@ -10,7 +10,7 @@ behaviour; ``R/IBD.R``, ``R/PCA.R``, ``R/IBS.R``, ``R/Internal.R``) on top of th
 ABI through ctypes.  There is no CPU fallback: importing works anywhere, but
 every compute call raises ``SNPRelError`` without the CUDA library and a B200.
 """
-from ._lib import SNPRelError, Context, load_library, library_path  # noqa: F401
+from ._lib import SNPRelError, Context, MultiContext, load_library, library_path  # noqa: F401
 from .api import (  # noqa: F401
     GenotypeData,
     snpgdsGRM,
@@ -29,7 +29,7 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "SNPRelError", "Context", "load_library", "library_path", "GenotypeData",
+    "SNPRelError", "Context", "MultiContext", "load_library", "library_path", "GenotypeData",
     "snpgdsGRM", "snpgdsPCA", "snpgdsEIGMIX", "snpgdsPCACorr", "snpgdsPCASNPLoading", "snpgdsPCASampLoading", "snpgdsIBS", "snpgdsIBSNum", "snpgdsIBDMoM", "snpgdsMergeGRM",
     "snpgdsIBDKING", "snpgdsIndivBeta", "snpgdsSNPRateFreq",
 ]

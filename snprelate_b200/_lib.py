@@ -98,6 +98,16 @@ def load_library():
         "snprel_debug_flags": [p, u32],
         "snprel_set_count_engine": [p, i32],
         "snprel_set_rounding": [p, i32],
+        "snprel_multi_create": [p, i32, C.POINTER(p)],
+        "snprel_multi_geno_begin": [p, i64, i64],
+        "snprel_multi_geno_push_u8": [p, p, i64],
+        "snprel_multi_geno_push_2b": [p, p, i64, i64],
+        "snprel_multi_geno_synth": [p, i64, u64, dbl, dbl, dbl, i64],
+        "snprel_multi_set_row_window": [p, i64, i64],
+        "snprel_multi_set_count_engine": [p, i32],
+        "snprel_multi_accumulate": [p, i32, i32, i32],
+        "snprel_multi_last_reduce": [p, C.POINTER(dbl), C.POINTER(i64)],
+        "snprel_multi_device_count": [p],
         "snprel_last_eigen_info": [p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(dbl)],
     }
     for name, args in sig.items():
@@ -112,6 +122,14 @@ def load_library():
     lib.snprel_version.restype = C.c_char_p
     lib.snprel_kernel_launches.argtypes = [p]
     lib.snprel_kernel_launches.restype = i64
+    lib.snprel_device_count.argtypes = []
+    lib.snprel_device_count.restype = i32
+    lib.snprel_multi_destroy.argtypes = [p]
+    lib.snprel_multi_destroy.restype = None
+    lib.snprel_multi_last_error.argtypes = [p]
+    lib.snprel_multi_last_error.restype = C.c_char_p
+    lib.snprel_multi_ctx.argtypes = [p, i32]
+    lib.snprel_multi_ctx.restype = p
     _LIB = lib
     return lib
 
@@ -127,6 +145,9 @@ EXPORTED_SYMBOLS = [
     "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced", "snprel_last_plan", "snprel_set_row_window", "snprel_window_count", "snprel_mem_info",
     "snprel_kernel_launches", "snprel_last_hot_kernel", "snprel_time_accumulate", "snprel_time_finish", "snprel_last_step_ms", "snprel_invalidate",
     "snprel_table_gram", "snprel_debug_flags", "snprel_set_count_engine", "snprel_last_eigen_info", "snprel_set_rounding",
+    "snprel_device_count", "snprel_multi_create", "snprel_multi_destroy", "snprel_multi_last_error", "snprel_multi_device_count", "snprel_multi_ctx",
+    "snprel_multi_geno_begin", "snprel_multi_geno_push_u8", "snprel_multi_geno_push_2b", "snprel_multi_geno_synth",
+    "snprel_multi_set_row_window", "snprel_multi_set_count_engine", "snprel_multi_accumulate", "snprel_multi_last_reduce",
 ]
 
 
@@ -147,18 +168,23 @@ class Context:
     """One CUDA device + one genotype workspace (the reference's process-global
     MCWorkingGeno, src/dGenGWAS.cpp:2000)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _borrowed=None):
         self.lib = load_library()
+        self.device = device
+        self._owned = _borrowed is None
+        if _borrowed is not None:      # a context that belongs to a MultiContext
+            self.h = C.c_void_p(_borrowed)
+            return
         h = C.c_void_p()
         rc = self.lib.snprel_create(C.byref(h), int(device))
         if rc != 0:
             raise SNPRelError(self.lib.snprel_last_error(None).decode())
         self.h = h
-        self.device = device
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.snprel_destroy(self.h)
+            if self._owned:
+                self.lib.snprel_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -597,3 +623,79 @@ class Context:
 
     def debug_flags(self, flags):
         self._ck(self.lib.snprel_debug_flags(self.h, int(flags)))
+
+
+class MultiContext:
+    """Several GPUs of one box behind one handle, one host process (snprel_multi_*, csrc/multi.cu):
+    SNP-block sharding, per-device accumulation on library threads, peer-memory reduction over
+    NVLink.  After accumulate() the finishing calls are made on `ctx(root)`.  `devices` may repeat
+    a GPU (the whole path then runs on one device)."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        if self.lib.snprel_multi_create(arr, len(self.devices), C.byref(h)) != 0:
+            raise SNPRelError(self.lib.snprel_multi_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.snprel_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SNPRelError(self.lib.snprel_multi_last_error(self.h).decode())
+
+    def ctx(self, i=0) -> Context:
+        p = self.lib.snprel_multi_ctx(self.h, int(i))
+        if not p:
+            raise SNPRelError("MultiContext.ctx: device index out of range")
+        return Context(self.devices[i], _borrowed=p)
+
+    def geno_begin(self, n_samp, snp_capacity):
+        self._ck(self.lib.snprel_multi_geno_begin(self.h, int(n_samp), int(snp_capacity)))
+
+    def geno_push_u8(self, block):
+        block = np.ascontiguousarray(block, dtype=np.uint8)
+        self._ck(self.lib.snprel_multi_geno_push_u8(self.h, _ptr(block), block.shape[0]))
+
+    def geno_push_2b(self, packed):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        self._ck(self.lib.snprel_multi_geno_push_2b(self.h, _ptr(packed), packed.shape[0], packed.shape[1]))
+
+    def geno_synth(self, n_snp, seed=20261017, maf_lo=0.05, maf_hi=0.5, miss_rate=0.005, snp_start=0):
+        self._ck(self.lib.snprel_multi_geno_synth(self.h, int(n_snp), int(seed), float(maf_lo), float(maf_hi),
+                                                  float(miss_rate), int(snp_start)))
+
+    def set_row_window(self, row0=0, rows=0):
+        self._ck(self.lib.snprel_multi_set_row_window(self.h, int(row0), int(rows)))
+
+    def set_count_engine(self, engine):
+        code = {"bits": 0, "tensor": 1}.get(engine, engine)
+        self._ck(self.lib.snprel_multi_set_count_engine(self.h, int(code)))
+
+    def accumulate(self, est, bayesian=False, root=0):
+        """est: a GRM method name, or EST_IBS / EST_KING_ROBUST / EST_BETA.  root = -1: all-reduce."""
+        if isinstance(est, str):
+            est = GRM_METHODS[est]
+        self._ck(self.lib.snprel_multi_accumulate(self.h, int(est), int(bool(bayesian)), int(root)))
+
+    def last_reduce(self):
+        ms, b = C.c_double(), C.c_int64()
+        self._ck(self.lib.snprel_multi_last_reduce(self.h, C.byref(ms), C.byref(b)))
+        return ms.value, b.value

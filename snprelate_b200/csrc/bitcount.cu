@@ -227,7 +227,8 @@ static void finish_accumulate(snprel_ctx *c, int est) {
     c->accum_est = est;
     c->accum_reduced = false;
     c->reduce_list.clear();
-    c->reduce_list.push_back({c->cnt.p, (int64_t)c->cnt.n, 1});
+    c->reduce_list.push_back({c->cnt.p, (int64_t)c->cnt_planes * row_window(c).rows * c->n_samp_pad, 1, c->n_samp_pad,
+                              row_window(c).rows, row_window(c).r0});
 }
 
 void bitcount_accumulate(snprel_ctx *c, int est) {

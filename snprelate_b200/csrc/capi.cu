@@ -30,7 +30,12 @@ static std::string g_create_error;
 
 extern "C" {
 
-const char *snprel_version(void) { return "snprel_b200 0.1 (sm_100a)"; }
+const char *snprel_version(void) { return "snprel_b200 0.2 (sm_100a)"; }
+
+int snprel_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 
 int snprel_create(snprel_ctx **out, int device) {
     if (!out) {

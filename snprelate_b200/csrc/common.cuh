@@ -103,6 +103,10 @@ struct ReduceBuf {
     void *ptr;
     int64_t count;
     int kind;   // 0 int64, 1 uint32, 2 float64
+    // ld > 0: the buffer is a stack of [rows][ld] planes of the row window starting at row0, and only
+    // the columns >= (row0 + r) rounded down to 256 of row r are live (upper triangle, 256-tiles): an
+    // in-library reduction (multi.cu) skips the dead half; a plain sum over `count` stays correct
+    int64_t ld = 0, rows = 0, row0 = 0;
 };
 
 

@@ -881,7 +881,7 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     c->accum_est = est;
     c->accum_reduced = false;
     c->reduce_list.clear();
-    c->reduce_list.push_back({c->acc.p, (int64_t)c->acc.n, 0});
+    c->reduce_list.push_back({c->acc.p, (int64_t)nplanes * row_window(c).rows * npad, 0, npad, row_window(c).rows, row_window(c).r0});
     if (!pc.reduced) {   // (kept from an earlier window: already summed over the ranks)
         c->reduce_list.push_back({c->samp_sum.p, (int64_t)c->samp_sum.n, 0});
         c->reduce_list.push_back({c->scalars.p, (int64_t)c->scalars.n, 2});

@@ -1,0 +1,395 @@
+// Several GPUs of one box behind ONE handle and ONE host process: what an R
+// session needs to use all eight B200s through the .Call entry points (r_shim.cpp).
+//
+//   * SNP-block sharding: device r owns the r-th contiguous SNP range; pushes are routed by SNP index.
+//   * accumulate: every device plans and accumulates its shard on its own host thread (the library's
+//     calls block on their stream), with ONE fixed-point format agreed from the merged plan statistics
+//     -- the same algebra as snprelate_b200/dist.py (reduce_plan / accumulate_sharded), no process group.
+//   * reduction over NVLink / NVSwitch peer memory, hand written (no NCCL in this path): every device
+//     sums ITS row slice of every partial plane straight out of its peers' HBM (reduce-scatter by
+//     peer loads), then the devices that finish the result pull the reduced slices (all devices for
+//     the small per-sample buffers).  Only the live upper-triangle columns of the N x N planes cross
+//     the links.  Partials are exact integers, so the sum is bit-identical for any device count.
+//   * finishing calls (snprel_grm, snprel_pca, snprel_ibs_num, ...) then run on the root device's
+//     context, which holds the global accumulators (snprel_multi_ctx).
+// Two entries of `devices` may name the same GPU (tests on a one-GPU box run the whole path that way).
+#include <thread>
+
+#include "common.cuh"
+
+using namespace snprel;
+
+struct snprel_multi {
+    std::vector<snprel_ctx *> ctx;
+    std::vector<int> dev;
+    int64_t n_samp = 0, cap = 0, per_dev = 0, pos = 0;
+    int active = 0;          // devices that own a non-empty SNP range
+    std::string err;
+    double reduce_ms = 0;    // last peer reduction (CUDA events on the root's stream + host barrier)
+    int64_t reduce_bytes = 0;   // bytes that crossed the links in it
+};
+
+namespace {
+
+constexpr int MAX_DEV = 16;
+
+template <class T>
+struct PeerSrc {
+    const T *p[MAX_DEV];
+    int n;
+};
+
+// dst[idx] (+)= sum_k src.p[k][idx] over rows [ra, rb) of every plane; live columns only
+template <class T, bool ASSIGN>
+__global__ void __launch_bounds__(256)
+peer_reduce_kernel(T *__restrict__ dst, const PeerSrc<T> src, int64_t count, int64_t ld, int64_t rows, int64_t row0,
+                   int tri, int64_t ra, int64_t rb, int planes) {
+    const int64_t r = ra + blockIdx.x;
+    if (r >= rb) return;
+    const int64_t c0 = tri ? ((row0 + r) & ~255ll) : 0;
+    for (int p = blockIdx.y; p < planes; p += gridDim.y) {
+        const int64_t base = ((int64_t)p * rows + r) * ld;
+        for (int64_t c = c0 + threadIdx.x; c < ld; c += blockDim.x) {
+            const int64_t idx = base + c;
+            if (idx >= count) break;
+            T v = ASSIGN ? T(0) : dst[idx];
+#pragma unroll 4
+            for (int k = 0; k < src.n; k++) v += src.p[k][idx];
+            dst[idx] = v;
+        }
+    }
+}
+
+struct Shape {
+    int64_t ld, rows, row0;
+    int planes, tri;
+};
+// a dense buffer is walked as rows of 4096 elements
+Shape shape_of(const ReduceBuf &b) {
+    if (b.ld > 0 && b.rows > 0) return Shape{b.ld, b.rows, b.row0, (int)(b.count / (b.ld * b.rows)), 1};
+    const int64_t ld = 4096;
+    return Shape{ld, (b.count + ld - 1) / ld, 0, 1, 0};
+}
+int64_t live_elems(const Shape &s, int64_t ra, int64_t rb) {
+    int64_t t = 0;
+    for (int64_t r = ra; r < rb; r++) t += s.ld - (s.tri ? ((s.row0 + r) & ~255ll) : 0);
+    return t * s.planes;
+}
+
+template <class T>
+void launch(bool assign, cudaStream_t st, void *dst, const std::vector<const void *> &srcs, const ReduceBuf &b,
+            const Shape &s, int64_t ra, int64_t rb) {
+    if (rb <= ra || srcs.empty()) return;
+    PeerSrc<T> ps;
+    ps.n = (int)srcs.size();
+    for (int k = 0; k < ps.n; k++) ps.p[k] = static_cast<const T *>(srcs[k]);
+    dim3 grid((unsigned)(rb - ra), (unsigned)std::min(s.planes, 8));
+    if (assign)
+        peer_reduce_kernel<T, true><<<grid, 256, 0, st>>>(static_cast<T *>(dst), ps, b.count, s.ld, s.rows, s.row0, s.tri, ra, rb, s.planes);
+    else
+        peer_reduce_kernel<T, false><<<grid, 256, 0, st>>>(static_cast<T *>(dst), ps, b.count, s.ld, s.rows, s.row0, s.tri, ra, rb, s.planes);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) fail("peer_reduce_kernel: %s", cudaGetErrorString(e));
+}
+void launch_kind(int kind, bool assign, cudaStream_t st, void *dst, const std::vector<const void *> &srcs,
+                 const ReduceBuf &b, const Shape &s, int64_t ra, int64_t rb) {
+    if (kind == 0) launch<long long>(assign, st, dst, srcs, b, s, ra, rb);
+    else if (kind == 1) launch<unsigned int>(assign, st, dst, srcs, b, s, ra, rb);
+    else launch<double>(assign, st, dst, srcs, b, s, ra, rb);
+}
+
+void set_dev(int d) {
+    cudaError_t e = cudaSetDevice(d);
+    if (e != cudaSuccess) fail("cudaSetDevice(%d): %s", d, cudaGetErrorString(e));
+}
+void sync_all(snprel_multi *m) {
+    for (int i = 0; i < m->active; i++) {
+        set_dev(m->dev[i]);
+        CUDA_CHECK(cudaStreamSynchronize(m->ctx[i]->stream));
+    }
+}
+
+// run fn(i) for every active device on its own host thread; the first error wins
+template <class F>
+void on_each(snprel_multi *m, F fn) {
+    std::vector<std::string> errs((size_t)m->active);
+    std::vector<std::thread> th;
+    for (int i = 0; i < m->active; i++)
+        th.emplace_back([&, i]() {
+            try {
+                fn(i);
+            } catch (const Error &e) {
+                errs[i] = e.msg.empty() ? "error" : e.msg;
+            } catch (const std::exception &e) {
+                errs[i] = e.what();
+            }
+        });
+    for (auto &t : th) t.join();
+    for (int i = 0; i < m->active; i++)
+        if (!errs[i].empty()) fail("device %d: %s", m->dev[i], errs[i].c_str());
+}
+void ck(snprel_multi *m, int i, int rc) {
+    if (rc != 0) fail("%s", snprel_last_error(m->ctx[i]));
+}
+
+// in-place sum of reduce buffer k of every active context; the result lands on device `root`
+// (root < 0: on every device).  Small buffers always go everywhere: each device's later epilogues need them.
+void peer_reduce(snprel_multi *m, int root) {
+    const int nd = m->active;
+    if (nd <= 1) return;
+    const size_t nb = m->ctx[0]->reduce_list.size();
+    for (int i = 1; i < nd; i++)
+        if (m->ctx[i]->reduce_list.size() != nb) fail("internal: the devices disagree on the reduce buffers");
+    cudaEvent_t e0, e1;
+    set_dev(m->dev[0]);
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    CUDA_CHECK(cudaEventRecord(e0, m->ctx[0]->stream));
+    m->reduce_bytes = 0;
+    // phase 1: device d sums row slice d of every buffer out of its peers' memory
+    std::vector<Shape> shapes(nb);
+    for (size_t k = 0; k < nb; k++) {
+        const ReduceBuf &b0 = m->ctx[0]->reduce_list[k];
+        for (int i = 1; i < nd; i++)
+            if (m->ctx[i]->reduce_list[k].count != b0.count || m->ctx[i]->reduce_list[k].kind != b0.kind)
+                fail("internal: reduce buffer %d differs between devices", (int)k);
+        shapes[k] = shape_of(b0);
+    }
+    const int esz[3] = {8, 4, 8};
+    for (int d = 0; d < nd; d++) {
+        set_dev(m->dev[d]);
+        for (size_t k = 0; k < nb; k++) {
+            const ReduceBuf &b = m->ctx[d]->reduce_list[k];
+            if (b.count <= 0) continue;
+            const Shape &s = shapes[k];
+            const int64_t ra = s.rows * d / nd, rb = s.rows * (d + 1) / nd;
+            std::vector<const void *> srcs;
+            for (int p = 0; p < nd; p++)
+                if (p != d) srcs.push_back(m->ctx[p]->reduce_list[k].ptr);
+            launch_kind(b.kind, false, m->ctx[d]->stream, b.ptr, srcs, b, s, ra, rb);
+            m->reduce_bytes += live_elems(s, ra, rb) * esz[b.kind] * (nd - 1);
+        }
+    }
+    sync_all(m);
+    // phase 2: the finishing device(s) pull the reduced slices of the others
+    for (int t = 0; t < nd; t++) {
+        set_dev(m->dev[t]);
+        for (size_t k = 0; k < nb; k++) {
+            const ReduceBuf &b = m->ctx[t]->reduce_list[k];
+            if (b.count <= 0) continue;
+            const bool everywhere = root < 0 || b.count <= (1 << 22);
+            if (!everywhere && t != root) continue;
+            const Shape &s = shapes[k];
+            for (int d = 0; d < nd; d++) {
+                if (d == t) continue;
+                const int64_t ra = s.rows * d / nd, rb = s.rows * (d + 1) / nd;
+                std::vector<const void *> srcs{m->ctx[d]->reduce_list[k].ptr};
+                launch_kind(b.kind, true, m->ctx[t]->stream, b.ptr, srcs, b, s, ra, rb);
+                m->reduce_bytes += live_elems(s, ra, rb) * esz[b.kind];
+            }
+        }
+    }
+    sync_all(m);
+    set_dev(m->dev[0]);
+    CUDA_CHECK(cudaEventRecord(e1, m->ctx[0]->stream));
+    CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    m->reduce_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+}
+
+// route `cnt` SNP rows starting at global position m->pos to their owners
+template <class F>
+void route(snprel_multi *m, int64_t cnt, const char *who, F push) {
+    if (m->n_samp <= 0) fail("%s: call snprel_multi_geno_begin first", who);
+    if (cnt < 0 || m->pos + cnt > m->cap) fail("%s: more SNPs than the capacity given to snprel_multi_geno_begin", who);
+    int64_t done = 0;
+    while (done < cnt) {
+        const int64_t g = m->pos + done;
+        const int i = (int)(g / m->per_dev);
+        const int64_t take = std::min(cnt - done, (int64_t)(i + 1) * m->per_dev - g);
+        push(i, done, take);
+        done += take;
+    }
+    m->pos += cnt;
+}
+
+}  // namespace
+
+#define MULTI_BEGIN(m)   \
+    if (!(m)) return 1;  \
+    try {
+#define MULTI_END(m)                 \
+    return 0;                        \
+    }                                \
+    catch (const Error &e) {         \
+        (m)->err = e.msg;            \
+        return 1;                    \
+    }                                \
+    catch (const std::exception &e) {\
+        (m)->err = e.what();         \
+        return 2;                    \
+    }
+
+static std::string g_multi_create_error;
+
+extern "C" {
+
+int snprel_multi_create(const int *devices, int n_dev, snprel_multi **out) {
+    if (!out || !devices || n_dev <= 0 || n_dev > MAX_DEV) {
+        g_multi_create_error = "snprel_multi_create: bad arguments (1..16 devices)";
+        return 1;
+    }
+    *out = nullptr;
+    snprel_multi *m = new snprel_multi();
+    for (int i = 0; i < n_dev; i++) {
+        snprel_ctx *c = nullptr;
+        if (snprel_create(&c, devices[i]) != 0) {
+            g_multi_create_error = snprel_last_error(nullptr);
+            for (auto *x : m->ctx) snprel_destroy(x);
+            delete m;
+            return 1;
+        }
+        m->ctx.push_back(c);
+        m->dev.push_back(devices[i]);
+    }
+    // peer access between every pair of distinct devices: the reduction reads peers' HBM directly
+    for (int i = 0; i < n_dev; i++)
+        for (int j = 0; j < n_dev; j++) {
+            if (devices[i] == devices[j]) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
+            cudaSetDevice(devices[i]);
+            cudaError_t e = can ? cudaDeviceEnablePeerAccess(devices[j], 0) : cudaErrorPeerAccessUnsupported;
+            if (e == cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();
+                e = cudaSuccess;
+            }
+            if (e != cudaSuccess) {
+                g_multi_create_error = "snprel_multi_create: no peer access from device " + std::to_string(devices[i]) +
+                                       " to device " + std::to_string(devices[j]) + " (" + cudaGetErrorString(e) + ")";
+                for (auto *x : m->ctx) snprel_destroy(x);
+                delete m;
+                return 1;
+            }
+        }
+    m->active = n_dev;
+    *out = m;
+    return 0;
+}
+
+void snprel_multi_destroy(snprel_multi *m) {
+    if (!m) return;
+    for (auto *c : m->ctx) snprel_destroy(c);
+    delete m;
+}
+
+const char *snprel_multi_last_error(snprel_multi *m) { return m ? m->err.c_str() : g_multi_create_error.c_str(); }
+
+int snprel_multi_device_count(snprel_multi *m) { return m ? (int)m->ctx.size() : 0; }
+
+snprel_ctx *snprel_multi_ctx(snprel_multi *m, int i) {
+    return (m && i >= 0 && i < (int)m->ctx.size()) ? m->ctx[i] : nullptr;
+}
+
+int snprel_multi_geno_begin(snprel_multi *m, int64_t n_samp, int64_t snp_capacity) {
+    MULTI_BEGIN(m)
+    if (snp_capacity < 0) fail("snprel_multi_geno_begin: negative SNP capacity");
+    const int nd = (int)m->ctx.size();
+    // contiguous SNP ranges, boundaries at multiples of the kernels' 128-SNP stage; never more
+    // devices than 128-SNP blocks
+    const int64_t blocks = std::max<int64_t>(1, (snp_capacity + SNP_PAD - 1) / SNP_PAD);
+    m->active = (int)std::min<int64_t>(nd, blocks);
+    m->per_dev = (blocks + m->active - 1) / m->active * SNP_PAD;
+    m->active = (int)std::min<int64_t>(m->active, (std::max<int64_t>(snp_capacity, 1) + m->per_dev - 1) / m->per_dev);
+    m->n_samp = n_samp;
+    m->cap = snp_capacity;
+    m->pos = 0;
+    for (int i = 0; i < m->active; i++) {
+        const int64_t lo = i * m->per_dev, hi = std::min(snp_capacity, lo + m->per_dev);
+        ck(m, i, snprel_geno_begin(m->ctx[i], n_samp, std::max<int64_t>(hi - lo, 0)));
+    }
+    MULTI_END(m)
+}
+
+int snprel_multi_geno_push_u8(snprel_multi *m, const uint8_t *geno, int64_t cnt) {
+    MULTI_BEGIN(m)
+    route(m, cnt, "snprel_multi_geno_push_u8", [&](int i, int64_t off, int64_t take) {
+        ck(m, i, snprel_geno_push_u8(m->ctx[i], geno + off * m->n_samp, take));
+    });
+    MULTI_END(m)
+}
+
+int snprel_multi_geno_push_2b(snprel_multi *m, const uint8_t *packed, int64_t cnt, int64_t row_bytes) {
+    MULTI_BEGIN(m)
+    route(m, cnt, "snprel_multi_geno_push_2b", [&](int i, int64_t off, int64_t take) {
+        ck(m, i, snprel_geno_push_2b(m->ctx[i], packed + off * row_bytes, take, row_bytes));
+    });
+    MULTI_END(m)
+}
+
+int snprel_multi_geno_synth(snprel_multi *m, int64_t n_snp, uint64_t seed, double maf_lo, double maf_hi, double miss_rate,
+                            int64_t snp_start) {
+    MULTI_BEGIN(m)
+    route(m, n_snp, "snprel_multi_geno_synth", [&](int i, int64_t off, int64_t take) {
+        ck(m, i, snprel_geno_synth(m->ctx[i], take, seed, maf_lo, maf_hi, miss_rate, snp_start + (m->pos + off)));
+    });
+    MULTI_END(m)
+}
+
+int snprel_multi_set_row_window(snprel_multi *m, int64_t row0, int64_t rows) {
+    MULTI_BEGIN(m)
+    for (int i = 0; i < m->active; i++) ck(m, i, snprel_set_row_window(m->ctx[i], row0, rows));
+    MULTI_END(m)
+}
+
+int snprel_multi_set_count_engine(snprel_multi *m, int engine) {
+    MULTI_BEGIN(m)
+    for (size_t i = 0; i < m->ctx.size(); i++) ck(m, (int)i, snprel_set_count_engine(m->ctx[i], engine));
+    MULTI_END(m)
+}
+
+int snprel_multi_accumulate(snprel_multi *m, int est, int bayesian, int root) {
+    MULTI_BEGIN(m)
+    const int nd = m->active;
+    if (m->n_samp <= 0) fail("snprel_multi_accumulate: no genotype workspace");
+    if (root >= nd) root = 0;      // (fewer active devices than asked for: tiny data sets)
+    const bool cov = est >= SNPREL_GRM_EIGENSTRAT && est <= SNPREL_GRM_EIGMIX;
+    if (!cov && est != SNPREL_EST_IBS && est != SNPREL_EST_KING_ROBUST && est != SNPREL_EST_BETA)
+        fail("snprel_multi_accumulate: unsupported estimator %d", est);
+    std::vector<snprel_plan> plans((size_t)nd);
+    for (auto &p : plans) {
+        p = snprel_plan{};
+        p.frac_bits = p.frac_bits_w = p.frac_bits_d = -1;
+        p.bayesian = bayesian;
+    }
+    on_each(m, [&](int i) { ck(m, i, snprel_plan_local(m->ctx[i], est, &plans[i])); });
+    // one fixed-point format for every device: max of the table ranges, sums of the rest (sums are
+    // conservative for the per-sample maxima); snprelate_b200/dist.py:reduce_plan
+    snprel_plan g = plans[0];
+    for (int i = 1; i < nd; i++) {
+        g.max_abs = std::max(g.max_abs, plans[i].max_abs);
+        g.max_abs_w = std::max(g.max_abs_w, plans[i].max_abs_w);
+        g.sum_bound += plans[i].sum_bound;
+        g.err_weight += plans[i].err_weight;
+        g.scale += plans[i].scale;
+        g.total_missing += plans[i].total_missing;
+        g.max_missing += plans[i].max_missing;
+        g.n_snp += plans[i].n_snp;
+    }
+    on_each(m, [&](int i) { ck(m, i, snprel_accumulate(m->ctx[i], est, &g)); });
+    peer_reduce(m, root);
+    for (int i = 0; i < nd; i++) ck(m, i, snprel_mark_reduced(m->ctx[i]));
+    MULTI_END(m)
+}
+
+int snprel_multi_last_reduce(snprel_multi *m, double *ms, int64_t *bytes) {
+    MULTI_BEGIN(m)
+    if (ms) *ms = m->reduce_ms;
+    if (bytes) *bytes = m->reduce_bytes;
+    MULTI_END(m)
+}
+
+}  // extern "C"

@@ -17,6 +17,8 @@
 // returns R objects of exactly the reference's shape.
 #if defined(SNPREL_BUILD_R_SHIM)
 
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "dGenGWAS.h"          // the reference's workspace (GWAS::MCWorkingGeno, SEXP helpers)
@@ -59,6 +61,77 @@ void load_workspace(Ctx &c) {
     }
 }
 
+// Several GPUs from one R process: SNPREL_DEVICES="0,1,2,3" (or "all") makes the N x N estimators
+// shard the selected SNPs over those devices (snprel_multi_*, csrc/multi.cu: per-device accumulation,
+// peer-memory reduction over NVLink onto the first device), and the routine then finishes on that
+// device's context exactly as in the single-device case.  Routines without a sharded form (PLINK
+// MoM, KING-homo, loadings, randomized PCA) keep using one device.
+snprel_multi *multi_handle() {
+    static snprel_multi *shared = nullptr;
+    static bool tried = false;
+    if (tried) return shared;
+    tried = true;
+    const char *env = getenv("SNPREL_DEVICES");
+    if (!env || !*env) return nullptr;
+    std::vector<int> dev;
+    if (!strcmp(env, "all")) {
+        const int n = snprel_device_count();
+        for (int i = 0; i < n; i++) dev.push_back(i);
+    } else {
+        for (const char *p = env; *p;) {
+            char *end = nullptr;
+            long v = strtol(p, &end, 10);
+            if (end == p) throw ErrCoreArray("SNPREL_DEVICES: expected a comma separated list of device indices or \"all\"");
+            dev.push_back((int)v);
+            p = (*end == ',') ? end + 1 : end;
+        }
+    }
+    if (dev.size() < 2) return nullptr;
+    if (snprel_multi_create(dev.data(), (int)dev.size(), &shared) != 0) {
+        shared = nullptr;
+        throw ErrCoreArray("%s", snprel_multi_last_error(nullptr));
+    }
+    return shared;
+}
+
+// load the selected genotypes for estimator `est`; with several devices also accumulate + reduce, after
+// which c.h is the context that holds the global accumulators
+void load_for(Ctx &c, int est, bool bayesian = false) {
+    snprel_multi *m = multi_handle();
+    if (!m) {
+        load_workspace(c);
+        return;
+    }
+    CdBaseWorkSpace &sp = MCWorkingGeno.Space();
+    const int n = sp.SampleNum(), msnp = sp.SNPNum();
+    auto mck = [&](int rc) { if (rc != 0) throw ErrCoreArray("%s", snprel_multi_last_error(m)); };
+    mck(snprel_multi_geno_begin(m, n, msnp));
+    const int block = std::max(1, (64 << 20) / std::max(n, 1));
+    std::vector<C_UInt8> buf((size_t)block * n);
+    for (int st = 0; st < msnp; st += block) {
+        int cnt = std::min(block, msnp - st);
+        sp.snpRead(st, cnt, &buf[0], RDim_Sample_X_SNP);
+        mck(snprel_multi_geno_push_u8(m, &buf[0], cnt));
+    }
+    mck(snprel_multi_accumulate(m, est, bayesian ? 1 : 0, 0));
+    c.h = snprel_multi_ctx(m, 0);
+}
+
+// allele frequencies of ALL selected SNPs in multi-device mode (each context holds its own range)
+void gather_afreq(double *af) {
+    snprel_multi *m = multi_handle();
+    int64_t off = 0;
+    for (int i = 0; i < snprel_multi_device_count(m); i++) {
+        snprel_ctx *h = snprel_multi_ctx(m, i);
+        int64_t ns = 0, ms = 0;
+        if (snprel_geno_dim(h, &ns, &ms) != 0 || ms <= 0) continue;
+        if (snprel_snp_ratefreq(h, af + off, NULL, NULL) != 0) throw ErrCoreArray("%s", snprel_last_error(h));
+        for (int64_t l = 0; l < ms; l++)
+            if (!(af[off + l] == af[off + l])) af[off + l] = 0.0;      // no valid genotype: avg_geno = 0 (src/genEIGMIX.cpp:116-118)
+        off += ms;
+    }
+}
+
 SEXP sym_result(size_t n, bool packed) {
     return packed ? NEW_NUMERIC(n * (n + 1) / 2) : Rf_allocMatrix(REALSXP, n, n);
 }
@@ -80,7 +153,7 @@ COREARRAY_DLL_EXPORT SEXP gnrGRM(SEXP NumThread, SEXP Method, SEXP GDS, SEXP use
                    : !strcmp(mt, "IndivBeta") ? SNPREL_GRM_INDIVBETA : -1;
         if (method < 0) throw ErrCoreArray("Invalid 'method'!");
         Ctx c;
-        load_workspace(c);
+        load_for(c, method == SNPREL_GRM_INDIVBETA ? SNPREL_EST_BETA : method);
         const size_t n = MCWorkingGeno.Space().SampleNum();
         const bool packed = (Rf_asLogical(useMatrix) == TRUE) && method != SNPREL_GRM_CORR;
         rv_ans = PROTECT(sym_result(n, packed));
@@ -94,9 +167,9 @@ COREARRAY_DLL_EXPORT SEXP gnrPCA(SEXP EigenCnt, SEXP Algorithm, SEXP NumThread, 
         const char *alg = CHAR(STRING_ELT(Algorithm, 0));
         if (strcmp(alg, "exact") != 0 && strcmp(alg, "randomized") != 0) throw "Invalid 'algorithm'.";
         Ctx c;
-        load_workspace(c);
         const int n = MCWorkingGeno.Space().SampleNum();
         if (strcmp(alg, "randomized") == 0) {
+            load_workspace(c);
             // src/genPCA.cpp:1436-1442, :781-793: list(sigma[n], V^T [hsize x n], 2 TraceXTX)
             const int aux_dim = Rf_asInteger(RGetListElement(ParamList, "aux.dim"));
             const int iter_num = Rf_asInteger(RGetListElement(ParamList, "iter.num"));
@@ -121,6 +194,7 @@ COREARRAY_DLL_EXPORT SEXP gnrPCA(SEXP EigenCnt, SEXP Algorithm, SEXP NumThread, 
         const bool bayes = Rf_asLogical(RGetListElement(ParamList, "bayesian")) == TRUE;
         const bool need = Rf_asLogical(RGetListElement(ParamList, "need.genmat")) == TRUE;
         const bool only = Rf_asLogical(RGetListElement(ParamList, "genmat.only")) == TRUE;
+        load_for(c, SNPREL_GRM_EIGENSTRAT, bayes);
         PROTECT(rv_ans = NEW_LIST(5));
         SEXP genmat = R_NilValue, eval = R_NilValue, evec = R_NilValue;
         if (need) { genmat = PROTECT(Rf_allocMatrix(REALSXP, n, n)); SET_ELEMENT(rv_ans, 1, genmat); UNPROTECT(1); }
@@ -144,7 +218,7 @@ COREARRAY_DLL_EXPORT SEXP gnrEigMix(SEXP EigenCnt, SEXP NumThread, SEXP ParamLis
     if (need_ibd == NA_LOGICAL) Rf_error("'ibdmat' must be TRUE or FALSE.");
     COREARRAY_TRY
         Ctx c;
-        load_workspace(c);
+        load_for(c, SNPREL_GRM_EIGMIX);
         const int n = MCWorkingGeno.Space().SampleNum();
         int nEig = Rf_asInteger(EigenCnt);
         if (nEig < 0 || nEig > n) nEig = n;
@@ -156,8 +230,9 @@ COREARRAY_DLL_EXPORT SEXP gnrEigMix(SEXP EigenCnt, SEXP NumThread, SEXP ParamLis
             eval = PROTECT(NEW_NUMERIC(n)); SET_ELEMENT(rv_ans, 0, eval); UNPROTECT(1);
             evec = PROTECT(Rf_allocMatrix(REALSXP, n, nEig)); SET_ELEMENT(rv_ans, 1, evec); UNPROTECT(1);
         }
-        c.ck(snprel_eigmix(c.h, nEig, diag_adj == TRUE, need_ibd ? REAL(ibd) : NULL, REAL(af),
+        c.ck(snprel_eigmix(c.h, nEig, diag_adj == TRUE, need_ibd ? REAL(ibd) : NULL, multi_handle() ? NULL : REAL(af),
                            nEig > 0 ? REAL(eval) : NULL, nEig > 0 ? REAL(evec) : NULL));
+        if (multi_handle()) gather_afreq(REAL(af));
         UNPROTECT(1);
     COREARRAY_CATCH
 }
@@ -165,7 +240,7 @@ COREARRAY_DLL_EXPORT SEXP gnrEigMix(SEXP EigenCnt, SEXP NumThread, SEXP ParamLis
 COREARRAY_DLL_EXPORT SEXP gnrIBSAve(SEXP NumThread, SEXP useMatrix, SEXP Verbose) {
     COREARRAY_TRY
         Ctx c;
-        load_workspace(c);
+        load_for(c, SNPREL_EST_IBS);
         const size_t n = MCWorkingGeno.Space().SampleNum();
         const bool packed = Rf_asLogical(useMatrix) == TRUE;
         rv_ans = PROTECT(sym_result(n, packed));
@@ -197,7 +272,7 @@ COREARRAY_DLL_EXPORT SEXP gnrIBD_PLINK(SEXP NumThread, SEXP AlleleFreq, SEXP Use
 COREARRAY_DLL_EXPORT SEXP gnrIBSNum(SEXP NumThread, SEXP Verbose) {
     COREARRAY_TRY
         Ctx c;
-        load_workspace(c);
+        load_for(c, SNPREL_EST_IBS);
         const int n = MCWorkingGeno.Space().SampleNum();
         PROTECT(rv_ans = NEW_LIST(3));
         SEXP m[3];
@@ -210,7 +285,7 @@ COREARRAY_DLL_EXPORT SEXP gnrIBSNum(SEXP NumThread, SEXP Verbose) {
 COREARRAY_DLL_EXPORT SEXP gnrIBD_KING_Robust(SEXP FamilyID, SEXP NumThread, SEXP useMatrix, SEXP Verbose) {
     COREARRAY_TRY
         Ctx c;
-        load_workspace(c);
+        load_for(c, SNPREL_EST_KING_ROBUST);
         const size_t n = MCWorkingGeno.Space().SampleNum();
         const bool packed = Rf_asLogical(useMatrix) == TRUE;
         PROTECT(rv_ans = NEW_LIST(2));
@@ -241,7 +316,7 @@ COREARRAY_DLL_EXPORT SEXP gnrIBD_Beta(SEXP Inbreeding, SEXP NumThread, SEXP useM
     if (inbreeding == NA_LOGICAL) Rf_error("'inbreeding' must be TRUE or FALSE.");
     COREARRAY_TRY
         Ctx c;
-        load_workspace(c);
+        load_for(c, SNPREL_EST_BETA);
         const size_t n = MCWorkingGeno.Space().SampleNum();
         const bool packed = Rf_asLogical(useMatrix) == TRUE;
         rv_ans = PROTECT(sym_result(n, packed));
