@@ -73,6 +73,14 @@ int snprel_geno_push_2b(snprel_ctx *ctx, const uint8_t *packed, int64_t cnt,
  * i.e. first_snp * n_samp.  EXPERIMENTAL: written at the end of round 1, not yet run on a GPU. */
 int snprel_geno_push_bitstream(snprel_ctx *ctx, const uint8_t *stream,
                                int64_t first_genotype, int64_t cnt);
+/* SNP-sharded loading of a workspace that finally holds ALL SNPs (N x N output tiled across GPUs when
+ * N^2 exceeds one GPU's HBM): reserve the whole SNP range with snprel_geno_begin, _seek to
+ * this rank's first SNP, push its block (only that block crosses PCIe), receive the other ranks'
+ * blocks straight into the device rows (an NCCL all-gather / broadcast over NVLink on the pointer
+ * _device_rows returns, pitch row_bytes), then _commit the total row count. */
+int snprel_geno_seek(snprel_ctx *ctx, int64_t snp_index);
+int snprel_geno_device_rows(snprel_ctx *ctx, void **dev_ptr, int64_t *row_bytes, int64_t *capacity);
+int snprel_geno_commit(snprel_ctx *ctx, int64_t n_snp);
 /* Fill the workspace with `n_snp` synthetic SNPs on the device (counter-based
  * generator; SNP l uses global index snp_start+l so SNP shards of one data
  * set can be generated independently).  Benchmark / test input only. */
@@ -383,6 +391,19 @@ int snprel_multi_set_count_engine(snprel_multi *m, int engine);
 int snprel_multi_accumulate(snprel_multi *m, int est, int bayesian, int root);
 /* duration (ms) and link traffic (bytes) of the last peer reduction */
 int snprel_multi_last_reduce(snprel_multi *m, double *ms, int64_t *bytes);
+
+/* Tiled N x N output over several devices (N^2 exceeds one GPU's HBM): _begin_replicated reserves the
+ * WHOLE SNP range on every device but routes each pushed block to its owner only (1/n of the data per
+ * PCIe link); _geno_gather then completes every device's copy with peer copies over NVLink.
+ * _grm_tiled walks the upper triangle in row windows of `window_rows` (multiple of 256; 0 = chosen from
+ * the free memory), window w on device w mod n, each device accumulating its windows over all SNPs with
+ * no reduction, and hands the packed rows (CdMatTri order, the layout gnrGRM returns with useMatrix) to
+ * `sink` strictly in order: sink(user, first_packed_index, values, count) != 0 aborts.  Methods:
+ * SNPREL_GRM_EIGENSTRAT / GCTA / EIGMIX. */
+int snprel_multi_geno_begin_replicated(snprel_multi *m, int64_t n_samp, int64_t snp_capacity);
+int snprel_multi_geno_gather(snprel_multi *m);
+typedef int (*snprel_sink_fn)(void *user, int64_t first_packed_index, const double *values, int64_t count);
+int snprel_multi_grm_tiled(snprel_multi *m, int method, int64_t window_rows, snprel_sink_fn sink, void *user);
 
 #ifdef __cplusplus
 }

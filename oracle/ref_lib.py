@@ -80,6 +80,17 @@ class RefWorkspace:
         _ck(_lib().ref_grm(method.encode(), int(nthread), _p(out)))
         return out
 
+    def grm_gds(self, method="GCTA", nthread=1):
+        """gnrGRM with a GDS output node: the float64 stream appended to "grm" (n rows of n values,
+        grm_save_to_gds, src/genPCA.cpp:1571-1584) as an [n, n] array."""
+        n = self.dims()[1]
+        out = np.empty((n, n))
+        cnt = C.c_longlong()
+        _ck(_lib().ref_grm_gds(method.encode(), int(nthread), _p(out), C.byref(cnt)))
+        if cnt.value != n * n:
+            raise RuntimeError(f"GDS stream has {cnt.value} values, expected {n * n}")
+        return out
+
     def pca(self, nthread=1, bayesian=False, eigen_cnt=0):
         n = self.dims()[1]
         genmat = np.empty((n, n))

@@ -170,13 +170,28 @@ void GDS_Array_ReadData(PdAbstractArray obj, const C_Int32 *st, const C_Int32 *l
                         enum C_SVType sv) {
     GDS_Array_ReadDataEx(obj, st, len, nullptr, out, sv);
 }
-void GDS_Array_AppendData(PdAbstractArray, ssize_t, const void *, enum C_SVType) {
-    throw ErrCoreArray("shim: GDS output is not modelled");
+// GDS output model: ONE extendable float64 node ("grm" of a SNPRELATE_OUTPUT file, R/IBD.R:589-590);
+// appended values are kept in memory in arrival order so that a test can read the stream back
+static std::vector<double> g_gds_out;
+static int g_gds_out_node = 0;            // its address stands for the node
+void GDS_Array_AppendData(PdAbstractArray obj, ssize_t cnt, const void *in, enum C_SVType sv) {
+    if (obj != (PdAbstractArray)&g_gds_out_node) throw ErrCoreArray("shim: append to an unknown GDS node");
+    if (sv != svFloat64) throw ErrCoreArray("shim: only svFloat64 appends are modelled");
+    const double *p = (const double *)in;
+    g_gds_out.insert(g_gds_out.end(), p, p + cnt);
 }
 int GDS_Attr_Name2Index(PdGDSObj, const char *name) { return strcmp(name, "sample.order") == 0 ? 0 : -1; }
-PdGDSObj GDS_Node_Path(PdGDSFolder, const char *, C_BOOL) { throw ErrCoreArray("shim: no GDS file"); }
+static int g_gds_out_root = 0;
+PdGDSObj GDS_Node_Path(PdGDSFolder root, const char *path, C_BOOL) {
+    if (root == (PdGDSFolder)&g_gds_out_root && strcmp(path, "grm") == 0) return (PdGDSObj)&g_gds_out_node;
+    throw ErrCoreArray("shim: no GDS file");
+}
 PdGDSObj GDS_R_SEXP2Obj(SEXP, C_BOOL) { throw ErrCoreArray("shim: no GDS file"); }
-PdGDSFolder GDS_R_SEXP2FileRoot(SEXP) { throw ErrCoreArray("shim: no GDS file"); }
+static shim_sexp g_gds_out_file{VECSXP, 0, nullptr, nullptr, nullptr};     // stands for the R object of the output file
+PdGDSFolder GDS_R_SEXP2FileRoot(SEXP s) {
+    if (s == &g_gds_out_file) return (PdGDSFolder)&g_gds_out_root;
+    throw ErrCoreArray("shim: no GDS file");
+}
 void GDS_Iter_GetStart(PdAbstractArray, PdIterator) { throw ErrCoreArray("shim: iterators are not modelled"); }
 C_Float64 GDS_Iter_GetFloat(PdIterator) { throw ErrCoreArray("shim: iterators are not modelled"); }
 C_UInt64 GDS_Mach_GetCPULevelCache(int level) {
@@ -321,6 +336,15 @@ int ref_grm(const char *method, int nthread, double *out) {
     SEXP r = gnrGRM(Rf_ScalarInteger(nthread), Rf_mkString(method), R_NilValue, Rf_ScalarLogical(0),
                     Rf_ScalarLogical(0));
     copy_real(r, out);
+    REF_CATCH
+}
+// gnrGRM with a GDS output file (R/IBD.R:570-594): returns the stream appended to the "grm" node
+int ref_grm_gds(const char *method, int nthread, double *out, long long *count) {
+    REF_TRY
+    g_gds_out.clear();
+    gnrGRM(Rf_ScalarInteger(nthread), Rf_mkString(method), &g_gds_out_file, Rf_ScalarLogical(1), Rf_ScalarLogical(0));
+    if (count) *count = (long long)g_gds_out.size();
+    if (out) memcpy(out, g_gds_out.data(), g_gds_out.size() * sizeof(double));
     REF_CATCH
 }
 int ref_pca(int nthread, int bayesian, int eigen_cnt, double *genmat, double *trace_xtx, double *eigval,

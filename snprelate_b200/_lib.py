@@ -98,6 +98,12 @@ def load_library():
         "snprel_debug_flags": [p, u32],
         "snprel_set_count_engine": [p, i32],
         "snprel_set_rounding": [p, i32],
+        "snprel_geno_seek": [p, i64],
+        "snprel_geno_commit": [p, i64],
+        "snprel_geno_device_rows": [p, C.POINTER(p), C.POINTER(i64), C.POINTER(i64)],
+        "snprel_multi_geno_begin_replicated": [p, i64, i64],
+        "snprel_multi_geno_gather": [p],
+        "snprel_multi_grm_tiled": [p, i32, i64, p, p],
         "snprel_multi_create": [p, i32, C.POINTER(p)],
         "snprel_multi_geno_begin": [p, i64, i64],
         "snprel_multi_geno_push_u8": [p, p, i64],
@@ -148,6 +154,8 @@ EXPORTED_SYMBOLS = [
     "snprel_device_count", "snprel_multi_create", "snprel_multi_destroy", "snprel_multi_last_error", "snprel_multi_device_count", "snprel_multi_ctx",
     "snprel_multi_geno_begin", "snprel_multi_geno_push_u8", "snprel_multi_geno_push_2b", "snprel_multi_geno_synth",
     "snprel_multi_set_row_window", "snprel_multi_set_count_engine", "snprel_multi_accumulate", "snprel_multi_last_reduce",
+    "snprel_geno_seek", "snprel_geno_device_rows", "snprel_geno_commit",
+    "snprel_multi_geno_begin_replicated", "snprel_multi_geno_gather", "snprel_multi_grm_tiled",
 ]
 
 
@@ -224,6 +232,18 @@ class Context:
         if (int(first_snp) + int(cnt)) * n * 2 > stream.size * 8:
             raise SNPRelError("geno_push_bitstream: the stream is shorter than the requested SNP range")
         self._ck(self.lib.snprel_geno_push_bitstream(self.h, _ptr(stream), int(first_snp) * n, int(cnt)))
+
+    def geno_seek(self, snp_index):
+        self._ck(self.lib.snprel_geno_seek(self.h, int(snp_index)))
+
+    def geno_commit(self, n_snp):
+        self._ck(self.lib.snprel_geno_commit(self.h, int(n_snp)))
+
+    def geno_device_rows(self):
+        """(device pointer of SNP row 0, row pitch in bytes, reserved rows) of the 2-bit workspace."""
+        ptr, rb, cap = C.c_void_p(), C.c_int64(), C.c_int64()
+        self._ck(self.lib.snprel_geno_device_rows(self.h, C.byref(ptr), C.byref(rb), C.byref(cap)))
+        return ptr.value, rb.value, cap.value
 
     def geno_synth(self, n_snp, seed=20261017, maf_lo=0.05, maf_hi=0.5, miss_rate=0.005, snp_start=0):
         self._ck(self.lib.snprel_geno_synth(self.h, int(n_snp), int(seed), float(maf_lo), float(maf_hi),
@@ -665,7 +685,9 @@ class MultiContext:
         p = self.lib.snprel_multi_ctx(self.h, int(i))
         if not p:
             raise SNPRelError("MultiContext.ctx: device index out of range")
-        return Context(self.devices[i], _borrowed=p)
+        c = Context(self.devices[i], _borrowed=p)
+        c._win = getattr(self, "_win", False)
+        return c
 
     def geno_begin(self, n_samp, snp_capacity):
         self._ck(self.lib.snprel_multi_geno_begin(self.h, int(n_samp), int(snp_capacity)))
@@ -684,6 +706,7 @@ class MultiContext:
 
     def set_row_window(self, row0=0, rows=0):
         self._ck(self.lib.snprel_multi_set_row_window(self.h, int(row0), int(rows)))
+        self._win = rows > 0
 
     def set_count_engine(self, engine):
         code = {"bits": 0, "tensor": 1}.get(engine, engine)
@@ -694,6 +717,32 @@ class MultiContext:
         if isinstance(est, str):
             est = GRM_METHODS[est]
         self._ck(self.lib.snprel_multi_accumulate(self.h, int(est), int(bool(bayesian)), int(root)))
+
+    def geno_begin_replicated(self, n_samp, snp_capacity):
+        self._ck(self.lib.snprel_multi_geno_begin_replicated(self.h, int(n_samp), int(snp_capacity)))
+
+    def geno_gather(self):
+        self._ck(self.lib.snprel_multi_geno_gather(self.h))
+
+    def grm_tiled(self, method, window_rows=0, out=None):
+        """Packed upper triangle (CdMatTri order) of the GRM computed window by window, window w on device
+        w mod n.  `out`: float64 buffer of n (n + 1) / 2 values (allocated when None)."""
+        n, _ = self.ctx(0).geno_dim()
+        need = n * (n + 1) // 2
+        if out is None:
+            out = np.empty(need)
+        flat = out.reshape(-1)
+        calls = []
+        SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_int64)
+
+        def sink(_user, first, vals, count):
+            flat[first: first + count] = np.ctypeslib.as_array(vals, shape=(count,))
+            calls.append((first, count))
+            return 0
+        cb = SINK(sink)
+        self._ck(self.lib.snprel_multi_grm_tiled(self.h, GRM_METHODS[method], int(window_rows), C.cast(cb, C.c_void_p), None))
+        self.tiled_calls = calls
+        return out
 
     def last_reduce(self):
         ms, b = C.c_double(), C.c_int64()

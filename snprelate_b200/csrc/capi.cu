@@ -111,6 +111,22 @@ int snprel_geno_push_bitstream(snprel_ctx *c, const uint8_t *stream, int64_t fir
     API_BEGIN(c) geno_push_bitstream(c, stream, first_genotype, cnt);
     API_END(c)
 }
+int snprel_geno_seek(snprel_ctx *c, int64_t snp_index) {
+    API_BEGIN(c) geno_seek(c, snp_index);
+    API_END(c)
+}
+int snprel_geno_commit(snprel_ctx *c, int64_t n_snp) {
+    API_BEGIN(c) geno_commit(c, n_snp);
+    API_END(c)
+}
+int snprel_geno_device_rows(snprel_ctx *c, void **dev_ptr, int64_t *row_bytes, int64_t *capacity) {
+    API_BEGIN(c)
+    if (c->n_samp <= 0) fail("snprel_geno_device_rows: no genotype workspace");
+    if (dev_ptr) *dev_ptr = c->geno2b.p;
+    if (row_bytes) *row_bytes = c->row_bytes;
+    if (capacity) *capacity = c->snp_cap;
+    API_END(c)
+}
 int snprel_geno_synth(snprel_ctx *c, int64_t n_snp, uint64_t seed, double maf_lo, double maf_hi,
                       double miss_rate, int64_t snp_start) {
     API_BEGIN(c) geno_synth(c, n_snp, seed, maf_lo, maf_hi, miss_rate, snp_start);

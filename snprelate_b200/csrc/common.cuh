@@ -275,6 +275,8 @@ void geno_synth(snprel_ctx *c, int64_t n_snp, uint64_t seed, double maf_lo, doub
                 double miss_rate, int64_t snp_start);
 void geno_copy_u8(snprel_ctx *c, uint8_t *out);
 void geno_copy_2b(snprel_ctx *c, uint8_t *out, int64_t row_bytes);
+void geno_seek(snprel_ctx *c, int64_t snp_index);
+void geno_commit(snprel_ctx *c, int64_t n_snp);
 void geno_pad_tail(snprel_ctx *c);
 void ensure_stats(snprel_ctx *c);
 void snp_ratefreq(snprel_ctx *c, double *af, double *maf, double *mr);

@@ -336,6 +336,22 @@ void geno_synth(snprel_ctx *c, int64_t n_snp, uint64_t seed, double maf_lo, doub
     invalidate(c);
 }
 
+// SNP-sharded loading of a workspace that finally holds ALL SNPs (tiled N x N output): a rank
+// reserves the whole range, seeks to its own SNP block, pushes it, receives the other blocks straight
+// into the device rows (NCCL all-gather / peer copies) and then commits the row count.
+void geno_seek(snprel_ctx *c, int64_t snp_index) {
+    if (c->n_samp <= 0) fail("snprel_geno_seek: no genotype workspace");
+    if (snp_index < 0 || snp_index > c->snp_cap) fail("snprel_geno_seek: position outside the reserved SNP range");
+    c->n_snp = snp_index;
+    invalidate(c);
+}
+void geno_commit(snprel_ctx *c, int64_t n_snp) {
+    if (c->n_samp <= 0) fail("snprel_geno_commit: no genotype workspace");
+    if (n_snp < 0 || n_snp > c->snp_cap) fail("snprel_geno_commit: more SNPs than the reserved range");
+    c->n_snp = n_snp;
+    invalidate(c);
+}
+
 // rows [n_snp, round_up(n_snp, SNP_PAD)) must read as all-missing
 void geno_pad_tail(snprel_ctx *c) {
     int64_t end = round_up(std::max<int64_t>(c->n_snp, 1), SNP_PAD);

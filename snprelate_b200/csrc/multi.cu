@@ -13,6 +13,8 @@
 //   * finishing calls (snprel_grm, snprel_pca, snprel_ibs_num, ...) then run on the root device's
 //     context, which holds the global accumulators (snprel_multi_ctx).
 // Two entries of `devices` may name the same GPU (tests on a one-GPU box run the whole path that way).
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 
 #include "common.cuh"
@@ -25,6 +27,8 @@ struct snprel_multi {
     int64_t n_samp = 0, cap = 0, per_dev = 0, pos = 0;
     int active = 0;          // devices that own a non-empty SNP range
     std::string err;
+    bool replicated = false; // every device reserves the whole SNP range (tiled N x N output)
+    bool gathered = false;
     double reduce_ms = 0;    // last peer reduction (CUDA events on the root's stream + host barrier)
     int64_t reduce_bytes = 0;   // bytes that crossed the links in it
 };
@@ -307,6 +311,8 @@ int snprel_multi_geno_begin(snprel_multi *m, int64_t n_samp, int64_t snp_capacit
     m->n_samp = n_samp;
     m->cap = snp_capacity;
     m->pos = 0;
+    m->replicated = false;
+    m->gathered = false;
     for (int i = 0; i < m->active; i++) {
         const int64_t lo = i * m->per_dev, hi = std::min(snp_capacity, lo + m->per_dev);
         ck(m, i, snprel_geno_begin(m->ctx[i], n_samp, std::max<int64_t>(hi - lo, 0)));
@@ -314,8 +320,131 @@ int snprel_multi_geno_begin(snprel_multi *m, int64_t n_samp, int64_t snp_capacit
     MULTI_END(m)
 }
 
+int snprel_multi_geno_begin_replicated(snprel_multi *m, int64_t n_samp, int64_t snp_capacity) {
+    MULTI_BEGIN(m)
+    if (snp_capacity < 0) fail("snprel_multi_geno_begin_replicated: negative SNP capacity");
+    const int nd = (int)m->ctx.size();
+    const int64_t blocks = std::max<int64_t>(1, (snp_capacity + SNP_PAD - 1) / SNP_PAD);
+    m->active = nd;                                   // every device computes windows, even with an empty SNP block
+    m->per_dev = (blocks + nd - 1) / nd * SNP_PAD;
+    m->n_samp = n_samp;
+    m->cap = snp_capacity;
+    m->pos = 0;
+    m->replicated = true;
+    m->gathered = false;
+    for (int i = 0; i < nd; i++) {
+        ck(m, i, snprel_geno_begin(m->ctx[i], n_samp, snp_capacity));
+        ck(m, i, snprel_geno_seek(m->ctx[i], std::min(snp_capacity, i * m->per_dev)));
+    }
+    MULTI_END(m)
+}
+
+// every device pulls the other devices' SNP blocks out of their HBM (cudaMemcpyPeerAsync over NVLink)
+int snprel_multi_geno_gather(snprel_multi *m) {
+    MULTI_BEGIN(m)
+    if (!m->replicated) fail("snprel_multi_geno_gather: call snprel_multi_geno_begin_replicated first");
+    if (m->pos != m->cap) fail("snprel_multi_geno_gather: %lld of %lld SNPs pushed", (long long)m->pos, (long long)m->cap);
+    const int nd = (int)m->ctx.size();
+    sync_all(m);
+    for (int t = 0; t < nd; t++) {
+        set_dev(m->dev[t]);
+        for (int s = 0; s < nd; s++) {
+            if (s == t) continue;
+            const int64_t lo = std::min(m->cap, s * m->per_dev), hi = std::min(m->cap, lo + m->per_dev);
+            if (hi <= lo) continue;
+            const size_t off = (size_t)lo * m->ctx[t]->row_bytes, bytes = (size_t)(hi - lo) * m->ctx[t]->row_bytes;
+            if (m->dev[s] == m->dev[t])
+                CUDA_CHECK(cudaMemcpyAsync(m->ctx[t]->geno2b.p + off, m->ctx[s]->geno2b.p + off, bytes, cudaMemcpyDeviceToDevice,
+                                           m->ctx[t]->stream));
+            else
+                CUDA_CHECK(cudaMemcpyPeerAsync(m->ctx[t]->geno2b.p + off, m->dev[t], m->ctx[s]->geno2b.p + off, m->dev[s], bytes,
+                                               m->ctx[t]->stream));
+        }
+    }
+    sync_all(m);
+    for (int i = 0; i < nd; i++) ck(m, i, snprel_geno_commit(m->ctx[i], m->cap));
+    m->gathered = true;
+    MULTI_END(m)
+}
+
+int snprel_multi_grm_tiled(snprel_multi *m, int method, int64_t window_rows, snprel_sink_fn sink, void *user) {
+    MULTI_BEGIN(m)
+    if (!m->replicated || !m->gathered) fail("snprel_multi_grm_tiled: needs snprel_multi_geno_begin_replicated + pushes + snprel_multi_geno_gather");
+    if (method != SNPREL_GRM_EIGENSTRAT && method != SNPREL_GRM_GCTA && method != SNPREL_GRM_EIGMIX)
+        fail("snprel_multi_grm_tiled: methods Eigenstrat, GCTA and EIGMIX only");
+    if (!sink) fail("snprel_multi_grm_tiled: NULL sink");
+    const int nd = (int)m->ctx.size();
+    const int64_t n = m->n_samp, npad = round_up(n, SAMP_PAD);
+    if (window_rows < 0 || window_rows % 256) fail("snprel_multi_grm_tiled: window_rows must be a non-negative multiple of 256");
+    if (window_rows == 0) {
+        // two int64 planes + the float64 result per window row, inside 60 % of the smallest free memory
+        int64_t free_min = INT64_MAX;
+        for (int i = 0; i < nd; i++) {
+            int64_t f = 0, t = 0;
+            ck(m, i, snprel_mem_info(m->ctx[i], &f, &t));
+            free_min = std::min(free_min, f);
+        }
+        const int64_t per_row = 3 * 8 * npad;
+        window_rows = std::max<int64_t>(256, std::min<int64_t>(npad, (int64_t)(0.6 * (double)free_min / (double)per_row) / 256 * 256));
+        // at least two windows per device keep all devices busy
+        const int64_t balanced = round_up((npad + 2 * nd - 1) / (2 * nd), 256);
+        if (nd > 1) window_rows = std::max<int64_t>(256, std::min(window_rows, balanced));
+    }
+    const int64_t nw = (n + window_rows - 1) / window_rows;
+    std::mutex mu;
+    std::condition_variable cv;
+    int64_t next = 0;        // next window the sink expects
+    bool abort = false;
+    std::string sink_err;
+    const int saved_active = m->active;
+    m->active = nd;
+    try {
+        on_each(m, [&](int d) {
+            snprel_ctx *c = m->ctx[d];
+            std::vector<double> host;
+            for (int64_t w = d; w < nw; w += nd) {
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (abort) return;
+                }
+                const int64_t r0 = w * window_rows;
+                ck(m, d, snprel_set_row_window(c, r0, std::min(window_rows, npad - r0)));
+                int64_t cnt = 0;
+                ck(m, d, snprel_window_count(c, &cnt));
+                host.resize((size_t)cnt);
+                int rc = snprel_grm(c, method, host.data(), 1, nullptr);
+                std::unique_lock<std::mutex> lk(mu);
+                if (rc != 0) {
+                    abort = true;
+                    cv.notify_all();
+                    lk.unlock();
+                    ck(m, d, rc);
+                }
+                cv.wait(lk, [&] { return next == w || abort; });
+                if (abort) return;
+                const int64_t first = r0 * n - r0 * (r0 - 1) / 2;      // packed index of (r0, r0)
+                if (sink(user, first, host.data(), cnt) != 0) {
+                    abort = true;
+                    sink_err = "snprel_multi_grm_tiled: the sink asked to stop";
+                }
+                next = w + 1;
+                cv.notify_all();
+            }
+        });
+    } catch (...) {
+        m->active = saved_active;
+        for (int i = 0; i < nd; i++) snprel_set_row_window(m->ctx[i], 0, 0);
+        throw;
+    }
+    m->active = saved_active;
+    for (int i = 0; i < nd; i++) ck(m, i, snprel_set_row_window(m->ctx[i], 0, 0));
+    if (!sink_err.empty()) fail("%s", sink_err.c_str());
+    MULTI_END(m)
+}
+
 int snprel_multi_geno_push_u8(snprel_multi *m, const uint8_t *geno, int64_t cnt) {
     MULTI_BEGIN(m)
+    m->gathered = false;
     route(m, cnt, "snprel_multi_geno_push_u8", [&](int i, int64_t off, int64_t take) {
         ck(m, i, snprel_geno_push_u8(m->ctx[i], geno + off * m->n_samp, take));
     });
@@ -324,6 +453,7 @@ int snprel_multi_geno_push_u8(snprel_multi *m, const uint8_t *geno, int64_t cnt)
 
 int snprel_multi_geno_push_2b(snprel_multi *m, const uint8_t *packed, int64_t cnt, int64_t row_bytes) {
     MULTI_BEGIN(m)
+    m->gathered = false;
     route(m, cnt, "snprel_multi_geno_push_2b", [&](int i, int64_t off, int64_t take) {
         ck(m, i, snprel_geno_push_2b(m->ctx[i], packed + off * row_bytes, take, row_bytes));
     });
@@ -333,6 +463,7 @@ int snprel_multi_geno_push_2b(snprel_multi *m, const uint8_t *packed, int64_t cn
 int snprel_multi_geno_synth(snprel_multi *m, int64_t n_snp, uint64_t seed, double maf_lo, double maf_hi, double miss_rate,
                             int64_t snp_start) {
     MULTI_BEGIN(m)
+    m->gathered = false;
     route(m, n_snp, "snprel_multi_geno_synth", [&](int i, int64_t off, int64_t take) {
         ck(m, i, snprel_geno_synth(m->ctx[i], take, seed, maf_lo, maf_hi, miss_rate, snp_start + (m->pos + off)));
     });
@@ -355,6 +486,7 @@ int snprel_multi_accumulate(snprel_multi *m, int est, int bayesian, int root) {
     MULTI_BEGIN(m)
     const int nd = m->active;
     if (m->n_samp <= 0) fail("snprel_multi_accumulate: no genotype workspace");
+    if (m->replicated) fail("snprel_multi_accumulate: the workspace is replicated (tiled output): use snprel_multi_grm_tiled");
     if (root >= nd) root = 0;      // (fewer active devices than asked for: tiny data sets)
     const bool cov = est >= SNPREL_GRM_EIGENSTRAT && est <= SNPREL_GRM_EIGMIX;
     if (!cov && est != SNPREL_EST_IBS && est != SNPREL_EST_KING_ROBUST && est != SNPREL_EST_BETA)

@@ -147,7 +147,8 @@ COREARRAY_DLL_EXPORT SEXP gnrGRM_avg_val() { return Rf_ScalarReal(g_avg_val); }
 COREARRAY_DLL_EXPORT SEXP gnrGRM(SEXP NumThread, SEXP Method, SEXP GDS, SEXP useMatrix, SEXP Verbose) {
     const char *mt = CHAR(STRING_ELT(Method, 0));
     COREARRAY_TRY
-        if (!Rf_isNull(GDS)) throw ErrCoreArray("GDS output is streamed by the host wrapper (INTEGRATION.md).");
+        // R/IBD.R:570-594: with out.fn the matrix goes to the "grm" node of a SNPRELATE_OUTPUT file
+        PdGDSObj gdsn = Rf_isNull(GDS) ? NULL : GDS_Node_Path(GDS_R_SEXP2FileRoot(GDS), "grm", TRUE);   // src/genPCA.cpp:1623-1625
         int method = !strcmp(mt, "Eigenstrat") ? SNPREL_GRM_EIGENSTRAT : !strcmp(mt, "GCTA") ? SNPREL_GRM_GCTA
                    : !strcmp(mt, "Corr") ? SNPREL_GRM_CORR : !strcmp(mt, "EIGMIX") ? SNPREL_GRM_EIGMIX
                    : !strcmp(mt, "IndivBeta") ? SNPREL_GRM_INDIVBETA : -1;
@@ -155,6 +156,24 @@ COREARRAY_DLL_EXPORT SEXP gnrGRM(SEXP NumThread, SEXP Method, SEXP GDS, SEXP use
         Ctx c;
         load_for(c, method == SNPREL_GRM_INDIVBETA ? SNPREL_EST_BETA : method);
         const size_t n = MCWorkingGeno.Space().SampleNum();
+        if (gdsn) {
+            // grm_save_to_gds (src/genPCA.cpp:1571-1584): n appends of one full row each, in row order --
+            // the node is extendable along its last dimension and usually compressed, so the stream is
+            // strictly sequential.  Like the reference (CdMatTri) the upper triangle is held on the host.
+            const bool pk = method != SNPREL_GRM_CORR;
+            std::vector<double> tri(pk ? n * (n + 1) / 2 : n * n), row(n);
+            c.ck(snprel_grm(c.h, method, tri.data(), pk, &g_avg_val));
+            for (size_t i = 0; i < n; i++) {
+                if (pk) {
+                    for (size_t j = 0; j < i; j++) row[j] = tri[j * (2 * n - j - 1) / 2 + i];      // (j, i), j < i
+                    memcpy(&row[i], &tri[i * (2 * n - i - 1) / 2 + i], (n - i) * sizeof(double));
+                } else {
+                    memcpy(&row[0], &tri[i * n], n * sizeof(double));
+                }
+                GDS_Array_AppendData(gdsn, n, &row[0], svFloat64);
+            }
+            return R_NilValue;
+        }
         const bool packed = (Rf_asLogical(useMatrix) == TRUE) && method != SNPREL_GRM_CORR;
         rv_ans = PROTECT(sym_result(n, packed));
         c.ck(snprel_grm(c.h, method, REAL(rv_ans), packed, &g_avg_val));

@@ -125,3 +125,30 @@ print("multi-device R shim ok")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "multi-device R shim ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("devices", device_sets()[::2], ids=lambda d: "dev" + "".join(map(str, d)))
+def test_tiled_grm_with_sharded_loading_and_gather(data, devices):
+    """N x N output tiled across devices: every device reserves the whole SNP range, only the
+    owner receives a pushed block, the gather completes the copies device to device, windows are dealt
+    w mod n and delivered to the sink in order."""
+    g = data
+    n = g.shape[1]
+    with S.MultiContext(devices) as m:
+        m.geno_begin_replicated(n, g.shape[0])
+        m.geno_push_u8(g[:3000])
+        m.geno_push_u8(g[3000:])
+        own = [m.ctx(i).geno_dim()[1] for i in range(len(devices))]          # before the gather: the append positions
+        m.geno_gather()
+        for i in range(len(devices)):
+            assert np.array_equal(m.ctx(i).geno_copy_u8(), g)                 # every device holds all SNPs
+        for method, ref in (("GCTA", O.grm_gcta(g)), ("Eigenstrat", O.grm_eigenstrat(g)), ("EIGMIX", O.grm_eigmix(g))):
+            out = m.grm_tiled(method, window_rows=256)
+            assert relerr(out, ref[np.triu_indices(n)]) < TOL, method
+            firsts = [f for f, _ in m.tiled_calls]
+            assert firsts == sorted(firsts) and len(firsts) == 3 and sum(c for _, c in m.tiled_calls) == out.size
+        out = m.grm_tiled("GCTA")                                             # automatic window height
+        assert relerr(out, O.grm_gcta(g)[np.triu_indices(n)]) < TOL
+        with pytest.raises(S.SNPRelError):
+            m.accumulate("GCTA")
+    assert len(own) == len(devices)

@@ -90,3 +90,14 @@ def test_randomized_pca_through_the_r_entry_point(data):
     assert abs(tr - rtr) <= 1e-12 * rtr and vt.shape == (aux_dim * (it + 1), n)
     assert np.max(np.abs(sig[:4] - rsig[:4]) / rsig[:4]) < 1e-7
     assert np.max(1 - np.abs(np.sum(vt[:4] * rvt[:4], axis=1))) < 1e-10
+
+
+def test_gds_output_through_the_r_entry_point(data):
+    """gnrGRM(..., GDS = <output file>) of the binding: the same n x n row stream the reference appends
+    to the "grm" node of a SNPRELATE_OUTPUT file (grm_save_to_gds, src/genPCA.cpp:1571-1584)."""
+    w = R.RefWorkspace(data, R.RSHIM_PATH)
+    for method, ref in (("GCTA", O.grm_gcta(data)), ("EIGMIX", O.grm_eigmix(data)),
+                        ("IndivBeta", O.grm_indivbeta(O.beta_counts(data))[0])):
+        got = w.grm_gds(method)
+        assert np.array_equal(got, got.T) and relerr(got, ref) < TOL, method
+        assert np.array_equal(got, w.grm(method)), method          # identical to the in-memory result

@@ -134,3 +134,11 @@ def test_randomized_pca(data):
     res = O.pca_randomized_result(sig, vt, tr, n, k)
     ev, evec = O.pca_eigen(O.pca_genmat(data)[0], k)
     assert np.max(np.abs(res["eigenval"][:k] - ev[:k]) / ev[:k]) < 1e-3
+
+
+def test_gds_output_stream_is_the_full_matrix_row_by_row(data):
+    """gnrGRM with out.fn (R/IBD.R:570-594): grm_save_to_gds appends n full rows to the "grm" node
+    (src/genPCA.cpp:1571-1584).  (method "Corr" never reaches the node in the reference, :1655-1685.)"""
+    w = R.RefWorkspace(data)
+    for method in ("GCTA", "Eigenstrat", "EIGMIX", "IndivBeta"):
+        assert np.array_equal(w.grm_gds(method, 2), w.grm(method, 2)), method
