@@ -38,7 +38,8 @@ class _DevArray:
                                          "data": (int(ptr), False), "version": 2}
 
 
-_KIND = {0: ("<i8", np.int64), 1: ("<i4", np.int32), 2: ("<f8", np.float64)}   # uint32 sums == int32 sums mod 2^32
+_KIND = {0: ("<i8", np.int64), 1: ("<i4", np.int32), 2: ("<f8", np.float64),   # uint32 sums == int32 sums mod 2^32
+         3: ("|u1", np.uint8)}                                                  # raw bytes (packed genotype rows)
 
 
 def buffer_tensor(ptr, count, kind, device):
@@ -167,3 +168,32 @@ def ibd_mom_sharded(ctx, allele_freq=None, kinship_constraint=False, packed=Fals
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     k0, k1 = ctx.ibd_mom_from_sums(t.cpu().numpy(), kinship_constraint, packed)
     return k0, k1, afreq
+
+
+def load_sharded_then_gather(ctx, n_samp, n_snp, fill, rank, world, group=None, device=None):
+    """Tiled N x N output ("when N^2 exceeds one GPU"): every rank finally holds
+    ALL SNPs, but only its own SNP block crosses its PCIe link -- `fill(lo, hi)` pushes SNPs [lo, hi)
+    into `ctx` (geno_push_2b / geno_push_u8 from the host, or the synthetic generator) -- and the other
+    blocks arrive over NVLink: one NCCL broadcast per block straight into the device rows of the
+    workspace (an all-gather with unequal block sizes).  Returns the bytes received from peers."""
+    import torch.distributed as dist
+    ctx.geno_begin(n_samp, n_snp)
+    lo, hi = shard_range(n_snp, rank, world)
+    ctx.geno_seek(lo)
+    if hi > lo:
+        fill(lo, hi)
+    ptr, row_bytes, _ = ctx.geno_device_rows()
+    received = 0
+    for s in range(world):
+        slo, shi = shard_range(n_snp, s, world)
+        if shi <= slo:
+            continue
+        t = buffer_tensor(ptr + slo * row_bytes, (shi - slo) * row_bytes, 3, device)
+        dist.broadcast(t, src=s if group is None else dist.get_global_rank(group, s), group=group)
+        if s != rank:
+            received += (shi - slo) * row_bytes
+    if device is not None:
+        import torch
+        torch.cuda.synchronize(device)
+    ctx.geno_commit(n_snp)
+    return received

@@ -53,6 +53,10 @@ def _worker(rank, world, port, q):
     ctx.geno_begin(n, hi - lo)
     ctx.geno_push_u8(g[lo:hi])
     out["mom"] = D.ibd_mom_sharded(ctx, kinship_constraint=True, device=dev)[:2]
+    # tiled mode: own SNP block from the host, the other block over NCCL straight into the device rows
+    recv = D.load_sharded_then_gather(ctx, n, m, lambda a, b: ctx.geno_push_u8(g[a:b]), rank, world, device=dev)
+    out["gathered"] = bool(np.array_equal(ctx.geno_copy_u8(), g)) and recv > 0
+    out["gcta_after_gather"] = ctx.grm("GCTA")[0]
     q.put((rank, out))
     tdist.destroy_process_group()
 
@@ -80,6 +84,8 @@ def test_two_rank_snp_sharding_matches_single_gpu():
             err = np.max(np.abs(res[rank][k] - r) / np.maximum(np.abs(r), 1))
             assert err < 1e-10, (rank, k, err)
         assert np.array_equal(res[rank]["ibs"], O.ibs_counts(g))
+        assert res[rank]["gathered"]
+        assert np.max(np.abs(res[rank]["gcta_after_gather"] - ref["GCTA"]) / np.maximum(np.abs(ref["GCTA"]), 1)) < 1e-10
         e, _ = O.ibd_mom_tables(g)
         r0, r1 = O.ibd_mom(O.ibs_counts(g), e, True)
         assert np.max(np.abs(res[rank]["mom"][0] - r0)) < 1e-13 and np.max(np.abs(res[rank]["mom"][1] - r1)) < 1e-13

@@ -1,6 +1,8 @@
 """BASELINE config 5 (snpgdsGRM GCTA, 500k samples x 800k SNPs, N x N output tiled across GPUs)
-or any other tiled run: every rank holds the whole 2-bit matrix (100 GB at C5), the row windows of
-the N x N output are dealt to the ranks in boustrophedon order, no collective.  On one GPU `--world 8 --rank r`
+or any other tiled run: every rank ends up holding the whole 2-bit matrix (100 GB at C5) -- under torchrun
+each rank loads only its own SNP block and the others arrive over NVLink (snprelate_b200.dist.
+load_sharded_then_gather: 100 GB cross PCIe in total instead of 800) -- the row windows of
+the N x N output are dealt to the ranks in boustrophedon order, no collective in the compute phase.  On one GPU `--world 8 --rank r`
 runs exactly the share rank r of an 8-GPU job would run (same windows, same time), so the
 8-GPU time can be measured at 1/8 of the GPU-minutes; under torchrun rank / world come from the
 environment and the job time is the max over ranks.
@@ -26,6 +28,8 @@ ap.add_argument("--rank", type=int, default=int(os.environ.get("RANK", "0")))
 ap.add_argument("--method", default="GCTA")
 ap.add_argument("--miss", type=float, default=0.005)
 ap.add_argument("--max-windows", type=int, default=0, help="stop after K of this rank's windows (0 = all)")
+ap.add_argument("--replicated-load", action="store_true", help="every rank loads ALL SNPs itself (round 1 behaviour) instead of "
+                "loading its own SNP block and gathering the others over NVLink")
 ap.add_argument("--check", type=int, default=48, help="oracle check on K scattered samples (first / middle / last tile rows); "
                 "every rank checks the entries of its own windows")
 args = ap.parse_args()
@@ -40,8 +44,18 @@ if dist:
 n, m = args.n, args.m
 ctx = S.Context(local)
 t0 = time.perf_counter()
-ctx.geno_begin(n, m)
-ctx.geno_synth(m, seed=20261017, miss_rate=args.miss)
+gathered_bytes = 0
+if dist and not args.replicated_load:
+    # SNP-sharded residency: this rank generates (stands in for: reads from the host) only its SNP block;
+    # the other blocks come over NVLink
+    from snprelate_b200 import dist as D
+    gathered_bytes = D.load_sharded_then_gather(
+        ctx, n, m, lambda lo, hi: ctx.geno_synth(hi - lo, seed=20261017, miss_rate=args.miss, snp_start=lo),
+        args.rank, args.world, device=torch.device("cuda", local))
+else:
+    ctx.geno_begin(n, m)
+    ctx.geno_synth(m, seed=20261017, miss_rate=args.miss)
+torch.cuda.synchronize()
 t_synth = time.perf_counter() - t0
 free0, total = ctx.mem_info()
 
@@ -119,7 +133,8 @@ if args.rank == 0:
         "workload": f"snpgdsGRM {args.method}, synthetic {n} samples x {m} SNPs, missing {args.miss}, "
                     f"N x N output tiled in {args.rows}-row windows dealt boustrophedon to {args.world} rank(s)",
         "rank": args.rank, "world": args.world, "torchrun": dist, "windows_this_rank": len(mine), "windows_total": len(wins),
-        "synth_s": round(t_synth, 2), "job_s": round(t_job_max, 3), "hot_kernel_s": round(hot_ms / 1e3, 3),
+        "load_s": round(t_synth, 2), "bytes_gathered_from_peers_rank0": int(gathered_bytes),
+        "loading": "own SNP block + NCCL broadcast gather" if gathered_bytes else "every rank loads all SNPs", "job_s": round(t_job_max, 3), "hot_kernel_s": round(hot_ms / 1e3, 3),
         "pairs_this_job": pairs_all, "share_of_all_pairs": pairs_all / total_pairs,
         "pair_snps_per_s": pairs_all * m / t_job_max,
         "pair_snps_per_s_per_gpu": pairs_all * m / t_job_max / (args.world if dist else 1),
