@@ -153,7 +153,8 @@ def workload_config(gpus):
     return {"workload": f"snpgdsPCA covariance (Eigenstrat), synthetic {N_SAMP} samples x {N_SNP} SNPs per GPU, "
                         f"2-bit packed, missing rate {MISS}, MAF U(0.05,0.5)",
             "n_samp": N_SAMP, "n_snp_per_gpu": N_SNP, "n_snp_total": N_SNP * gpus, "miss_rate": MISS,
-            "sharding": "SNP blocks per rank, one all-reduce of the int64 partial planes" if gpus > 1 else "single GPU",
+            "sharding": "SNP blocks per rank, one sum-reduction of the int64 partial planes over NVLink peer memory "
+                        "(library kernel, upper triangle only; SNPREL_REDUCE=nccl switches to an NCCL all-reduce)" if gpus > 1 else "single GPU",
             "l2": "inputs (2.56 GB of 2-bit genotypes per GPU) are larger than the 126 MB L2"}
 
 
@@ -250,6 +251,9 @@ def run_ours(args):
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
+    REDUCE = os.environ.get("SNPREL_REDUCE", "peer")      # "peer" (default) or "nccl"
+    link_bytes, reduce_ms = [0], [0.0]
+
     def step():
         """one pass of the hot path; returns device ms (library events + collective events)"""
         if world == 1:
@@ -260,10 +264,14 @@ def run_ours(args):
         ctx.accumulate(est, plan)
         ms = ctx.last_step_ms()
         ev0.record()
-        D.allreduce_buffers(ctx.reduce_buffers(), device=dev)
+        if REDUCE == "nccl":
+            D.allreduce_buffers(ctx.reduce_buffers(), device=dev)
+        else:       # the library's own peer-memory reduction (CUDA IPC + NVLink loads), upper triangle only
+            link_bytes[0] = D.peer_reduce_buffers(ctx, rank, world, device=dev)
         ev1.record()
         torch.cuda.synchronize()
         ms += ev0.elapsed_time(ev1)
+        reduce_ms[0] = ev0.elapsed_time(ev1)
         ctx.mark_reduced()
         ms += ctx.time_finish(est)     # int64 planes -> final float64 matrix ("final N x N complete")
         return ms
@@ -315,7 +323,7 @@ def run_ours(args):
         ctx.geno_push_2b(hg)
         tc = time.perf_counter()
         if world > 1:
-            D.accumulate_sharded(ctx, est, device=dev)
+            D.accumulate_sharded(ctx, est, device=dev, reduce=REDUCE)
         td = time.perf_counter()
         e2e_last.update(ctx.pca(genmat_only=True, genmat_out=ho))
         te = time.perf_counter()
@@ -437,6 +445,8 @@ def run_ours(args):
     extra = {}
     if strong:
         extra["strong"] = strong
+    if world > 1:
+        extra["reduction"] = {"kind": REDUCE, "ms_last_step": reduce_ms[0], "link_bytes_this_rank": int(link_bytes[0])}
     if world == 1 and not args.no_extra:
         ctx.close()
         extra["pair_counters"] = pair_counter_legs(local, None)

@@ -392,6 +392,18 @@ int snprel_multi_accumulate(snprel_multi *m, int est, int bayesian, int root);
 /* duration (ms) and link traffic (bytes) of the last peer reduction */
 int snprel_multi_last_reduce(snprel_multi *m, double *ms, int64_t *bytes);
 
+/* The same peer-memory reduction for ONE PROCESS PER GPU (torchrun, bench.py --gpus N): every rank
+ * exports a CUDA IPC handle (+ byte offset inside the allocation) for each of its reduce buffers
+ * (snprel_reduce_buffer), the host gathers them from all ranks ([world][n_buffers], 64 bytes each) and
+ * opens them; phase 1 sums this rank's row slice of every buffer out of the peers' HBM, phase 2 pulls
+ * the other ranks' reduced slices (all ranks when root < 0, else the root; the small per-sample
+ * buffers always).  The caller places a cross-process barrier before phase 1, between the phases and
+ * after phase 2, then calls snprel_mark_reduced (snprelate_b200/dist.py:peer_reduce_buffers). */
+int snprel_reduce_ipc_export(snprel_ctx *ctx, int idx, void *handle64, int64_t *offset);
+int snprel_peer_reduce_open(snprel_ctx *ctx, int rank, int world, const void *handles, const int64_t *offsets);
+int snprel_peer_reduce_phase(snprel_ctx *ctx, int phase, int root, int64_t *link_bytes);
+void snprel_peer_reduce_close(snprel_ctx *ctx);
+
 /* Tiled N x N output over several devices (N^2 exceeds one GPU's HBM): _begin_replicated reserves the
  * WHOLE SNP range on every device but routes each pushed block to its owner only (1/n of the data per
  * PCIe link); _geno_gather then completes every device's copy with peer copies over NVLink.

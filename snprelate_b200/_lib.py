@@ -104,6 +104,9 @@ def load_library():
         "snprel_multi_geno_begin_replicated": [p, i64, i64],
         "snprel_multi_geno_gather": [p],
         "snprel_multi_grm_tiled": [p, i32, i64, p, p],
+        "snprel_reduce_ipc_export": [p, i32, p, C.POINTER(i64)],
+        "snprel_peer_reduce_open": [p, i32, i32, p, p],
+        "snprel_peer_reduce_phase": [p, i32, i32, C.POINTER(i64)],
         "snprel_multi_create": [p, i32, C.POINTER(p)],
         "snprel_multi_geno_begin": [p, i64, i64],
         "snprel_multi_geno_push_u8": [p, p, i64],
@@ -130,6 +133,8 @@ def load_library():
     lib.snprel_kernel_launches.restype = i64
     lib.snprel_device_count.argtypes = []
     lib.snprel_device_count.restype = i32
+    lib.snprel_peer_reduce_close.argtypes = [p]
+    lib.snprel_peer_reduce_close.restype = None
     lib.snprel_multi_destroy.argtypes = [p]
     lib.snprel_multi_destroy.restype = None
     lib.snprel_multi_last_error.argtypes = [p]
@@ -156,6 +161,7 @@ EXPORTED_SYMBOLS = [
     "snprel_multi_set_row_window", "snprel_multi_set_count_engine", "snprel_multi_accumulate", "snprel_multi_last_reduce",
     "snprel_geno_seek", "snprel_geno_device_rows", "snprel_geno_commit",
     "snprel_multi_geno_begin_replicated", "snprel_multi_geno_gather", "snprel_multi_grm_tiled",
+    "snprel_reduce_ipc_export", "snprel_peer_reduce_open", "snprel_peer_reduce_phase", "snprel_peer_reduce_close",
 ]
 
 
@@ -573,6 +579,27 @@ class Context:
             self._ck(self.lib.snprel_reduce_buffer(self.h, i, C.byref(ptr), C.byref(cnt), C.byref(kind)))
             out.append((ptr.value, cnt.value, kind.value))
         return out
+
+    def reduce_ipc_handles(self):
+        """(handles bytes [n_buffers * 64], offsets int64 [n_buffers]) of this context's reduce buffers."""
+        nb = self.lib.snprel_reduce_buffer_count(self.h)
+        hb = np.zeros(nb * 64, dtype=np.uint8)
+        off = np.zeros(nb, dtype=np.int64)
+        for k in range(nb):
+            o = C.c_int64()
+            self._ck(self.lib.snprel_reduce_ipc_export(self.h, k, hb[k * 64:].ctypes.data_as(C.c_void_p), C.byref(o)))
+            off[k] = o.value
+        return hb, off
+
+    def peer_reduce_open(self, rank, world, handles, offsets):
+        handles = np.ascontiguousarray(handles, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._ck(self.lib.snprel_peer_reduce_open(self.h, int(rank), int(world), _ptr(handles), _ptr(offsets)))
+
+    def peer_reduce_phase(self, phase, root=-1):
+        b = C.c_int64()
+        self._ck(self.lib.snprel_peer_reduce_phase(self.h, int(phase), int(root), C.byref(b)))
+        return b.value
 
     def last_plan(self):
         pl = Plan()

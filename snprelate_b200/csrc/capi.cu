@@ -84,6 +84,7 @@ void snprel_destroy(snprel_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     eigen_release(c);
+    snprel_peer_reduce_close(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->evs0) cudaEventDestroy(c->evs0);

@@ -217,6 +217,7 @@ struct snprel_ctx {
 
     // eigen step (eigen.cu): persistent cuBLAS / cuSOLVER handles and what the last solve did
     void *eig_handles = nullptr;
+    void *ipc_peers = nullptr;   // multi.cu: peers' reduce buffers mapped through CUDA IPC (one process per GPU)
     int eig_solver = 0;          // 0 dense (Xsyevd), 1 Chebyshev-filtered subspace iteration
     int eig_rounds = 0, eig_gemms = 0;
     double eig_phase_ms[3] = {0, 0, 0};   // filter, orthonormalisation, Rayleigh-Ritz

@@ -539,6 +539,7 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     if (!(c->debug_flags & 2u) && base_items < 8 * slots)
         parts = (int)std::min<int64_t>(std::min<int64_t>((8 * slots + base_items - 1) / base_items, 64),
                                        std::max(1, stages_total / 4));
+    if (c->debug_flags & 0xF00u) parts = (int)((c->debug_flags >> 8) & 15u);   // experiment: forced SNP segments per item
     std::vector<std::vector<int>> cuts(groups.size());   // stage boundaries, ascending, first 0, last stages_total
     const int CH = GRAM_CHUNK / SK;                        // stages per bound chunk
     for (size_t gi = 0; gi < groups.size(); gi++) {
@@ -574,7 +575,7 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     // CTA pairs share genotype panels in L2), tiles in a super-tile raster
     std::vector<Item> items;
     auto width = [&](int t) { return tile_ncols(std::min<int64_t>(TN2, n - (int64_t)t * TN2)); };
-    int only_group = -1;
+    int only_group = -1, only_seg = -1;
     auto emit = [&](int tm, int tn) {
         const int first_col = upper_only ? tm : 0;
         for (size_t gi = 0; gi < groups.size(); gi++) {
@@ -597,6 +598,7 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
                 it.ncols[1] = (short)(2 * tn2 + 1 < nt ? width(2 * tn2 + 1) : 0);
             }
             for (size_t k = 0; k + 1 < cuts[gi].size(); k++) {
+                if (only_seg >= 0 && (int)k != only_seg) continue;
                 it.st_begin = cuts[gi][k];
                 it.st_end = cuts[gi][k + 1];
                 items.push_back(it);
@@ -611,7 +613,18 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
                 for (int tm = std::max(rb, tm_lo); tm < std::min(rb + RB, tm_hi); tm++)
                     for (int tn = std::max(cb, upper_only ? tm : 0); tn < std::min(cb + CB, nt); tn++) emit(tm, tn);
     };
-    if (c->debug_flags & 128u) {      // experiment: group-major (all tiles of one pass group, then the next)
+    if (c->debug_flags & 0xF00u) {    // experiment: SNP-segment-major inside every super-tile (co-resident items walk the same SNP range)
+        size_t nseg = 0;
+        for (auto &cu : cuts) nseg = std::max(nseg, cu.size() - 1);
+        for (int rb = tm_lo / RB * RB; rb < tm_hi; rb += RB)
+            for (int cb = (upper_only ? rb / CB * CB : 0); cb < nt; cb += CB)
+                for (size_t sg = 0; sg < nseg; sg++) {
+                    only_seg = (int)sg;
+                    for (int tm = std::max(rb, tm_lo); tm < std::min(rb + RB, tm_hi); tm++)
+                        for (int tn = std::max(cb, upper_only ? tm : 0); tn < std::min(cb + CB, nt); tn++) emit(tm, tn);
+                }
+        only_seg = -1;
+    } else if (c->debug_flags & 128u) {      // experiment: group-major (all tiles of one pass group, then the next)
         for (size_t g = g_lo; g < g_hi; g++) {
             only_group = (int)g;
             raster();

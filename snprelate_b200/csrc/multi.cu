@@ -19,6 +19,8 @@
 
 #include "common.cuh"
 
+#include <cuda.h>
+
 using namespace snprel;
 
 struct snprel_multi {
@@ -203,6 +205,32 @@ void peer_reduce(snprel_multi *m, int root) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
 }
+
+
+// ---------------------------------------------------------------------------
+// The same reduction for ONE PROCESS PER GPU (torchrun / torch.distributed, bench.py --gpus N): the peers'
+// buffers are mapped through CUDA IPC handles instead of being plain pointers of this process.  The
+// host side (snprelate_b200/dist.py:peer_reduce_buffers) exchanges the handles once per buffer
+// allocation and places a barrier between the phases; the kernels are the ones above.
+// ---------------------------------------------------------------------------
+struct IpcPeers {
+    struct Map { cudaIpcMemHandle_t h; void *base; };
+    std::vector<Map> maps;                       // opened allocations (cached: the buffers are persistent)
+    std::vector<std::vector<const void *>> ptr;  // [buffer][rank] (own rank: the local pointer)
+    int world = 0, rank = 0;
+    ~IpcPeers() {
+        for (auto &m : maps) cudaIpcCloseMemHandle(m.base);
+    }
+    void *open(const cudaIpcMemHandle_t &h) {
+        for (auto &m : maps)
+            if (memcmp(&m.h, &h, sizeof(h)) == 0) return m.base;
+        void *base = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) fail("cudaIpcOpenMemHandle: %s (peer-memory reduction needs NVLink / PCIe peer access between the ranks' GPUs)", cudaGetErrorString(e));
+        maps.push_back({h, base});
+        return base;
+    }
+};
 
 // route `cnt` SNP rows starting at global position m->pos to their owners
 template <class F>
@@ -522,6 +550,127 @@ int snprel_multi_last_reduce(snprel_multi *m, double *ms, int64_t *bytes) {
     if (ms) *ms = m->reduce_ms;
     if (bytes) *bytes = m->reduce_bytes;
     MULTI_END(m)
+}
+
+// ---- one process per GPU: peer-memory reduction through CUDA IPC -----------------------------------
+int snprel_reduce_ipc_export(snprel_ctx *c, int idx, void *handle64, int64_t *offset) {
+    if (!c) return 1;
+    try {
+        set_dev(c->device);
+        if (idx < 0 || idx >= (int)c->reduce_list.size()) fail("snprel_reduce_ipc_export: index out of range");
+        if (!handle64 || !offset) fail("snprel_reduce_ipc_export: NULL output");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+        void *p = c->reduce_list[idx].ptr;
+        memset(handle64, 0, 64);
+        *offset = 0;
+        if (p && c->reduce_list[idx].count > 0) {
+            // the handle names the whole allocation; the buffer may start inside it
+            CUdeviceptr base = 0;
+            size_t size = 0;
+            cudaPointerAttributes at;
+            CUDA_CHECK(cudaPointerGetAttributes(&at, p));
+            typedef CUresult (*RangeFn)(CUdeviceptr *, size_t *, CUdeviceptr);
+            static RangeFn range = nullptr;
+            if (!range) {
+                void *fn = nullptr;
+                cudaDriverEntryPointQueryResult q;
+                CUDA_CHECK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q));
+                if (!fn || q != cudaDriverEntryPointSuccess) fail("cuMemGetAddressRange is not available");
+                range = reinterpret_cast<RangeFn>(fn);
+            }
+            if (range(&base, &size, (CUdeviceptr)p) != CUDA_SUCCESS) fail("cuMemGetAddressRange failed");
+            cudaIpcMemHandle_t h;
+            CUDA_CHECK(cudaIpcGetMemHandle(&h, (void *)base));
+            memcpy(handle64, &h, 64);
+            *offset = (int64_t)((CUdeviceptr)p - base);
+        }
+        return 0;
+    } catch (const Error &e) {
+        c->err = e.msg;
+        return 1;
+    }
+}
+
+// handles / offsets: [world][n_buffers] (64 bytes each / int64 each), as gathered from every rank
+int snprel_peer_reduce_open(snprel_ctx *c, int rank, int world, const void *handles, const int64_t *offsets) {
+    if (!c) return 1;
+    try {
+        set_dev(c->device);
+        if (world < 1 || world > MAX_DEV || rank < 0 || rank >= world) fail("snprel_peer_reduce_open: bad rank / world");
+        if (!c->ipc_peers) c->ipc_peers = new IpcPeers();
+        IpcPeers *ip = static_cast<IpcPeers *>(c->ipc_peers);
+        const size_t nb = c->reduce_list.size();
+        ip->world = world;
+        ip->rank = rank;
+        ip->ptr.assign(nb, std::vector<const void *>((size_t)world, nullptr));
+        const unsigned char *hb = static_cast<const unsigned char *>(handles);
+        for (size_t k = 0; k < nb; k++)
+            for (int r = 0; r < world; r++) {
+                if (r == rank) {
+                    ip->ptr[k][r] = c->reduce_list[k].ptr;
+                    continue;
+                }
+                if (c->reduce_list[k].count <= 0) continue;
+                cudaIpcMemHandle_t h;
+                memcpy(&h, hb + ((size_t)r * nb + k) * 64, 64);
+                ip->ptr[k][r] = static_cast<const char *>(ip->open(h)) + offsets[(size_t)r * nb + k];
+            }
+        return 0;
+    } catch (const Error &e) {
+        c->err = e.msg;
+        return 1;
+    }
+}
+
+// phase 1: sum this rank's row slice of every buffer out of the peers' memory (in place).
+// phase 2: pull the other ranks' reduced slices (every rank when root < 0, else the root only; small
+// buffers always).  The caller puts a cross-process barrier before phase 1, between the phases and after.
+int snprel_peer_reduce_phase(snprel_ctx *c, int phase, int root, int64_t *link_bytes) {
+    if (!c) return 1;
+    try {
+        set_dev(c->device);
+        IpcPeers *ip = static_cast<IpcPeers *>(c->ipc_peers);
+        if (!ip || ip->ptr.size() != c->reduce_list.size()) fail("snprel_peer_reduce_phase: call snprel_peer_reduce_open first");
+        const int nd = ip->world, me = ip->rank;
+        const int esz[3] = {8, 4, 8};
+        int64_t bytes = 0;
+        for (size_t k = 0; k < c->reduce_list.size(); k++) {
+            const ReduceBuf &b = c->reduce_list[k];
+            if (b.count <= 0) continue;
+            const Shape s = shape_of(b);
+            if (phase == 1) {
+                const int64_t ra = s.rows * me / nd, rb = s.rows * (me + 1) / nd;
+                std::vector<const void *> srcs;
+                for (int p = 0; p < nd; p++)
+                    if (p != me) srcs.push_back(ip->ptr[k][p]);
+                launch_kind(b.kind, false, c->stream, b.ptr, srcs, b, s, ra, rb);
+                bytes += live_elems(s, ra, rb) * esz[b.kind] * (nd - 1);
+            } else {
+                const bool everywhere = root < 0 || b.count <= (1 << 22);
+                if (!everywhere && me != root) continue;
+                for (int d = 0; d < nd; d++) {
+                    if (d == me) continue;
+                    const int64_t ra = s.rows * d / nd, rb = s.rows * (d + 1) / nd;
+                    std::vector<const void *> srcs{ip->ptr[k][d]};
+                    launch_kind(b.kind, true, c->stream, b.ptr, srcs, b, s, ra, rb);
+                    bytes += live_elems(s, ra, rb) * esz[b.kind];
+                }
+            }
+        }
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (link_bytes) *link_bytes = bytes;
+        return 0;
+    } catch (const Error &e) {
+        c->err = e.msg;
+        return 1;
+    }
+}
+
+void snprel_peer_reduce_close(snprel_ctx *c) {
+    if (!c || !c->ipc_peers) return;
+    cudaSetDevice(c->device);
+    delete static_cast<IpcPeers *>(c->ipc_peers);
+    c->ipc_peers = nullptr;
 }
 
 }  // extern "C"

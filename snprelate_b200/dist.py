@@ -140,15 +140,48 @@ def allreduce_buffers(buffers, group=None, device=None, dst=None):
             dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM, group=group)
 
 
-def accumulate_sharded(ctx, est, bayesian=False, group=None, device=None):
-    """Plan -> agree on the fixed-point format -> accumulate the local SNP shard ->
-    all-reduce the partial accumulators -> mark reduced.  Afterwards the usual
-    finish calls (ctx.grm / ctx.pca / ctx.ibs_num ...) read the global result."""
+def peer_reduce_buffers(ctx, rank, world, root=None, group=None, device=None):
+    """The library's own reduction over NVLink peer memory for one process per GPU (csrc/multi.cu):
+    every rank maps its peers' reduce buffers through CUDA IPC (handles exchanged with one
+    all_gather, re-used while the buffers keep their allocations), sums ITS row slice of every
+    buffer out of the peers' HBM, and after a barrier pulls the other ranks' reduced slices -- every
+    rank (`root` None: an all-reduce) or only the finishing rank (`root`).  Only the live
+    upper-triangle columns of the N x N planes cross the links.  NCCL carries the 64-byte handles
+    and the barriers only.  Returns the bytes this rank moved over the links."""
     import torch
+    import torch.distributed as dist
+    hb, off = ctx.reduce_ipc_handles()
+    nb = off.size
+    dev = "cpu" if device is None else device
+    th = torch.from_numpy(hb).to(dev)
+    to = torch.from_numpy(off).to(dev)
+    gh = torch.empty(world * nb * 64, dtype=torch.uint8, device=dev)
+    go = torch.empty(world * nb, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gh, th, group=group)
+    dist.all_gather_into_tensor(go, to, group=group)      # (also the barrier before phase 1: every rank has accumulated)
+    ctx.peer_reduce_open(rank, world, gh.cpu().numpy(), go.cpu().numpy())
+    moved = ctx.peer_reduce_phase(1, -1 if root is None else root)
+    dist.barrier(group=group)
+    moved += ctx.peer_reduce_phase(2, -1 if root is None else root)
+    dist.barrier(group=group)                             # nobody re-uses its buffers while a peer still reads them
+    return moved
+
+
+def accumulate_sharded(ctx, est, bayesian=False, group=None, device=None, reduce="nccl", root=None):
+    """Plan -> agree on the fixed-point format -> accumulate the local SNP shard ->
+    sum the partial accumulators over the ranks -> mark reduced.  Afterwards the usual
+    finish calls (ctx.grm / ctx.pca / ctx.ibs_num ...) read the global result.
+    reduce: "nccl" (all-reduce / reduce to `root`) or "peer" (the library's peer-memory reduction,
+    GPUs of one box only)."""
+    import torch
+    import torch.distributed as dist
     plan = ctx.plan_local(est, bayesian)
     plan = reduce_plan(plan, group, device)
     ctx.accumulate(est, plan)
-    allreduce_buffers(ctx.reduce_buffers(), group, device)
+    if reduce == "peer":
+        peer_reduce_buffers(ctx, dist.get_rank(group), dist.get_world_size(group), root, group, device)
+    else:
+        allreduce_buffers(ctx.reduce_buffers(), group, device, dst=root)
     if device is not None:
         torch.cuda.synchronize(device)
     ctx.mark_reduced()

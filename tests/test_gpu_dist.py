@@ -53,6 +53,15 @@ def _worker(rank, world, port, q):
     ctx.geno_begin(n, hi - lo)
     ctx.geno_push_u8(g[lo:hi])
     out["mom"] = D.ibd_mom_sharded(ctx, kinship_constraint=True, device=dev)[:2]
+    # the library's own peer-memory reduction (CUDA IPC) instead of NCCL: all-reduce and reduce-to-root
+    ctx.geno_begin(n, hi - lo)
+    ctx.geno_push_u8(g[lo:hi])
+    D.accumulate_sharded(ctx, 1, device=dev, reduce="peer")
+    out["gcta_peer"] = ctx.grm("GCTA")[0]
+    ctx.accumulate(11)
+    D.peer_reduce_buffers(ctx, rank, world, root=1, device=dev)
+    ctx.mark_reduced()
+    out["king_peer_root1"] = ctx.king_robust_counts() if rank == 1 else None
     # tiled mode: own SNP block from the host, the other block over NCCL straight into the device rows
     recv = D.load_sharded_then_gather(ctx, n, m, lambda a, b: ctx.geno_push_u8(g[a:b]), rank, world, device=dev)
     out["gathered"] = bool(np.array_equal(ctx.geno_copy_u8(), g)) and recv > 0
@@ -85,6 +94,9 @@ def test_two_rank_snp_sharding_matches_single_gpu():
             assert err < 1e-10, (rank, k, err)
         assert np.array_equal(res[rank]["ibs"], O.ibs_counts(g))
         assert res[rank]["gathered"]
+        assert np.array_equal(res[rank]["gcta_peer"], res[rank]["GCTA"])          # same exact integers, same epilogue
+    assert np.array_equal(res[1]["king_peer_root1"], O.king_robust_counts(g))
+    for rank in (0, 1):
         assert np.max(np.abs(res[rank]["gcta_after_gather"] - ref["GCTA"]) / np.maximum(np.abs(ref["GCTA"]), 1)) < 1e-10
         e, _ = O.ibd_mom_tables(g)
         r0, r1 = O.ibd_mom(O.ibs_counts(g), e, True)
