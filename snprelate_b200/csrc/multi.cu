@@ -604,6 +604,20 @@ int snprel_peer_reduce_open(snprel_ctx *c, int rank, int world, const void *hand
         ip->rank = rank;
         ip->ptr.assign(nb, std::vector<const void *>((size_t)world, nullptr));
         const unsigned char *hb = static_cast<const unsigned char *>(handles);
+        // mappings of allocations a peer has since replaced are closed before anything new is opened
+        for (size_t i = 0; i < ip->maps.size();) {
+            bool wanted = false;
+            for (size_t k = 0; k < nb && !wanted; k++)
+                for (int r = 0; r < world && !wanted; r++)
+                    wanted = r != rank && c->reduce_list[k].count > 0 &&
+                             memcmp(&ip->maps[i].h, hb + ((size_t)r * nb + k) * 64, 64) == 0;
+            if (wanted) {
+                i++;
+            } else {
+                cudaIpcCloseMemHandle(ip->maps[i].base);
+                ip->maps.erase(ip->maps.begin() + (long)i);
+            }
+        }
         for (size_t k = 0; k < nb; k++)
             for (int r = 0; r < world; r++) {
                 if (r == rank) {
