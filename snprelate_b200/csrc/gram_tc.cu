@@ -539,7 +539,21 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     if (!(c->debug_flags & 2u) && base_items < 8 * slots)
         parts = (int)std::min<int64_t>(std::min<int64_t>((8 * slots + base_items - 1) / base_items, 64),
                                        std::max(1, stages_total / 4));
-    if (c->debug_flags & 0xF00u) parts = (int)((c->debug_flags >> 8) & 15u);   // experiment: forced SNP segments per item
+    // Large tile grids: cut the SNP range into segments of ~1024 stages (131072 SNPs) and emit the items
+    // SEGMENT-MAJOR inside every super-tile, so that everything co-resident (and the next few waves)
+    // walks the same 8 MB slice of at most RB + CB genotype panels -- a working set the 126 MB L2 holds.
+    // Without it the ~74 resident items drift apart along their 1M-SNP walks and every panel is
+    // streamed from HBM again by every item (measured at 10k x 1M: 522 GB -> 64 GB of DRAM reads per
+    // step, SM clock under the power cap 1547 -> 1677 MHz, kernel -4 %; profiles/r02_notes.md).
+    bool seg_major = false;
+    if (!(c->debug_flags & 2u) && parts == 1 && !(c->debug_flags & 256u)) {
+        parts = std::max(1, (stages_total + 512) / 1024);
+        seg_major = parts > 1;
+    }
+    if (c->debug_flags & 0xF000u) {     // experiment: forced number of segments
+        parts = (int)((c->debug_flags >> 12) & 15u);
+        seg_major = parts > 1;
+    }
     std::vector<std::vector<int>> cuts(groups.size());   // stage boundaries, ascending, first 0, last stages_total
     const int CH = GRAM_CHUNK / SK;                        // stages per bound chunk
     for (size_t gi = 0; gi < groups.size(); gi++) {
@@ -613,7 +627,7 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
                 for (int tm = std::max(rb, tm_lo); tm < std::min(rb + RB, tm_hi); tm++)
                     for (int tn = std::max(cb, upper_only ? tm : 0); tn < std::min(cb + CB, nt); tn++) emit(tm, tn);
     };
-    if (c->debug_flags & 0xF00u) {    // experiment: SNP-segment-major inside every super-tile (co-resident items walk the same SNP range)
+    if (seg_major) {
         size_t nseg = 0;
         for (auto &cu : cuts) nseg = std::max(nseg, cu.size() - 1);
         for (int rb = tm_lo / RB * RB; rb < tm_hi; rb += RB)
@@ -635,7 +649,7 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     }
     if (items.empty()) return;
     // wave tail: the items that start last are cut in four, so the chip drains in quarter steps
-    if (!(c->debug_flags & 2u) && parts == 1 && (int64_t)items.size() > 4 * slots) {
+    if (!(c->debug_flags & 2u) && parts == 1 && !seg_major && (int64_t)items.size() > 4 * slots) {
         const size_t ntail = (size_t)(slots + slots / 2);
         std::vector<Item> tail(items.end() - ntail, items.end());
         items.resize(items.size() - ntail);

@@ -1,5 +1,5 @@
-"""K1 experiment knobs (snprel_debug_flags): 16 = 32-byte swizzled genotype boxes, 32 = no L2 promotion,
-64 = 256-byte L2 promotion, 128 = group-major item order.  Checks each variant against the oracle on a
+"""K1 experiment knobs (snprel_debug_flags): 16 = the round-1 16-byte genotype boxes (default: 32-byte swizzled), 32 = no L2 promotion,
+64 = 256-byte L2 promotion, 128 = group-major item order, 256 = no SNP segments (round-2 first half), 0xN000 = N segments.  Checks each variant against the oracle on a
 small problem, then times it at the bench size (or the size given).  `--one FLAGS N M` runs a single
 accumulate (for ncu)."""
 import os, sys
