@@ -383,6 +383,28 @@ def run_ours(args):
                   "ms_per_step": sm, "value": 0.5 * N_SAMP * N_SAMP * N_SNP / (sm * 1e-3), "unit": UNIT, "scaling": "strong",
                   "steps": 3, "warmup": 1}
 
+    # ---- extra: BASELINE configs 3 / 4 at full size under this clock (--gpus 4: snpgdsIBS 50k x 500k;
+    # --gpus 8: KING-robust 100k x 1M, packed-bit kernels and the tensor engine) ----
+    big = {}
+    pl = ctx.last_plan()
+    if not args.no_extra and world in (4, 8):
+        from snprelate_b200.configs import run_pair_config
+        ctx.close()
+        legs = [("config3_ibs_50k_x_500k", "ibs", 50000, 500000, "bits")] if world == 4 else \
+               [("config4_king_100k_x_1M_tensor", "king", 100000, 1000000, "tensor"),
+                ("config4_king_100k_x_1M_bits", "king", 100000, 1000000, "bits")]
+        for key, en, bn, bm, engine in legs:
+            bidx = O.scattered_samples(bn, 24, seed=7)
+            res, kept = run_pair_config(local, en, bn, bm, rank, world, engine, REDUCE, -1, MISS, bidx, True)
+            perr, pcnt = O.check_pair_rows(en, bidx, bm, kept, seed=SEED, miss_rate=MISS)
+            tt = torch.tensor([perr], dtype=torch.float64, device=dev)
+            tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
+            cc = torch.tensor([float(pcnt)], dtype=torch.float64, device=dev)
+            tdist.all_reduce(cc)
+            res["parity"] = {"scattered_samples": int(len(bidx)), "entries_checked": int(cc[0]), "max_abs_err": float(tt[0]),
+                             "ok": bool(float(tt[0]) < 1e-12)}
+            big[key] = res
+
     if rank != 0:
         if world > 1:
             tdist.destroy_process_group()
@@ -408,7 +430,6 @@ def run_ours(args):
                     "first_call_ms": eig_calls[0], "warm_call_ms": eig_calls[1],
                     "max_residual_over_lambda1": resid, "max_orthonormality_defect": ortho}
 
-    pl = ctx.last_plan()
     passes = {"digits_U": int(pl.digits), "digits_W": int(pl.digits_w), "frac_bits": int(pl.frac_bits),
               "frac_bits_W": int(pl.frac_bits_w),
               "tensor_passes_per_step": int(pl.digits) + int(pl.digits_w) + int(pl.digits_d)}
@@ -445,6 +466,7 @@ def run_ours(args):
     extra = {}
     if strong:
         extra["strong"] = strong
+    extra.update(big)
     if world > 1:
         extra["reduction"] = {"kind": REDUCE, "ms_last_step": reduce_ms[0], "link_bytes_this_rank": int(link_bytes[0])}
     if world == 1 and not args.no_extra:

@@ -709,3 +709,20 @@ def synth_geno(nsamp, nsnp, seed=20261017, maf_lo=0.05, maf_hi=0.5,
         g = (r >= th0[:, None]).astype(np.uint8) + (r >= th1[:, None]).astype(np.uint8)
         g = np.where(rm < thm, np.uint8(3), g).astype(np.uint8)
     return g
+
+
+def check_pair_rows(est_name, idx, n_snp, kept_rows, seed=20261017, miss_rate=0.005):
+    """Checker for snprelate_b200.configs.run_pair_config: `kept_rows` = [(a, [values (idx[a], idx[a:]) of
+    each result matrix])] against ibs_ave / king_robust of the scattered samples `idx` over ALL n_snp SNPs of
+    the synthetic data set.  Returns (max abs error, entries checked).  The results are exact rational
+    functions of exact integer counters, so the error is float64 rounding only."""
+    sub = synth_geno(0, n_snp, seed=seed, miss_rate=miss_rate, samples=idx)
+    refs = [ibs_ave(ibs_counts(sub))] if est_name == "ibs" else list(king_robust(king_robust_counts(sub)))
+    err, cnt = 0.0, 0
+    for a, vals in kept_rows:
+        for v, ref in zip(vals, refs):
+            d = np.abs(v - ref[a, a:])
+            if d.size:
+                err = max(err, float(np.nanmax(d)))
+            cnt += d.size
+    return err, cnt
