@@ -65,6 +65,18 @@ int snprel_geno_push_u8(snprel_ctx *ctx, const uint8_t *geno, int64_t cnt);
  * code 3 = missing; GDS dBit2 encoding) with `row_bytes` bytes per SNP row. */
 int snprel_geno_push_2b(snprel_ctx *ctx, const uint8_t *packed, int64_t cnt,
                         int64_t row_bytes);
+/* The same push without waiting for the copy (the reference double-buffers its block reader against
+ * the compute threads, src/dGenGWAS.cpp:1298-1324): the rows go out in chunks on a copy stream and the
+ * call returns at once.  `packed` must stay valid (pinned memory recommended) until the next call on
+ * this context returns.  snprel_pca / snprel_grm (Eigenstrat, GCTA, Corr, EIGMIX) / snprel_eigmix that
+ * follow consume the chunks as they arrive -- statistics, digit tables and tensor passes of a chunk
+ * run while later chunks are still crossing PCIe; the fixed-point format is chosen from the first
+ * chunk's statistics extrapolated with safety margins and verified against the true statistics at the
+ * end (on failure the ordinary path recomputes everything on the resident data; snprel_stream_stats
+ * counts both outcomes).  Every other entry point first waits for the copies (snprel_geno_wait). */
+int snprel_geno_push_2b_async(snprel_ctx *ctx, const uint8_t *packed, int64_t cnt, int64_t row_bytes);
+int snprel_geno_wait(snprel_ctx *ctx);
+int snprel_stream_stats(snprel_ctx *ctx, int64_t *streamed, int64_t *fallbacks);
 /* Append `cnt` SNPs straight from the payload of an uncompressed GDS dBit2 genotype node
  * (sample.order layout): one continuous LSB-first 2-bit stream, sample fastest, with NO per-row
  * padding, so rows are not byte aligned when n_samp % 4 != 0 (what CdSNPWorkSpace::snpRead

@@ -98,6 +98,9 @@ def load_library():
         "snprel_debug_flags": [p, u32],
         "snprel_set_count_engine": [p, i32],
         "snprel_set_rounding": [p, i32],
+        "snprel_geno_push_2b_async": [p, p, i64, i64],
+        "snprel_geno_wait": [p],
+        "snprel_stream_stats": [p, C.POINTER(i64), C.POINTER(i64)],
         "snprel_geno_seek": [p, i64],
         "snprel_geno_commit": [p, i64],
         "snprel_geno_device_rows": [p, C.POINTER(p), C.POINTER(i64), C.POINTER(i64)],
@@ -161,6 +164,7 @@ EXPORTED_SYMBOLS = [
     "snprel_multi_set_row_window", "snprel_multi_set_count_engine", "snprel_multi_accumulate", "snprel_multi_last_reduce",
     "snprel_geno_seek", "snprel_geno_device_rows", "snprel_geno_commit",
     "snprel_multi_geno_begin_replicated", "snprel_multi_geno_gather", "snprel_multi_grm_tiled",
+    "snprel_geno_push_2b_async", "snprel_geno_wait", "snprel_stream_stats",
     "snprel_reduce_ipc_export", "snprel_peer_reduce_open", "snprel_peer_reduce_phase", "snprel_peer_reduce_close",
 ]
 
@@ -238,6 +242,23 @@ class Context:
         if (int(first_snp) + int(cnt)) * n * 2 > stream.size * 8:
             raise SNPRelError("geno_push_bitstream: the stream is shorter than the requested SNP range")
         self._ck(self.lib.snprel_geno_push_bitstream(self.h, _ptr(stream), int(first_snp) * n, int(cnt)))
+
+    def geno_push_2b_async(self, packed):
+        """Queue the host-to-device copy and return; `packed` (ideally pinned) must stay alive until the next
+        call on this context returns.  A following pca() / grm() / eigmix() overlaps with the copy."""
+        if packed.dtype != np.uint8 or not packed.flags.c_contiguous or packed.ndim != 2:
+            raise SNPRelError("geno_push_2b_async: a C-contiguous uint8 [cnt, row_bytes] array is required (no copy is made)")
+        self._async_keepalive = packed
+        self._ck(self.lib.snprel_geno_push_2b_async(self.h, _ptr(packed), packed.shape[0], packed.shape[1]))
+
+    def geno_wait(self):
+        self._ck(self.lib.snprel_geno_wait(self.h))
+        self._async_keepalive = None
+
+    def stream_stats(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self.lib.snprel_stream_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def geno_seek(self, snp_index):
         self._ck(self.lib.snprel_geno_seek(self.h, int(snp_index)))

@@ -14,6 +14,17 @@ static std::string g_create_error;
     }                                                        \
     try {                                                    \
         cudaError_t _se = cudaSetDevice((ctx)->device);      \
+        if (_se != cudaSuccess) fail("cudaSetDevice(%d): %s", (ctx)->device, cudaGetErrorString(_se)); \
+        geno_wait(ctx);
+
+/* entry points that may consume host-to-device copies still in flight chunk by chunk (grm.cu) */
+#define API_BEGIN_STREAMING(ctx)                             \
+    if (!(ctx)) {                                            \
+        g_create_error = "NULL snprel_ctx";                  \
+        return 1;                                            \
+    }                                                        \
+    try {                                                    \
+        cudaError_t _se = cudaSetDevice((ctx)->device);      \
         if (_se != cudaSuccess) fail("cudaSetDevice(%d): %s", (ctx)->device, cudaGetErrorString(_se));
 
 #define API_END(ctx)                                         \
@@ -83,6 +94,11 @@ void snprel_destroy(snprel_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        for (auto &p : c->pending) cudaEventDestroy(p.ev);
+        cudaStreamDestroy(c->copy_stream);
+    }
     eigen_release(c);
     snprel_peer_reduce_close(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -110,6 +126,20 @@ int snprel_geno_push_2b(snprel_ctx *c, const uint8_t *packed, int64_t cnt, int64
 }
 int snprel_geno_push_bitstream(snprel_ctx *c, const uint8_t *stream, int64_t first_genotype, int64_t cnt) {
     API_BEGIN(c) geno_push_bitstream(c, stream, first_genotype, cnt);
+    API_END(c)
+}
+int snprel_geno_push_2b_async(snprel_ctx *c, const uint8_t *packed, int64_t cnt, int64_t row_bytes) {
+    API_BEGIN_STREAMING(c) geno_push_2b_async(c, packed, cnt, row_bytes);
+    API_END(c)
+}
+int snprel_geno_wait(snprel_ctx *c) {
+    API_BEGIN(c)
+    API_END(c)
+}
+int snprel_stream_stats(snprel_ctx *c, int64_t *streamed, int64_t *fallbacks) {
+    API_BEGIN_STREAMING(c)
+    if (streamed) *streamed = c->streamed_steps;
+    if (fallbacks) *fallbacks = c->stream_fallbacks;
     API_END(c)
 }
 int snprel_geno_seek(snprel_ctx *c, int64_t snp_index) {
@@ -216,7 +246,8 @@ int snprel_indiv_beta_counts(snprel_ctx *c, int32_t *out2) {
 
 // ---- covariance-type estimators --------------------------------------------
 int snprel_grm(snprel_ctx *c, int method, double *out, int packed, double *avg_out) {
-    API_BEGIN(c)
+    API_BEGIN_STREAMING(c)
+    if (method == SNPREL_GRM_INDIVBETA) geno_wait(c);
     switch (method) {
         case SNPREL_GRM_EIGENSTRAT:
         case SNPREL_GRM_GCTA:
@@ -229,12 +260,12 @@ int snprel_grm(snprel_ctx *c, int method, double *out, int packed, double *avg_o
 }
 int snprel_pca(snprel_ctx *c, int eigen_cnt, int bayesian, double *genmat, double *trace_xtx,
                double *trace_val, double *eigval, double *eigvec) {
-    API_BEGIN(c) pca_finish(c, eigen_cnt, bayesian, genmat, trace_xtx, trace_val, eigval, eigvec);
+    API_BEGIN_STREAMING(c) pca_finish(c, eigen_cnt, bayesian, genmat, trace_xtx, trace_val, eigval, eigvec);
     API_END(c)
 }
 int snprel_eigmix(snprel_ctx *c, int eigen_cnt, int diagadj, double *ibd, double *afreq, double *eigval,
                   double *eigvec) {
-    API_BEGIN(c)
+    API_BEGIN_STREAMING(c)
     if (diagadj != 0 && diagadj != 1) fail("'diagadj' must be TRUE or FALSE.");   // src/genEIGMIX.cpp:661-662
     eigmix_finish(c, eigen_cnt, diagadj, ibd, afreq, eigval, eigvec);
     API_END(c)

@@ -217,7 +217,14 @@ struct snprel_ctx {
 
     // eigen step (eigen.cu): persistent cuBLAS / cuSOLVER handles and what the last solve did
     void *eig_handles = nullptr;
-    void *ipc_peers = nullptr;   // multi.cu: peers' reduce buffers mapped through CUDA IPC (one process per GPU)
+    void *ipc_peers = nullptr;
+    // host-to-device copies still in flight (snprel_geno_push_2b_async): SNP rows [l0, l1) are valid once
+    // `ev` has fired on copy_stream.  The covariance accumulate consumes them chunk by chunk (grm.cu);
+    // every other entry point waits for all of them first (API_BEGIN).
+    struct PendingCopy { int64_t l0, l1; cudaEvent_t ev; };
+    std::vector<PendingCopy> pending;
+    cudaStream_t copy_stream = nullptr;
+    int64_t streamed_steps = 0, stream_fallbacks = 0;   // accumulates that consumed in-flight copies / that had to be redone   // multi.cu: peers' reduce buffers mapped through CUDA IPC (one process per GPU)
     int eig_solver = 0;          // 0 dense (Xsyevd), 1 Chebyshev-filtered subspace iteration
     int eig_rounds = 0, eig_gemms = 0;
     double eig_phase_ms[3] = {0, 0, 0};   // filter, orthonormalisation, Rayleigh-Ritz
@@ -277,6 +284,10 @@ void geno_synth(snprel_ctx *c, int64_t n_snp, uint64_t seed, double maf_lo, doub
 void geno_copy_u8(snprel_ctx *c, uint8_t *out);
 void geno_copy_2b(snprel_ctx *c, uint8_t *out, int64_t row_bytes);
 void geno_seek(snprel_ctx *c, int64_t snp_index);
+void snp_stats_range(snprel_ctx *c, int64_t l0, int64_t rows);
+void geno_push_2b_async(snprel_ctx *c, const uint8_t *host, int64_t cnt, int64_t row_bytes);
+void geno_wait(snprel_ctx *c);
+constexpr int64_t STREAM_CHUNK = 131072;   // SNP rows per in-flight copy chunk = one K1 segment (1024 stages)
 void geno_commit(snprel_ctx *c, int64_t n_snp);
 void geno_pad_tail(snprel_ctx *c);
 void ensure_stats(snprel_ctx *c);
@@ -311,7 +322,8 @@ struct GramPass {
 };
 const uint32_t *gram_const_table(snprel_ctx *c, uint32_t word);
 void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *out_planes,
-                 bool upper_only);
+                 bool upper_only, int64_t snp_lo = 0, int64_t snp_hi = -1, bool sync = true);
+void gram_tc_check(snprel_ctx *c);
 
 // grm.cu
 void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan);

@@ -188,6 +188,7 @@ __global__ void planes_kernel(const uint8_t *__restrict__ g, uint4 *__restrict__
 // host side
 // ---------------------------------------------------------------------------
 void geno_begin(snprel_ctx *c, int64_t n_samp, int64_t cap) {
+    geno_wait(c);
     if (n_samp <= 0) fail("snprel_geno_begin: n_samp must be positive");
     if (cap < 0) fail("snprel_geno_begin: negative SNP capacity");
     if (n_samp >= (1ll << 30)) fail("snprel_geno_begin: too many samples");
@@ -265,6 +266,52 @@ void geno_push_2b(snprel_ctx *c, const uint8_t *host, int64_t cnt, int64_t row_b
     CUDA_CHECK(cudaStreamSynchronize(c->stream));   // the host block may be reused by the caller
     c->n_snp += cnt;
     invalidate(c);
+}
+
+// The same push without waiting for the copies: the block goes out in chunks that end at multiples of
+// STREAM_CHUNK rows (the K1 segment) on a second stream, each followed by an event.  The host block must
+// stay valid (and should be pinned) until the next library call on this context returns.
+void geno_push_2b_async(snprel_ctx *c, const uint8_t *host, int64_t cnt, int64_t row_bytes_in) {
+    need_room(c, cnt, "snprel_geno_push_2b_async");
+    if (cnt == 0) return;
+    if (!host) fail("snprel_geno_push_2b_async: NULL block");
+    if (row_bytes_in < (c->n_samp + 3) / 4)
+        fail("snprel_geno_push_2b_async: row_bytes %lld too small for %lld samples", (long long)row_bytes_in,
+             (long long)c->n_samp);
+    if (!c->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    // anything queued on the compute stream that still reads these rows must finish first
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    const int64_t w = (c->n_samp + 3) / 4, pad_from = c->n_samp / 4, pad_bytes = c->row_bytes - pad_from;
+    for (int64_t l0 = c->n_snp, end = c->n_snp + cnt; l0 < end;) {
+        const int64_t l1 = std::min(end, (l0 / STREAM_CHUNK + 1) * STREAM_CHUNK), rows = l1 - l0;
+        uint8_t *dst = c->geno2b.p + l0 * c->row_bytes;
+        const uint8_t *src = host + (l0 - c->n_snp) * row_bytes_in;
+        if (row_bytes_in == c->row_bytes)
+            CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)rows * c->row_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        else
+            CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)c->row_bytes, src, (size_t)row_bytes_in, (size_t)w, (size_t)rows,
+                                         cudaMemcpyHostToDevice, c->copy_stream));
+        if (pad_bytes > 0) {
+            const int64_t total = rows * pad_bytes;
+            fix_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->copy_stream>>>(
+                dst, rows, c->n_samp, pad_from, pad_bytes, row_bytes_in == c->row_bytes ? c->row_bytes : w, c->row_bytes);
+            KERNEL_CHECK(c);
+        }
+        cudaEvent_t ev;
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventRecord(ev, c->copy_stream));
+        c->pending.push_back({l0, l1, ev});
+        l0 = l1;
+    }
+    c->n_snp += cnt;
+    invalidate(c);
+}
+
+void geno_wait(snprel_ctx *c) {
+    if (c->pending.empty()) return;
+    CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
+    for (auto &p : c->pending) cudaEventDestroy(p.ev);
+    c->pending.clear();
 }
 
 // GDS dBit2 payload (uncompressed genotype node of a SNP GDS file with sample.order): ONE continuous
@@ -388,6 +435,15 @@ void geno_copy_2b(snprel_ctx *c, uint8_t *out, int64_t row_bytes_out) {
     CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)row_bytes_out, c->geno2b.p, (size_t)c->row_bytes, (size_t)w,
                                  (size_t)c->n_snp, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+// per-SNP statistics of rows [l0, l0 + rows) only (streamed accumulate, grm.cu)
+void snp_stats_range(snprel_ctx *c, int64_t l0, int64_t rows) {
+    if (rows <= 0) return;
+    const int warps = 8;
+    snp_stat_kernel<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, c->stream>>>(
+        c->geno2b.p + l0 * c->row_bytes, c->stat.p + l0, rows, c->row_bytes, (int)c->n_samp_pad);
+    KERNEL_CHECK(c);
 }
 
 void ensure_stats(snprel_ctx *c) {

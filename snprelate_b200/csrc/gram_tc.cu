@@ -490,7 +490,8 @@ static int tile_ncols(int64_t nvalid) {
     return nvalid <= 128 ? 128 : 256;
 }
 
-void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *out_planes, bool upper_only) {
+void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *out_planes, bool upper_only,
+                 int64_t snp_lo, int64_t snp_hi, bool sync) {
     using namespace tc2;
     if (npass <= 0) return;
     geno_pad_tail(c);
@@ -499,7 +500,12 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     const RowWin win = row_window(c);
     const int tm_lo = (int)(win.r0 / TM2), tm_hi = (int)std::min<int64_t>(nt, (win.r1 + TM2 - 1) / TM2);
     if (tm_hi <= tm_lo) return;
-    const int stages_total = (int)(round_up(std::max<int64_t>(c->n_snp, 1), SK) / SK);
+    // SNP range of this launch (default: everything resident); boundaries are stage aligned
+    if (snp_hi < 0) snp_hi = c->n_snp;
+    if (snp_lo % SK) fail("internal: gram_tc_run range must start at a multiple of %d SNPs", SK);
+    const int st_lo = (int)(snp_lo / SK);
+    const int st_hi = (int)(round_up(std::max<int64_t>(snp_hi, snp_lo + 1), SK) / SK);
+    const int stages_total = st_hi - st_lo;
     const int64_t slots = std::max(1, c->num_sms / 2);
 
     // ---- pass groups: two passes that share a B table fill the two accumulators of a 256 x 256
@@ -559,15 +565,15 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     for (size_t gi = 0; gi < groups.size(); gi++) {
         const GramPass &ps = passes[groups[gi].pass[0]];
         std::vector<int> &cu = cuts[gi];
-        cu.push_back(0);
+        cu.push_back(st_lo);
         std::vector<int> want;                             // wished part boundaries, multiples of a chunk
         for (int k = 1; k < parts; k++) {
-            const int bnd = (int)((long long)k * stages_total / parts) / CH * CH;
-            if (bnd > 0 && bnd < stages_total && (want.empty() || bnd > want.back())) want.push_back(bnd);
+            const int bnd = (st_lo + (int)((long long)k * stages_total / parts)) / CH * CH;
+            if (bnd > st_lo && bnd < st_hi && (want.empty() || bnd > want.back())) want.push_back(bnd);
         }
         size_t wi = 0;
         long long acc = 0;
-        for (int st = 0; st < stages_total; st += CH) {
+        for (int st = st_lo / CH * CH; st < st_hi; st += CH) {
             const size_t ck = (size_t)(st / CH);
             long long cb = (ps.b_chunk_bound && ck < ps.b_chunk_bound->size())
                                ? std::min<long long>((*ps.b_chunk_bound)[ck], (long long)ps.b_abs_max * GRAM_CHUNK)
@@ -582,7 +588,7 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
             while (wi < want.size() && st >= want[wi]) wi++;
             acc += cb;
         }
-        cu.push_back(stages_total);
+        cu.push_back(st_hi);
     }
 
     // ---- the item list: tile-major (all pass groups of a tile are neighbours, so the co-resident
@@ -675,7 +681,7 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     CUDA_CHECK(cudaMemcpyAsync(c->scr_passes.p, pd.data(), pd.size() * sizeof(PassDesc), cudaMemcpyHostToDevice, c->stream));
     c->scr_flags.alloc(2);
     int *derr = c->scr_flags.p + 1;
-    CUDA_CHECK(cudaMemsetAsync(derr, 0, sizeof(int), c->stream));
+    if (sync || snp_lo == 0) CUDA_CHECK(cudaMemsetAsync(derr, 0, sizeof(int), c->stream));
 
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -726,9 +732,15 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     KERNEL_CHECK(c);
     c->hot_launches++;
     c->hot_items = (int64_t)items.size();
+    if (sync) gram_tc_check(c);
+}
+
+// wait for the launches queued so far and surface a pipeline time-out
+void gram_tc_check(snprel_ctx *c) {
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (!c->scr_flags.p) return;
     int herr = 0;
-    CUDA_CHECK(cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(&herr, c->scr_flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost));
     if (herr) fail("table_gram_kernel3: pipeline barrier %d timed out", herr);
 }
 

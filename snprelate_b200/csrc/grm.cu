@@ -891,6 +891,287 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
 }
 
 // ---------------------------------------------------------------------------
+// Streamed accumulate: the covariance path over host-to-device copies that are still in flight
+// (snprel_geno_push_2b_async).  The reference double-buffers its block reader against the compute
+// threads (CGenoReadBySNP, src/dGenGWAS.cpp:1298-1324); here the 2-bit matrix arrives in chunks of
+// STREAM_CHUNK SNP rows on a copy stream and every chunk is consumed as soon as its event has fired:
+// per-SNP statistics, column tables, plan statistics, per-sample statistics, digit tables, per-sample
+// vectors and the tensor passes of that SNP range -- all of them sums over SNPs that accumulate
+// across chunks.  The one thing that needs the whole matrix is the fixed-point FORMAT (it is chosen
+// from global statistics), so it is chosen speculatively from the first chunk's statistics
+// extrapolated to the full SNP count with safety margins, and verified at the end against the true
+// statistics (digit overflow flag, int64 headroom, error bound <= tol): on failure everything is
+// recomputed by the ordinary path on the now resident data.  Whole matrix (no row window) only.
+// ---------------------------------------------------------------------------
+static void prep_stats_range(snprel_ctx *c, int est, int bayesian, int64_t l0, int64_t l1, int64_t l1_pad) {
+    // per-SNP statistics (padding rows of the last chunk included: they read as all-missing)
+    snp_stats_range(c, l0, l1_pad - l0);
+    const int64_t n = l1 - l0;
+    if (n <= 0) return;
+    coltab_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->stat.p + l0, n, est, bayesian, c->scr_coltab.p + l0,
+                                                                   c->scr_tabb.p + l0, c->scr_tabb.p + c->snp_cap + l0);
+    KERNEL_CHECK(c);
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 1024);
+    plan_kernel<<<blocks, 256, 0, c->stream>>>(c->stat.p + l0, c->scr_coltab.p + l0, n, c->n_samp, est, bayesian, c->scr_plan.p);
+    KERNEL_CHECK(c);
+    const int64_t row_words = c->row_bytes / 4;
+    dim3 grid((unsigned)((row_words + SS_THREADS - 1) / SS_THREADS), (unsigned)((n + GRAM_CHUNK - 1) / GRAM_CHUNK));
+    sample_stats_kernel<<<grid, SS_THREADS, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(c->geno2b.p) + l0 * row_words,
+                                                           c->scr_tabb.p + c->snp_cap + l0, n, row_words, c->n_samp_pad,
+                                                           c->scr_ew.p, c->scr_cnt.p, c->scr_chunk.p + l0 / GRAM_CHUNK);
+    KERNEL_CHECK(c);
+}
+
+// plan statistics accumulated so far -> host
+static void read_plan_stats(snprel_ctx *c, int est, snprel_plan &plan, int64_t n_snp_seen) {
+    const int64_t npad = c->n_samp_pad;
+    double h[5];
+    c->host_cnt.resize((size_t)npad);
+    c->host_ew.resize((size_t)npad);
+    CUDA_CHECK(cudaMemcpyAsync(h, c->scr_plan.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->host_cnt.data(), c->scr_cnt.p + npad, (size_t)npad * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->host_ew.data(), c->scr_ew.p, (size_t)npad * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    long long ew = 0, mm = 0;
+    for (int64_t i = 0; i < c->n_samp; i++) {
+        ew = std::max(ew, c->host_ew[i]);
+        mm = std::max<long long>(mm, c->host_cnt[i]);
+    }
+    plan.max_abs = h[0];
+    plan.max_abs_w = h[4];
+    plan.sum_bound = h[1];
+    plan.total_missing = (int64_t)h[2];
+    plan.scale = (est == SNPREL_GRM_EIGENSTRAT) ? h[3] / (double)std::max<int64_t>(c->n_samp - 1, 1)
+                 : (est == SNPREL_GRM_GCTA)     ? 2.0 * h[3]
+                                                : h[3];
+    plan.err_weight = (double)ew;
+    plan.max_missing = mm;
+    plan.n_snp = n_snp_seen;
+}
+
+// true: accumulated (c->acc etc. hold the result, caches set); false: the caller must take the ordinary path
+static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
+    if (est == SNPREL_GRM_CORR) est = SNPREL_GRM_GCTA;
+    if (c->pending.empty() || !full_window(c) || c->round_mode != 0 || (c->debug_flags & 2u) || c->n_snp <= 0) return false;
+    std::vector<snprel_ctx::PendingCopy> chunks = c->pending;
+    for (size_t k = 0; k < chunks.size(); k++) {   // contiguous, chunk aligned, up to the last row
+        const int64_t expect = k ? chunks[k - 1].l1 : chunks[0].l0;
+        if (chunks[k].l0 != expect || (chunks[k].l0 % GRAM_CHUNK)) return false;
+    }
+    if (chunks.back().l1 != c->n_snp) return false;
+    const int64_t m = c->n_snp, cap = c->snp_cap, npad = c->n_samp_pad, first_l0 = chunks[0].l0;
+    if (chunks.back().l1 - first_l0 < 2 * STREAM_CHUNK) return false;      // nothing to overlap
+    CUDA_CHECK(cudaEventRecord(c->evs0, c->stream));
+    geno_pad_tail(c);
+
+    // accumulators of the statistics
+    c->scr_coltab.alloc((size_t)cap);
+    c->scr_tabb.alloc((size_t)2 * cap);
+    c->scr_tabb.zero(c->stream);
+    c->scr_plan.alloc(5);
+    c->scr_plan.zero(c->stream);
+    c->scr_cnt.alloc((size_t)2 * npad);
+    c->scr_cnt.zero(c->stream);
+    c->scr_ew.alloc((size_t)npad);
+    c->scr_ew.zero(c->stream);
+    const int64_t nchunk = (cap + GRAM_CHUNK - 1) / GRAM_CHUNK;
+    c->scr_chunk.alloc((size_t)nchunk);
+    c->scr_chunk.zero(c->stream);
+
+    // ---- first range: rows that were already resident plus the first chunk in flight -> speculative format
+    const int64_t m_pad = round_up(m, SNP_PAD);
+    auto pad_end = [&](int64_t l1) { return l1 == m ? m_pad : l1; };
+    CUDA_CHECK(cudaStreamWaitEvent(c->stream, chunks[0].ev, 0));
+    const int64_t a1 = chunks[0].l1;
+    prep_stats_range(c, est, bayesian, 0, a1, pad_end(a1));
+    snprel_plan plan{};
+    plan.frac_bits = plan.frac_bits_w = plan.frac_bits_d = -1;
+    plan.bayesian = bayesian;
+    read_plan_stats(c, est, plan, a1);
+    {
+        const double fac = (double)m / (double)a1;
+        plan.max_abs *= 2.0;                       // a later SNP may have a rarer allele
+        plan.max_abs_w *= 2.0;
+        plan.sum_bound *= fac * 1.05;
+        plan.err_weight *= fac * 1.08;
+        plan.max_missing = (int64_t)std::ceil((double)plan.max_missing * fac * 1.15 + 16.0);
+        plan.total_missing = (int64_t)((double)plan.total_missing * fac) + (m > a1 ? 1 : 0);
+        plan.scale *= fac * 0.95;                  // a LOWER bound of the normaliser
+        plan.n_snp = m;
+    }
+    int nU = 0, nW = 0, nD = 0;
+    choose_format(est, plan, nU, nW, nD, 0, (double)c->n_samp);
+    if (plan.total_missing > 0 && nW == 0) return false;
+    const int f = plan.frac_bits, fw = plan.frac_bits_w, fd = plan.frac_bits_d, fv = plan.frac_bits_v;
+    const int npass = nU + nW + nD;
+
+    DevBuf<uint32_t> &tab = c->scr_tab;
+    tab.alloc((size_t)std::max(npass, 1) * cap);
+    tab.zero(c->stream);
+    c->scalars.alloc(4);
+    c->scalars.zero(c->stream);
+    c->iscalars.alloc(4);
+    c->iscalars.zero(c->stream);
+    c->scr_flags.alloc(2);
+    c->scr_flags.zero(c->stream);
+    const int64_t tblocks_max = (m + 255) / 256 + (int64_t)chunks.size() + 1;
+    c->scr_part.alloc((size_t)tblocks_max * 2);
+    CUDA_CHECK(cudaMemsetAsync(c->scr_part.p, 0, (size_t)tblocks_max * 2 * sizeof(double), c->stream));
+    c->samp_sum.alloc((size_t)NVEC * npad);
+    c->samp_sum.zero(c->stream);
+    c->samp_vecs = NVEC;
+    const int nplanes = (nD > 0) ? 2 : 1;
+    c->acc.alloc((size_t)nplanes * npad * npad);
+    c->acc.zero(c->stream);
+    c->acc_planes = nplanes;
+
+    const uint32_t *tabB = c->scr_tabb.p;
+    const uint32_t *tabM = gram_const_table(c, TABB_M);
+    std::vector<GramPass> passes;
+    {
+        int pass = 0;
+        // |B| <= 127 and at most STREAM_CHUNK SNPs per item: 127 x 131072 x 128 < 2^31, no measured bound needed
+        for (int k = 0; k < nU; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, tabB, 0, 8 * k, 127, nullptr});
+        for (int k = 0; k < nW; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, tabM, 0, 8 * k + (f - fw), 1, nullptr});
+        for (int k = 0; k < nD; k++, pass++) passes.push_back({tab.p + (int64_t)pass * cap, tabM, 1, 8 * k, 1, nullptr});
+    }
+    const double qbits = (double)fv + 1.0 + std::log2(std::max(plan.max_abs_w, 1e-300));
+    const int64_t row_words = c->row_bytes / 4;
+    const uint32_t *g32 = reinterpret_cast<const uint32_t *>(c->geno2b.p);
+    int64_t tblock0 = 0;
+    c->hot_launches = 0;
+    CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+    auto consume = [&](int64_t l0, int64_t l1) {
+        const int64_t n = l1 - l0;
+        const unsigned tb = (unsigned)((n + 255) / 256);
+        tables_kernel<<<tb, 256, 0, c->stream>>>(c->stat.p + l0, c->scr_coltab.p + l0, n, cap, est, bayesian, f, fw, fd, fv, nU, nW, nD, 0,
+                                                 tab.p + l0, c->scr_part.p + 2 * tblock0, c->iscalars.p, c->scr_flags.p, 0ull);
+        KERNEL_CHECK(c);
+        tblock0 += tb;
+        dim3 grid((unsigned)((row_words + 31) / 32), (unsigned)((n + SV_ROWS - 1) / SV_ROWS));
+        if (qbits < 38.0)
+            sample_vec_kernel<2><<<grid, SV_THREADS, 0, c->stream>>>(g32 + l0 * row_words, c->stat.p + l0, c->scr_coltab.p + l0, n, c->n_samp,
+                                                                    row_words, npad, est, bayesian, fd, fv, c->samp_sum.p);
+        else
+            sample_vec_kernel<3><<<grid, SV_THREADS, 0, c->stream>>>(g32 + l0 * row_words, c->stat.p + l0, c->scr_coltab.p + l0, n, c->n_samp,
+                                                                    row_words, npad, est, bayesian, fd, fv, c->samp_sum.p);
+        KERNEL_CHECK(c);
+        gram_tc_run(c, passes.data(), (int)passes.size(), c->acc.p, true, l0, l1, false);
+    };
+    consume(0, a1);
+    for (size_t k = 1; k < chunks.size(); k++) {
+        CUDA_CHECK(cudaStreamWaitEvent(c->stream, chunks[k].ev, 0));
+        prep_stats_range(c, est, bayesian, chunks[k].l0, chunks[k].l1, pad_end(chunks[k].l1));
+        consume(chunks[k].l0, chunks[k].l1);
+    }
+    CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
+    het_to_vec_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, c->stream>>>(c->scr_cnt.p, c->samp_sum.p, npad);
+    KERNEL_CHECK(c);
+    gram_tc_check(c);           // waits for everything queued
+    geno_wait(c);               // the copies are done (their events were waited on): drop them
+
+    // ---- verification against the true statistics
+    snprel_plan truth{};
+    truth.frac_bits = truth.frac_bits_w = truth.frac_bits_d = -1;
+    truth.bayesian = bayesian;
+    read_plan_stats(c, est, truth, m);
+    int hovf = 0;
+    const unsigned tblocks = (unsigned)tblock0;
+    std::vector<double> part((size_t)tblocks * 2);
+    CUDA_CHECK(cudaMemcpyAsync(&hovf, c->scr_flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(part.data(), c->scr_part.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<int> hchunk((size_t)((m + GRAM_CHUNK - 1) / GRAM_CHUNK));
+    CUDA_CHECK(cudaMemcpyAsync(hchunk.data(), c->scr_chunk.p, hchunk.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    bool ok = hovf == 0;
+    {
+        // the format that was used must satisfy the ordinary criterion under the true statistics
+        const double tol = (truth.tol > 0 ? truth.tol : 1e-10) * 0.9;
+        double scale = truth.scale;
+        if (est == SNPREL_GRM_GCTA) scale -= 4.0 * (double)truth.max_missing;
+        if (est == SNPREL_GRM_EIGMIX) scale -= 2.0 * (double)truth.max_missing;
+        scale = std::max(scale, 0.05 * truth.scale);
+        const double budget = tol * std::max(scale, 1e-300);
+        const int head = 61 - (int)std::ceil(std::log2(std::max(truth.sum_bound, 1.0)));
+        double err = std::ldexp(truth.err_weight, -(f + 1));
+        if (truth.total_missing > 0) err += nW > 0 ? std::ldexp((double)truth.max_missing, -(fw + 1)) : 1e300;
+        ok = ok && err <= budget && f <= head;
+        if (truth.total_missing > 0 && est == SNPREL_GRM_GCTA) ok = ok && nD == 1;
+        if (truth.total_missing > 0 && est == SNPREL_GRM_EIGMIX)
+            ok = ok && nD > 0 && std::ldexp(2.0 * (double)truth.max_missing, -(fd + 1)) <= budget;
+        // the per-sample vector's format
+        ok = ok && 1.5 * (double)m * std::ldexp(1.0, -fv) <= 0.05 * budget / 0.9 * 1.0001;
+    }
+    if (!ok) {
+        c->stream_fallbacks++;
+        c->plan_cache.version = 0;
+        c->prep_cache.version = 0;
+        c->stat_valid = false;
+        c->coltab_version = 0;
+        return false;
+    }
+    double hsc[4] = {0, 0, 0, 0};
+    for (unsigned b = 0; b < tblocks; b++) {
+        hsc[0] += part[2 * b];
+        hsc[1] += part[2 * b + 1];
+    }
+    CUDA_CHECK(cudaMemcpyAsync(c->scalars.p, hsc, sizeof(hsc), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+
+    // ---- the state an ordinary plan + accumulate leaves behind
+    plan.max_abs = truth.max_abs;
+    plan.max_abs_w = truth.max_abs_w;
+    plan.sum_bound = truth.sum_bound;
+    plan.err_weight = truth.err_weight;
+    plan.scale = truth.scale;
+    plan.total_missing = truth.total_missing;
+    plan.max_missing = truth.max_missing;
+    plan.n_snp = m;
+    plan.digits = nU;
+    plan.digits_w = nW;
+    plan.digits_d = nD;
+    c->plan = plan;
+    c->chunk_bound.assign(hchunk.begin(), hchunk.end());
+    c->stat_valid = true;
+    c->coltab_version = c->geno_version;
+    c->coltab_est = est;
+    c->coltab_bayesian = bayesian;
+    c->plan_cache.version = c->geno_version;
+    c->plan_cache.est = est;
+    c->plan_cache.bayesian = bayesian;
+    c->plan_cache.stats = truth;
+    snprel_ctx::PrepCache &pc = c->prep_cache;
+    pc.version = c->geno_version;
+    pc.est = est;
+    pc.bayesian = bayesian;
+    pc.f = f; pc.fw = fw; pc.fd = fd; pc.fv = fv;
+    pc.nU = nU; pc.nW = nW; pc.nD = nD; pc.nD2 = 0;
+    pc.round_mode = 0;
+    pc.reduced = false;
+    float ms = 0, total = 0;
+    CUDA_CHECK(cudaEventRecord(c->evs1, c->stream));
+    CUDA_CHECK(cudaEventSynchronize(c->evs1));
+    CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    CUDA_CHECK(cudaEventElapsedTime(&total, c->evs0, c->evs1));
+    c->hot_ms = ms;            // first tensor pass queued -> last one done (includes waiting for copies)
+    c->step_ms = total;
+    c->hot_units = 0.5 * (double)c->n_samp * (double)c->n_samp * (double)m;
+    c->accum_win_r0 = 0;
+    c->accum_win_rows = row_window(c).rows;
+    c->accum_bayesian = bayesian ? 1 : 0;
+    c->accum_est = est;
+    c->accum_reduced = false;
+    c->streamed_steps++;
+    c->reduce_list.clear();
+    c->reduce_list.push_back({c->acc.p, (int64_t)nplanes * npad * npad, 0, npad, npad, 0});
+    c->reduce_list.push_back({c->samp_sum.p, (int64_t)c->samp_sum.n, 0});
+    c->reduce_list.push_back({c->scalars.p, (int64_t)c->scalars.n, 2});
+    c->reduce_list.push_back({c->iscalars.p, (int64_t)c->iscalars.n, 0});
+    c->reduce_list.push_back({c->scr_cnt.p, (int64_t)c->scr_cnt.n, 1});
+    return true;
+}
+
+// ---------------------------------------------------------------------------
 // epilogues
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void store_sym2(double *out, int packed, int64_t n, int64_t i, int64_t j,
@@ -1025,6 +1306,9 @@ static void need_grm_accum(snprel_ctx *c, int est, int bayesian) {
                  c->accum_bayesian ? "TRUE" : "FALSE");
         return;
     }
+    // copies still in flight: consume them chunk by chunk (or wait and take the ordinary path)
+    if (!c->pending.empty() && grm_accumulate_streamed(c, est, bayesian)) return;
+    geno_wait(c);
     snprel_plan plan{};
     plan.frac_bits = -1;
     plan.frac_bits_w = -1;

@@ -45,23 +45,82 @@ struct PeerSrc {
     int n;
 };
 
-// dst[idx] (+)= sum_k src.p[k][idx] over rows [ra, rb) of every plane; live columns only
+// dst[idx] (+)= sum_k src.p[k][idx] over rows [ra, rb) of every plane; live columns only.
+// 16-byte peer loads, four independent vectors per thread in flight (the loads cross NVLink: latency,
+// not issue, is what has to be covered); ld and the first live column are multiples of 256 elements, so
+// every row segment is 16-byte aligned.
+template <class T>
+struct Vec16 {
+    static constexpr int N = 16 / sizeof(T);
+    T v[N];
+};
+template <class T>
+__device__ __forceinline__ Vec16<T> ld16(const T *p) {
+    Vec16<T> r;
+    const uint4 u = *reinterpret_cast<const uint4 *>(p);
+    memcpy(r.v, &u, 16);
+    return r;
+}
+template <class T>
+__device__ __forceinline__ void st16(T *p, const Vec16<T> &r) {
+    uint4 u;
+    memcpy(&u, r.v, 16);
+    *reinterpret_cast<uint4 *>(p) = u;
+}
+
 template <class T, bool ASSIGN>
 __global__ void __launch_bounds__(256)
 peer_reduce_kernel(T *__restrict__ dst, const PeerSrc<T> src, int64_t count, int64_t ld, int64_t rows, int64_t row0,
                    int tri, int64_t ra, int64_t rb, int planes) {
+    constexpr int V = Vec16<T>::N, U = 4;
     const int64_t r = ra + blockIdx.x;
     if (r >= rb) return;
     const int64_t c0 = tri ? ((row0 + r) & ~255ll) : 0;
     for (int p = blockIdx.y; p < planes; p += gridDim.y) {
         const int64_t base = ((int64_t)p * rows + r) * ld;
-        for (int64_t c = c0 + threadIdx.x; c < ld; c += blockDim.x) {
-            const int64_t idx = base + c;
-            if (idx >= count) break;
-            T v = ASSIGN ? T(0) : dst[idx];
-#pragma unroll 4
-            for (int k = 0; k < src.n; k++) v += src.p[k][idx];
-            dst[idx] = v;
+        const int64_t end = min(ld, count - base);            // elements of this row that exist
+        const int64_t nvec = end > c0 ? (end - c0) / V : 0;
+        for (int64_t i0 = (int64_t)threadIdx.x; i0 < nvec; i0 += (int64_t)blockDim.x * U) {
+            Vec16<T> acc[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int64_t i = i0 + (int64_t)u * blockDim.x;
+                if (i < nvec) {
+                    if (ASSIGN) {
+#pragma unroll
+                        for (int e = 0; e < V; e++) acc[u].v[e] = T(0);
+                    } else {
+                        acc[u] = ld16(dst + base + c0 + i * V);
+                    }
+                }
+            }
+            for (int k = 0; k < src.n; k++) {
+                Vec16<T> x[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int64_t i = i0 + (int64_t)u * blockDim.x;
+                    if (i < nvec) x[u] = ld16(src.p[k] + base + c0 + i * V);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int64_t i = i0 + (int64_t)u * blockDim.x;
+                    if (i < nvec) {
+#pragma unroll
+                        for (int e = 0; e < V; e++) acc[u].v[e] += x[u].v[e];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int64_t i = i0 + (int64_t)u * blockDim.x;
+                if (i < nvec) st16(dst + base + c0 + i * V, acc[u]);
+            }
+        }
+        // scalar tail of a dense buffer whose length is not a multiple of the vector
+        for (int64_t c = c0 + nvec * V + threadIdx.x; c < end; c += blockDim.x) {
+            T v = ASSIGN ? T(0) : dst[base + c];
+            for (int k = 0; k < src.n; k++) v += src.p[k][base + c];
+            dst[base + c] = v;
         }
     }
 }

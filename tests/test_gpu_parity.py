@@ -585,3 +585,74 @@ def test_randomized_pca_through_the_api(gds, hapmap):
     assert abs(r["TraceXTX"] - 2.0 * 0.5 * e["TraceXTX"]) / e["TraceXTX"] < 1e-12   # 2 x sum y^2 with y = z / sqrt(2)
     with pytest.raises(S.SNPRelError):
         S.snpgdsPCA(gds, algorithm="fast")
+
+
+def _pack2b(g, pitch):
+    """uint8 [m, n] codes -> 2-bit rows (4 per byte, LSB first) with `pitch` bytes per row, padding = missing"""
+    m, n = g.shape
+    q = np.full((m, pitch * 4), 3, dtype=np.uint8)
+    q[:, :n] = g
+    q = q.reshape(m, pitch, 4)
+    return np.ascontiguousarray(q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6))
+
+
+@pytest.mark.parametrize("pitch_pad", [0, 7])
+def test_streamed_ingest_matches_the_blocking_path(pitch_pad):
+    """snprel_geno_push_2b_async + snprel_pca / snprel_grm: the copy chunks are consumed while later chunks
+    are in flight, with a speculative fixed-point format verified at the end.  Exact integer planes and the
+    same epilogue: the result must equal the blocking path's bit for bit whenever the format agrees, and the
+    oracle to 1e-10 in any case."""
+    import torch
+    n, m = 520, 131072 * 3 + 4321                  # four copy chunks, the last one ragged
+    g = O.synth_geno(n, m, seed=77, miss_rate=0.01)
+    pitch = (n + 3) // 4 + pitch_pad
+    host = torch.from_numpy(_pack2b(g, pitch)).pin_memory()
+    idx = O.scattered_samples(n, 40, seed=3)
+    with S.Context(0) as c:
+        c.geno_begin(n, m)
+        c.geno_push_2b(host.numpy())
+        ref = c.pca(genmat_only=True)
+        plan_ref = c.last_plan()
+        gcta_ref = c.grm("GCTA")[0]
+        c.geno_begin(n, m)
+        c.geno_push_2b_async(host.numpy())
+        got = c.pca(genmat_only=True)
+        plan = c.last_plan()
+        assert c.stream_stats() == (1, 0)
+        if (plan.digits, plan.digits_w, plan.frac_bits, plan.frac_bits_w) == (plan_ref.digits, plan_ref.digits_w, plan_ref.frac_bits, plan_ref.frac_bits_w):
+            assert np.array_equal(got["genmat"], ref["genmat"])
+        assert relerr(got["genmat"], ref["genmat"]) < 1e-11 and abs(got["TraceXTX"] - ref["TraceXTX"]) <= 1e-12 * ref["TraceXTX"]
+        af, _, _ = c.snp_ratefreq()
+        sub = g[:, idx]
+        oref = O.subset_entries(sub, af, "Eigenstrat", n_total=n, trace=got["TraceXTX"])
+        assert relerr(got["genmat"][np.ix_(idx, idx)], oref) < TOL
+        # GCTA (one more plane for the missing-pair denominators) and a second use of the same context
+        c.geno_begin(n, m)
+        c.geno_push_2b_async(host.numpy())
+        assert relerr(c.grm("GCTA")[0], gcta_ref) < 1e-11
+        assert c.stream_stats() == (2, 0)
+        # any other entry point simply waits for the copies
+        c.geno_begin(n, m)
+        c.geno_push_2b_async(host.numpy())
+        assert np.array_equal(np.stack([a[np.ix_(idx, idx)] for a in c.ibs_num()]), O.ibs_counts(sub))
+
+
+def test_streamed_ingest_falls_back_when_the_guess_fails():
+    """Later chunks with much rarer alleles than the first one: the speculative format overflows its digits,
+    the verification notices and the ordinary path recomputes the result."""
+    import torch
+    n, m1 = 300, 131072
+    g1 = O.synth_geno(n, m1, seed=5, miss_rate=0.0, maf_lo=0.3, maf_hi=0.5)
+    g2 = O.synth_geno(n, 2 * m1, seed=6, miss_rate=0.02, maf_lo=0.002, maf_hi=0.01)
+    g = np.concatenate([g1, g2])
+    keep = O.select_snp_base(g, True, float("nan"), float("nan"))
+    keep[:m1] = True
+    g = np.ascontiguousarray(g[keep])
+    host = torch.from_numpy(_pack2b(g, (n + 3) // 4)).pin_memory()
+    with S.Context(0) as c:
+        c.geno_begin(n, g.shape[0])
+        c.geno_push_2b_async(host.numpy())
+        got = c.grm("GCTA")[0]
+        streamed, fallbacks = c.stream_stats()
+        assert streamed + fallbacks == 1
+        assert relerr(got, O.grm_gcta(g)) < TOL
