@@ -165,7 +165,7 @@ int snprel_geno_synth(snprel_ctx *c, int64_t n_snp, uint64_t seed, double maf_lo
     API_END(c)
 }
 int snprel_geno_dim(snprel_ctx *c, int64_t *n_samp, int64_t *n_snp) {
-    API_BEGIN(c)
+    API_BEGIN_STREAMING(c)      // (reads two integers: copies in flight are not waited for)
     if (n_samp) *n_samp = c->n_samp;
     if (n_snp) *n_snp = c->n_snp;
     API_END(c)
@@ -417,7 +417,7 @@ int snprel_set_row_window(snprel_ctx *c, int64_t row0, int64_t rows) {
     API_END(c)
 }
 int snprel_mem_info(snprel_ctx *c, int64_t *free_bytes, int64_t *total_bytes) {
-    API_BEGIN(c)
+    API_BEGIN_STREAMING(c)
     size_t f = 0, t = 0;
     CUDA_CHECK(cudaMemGetInfo(&f, &t));
     if (free_bytes) *free_bytes = (int64_t)f;
@@ -425,7 +425,7 @@ int snprel_mem_info(snprel_ctx *c, int64_t *free_bytes, int64_t *total_bytes) {
     API_END(c)
 }
 int snprel_window_count(snprel_ctx *c, int64_t *count) {
-    API_BEGIN(c)
+    API_BEGIN_STREAMING(c)
     if (c->n_samp <= 0) fail("snprel_window_count: no genotype workspace");
     if (count) *count = (int64_t)window_packed_count(c);
     API_END(c)
