@@ -221,7 +221,7 @@ struct snprel_ctx {
     // host-to-device copies still in flight (snprel_geno_push_2b_async): SNP rows [l0, l1) are valid once
     // `ev` has fired on copy_stream.  The covariance accumulate consumes them chunk by chunk (grm.cu);
     // every other entry point waits for all of them first (API_BEGIN).
-    struct PendingCopy { int64_t l0, l1; cudaEvent_t ev; };
+    struct PendingCopy { int64_t l0, l1; cudaEvent_t ev; int64_t copied; bool consumed = false; };   // copied: bytes per row the host copy covered (-1: no padding to fix)
     std::vector<PendingCopy> pending;
     cudaStream_t copy_stream = nullptr;
     int64_t streamed_steps = 0, stream_fallbacks = 0;   // accumulates that consumed in-flight copies / that had to be redone   // multi.cu: peers' reduce buffers mapped through CUDA IPC (one process per GPU)
@@ -287,6 +287,7 @@ void geno_seek(snprel_ctx *c, int64_t snp_index);
 void snp_stats_range(snprel_ctx *c, int64_t l0, int64_t rows);
 void geno_push_2b_async(snprel_ctx *c, const uint8_t *host, int64_t cnt, int64_t row_bytes);
 void geno_wait(snprel_ctx *c);
+void geno_fix_chunk_padding(snprel_ctx *c, const snprel_ctx::PendingCopy &p);
 constexpr int64_t STREAM_CHUNK = 131072;   // SNP rows per in-flight copy chunk = one K1 segment (1024 stages)
 void geno_commit(snprel_ctx *c, int64_t n_snp);
 void geno_pad_tail(snprel_ctx *c);

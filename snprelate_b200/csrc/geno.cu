@@ -281,7 +281,7 @@ void geno_push_2b_async(snprel_ctx *c, const uint8_t *host, int64_t cnt, int64_t
     if (!c->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     // anything queued on the compute stream that still reads these rows must finish first
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    const int64_t w = (c->n_samp + 3) / 4, pad_from = c->n_samp / 4, pad_bytes = c->row_bytes - pad_from;
+    const int64_t w = (c->n_samp + 3) / 4, pad_bytes = c->row_bytes - c->n_samp / 4;
     for (int64_t l0 = c->n_snp, end = c->n_snp + cnt; l0 < end;) {
         const int64_t l1 = std::min(end, (l0 / STREAM_CHUNK + 1) * STREAM_CHUNK), rows = l1 - l0;
         uint8_t *dst = c->geno2b.p + l0 * c->row_bytes;
@@ -291,26 +291,37 @@ void geno_push_2b_async(snprel_ctx *c, const uint8_t *host, int64_t cnt, int64_t
         else
             CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)c->row_bytes, src, (size_t)row_bytes_in, (size_t)w, (size_t)rows,
                                          cudaMemcpyHostToDevice, c->copy_stream));
-        if (pad_bytes > 0) {
-            const int64_t total = rows * pad_bytes;
-            fix_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->copy_stream>>>(
-                dst, rows, c->n_samp, pad_from, pad_bytes, row_bytes_in == c->row_bytes ? c->row_bytes : w, c->row_bytes);
-            KERNEL_CHECK(c);
-        }
+        // (the padding bytes of the rows are rewritten by whoever consumes the chunk, on the compute stream:
+        //  a kernel on the copy stream would queue behind the resident tensor-pass CTAs and stall the copies)
         cudaEvent_t ev;
         CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventRecord(ev, c->copy_stream));
-        c->pending.push_back({l0, l1, ev});
+        c->pending.push_back({l0, l1, ev, pad_bytes > 0 ? (row_bytes_in == c->row_bytes ? c->row_bytes : w) : (int64_t)-1});
         l0 = l1;
     }
     c->n_snp += cnt;
     invalidate(c);
 }
 
+// padding bytes of an arrived chunk (compute stream; the caller has ordered it after the chunk's event)
+void geno_fix_chunk_padding(snprel_ctx *c, const snprel_ctx::PendingCopy &p) {
+    if (p.copied < 0) return;
+    const int64_t pad_from = c->n_samp / 4, pad_bytes = c->row_bytes - pad_from, rows = p.l1 - p.l0;
+    const int64_t total = rows * pad_bytes;
+    if (total <= 0) return;
+    fix_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->geno2b.p + p.l0 * c->row_bytes, rows, c->n_samp,
+                                                                         pad_from, pad_bytes, p.copied, c->row_bytes);
+    KERNEL_CHECK(c);
+}
+
 void geno_wait(snprel_ctx *c) {
     if (c->pending.empty()) return;
     CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
-    for (auto &p : c->pending) cudaEventDestroy(p.ev);
+    for (auto &p : c->pending) {
+        if (!p.consumed) geno_fix_chunk_padding(c, p);
+        cudaEventDestroy(p.ev);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
     c->pending.clear();
 }
 

@@ -982,6 +982,8 @@ static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
     const int64_t m_pad = round_up(m, SNP_PAD);
     auto pad_end = [&](int64_t l1) { return l1 == m ? m_pad : l1; };
     CUDA_CHECK(cudaStreamWaitEvent(c->stream, chunks[0].ev, 0));
+    geno_fix_chunk_padding(c, chunks[0]);
+    c->pending[0].consumed = true;
     const int64_t a1 = chunks[0].l1;
     prep_stats_range(c, est, bayesian, 0, a1, pad_end(a1));
     snprel_plan plan{};
@@ -1061,6 +1063,8 @@ static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
     consume(0, a1);
     for (size_t k = 1; k < chunks.size(); k++) {
         CUDA_CHECK(cudaStreamWaitEvent(c->stream, chunks[k].ev, 0));
+        geno_fix_chunk_padding(c, chunks[k]);
+        c->pending[k].consumed = true;
         prep_stats_range(c, est, bayesian, chunks[k].l0, chunks[k].l1, pad_end(chunks[k].l1));
         consume(chunks[k].l0, chunks[k].l1);
     }
