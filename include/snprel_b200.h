@@ -77,6 +77,8 @@ int snprel_geno_push_2b(snprel_ctx *ctx, const uint8_t *packed, int64_t cnt,
 int snprel_geno_push_2b_async(snprel_ctx *ctx, const uint8_t *packed, int64_t cnt, int64_t row_bytes);
 int snprel_geno_wait(snprel_ctx *ctx);
 int snprel_stream_stats(snprel_ctx *ctx, int64_t *streamed, int64_t *fallbacks);
+/* device time from the first asynchronous copy chunk being queued to the last one having arrived */
+int snprel_stream_last_copy_ms(snprel_ctx *ctx, double *ms);
 /* Append `cnt` SNPs straight from the payload of an uncompressed GDS dBit2 genotype node
  * (sample.order layout): one continuous LSB-first 2-bit stream, sample fastest, with NO per-row
  * padding, so rows are not byte aligned when n_samp % 4 != 0 (what CdSNPWorkSpace::snpRead

@@ -97,10 +97,12 @@ void snprel_destroy(snprel_ctx *c) {
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         for (auto &p : c->pending) cudaEventDestroy(p.ev);
+        if (c->copy_ev0) cudaEventDestroy(c->copy_ev0);
         cudaStreamDestroy(c->copy_stream);
     }
     eigen_release(c);
     snprel_peer_reduce_close(c);
+    if (c->stage_host) cudaFreeHost(c->stage_host);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->evs0) cudaEventDestroy(c->evs0);
@@ -140,6 +142,11 @@ int snprel_stream_stats(snprel_ctx *c, int64_t *streamed, int64_t *fallbacks) {
     API_BEGIN_STREAMING(c)
     if (streamed) *streamed = c->streamed_steps;
     if (fallbacks) *fallbacks = c->stream_fallbacks;
+    API_END(c)
+}
+int snprel_stream_last_copy_ms(snprel_ctx *c, double *ms) {
+    API_BEGIN_STREAMING(c)
+    if (ms) *ms = c->last_copy_ms;
     API_END(c)
 }
 int snprel_geno_seek(snprel_ctx *c, int64_t snp_index) {

@@ -175,7 +175,9 @@ struct snprel_ctx {
     snprel::DevBuf<uint32_t> scr_tab;     // digit tables [npass][snp_cap]
     snprel::DevBuf<int> scr_flags;        // [0] digit overflow, [1] pipeline error
     snprel::DevBuf<double> scr_plan;      // plan statistics [3]
-    snprel::DevBuf<uint8_t> scr_items, scr_passes;   // K1 work items / pass descriptors
+    snprel::DevBuf<uint8_t> scr_items, scr_passes;   // K1 work items / pass descriptors (slices, see gram_tc_run)
+    uint8_t *stage_host = nullptr;        // mapped pinned staging of the same slices
+    size_t stage_bytes = 0, stage_used = 0;
     struct ConstTab {
         uint32_t word = 0;
         snprel::DevBuf<uint32_t> buf;
@@ -224,6 +226,8 @@ struct snprel_ctx {
     struct PendingCopy { int64_t l0, l1; cudaEvent_t ev; int64_t copied; bool consumed = false; };   // copied: bytes per row the host copy covered (-1: no padding to fix)
     std::vector<PendingCopy> pending;
     cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev0 = nullptr;
+    double last_copy_ms = 0;     // first async copy chunk queued -> last one arrived
     int64_t streamed_steps = 0, stream_fallbacks = 0;   // accumulates that consumed in-flight copies / that had to be redone   // multi.cu: peers' reduce buffers mapped through CUDA IPC (one process per GPU)
     int eig_solver = 0;          // 0 dense (Xsyevd), 1 Chebyshev-filtered subspace iteration
     int eig_rounds = 0, eig_gemms = 0;

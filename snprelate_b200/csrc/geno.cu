@@ -282,6 +282,8 @@ void geno_push_2b_async(snprel_ctx *c, const uint8_t *host, int64_t cnt, int64_t
     // anything queued on the compute stream that still reads these rows must finish first
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     const int64_t w = (c->n_samp + 3) / 4, pad_bytes = c->row_bytes - c->n_samp / 4;
+    if (!c->copy_ev0) CUDA_CHECK(cudaEventCreate(&c->copy_ev0));
+    if (c->pending.empty()) CUDA_CHECK(cudaEventRecord(c->copy_ev0, c->copy_stream));
     for (int64_t l0 = c->n_snp, end = c->n_snp + cnt; l0 < end;) {
         const int64_t l1 = std::min(end, (l0 / STREAM_CHUNK + 1) * STREAM_CHUNK), rows = l1 - l0;
         uint8_t *dst = c->geno2b.p + l0 * c->row_bytes;
@@ -294,7 +296,7 @@ void geno_push_2b_async(snprel_ctx *c, const uint8_t *host, int64_t cnt, int64_t
         // (the padding bytes of the rows are rewritten by whoever consumes the chunk, on the compute stream:
         //  a kernel on the copy stream would queue behind the resident tensor-pass CTAs and stall the copies)
         cudaEvent_t ev;
-        CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreate(&ev));
         CUDA_CHECK(cudaEventRecord(ev, c->copy_stream));
         c->pending.push_back({l0, l1, ev, pad_bytes > 0 ? (row_bytes_in == c->row_bytes ? c->row_bytes : w) : (int64_t)-1});
         l0 = l1;
@@ -317,6 +319,10 @@ void geno_fix_chunk_padding(snprel_ctx *c, const snprel_ctx::PendingCopy &p) {
 void geno_wait(snprel_ctx *c) {
     if (c->pending.empty()) return;
     CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
+    {   // span of the copies: first chunk queued -> last chunk arrived
+        float ms = 0;
+        if (c->copy_ev0 && cudaEventElapsedTime(&ms, c->copy_ev0, c->pending.back().ev) == cudaSuccess) c->last_copy_ms = ms;
+    }
     for (auto &p : c->pending) {
         if (!p.consumed) geno_fix_chunk_padding(c, p);
         cudaEventDestroy(p.ev);

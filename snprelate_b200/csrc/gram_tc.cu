@@ -469,6 +469,10 @@ __global__ void fill_table_kernel(uint32_t *__restrict__ p, int64_t n, uint32_t 
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
+__global__ void pull_staged_kernel(const uint4 *__restrict__ host_mapped, uint4 *__restrict__ dev, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dev[i] = host_mapped[i];
+}
 const uint32_t *gram_const_table(snprel_ctx *c, uint32_t word) {
     for (auto &t : c->const_tabs)
         if (t->word == word && (int64_t)t->buf.n >= c->snp_cap) return t->buf.p;
@@ -675,10 +679,31 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     }
     if (items.size() > 0x3fffffffull) fail("too many work items");
 
-    c->scr_items.alloc(items.size() * sizeof(Item));
-    c->scr_passes.alloc(pd.size() * sizeof(PassDesc));
-    CUDA_CHECK(cudaMemcpyAsync(c->scr_items.p, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, c->stream));
-    CUDA_CHECK(cudaMemcpyAsync(c->scr_passes.p, pd.data(), pd.size() * sizeof(PassDesc), cudaMemcpyHostToDevice, c->stream));
+    // Work list and pass descriptors go to the device WITHOUT the host-to-device copy engine: a copy queued
+    // on the compute stream would wait behind every genotype chunk still crossing PCIe (one H2D engine
+    // queue), and the first tensor pass with it.  The host writes them into mapped pinned memory and a tiny
+    // kernel of this stream pulls them into device memory (each un-synchronised launch gets its own slice).
+    const size_t ibytes = round_up((int64_t)(items.size() * sizeof(Item)), 256), pbytes = round_up((int64_t)(pd.size() * sizeof(PassDesc)), 256);
+    if (c->stage_used + ibytes + pbytes > c->stage_bytes) {
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));            // nothing may still read the old buffers
+        const size_t want = std::max<size_t>(2 * (c->stage_used + ibytes + pbytes), 4u << 20);
+        if (c->stage_host) cudaFreeHost(c->stage_host);
+        c->stage_host = nullptr;
+        CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void **>(&c->stage_host), want, cudaHostAllocMapped));
+        c->stage_bytes = want;
+        c->stage_used = 0;
+        c->scr_items.alloc(want);
+    }
+    uint8_t *hslice = c->stage_host + c->stage_used, *dslice = c->scr_items.p + c->stage_used;
+    memcpy(hslice, items.data(), items.size() * sizeof(Item));
+    memcpy(hslice + ibytes, pd.data(), pd.size() * sizeof(PassDesc));
+    {
+        const int64_t words = (int64_t)((ibytes + pbytes) / 16);
+        pull_staged_kernel<<<(unsigned)((words + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint4 *>(hslice),
+                                                                                reinterpret_cast<uint4 *>(dslice), words);
+        KERNEL_CHECK(c);
+    }
+    c->stage_used += ibytes + pbytes;
     c->scr_flags.alloc(2);
     int *derr = c->scr_flags.p + 1;
     if (sync || snp_lo == 0) CUDA_CHECK(cudaMemsetAsync(derr, 0, sizeof(int), c->stream));
@@ -717,8 +742,8 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     }
 
     Params P{};
-    P.items = reinterpret_cast<const Item *>(c->scr_items.p);
-    P.passes = reinterpret_cast<const PassDesc *>(c->scr_passes.p);
+    P.items = reinterpret_cast<const Item *>(dslice);
+    P.passes = reinterpret_cast<const PassDesc *>(dslice + ibytes);
     P.out = out_planes;
     P.ld = npad;
     P.plane_stride = win.rows * npad;
@@ -735,9 +760,12 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     if (sync) gram_tc_check(c);
 }
 
+void gram_tc_stage_reset(snprel_ctx *c) { c->stage_used = 0; }
+
 // wait for the launches queued so far and surface a pipeline time-out
 void gram_tc_check(snprel_ctx *c) {
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->stage_used = 0;
     if (!c->scr_flags.p) return;
     int herr = 0;
     CUDA_CHECK(cudaMemcpy(&herr, c->scr_flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost));
