@@ -228,6 +228,7 @@ struct snprel_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_ev0 = nullptr;
     double last_copy_ms = 0;     // first async copy chunk queued -> last one arrived
+    int stream_ranges = 0;       // launches the last streamed accumulate was cut into
     int64_t streamed_steps = 0, stream_fallbacks = 0;   // accumulates that consumed in-flight copies / that had to be redone   // multi.cu: peers' reduce buffers mapped through CUDA IPC (one process per GPU)
     int eig_solver = 0;          // 0 dense (Xsyevd), 1 Chebyshev-filtered subspace iteration
     int eig_rounds = 0, eig_gemms = 0;

@@ -1016,7 +1016,7 @@ static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
     c->iscalars.zero(c->stream);
     c->scr_flags.alloc(2);
     c->scr_flags.zero(c->stream);
-    const int64_t tblocks_max = (m + 255) / 256 + (int64_t)chunks.size() + 1;
+    const int64_t tblocks_max = (m + 255) / 256 + (int64_t)chunks.size() + 1;     // (every range rounds its block count up)
     c->scr_part.alloc((size_t)tblocks_max * 2);
     CUDA_CHECK(cudaMemsetAsync(c->scr_part.p, 0, (size_t)tblocks_max * 2 * sizeof(double), c->stream));
     c->samp_sum.alloc((size_t)NVEC * npad);
@@ -1060,14 +1060,34 @@ static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
         KERNEL_CHECK(c);
         gram_tc_run(c, passes.data(), (int)passes.size(), c->acc.p, true, l0, l1, false);
     };
+    // Pacing: the host stays exactly one range ahead of the device.  `gate` fires when the previous
+    // range's tensor passes have been reached in the stream; the next range then takes EVERY chunk that
+    // has arrived by that time (the copies run five times faster than the tensor passes, so after the
+    // first two single-chunk ranges everything left is usually one launch).
+    cudaEvent_t gate;
+    CUDA_CHECK(cudaEventCreateWithFlags(&gate, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventRecord(gate, c->stream));
     consume(0, a1);
-    for (size_t k = 1; k < chunks.size(); k++) {
-        CUDA_CHECK(cudaStreamWaitEvent(c->stream, chunks[k].ev, 0));
-        geno_fix_chunk_padding(c, chunks[k]);
-        c->pending[k].consumed = true;
-        prep_stats_range(c, est, bayesian, chunks[k].l0, chunks[k].l1, pad_end(chunks[k].l1));
-        consume(chunks[k].l0, chunks[k].l1);
+    int nranges = 1;
+    for (size_t k = 1; k < chunks.size();) {
+        cudaEventSynchronize(gate);
+        cudaEventSynchronize(chunks[k].ev);
+        size_t k2 = k + 1;
+        while (k2 < chunks.size() && cudaEventQuery(chunks[k2].ev) == cudaSuccess) k2++;
+        for (size_t j = k; j < k2; j++) {
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream, chunks[j].ev, 0));
+            geno_fix_chunk_padding(c, chunks[j]);
+            c->pending[j].consumed = true;
+        }
+        const int64_t l0 = chunks[k].l0, l1 = chunks[k2 - 1].l1;
+        prep_stats_range(c, est, bayesian, l0, l1, pad_end(l1));
+        CUDA_CHECK(cudaEventRecord(gate, c->stream));
+        consume(l0, l1);
+        nranges++;
+        k = k2;
     }
+    cudaEventDestroy(gate);
+    c->stream_ranges = nranges;
     CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
     het_to_vec_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, c->stream>>>(c->scr_cnt.p, c->samp_sum.p, npad);
     KERNEL_CHECK(c);

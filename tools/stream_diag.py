@@ -39,7 +39,7 @@ for _ in range(3):
     c.geno_begin(N, M); c.geno_push_2b_async(hg); t1 = time.perf_counter()
     c.pca(genmat_only=True, genmat_out=ho); t2 = time.perf_counter()
     print(f"streamed: push returns after {1e3*(t1-t0):.2f} ms, pca {1e3*(t2-t1):.1f} ms; device step {c.last_step_ms():.1f} ms, "
-          f"first tensor pass -> last {c.last_hot_kernel()[0]:.1f} ms, copies {c.stream_last_copy_ms():.1f} ms, stats {c.stream_stats()}")
+          f"first tensor pass -> last {c.last_hot_kernel()[0]:.1f} ms in {c.last_hot_kernel()[1]} launches, copies {c.stream_last_copy_ms():.1f} ms, stats {c.stream_stats()}")
 # pca only on resident data, for reference
 c.geno_begin(N, M); c.geno_push_2b(hg)
 print("pca on resident data     ", t(lambda: c.pca(genmat_only=True, genmat_out=ho)))
