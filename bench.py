@@ -296,6 +296,7 @@ def run_ours(args):
         sampler.stop_flag = True
         sampler.join(timeout=2)
     launches = ctx.kernel_launches() - launches0
+    pl_timed = ctx.last_plan()           # fixed-point format of the device-timed steps
 
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -390,7 +391,8 @@ def run_ours(args):
     # ---- extra: BASELINE configs 3 / 4 at full size under this clock (--gpus 4: snpgdsIBS 50k x 500k;
     # --gpus 8: KING-robust 100k x 1M, packed-bit kernels and the tensor engine) ----
     big = {}
-    pl = ctx.last_plan()
+    pl = pl_timed
+    pl_e2e = ctx.last_plan()
     if not args.no_extra and world in (4, 8):
         from snprelate_b200.configs import run_pair_config
         ctx.close()
@@ -498,6 +500,7 @@ def run_ours(args):
                          "+ snprel_pca (genmat to host)") if world == 1 and not args.sync_ingest else
                         "snprel_geno_begin + snprel_geno_push_2b (pinned host 2-bit rows) + snprel_pca (genmat to host)",
                 "streamed_steps_fallbacks": list(ctx_stream_stats),
+                "tensor_passes_per_step": int(pl_e2e.digits) + int(pl_e2e.digits_w) + int(pl_e2e.digits_d),
                 "ms_per_step": e2e_s * 1e3, "ms_parts": e2e_parts},
         "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
         "parity": parity, "roofline": roofline, "cpu_baseline": cpu,

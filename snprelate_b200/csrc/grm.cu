@@ -992,9 +992,11 @@ static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
     read_plan_stats(c, est, plan, a1);
     {
         const double fac = (double)m / (double)a1;
-        plan.max_abs *= 2.0;                       // a later SNP may have a rarer allele
-        plan.max_abs_w *= 2.0;
-        plan.sum_bound *= fac * 1.05;
+        // the row tables are range-equalised by construction (coltab_kernel: s follows |U|), so a later SNP
+        // exceeds the first 131k SNPs' maximum only marginally; a wrong guess is caught by the overflow flag
+        plan.max_abs *= 1.25;
+        plan.max_abs_w *= 1.25;
+        plan.sum_bound *= fac * 1.03;
         plan.err_weight *= fac * 1.08;
         plan.max_missing = (int64_t)std::ceil((double)plan.max_missing * fac * 1.15 + 16.0);
         plan.total_missing = (int64_t)((double)plan.total_missing * fac) + (m > a1 ? 1 : 0);
