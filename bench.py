@@ -343,6 +343,7 @@ def run_ours(args):
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     ctx_stream_stats = ctx.stream_stats()
+    pl_e2e = ctx.last_plan()
     e2e_parts = {k: round(v / e2e_steps, 2) for k, v in e2e_parts.items()}
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -392,7 +393,6 @@ def run_ours(args):
     # --gpus 8: KING-robust 100k x 1M, packed-bit kernels and the tensor engine) ----
     big = {}
     pl = pl_timed
-    pl_e2e = ctx.last_plan()
     if not args.no_extra and world in (4, 8):
         from snprelate_b200.configs import run_pair_config
         ctx.close()
