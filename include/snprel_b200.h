@@ -302,6 +302,9 @@ typedef struct snprel_plan {
     int32_t digits_d;      /* out: digits of the denominator table                     */
     int32_t bayesian;      /* Eigenstrat only                                          */
     int32_t frac_bits_v;   /* out: fixed point of the per-sample vector sum_l R_l[g_il] */
+    int32_t reserved;
+    double diag_bound;     /* measured X >= max_i C_ii of the local SNPs (0: not measured); sum-reduced  */
+    double sum_rest;       /* the part of sum_bound that is not the main T x B product; sum-reduced       */
 } snprel_plan;
 
 int snprel_plan_local(snprel_ctx *ctx, int estimator, snprel_plan *plan);

@@ -29,7 +29,8 @@ class Plan(C.Structure):
                 ("total_missing", C.c_int64), ("max_missing", C.c_int64), ("n_snp", C.c_int64),
                 ("frac_bits", C.c_int32), ("frac_bits_w", C.c_int32), ("frac_bits_d", C.c_int32),
                 ("digits", C.c_int32), ("digits_w", C.c_int32), ("digits_d", C.c_int32),
-                ("bayesian", C.c_int32), ("frac_bits_v", C.c_int32)]
+                ("bayesian", C.c_int32), ("frac_bits_v", C.c_int32), ("reserved", C.c_int32),
+                ("diag_bound", C.c_double), ("sum_rest", C.c_double)]
 
 
 def library_path() -> str:

@@ -185,6 +185,8 @@ struct snprel_ctx {
     std::vector<std::unique_ptr<ConstTab>> const_tabs;   // constant per-SNP tables (gram_const_table)
     snprel::DevBuf<int> scr_cnt;          // per-sample heterozygote / missing counts [2][npad]
     snprel::DevBuf<long long> scr_ew;     // per-sample error weight sum_l |B_l[g_il]| [npad]
+    snprel::DevBuf<long long> scr_dg;     // per-sample diagonal bound, in units of c (diagtab_kernel) [npad]
+    snprel::DevBuf<uint32_t> scr_tabf;    // [snp_cap]: ceil(w (g - mu)^2 / c) as bytes by genotype code
     snprel::DevBuf<int> scr_chunk;        // per GRAM_CHUNK SNPs: max over samples of the chunk's error weight
     snprel::DevBuf<int2> scr_coltab;      // per-SNP integer column table (s_l, t_l), B_l[g] = s_l g - t_l
     snprel::DevBuf<uint32_t> scr_tabb;    // [2][snp_cap]: B_l as int8 bytes by genotype code, and |B_l|

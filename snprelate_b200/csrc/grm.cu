@@ -191,10 +191,12 @@ __device__ __forceinline__ uint32_t digit_of(long long &q) {
 
 // ---- plan statistics ---------------------------------------------------------
 // out[0] max |T|, out[1] int64-range bound, out[2] total missing,
-// out[3] local share of the normaliser (trace(C) / nLocus / sum d / sum d2), out[4] max |R|
+// out[3] local share of the normaliser (trace(C) / nLocus / sum d / sum d2), out[4] max |R|,
+// out[5] max over SNPs and genotypes of w (g - mu)^2 (scale of the measured diagonal bound, diagtab_kernel),
+// out[6] the part of out[1] that is not the main T x B product (2 max|R| + 2 dmax + w delta^2)
 __global__ void plan_kernel(const SnpStat *__restrict__ st, const int2 *__restrict__ coltab, int64_t n_snp,
                             int64_t n_samp, int est, int bayesian, double *__restrict__ out) {
-    double mx = 0, mxw = 0, sb = 0, tm = 0, sc = 0;
+    double mx = 0, mxw = 0, sb = 0, tm = 0, sc = 0, mv = 0, sr = 0;
     for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n_snp;
          l += (int64_t)gridDim.x * blockDim.x) {
         SnpTables t;
@@ -203,14 +205,21 @@ __global__ void plan_kernel(const SnpStat *__restrict__ st, const int2 *__restri
         double dmax = realD ? fmax(t.d, t.d2) : 0.0;
         mx = fmax(mx, t.maxU);
         mxw = fmax(mxw, t.maxW);
-        sb += (double)t.maxB * t.maxU + 2 * t.maxW + 2 * dmax;
+        const SnpCoef k = snp_coef(st[l], est, bayesian);
+        const double delta = k.mu - (double)coltab[l].y / (double)coltab[l].x;
+        const double rest = 2 * t.maxW + 2 * dmax + k.w * delta * delta;
+        sb += (double)t.maxB * t.maxU + rest;
+        sr += rest;
+        if (est != SNPREL_EST_KING_HOMO) mv = fmax(mv, k.w * fmax(k.mu, 2.0 - k.mu) * fmax(k.mu, 2.0 - k.mu));
         tm += (double)(n_samp - st[l].num);
         if (est == SNPREL_GRM_EIGENSTRAT) sc += t.diag;
         else if (est == SNPREL_GRM_EIGMIX) sc += t.d;
         else if (est == SNPREL_EST_KING_HOMO) sc += t.d2;
         else sc += t.d;   // GCTA: number of polymorphic SNPs
     }
-    __shared__ double s0[256], s1[256], s2[256], s3[256], s4[256];
+    __shared__ double s0[256], s1[256], s2[256], s3[256], s4[256], s5[256], s6[256];
+    s5[threadIdx.x] = mv;
+    s6[threadIdx.x] = sr;
     s4[threadIdx.x] = mxw;
     s0[threadIdx.x] = mx;
     s1[threadIdx.x] = sb;
@@ -221,6 +230,8 @@ __global__ void plan_kernel(const SnpStat *__restrict__ st, const int2 *__restri
         if (threadIdx.x < o) {
             s0[threadIdx.x] = fmax(s0[threadIdx.x], s0[threadIdx.x + o]);
             s4[threadIdx.x] = fmax(s4[threadIdx.x], s4[threadIdx.x + o]);
+            s5[threadIdx.x] = fmax(s5[threadIdx.x], s5[threadIdx.x + o]);
+            s6[threadIdx.x] += s6[threadIdx.x + o];
             s1[threadIdx.x] += s1[threadIdx.x + o];
             s2[threadIdx.x] += s2[threadIdx.x + o];
             s3[threadIdx.x] += s3[threadIdx.x + o];
@@ -233,7 +244,33 @@ __global__ void plan_kernel(const SnpStat *__restrict__ st, const int2 *__restri
         atomicAdd(out + 2, s2[0]);
         atomicAdd(out + 3, s3[0]);
         atomicMax(reinterpret_cast<unsigned long long *>(out + 4), (unsigned long long)__double_as_longlong(s4[0]));
+        atomicMax(reinterpret_cast<unsigned long long *>(out + 5), (unsigned long long)__double_as_longlong(s5[0]));
+        atomicAdd(out + 6, s6[0]);
     }
+}
+
+// ---- measured bound of the diagonal --------------------------------------------------------
+// tabF[l] = bytes ceil(w_l (g - mu_l)^2 / c) for g = 0, 1, 2 (0 for missing), c = out[5] / 127: summed per
+// sample by sample_stats_kernel it gives X_i >= C_ii, and by Cauchy-Schwarz every entry of the main
+// plane obeys |sum_l T_l[g_il] B_l[g_jl]| <= sqrt(X_i (2 X_j + 2 sum_l w_l delta_l^2)) -- a bound that follows
+// the data (about 2 per SNP) where the worst case sum_l max|T_l| max|B_l| assumes a sample that is
+// homozygous for the rare allele everywhere (about 16 per SNP at the bench's MAF range).  It only decides how
+// many fractional bits the int64 planes can carry.
+__global__ void diagtab_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int est, int bayesian,
+                               const double *__restrict__ plan_out, uint32_t *__restrict__ tabF) {
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_snp) return;
+    const SnpCoef k = snp_coef(st[l], est, bayesian);
+    const double c = plan_out[5] / 127.0;
+    uint32_t word = 0;
+    if (c > 0 && k.w > 0) {
+        for (int g = 0; g < 3; g++) {
+            const double v = k.w * ((double)g - k.mu) * ((double)g - k.mu);
+            const double q = fmin(127.0, ceil(v / c * (1.0 + 1e-12)));
+            word |= (uint32_t)q << (8 * g);
+        }
+    }
+    tabF[l] = word;
 }
 
 // ---- per-sample statistics in one pass over the 2-bit matrix -----------------
@@ -248,17 +285,22 @@ constexpr int SS_THREADS = 128;
 __global__ void __launch_bounds__(SS_THREADS)
 sample_stats_kernel(const uint32_t *__restrict__ geno, const uint32_t *__restrict__ tabBabs, int64_t n_snp,
                     int64_t row_words, int64_t npad, long long *__restrict__ ew, int *__restrict__ cnt,
-                    int *__restrict__ chunk_ew) {
-    __shared__ uint32_t tab[GRAM_CHUNK + 4];
+                    int *__restrict__ chunk_ew, const uint32_t *__restrict__ tabF, long long *__restrict__ dg) {
+    __shared__ uint32_t tab[GRAM_CHUNK + 4], tabf[GRAM_CHUNK + 4];
     __shared__ int smax[SS_THREADS / 32];
     const int64_t l0 = (int64_t)blockIdx.y * GRAM_CHUNK;
     const int nl = (int)min((int64_t)GRAM_CHUNK, n_snp - l0);
-    for (int s = threadIdx.x; s < GRAM_CHUNK + 4; s += blockDim.x) tab[s] = s < nl ? tabBabs[l0 + s] : 0u;
+    const bool with_f = tabF != nullptr;
+    for (int s = threadIdx.x; s < GRAM_CHUNK + 4; s += blockDim.x) {
+        tab[s] = s < nl ? tabBabs[l0 + s] : 0u;
+        tabf[s] = (with_f && s < nl) ? tabF[l0 + s] : 0u;
+    }
     __syncthreads();
     const int64_t wc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = wc < row_words;
     const uint32_t *p = geno + l0 * row_words + (live ? wc : 0);
     uint32_t e16[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // |B| sums: selector q -> e16[2q] (bytes 0,2), e16[2q+1] (bytes 1,3)
+    uint32_t f16[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // diagonal-bound sums, same lanes (entries <= 127: 512 rows fit 16 bits)
     uint32_t m16[8] = {0, 0, 0, 0, 0, 0, 0, 0}, h16[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t m8[4] = {0, 0, 0, 0}, h8[4] = {0, 0, 0, 0};
     int in8 = 0;
@@ -276,7 +318,7 @@ sample_stats_kernel(const uint32_t *__restrict__ geno, const uint32_t *__restric
 #pragma unroll
             for (int r = 0; r < 3; r++) {
                 const int row = min(r0 + 3 * g5 + r, GRAM_CHUNK + 3);
-                const uint32_t x = w[r], t = tab[row];
+                const uint32_t x = w[r], t = tab[row], tf = tabf[row];
                 const uint32_t hi = x >> 1;
                 m2 += x & hi & 0x55555555u;
                 h2 += x & ~hi & 0x55555555u;
@@ -287,6 +329,11 @@ sample_stats_kernel(const uint32_t *__restrict__ geno, const uint32_t *__restric
                     const uint32_t v = __byte_perm(t, 0, sel[q]);
                     e16[2 * q] += __byte_perm(v, 0, 0x4240);
                     e16[2 * q + 1] += __byte_perm(v, 0, 0x4341);
+                    if (with_f) {
+                        const uint32_t vf = __byte_perm(tf, 0, sel[q]);
+                        f16[2 * q] += __byte_perm(vf, 0, 0x4240);
+                        f16[2 * q + 1] += __byte_perm(vf, 0, 0x4341);
+                    }
                 }
             }
             m4a += m2 & 0x33333333u;
@@ -333,6 +380,10 @@ sample_stats_kernel(const uint32_t *__restrict__ geno, const uint32_t *__restric
                     const int es = 2 * byte + (q & 1) + 8 * (q >> 1);
                     best = max(best, ev);
                     if (ev) atomicAdd(reinterpret_cast<unsigned long long *>(ew) + s0 + es, (unsigned long long)ev);
+                    if (with_f) {
+                        const int fv = (int)((f16[2 * q + hb] >> (16 * half)) & 0xFFFFu);
+                        if (fv) atomicAdd(reinterpret_cast<unsigned long long *>(dg) + s0 + es, (unsigned long long)fv);
+                    }
                     const int ms = (q == 0 ? 0 : q == 1 ? 2 : q == 2 ? 1 : 3) + 4 * byte;
                     const int mv = (int)((m16[2 * q + hb] >> (16 * half)) & 0xFFFFu);
                     const int hv = (int)((h16[2 * q + hb] >> (16 * half)) & 0xFFFFu);
@@ -563,8 +614,17 @@ static void ensure_coltab(snprel_ctx *c, int est, int bayesian) {
 
 // scr_ew[npad], scr_cnt[2][npad], scr_chunk[nchunk]: this rank's per-sample error weights, het / missing
 // counts and the per-chunk maxima of the error weight
-static void sample_stats(snprel_ctx *c) {
+static void sample_stats(snprel_ctx *c, int est = -1, int bayesian = 0) {   // est >= 0: also the diagonal bound (needs scr_plan of plan_kernel)
     const int64_t npad = c->n_samp_pad;
+    const bool with_diag = est >= 0 && est != SNPREL_EST_KING_HOMO && c->n_snp > 0;
+    c->scr_dg.alloc((size_t)npad);
+    c->scr_dg.zero(c->stream);
+    if (with_diag) {
+        c->scr_tabf.alloc((size_t)c->snp_cap);
+        diagtab_kernel<<<(unsigned)((c->n_snp + 255) / 256), 256, 0, c->stream>>>(c->stat.p, c->n_snp, est, bayesian, c->scr_plan.p,
+                                                                                  c->scr_tabf.p);
+        KERNEL_CHECK(c);
+    }
     const int64_t nchunk = (c->snp_cap + GRAM_CHUNK - 1) / GRAM_CHUNK;
     c->scr_cnt.alloc((size_t)2 * npad);
     c->scr_cnt.zero(c->stream);
@@ -577,7 +637,8 @@ static void sample_stats(snprel_ctx *c) {
         dim3 grid((unsigned)((row_words + SS_THREADS - 1) / SS_THREADS), (unsigned)((c->n_snp + GRAM_CHUNK - 1) / GRAM_CHUNK));
         sample_stats_kernel<<<grid, SS_THREADS, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(c->geno2b.p),
                                                                c->scr_tabb.p + c->snp_cap, c->n_snp, row_words, npad,
-                                                               c->scr_ew.p, c->scr_cnt.p, c->scr_chunk.p);
+                                                               c->scr_ew.p, c->scr_cnt.p, c->scr_chunk.p,
+                                                               with_diag ? c->scr_tabf.p : nullptr, c->scr_dg.p);
         KERNEL_CHECK(c);
     }
 }
@@ -596,13 +657,15 @@ void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
             plan->err_weight = s.err_weight;
             plan->max_missing = s.max_missing;
             plan->n_snp = s.n_snp;
+            plan->diag_bound = s.diag_bound;
+            plan->sum_rest = s.sum_rest;
             return;
         }
     }
     ensure_coltab(c, est, plan->bayesian);
     const int64_t npad = c->n_samp_pad;
     DevBuf<double> &out = c->scr_plan;
-    out.alloc(5);
+    out.alloc(8);
     out.zero(c->stream);
     if (c->n_snp > 0) {
         int blocks = (int)std::min<int64_t>((c->n_snp + 255) / 256, 1024);
@@ -610,10 +673,12 @@ void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
                                                    plan->bayesian, out.p);
         KERNEL_CHECK(c);
     }
-    sample_stats(c);
-    double h[5];
+    sample_stats(c, est, plan->bayesian);
+    double h[8];
     c->host_cnt.resize((size_t)npad);
     c->host_ew.resize((size_t)npad);
+    std::vector<long long> hdg((size_t)npad);
+    CUDA_CHECK(cudaMemcpyAsync(hdg.data(), c->scr_dg.p, (size_t)npad * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     const size_t nchunk = (size_t)((c->n_snp + GRAM_CHUNK - 1) / GRAM_CHUNK);
     std::vector<int> hchunk(nchunk);
     CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
@@ -624,11 +689,15 @@ void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
     if (nchunk)
         CUDA_CHECK(cudaMemcpyAsync(hchunk.data(), c->scr_chunk.p, nchunk * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    long long ew = 0, mm = 0;
+    long long ew = 0, mm = 0, dg = 0;
     for (int64_t i = 0; i < c->n_samp; i++) {
         ew = std::max(ew, c->host_ew[i]);
         mm = std::max<long long>(mm, c->host_cnt[i]);
+        dg = std::max(dg, hdg[i]);
     }
+    // X = max_i sum_l ceil(w (g - mu)^2 / c) c  >=  max_i C_ii   (0: not measured)
+    plan->diag_bound = (est == SNPREL_EST_KING_HOMO) ? 0.0 : (double)dg * (h[5] / 127.0);
+    plan->sum_rest = h[6];
     c->chunk_bound.assign(hchunk.begin(), hchunk.end());
     plan->max_abs = h[0];
     plan->max_abs_w = h[4];
@@ -670,7 +739,12 @@ static void choose_format(int est, snprel_plan &plan, int &nU, int &nW, int &nD,
     const double tol = (plan.tol > 0 ? plan.tol : 1e-10) * 0.9;   // 10 % left for the per-sample vector and float64 rounding in the epilogue
     const bool homo = est == SNPREL_EST_KING_HOMO;
     const bool any_missing = plan.total_missing > 0;
-    const int head = 61 - (int)std::ceil(std::log2(std::max(plan.sum_bound, 1.0)));   // int64 plane headroom
+    // int64 plane headroom.  Sums wrap modulo 2^64 harmlessly on the way (atomics, reductions over GPUs): only
+    // the FINAL entries must fit.  Worst case: sum_bound = sum_l max|T_l| max|B_l| + rest.  Measured
+    // (diagtab_kernel / sample_stats_kernel, Cauchy-Schwarz + AM-GM): 1.5 X + rest with X >= max_i C_ii.
+    double range_bound = plan.sum_bound;
+    if (plan.diag_bound > 0) range_bound = std::min(range_bound, 1.5 * plan.diag_bound + plan.sum_rest);
+    const int head = 61 - (int)std::ceil(std::log2(std::max(range_bound, 1.0)));
     if (head < 16) fail("fixed-point accumulator cannot hold this data set (sum bound %.3g)", plan.sum_bound);
     double scale = plan.scale;
     if (est == SNPREL_GRM_GCTA) scale -= 4.0 * (double)plan.max_missing;   // 2 (nLocus - D_ij), D_ij <= 2 max_missing
@@ -773,7 +847,7 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
         // scr_cnt was summed over the ranks together with an earlier format's vectors while the
         // cached plan statistics kept it from being rebuilt: restore this rank's own counts
         if ((pc.reduced && pc.version == c->geno_version) || !c->scr_cnt.p || c->plan_cache.version != c->geno_version)
-            sample_stats(c);
+            sample_stats(c);      // (counts only: the diagonal bound lives in the plan)
         pc.version = 0;
         tab.alloc((size_t)std::max(npass, 1) * cap);
         tab.zero(c->stream);
@@ -918,14 +992,14 @@ static void prep_stats_range(snprel_ctx *c, int est, int bayesian, int64_t l0, i
     dim3 grid((unsigned)((row_words + SS_THREADS - 1) / SS_THREADS), (unsigned)((n + GRAM_CHUNK - 1) / GRAM_CHUNK));
     sample_stats_kernel<<<grid, SS_THREADS, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(c->geno2b.p) + l0 * row_words,
                                                            c->scr_tabb.p + c->snp_cap + l0, n, row_words, c->n_samp_pad,
-                                                           c->scr_ew.p, c->scr_cnt.p, c->scr_chunk.p + l0 / GRAM_CHUNK);
+                                                           c->scr_ew.p, c->scr_cnt.p, c->scr_chunk.p + l0 / GRAM_CHUNK, nullptr, nullptr);
     KERNEL_CHECK(c);
 }
 
 // plan statistics accumulated so far -> host
 static void read_plan_stats(snprel_ctx *c, int est, snprel_plan &plan, int64_t n_snp_seen) {
     const int64_t npad = c->n_samp_pad;
-    double h[5];
+    double h[8];
     c->host_cnt.resize((size_t)npad);
     c->host_ew.resize((size_t)npad);
     CUDA_CHECK(cudaMemcpyAsync(h, c->scr_plan.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
@@ -947,6 +1021,8 @@ static void read_plan_stats(snprel_ctx *c, int est, snprel_plan &plan, int64_t n
     plan.err_weight = (double)ew;
     plan.max_missing = mm;
     plan.n_snp = n_snp_seen;
+    plan.diag_bound = 0;          // (not measured chunk by chunk: the worst-case headroom is used)
+    plan.sum_rest = h[6];
 }
 
 // true: accumulated (c->acc etc. hold the result, caches set); false: the caller must take the ordinary path
@@ -968,7 +1044,7 @@ static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
     c->scr_coltab.alloc((size_t)cap);
     c->scr_tabb.alloc((size_t)2 * cap);
     c->scr_tabb.zero(c->stream);
-    c->scr_plan.alloc(5);
+    c->scr_plan.alloc(8);
     c->scr_plan.zero(c->stream);
     c->scr_cnt.alloc((size_t)2 * npad);
     c->scr_cnt.zero(c->stream);
@@ -1001,6 +1077,7 @@ static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
         plan.max_missing = (int64_t)std::ceil((double)plan.max_missing * fac * 1.15 + 16.0);
         plan.total_missing = (int64_t)((double)plan.total_missing * fac) + (m > a1 ? 1 : 0);
         plan.scale *= fac * 0.95;                  // a LOWER bound of the normaliser
+        plan.sum_rest *= fac * 1.03;
         plan.n_snp = m;
     }
     int nU = 0, nW = 0, nD = 0;

@@ -597,6 +597,9 @@ int snprel_multi_accumulate(snprel_multi *m, int est, int bayesian, int root) {
         g.total_missing += plans[i].total_missing;
         g.max_missing += plans[i].max_missing;
         g.n_snp += plans[i].n_snp;
+        // (a sum of per-device maxima bounds the maximum of the sums; 0 = some device did not measure it)
+        g.diag_bound = (g.diag_bound > 0 && plans[i].diag_bound > 0) ? g.diag_bound + plans[i].diag_bound : 0.0;
+        g.sum_rest += plans[i].sum_rest;
     }
     on_each(m, [&](int i) { ck(m, i, snprel_accumulate(m->ctx[i], est, &g)); });
     peer_reduce(m, root);

@@ -56,7 +56,7 @@ def buffer_tensor(ptr, count, kind, device):
 
 _PLAN_MAX = ("max_abs", "max_abs_w")
 # sums are conservative for the per-sample maxima (max of sums <= sum of maxima)
-_PLAN_SUM = ("sum_bound", "err_weight", "scale", "total_missing", "max_missing", "n_snp")
+_PLAN_SUM = ("sum_bound", "err_weight", "scale", "total_missing", "max_missing", "n_snp", "diag_bound", "sum_rest")
 _PLAN_INT = ("total_missing", "max_missing", "n_snp")
 
 
@@ -150,16 +150,25 @@ def peer_reduce_buffers(ctx, rank, world, root=None, group=None, device=None):
     and the barriers only.  Returns the bytes this rank moved over the links."""
     import torch
     import torch.distributed as dist
-    hb, off = ctx.reduce_ipc_handles()
-    nb = off.size
     dev = "cpu" if device is None else device
-    th = torch.from_numpy(hb).to(dev)
-    to = torch.from_numpy(off).to(dev)
-    gh = torch.empty(world * nb * 64, dtype=torch.uint8, device=dev)
-    go = torch.empty(world * nb, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(gh, th, group=group)
-    dist.all_gather_into_tensor(go, to, group=group)      # (also the barrier before phase 1: every rank has accumulated)
-    ctx.peer_reduce_open(rank, world, gh.cpu().numpy(), go.cpu().numpy())
+    # The handles are exchanged only when some rank's buffers changed (they are persistent allocations,
+    # so after the first window this is one tiny all-reduce -- which is also the barrier that tells every
+    # rank that its peers have finished accumulating).
+    key = tuple((int(p), int(c), int(k)) for p, c, k in ctx.reduce_buffers())
+    cache = getattr(ctx, "_peer_cache", None)
+    changed = torch.tensor([0 if (cache is not None and cache == (key, rank, world)) else 1], dtype=torch.int32, device=dev)
+    dist.all_reduce(changed, op=dist.ReduceOp.MAX, group=group)
+    if int(changed.item()):
+        hb, off = ctx.reduce_ipc_handles()
+        nb = off.size
+        th = torch.from_numpy(hb).to(dev)
+        to = torch.from_numpy(off).to(dev)
+        gh = torch.empty(world * nb * 64, dtype=torch.uint8, device=dev)
+        go = torch.empty(world * nb, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gh, th, group=group)
+        dist.all_gather_into_tensor(go, to, group=group)
+        ctx.peer_reduce_open(rank, world, gh.cpu().numpy(), go.cpu().numpy())
+        ctx._peer_cache = (key, rank, world)
     moved = ctx.peer_reduce_phase(1, -1 if root is None else root)
     dist.barrier(group=group)
     moved += ctx.peer_reduce_phase(2, -1 if root is None else root)
