@@ -374,6 +374,14 @@ int snprel_table_gram(snprel_ctx *ctx, const int8_t *tabA /*[n_snp][4]*/,
  * step on two streams (they only meet in commutative atomics) so that wave tails overlap. */
 int snprel_debug_flags(snprel_ctx *ctx, uint32_t flags);
 
+/* Asynchronous result delivery for row-window pipelines (C4 / C5 style jobs): with on = 1 snprel_ibs_ave,
+ * snprel_king_robust and snprel_grm return as soon as the device-to-host copy of their result has been
+ * QUEUED (on a second stream), so the copy of window w overlaps the accumulate of window w + 1; the host
+ * buffer (pinned memory) must not be read or reused before snprel_output_wait returns.  The next finishing
+ * call on the context waits by itself before it rewrites the device-side result scratch. */
+int snprel_set_async_output(snprel_ctx *ctx, int on);
+int snprel_output_wait(snprel_ctx *ctx);
+
 /* ---- several GPUs of one box behind one handle (single host process) --------------------
  * What an R session needs to spread gnrGRM / gnrPCA / gnrIBSNum / gnrIBD_KING_Robust ... over the
  * eight B200s of a box (north star: "partition across the 8 GPUs by SNP block, each GPU

@@ -99,6 +99,8 @@ def load_library():
         "snprel_debug_flags": [p, u32],
         "snprel_set_count_engine": [p, i32],
         "snprel_set_rounding": [p, i32],
+        "snprel_set_async_output": [p, i32],
+        "snprel_output_wait": [p],
         "snprel_geno_push_2b_async": [p, p, i64, i64],
         "snprel_geno_wait": [p],
         "snprel_stream_stats": [p, C.POINTER(i64), C.POINTER(i64)],
@@ -166,7 +168,7 @@ EXPORTED_SYMBOLS = [
     "snprel_multi_set_row_window", "snprel_multi_set_count_engine", "snprel_multi_accumulate", "snprel_multi_last_reduce",
     "snprel_geno_seek", "snprel_geno_device_rows", "snprel_geno_commit",
     "snprel_multi_geno_begin_replicated", "snprel_multi_geno_gather", "snprel_multi_grm_tiled",
-    "snprel_geno_push_2b_async", "snprel_geno_wait", "snprel_stream_stats", "snprel_stream_last_copy_ms",
+    "snprel_set_async_output", "snprel_output_wait", "snprel_geno_push_2b_async", "snprel_geno_wait", "snprel_stream_stats", "snprel_stream_last_copy_ms",
     "snprel_reduce_ipc_export", "snprel_peer_reduce_open", "snprel_peer_reduce_phase", "snprel_peer_reduce_close",
 ]
 
@@ -244,6 +246,14 @@ class Context:
         if (int(first_snp) + int(cnt)) * n * 2 > stream.size * 8:
             raise SNPRelError("geno_push_bitstream: the stream is shorter than the requested SNP range")
         self._ck(self.lib.snprel_geno_push_bitstream(self.h, _ptr(stream), int(first_snp) * n, int(cnt)))
+
+    def set_async_output(self, on=True):
+        """Row-window pipelines: ibs_ave / king_robust / grm return once their device-to-host copy is queued;
+        call output_wait() before reading (or reusing) the host buffer."""
+        self._ck(self.lib.snprel_set_async_output(self.h, int(bool(on))))
+
+    def output_wait(self):
+        self._ck(self.lib.snprel_output_wait(self.h))
 
     def geno_push_2b_async(self, packed):
         """Queue the host-to-device copy and return; `packed` (ideally pinned) must stay alive until the next

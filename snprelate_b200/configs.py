@@ -38,6 +38,7 @@ def run_pair_config(local, est_name, n, m, rank=0, world=1, engine="bits", reduc
     ctx = Context(local)
     try:
         ctx.set_count_engine(engine)
+        ctx.set_async_output(True)        # the D2H of a finished window overlaps the next window's accumulate
         ctx.geno_begin(n, hi - lo)
         t0 = time.perf_counter()
         ctx.geno_synth(hi - lo, seed=SEED, miss_rate=miss, snp_start=lo)
@@ -62,6 +63,14 @@ def run_pair_config(local, est_name, n, m, rank=0, world=1, engine="bits", reduc
 
         idx = np.zeros(0, dtype=np.int64) if check_idx is None else np.asarray(check_idx, dtype=np.int64)
         got_rows = []
+        wanted = []                        # rows of the window whose copy is still in flight: (a, offset in the slice)
+
+        def collect(out):
+            ctx.output_wait()
+            for a, base in wanted:
+                got_rows.append((a, [o[base + idx[a:]].copy() for o in out]))
+            wanted.clear()
+        last_out = None
 
         def barrier():
             if world > 1:
@@ -87,17 +96,21 @@ def run_pair_config(local, est_name, n, m, rank=0, world=1, engine="bits", reduc
             ctx.mark_reduced()
             tc = time.perf_counter()
             if root == rank:
+                if last_out is not None:
+                    collect(last_out)      # the previous window of this rank has long arrived; its host buffer is reused now
                 out = (ctx.ibs_ave(packed=True, out=host[0]),) if est_name == "ibs" else ctx.king_robust(None, packed=True, out=host)
+                last_out = out
                 r1 = min(r0 + h, n) if h else n
                 pbase = r0 * (2 * n - r0 - 1) // 2 + r0
                 for a, i in enumerate(idx):
                     if r0 <= i < r1:
-                        base = int(i) * (2 * n - int(i) - 1) // 2 - pbase
-                        got_rows.append((a, [o[base + idx[a:]].copy() for o in out]))
+                        wanted.append((a, int(i) * (2 * n - int(i) - 1) // 2 - pbase))
             td_ = time.perf_counter()
             t_acc += tb - ta
             t_red += tc - tb
             t_fin += td_ - tc
+        if last_out is not None:
+            collect(last_out)              # (inside the timed region: the last result must be on the host)
         barrier()
         t_job = time.perf_counter() - t_start
         if world > 1:

@@ -509,11 +509,12 @@ void ibs_ave_finish(snprel_ctx *c, double *out, int packed) {
     need_accum(c, SNPREL_EST_IBS);
     int64_t n = c->n_samp;
     check_grid_rows(n);
-    DevBuf<double> o;
+    output_wait(c);                       // the scratch may still be on its way to the host
+    DevBuf<double> &o = c->scr_out;       // persistent: no 10 GB cudaMalloc / cudaFree per row window
     o.alloc(win_out_count(c, packed));
     ibs_ave_kernel<<<win_grid(c), 128, 0, c->stream>>>(c->cnt.p, o.p, packed, n, c->n_samp_pad, row_window(c));
     KERNEL_CHECK(c);
-    d2h(c, out, o.p, win_out_count(c, packed));
+    deliver(c, out, o.p, win_out_count(c, packed));
 }
 
 void king_robust_finish(snprel_ctx *c, const int32_t *fam, double *ibs0, double *kin, int packed) {
@@ -528,14 +529,16 @@ void king_robust_finish(snprel_ctx *c, const int32_t *fam, double *ibs0, double 
         CUDA_CHECK(cudaMemcpyAsync(dfam.p, fam, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice,
                                    c->stream));
     }
-    DevBuf<double> o;
+    output_wait(c);
+    DevBuf<double> &o = c->scr_out;
     size_t oc = win_out_count(c, packed);
     o.alloc(2 * oc);
     king_robust_kernel<<<win_grid(c), 128, 0, c->stream>>>(c->cnt.p, fam ? dfam.p : nullptr, o.p, o.p + oc,
                                                            packed, n, c->n_samp_pad, row_window(c));
     KERNEL_CHECK(c);
-    d2h(c, ibs0, o.p, oc);
-    d2h(c, kin, o.p + oc, oc);
+    if (fam) CUDA_CHECK(cudaStreamSynchronize(c->stream));    // dfam is freed when this function returns
+    deliver(c, ibs0, o.p, oc, false);
+    deliver(c, kin, o.p + oc, oc, true);
 }
 
 // gnrIBD_PLINK (src/genIBS.cpp:558-639) from the IBS counters and the summed per-SNP terms

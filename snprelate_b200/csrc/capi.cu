@@ -94,6 +94,12 @@ void snprel_destroy(snprel_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->out_stream) {
+        cudaStreamSynchronize(c->out_stream);
+        cudaEventDestroy(c->out_ready);
+        cudaEventDestroy(c->out_done);
+        cudaStreamDestroy(c->out_stream);
+    }
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         for (auto &p : c->pending) cudaEventDestroy(p.ev);
@@ -136,6 +142,17 @@ int snprel_geno_push_2b_async(snprel_ctx *c, const uint8_t *packed, int64_t cnt,
 }
 int snprel_geno_wait(snprel_ctx *c) {
     API_BEGIN(c)
+    API_END(c)
+}
+int snprel_set_async_output(snprel_ctx *c, int on) {
+    API_BEGIN(c)
+    output_wait(c);
+    c->async_output = on ? 1 : 0;
+    API_END(c)
+}
+int snprel_output_wait(snprel_ctx *c) {
+    API_BEGIN_STREAMING(c)
+    output_wait(c);
     API_END(c)
 }
 int snprel_stream_stats(snprel_ctx *c, int64_t *streamed, int64_t *fallbacks) {

@@ -228,6 +228,13 @@ struct snprel_ctx {
     struct PendingCopy { int64_t l0, l1; cudaEvent_t ev; int64_t copied; bool consumed = false; };   // copied: bytes per row the host copy covered (-1: no padding to fix)
     std::vector<PendingCopy> pending;
     cudaStream_t copy_stream = nullptr;
+    // asynchronous result delivery (snprel_set_async_output): the device-to-host copy of a finished row window
+    // runs on out_stream while the next window accumulates; the result scratch (scr_out) is not rewritten
+    // before output_wait
+    int async_output = 0;
+    cudaStream_t out_stream = nullptr;
+    cudaEvent_t out_ready = nullptr, out_done = nullptr;
+    bool out_pending = false;
     cudaEvent_t copy_ev0 = nullptr;
     double last_copy_ms = 0;     // first async copy chunk queued -> last one arrived
     int stream_ranges = 0;       // launches the last streamed accumulate was cut into
@@ -273,6 +280,34 @@ inline bool full_window(const snprel_ctx *c) { return c->win_rows <= 0; }
 inline size_t window_packed_count(const snprel_ctx *c) {
     RowWin w = row_window(c);
     return (size_t)(tri_idx(c->n_samp, w.r1 - 1, c->n_samp - 1) + 1 - w.pbase);
+}
+
+// ---- result delivery ----------------------------------------------------------------
+inline void output_wait(snprel_ctx *c) {
+    if (!c->out_pending) return;
+    CUDA_CHECK(cudaEventSynchronize(c->out_done));
+    c->out_pending = false;
+}
+// copy `count` elements of a finished result to the caller; `last`: no more pieces of this result follow
+template <class T>
+inline void deliver(snprel_ctx *c, T *host, const T *dev, size_t count, bool last = true) {
+    if (!c->async_output) {
+        CUDA_CHECK(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+        if (last) CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        return;
+    }
+    if (!c->out_stream) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->out_ready, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->out_done, cudaEventDisableTiming));
+    }
+    CUDA_CHECK(cudaEventRecord(c->out_ready, c->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(c->out_stream, c->out_ready, 0));
+    CUDA_CHECK(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->out_stream));
+    if (last) {
+        CUDA_CHECK(cudaEventRecord(c->out_done, c->out_stream));
+        c->out_pending = true;
+    }
 }
 
 #define KERNEL_CHECK(ctx)                                   \

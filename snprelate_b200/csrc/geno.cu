@@ -189,6 +189,7 @@ __global__ void planes_kernel(const uint8_t *__restrict__ g, uint4 *__restrict__
 // ---------------------------------------------------------------------------
 void geno_begin(snprel_ctx *c, int64_t n_samp, int64_t cap) {
     geno_wait(c);
+    output_wait(c);
     if (n_samp <= 0) fail("snprel_geno_begin: n_samp must be positive");
     if (cap < 0) fail("snprel_geno_begin: negative SNP capacity");
     if (n_samp >= (1ll << 30)) fail("snprel_geno_begin: too many samples");

@@ -1465,6 +1465,7 @@ static double trace_of(snprel_ctx *c, const double *m, int64_t n) {
 static void grm_device(snprel_ctx *c, int method, int packed, int diagadj, double mul, double *trace_xtx) {
     const int64_t n = c->n_samp;
     if (!full_window(c) && !packed) fail("a row window returns the packed upper triangle only (useMatrix)");
+    output_wait(c);
     DevBuf<double> &o = c->scr_out;
     o.alloc(win_out_count(c, packed));
     FinalArgs a{};
@@ -1542,7 +1543,7 @@ void grm_finish(snprel_ctx *c, int method, double *out, int packed) {
         return;
     }
     grm_device(c, method, packed, 0, method == SNPREL_GRM_EIGMIX ? 2.0 : 1.0, nullptr);
-    d2h(c, out, o.p, win_out_count(c, packed));
+    deliver(c, out, o.p, win_out_count(c, packed));
 }
 
 void pca_finish(snprel_ctx *c, int eigen_cnt, int bayesian, double *genmat, double *trace_xtx,

@@ -656,3 +656,50 @@ def test_streamed_ingest_falls_back_when_the_guess_fails():
         streamed, fallbacks = c.stream_stats()
         assert streamed + fallbacks == 1
         assert relerr(got, O.grm_gcta(g)) < TOL
+
+
+def test_async_output_of_row_windows():
+    """snprel_set_async_output: the device-to-host copy of window w is only queued when the finishing call
+    returns (it overlaps the next window's accumulate); after output_wait the slices equal the blocking ones."""
+    import torch
+    n, m = 1100, 6000
+    g = O.synth_geno(n, m, seed=61, miss_rate=0.02)
+    with S.Context(0) as c:
+        c.geno_begin(n, m)
+        c.geno_push_u8(g)
+        ref_ibs = c.ibs_ave(packed=True)
+        ref_king = c.king_robust(None, packed=True)
+        ref_grm = c.grm("GCTA", packed=True)[0]
+        c.set_async_output(True)
+        bufs = [torch.empty(n * 256, dtype=torch.float64, pin_memory=True).numpy() for _ in range(8)]
+        for name, ref in (("ibs", [ref_ibs]), ("king", list(ref_king)), ("grm", [ref_grm])):
+            got = [np.full(n * (n + 1) // 2, np.nan) for _ in ref]
+            pos, pending = 0, None
+            for k, (r0, h) in enumerate(c.windows(256)):
+                c.set_row_window(r0, h)
+                cnt = c.window_count()
+                mine = bufs[2 * (k % 4): 2 * (k % 4) + 2]           # a buffer pair is reused four windows later
+                if name == "ibs":
+                    out = [c.ibs_ave(packed=True, out=mine[0])]
+                elif name == "king":
+                    out = list(c.king_robust(None, packed=True, out=mine))
+                else:
+                    out = [c.grm("GCTA", packed=True, out=mine[0])[0]]
+                if pending is not None:                              # the previous window: wait, then read
+                    c.output_wait()
+                # (the call above already waited for the previous copy before rewriting the device scratch)
+                if pending is not None:
+                    p0, pc, pout = pending
+                    for gk, o in zip(got, pout):
+                        gk[p0:p0 + pc] = o[:pc]
+                pending = (pos, cnt, out)
+                pos += cnt
+            c.output_wait()
+            p0, pc, pout = pending
+            for gk, o in zip(got, pout):
+                gk[p0:p0 + pc] = o[:pc]
+            c.set_row_window(0, 0)
+            for gk, r in zip(got, ref):
+                assert np.array_equal(gk, r, equal_nan=True), name
+        c.set_async_output(False)
+        assert np.array_equal(c.ibs_ave(packed=True), ref_ibs)
