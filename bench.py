@@ -252,7 +252,7 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     REDUCE = os.environ.get("SNPREL_REDUCE", "peer")      # "peer" (default) or "nccl"
-    link_bytes, reduce_ms = [0], [0.0]
+    link_bytes, reduce_ms, reduce_kind, reduce_note = [0], [0.0], [REDUCE], [None]
 
     def step():
         """one pass of the hot path; returns device ms (library events + collective events)"""
@@ -264,10 +264,17 @@ def run_ours(args):
         ctx.accumulate(est, plan)
         ms = ctx.last_step_ms()
         ev0.record()
-        if REDUCE == "nccl":
+        if reduce_kind[0] == "nccl":
             D.allreduce_buffers(ctx.reduce_buffers(), device=dev)
         else:       # the library's own peer-memory reduction (CUDA IPC + NVLink loads), upper triangle only
-            link_bytes[0] = D.peer_reduce_buffers(ctx, rank, world, device=dev)
+            try:
+                link_bytes[0] = D.peer_reduce_buffers(ctx, rank, world, device=dev)
+            except S.SNPRelError as e:
+                # CUDA IPC can be unavailable in a container (every rank sees the same failure at the same point,
+                # before any data moved): the same sums go through NCCL instead, and the line says so
+                reduce_kind[0] = "nccl"
+                reduce_note[0] = f"peer-memory reduction unavailable here ({e}); NCCL all-reduce used"
+                D.allreduce_buffers(ctx.reduce_buffers(), device=dev)
         ev1.record()
         torch.cuda.synchronize()
         ms += ev0.elapsed_time(ev1)
@@ -328,7 +335,7 @@ def run_ours(args):
         tc = time.perf_counter()
         if world > 1:
             # the caller's matrix lands in ONE host buffer: the partial planes are reduced to rank 0, which finishes
-            D.accumulate_sharded(ctx, est, device=dev, reduce=REDUCE, root=0)
+            D.accumulate_sharded(ctx, est, device=dev, reduce=reduce_kind[0], root=0)
         td = time.perf_counter()
         if rank == 0:
             e2e_last.update(ctx.pca(genmat_only=True, genmat_out=ho))
@@ -406,7 +413,7 @@ def run_ours(args):
                 ("config4_king_100k_x_1M_bits", "king", 100000, 1000000, "bits")]
         for key, en, bn, bm, engine in legs:
             bidx = O.scattered_samples(bn, 24, seed=7)
-            res, kept = run_pair_config(local, en, bn, bm, rank, world, engine, REDUCE, -1, MISS, bidx, True)
+            res, kept = run_pair_config(local, en, bn, bm, rank, world, engine, reduce_kind[0], -1, MISS, bidx, True)
             perr, pcnt = O.check_pair_rows(en, bidx, bm, kept, seed=SEED, miss_rate=MISS)
             tt = torch.tensor([perr], dtype=torch.float64, device=dev)
             tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
@@ -479,7 +486,8 @@ def run_ours(args):
         extra["strong"] = strong
     extra.update(big)
     if world > 1:
-        extra["reduction"] = {"kind": REDUCE, "ms_last_step": reduce_ms[0], "link_bytes_this_rank": int(link_bytes[0])}
+        extra["reduction"] = {"kind": reduce_kind[0], "ms_last_step": reduce_ms[0], "link_bytes_this_rank": int(link_bytes[0]),
+                              "note": reduce_note[0]}
     if world == 1 and not args.no_extra:
         ctx.close()
         extra["pair_counters"] = pair_counter_legs(local, None)
