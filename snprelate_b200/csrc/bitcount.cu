@@ -17,6 +17,7 @@ namespace snprel {
 constexpr int BT = 64;        // pairs tile edge
 constexpr int BKW = 9;        // 64-SNP words per pipeline stage (three carry-save groups of 3)
 constexpr int BTHREADS = 256;
+constexpr int PAIR_DIRECT_DEFAULT = 0;   // streams that bypass the carry-save adder by default (see pair_update3)
 
 template <int EST> struct EstTraits;
 template <> struct EstTraits<SNPREL_EST_IBS> { static constexpr int NC = 3; };          // ibs0, ibs2, mask
@@ -79,7 +80,9 @@ __device__ __forceinline__ void pair_streams(uint32_t (&st)[EstTraits<EST>::NC],
 // profiles/r01_ibs_pair_count_full.txt).  Three words of every stream go through a carry-save
 // adder first (sum = a^b^c, carry = maj(a,b,c): two LOP3 on the full-rate ALU pipe), so three
 // populations cost two POPCs: pop(a)+pop(b)+pop(c) = pop(sum) + 2 pop(carry).
-template <int EST>
+// DIRECT: the last DIRECT streams skip the carry-save adder and are popcounted word by word (3 POPC + 3 IMAD
+// instead of 2 LOP3 + 2 POPC + 2 IMAD per three words): it moves load from the ALU pipe to the XU / FMA pipes.
+template <int EST, int DIRECT>
 __device__ __forceinline__ void pair_update3(uint32_t (&acc)[EstTraits<EST>::NC], const uint32_t (&a1)[3],
                                              const uint32_t (&a2)[3], const uint32_t (&b1)[3],
                                              const uint32_t (&b2)[3], const uint32_t (&vb)[3],
@@ -91,6 +94,13 @@ __device__ __forceinline__ void pair_update3(uint32_t (&acc)[EstTraits<EST>::NC]
     pair_streams<EST>(s2, a1[2], a2[2], b1[2], b2[2], vb[2], hb[2]);
 #pragma unroll
     for (int k = 0; k < NC; k++) {
+        if (k >= NC - DIRECT) {
+            uint32_t t, u;
+            asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(t) : "r"((uint32_t)__popc(s0[k])), "r"(acc[k]));
+            asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(u) : "r"((uint32_t)__popc(s1[k])), "r"(t));
+            asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(acc[k]) : "r"((uint32_t)__popc(s2[k])), "r"(u));
+            continue;
+        }
         uint32_t sum = s0[k] ^ s1[k] ^ s2[k];
         uint32_t carry = (s0[k] & s1[k]) | (s2[k] & (s0[k] ^ s1[k]));
         // acc += pop(sum) + 2 pop(carry) as two IMADs: the FMA pipe is idle in this kernel while the
@@ -101,7 +111,7 @@ __device__ __forceinline__ void pair_update3(uint32_t (&acc)[EstTraits<EST>::NC]
     }
 }
 
-template <int EST>
+template <int EST, int DIRECT>
 __global__ void __launch_bounds__(BTHREADS, EstTraits<EST>::NC <= 3 ? 2 : 1)
 pair_count_kernel(const uint4 *__restrict__ planes, uint32_t *__restrict__ cnt, int64_t n_pad,
                   int64_t n_words, int words_per_split, RowWin win) {
@@ -167,7 +177,7 @@ pair_count_kernel(const uint4 *__restrict__ planes, uint32_t *__restrict__ cnt, 
 #pragma unroll
                     for (int r = 0; r < 4; r++) {
                         const uint32_t a1[3] = {a[r][0].x, a[r][1].x, a[r][2].x}, a2[3] = {a[r][0].z, a[r][1].z, a[r][2].z};
-                        pair_update3<EST>(acc[r][q], a1, a2, b1, b2, vb, hb);
+                        pair_update3<EST, DIRECT>(acc[r][q], a1, a2, b1, b2, vb, hb);
                     }
                 }
                 {   // high 32 SNPs
@@ -177,7 +187,7 @@ pair_count_kernel(const uint4 *__restrict__ planes, uint32_t *__restrict__ cnt, 
 #pragma unroll
                     for (int r = 0; r < 4; r++) {
                         const uint32_t a1[3] = {a[r][0].y, a[r][1].y, a[r][2].y}, a2[3] = {a[r][0].w, a[r][1].w, a[r][2].w};
-                        pair_update3<EST>(acc[r][q], a1, a2, b1, b2, vb, hb);
+                        pair_update3<EST, DIRECT>(acc[r][q], a1, a2, b1, b2, vb, hb);
                     }
                 }
             }
@@ -216,8 +226,14 @@ static void launch_pair_count(snprel_ctx *c) {
     int64_t wps = round_up((n_words + splits - 1) / splits, BKW);
     splits = (n_words + wps - 1) / wps;
     dim3 grid((unsigned)tiles, (unsigned)wtiles, (unsigned)splits);
-    pair_count_kernel<EST><<<grid, BTHREADS, 0, c->stream>>>(c->planes.p, c->cnt.p, npad, n_words,
-                                                            (int)wps, win);
+    // streams popcounted without the carry-save adder (experiment knob: debug flags 0x400 / 0x800 / 0xC00 = 1 / 2 / 3)
+    const int direct = (c->debug_flags & 0xC00u) ? (int)((c->debug_flags >> 10) & 3u) : PAIR_DIRECT_DEFAULT;
+    switch (direct) {
+        case 1: pair_count_kernel<EST, 1><<<grid, BTHREADS, 0, c->stream>>>(c->planes.p, c->cnt.p, npad, n_words, (int)wps, win); break;
+        case 2: pair_count_kernel<EST, 2><<<grid, BTHREADS, 0, c->stream>>>(c->planes.p, c->cnt.p, npad, n_words, (int)wps, win); break;
+        case 3: pair_count_kernel<EST, 3><<<grid, BTHREADS, 0, c->stream>>>(c->planes.p, c->cnt.p, npad, n_words, (int)wps, win); break;
+        default: pair_count_kernel<EST, 0><<<grid, BTHREADS, 0, c->stream>>>(c->planes.p, c->cnt.p, npad, n_words, (int)wps, win); break;
+    }
     KERNEL_CHECK(c);
 }
 
