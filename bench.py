@@ -180,7 +180,8 @@ def pair_counter_legs(local, clocks_mhz):
     pk = measured_peaks_r02()
     out = {"n_samp": X_N, "n_snp": X_M, "miss_rate": MISS,
            "note": "device time of planes + pair kernel from resident 2-bit genotypes (snprel_time_accumulate); "
-                   "alu_frac = ALU-pipe instructions issued / measured LOP3 issue peak (profiles/peaks_r02.json) at the max clock"}
+                   "alu_frac = ALU-pipe instructions issued / measured LOP3 issue peak (profiles/peaks_r02.json) at the max clock; "
+                   "the POPC (XU pipe) ceiling is the nearer one, see DESIGN.md section 4"}
     idx = O.scattered_samples(X_N, 24, seed=7)
     sub = O.synth_geno(0, X_M, seed=SEED + 1, miss_rate=MISS, samples=idx)
     refs = {"ibs": O.ibs_counts(sub), "king": O.king_robust_counts(sub), "beta": O.beta_counts(sub)}
@@ -213,7 +214,9 @@ def pair_counter_legs(local, clocks_mhz):
                     rec["alu_ops_per_word_pair"] = PAIR_ALU_OPS[name]
                     if pk and "alu_lop3" in pk:
                         rec["alu_frac_of_measured_lop3_peak"] = wp_per_s * PAIR_ALU_OPS[name] / pk["alu_lop3"]["thread_inst_per_s"]
-                        rec["popc_frac_of_measured_popc_peak"] = wp_per_s * PAIR_POPC[name] / pk["alu_popc"]["thread_inst_per_s"]
+                        # POPC next to LOP3 traffic runs at 16 per SM and clock (profiles/r02_pair_variants.log), not at the
+                        # 31.9 of a pure POPC chain (peaks_r02.json alu_popc)
+                        rec["popc_frac_of_16_per_sm_clk"] = wp_per_s * PAIR_POPC[name] / (16.0 * pk["sms"] * pk["sm_max_mhz"] * 1e6)
                 leg[engine] = rec
                 if not exact:
                     raise SystemExit(f"extra leg {name}/{engine}: counters differ from the oracle")
