@@ -386,13 +386,34 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
         tc_fence_after();
         const int quarter = warp & 3;
         const int colhalf = (warp - FIRST_PROD_WARP) >> 2;
-        const int row = quarter * 32 + lane;
-        const long long gi = (long long)item.tm * TM2 + (long long)rank * HM + (row & ~15) + core_pos_to_sample(row & 15);
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        // A TMEM lane is a ROW: straight out of tcgen05.ld a warp's 32 lanes would hit 32 different rows of the
+        // plane with every reduction (32 sectors per instruction, 65 536 sector reductions per CTA and item: the
+        // 40 us per item that kept the tensor pipe at 90 %).  The block is transposed through the operand
+        // stages (free once the last MMA has been committed), so that a warp's reduction covers 32
+        // consecutive columns of ONE row.
+        long long *stage = reinterpret_cast<long long *>(smem + (size_t)(warp - FIRST_PROD_WARP) * (32 * 33 * 8));
+        const long long row_base = (long long)item.tm * TM2 + (long long)rank * HM + quarter * 32;
+        auto flush = [&](const long long (&val)[32], long long *plane, long long tn_eff, int col0) {
+#pragma unroll
+            for (int k = 0; k < 32; k++) stage[lane * 33 + k] = val[k];
+            __syncwarp();
+            const int col = col0 + lane;
+            const long long gj = tn_eff * TN2 + (col & ~15) + core_pos_to_sample(col & 15);
+            const bool col_ok = gj < P.n_samp;
+#pragma unroll 4
+            for (int r = 0; r < 32; r++) {
+                const long long v = stage[r * 33 + lane];
+                const long long gr = row_base + (r & ~15) + core_pos_to_sample(r & 15);
+                if (v != 0 && col_ok && gr < P.n_samp && (!P.upper_only || gj >= gr))
+                    atomicAdd(reinterpret_cast<unsigned long long *>(plane + (gr - P.row0) * P.ld + gj), (unsigned long long)v);
+            }
+            __syncwarp();
+        };
         // two digit passes that feed the same plane leave as ONE 64-bit atomic per entry
         const bool combine = NP == 2 && pd[0].plane == pd[NP - 1].plane;
         if (combine) {
-            long long *outp = P.out + (long long)pd[0].plane * P.plane_stride + (gi - P.row0) * P.ld;
+            long long *plane = P.out + (long long)pd[0].plane * P.plane_stride;
             const long long mul0 = 1ll << pd[0].shift, mul1 = 1ll << pd[NP - 1].shift;
 #pragma unroll 1
             for (int cc = 0; cc < 4; cc++) {
@@ -401,22 +422,16 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
                 uint32_t v0[32], v1[32];
                 tmem_ld32(lane_base + (uint32_t)col0, v0);
                 tmem_ld32(lane_base + (uint32_t)(TN2 + col0), v1);
-                if (gi < P.n_samp) {
+                long long val[32];
 #pragma unroll
-                    for (int k = 0; k < 32; k++) {
-                        const int col = col0 + k;
-                        const long long gj = (long long)item.tn * TN2 + (col & ~15) + core_pos_to_sample(col & 15);
-                        const long long val = (long long)(int)v0[k] * mul0 + (long long)(int)v1[k] * mul1;
-                        if (val != 0 && gj < P.n_samp && (!P.upper_only || gj >= gi))
-                            atomicAdd(reinterpret_cast<unsigned long long *>(outp + gj), (unsigned long long)val);
-                    }
-                }
+                for (int k = 0; k < 32; k++) val[k] = (long long)(int)v0[k] * mul0 + (long long)(int)v1[k] * mul1;
+                flush(val, plane, (long long)item.tn, col0);
             }
         } else {
 #pragma unroll 1
             for (int a = 0; a < 2; a++) {        // accumulator a = pass (a / NB), B tile (a % NB)
                 const int q = a / NB, bt = a % NB;
-                long long *outp = P.out + (long long)pd[q].plane * P.plane_stride + (gi - P.row0) * P.ld;
+                long long *plane = P.out + (long long)pd[q].plane * P.plane_stride;
                 const long long mul = 1ll << pd[q].shift;
 #pragma unroll 1
                 for (int cc = 0; cc < 4; cc++) {
@@ -424,17 +439,10 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
                     if (col0 >= ncols[bt]) break;
                     uint32_t v[32];
                     tmem_ld32(lane_base + (uint32_t)(a * TN2 + col0), v);
-                    if (gi < P.n_samp) {
+                    long long val[32];
 #pragma unroll
-                        for (int k = 0; k < 32; k++) {
-                            const int col = col0 + k;
-                            const long long gj = ((long long)item.tn + bt) * TN2 + (col & ~15) + core_pos_to_sample(col & 15);
-                            const int val = (int)v[k];
-                            if (val != 0 && gj < P.n_samp && (!P.upper_only || gj >= gi))
-                                atomicAdd(reinterpret_cast<unsigned long long *>(outp + gj),
-                                          (unsigned long long)((long long)val * mul));
-                        }
-                    }
+                    for (int k = 0; k < 32; k++) val[k] = (long long)(int)v[k] * mul;
+                    flush(val, plane, (long long)item.tn + bt, col0);
                 }
             }
         }
