@@ -77,6 +77,9 @@ int snprel_geno_push_2b(snprel_ctx *ctx, const uint8_t *packed, int64_t cnt,
 int snprel_geno_push_2b_async(snprel_ctx *ctx, const uint8_t *packed, int64_t cnt, int64_t row_bytes);
 int snprel_geno_wait(snprel_ctx *ctx);
 int snprel_stream_stats(snprel_ctx *ctx, int64_t *streamed, int64_t *fallbacks);
+/* Per-item clock stamps of the last table-Gram launch made with snprel_debug_flags(ctx, 1) (tools/k1_trace.py):
+ * out[items][8] = entry, set-up done, first MMA, last commit issued, MMAs complete, epilogue done, exit, stages. */
+int snprel_k1_trace(snprel_ctx *ctx, int64_t *out, int64_t capacity_items, int64_t *items);
 /* device time from the first asynchronous copy chunk being queued to the last one having arrived */
 int snprel_stream_last_copy_ms(snprel_ctx *ctx, double *ms);
 /* Append `cnt` SNPs straight from the payload of an uncompressed GDS dBit2 genotype node

@@ -105,6 +105,7 @@ def load_library():
         "snprel_geno_wait": [p],
         "snprel_stream_stats": [p, C.POINTER(i64), C.POINTER(i64)],
         "snprel_stream_last_copy_ms": [p, C.POINTER(dbl)],
+        "snprel_k1_trace": [p, p, i64, C.POINTER(i64)],
         "snprel_geno_seek": [p, i64],
         "snprel_geno_commit": [p, i64],
         "snprel_geno_device_rows": [p, C.POINTER(p), C.POINTER(i64), C.POINTER(i64)],
@@ -168,7 +169,7 @@ EXPORTED_SYMBOLS = [
     "snprel_multi_set_row_window", "snprel_multi_set_count_engine", "snprel_multi_accumulate", "snprel_multi_last_reduce",
     "snprel_geno_seek", "snprel_geno_device_rows", "snprel_geno_commit",
     "snprel_multi_geno_begin_replicated", "snprel_multi_geno_gather", "snprel_multi_grm_tiled",
-    "snprel_set_async_output", "snprel_output_wait", "snprel_geno_push_2b_async", "snprel_geno_wait", "snprel_stream_stats", "snprel_stream_last_copy_ms",
+    "snprel_set_async_output", "snprel_output_wait", "snprel_geno_push_2b_async", "snprel_geno_wait", "snprel_stream_stats", "snprel_stream_last_copy_ms", "snprel_k1_trace",
     "snprel_reduce_ipc_export", "snprel_peer_reduce_open", "snprel_peer_reduce_phase", "snprel_peer_reduce_close",
 ]
 
@@ -271,6 +272,14 @@ class Context:
         a, b = C.c_int64(), C.c_int64()
         self._ck(self.lib.snprel_stream_stats(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def k1_trace(self):
+        """[items, 8] clock64 stamps of the last table-Gram launch (after debug_flags(1))."""
+        n = C.c_int64()
+        self._ck(self.lib.snprel_k1_trace(self.h, None, 0, C.byref(n)))
+        out = np.zeros((max(n.value, 1), 8), dtype=np.int64)
+        self._ck(self.lib.snprel_k1_trace(self.h, _ptr(out), n.value, C.byref(n)))
+        return out[: n.value]
 
     def stream_last_copy_ms(self):
         ms = C.c_double()

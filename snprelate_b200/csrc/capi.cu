@@ -161,6 +161,17 @@ int snprel_stream_stats(snprel_ctx *c, int64_t *streamed, int64_t *fallbacks) {
     if (fallbacks) *fallbacks = c->stream_fallbacks;
     API_END(c)
 }
+// clock stamps of the last K1 launch made with snprel_debug_flags(ctx, 1): out[items][8] (entry, set-up done,
+// first MMA, last commit issued, MMAs complete, epilogue done, exit, stages); returns the item count in *items
+int snprel_k1_trace(snprel_ctx *c, int64_t *out, int64_t capacity_items, int64_t *items) {
+    API_BEGIN(c)
+    if (items) *items = c->trace_items;
+    if (out && c->scr_trace.p && c->trace_items > 0) {
+        const int64_t n = std::min<int64_t>(capacity_items, c->trace_items);
+        CUDA_CHECK(cudaMemcpy(out, c->scr_trace.p, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    }
+    API_END(c)
+}
 int snprel_stream_last_copy_ms(snprel_ctx *c, double *ms) {
     API_BEGIN_STREAMING(c)
     if (ms) *ms = c->last_copy_ms;

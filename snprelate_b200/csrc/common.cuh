@@ -176,6 +176,8 @@ struct snprel_ctx {
     snprel::DevBuf<int> scr_flags;        // [0] digit overflow, [1] pipeline error
     snprel::DevBuf<double> scr_plan;      // plan statistics [3]
     snprel::DevBuf<uint8_t> scr_items, scr_passes;   // K1 work items / pass descriptors (slices, see gram_tc_run)
+    snprel::DevBuf<long long> scr_trace;  // [items][8] clock stamps of the last K1 launch (debug flag 1)
+    int64_t trace_items = 0;
     uint8_t *stage_host = nullptr;        // mapped pinned staging of the same slices
     size_t stage_bytes = 0, stage_used = 0;
     struct ConstTab {

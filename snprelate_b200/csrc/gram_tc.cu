@@ -107,6 +107,7 @@ struct Params {
     uint32_t sh32;
     int box32;               // genotype boxes are 32 bytes wide with the 32-byte TMA swizzle (else 16 bytes, plain)
     int *error_flag;
+    long long *trace;        // optional [items][8] clock64 stamps of the leader CTA (snprel_debug_flags 1, tools/k1_trace.py)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -203,6 +204,11 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
     const int st_begin = item.st_begin;
     const int nst = item.st_end - item.st_begin;   // identical in both CTAs of the pair
     if (nst <= 0) return;
+    long long *tr = (P.trace && cluster_ctarank() == 0) ? P.trace + (long long)(blockIdx.x >> 1) * 8 : nullptr;
+    if (tr && threadIdx.x == 0) {
+        tr[0] = clock64();
+        tr[7] = nst;
+    }
     int ncols[NB];
 #pragma unroll
     for (int b = 0; b < NB; b++) ncols[b] = item.ncols[b];
@@ -231,6 +237,7 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
     cluster_sync();          // peer barriers are initialised before anyone arrives remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    if (tr && threadIdx.x == 0) tr[1] = clock64();
 
     if (warp == 0) {
         // ===================== MMA issuer (leader CTA only) =====================
@@ -243,6 +250,7 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
                 const uint32_t phase = (uint32_t)(it / NSTAGE) & 1u;
                 mbar_wait_cluster(full_bar(s), phase, P.error_flag, 1);
                 tc_fence_after();
+                if (tr && it == 0 && lane == 0) tr[2] = clock64();
                 if (lane == 0) {
                     const uint32_t stage_addr = smem_base + s * STAGE_BYTES;
 #pragma unroll
@@ -264,6 +272,7 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
                 __syncwarp();
             }
             if (lane == 0) umma2_commit_mc(accum_bar);
+            if (tr && lane == 0) tr[3] = clock64();
             __syncwarp();
         }
     } else if (warp == 1) {
@@ -384,6 +393,7 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
         // ===================== epilogue (each CTA drains its own 128 rows) =====================
         mbar_wait(accum_bar, 0, P.error_flag, 3);
         tc_fence_after();
+        if (tr && threadIdx.x == 32 * FIRST_PROD_WARP) tr[4] = clock64();
         const int quarter = warp & 3;
         const int colhalf = (warp - FIRST_PROD_WARP) >> 2;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -447,6 +457,7 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
             }
         }
     }
+    if (tr && threadIdx.x == 32 * FIRST_PROD_WARP) tr[5] = clock64();
     tc_fence_before();
     __syncthreads();
     cluster_sync();          // both CTAs are done with TMEM and with each other's barriers
@@ -454,6 +465,7 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
         tc_fence_after();
         tmem_dealloc2(tmem_base, TMEM_COLS);
     }
+    if (tr && threadIdx.x == 0) tr[6] = clock64();
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -761,6 +773,13 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
     P.sh32 = 32;
     P.box32 = box32 ? 1 : 0;
     P.error_flag = derr;
+    P.trace = nullptr;
+    if (c->debug_flags & 1u) {          // per-item clock stamps for tools/k1_trace.py
+        c->scr_trace.alloc(items.size() * 8);
+        c->scr_trace.zero(c->stream);
+        P.trace = c->scr_trace.p;
+        c->trace_items = (int64_t)items.size();
+    }
     table_gram_kernel3<<<dim3((unsigned)(2 * items.size())), THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
     KERNEL_CHECK(c);
     c->hot_launches++;
