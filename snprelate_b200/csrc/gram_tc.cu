@@ -207,7 +207,7 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
     long long *tr = (P.trace && cluster_ctarank() == 0) ? P.trace + (long long)(blockIdx.x >> 1) * 8 : nullptr;
     if (tr && threadIdx.x == 0) {
         tr[0] = clock64();
-        tr[7] = nst;
+        tr[7] = (long long)nst | ((long long)item.mode << 32) | ((long long)(item.ncols[0] + item.ncols[1]) << 40);
     }
     int ncols[NB];
 #pragma unroll

@@ -12,6 +12,18 @@ ms = c.time_accumulate(0, 1)
 hot = c.last_hot_kernel()[0]
 t = c.k1_trace()
 t = t[(t[:, 0] > 0) & (t[:, 6] > 0)]
+mode = (t[:, 7] >> 32) & 0xFF
+cols = t[:, 7] >> 40
+t = t.copy()
+t[:, 7] &= 0xFFFFFFFF
+for md in (0, 1):
+    for nc in sorted(set(cols[mode == md].tolist())):
+        sel = (mode == md) & (cols == nc)
+        if sel.sum() == 0:
+            continue
+        per_stage = (t[sel, 3] - t[sel, 2]) / np.maximum(t[sel, 7], 1)
+        print(f"mode {md} (B columns {nc:3d}): {int(sel.sum()):6d} items, main loop {np.median(per_stage):7.1f} clocks per stage (median), "
+              f"p90 {np.percentile(per_stage, 90):7.1f}, epilogue {np.median(t[sel, 5] - t[sel, 4]):8.0f}")
 full = t[t[:, 7] >= np.median(t[:, 7])]
 names = ["set-up (entry -> cluster sync)", "ramp (-> first MMA)", "main loop (-> last commit issued)", "drain (-> MMAs complete)",
          "epilogue", "exit (fences, cluster sync, dealloc)"]
