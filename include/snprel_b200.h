@@ -372,9 +372,12 @@ int snprel_invalidate(snprel_ctx *ctx);
  * (n_samp x n_samp row-major, all entries). */
 int snprel_table_gram(snprel_ctx *ctx, const int8_t *tabA /*[n_snp][4]*/,
                       const int8_t *tabB /*[4]*/, int64_t *out);
-/* Test hooks (OR of): 2 = one CTA pair walks the whole SNP range of a tile (no SNP splits),
- * 4 = always use the dense eigen solver, 8 = experimental: issue the tensor-pass launches of a
- * step on two streams (they only meet in commutative atomics) so that wave tails overlap. */
+/* Test / experiment hooks (OR of): 1 = record per-item clock stamps of the table Gram (snprel_k1_trace);
+ * 2 = one CTA pair walks the whole SNP range of a tile (no SNP splits); 4 = always use the dense eigen
+ * solver; table-Gram A/B knobs measured in profiles/r02_k1_variants*.log: 16 = the round-1 16-byte genotype
+ * boxes, 32 / 64 = no / 256-byte L2 promotion, 128 = group-major item order, 256 = no SNP segments,
+ * 0xN000 = N SNP segments; pair counters: 0x400 / 0x800 / 0xC00 = 1 / 2 / 3 streams straight to POPC
+ * (profiles/r02_pair_variants.log).  None of them changes a result. */
 int snprel_debug_flags(snprel_ctx *ctx, uint32_t flags);
 
 /* Asynchronous result delivery for row-window pipelines (C4 / C5 style jobs): with on = 1 snprel_ibs_ave,
