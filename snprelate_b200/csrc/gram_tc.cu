@@ -179,7 +179,7 @@ __device__ __forceinline__ uint32_t make_idesc2(int ncols) {
            ((uint32_t)(TM2 >> 4) << 24);
 }
 
-template <int NP, int NB>
+template <int NP, int NB, bool TRACE>
 __device__ __forceinline__ void gram_item(const Params &P, const Item &item, const CUtensorMap *tmap, uint8_t *smem) {
     static_assert(NP * NB == 2, "two TMEM accumulators of 256 columns");
     constexpr int PF_DEPTH = NB == 1 ? 3 : 2;
@@ -204,8 +204,9 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
     const int st_begin = item.st_begin;
     const int nst = item.st_end - item.st_begin;   // identical in both CTAs of the pair
     if (nst <= 0) return;
-    long long *tr = (P.trace && cluster_ctarank() == 0) ? P.trace + (long long)(blockIdx.x >> 1) * 8 : nullptr;
-    if (tr && threadIdx.x == 0) {
+    // (clock stamps exist in the TRACE instantiation only: the shipped path carries no extra code)
+    long long *tr = (TRACE && P.trace && cluster_ctarank() == 0) ? P.trace + (long long)(blockIdx.x >> 1) * 8 : nullptr;
+    if (TRACE && tr && threadIdx.x == 0) {
         tr[0] = clock64();
         tr[7] = (long long)nst | ((long long)item.mode << 32) | ((long long)(item.ncols[0] + item.ncols[1]) << 40);
     }
@@ -237,7 +238,7 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
     cluster_sync();          // peer barriers are initialised before anyone arrives remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    if (tr && threadIdx.x == 0) tr[1] = clock64();
+    if (TRACE && tr && threadIdx.x == 0) tr[1] = clock64();
 
     if (warp == 0) {
         // ===================== MMA issuer (leader CTA only) =====================
@@ -250,7 +251,7 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
                 const uint32_t phase = (uint32_t)(it / NSTAGE) & 1u;
                 mbar_wait_cluster(full_bar(s), phase, P.error_flag, 1);
                 tc_fence_after();
-                if (tr && it == 0 && lane == 0) tr[2] = clock64();
+                if (TRACE && tr && it == 0 && lane == 0) tr[2] = clock64();
                 if (lane == 0) {
                     const uint32_t stage_addr = smem_base + s * STAGE_BYTES;
 #pragma unroll
@@ -272,7 +273,7 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
                 __syncwarp();
             }
             if (lane == 0) umma2_commit_mc(accum_bar);
-            if (tr && lane == 0) tr[3] = clock64();
+            if (TRACE && tr && lane == 0) tr[3] = clock64();
             __syncwarp();
         }
     } else if (warp == 1) {
@@ -393,7 +394,7 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
         // ===================== epilogue (each CTA drains its own 128 rows) =====================
         mbar_wait(accum_bar, 0, P.error_flag, 3);
         tc_fence_after();
-        if (tr && threadIdx.x == 32 * FIRST_PROD_WARP) tr[4] = clock64();
+        if (TRACE && tr && threadIdx.x == 32 * FIRST_PROD_WARP) tr[4] = clock64();
         const int quarter = warp & 3;
         const int colhalf = (warp - FIRST_PROD_WARP) >> 2;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -457,7 +458,7 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
             }
         }
     }
-    if (tr && threadIdx.x == 32 * FIRST_PROD_WARP) tr[5] = clock64();
+    if (TRACE && tr && threadIdx.x == 32 * FIRST_PROD_WARP) tr[5] = clock64();
     tc_fence_before();
     __syncthreads();
     cluster_sync();          // both CTAs are done with TMEM and with each other's barriers
@@ -465,17 +466,26 @@ __device__ __forceinline__ void gram_item(const Params &P, const Item &item, con
         tc_fence_after();
         tmem_dealloc2(tmem_base, TMEM_COLS);
     }
-    if (tr && threadIdx.x == 0) tr[6] = clock64();
+    if (TRACE && tr && threadIdx.x == 0) tr[6] = clock64();
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-table_gram_kernel3(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap tmap) {
+template <bool TRACE>
+__device__ __forceinline__ void table_gram_body(const Params &P, const CUtensorMap *tmap) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const Item item = P.items[blockIdx.x >> 1];
     if (item.mode == 0)
-        gram_item<2, 1>(P, item, &tmap, smem);
+        gram_item<2, 1, TRACE>(P, item, tmap, smem);
     else
-        gram_item<1, 2>(P, item, &tmap, smem);
+        gram_item<1, 2, TRACE>(P, item, tmap, smem);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+table_gram_kernel3(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap tmap) {
+    table_gram_body<false>(P, &tmap);
+}
+// the same kernel with per-item clock stamps (snprel_debug_flags 1, tools/k1_trace.py)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+table_gram_kernel3_traced(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap tmap) {
+    table_gram_body<true>(P, &tmap);
 }
 
 }  // namespace tc2
@@ -758,6 +768,7 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
 
     if (!c->gram_attr_done) {   // per device: a process may hold contexts on several GPUs
         CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(table_gram_kernel3_traced, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         c->gram_attr_done = true;
     }
 
@@ -780,7 +791,10 @@ void gram_tc_run(snprel_ctx *c, const GramPass *passes, int npass, long long *ou
         P.trace = c->scr_trace.p;
         c->trace_items = (int64_t)items.size();
     }
-    table_gram_kernel3<<<dim3((unsigned)(2 * items.size())), THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
+    if (P.trace)
+        table_gram_kernel3_traced<<<dim3((unsigned)(2 * items.size())), THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
+    else
+        table_gram_kernel3<<<dim3((unsigned)(2 * items.size())), THREADS, SMEM_BYTES, c->stream>>>(P, tmap);
     KERNEL_CHECK(c);
     c->hot_launches++;
     c->hot_items = (int64_t)items.size();
