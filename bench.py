@@ -330,6 +330,7 @@ def run_ours(args):
     def e2e_step():
         ta = time.perf_counter()
         ctx.geno_begin(N_SAMP, N_SNP)
+        ctx.set_snp_origin(rank * N_SNP)     # this rank's SNP block of the data set (keys the rounding draws)
         tb = time.perf_counter()
         if world == 1 and not args.sync_ingest:
             ctx.geno_push_2b_async(hg)       # returns at once; snprel_pca consumes the chunks as they arrive
@@ -453,6 +454,9 @@ def run_ours(args):
 
     passes = {"digits_U": int(pl.digits), "digits_W": int(pl.digits_w), "frac_bits": int(pl.frac_bits),
               "frac_bits_W": int(pl.frac_bits_w),
+              "rounding": ("randomised (unbiased, one draw per SNP and genotype; Hoeffding bound <= 1e-10 with probability "
+                           ">= 1 - 1e-12 over the draws)" if pl.rounding else "nearest (worst-case bound <= 1e-10)"),
+              "rounding_mode": "auto: randomised only where it needs fewer tensor passes (snprel_set_rounding)",
               "tensor_passes_per_step": int(pl.digits) + int(pl.digits_w) + int(pl.digits_d)}
     pk, pk_kind = peaks()
     traffic, tensor_pct = None, None

@@ -100,7 +100,9 @@ int snprel_geno_device_rows(snprel_ctx *ctx, void **dev_ptr, int64_t *row_bytes,
 int snprel_geno_commit(snprel_ctx *ctx, int64_t n_snp);
 /* Fill the workspace with `n_snp` synthetic SNPs on the device (counter-based
  * generator; SNP l uses global index snp_start+l so SNP shards of one data
- * set can be generated independently).  Benchmark / test input only. */
+ * set can be generated independently; a shard, i.e. snp_start beyond the write
+ * position, also sets the SNP origin, see snprel_set_snp_origin).  Benchmark /
+ * test input only. */
 int snprel_geno_synth(snprel_ctx *ctx, int64_t n_snp, uint64_t seed,
                       double maf_lo, double maf_hi, double miss_rate,
                       int64_t snp_start);
@@ -202,14 +204,28 @@ int snprel_pca(snprel_ctx *ctx, int eigen_cnt, int bayesian, double *genmat,
 int snprel_eigmix(snprel_ctx *ctx, int eigen_cnt, int diagadj, double *ibd,
                   double *afreq, double *eigval, double *eigvec);
 
-/* Rounding of the fixed-point U table of the covariance estimators (EXPERIMENTAL, default 0).
+/* Rounding of the fixed-point row table T of the covariance estimators' main passes.
  * 0: round to nearest; the format is chosen from the worst-case error bound
- *    2^-(frac_bits+1) * err_weight (proven <= tol for every entry).
- * 1: unbiased randomised rounding, one draw per (SNP, genotype) table entry; the format is chosen
- *    from the Hoeffding bound 2^-frac_bits * sqrt(err_weight * ln(2 #pairs / 1e-12)), which holds
- *    for all entries simultaneously with probability 1 - 1e-12 over the draws and needs one digit
- *    (tensor pass) less at config-2 size.  All ranks of a multi-GPU run must use the same mode. */
+ *    2^-(frac_bits+1) * err_weight (every rounding error at its maximum with the same sign).
+ * 1: unbiased randomised rounding, floor(T 2^frac_bits + u) with one uniform draw u per (SNP,
+ *    genotype) table entry from a counter-based generator keyed by the SNP's global index
+ *    (snprel_set_snp_origin).  The error of an entry is then a sum of independent zero-mean terms
+ *    of width |B_l| 2^-frac_bits, and by Hoeffding's inequality it stays below
+ *    2^-frac_bits * sqrt(1/2 sum_l B_l^2 ln(2 #pairs / 1e-12)) for ALL entries simultaneously with
+ *    probability >= 1 - 1e-12 over the draws, for any data set; sum B^2 <= 127 err_weight.  The
+ *    bound grows with sqrt(#SNPs) where the worst case grows with #SNPs: from about 5e5 SNPs on it
+ *    saves one base-256 digit of T, i.e. one of eight tensor passes at config-2 size.
+ * 2 (default): whichever of the two needs FEWER tensor passes for the requested tolerance; ties
+ *    go to 0.  snprel_plan.rounding reports what the last accumulate used.
+ * Results are a pure function of (genotypes, SNP origin, mode): run-to-run identical, and identical
+ * for any SNP sharding whose origins are the shards' global offsets.  All ranks of a multi-GPU run
+ * must use the same mode. */
 int snprel_set_rounding(snprel_ctx *ctx, int mode);
+/* Global index of this context's first SNP row (default 0; snprel_geno_begin resets it).  Only keys
+ * the rounding draws of mode 1 / 2: SNP shards of one data set must cover disjoint index ranges
+ * (snprel_multi_* and snprelate_b200/dist.py set the shard offsets). */
+int snprel_set_snp_origin(snprel_ctx *ctx, int64_t origin);
+
 
 /* The eigen step of snprel_pca / snprel_eigmix (CalcEigen, LAPACK dspevx on -C,
  * src/genPCA.cpp:1262-1346) runs in csrc/eigen.cu: a Chebyshev-filtered subspace iteration
@@ -283,7 +299,8 @@ int snprel_pca_randomized(snprel_ctx *ctx, const double *aux_mat, int aux_dim, i
  * split into `digits` balanced base-256 digits (one int8 tensor pass each) and multiplied
  * with a per-SNP INTEGER column table B_l (main passes) or the missing indicator.  The
  * quantisation error of an output entry is at most
- *   2^-(frac_bits+1) * err_weight + 2^-(frac_bits_w+1) * max_missing,
+ *   2^-(frac_bits+1) * err_weight + 2^-(frac_bits_w+1) * max_missing
+ * (first term with randomised rounding: the Hoeffding bound of snprel_set_rounding),
  * so the library picks the fewest passes for which that bound is <= tol * scale, where
  * scale is (a lower bound of) the estimator's normaliser (trace/(n-1), 2 nLocus,
  * sum 4p(1-p)).  tol defaults to 1e-10. */
@@ -305,12 +322,20 @@ typedef struct snprel_plan {
     int32_t digits_d;      /* out: digits of the denominator table                     */
     int32_t bayesian;      /* Eigenstrat only                                          */
     int32_t frac_bits_v;   /* out: fixed point of the per-sample vector sum_l R_l[g_il] */
-    int32_t reserved;
+    int32_t rounding;      /* frac_bits < 0 (library chooses): out, 0 = nearest / 1 = randomised (snprel_set_rounding);
+                              caller-fixed frac_bits: in, the rounding that goes with it */
     double diag_bound;     /* measured X >= max_i C_ii of the local SNPs (0: not measured); sum-reduced  */
     double sum_rest;       /* the part of sum_bound that is not the main T x B product; sum-reduced       */
+    double err_weight2;    /* >= max over samples of sum_l B_l[g]^2 over the local SNPs (0: not measured, 127 err_weight
+                              is used); sum-reduced.  Variance proxy of the randomised-rounding bound */
 } snprel_plan;
 
 int snprel_plan_local(snprel_ctx *ctx, int estimator, snprel_plan *plan);
+/* Host-only (no device, no context): the fixed-point format the library chooses for the given
+ * (merged) plan statistics -- fills frac_bits*, digits*, rounding exactly as snprel_accumulate
+ * would.  mode as in snprel_set_rounding; n_samp enters the union bound of mode 1.  Returns the
+ * number of tensor passes, or -1 (snprel_last_error(NULL)). */
+int snprel_plan_format(int estimator, snprel_plan *plan, int mode, int64_t n_samp);
 /* Accumulate this rank's SNPs into the device accumulators. */
 int snprel_accumulate(snprel_ctx *ctx, int estimator, const snprel_plan *plan);
 /* Enumerate the device buffers that must be sum-reduced across ranks.
@@ -415,6 +440,7 @@ int snprel_multi_geno_synth(snprel_multi *m, int64_t n_snp, uint64_t seed, doubl
                             double miss_rate, int64_t snp_start);
 int snprel_multi_set_row_window(snprel_multi *m, int64_t row0, int64_t rows);
 int snprel_multi_set_count_engine(snprel_multi *m, int engine);
+int snprel_multi_set_rounding(snprel_multi *m, int mode);      /* snprel_set_rounding on every device */
 /* plan (all devices) -> merged format -> accumulate (all devices) -> peer reduction -> mark reduced.
  * est: SNPREL_GRM_EIGENSTRAT / GCTA / CORR / EIGMIX or SNPREL_EST_IBS / KING_ROBUST / BETA.
  * root: device index (position in `devices`) that receives the reduced N x N planes; -1: every device

@@ -29,8 +29,21 @@ class Plan(C.Structure):
                 ("total_missing", C.c_int64), ("max_missing", C.c_int64), ("n_snp", C.c_int64),
                 ("frac_bits", C.c_int32), ("frac_bits_w", C.c_int32), ("frac_bits_d", C.c_int32),
                 ("digits", C.c_int32), ("digits_w", C.c_int32), ("digits_d", C.c_int32),
-                ("bayesian", C.c_int32), ("frac_bits_v", C.c_int32), ("reserved", C.c_int32),
-                ("diag_bound", C.c_double), ("sum_rest", C.c_double)]
+                ("bayesian", C.c_int32), ("frac_bits_v", C.c_int32), ("rounding", C.c_int32),
+                ("diag_bound", C.c_double), ("sum_rest", C.c_double), ("err_weight2", C.c_double)]
+
+
+ROUNDING_MODES = {"nearest": 0, "random": 1, "auto": 2}
+
+
+def plan_format(est, plan, mode="auto", n_samp=0):
+    """Host-only: the fixed-point format the library chooses for (merged) plan statistics; fills
+    frac_bits / digits / rounding of `plan` and returns the number of tensor passes."""
+    lib = load_library()
+    rc = lib.snprel_plan_format(int(est), C.byref(plan), int(ROUNDING_MODES.get(mode, mode)), int(n_samp))
+    if rc < 0:
+        raise SNPRelError(lib.snprel_last_error(None).decode())
+    return rc
 
 
 def library_path() -> str:
@@ -99,6 +112,8 @@ def load_library():
         "snprel_debug_flags": [p, u32],
         "snprel_set_count_engine": [p, i32],
         "snprel_set_rounding": [p, i32],
+        "snprel_set_snp_origin": [p, i64],
+        "snprel_plan_format": [i32, p, i32, i64],
         "snprel_set_async_output": [p, i32],
         "snprel_output_wait": [p],
         "snprel_geno_push_2b_async": [p, p, i64, i64],
@@ -122,6 +137,7 @@ def load_library():
         "snprel_multi_geno_synth": [p, i64, u64, dbl, dbl, dbl, i64],
         "snprel_multi_set_row_window": [p, i64, i64],
         "snprel_multi_set_count_engine": [p, i32],
+        "snprel_multi_set_rounding": [p, i32],
         "snprel_multi_accumulate": [p, i32, i32, i32],
         "snprel_multi_last_reduce": [p, C.POINTER(dbl), C.POINTER(i64)],
         "snprel_multi_device_count": [p],
@@ -164,6 +180,7 @@ EXPORTED_SYMBOLS = [
     "snprel_reduce_buffer_count", "snprel_reduce_buffer", "snprel_mark_reduced", "snprel_last_plan", "snprel_set_row_window", "snprel_window_count", "snprel_mem_info",
     "snprel_kernel_launches", "snprel_last_hot_kernel", "snprel_time_accumulate", "snprel_time_finish", "snprel_last_step_ms", "snprel_invalidate",
     "snprel_table_gram", "snprel_debug_flags", "snprel_set_count_engine", "snprel_last_eigen_info", "snprel_set_rounding",
+    "snprel_set_snp_origin", "snprel_plan_format", "snprel_multi_set_rounding",
     "snprel_device_count", "snprel_multi_create", "snprel_multi_destroy", "snprel_multi_last_error", "snprel_multi_device_count", "snprel_multi_ctx",
     "snprel_multi_geno_begin", "snprel_multi_geno_push_u8", "snprel_multi_geno_push_2b", "snprel_multi_geno_synth",
     "snprel_multi_set_row_window", "snprel_multi_set_count_engine", "snprel_multi_accumulate", "snprel_multi_last_reduce",
@@ -704,10 +721,16 @@ class Context:
         return a.value, b.value, g.value
 
     def set_rounding(self, mode):
-        """'nearest' (default, worst-case error bound) or 'random' (experimental: unbiased randomised
-        rounding of the U table + Hoeffding bound, one tensor pass fewer at config-2 size)."""
-        code = {"nearest": 0, "random": 1}.get(mode, mode)
+        """Rounding of the main row table of the covariance estimators: 'nearest' (worst-case error
+        bound), 'random' (unbiased randomised rounding + Hoeffding bound, failure probability 1e-12)
+        or 'auto' (default: whichever needs fewer tensor passes for the tolerance)."""
+        code = ROUNDING_MODES.get(mode, mode)
         self._ck(self.lib.snprel_set_rounding(self.h, int(code)))
+
+    def set_snp_origin(self, origin):
+        """Global index of this context's first SNP row (SNP shards: the shard offset); keys the
+        rounding draws so that a sharded run reproduces the one-context result bit for bit."""
+        self._ck(self.lib.snprel_set_snp_origin(self.h, int(origin)))
 
     def set_count_engine(self, engine):
         """'bits' (default: packed-bit XOR/AND/popcount kernels) or 'tensor' (same exact counters
@@ -785,6 +808,9 @@ class MultiContext:
     def set_count_engine(self, engine):
         code = {"bits": 0, "tensor": 1}.get(engine, engine)
         self._ck(self.lib.snprel_multi_set_count_engine(self.h, int(code)))
+
+    def set_rounding(self, mode):
+        self._ck(self.lib.snprel_multi_set_rounding(self.h, int(ROUNDING_MODES.get(mode, mode))))
 
     def accumulate(self, est, bayesian=False, root=0):
         """est: a GRM method name, or EST_IBS / EST_KING_ROBUST / EST_BETA.  root = -1: all-reduce."""

@@ -122,6 +122,7 @@ const char *snprel_last_error(snprel_ctx *c) { return c ? c->err.c_str() : g_cre
 
 int snprel_geno_begin(snprel_ctx *c, int64_t n_samp, int64_t cap) {
     API_BEGIN(c) geno_begin(c, n_samp, cap);
+    c->snp_origin = 0;
     API_END(c)
 }
 int snprel_geno_push_u8(snprel_ctx *c, const uint8_t *geno, int64_t cnt) {
@@ -500,11 +501,33 @@ int snprel_table_gram(snprel_ctx *c, const int8_t *tabA, const int8_t *tabB, int
 }
 int snprel_set_rounding(snprel_ctx *c, int mode) {
     API_BEGIN(c)
-    if (mode != 0 && mode != 1) fail("snprel_set_rounding: 0 (round to nearest, worst-case bound) or 1 (randomised, Hoeffding bound)");
+    if (mode < 0 || mode > 2)
+        fail("snprel_set_rounding: 0 (round to nearest, worst-case bound), 1 (randomised, Hoeffding bound) or 2 (the one with fewer tensor passes)");
     c->round_mode = mode;
     c->accum_est = -1;
     c->accum_reduced = false;
     API_END(c)
+}
+int snprel_set_snp_origin(snprel_ctx *c, int64_t origin) {
+    API_BEGIN_STREAMING(c)      // (does not wait for copies in flight)
+    if (origin < 0) fail("snprel_set_snp_origin: negative origin");
+    if (origin != c->snp_origin) {
+        c->snp_origin = origin;
+        c->accum_est = -1;        // (tables drawn with another origin are rebuilt: the prep cache compares it)
+        c->accum_reduced = false;
+    }
+    API_END(c)
+}
+int snprel_plan_format(int est, snprel_plan *plan, int mode, int64_t n_samp) {
+    try {
+        grm_plan_format(est, plan, mode, n_samp);
+        return plan->digits + plan->digits_w + plan->digits_d;
+    } catch (const Error &e) {
+        g_create_error = e.msg;
+    } catch (const std::exception &e) {
+        g_create_error = e.what();
+    }
+    return -1;
 }
 int snprel_last_eigen_info(snprel_ctx *c, int *solver, int *rounds, int *block_gemms, double *phase_ms) {
     API_BEGIN(c)

@@ -187,6 +187,7 @@ struct snprel_ctx {
     std::vector<std::unique_ptr<ConstTab>> const_tabs;   // constant per-SNP tables (gram_const_table)
     snprel::DevBuf<int> scr_cnt;          // per-sample heterozygote / missing counts [2][npad]
     snprel::DevBuf<long long> scr_ew;     // per-sample error weight sum_l |B_l[g_il]| [npad]
+    snprel::DevBuf<long long> scr_sq;     // per-sample sum_l ceil(B_l[g_il]^2 / 127) [npad] (randomised-rounding bound)
     snprel::DevBuf<long long> scr_dg;     // per-sample diagonal bound, in units of c (diagtab_kernel) [npad]
     snprel::DevBuf<uint32_t> scr_tabf;    // [snp_cap]: ceil(w (g - mu)^2 / c) as bytes by genotype code
     snprel::DevBuf<int> scr_chunk;        // per GRAM_CHUNK SNPs: max over samples of the chunk's error weight
@@ -203,7 +204,8 @@ struct snprel_ctx {
     snprel::DevBuf<uint32_t> scr_ctab;    // constant tables of the tensor count engine
     snprel::DevBuf<long long> scr_cacc;   // int64 planes of the tensor count engine (acc belongs to the covariance path)
     int count_engine = 0;                 // 0: packed-bit pair kernels (default), 1: tensor pipe
-    int round_mode = 0;                   // 0: round to nearest + worst-case bound (default), 1: randomised + Hoeffding
+    int round_mode = 2;                   // 0: round to nearest + worst-case bound, 1: randomised + Hoeffding, 2 (default): the one with fewer passes
+    int64_t snp_origin = 0;               // global index of the first SNP row: keys the rounding draws (snprel_set_snp_origin)
     std::vector<int> host_cnt;
 
     // window-invariant products of the covariance path, kept across row windows (tiled N x N
@@ -217,7 +219,8 @@ struct snprel_ctx {
     } plan_cache;
     struct PrepCache {
         uint64_t version = 0;
-        int est = -1, bayesian = 0, f = 0, fw = 0, fd = 0, fv = 0, nU = 0, nW = 0, nD = 0, nD2 = 0, round_mode = 0;
+        int est = -1, bayesian = 0, f = 0, fw = 0, fd = 0, fv = 0, nU = 0, nW = 0, nD = 0, nD2 = 0, rounding = 0;
+        int64_t origin = 0;     // SNP origin the (randomised) tables were drawn with
         bool reduced = false;   // the per-sample vectors / scalars already hold the all-reduced sums
     } prep_cache;
 
@@ -373,6 +376,7 @@ void gram_tc_check(snprel_ctx *c);
 // grm.cu
 void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan);
 void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan);
+void grm_plan_format(int est, snprel_plan *plan, int round_mode, int64_t n_samp);   // host only
 void grm_finish(snprel_ctx *c, int method, double *out, int packed);
 void grm_finish_device(snprel_ctx *c, int est);
 void pca_finish(snprel_ctx *c, int eigen_cnt, int bayesian, double *genmat, double *trace_xtx,

@@ -397,6 +397,9 @@ void geno_synth(snprel_ctx *c, int64_t n_snp, uint64_t seed, double maf_lo, doub
                                                   maf_hi, thm, snp_start + r0);
         KERNEL_CHECK(c);
     }
+    // a shard of a larger data set (row 0 of this workspace is SNP snp_start - position > 0 of it): the same
+    // offset keys the rounding draws of the covariance path (snprel_set_snp_origin)
+    if (snp_start - c->n_snp > 0) c->snp_origin = snp_start - c->n_snp;
     c->n_snp += n_snp;
     invalidate(c);
 }

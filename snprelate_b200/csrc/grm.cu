@@ -42,6 +42,8 @@ constexpr int LIMB = 20;           // the per-sample vector is accumulated in 20
 // scalars[]: 0 = sum of d_l (EIGMIX SumDenominator / KING-homo sum p(1-p)), 1 = sum d2_l
 // iscalars[]: 0 = nLocus (GCTA), 2 = low limb and 3 = upper limbs of sum_l qb_l (constant of the vector)
 
+constexpr int SQ_UNIT = 127;       // unit of the per-sample sum of squared column-table entries (127^2 / 127 fits a byte lane)
+
 struct SnpTables {
     long long qU[4];   // fixed-point T = U / s (row table of the main passes)
     long long qW[4];   // fixed-point R = delta U (row table of the missing-data passes)
@@ -54,7 +56,8 @@ struct SnpTables {
     int maxB;          // max |B_l[g]|
 };
 
-// uniform [0, 1) draw of table entry (SNP l, genotype g): randomised rounding (snprel_set_rounding)
+constexpr uint64_t DITHER_SEED = 0xD17E5ull | 1ull;
+// uniform [0, 1) draw of table entry (global SNP index l, genotype g): randomised rounding (snprel_set_rounding)
 __device__ __forceinline__ double dither_u01(uint64_t seed, long long l, int g) {
     uint64_t x = seed ^ ((uint64_t)l * 4u + (uint64_t)g) * 0xD1342543DE82EF95ull;
     x += 0x9E3779B97F4A7C15ull;
@@ -105,11 +108,14 @@ __device__ __forceinline__ SnpCoef snp_coef(const SnpStat st, int est, int bayes
 }
 
 // ---- per-SNP integer column tables ---------------------------------------------
-// coltab[l] = (s_l, t_l); tabB[l] = bytes (B[0], B[1], B[2], 0); tabBabs[l] = their magnitudes.
+// coltab[l] = (s_l, t_l); tabB[l] = bytes (B[0], B[1], B[2], 0); tabBabs[l] = their magnitudes;
+// tabBsq[l] = bytes ceil(B[g]^2 / SQ_UNIT) (<= 127): summed per sample they bound sum_l B_l[g]^2, the
+// variance proxy of the randomised-rounding error bound (u_table_error).
 // A pure function of the SNP's own counts, so every rank of a sharded run picks the same table
 // for the same SNP without communication.
 __global__ void coltab_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int est, int bayesian,
-                              int2 *__restrict__ coltab, uint32_t *__restrict__ tabB, uint32_t *__restrict__ tabBabs) {
+                              int2 *__restrict__ coltab, uint32_t *__restrict__ tabB, uint32_t *__restrict__ tabBabs,
+                              uint32_t *__restrict__ tabBsq) {
     const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_snp) return;
     const SnpCoef k = snp_coef(st[l], est, bayesian);
@@ -139,6 +145,8 @@ __global__ void coltab_kernel(const SnpStat *__restrict__ st, int64_t n_snp, int
     const int b0 = -t, b1 = s - t, b2 = 2 * s - t;
     tabB[l] = (uint32_t)(b0 & 255) | ((uint32_t)(b1 & 255) << 8) | ((uint32_t)(b2 & 255) << 16);
     tabBabs[l] = (uint32_t)abs(b0) | ((uint32_t)abs(b1) << 8) | ((uint32_t)abs(b2) << 16);
+    tabBsq[l] = (uint32_t)((b0 * b0 + SQ_UNIT - 1) / SQ_UNIT) | ((uint32_t)((b1 * b1 + SQ_UNIT - 1) / SQ_UNIT) << 8) |
+                ((uint32_t)((b2 * b2 + SQ_UNIT - 1) / SQ_UNIT) << 16);
 }
 
 // dither != 0: the T table is rounded at random, floor(v 2^f + u) with u ~ U[0, 1) drawn per
@@ -275,6 +283,7 @@ __global__ void diagtab_kernel(const SnpStat *__restrict__ st, int64_t n_snp, in
 
 // ---- per-sample statistics in one pass over the 2-bit matrix -----------------
 //   ew[i]      = sum_l |B_l[g_il]|     (error weight of the main passes; int64)
+//   sq[i]      = sum_l ceil(B_l[g_il]^2 / SQ_UNIT)   (optional, tabS != nullptr)
 //   cnt[0][i]  = #heterozygous, cnt[1][i] = #missing
 //   chunk_ew[y] = max over samples of the sum over SNP chunk y (int32 accumulator headroom of K1)
 // One thread per 32-bit word column (16 samples), one block row per GRAM_CHUNK SNPs.  |B| comes from a
@@ -282,18 +291,20 @@ __global__ void diagtab_kernel(const SnpStat *__restrict__ st, int64_t n_snp, in
 // in 16-bit lanes (512 x 127 < 2^16); the two indicator counts use bit-sliced vertical counters
 // (3 rows in 2-bit fields -> 15 in 4-bit fields -> 255 in bytes -> 16-bit lanes).
 constexpr int SS_THREADS = 128;
+template <bool with_f, bool with_s>
 __global__ void __launch_bounds__(SS_THREADS)
 sample_stats_kernel(const uint32_t *__restrict__ geno, const uint32_t *__restrict__ tabBabs, int64_t n_snp,
                     int64_t row_words, int64_t npad, long long *__restrict__ ew, int *__restrict__ cnt,
-                    int *__restrict__ chunk_ew, const uint32_t *__restrict__ tabF, long long *__restrict__ dg) {
-    __shared__ uint32_t tab[GRAM_CHUNK + 4], tabf[GRAM_CHUNK + 4];
+                    int *__restrict__ chunk_ew, const uint32_t *__restrict__ tabF, long long *__restrict__ dg,
+                    const uint32_t *__restrict__ tabS, long long *__restrict__ sq) {
+    __shared__ uint32_t tab[GRAM_CHUNK + 4], tabf[GRAM_CHUNK + 4], tabs[GRAM_CHUNK + 4];
     __shared__ int smax[SS_THREADS / 32];
     const int64_t l0 = (int64_t)blockIdx.y * GRAM_CHUNK;
     const int nl = (int)min((int64_t)GRAM_CHUNK, n_snp - l0);
-    const bool with_f = tabF != nullptr;
     for (int s = threadIdx.x; s < GRAM_CHUNK + 4; s += blockDim.x) {
         tab[s] = s < nl ? tabBabs[l0 + s] : 0u;
         tabf[s] = (with_f && s < nl) ? tabF[l0 + s] : 0u;
+        tabs[s] = (with_s && s < nl) ? tabS[l0 + s] : 0u;
     }
     __syncthreads();
     const int64_t wc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -301,6 +312,7 @@ sample_stats_kernel(const uint32_t *__restrict__ geno, const uint32_t *__restric
     const uint32_t *p = geno + l0 * row_words + (live ? wc : 0);
     uint32_t e16[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // |B| sums: selector q -> e16[2q] (bytes 0,2), e16[2q+1] (bytes 1,3)
     uint32_t f16[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // diagonal-bound sums, same lanes (entries <= 127: 512 rows fit 16 bits)
+    uint32_t s16[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // squared column-table sums in SQ_UNIT, same lanes
     uint32_t m16[8] = {0, 0, 0, 0, 0, 0, 0, 0}, h16[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t m8[4] = {0, 0, 0, 0}, h8[4] = {0, 0, 0, 0};
     int in8 = 0;
@@ -318,7 +330,7 @@ sample_stats_kernel(const uint32_t *__restrict__ geno, const uint32_t *__restric
 #pragma unroll
             for (int r = 0; r < 3; r++) {
                 const int row = min(r0 + 3 * g5 + r, GRAM_CHUNK + 3);
-                const uint32_t x = w[r], t = tab[row], tf = tabf[row];
+                const uint32_t x = w[r], t = tab[row], tf = tabf[row], ts = tabs[row];
                 const uint32_t hi = x >> 1;
                 m2 += x & hi & 0x55555555u;
                 h2 += x & ~hi & 0x55555555u;
@@ -333,6 +345,11 @@ sample_stats_kernel(const uint32_t *__restrict__ geno, const uint32_t *__restric
                         const uint32_t vf = __byte_perm(tf, 0, sel[q]);
                         f16[2 * q] += __byte_perm(vf, 0, 0x4240);
                         f16[2 * q + 1] += __byte_perm(vf, 0, 0x4341);
+                    }
+                    if (with_s) {
+                        const uint32_t vs = __byte_perm(ts, 0, sel[q]);
+                        s16[2 * q] += __byte_perm(vs, 0, 0x4240);
+                        s16[2 * q + 1] += __byte_perm(vs, 0, 0x4341);
                     }
                 }
             }
@@ -384,6 +401,10 @@ sample_stats_kernel(const uint32_t *__restrict__ geno, const uint32_t *__restric
                         const int fv = (int)((f16[2 * q + hb] >> (16 * half)) & 0xFFFFu);
                         if (fv) atomicAdd(reinterpret_cast<unsigned long long *>(dg) + s0 + es, (unsigned long long)fv);
                     }
+                    if (with_s) {
+                        const int sv = (int)((s16[2 * q + hb] >> (16 * half)) & 0xFFFFu);
+                        if (sv) atomicAdd(reinterpret_cast<unsigned long long *>(sq) + s0 + es, (unsigned long long)sv);
+                    }
                     const int ms = (q == 0 ? 0 : q == 1 ? 2 : q == 2 ? 1 : 3) + 4 * byte;
                     const int mv = (int)((m16[2 * q + hb] >> (16 * half)) & 0xFFFFu);
                     const int hv = (int)((h16[2 * q + hb] >> (16 * half)) & 0xFFFFu);
@@ -408,13 +429,14 @@ sample_stats_kernel(const uint32_t *__restrict__ geno, const uint32_t *__restric
 __global__ void tables_kernel(const SnpStat *__restrict__ st, const int2 *__restrict__ coltab, int64_t n_snp, int64_t cap, int est,
                               int bayesian, int frac_bits, int frac_bits_w, int frac_bits_d, int frac_bits_v, int nU, int nW, int nD, int nD2,
                               uint32_t *__restrict__ tab, double *__restrict__ scalars /*[gridDim.x][2] partials*/,
-                              long long *__restrict__ iscalars, int *__restrict__ overflow, uint64_t dither) {
+                              long long *__restrict__ iscalars, int *__restrict__ overflow, uint64_t dither,
+                              long long snp_base /* global index of st[0] */) {
     int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double d = 0, d2 = 0;
     long long poly = 0, qb = 0;
     if (l < n_snp) {
         SnpTables t;
-        snp_tables(st[l], est, bayesian, coltab[l], frac_bits, frac_bits_w, frac_bits_d, frac_bits_v, t, (long long)l, dither);
+        snp_tables(st[l], est, bayesian, coltab[l], frac_bits, frac_bits_w, frac_bits_d, frac_bits_v, t, snp_base + (long long)l, dither);
         d = t.d;
         d2 = t.d2;
         qb = t.qb;
@@ -600,11 +622,12 @@ static void ensure_coltab(snprel_ctx *c, int est, int bayesian) {
     ensure_stats(c);
     if (c->coltab_version == c->geno_version && c->coltab_est == est && c->coltab_bayesian == bayesian) return;
     c->scr_coltab.alloc((size_t)c->snp_cap);
-    c->scr_tabb.alloc((size_t)2 * c->snp_cap);
+    c->scr_tabb.alloc((size_t)3 * c->snp_cap);
     c->scr_tabb.zero(c->stream);               // padding rows: all-zero tables
     if (c->n_snp > 0) {
         coltab_kernel<<<(unsigned)((c->n_snp + 255) / 256), 256, 0, c->stream>>>(
-            c->stat.p, c->n_snp, est, bayesian, c->scr_coltab.p, c->scr_tabb.p, c->scr_tabb.p + c->snp_cap);
+            c->stat.p, c->n_snp, est, bayesian, c->scr_coltab.p, c->scr_tabb.p, c->scr_tabb.p + c->snp_cap,
+            c->scr_tabb.p + 2 * c->snp_cap);
         KERNEL_CHECK(c);
     }
     c->coltab_version = c->geno_version;
@@ -630,15 +653,24 @@ static void sample_stats(snprel_ctx *c, int est = -1, int bayesian = 0) {   // e
     c->scr_cnt.zero(c->stream);
     c->scr_ew.alloc((size_t)npad);
     c->scr_ew.zero(c->stream);
+    c->scr_sq.alloc((size_t)npad);
+    c->scr_sq.zero(c->stream);
     c->scr_chunk.alloc((size_t)nchunk);
     c->scr_chunk.zero(c->stream);
     if (c->n_snp > 0) {
         const int64_t row_words = c->row_bytes / 4;
         dim3 grid((unsigned)((row_words + SS_THREADS - 1) / SS_THREADS), (unsigned)((c->n_snp + GRAM_CHUNK - 1) / GRAM_CHUNK));
-        sample_stats_kernel<<<grid, SS_THREADS, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(c->geno2b.p),
-                                                               c->scr_tabb.p + c->snp_cap, c->n_snp, row_words, npad,
-                                                               c->scr_ew.p, c->scr_cnt.p, c->scr_chunk.p,
-                                                               with_diag ? c->scr_tabf.p : nullptr, c->scr_dg.p);
+        const uint32_t *g32 = reinterpret_cast<const uint32_t *>(c->geno2b.p);
+        const uint32_t *tabA = c->scr_tabb.p + c->snp_cap, *tabS = c->scr_tabb.p + 2 * c->snp_cap;
+        if (with_diag)      // the plan: error weight, counts, diagonal bound and the sum of squares
+            sample_stats_kernel<true, true><<<grid, SS_THREADS, 0, c->stream>>>(g32, tabA, c->n_snp, row_words, npad, c->scr_ew.p, c->scr_cnt.p,
+                                                                               c->scr_chunk.p, c->scr_tabf.p, c->scr_dg.p, tabS, c->scr_sq.p);
+        else if (est >= 0)
+            sample_stats_kernel<false, true><<<grid, SS_THREADS, 0, c->stream>>>(g32, tabA, c->n_snp, row_words, npad, c->scr_ew.p, c->scr_cnt.p,
+                                                                                c->scr_chunk.p, nullptr, nullptr, tabS, c->scr_sq.p);
+        else                // counts only
+            sample_stats_kernel<false, false><<<grid, SS_THREADS, 0, c->stream>>>(g32, tabA, c->n_snp, row_words, npad, c->scr_ew.p, c->scr_cnt.p,
+                                                                                 c->scr_chunk.p, nullptr, nullptr, nullptr, nullptr);
         KERNEL_CHECK(c);
     }
 }
@@ -659,6 +691,7 @@ void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
             plan->n_snp = s.n_snp;
             plan->diag_bound = s.diag_bound;
             plan->sum_rest = s.sum_rest;
+            plan->err_weight2 = s.err_weight2;
             return;
         }
     }
@@ -686,15 +719,19 @@ void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
                                cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaMemcpyAsync(c->host_ew.data(), c->scr_ew.p, (size_t)npad * sizeof(long long),
                                cudaMemcpyDeviceToHost, c->stream));
+    std::vector<long long> hsq((size_t)npad);
+    CUDA_CHECK(cudaMemcpyAsync(hsq.data(), c->scr_sq.p, (size_t)npad * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     if (nchunk)
         CUDA_CHECK(cudaMemcpyAsync(hchunk.data(), c->scr_chunk.p, nchunk * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    long long ew = 0, mm = 0, dg = 0;
+    long long ew = 0, mm = 0, dg = 0, sq = 0;
     for (int64_t i = 0; i < c->n_samp; i++) {
         ew = std::max(ew, c->host_ew[i]);
         mm = std::max<long long>(mm, c->host_cnt[i]);
         dg = std::max(dg, hdg[i]);
+        sq = std::max(sq, hsq[i]);
     }
+    plan->err_weight2 = (est == SNPREL_EST_KING_HOMO) ? 0.0 : (double)sq * (double)SQ_UNIT;   // >= max_i sum_l B_l[g_il]^2
     // X = max_i sum_l ceil(w (g - mu)^2 / c) c  >=  max_i C_ii   (0: not measured)
     plan->diag_bound = (est == SNPREL_EST_KING_HOMO) ? 0.0 : (double)dg * (h[5] / 127.0);
     plan->sum_rest = h[6];
@@ -725,17 +762,22 @@ void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
 static double launch_cost(int n) { return (double)n; }
 
 // round_mode 1 (snprel_set_rounding): the T table is rounded at random, so for a fixed pair (i, j)
-// the error sum_l e_l[g_il] B_l[g_jl] is a sum of independent zero-mean terms of width |B| 2^-f, and by
-// Hoeffding it exceeds 2^-f sqrt(1/2 sum_l B^2 ln(2/delta)) with probability < delta; delta is
-// 1e-12 divided by the number of pairs (union bound) and sum B^2 <= 127 sum |B| = 127 err_weight.
+// the error sum_l e_l[g_il] B_l[g_jl] is a sum of independent zero-mean terms, the l-th confined to an
+// interval of width |B_l[g_jl]| 2^-f, and by Hoeffding it exceeds 2^-f sqrt(1/2 sum_l B^2 ln(2/delta)) with
+// probability < delta; delta is 1e-12 divided by the number of pairs (union bound over the whole matrix).
+// sum_l B^2 is bounded per column sample: measured (err_weight2, sample_stats_kernel), else <= 127 sum |B|.
 static double u_table_error(const snprel_plan &plan, int fa, int round_mode, double n_samp) {
     if (round_mode != 1) return std::ldexp(plan.err_weight, -(fa + 1));
     const double pairs = std::max(1.0, 0.5 * n_samp * (n_samp + 1.0));
-    return std::ldexp(std::sqrt(0.5 * 127.0 * plan.err_weight * std::log(2.0 * pairs / 1e-12)), -fa);
+    double s2 = 127.0 * plan.err_weight;
+    if (plan.err_weight2 > 0) s2 = std::min(s2, plan.err_weight2);
+    return std::ldexp(std::sqrt(0.5 * s2 * std::log(2.0 * pairs / 1e-12)), -fa);
 }
 
-static void choose_format(int est, snprel_plan &plan, int &nU, int &nW, int &nD, int round_mode = 0,
-                          double n_samp = 0) {
+// one rounding rule (0 nearest / 1 randomised); true: the error bound meets the tolerance
+static bool choose_format_one(int est, snprel_plan &plan, int &nU, int &nW, int &nD, int round_mode,
+                              double n_samp) {
+    bool feasible = true;
     const double tol = (plan.tol > 0 ? plan.tol : 1e-10) * 0.9;   // 10 % left for the per-sample vector and float64 rounding in the epilogue
     const bool homo = est == SNPREL_EST_KING_HOMO;
     const bool any_missing = plan.total_missing > 0;
@@ -765,7 +807,7 @@ static void choose_format(int est, snprel_plan &plan, int &nU, int &nW, int &nD,
         } else {
             double best_cost = 1e30, best_err = 1e300;
             int bU = MAX_DIGITS, bW = any_missing ? MAX_DIGITS : 0;
-            bool feasible = false;
+            feasible = false;
             for (int a = 1; a <= MAX_DIGITS; a++) {
                 int fa = std::min(frac_cap(plan.max_abs, a), fmax);
                 if (fa < 8) continue;
@@ -821,6 +863,42 @@ static void choose_format(int est, snprel_plan &plan, int &nU, int &nW, int &nD,
         }
     }
     plan.digits_d = nD;
+    plan.rounding = (round_mode == 1 && !homo) ? 1 : 0;
+    return feasible;
+}
+
+// round_mode as in snprel_set_rounding.  A caller-fixed format (frac_bits >= 0) brings its rounding
+// along in plan.rounding; otherwise mode 2 takes randomised rounding only where its (probabilistic)
+// bound is met with FEWER tensor passes than the worst-case bound needs.
+static void choose_format(int est, snprel_plan &plan, int &nU, int &nW, int &nD, int round_mode, double n_samp) {
+    if (plan.frac_bits >= 0) {
+        choose_format_one(est, plan, nU, nW, nD, plan.rounding ? 1 : 0, n_samp);
+        return;
+    }
+    if (round_mode != 2 || est == SNPREL_EST_KING_HOMO) {
+        choose_format_one(est, plan, nU, nW, nD, round_mode == 1 ? 1 : 0, n_samp);
+        return;
+    }
+    snprel_plan pr = plan;
+    int rU = 0, rW = 0, rD = 0;
+    const bool ok_near = choose_format_one(est, plan, nU, nW, nD, 0, n_samp);
+    const bool ok_rand = choose_format_one(est, pr, rU, rW, rD, 1, n_samp);
+    if (ok_rand && (!ok_near || rU + rW + rD < nU + nW + nD)) {
+        plan = pr;
+        nU = rU;
+        nW = rW;
+        nD = rD;
+    }
+}
+
+void grm_plan_format(int est, snprel_plan *plan, int round_mode, int64_t n_samp) {
+    if (!plan) fail("snprel_plan_format: NULL plan");
+    if (est == SNPREL_GRM_CORR) est = SNPREL_GRM_GCTA;
+    if (!((est >= SNPREL_GRM_EIGENSTRAT && est <= SNPREL_GRM_EIGMIX) || est == SNPREL_EST_KING_HOMO))
+        fail("snprel_plan_format: not a covariance estimator (%d)", est);
+    if (round_mode < 0 || round_mode > 2) fail("snprel_plan_format: rounding mode 0, 1 or 2");
+    int nU = 0, nW = 0, nD = 0;
+    choose_format(est, *plan, nU, nW, nD, round_mode, (double)n_samp);
 }
 
 void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
@@ -839,7 +917,7 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
     // fixed-point format only, not on the row window: a tiled N x N run builds them once.
     snprel_ctx::PrepCache &pc = c->prep_cache;
     const bool prep_hit = pc.version == c->geno_version && pc.est == est && pc.bayesian == plan.bayesian &&
-                          pc.round_mode == c->round_mode && pc.fv == fv &&
+                          pc.rounding == plan.rounding && (!plan.rounding || pc.origin == c->snp_origin) && pc.fv == fv &&
                           pc.f == f && pc.fw == fw && pc.fd == fd && pc.nU == nU && pc.nW == nW && pc.nD == nD &&
                           pc.nD2 == nD2 && c->scr_tab.p && c->samp_sum.p && c->scr_cnt.p;
     DevBuf<uint32_t> &tab = c->scr_tab;
@@ -861,11 +939,11 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
         const unsigned tblocks = (unsigned)((c->n_snp + 255) / 256);
         c->scr_part.alloc((size_t)std::max(tblocks, 1u) * 2);
         if (c->n_snp > 0) {
-            // (the draw is keyed by the LOCAL SNP index: shards of a multi-GPU run use different SNPs, so
-            //  different local indices on different ranks still give independent draws per SNP)
-            const uint64_t dither = (c->round_mode == 1 && !homo) ? (0xD17E5ull + (uint64_t)c->device * 0x9E3779B97F4A7C15ull) | 1ull : 0ull;
+            // (the draws are keyed by the GLOBAL SNP index, origin + local row: one draw per SNP of the data
+            //  set however it is sharded, independent across SNPs)
             tables_kernel<<<tblocks, 256, 0, c->stream>>>(c->stat.p, c->scr_coltab.p, c->n_snp, cap, est, plan.bayesian, f, fw, fd, fv, nU,
-                                                          nW, nD, nD2, tab.p, c->scr_part.p, c->iscalars.p, ovf.p, dither);
+                                                          nW, nD, nD2, tab.p, c->scr_part.p, c->iscalars.p, ovf.p,
+                                                          (plan.rounding && !homo) ? DITHER_SEED : 0ull, (long long)c->snp_origin);
             KERNEL_CHECK(c);
         }
         int hovf = 0;
@@ -915,7 +993,8 @@ void grm_accumulate(snprel_ctx *c, int est, const snprel_plan *plan_in) {
         pc.nW = nW;
         pc.nD = nD;
         pc.nD2 = nD2;
-        pc.round_mode = c->round_mode;
+        pc.rounding = plan.rounding;
+        pc.origin = c->snp_origin;
         pc.reduced = false;
     }
 
@@ -983,16 +1062,18 @@ static void prep_stats_range(snprel_ctx *c, int est, int bayesian, int64_t l0, i
     const int64_t n = l1 - l0;
     if (n <= 0) return;
     coltab_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->stat.p + l0, n, est, bayesian, c->scr_coltab.p + l0,
-                                                                   c->scr_tabb.p + l0, c->scr_tabb.p + c->snp_cap + l0);
+                                                                   c->scr_tabb.p + l0, c->scr_tabb.p + c->snp_cap + l0,
+                                                                   c->scr_tabb.p + 2 * c->snp_cap + l0);
     KERNEL_CHECK(c);
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, 1024);
     plan_kernel<<<blocks, 256, 0, c->stream>>>(c->stat.p + l0, c->scr_coltab.p + l0, n, c->n_samp, est, bayesian, c->scr_plan.p);
     KERNEL_CHECK(c);
     const int64_t row_words = c->row_bytes / 4;
     dim3 grid((unsigned)((row_words + SS_THREADS - 1) / SS_THREADS), (unsigned)((n + GRAM_CHUNK - 1) / GRAM_CHUNK));
-    sample_stats_kernel<<<grid, SS_THREADS, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(c->geno2b.p) + l0 * row_words,
+    sample_stats_kernel<false, true><<<grid, SS_THREADS, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(c->geno2b.p) + l0 * row_words,
                                                            c->scr_tabb.p + c->snp_cap + l0, n, row_words, c->n_samp_pad,
-                                                           c->scr_ew.p, c->scr_cnt.p, c->scr_chunk.p + l0 / GRAM_CHUNK, nullptr, nullptr);
+                                                           c->scr_ew.p, c->scr_cnt.p, c->scr_chunk.p + l0 / GRAM_CHUNK, nullptr, nullptr,
+                                                           c->scr_tabb.p + 2 * c->snp_cap + l0, c->scr_sq.p);
     KERNEL_CHECK(c);
 }
 
@@ -1005,12 +1086,16 @@ static void read_plan_stats(snprel_ctx *c, int est, snprel_plan &plan, int64_t n
     CUDA_CHECK(cudaMemcpyAsync(h, c->scr_plan.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaMemcpyAsync(c->host_cnt.data(), c->scr_cnt.p + npad, (size_t)npad * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaMemcpyAsync(c->host_ew.data(), c->scr_ew.p, (size_t)npad * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<long long> hsq((size_t)npad);
+    CUDA_CHECK(cudaMemcpyAsync(hsq.data(), c->scr_sq.p, (size_t)npad * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    long long ew = 0, mm = 0;
+    long long ew = 0, mm = 0, sq = 0;
     for (int64_t i = 0; i < c->n_samp; i++) {
         ew = std::max(ew, c->host_ew[i]);
         mm = std::max<long long>(mm, c->host_cnt[i]);
+        sq = std::max(sq, hsq[i]);
     }
+    plan.err_weight2 = (double)sq * (double)SQ_UNIT;
     plan.max_abs = h[0];
     plan.max_abs_w = h[4];
     plan.sum_bound = h[1];
@@ -1028,7 +1113,7 @@ static void read_plan_stats(snprel_ctx *c, int est, snprel_plan &plan, int64_t n
 // true: accumulated (c->acc etc. hold the result, caches set); false: the caller must take the ordinary path
 static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
     if (est == SNPREL_GRM_CORR) est = SNPREL_GRM_GCTA;
-    if (c->pending.empty() || !full_window(c) || c->round_mode != 0 || (c->debug_flags & 2u) || c->n_snp <= 0) return false;
+    if (c->pending.empty() || !full_window(c) || (c->debug_flags & 2u) || c->n_snp <= 0) return false;
     std::vector<snprel_ctx::PendingCopy> chunks = c->pending;
     for (size_t k = 0; k < chunks.size(); k++) {   // contiguous, chunk aligned, up to the last row
         const int64_t expect = k ? chunks[k - 1].l1 : chunks[0].l0;
@@ -1042,8 +1127,10 @@ static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
 
     // accumulators of the statistics
     c->scr_coltab.alloc((size_t)cap);
-    c->scr_tabb.alloc((size_t)2 * cap);
+    c->scr_tabb.alloc((size_t)3 * cap);
     c->scr_tabb.zero(c->stream);
+    c->scr_sq.alloc((size_t)npad);
+    c->scr_sq.zero(c->stream);
     c->scr_plan.alloc(8);
     c->scr_plan.zero(c->stream);
     c->scr_cnt.alloc((size_t)2 * npad);
@@ -1074,6 +1161,7 @@ static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
         plan.max_abs_w *= 1.25;
         plan.sum_bound *= fac * 1.03;
         plan.err_weight *= fac * 1.08;
+        plan.err_weight2 *= fac * 1.08;
         plan.max_missing = (int64_t)std::ceil((double)plan.max_missing * fac * 1.15 + 16.0);
         plan.total_missing = (int64_t)((double)plan.total_missing * fac) + (m > a1 ? 1 : 0);
         plan.scale *= fac * 0.95;                  // a LOWER bound of the normaliser
@@ -1081,7 +1169,7 @@ static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
         plan.n_snp = m;
     }
     int nU = 0, nW = 0, nD = 0;
-    choose_format(est, plan, nU, nW, nD, 0, (double)c->n_samp);
+    choose_format(est, plan, nU, nW, nD, c->round_mode, (double)c->n_samp);
     if (plan.total_missing > 0 && nW == 0) return false;
     const int f = plan.frac_bits, fw = plan.frac_bits_w, fd = plan.frac_bits_d, fv = plan.frac_bits_v;
     const int npass = nU + nW + nD;
@@ -1126,7 +1214,8 @@ static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
         const int64_t n = l1 - l0;
         const unsigned tb = (unsigned)((n + 255) / 256);
         tables_kernel<<<tb, 256, 0, c->stream>>>(c->stat.p + l0, c->scr_coltab.p + l0, n, cap, est, bayesian, f, fw, fd, fv, nU, nW, nD, 0,
-                                                 tab.p + l0, c->scr_part.p + 2 * tblock0, c->iscalars.p, c->scr_flags.p, 0ull);
+                                                 tab.p + l0, c->scr_part.p + 2 * tblock0, c->iscalars.p, c->scr_flags.p,
+                                                 plan.rounding ? DITHER_SEED : 0ull, (long long)(c->snp_origin + l0));
         KERNEL_CHECK(c);
         tblock0 += tb;
         dim3 grid((unsigned)((row_words + 31) / 32), (unsigned)((n + SV_ROWS - 1) / SV_ROWS));
@@ -1196,7 +1285,7 @@ static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
         scale = std::max(scale, 0.05 * truth.scale);
         const double budget = tol * std::max(scale, 1e-300);
         const int head = 61 - (int)std::ceil(std::log2(std::max(truth.sum_bound, 1.0)));
-        double err = std::ldexp(truth.err_weight, -(f + 1));
+        double err = u_table_error(truth, f, plan.rounding, (double)c->n_samp);
         if (truth.total_missing > 0) err += nW > 0 ? std::ldexp((double)truth.max_missing, -(fw + 1)) : 1e300;
         ok = ok && err <= budget && f <= head;
         if (truth.total_missing > 0 && est == SNPREL_GRM_GCTA) ok = ok && nD == 1;
@@ -1226,6 +1315,7 @@ static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
     plan.max_abs_w = truth.max_abs_w;
     plan.sum_bound = truth.sum_bound;
     plan.err_weight = truth.err_weight;
+    plan.err_weight2 = truth.err_weight2;
     plan.scale = truth.scale;
     plan.total_missing = truth.total_missing;
     plan.max_missing = truth.max_missing;
@@ -1249,7 +1339,8 @@ static bool grm_accumulate_streamed(snprel_ctx *c, int est, int bayesian) {
     pc.bayesian = bayesian;
     pc.f = f; pc.fw = fw; pc.fd = fd; pc.fv = fv;
     pc.nU = nU; pc.nW = nW; pc.nD = nD; pc.nD2 = 0;
-    pc.round_mode = 0;
+    pc.rounding = plan.rounding;
+    pc.origin = c->snp_origin;
     pc.reduced = false;
     float ms = 0, total = 0;
     CUDA_CHECK(cudaEventRecord(c->evs1, c->stream));

@@ -403,6 +403,7 @@ int snprel_multi_geno_begin(snprel_multi *m, int64_t n_samp, int64_t snp_capacit
     for (int i = 0; i < m->active; i++) {
         const int64_t lo = i * m->per_dev, hi = std::min(snp_capacity, lo + m->per_dev);
         ck(m, i, snprel_geno_begin(m->ctx[i], n_samp, std::max<int64_t>(hi - lo, 0)));
+        ck(m, i, snprel_set_snp_origin(m->ctx[i], lo));     // keys the rounding draws by the global SNP index
     }
     MULTI_END(m)
 }
@@ -569,6 +570,12 @@ int snprel_multi_set_count_engine(snprel_multi *m, int engine) {
     MULTI_END(m)
 }
 
+int snprel_multi_set_rounding(snprel_multi *m, int mode) {
+    MULTI_BEGIN(m)
+    for (size_t i = 0; i < m->ctx.size(); i++) ck(m, (int)i, snprel_set_rounding(m->ctx[i], mode));
+    MULTI_END(m)
+}
+
 int snprel_multi_accumulate(snprel_multi *m, int est, int bayesian, int root) {
     MULTI_BEGIN(m)
     const int nd = m->active;
@@ -600,6 +607,7 @@ int snprel_multi_accumulate(snprel_multi *m, int est, int bayesian, int root) {
         // (a sum of per-device maxima bounds the maximum of the sums; 0 = some device did not measure it)
         g.diag_bound = (g.diag_bound > 0 && plans[i].diag_bound > 0) ? g.diag_bound + plans[i].diag_bound : 0.0;
         g.sum_rest += plans[i].sum_rest;
+        g.err_weight2 += plans[i].err_weight2;
     }
     on_each(m, [&](int i) { ck(m, i, snprel_accumulate(m->ctx[i], est, &g)); });
     peer_reduce(m, root);

@@ -56,7 +56,8 @@ def buffer_tensor(ptr, count, kind, device):
 
 _PLAN_MAX = ("max_abs", "max_abs_w")
 # sums are conservative for the per-sample maxima (max of sums <= sum of maxima)
-_PLAN_SUM = ("sum_bound", "err_weight", "scale", "total_missing", "max_missing", "n_snp", "diag_bound", "sum_rest")
+_PLAN_SUM = ("sum_bound", "err_weight", "scale", "total_missing", "max_missing", "n_snp", "diag_bound", "sum_rest",
+             "err_weight2")
 _PLAN_INT = ("total_missing", "max_missing", "n_snp")
 
 

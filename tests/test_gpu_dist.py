@@ -40,10 +40,12 @@ def _worker(rank, world, port, q):
     out = {}
     for name, est in (("GCTA", 1), ("EIGMIX", 3), ("Eigenstrat", 0)):
         ctx.geno_begin(n, hi - lo)
+        ctx.set_snp_origin(lo)
         ctx.geno_push_u8(g[lo:hi])
         D.accumulate_sharded(ctx, est, device=dev)
         out[name] = ctx.grm(name)[0]
     ctx.geno_begin(n, hi - lo)
+    ctx.set_snp_origin(lo)
     ctx.geno_push_u8(g[lo:hi])
     ctx.accumulate(10)
     D.allreduce_buffers(ctx.reduce_buffers(), device=dev)
@@ -51,10 +53,12 @@ def _worker(rank, world, port, q):
     ctx.mark_reduced()
     out["ibs"] = np.stack(ctx.ibs_num())
     ctx.geno_begin(n, hi - lo)
+    ctx.set_snp_origin(lo)
     ctx.geno_push_u8(g[lo:hi])
     out["mom"] = D.ibd_mom_sharded(ctx, kinship_constraint=True, device=dev)[:2]
     # the library's own peer-memory reduction (CUDA IPC) instead of NCCL: all-reduce and reduce-to-root
     ctx.geno_begin(n, hi - lo)
+    ctx.set_snp_origin(lo)
     ctx.geno_push_u8(g[lo:hi])
     D.accumulate_sharded(ctx, 1, device=dev, reduce="peer")
     out["gcta_peer"] = ctx.grm("GCTA")[0]

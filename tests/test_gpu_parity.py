@@ -619,9 +619,11 @@ def test_streamed_ingest_matches_the_blocking_path(pitch_pad):
         got = c.pca(genmat_only=True)
         plan = c.last_plan()
         assert c.stream_stats() == (1, 0)
-        if (plan.digits, plan.digits_w, plan.frac_bits, plan.frac_bits_w) == (plan_ref.digits, plan_ref.digits_w, plan_ref.frac_bits, plan_ref.frac_bits_w):
+        fmt = lambda p: (p.digits, p.digits_w, p.frac_bits, p.frac_bits_w, p.rounding)
+        if fmt(plan) == fmt(plan_ref):
             assert np.array_equal(got["genmat"], ref["genmat"])
-        assert relerr(got["genmat"], ref["genmat"]) < 1e-11 and abs(got["TraceXTX"] - ref["TraceXTX"]) <= 1e-12 * ref["TraceXTX"]
+        # (different formats: two quantisations of the same matrix, each within the tolerance of the exact one)
+        assert relerr(got["genmat"], ref["genmat"]) < 5e-11 and abs(got["TraceXTX"] - ref["TraceXTX"]) <= 1e-12 * ref["TraceXTX"]
         af, _, _ = c.snp_ratefreq()
         sub = g[:, idx]
         oref = O.subset_entries(sub, af, "Eigenstrat", n_total=n, trace=got["TraceXTX"])
@@ -629,7 +631,7 @@ def test_streamed_ingest_matches_the_blocking_path(pitch_pad):
         # GCTA (one more plane for the missing-pair denominators) and a second use of the same context
         c.geno_begin(n, m)
         c.geno_push_2b_async(host.numpy())
-        assert relerr(c.grm("GCTA")[0], gcta_ref) < 1e-11
+        assert relerr(c.grm("GCTA")[0], gcta_ref) < 5e-11
         assert c.stream_stats() == (2, 0)
         # any other entry point simply waits for the copies
         c.geno_begin(n, m)

@@ -35,6 +35,7 @@ def load(ctxs, g, cut, parts=None):
     parts = parts or [(0, cut), (cut, g.shape[0])]
     for c, (lo, hi) in zip(ctxs, parts):
         c.geno_begin(g.shape[1], hi - lo)
+        c.set_snp_origin(lo)                # keys the rounding draws by the global SNP index (snprel_set_rounding)
         c.geno_push_u8(g[lo:hi])
 
 

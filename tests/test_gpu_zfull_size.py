@@ -89,3 +89,39 @@ def test_pca_genmat_and_top32_eigenvectors_full_size(ws):
         assert float(np.max(np.abs(sgn * V[:, k] - v[:, k]))) < tol, (k, gap, tol)
     resid = np.linalg.norm(gm @ V - V * r["eigenval"][None, :32], axis=0)
     assert float(resid.max()) < 1e-9 * w[0]
+
+
+def test_rounding_modes_and_draws_full_size(ws):
+    """Config 2 under the default rounding mode ('auto'): randomised rounding of the main row table saves one
+    of eight tensor passes here (Hoeffding bound, failure probability 1e-12).  The
+    1e-10 tolerance is checked against the oracle for round-to-nearest and for four independent draws
+    (the SNP origin keys the draws), all at the scattered samples."""
+    ctx, sub = ws
+    af, _, _ = ctx.snp_ratefreq()
+    ix = np.ix_(IDX, IDX)
+
+    def run():
+        r = ctx.pca(genmat_only=True)
+        ref = O.subset_entries(sub, af, "Eigenstrat", n_total=N, trace=r["TraceXTX"])
+        pl = ctx.last_plan()
+        return float(np.max(np.abs(r["genmat"][ix] - ref) / np.maximum(np.abs(ref), 1.0))), pl, r["genmat"][ix].copy()
+
+    try:
+        ctx.set_rounding("nearest")
+        e0, p0, g0 = run()
+        assert p0.rounding == 0 and e0 < 1e-10
+        ctx.set_rounding("auto")
+        errs, mats = [], []
+        for origin in (0, 1000003, 987654321, 2 ** 41 + 5):
+            ctx.set_snp_origin(origin)
+            e, pl, gm = run()
+            assert pl.rounding == 1, "auto should pick randomised rounding at 1M SNPs"
+            assert pl.digits + pl.digits_w + pl.digits_d == p0.digits + p0.digits_w + p0.digits_d - 1 == 7
+            assert e < 1e-10, (origin, e)
+            errs.append(e)
+            mats.append(gm)
+        assert not np.array_equal(mats[0], mats[1])
+        print(f"config 2: nearest {e0:.2e} (8 passes), randomised draws {', '.join(f'{e:.2e}' for e in errs)} (7 passes)")
+    finally:
+        ctx.set_rounding("auto")
+        ctx.set_snp_origin(0)

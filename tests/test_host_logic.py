@@ -98,3 +98,71 @@ def test_window_owner_is_a_permutation_per_round():
             fwd = [window_owner(base + i, world) for i in range(world)]
             back = [window_owner(base + world + i, world) for i in range(world)]
             assert fwd == list(range(world)) and back == list(range(world))[::-1]
+
+
+def _plan(**kw):
+    from snprelate_b200._lib import Plan
+    p = Plan()
+    p.frac_bits = p.frac_bits_w = p.frac_bits_d = -1
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+# plan statistics of BASELINE config 2 (10 000 samples x 1 000 000 SNPs, 0.5 % missing) as the device measures them
+CONFIG2 = dict(max_abs=0.807, max_abs_w=0.085, err_weight=1.264e7, err_weight2=3.15e8, scale=1.99e6, sum_bound=1.651e7,
+               diag_bound=2.365e6, sum_rest=2.804e4, total_missing=50000343, max_missing=5300, n_snp=1000000)
+
+
+def test_format_choice_at_config2_statistics():
+    """snprel_plan_format (host only): round-to-nearest needs T5 + R3 = 8 tensor passes for the 1e-10 bound,
+    randomised rounding T4 + R3 = 7, 'auto' takes the cheaper one and reports which rounding it used."""
+    from snprelate_b200._lib import plan_format
+    p = _plan(**CONFIG2)
+    assert plan_format(0, p, "nearest", 10000) == 8 and (p.digits, p.digits_w, p.digits_d, p.rounding) == (5, 3, 0, 0)
+    near_f = p.frac_bits
+    p = _plan(**CONFIG2)
+    assert plan_format(0, p, "random", 10000) == 7 and (p.digits, p.digits_w, p.rounding) == (4, 3, 1)
+    assert p.frac_bits < near_f
+    p = _plan(**CONFIG2)
+    assert plan_format(0, p, "auto", 10000) == 7 and p.rounding == 1
+    # GCTA: one more exact pass for the missing-pair denominators
+    p = _plan(**dict(CONFIG2, scale=2e6))
+    assert plan_format(1, p, "auto", 10000) == 8 and (p.digits, p.digits_w, p.digits_d) == (4, 3, 1)
+    # the Hoeffding bound the library promises: 2^-f sqrt(1/2 sum B^2 ln(2 pairs / 1e-12)) + the R term <= 0.9e-10 scale
+    import math
+    p = _plan(**CONFIG2)
+    plan_format(0, p, "random", 10000)
+    t = 2.0 ** -p.frac_bits * math.sqrt(0.5 * p.err_weight2 * math.log(2 * (0.5 * 1e4 * (1e4 + 1)) / 1e-12))
+    r = 2.0 ** -(p.frac_bits_w + 1) * p.max_missing
+    assert t + r <= 0.9e-10 * p.scale
+    # without the measured sum of squares the bound falls back to sum B^2 <= 127 sum |B|
+    p = _plan(**dict(CONFIG2, err_weight2=0.0))
+    assert plan_format(0, p, "auto", 10000) == 7
+
+
+def test_format_choice_keeps_round_to_nearest_where_nothing_is_saved():
+    from snprelate_b200._lib import plan_format
+    for frac in (0.009, 0.02, 0.05):          # 9 000 ... 50 000 SNPs: the sqrt(M) advantage is below one digit
+        st = {k: (v * frac if k not in ("max_abs", "max_abs_w") else v) for k, v in CONFIG2.items()}
+        st.update(total_missing=int(st["total_missing"]), max_missing=int(st["max_missing"]) + 20, n_snp=int(st["n_snp"]), diag_bound=0.0)
+        a, b = _plan(**st), _plan(**st)
+        assert plan_format(0, a, "nearest", 700) == plan_format(0, b, "auto", 700)
+        assert b.rounding == 0 and (a.frac_bits, a.digits) == (b.frac_bits, b.digits)
+    # a caller-fixed format brings its rounding along
+    p = _plan(**CONFIG2)
+    p.frac_bits, p.frac_bits_w, p.rounding = 31, 26, 1
+    assert plan_format(0, p, "nearest", 10000) == 7 and p.rounding == 1
+    # KING-homo has no real row table: never randomised
+    p = _plan(**dict(CONFIG2, err_weight=0.0, err_weight2=0.0))
+    plan_format(13, p, "random", 10000)
+    assert p.rounding == 0
+
+
+def test_plan_format_rejects_bad_arguments():
+    import snprelate_b200 as S
+    from snprelate_b200._lib import plan_format
+    with pytest.raises(S.SNPRelError):
+        plan_format(10, _plan(**CONFIG2), "auto", 100)       # IBS is not a covariance estimator
+    with pytest.raises(S.SNPRelError):
+        plan_format(0, _plan(**CONFIG2), 7, 100)

@@ -4,6 +4,8 @@ evaluate format changes before touching the kernel.  Two schemes on the bench ge
 
   A (round 1)  C = sum U[g_i] x_j - sum W[g_i] + sum W[g_i] m_j,            U 5 digits, W 4 digits
   B (shipped since round 2) C = sum T[g_i] B_l[g_j] - sum D[g_i] + sum D[g_i] m_j        T 5 digits, D 3 digits
+  B' (the default from ~1e5 SNPs on: snprel_set_rounding 'auto') the same with T rounded at random
+               (the library's own counter-based draws, keyed by the global SNP index)      T 4 digits, D 3 digits
                with per-SNP integer column tables B_l[g] = s_l g - t_l (|B| <= 127, 0 for missing),
                T = U / s_l, D = (mu_l - t_l / s_l) U: the centring of the column sample moves into
                the main passes and the missing-data pass only carries the rational-approximation
@@ -82,10 +84,23 @@ def table_gram(qtab3, nd, bvals):
     return big, ovf
 
 
-def run(name, T3, f, nT, Bv, D3, fw, nD, ew, maxmiss, dither=False, s2=None):
+def dither_u01(origin, shape):
+    """the library's draw for table entry (global SNP index origin + l, genotype g): grm.cu:dither_u01"""
+    M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+    l = (np.arange(shape[0], dtype=np.uint64) + np.uint64(origin))[:, None]
+    g = np.arange(shape[1], dtype=np.uint64)[None, :]
+    with np.errstate(over="ignore"):
+        x = np.uint64(0xD17E5 | 1) ^ ((l * np.uint64(4) + g) * np.uint64(0xD1342543DE82EF95))
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    return (x >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+
+
+def run(name, T3, f, nT, Bv, D3, fw, nD, ew, maxmiss, dither=False, s2=None, origin=0):
     if dither:   # unbiased randomised rounding, one draw per table entry: floor(v 2^f + u), u ~ U[0, 1)
-        rng = np.random.default_rng(7)
-        qT = np.floor(T3 * 2.0 ** f + rng.random(T3.shape)).astype(np.int64)
+        qT = np.floor(T3 * 2.0 ** f + dither_u01(origin, T3.shape)).astype(np.int64)
     else:
         qT = np.rint(T3 * 2.0 ** f).astype(np.int64)
     qD = np.rint(D3 * 2.0 ** fw).astype(np.int64)
@@ -137,5 +152,7 @@ fU4 = int(np.floor(np.log2((127 * (256.0 ** 4 - 1) / 255 - 1) / np.max(np.abs(U)
 fT4 = int(np.floor(np.log2((127 * (256.0 ** 4 - 1) / 255 - 1) / np.max(np.abs(T3)))))
 print("   randomised rounding of the main table (probabilistic bound, failure probability 1e-12):")
 run("A', U 4 digits dithered", U, fU4, 4, x, W3, 28, 4, ewA, maxmiss, True, float(np.max((x * x).sum(axis=0))))
-run("B', T 4 digits dithered", T3, fT4, 4, Bv, D3, fD, 3, ewB, maxmiss, True, float(np.max((Bv * Bv).sum(axis=0))))
+s2B = float(np.max((np.ceil(Bv * Bv / 127.0) * 127.0).sum(axis=0)))      # as measured by sample_stats_kernel (unit 127)
+for origin in (0, 1000003, 987654321, 2 ** 41 + 5, 31337):         # shipped default at this size ('auto' -> randomised)
+    run(f"B', T 4 digits dithered, SNP origin {origin}", T3, fT4, 4, Bv, D3, fD, 3, ewB, maxmiss, True, s2B, origin)
 print(f"   ({time.time() - t0:.0f} s)   target: 1e-10")
