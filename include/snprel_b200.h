@@ -219,7 +219,8 @@ int snprel_eigmix(snprel_ctx *ctx, int eigen_cnt, int diagadj, double *ibd,
  *    go to 0.  snprel_plan.rounding reports what the last accumulate used.
  * Results are a pure function of (genotypes, SNP origin, mode): run-to-run identical, and identical
  * for any SNP sharding whose origins are the shards' global offsets.  All ranks of a multi-GPU run
- * must use the same mode. */
+ * must use the same mode.  The environment variable SNPREL_ROUNDING = nearest | random | auto gives the
+ * initial mode of every context created afterwards (R sessions, the Python host). */
 int snprel_set_rounding(snprel_ctx *ctx, int mode);
 /* Global index of this context's first SNP row (default 0; snprel_geno_begin resets it).  Only keys
  * the rounding draws of mode 1 / 2: SNP shards of one data set must cover disjoint index ranges

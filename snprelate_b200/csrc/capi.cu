@@ -1,6 +1,7 @@
 // extern "C" surface of libsnprel_b200.so (see include/snprel_b200.h).
 // Every entry point catches snprel::Error and returns a code; messages are kept
 // per context (and in a process-wide slot for failures before a context exists).
+#include <cstdlib>
 #include "common.cuh"
 
 using namespace snprel;
@@ -54,6 +55,17 @@ int snprel_create(snprel_ctx **out, int device) {
         return 1;
     }
     *out = nullptr;
+    // SNPREL_ROUNDING = nearest | random | auto: initial mode of snprel_set_rounding (default auto)
+    int round_mode = 2;
+    if (const char *env = getenv("SNPREL_ROUNDING")) {
+        const std::string v(env);
+        if (v == "nearest") round_mode = 0;
+        else if (v == "random") round_mode = 1;
+        else if (!(v == "auto" || v.empty())) {
+            g_create_error = "SNPREL_ROUNDING: expected \"nearest\", \"random\" or \"auto\", got \"" + v + "\"";
+            return 1;
+        }
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= 0) {
@@ -68,6 +80,7 @@ int snprel_create(snprel_ctx **out, int device) {
     }
     snprel_ctx *c = new snprel_ctx();
     c->device = device;
+    c->round_mode = round_mode;
     try {
         CUDA_CHECK(cudaSetDevice(device));
         cudaDeviceProp prop;

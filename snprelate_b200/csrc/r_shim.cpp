@@ -32,27 +32,13 @@ namespace {
 // counterpart of the reference's process-global GWAS::MCWorkingGeno (src/dGenGWAS.cpp:2000) and
 // saves a CUDA stream / event / buffer set-up per .Call.  Every routine re-loads the SELECTED
 // genotypes, because gnrSetGenoSpace / gnrSelSNP_Base may have changed the selection in between.
-// SNPREL_ROUNDING = nearest | random | auto (default): rounding of the covariance path's main fixed-point
-// table (snprel_set_rounding; "nearest" keeps the worst-case error bound at the price of one tensor pass)
-int rounding_mode() {
-    const char *env = getenv("SNPREL_ROUNDING");
-    if (!env || !*env || !strcmp(env, "auto")) return 2;
-    if (!strcmp(env, "nearest")) return 0;
-    if (!strcmp(env, "random")) return 1;
-    throw ErrCoreArray("SNPREL_ROUNDING: expected \"nearest\", \"random\" or \"auto\"");
-}
-
 struct Ctx {
     snprel_ctx *h = nullptr;
     Ctx() {
         static snprel_ctx *shared = nullptr;
-        if (!shared) {
-            const int mode = rounding_mode();
-            if (snprel_create(&shared, 0) != 0) {
-                shared = nullptr;
-                throw ErrCoreArray("%s", snprel_last_error(nullptr));
-            }
-            snprel_set_rounding(shared, mode);
+        if (!shared && snprel_create(&shared, 0) != 0) {
+            shared = nullptr;
+            throw ErrCoreArray("%s", snprel_last_error(nullptr));
         }
         h = shared;
     }
@@ -101,12 +87,10 @@ snprel_multi *multi_handle() {
         }
     }
     if (dev.size() < 2) return nullptr;
-    const int mode = rounding_mode();
     if (snprel_multi_create(dev.data(), (int)dev.size(), &shared) != 0) {
         shared = nullptr;
         throw ErrCoreArray("%s", snprel_multi_last_error(nullptr));
     }
-    snprel_multi_set_rounding(shared, mode);
     return shared;
 }
 

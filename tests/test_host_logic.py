@@ -166,3 +166,12 @@ def test_plan_format_rejects_bad_arguments():
         plan_format(10, _plan(**CONFIG2), "auto", 100)       # IBS is not a covariance estimator
     with pytest.raises(S.SNPRelError):
         plan_format(0, _plan(**CONFIG2), 7, 100)
+
+
+def test_rounding_environment_variable_is_validated(monkeypatch):
+    """SNPREL_ROUNDING gives the initial rounding mode of every context; a bad value fails snprel_create
+    before any device is touched."""
+    import snprelate_b200 as S
+    monkeypatch.setenv("SNPREL_ROUNDING", "stochastic")
+    with pytest.raises(S.SNPRelError, match="SNPREL_ROUNDING"):
+        S.Context(0)
