@@ -216,7 +216,9 @@ int snprel_eigmix(snprel_ctx *ctx, int eigen_cnt, int diagadj, double *ibd,
  *    bound grows with sqrt(#SNPs) where the worst case grows with #SNPs: from about 5e5 SNPs on it
  *    saves one base-256 digit of T, i.e. one of eight tensor passes at config-2 size.
  * 2 (default): whichever of the two needs FEWER tensor passes for the requested tolerance; ties
- *    go to 0.  snprel_plan.rounding reports what the last accumulate used.
+ *    go to 0, and so do small problems (n_samp^2 * n_snp < 2^36, where a pass costs microseconds and
+ *    round-to-nearest leaves the larger margin).  snprel_plan.rounding reports what the last
+ *    accumulate used.
  * Results are a pure function of (genotypes, SNP origin, mode): run-to-run identical, and identical
  * for any SNP sharding whose origins are the shards' global offsets.  All ranks of a multi-GPU run
  * must use the same mode.  The environment variable SNPREL_ROUNDING = nearest | random | auto gives the

@@ -867,6 +867,7 @@ static bool choose_format_one(int est, snprel_plan &plan, int &nU, int &nW, int 
     return feasible;
 }
 
+constexpr double AUTO_ROUNDING_MIN_WORK = 68719476736.0;   // 2^36 pair-SNPs per pass
 // round_mode as in snprel_set_rounding.  A caller-fixed format (frac_bits >= 0) brings its rounding
 // along in plan.rounding; otherwise mode 2 takes randomised rounding only where its (probabilistic)
 // bound is met with FEWER tensor passes than the worst-case bound needs.
@@ -875,7 +876,10 @@ static void choose_format(int est, snprel_plan &plan, int &nU, int &nW, int &nD,
         choose_format_one(est, plan, nU, nW, nD, plan.rounding ? 1 : 0, n_samp);
         return;
     }
-    if (round_mode != 2 || est == SNPREL_EST_KING_HOMO) {
+    // mode 2 on a small problem (n_samp^2 n_snp < 2^36: a tensor pass costs microseconds): nothing to gain, and
+    // round-to-nearest leaves the larger margin to the tolerance
+    const bool small = n_samp * n_samp * (double)std::max<int64_t>(plan.n_snp, 0) < AUTO_ROUNDING_MIN_WORK;
+    if (round_mode != 2 || est == SNPREL_EST_KING_HOMO || small) {
         choose_format_one(est, plan, nU, nW, nD, round_mode == 1 ? 1 : 0, n_samp);
         return;
     }

@@ -43,9 +43,8 @@ def test_every_mode_meets_the_tolerance_small():
             r = c.pca(eigen_cnt=4, need_genmat=True)
             assert relerr(r["genmat"], pref) < TOL, mode
         assert seen["random"][0] <= seen["nearest"][0]
-        # auto: randomised only where it saves a pass, never more passes than round-to-nearest
-        assert seen["auto"][0] == min(seen["nearest"][0], seen["random"][0])
-        assert seen["auto"][1] == (1 if seen["random"][0] < seen["nearest"][0] else 0)
+        # auto on a small problem (n_samp^2 n_snp < 2^36): round to nearest, whatever randomised rounding would save
+        assert seen["auto"] == seen["nearest"]
         with pytest.raises(S.SNPRelError):
             c.set_rounding(3)
 

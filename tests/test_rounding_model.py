@@ -14,6 +14,8 @@ from oracle import snprel_oracle as O
 from snprelate_b200._lib import Plan, plan_format
 
 N, M, SEED, MISS = 64, 200000, 424242, 0.005
+N_FORMAT = 10000      # the format is chosen as for a 10 000-sample matrix of the same SNPs (more pairs in the union
+                      # bound than the 64 samples modelled: conservative; and above the work threshold of 'auto')
 
 
 def dither_u01(origin, m):
@@ -117,7 +119,7 @@ def _evaluate(m, plan, origin):
 
 def test_round_to_nearest_meets_its_worst_case_bound(model):
     p = _plan(model["stats"])
-    plan_format(0, p, "nearest", N)
+    plan_format(0, p, "nearest", N_FORMAT)
     err = _evaluate(model, p, 0)
     bound = (2.0 ** -(p.frac_bits + 1) * p.err_weight + 2.0 ** -(p.frac_bits_w + 1) * p.max_missing) / p.scale
     assert p.rounding == 0 and err <= bound <= 1e-10, (err, bound)
@@ -125,9 +127,11 @@ def test_round_to_nearest_meets_its_worst_case_bound(model):
 
 def test_randomised_rounding_meets_the_hoeffding_bound_over_draws(model):
     p = _plan(model["stats"])
-    n_near = plan_format(0, _plan(model["stats"]), "nearest", N)
-    assert plan_format(0, p, "auto", N) == n_near - 1 and p.rounding == 1       # 200 000 SNPs: one digit of T saved
-    pairs = 0.5 * N * (N + 1)
+    n_near = plan_format(0, _plan(model["stats"]), "nearest", N_FORMAT)
+    assert plan_format(0, p, "auto", N_FORMAT) == n_near - 1 and p.rounding == 1       # 200 000 SNPs: one digit of T saved
+    small = _plan(model["stats"])
+    assert plan_format(0, small, "auto", N) == n_near and small.rounding == 0    # 64^2 x 200 000 < 2^36: not worth it
+    pairs = 0.5 * N_FORMAT * (N_FORMAT + 1)
     bound = (2.0 ** -p.frac_bits * math.sqrt(0.5 * p.err_weight2 * math.log(2 * pairs / 1e-12))
              + 2.0 ** -(p.frac_bits_w + 1) * p.max_missing) / p.scale
     assert bound <= 0.9e-10 * 1.0000001
