@@ -333,6 +333,9 @@ typedef struct snprel_plan {
                               is used); sum-reduced.  Variance proxy of the randomised-rounding bound */
 } snprel_plan;
 
+/* sizeof(snprel_plan) of the library build: a binding that mirrors the struct (ctypes, R) checks its own
+ * layout against it when it loads the library. */
+int64_t snprel_abi_sizeof_plan(void);
 int snprel_plan_local(snprel_ctx *ctx, int estimator, snprel_plan *plan);
 /* Host-only (no device, no context): the fixed-point format the library chooses for the given
  * (merged) plan statistics -- fills frac_bits*, digits*, rounding exactly as snprel_accumulate

@@ -149,6 +149,11 @@ def load_library():
         fn.restype = i32
     lib.snprel_destroy.argtypes = [p]
     lib.snprel_destroy.restype = None
+    lib.snprel_abi_sizeof_plan.argtypes = []
+    lib.snprel_abi_sizeof_plan.restype = C.c_int64
+    if lib.snprel_abi_sizeof_plan() != C.sizeof(Plan):
+        raise SNPRelError(f"{path}: snprel_plan is {lib.snprel_abi_sizeof_plan()} bytes in the library but "
+                          f"{C.sizeof(Plan)} in this binding: rebuild the library (or update _lib.Plan)")
     lib.snprel_last_error.argtypes = [p]
     lib.snprel_last_error.restype = C.c_char_p
     lib.snprel_version.argtypes = []
@@ -170,7 +175,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "snprel_create", "snprel_destroy", "snprel_last_error", "snprel_version",
+    "snprel_create", "snprel_destroy", "snprel_last_error", "snprel_version", "snprel_abi_sizeof_plan",
     "snprel_geno_begin", "snprel_geno_push_u8", "snprel_geno_push_2b", "snprel_geno_push_bitstream", "snprel_geno_synth",
     "snprel_geno_dim", "snprel_geno_copy_u8", "snprel_geno_copy_2b", "snprel_snp_ratefreq", "snprel_select_snp_base", "snprel_select_snp_base_ex",
     "snprel_ibs_num", "snprel_ibs_ave", "snprel_ibd_mom", "snprel_ibd_mom_sums", "snprel_ibd_mom_from_sums", "snprel_king_robust", "snprel_king_robust_counts",

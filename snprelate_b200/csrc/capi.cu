@@ -42,6 +42,8 @@ static std::string g_create_error;
 
 extern "C" {
 
+int64_t snprel_abi_sizeof_plan(void) { return (int64_t)sizeof(snprel_plan); }
+
 const char *snprel_version(void) { return "snprel_b200 0.2 (sm_100a)"; }
 
 int snprel_device_count(void) {
