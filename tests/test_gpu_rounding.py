@@ -121,3 +121,47 @@ def test_shards_reproduce_the_one_context_result_under_random_rounding():
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_plan_statistics_match_a_numpy_restatement():
+    """The statistics every error bound rests on -- max_j sum_l |B_l[g_jl]|, max_j sum_l B_l[g_jl]^2 (in units of
+    127, rounded up per SNP), the per-sample missing counts -- against a numpy restatement of the per-SNP integer
+    column tables (grm.cu:coltab_kernel).  The device may pick a neighbouring s for a handful of SNPs (fused
+    multiply-adds in the candidate loop), hence the small relative tolerance on the two sums; they must never be
+    BELOW what the data says by more than that."""
+    n, m = 333, 6000
+    g = O.synth_geno(n, m, seed=12, miss_rate=0.03, maf_lo=0.02)
+    valid = g <= 2
+    x = np.where(valid, g, 0).astype(np.float64)
+    num = valid.sum(axis=1)
+    mu = x.sum(axis=1) / np.maximum(num, 1)
+    sfrq = mu * 0.5
+    ok = (sfrq > 0) & (sfrq < 1)
+    r = 1.0 / np.sqrt(np.where(ok, sfrq * (1 - sfrq), 1.0))
+    w = np.where(ok, r * r, 0.0)
+    umax = w * np.maximum(mu, 2.0 - mu)
+    s_hi = np.minimum(np.floor(127.0 / np.maximum(2.0 - mu, 1e-9)), 127.0)
+    s_tgt = np.minimum(s_hi, np.maximum(24.0, 127.0 * umax / 40.0))
+    bs, bt, be = np.ones(m), np.rint(mu), np.full(m, 1e300)
+    for q in range(31):
+        sc = np.maximum(1.0, np.floor(s_tgt * (0.7 + 0.01 * q)))
+        tc = np.rint(sc * mu)
+        good = ~((2 * sc - tc > 127.0) | (tc > 127.0))
+        e = np.where(good, np.abs(mu - tc / sc), np.inf)
+        better = e < be
+        bs, bt, be = np.where(better, sc, bs), np.where(better, tc, bt), np.where(better, e, be)
+    live = (w > 0) & (num > 0)
+    s, t = np.where(live, bs, 1.0), np.where(live, bt, 0.0)
+    B = np.where(valid, s[:, None] * x - t[:, None], 0.0)
+    ew = float(np.abs(B).sum(axis=0).max())
+    s2 = float((np.ceil(B * B / 127.0) * 127.0).sum(axis=0).max())
+    with S.Context(0) as c:
+        c.geno_begin(n, m)
+        c.geno_push_u8(g)
+        p = c.plan_local(0)
+    assert p.n_snp == m and p.total_missing == int((~valid).sum()) and p.max_missing == int((~valid).sum(axis=0).max())
+    assert abs(p.err_weight - ew) <= 2e-3 * ew, (p.err_weight, ew)
+    assert abs(p.err_weight2 - s2) <= 4e-3 * s2, (p.err_weight2, s2)
+    assert p.err_weight2 <= 127.0 * p.err_weight and p.err_weight2 >= p.err_weight     # |B| >= 1 wherever B != 0
+    T = np.where(live[:, None], w[:, None] * (np.arange(3)[None, :] - mu[:, None]) / s[:, None], 0.0)
+    assert abs(p.max_abs - float(np.abs(T).max())) <= 0.05 * p.max_abs

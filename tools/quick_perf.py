@@ -8,14 +8,22 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 m = int(sys.argv[2]) if len(sys.argv) > 2 else 1000000
 ests = sys.argv[3].split(",") if len(sys.argv) > 3 else ["pca", "gcta"]
 miss = float(sys.argv[4]) if len(sys.argv) > 4 else 0.005
+reps = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 ctx = S.Context(0)
 ctx.geno_begin(n, m)
 t0 = time.time(); ctx.geno_synth(m, miss_rate=miss); print(f"synth {time.time()-t0:.2f}s", flush=True)
 ids = {"pca": 0, "gcta": 1, "eigmix": 3, "ibs": EST_IBS, "king": EST_KING_ROBUST, "beta": EST_BETA}
 for e in ests:
     t0 = time.time()
-    ms = ctx.time_accumulate(ids[e], 1)
+    ms = ctx.time_accumulate(ids[e], 1)        # first call of this estimator: includes its buffer allocations
     wall = time.time() - t0
+    if reps > 1:
+        again = []
+        for _ in range(reps - 1):
+            t1 = time.time()
+            ms = ctx.time_accumulate(ids[e], 1)
+            again.append((ms, (time.time() - t1) * 1e3, ctx.last_hot_kernel()[0]))
+        print("   repeat calls (device step ms, wall ms, hot ms): " + "; ".join(f"{a:.1f}, {b:.1f}, {c:.1f}" for a, b, c in again))
     hot, nl, units = ctx.last_hot_kernel()
     pl = ctx.last_plan() if ids[e] < 10 else None
     if pl is not None:
