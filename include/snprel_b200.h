@@ -212,9 +212,10 @@ int snprel_eigmix(snprel_ctx *ctx, int eigen_cnt, int diagadj, double *ibd,
  *    (snprel_set_snp_origin).  The error of an entry is then a sum of independent zero-mean terms
  *    of width |B_l| 2^-frac_bits, and by Hoeffding's inequality it stays below
  *    2^-frac_bits * sqrt(1/2 sum_l B_l^2 ln(2 #pairs / 1e-12)) for ALL entries simultaneously with
- *    probability >= 1 - 1e-12 over the draws, for any data set; sum B^2 <= 127 err_weight.  The
- *    bound grows with sqrt(#SNPs) where the worst case grows with #SNPs: from about 5e5 SNPs on it
- *    saves one base-256 digit of T, i.e. one of eight tensor passes at config-2 size.
+ *    probability >= 1 - 1e-12 over the draws, for any data set; max_j sum_l B_l[g_jl]^2 is measured
+ *    (snprel_plan.err_weight2, else <= 127 err_weight).  The bound grows with sqrt(#SNPs) where the
+ *    worst case grows with #SNPs: from about 1e5 SNPs on it saves one base-256 digit, i.e. one of
+ *    eight tensor passes at config-2 size (10 000 samples x 1 000 000 SNPs).
  * 2 (default): whichever of the two needs FEWER tensor passes for the requested tolerance; ties
  *    go to 0, and so do small problems (n_samp^2 * n_snp < 2^36, where a pass costs microseconds and
  *    round-to-nearest leaves the larger margin).  snprel_plan.rounding reports what the last
@@ -226,7 +227,8 @@ int snprel_eigmix(snprel_ctx *ctx, int eigen_cnt, int diagadj, double *ibd,
 int snprel_set_rounding(snprel_ctx *ctx, int mode);
 /* Global index of this context's first SNP row (default 0; snprel_geno_begin resets it).  Only keys
  * the rounding draws of mode 1 / 2: SNP shards of one data set must cover disjoint index ranges
- * (snprel_multi_* and snprelate_b200/dist.py set the shard offsets). */
+ * (snprel_multi_* sets the shard offsets itself, snprel_geno_synth does for generated shards; a host that
+ * pushes its own SNP ranges into several contexts calls this after snprel_geno_begin). */
 int snprel_set_snp_origin(snprel_ctx *ctx, int64_t origin);
 
 
