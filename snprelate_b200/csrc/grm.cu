@@ -42,7 +42,8 @@ constexpr int LIMB = 20;           // the per-sample vector is accumulated in 20
 // scalars[]: 0 = sum of d_l (EIGMIX SumDenominator / KING-homo sum p(1-p)), 1 = sum d2_l
 // iscalars[]: 0 = nLocus (GCTA), 2 = low limb and 3 = upper limbs of sum_l qb_l (constant of the vector)
 
-constexpr int SQ_UNIT = 127;       // unit of the per-sample sum of squared column-table entries (127^2 / 127 fits a byte lane)
+constexpr int AUX_MAX = 84;        // largest entry of the auxiliary byte tables (diagonal bound, squares): THREE rows add up in a byte lane
+constexpr int SQ_UNIT = 193;       // unit of the per-sample sum of squared column-table entries: ceil(127^2 / 193) = 84
 
 struct SnpTables {
     long long qU[4];   // fixed-point T = U / s (row table of the main passes)
@@ -109,7 +110,7 @@ __device__ __forceinline__ SnpCoef snp_coef(const SnpStat st, int est, int bayes
 
 // ---- per-SNP integer column tables ---------------------------------------------
 // coltab[l] = (s_l, t_l); tabB[l] = bytes (B[0], B[1], B[2], 0); tabBabs[l] = their magnitudes;
-// tabBsq[l] = bytes ceil(B[g]^2 / SQ_UNIT) (<= 127): summed per sample they bound sum_l B_l[g]^2, the
+// tabBsq[l] = bytes ceil(B[g]^2 / SQ_UNIT) (<= AUX_MAX): summed per sample they bound sum_l B_l[g]^2, the
 // variance proxy of the randomised-rounding error bound (u_table_error).
 // A pure function of the SNP's own counts, so every rank of a sharded run picks the same table
 // for the same SNP without communication.
@@ -258,7 +259,7 @@ __global__ void plan_kernel(const SnpStat *__restrict__ st, const int2 *__restri
 }
 
 // ---- measured bound of the diagonal --------------------------------------------------------
-// tabF[l] = bytes ceil(w_l (g - mu_l)^2 / c) for g = 0, 1, 2 (0 for missing), c = out[5] / 127: summed per
+// tabF[l] = bytes ceil(w_l (g - mu_l)^2 / c) for g = 0, 1, 2 (0 for missing), c = out[5] / AUX_MAX: summed per
 // sample by sample_stats_kernel it gives X_i >= C_ii, and by Cauchy-Schwarz every entry of the main
 // plane obeys |sum_l T_l[g_il] B_l[g_jl]| <= sqrt(X_i (2 X_j + 2 sum_l w_l delta_l^2)) -- a bound that follows
 // the data (about 2 per SNP) where the worst case sum_l max|T_l| max|B_l| assumes a sample that is
@@ -269,12 +270,12 @@ __global__ void diagtab_kernel(const SnpStat *__restrict__ st, int64_t n_snp, in
     const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_snp) return;
     const SnpCoef k = snp_coef(st[l], est, bayesian);
-    const double c = plan_out[5] / 127.0;
+    const double c = plan_out[5] / (double)AUX_MAX;
     uint32_t word = 0;
     if (c > 0 && k.w > 0) {
         for (int g = 0; g < 3; g++) {
             const double v = k.w * ((double)g - k.mu) * ((double)g - k.mu);
-            const double q = fmin(127.0, ceil(v / c * (1.0 + 1e-12)));
+            const double q = fmin((double)AUX_MAX, ceil(v / c * (1.0 + 1e-12)));
             word |= (uint32_t)q << (8 * g);
         }
     }
@@ -311,7 +312,7 @@ sample_stats_kernel(const uint32_t *__restrict__ geno, const uint32_t *__restric
     const bool live = wc < row_words;
     const uint32_t *p = geno + l0 * row_words + (live ? wc : 0);
     uint32_t e16[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // |B| sums: selector q -> e16[2q] (bytes 0,2), e16[2q+1] (bytes 1,3)
-    uint32_t f16[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // diagonal-bound sums, same lanes (entries <= 127: 512 rows fit 16 bits)
+    uint32_t f16[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // diagonal-bound sums, same lanes (entries <= AUX_MAX: 512 rows fit 16 bits)
     uint32_t s16[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // squared column-table sums in SQ_UNIT, same lanes
     uint32_t m16[8] = {0, 0, 0, 0, 0, 0, 0, 0}, h16[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t m8[4] = {0, 0, 0, 0}, h8[4] = {0, 0, 0, 0};
@@ -321,6 +322,7 @@ sample_stats_kernel(const uint32_t *__restrict__ geno, const uint32_t *__restric
 #pragma unroll
         for (int g5 = 0; g5 < 5; g5++) {
             uint32_t m2 = 0, h2 = 0;
+            uint32_t fb[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};   // byte-lane sums of the group's three rows (3 x AUX_MAX <= 255)
             uint32_t w[3];
 #pragma unroll
             for (int r = 0; r < 3; r++) {
@@ -341,16 +343,19 @@ sample_stats_kernel(const uint32_t *__restrict__ geno, const uint32_t *__restric
                     const uint32_t v = __byte_perm(t, 0, sel[q]);
                     e16[2 * q] += __byte_perm(v, 0, 0x4240);
                     e16[2 * q + 1] += __byte_perm(v, 0, 0x4341);
-                    if (with_f) {
-                        const uint32_t vf = __byte_perm(tf, 0, sel[q]);
-                        f16[2 * q] += __byte_perm(vf, 0, 0x4240);
-                        f16[2 * q + 1] += __byte_perm(vf, 0, 0x4341);
-                    }
-                    if (with_s) {
-                        const uint32_t vs = __byte_perm(ts, 0, sel[q]);
-                        s16[2 * q] += __byte_perm(vs, 0, 0x4240);
-                        s16[2 * q + 1] += __byte_perm(vs, 0, 0x4341);
-                    }
+                    if (with_f) fb[q] += __byte_perm(tf, 0, sel[q]);
+                    if (with_s) sb[q] += __byte_perm(ts, 0, sel[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {        // spread the three-row byte sums into the 16-bit lanes
+                if (with_f) {
+                    f16[2 * q] += __byte_perm(fb[q], 0, 0x4240);
+                    f16[2 * q + 1] += __byte_perm(fb[q], 0, 0x4341);
+                }
+                if (with_s) {
+                    s16[2 * q] += __byte_perm(sb[q], 0, 0x4240);
+                    s16[2 * q + 1] += __byte_perm(sb[q], 0, 0x4341);
                 }
             }
             m4a += m2 & 0x33333333u;
@@ -733,7 +738,7 @@ void grm_plan_local(snprel_ctx *c, int est, snprel_plan *plan) {
     }
     plan->err_weight2 = (est == SNPREL_EST_KING_HOMO) ? 0.0 : (double)sq * (double)SQ_UNIT;   // >= max_i sum_l B_l[g_il]^2
     // X = max_i sum_l ceil(w (g - mu)^2 / c) c  >=  max_i C_ii   (0: not measured)
-    plan->diag_bound = (est == SNPREL_EST_KING_HOMO) ? 0.0 : (double)dg * (h[5] / 127.0);
+    plan->diag_bound = (est == SNPREL_EST_KING_HOMO) ? 0.0 : (double)dg * (h[5] / (double)AUX_MAX);
     plan->sum_rest = h[6];
     c->chunk_bound.assign(hchunk.begin(), hchunk.end());
     plan->max_abs = h[0];

@@ -70,7 +70,7 @@ def build_model():
     trace = float(np.trace(C))
     stats = dict(max_abs=float(np.abs(T3).max()), max_abs_w=float(np.abs(R3).max()),
                  err_weight=float(np.abs(B).sum(axis=0).max()),
-                 err_weight2=float((np.ceil(B * B / 127.0) * 127.0).sum(axis=0).max()),   # as sample_stats_kernel measures it
+                 err_weight2=float((np.ceil(B * B / 193.0) * 193.0).sum(axis=0).max()),   # as sample_stats_kernel measures it
                  scale=trace / (N - 1), sum_bound=float((np.abs(T3).max(axis=1) * np.abs(B).max(axis=1)).sum() * 1.1),
                  total_missing=int(mis.sum()), max_missing=int(mis.sum(axis=0).max()), n_snp=M)
     return dict(T3=T3, R3=R3, code=code, B=B, mis=mis, C=C, stats=stats)

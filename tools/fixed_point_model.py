@@ -152,7 +152,7 @@ fU4 = int(np.floor(np.log2((127 * (256.0 ** 4 - 1) / 255 - 1) / np.max(np.abs(U)
 fT4 = int(np.floor(np.log2((127 * (256.0 ** 4 - 1) / 255 - 1) / np.max(np.abs(T3)))))
 print("   randomised rounding of the main table (probabilistic bound, failure probability 1e-12):")
 run("A', U 4 digits dithered", U, fU4, 4, x, W3, 28, 4, ewA, maxmiss, True, float(np.max((x * x).sum(axis=0))))
-s2B = float(np.max((np.ceil(Bv * Bv / 127.0) * 127.0).sum(axis=0)))      # as measured by sample_stats_kernel (unit 127)
+s2B = float(np.max((np.ceil(Bv * Bv / 193.0) * 193.0).sum(axis=0)))      # as measured by sample_stats_kernel (unit 193)
 for origin in (0, 1000003, 987654321, 2 ** 41 + 5, 31337):         # shipped default at this size ('auto' -> randomised)
     run(f"B', T 4 digits dithered, SNP origin {origin}", T3, fT4, 4, Bv, D3, fD, 3, ewB, maxmiss, True, s2B, origin)
 print(f"   ({time.time() - t0:.0f} s)   target: 1e-10")
