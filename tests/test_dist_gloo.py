@@ -41,9 +41,22 @@ def _worker(rank, world, port, q):
     plan.max_missing = 5 + rank
     plan.total_missing = 50 + rank
     plan.err_weight = 7.0
+    plan.err_weight2 = 40.0 + rank
     plan.scale = 2.5
     plan.n_snp = 1000 * (rank + 1)
     plan = D.reduce_plan(plan, device=None)
+    # every rank derives the SAME fixed-point format (digits, fractional bits, rounding rule) from the merged
+    # statistics, here those of two half shards of config 2 (host-only format choice of the library)
+    half = Plan()
+    half.frac_bits = half.frac_bits_w = half.frac_bits_d = -1
+    for k, v in dict(max_abs=0.80 + 0.007 * rank, max_abs_w=0.085, err_weight=6.3e6 + rank, err_weight2=1.6e8, scale=1.0e6,
+                     sum_bound=8.2e6, diag_bound=1.2e6, sum_rest=1.4e4, total_missing=25000000 + rank,
+                     max_missing=2700 + rank, n_snp=500000).items():
+        setattr(half, k, v)
+    half = D.reduce_plan(half, device=None)
+    from snprelate_b200._lib import plan_format
+    npass = plan_format(0, half, "auto", 10000)
+    fmt = (npass, half.digits, half.digits_w, half.frac_bits, half.frac_bits_w, half.rounding, half.n_snp, half.err_weight2)
     # three buffers of the three kinds the library exposes, as raw host pointers
     a = np.arange(6, dtype=np.int64) * (rank + 1) - 3
     b = (np.arange(4, dtype=np.uint32) + 4294967290 + rank).astype(np.uint32)   # wraps mod 2^32
@@ -55,7 +68,8 @@ def _worker(rank, world, port, q):
     D.allreduce_buffers([(d.ctypes.data, d.size, 0)], device=None, dst=1)
     if rank == 1:
         assert d.tolist() == (2 * np.arange(5) + 10).tolist()
-    q.put((rank, plan.max_abs, plan.sum_bound, plan.max_missing, plan.n_snp, plan.total_missing, plan.err_weight, plan.scale, a.tolist(), b.tolist(), c.tolist()))
+    q.put((rank, plan.max_abs, plan.sum_bound, plan.max_missing, plan.n_snp, plan.total_missing, plan.err_weight, plan.scale, a.tolist(), b.tolist(), c.tolist(),
+           plan.err_weight2, fmt))
     dist.destroy_process_group()
 
 
@@ -72,9 +86,11 @@ def test_plan_and_buffer_reduction_world2():
         assert p.exitcode == 0
     exp_a = ((np.arange(6) * 1 - 3) + (np.arange(6) * 2 - 3)).tolist()
     exp_b = ((np.arange(4, dtype=np.uint64) + 4294967290) + (np.arange(4, dtype=np.uint64) + 4294967291)) % (1 << 32)
-    for rank, mx, sb, mm, ns, tmiss, ew, sc, a, b, c in res:
+    assert res[0][-1] == res[1][-1]                       # one format on all ranks
+    assert res[0][-1][:3] == (7, 4, 3) and res[0][-1][5] == 1 and res[0][-1][6] == 1000000 and res[0][-1][7] == 3.2e8
+    for rank, mx, sb, mm, ns, tmiss, ew, sc, a, b, c, ew2, fmt in res:
         assert mx == 11.0 and sb == 300.0 and mm == 11 and ns == 3000
-        assert tmiss == 101 and ew == 14.0 and sc == 5.0
+        assert tmiss == 101 and ew == 14.0 and sc == 5.0 and ew2 == 81.0
         assert a == exp_a
         assert b == exp_b.astype(np.uint32).tolist()
         assert c == [1.5, 3.75]
